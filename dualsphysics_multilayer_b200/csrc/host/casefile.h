@@ -1,0 +1,42 @@
+// casefile.h -- Case.xml + Case.bi4 input (GenCase output format) and the synthetic case generator.
+// XML keys follow S/JSph.cpp:551-757 (LoadKernelSelection/LoadConfigCtes/LoadConfigParameters),
+// S/JCaseCtes.cpp:201-215, S/JCaseParts.cpp:484-508,60-64, S/JCaseEParms.cpp:286-375 and, for the
+// multiphase fork, M/JSph.cpp:608-628,3137-3214.
+#pragma once
+#include "../../../include/dsph_b200.h"
+#include <string>
+#include <vector>
+
+namespace dsph {
+
+struct MkBlock { int type; /*0 fixed,1 moving,2 floating,3 fluid*/ unsigned mktype, mk, begin, count; };
+
+struct DomainLimit { int mode=0; /*0 default,1 default+-value,2 default+-prc,3 fixed*/ double value=0; };
+
+struct CaseData {
+  dsph_config cfg;
+  std::string name;
+  std::vector<MkBlock> blocks;
+  unsigned mkboundfirst=11, mkfluidfirst=1;
+  DomainLimit posmin[3], posmax[3];        // <simulationdomain>
+  double caseposmin[3]={0,0,0}, caseposmax[3]={0,0,0};
+  std::vector<unsigned> idp;
+  std::vector<double> pos;                 // xyz packed
+  std::vector<float> velrhop;              // xyzw packed
+  unsigned np()const{ return (unsigned)idp.size(); }
+  unsigned npb()const{ return cfg.casenfixed+cfg.casenmoving; }
+};
+
+void ConfigDefaults(dsph_config &c);
+// MapRealPosMin/Max from CasePosMin/Max (JPartsLoad4::CalculeLimits + JSph::ResizeMapLimits)
+void ComputeMapRealPos(CaseData &cd);
+// particle code from id (JSph::LoadCodeParticles -> JSphMk::GetCodeById)
+void ComputeCodes(const CaseData &cd,unsigned np,const unsigned *idp,dsph_typecode *code);
+
+void SaveCase(const CaseData &cd,const std::string &dir,const std::string &casename);
+void LoadCase(CaseData &cd,const std::string &dir,const std::string &casename);
+
+// kind: "dambreak", "periodicbox", "nn2layer" (DB(N), PB(N), NN(N))
+void MakeCase(CaseData &cd,const std::string &kind,unsigned long long nptarget,unsigned seed);
+
+} // namespace dsph

@@ -1,0 +1,225 @@
+/* dsph_b200.h -- C ABI of the B200-native per-step particle hot path of DualSPHysics
+ * (cell-linked list -> Interaction_Forces -> ComputeStep).
+ *
+ * The reference (wjin33/DualSPHysics_MultiLayer) has no FFI: its GPU seam is the set of free host
+ * functions in the *_ker.h headers (namespaces cudiv::, cusph::, cusphs::, cushift::, cusphNN::) that
+ * JSphGpuSingle / JSphGpu / JCellDivGpuSingle call with raw device pointers.  This header is the
+ * drop-in replacement for that seam: plain C, opaque context, plain pointers and sizes, int status.
+ * Each entry point cites the reference interface it replaces
+ *   S/ = src/source/   M/ = src_mphase/DSPH_v5.0_NNewtonian/source/
+ * INTEGRATION.md shows the binding a maintainer adds to JSphGpuSingle.cpp.
+ *
+ * Conventions
+ *   - every function returns DSPH_OK (0) or a negative error; dsph_last_error() gives the text
+ *     (the reference polls cudaGetLastError() and throws JException, S/RunExceptionGpuDef.h:20-34).
+ *   - host arrays are caller-owned; device memory is owned by the context (the reference's
+ *     JArraysGpu pool + JCellDivGpu buffers, S/JArraysGpu.h:73-165, S/JCellDivGpu.cpp:110-161).
+ *   - particle order on the device is the cell-sorted order produced by dsph_celldiv_run().
+ *   - there is NO CPU fallback: every compute entry point fails with DSPH_ERR_NOGPU without a device.
+ */
+#ifndef DSPH_B200_H
+#define DSPH_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSPH_OK            0
+#define DSPH_ERR_ARG      (-1)
+#define DSPH_ERR_CUDA     (-2)
+#define DSPH_ERR_NOGPU    (-3)
+#define DSPH_ERR_STATE    (-4)
+#define DSPH_ERR_IO       (-5)
+#define DSPH_ERR_PHYSICS  (-6)   /* NaN dt, boundary particle out, too many particles out ... */
+
+/* ---- particle code (typecode, 16 bit) : S/DualSphDef.h:164-226 -------------------------------- */
+typedef uint16_t dsph_typecode;
+#define DSPH_CODE_MASKSPECIAL   0xe000u
+#define DSPH_CODE_NORMAL        0x0000u
+#define DSPH_CODE_PERIODIC      0x2000u
+#define DSPH_CODE_OUTIGNORE     0x4000u
+#define DSPH_CODE_OUTMOVE       0x6000u
+#define DSPH_CODE_OUTPOS        0x8000u
+#define DSPH_CODE_OUTRHOP       0xA000u
+#define DSPH_CODE_MASKTYPE      0x1800u
+#define DSPH_CODE_TYPE_FIXED    0x0000u
+#define DSPH_CODE_TYPE_MOVING   0x0800u
+#define DSPH_CODE_TYPE_FLOATING 0x1000u
+#define DSPH_CODE_TYPE_FLUID    0x1800u
+#define DSPH_CODE_MASKVALUE     0x07ffu
+
+/* ---- option enums (values of the reference's XML keys / enums) ------------------------------- */
+enum { DSPH_KERNEL_CUBIC=1, DSPH_KERNEL_WENDLAND=2 };                  /* TpKernel, key Kernel            */
+enum { DSPH_STEP_VERLET=1, DSPH_STEP_SYMPLECTIC=2 };                   /* TpStep, key StepAlgorithm       */
+enum { DSPH_VISCO_ARTIFICIAL=1, DSPH_VISCO_LAMINARSPS=2, DSPH_VISCO_CONSTEQ=3 }; /* TpVisco               */
+enum { DSPH_DDT_NONE=0, DSPH_DDT_DDT=1, DSPH_DDT_DDT2=2, DSPH_DDT_DDT2FULL=3 };   /* TpDensity, DensityDT */
+enum { DSPH_SHIFT_NONE=0, DSPH_SHIFT_NOBOUND=1, DSPH_SHIFT_NOFIXED=2, DSPH_SHIFT_FULL=3 }; /* TpShifting  */
+enum { DSPH_CELLMODE_FULL=1, DSPH_CELLMODE_HALF=2 };                   /* cells of 2h or h (ScellDiv 1|2) */
+enum { DSPH_VELGRAD_NONE=0, DSPH_VELGRAD_FDA=1, DSPH_VELGRAD_SPH=2 };  /* M/DualSphDef.h TpVelGrad        */
+enum { DSPH_INTERSTEP_VERLET=1, DSPH_INTERSTEP_SYMPREDICTOR=2, DSPH_INTERSTEP_SYMCORRECTOR=3 };
+
+#define DSPH_MAXPHASES 10   /* M/JSphGpu_NN_ker.cu:44-47: __constant__ arrays of 10 phases */
+
+/* One non-Newtonian phase (M/DualSphDef.h StPhaseCte + StPhaseArray; XML <special><nnphases>). */
+typedef struct dsph_phase {
+  uint32_t mkfluid;       /* mk of the phase = CODE_GetTypeValue(code) of its particles          */
+  float rho;              /* rest density                                                        */
+  float mass;             /* particle mass = rho*dp^3 (dp^2 in 2-D)                               */
+  float cs0;              /* speed of sound                                                      */
+  float cteb;             /* B = cs0^2*rho/gamma                                                  */
+  float gamma;            /* polytropic index                                                    */
+  float visco;            /* kinematic viscosity / consistency index                             */
+  float tau_yield;        /* yield stress                                                        */
+  float tau_max;          /* bi-viscosity cap (0: Papanastasiou regularisation)                  */
+  float bi_multi;         /* bi-viscosity multiplier                                              */
+  float m_nn;             /* Papanastasiou exponential growth m                                  */
+  float n_nn;             /* Herschel-Bulkley power index n                                      */
+  uint32_t phasetype;     /* 0 liquid, 1 gas ...                                                 */
+  uint32_t reserved;
+} dsph_phase;
+
+/* Everything the hot path needs from <execution><constants>/<parameters> and the case domain.
+ * Mirrors what JSph::LoadCaseConfig + ConfigConstants1/2 + LoadCaseParticles + ConfigCellDivision
+ * hand to the device side (StCteInteraction S/JSphGpu_ker.h:39-74, StCteSph S/DualSphDef.h:379-410).
+ * Derived constants (KernelSize, Eta2, Cs0, awen, bwen, DDTkh, DDTgz, Scell, MovLimit ...) are computed
+ * inside the library exactly as S/JSph.cpp:1392-1457,1772-1779 do. */
+typedef struct dsph_config {
+  /* formulation */
+  int32_t tkernel, tstep, tvisco, tdensity, shiftmode, cellmode, verletsteps, simulate2d;
+  int32_t perix, periy, periz;            /* periodic axes (JSph.cpp:716-730)                    */
+  int32_t dtallparticles, dtfixed_on, stable;
+  int32_t nn_on;                          /* 1: multiphase non-Newtonian formulation (src_mphase) */
+  int32_t nn_velgrad, nn_nphases, reserved_i;
+  /* constants (float where the reference stores float, JSph.cpp:567-586) */
+  float kernelh, cteb, gamma, rhopzero, massfluid, massbound;
+  float gravity[3];
+  float visco, viscoboundfactor, ddtvalue, shiftcoef, shifttfs;
+  float coefdtmin, rhopoutmin, rhopoutmax, nn_relaxationdt;
+  double dp, cflnumber, dtini, dtmin, dtfixed, simulate2dposy;
+  double timemax, timeout;
+  /* domain: MapRealPosMin/Max after ResizeMapLimits (JSph.cpp:2056-2066); periodic inc vectors */
+  double maprealposmin[3], maprealposmax[3];
+  double perixinc[3], periyinc[3], perizinc[3];
+  /* case counts (JSph.cpp:952-960): ids [0,casenfixed) fixed ... fluid last */
+  uint32_t casenp, casenfixed, casenmoving, casenfloat, casenfluid;
+  uint32_t partsoutmax_on; float partsoutmax;
+  dsph_phase phases[DSPH_MAXPHASES];
+} dsph_config;
+
+/* Result of one neighbour-list build (JCellDivGpuSingle::Divide + MakeDivDataGpu,
+ * S/JCellDivGpuSingle.cpp:152-235, S/JCellDivDataGpu.h:28-68). */
+typedef struct dsph_divinfo {
+  uint32_t np, npb, npbok;                 /* after removing excluded particles                  */
+  uint32_t npbper, npfper;                 /* periodic duplicates included in np                  */
+  uint32_t npbout, npfout, npbignore, npboutignore, npfoutignore;
+  uint32_t ncx, ncy, ncz, nct;             /* cells of the current cell domain                   */
+  uint32_t cellmin[3], cellmax[3];         /* CellDomainMin/Max                                   */
+  uint32_t domcells[3], domcellcode;       /* DomCells, DomCellCode (JSph.cpp:1794-1829)          */
+  uint32_t dividefull;                     /* 1 if every particle was re-sorted                   */
+  uint32_t nctt;                           /* length of the begin-cell table = 2*nct+6            */
+  double scell;                            /* cell size                                           */
+  double domposmin[3];
+} dsph_divinfo;
+
+/* Result of one force evaluation (ViscDtMax/AceMax/VelMax of S/JSphGpuSingle.cpp:435-486,
+ * S/JSphGpu.cpp:846-849; ViscEtaDtMax of M/JSphGpuSingle.cpp:497). */
+typedef struct dsph_forceres {
+  float viscdtmax;      /* max(dot(dr,dv)/(rr2+eta2))                                             */
+  float acemax;         /* sqrt(max |ace|^2) over normal fluid particles                          */
+  float velmax;         /* sqrt(max |vel|^2) over fluid particles                                 */
+  float viscetadtmax;   /* NN only                                                                */
+  double dt1, dt2, dt3, dt;  /* DtVariable(), S/JSphGpu.cpp:984-1009                              */
+} dsph_forceres;
+
+/* Timers of the last step, milliseconds of device time (names of S/JDsTimersGpu.h:64-88). */
+typedef struct dsph_timers {
+  double nl_limits, nl_presort, nl_radixsort, nl_cellbegin, nl_sortdata, nl_outcheck;
+  double cf_preforces, cf_forces, su_computestep, su_periodic, su_shifting, total;
+  uint64_t kernel_launches;
+} dsph_timers;
+
+typedef struct dsph_ctx dsph_ctx;
+
+/* ---- library --------------------------------------------------------------------------------- */
+const char* dsph_version(void);
+const char* dsph_last_error(void);
+int dsph_device_count(void);
+
+/* ---- context : replaces JSphGpuSingle ctor / SelecDevice / Alloc*Memory
+ *      (S/JSphGpu.cpp:622-630, S/JSphGpu.cpp:246-349) ---------------------------------------- */
+int dsph_ctx_create(dsph_ctx **out,int device,const dsph_config *cfg,uint32_t np_capacity);
+int dsph_ctx_destroy(dsph_ctx *ctx);
+/* replaces cusph::CteInteractionUp (S/JSphGpu_ker.h:191) + cusphNN::CteInteractionUp_NN; may be called
+ * again when a constant changes (DDT ramp, S/JSphGpuSingle.cpp:520-539). */
+int dsph_constants_upload(dsph_ctx *ctx,const dsph_config *cfg);
+
+/* ---- particle state : replaces JSphGpu::ParticlesDataUp / ParticlesDataDown
+ *      (S/JSphGpu.cpp:563-616) and LoadCodeParticles/LoadDcellParticles (S/JSph.cpp:1257,1690) --- */
+int dsph_particles_upload(dsph_ctx *ctx,uint32_t np,uint32_t npb,const uint32_t *idp,
+                          const dsph_typecode *code /*may be NULL: derived from idp*/,
+                          const double *pos_xyz,const float *velrhop_xyzw);
+/* optional restart of a mid-state: Verlet VelrhopM1 (NULL -> copy of velrhop, S/JSphGpu.cpp:800) */
+int dsph_particles_set_velrhopm1(dsph_ctx *ctx,const float *velrhopm1_xyzw);
+/* downloads in the current (cell-sorted) order; any pointer may be NULL */
+int dsph_particles_download(dsph_ctx *ctx,uint32_t first,uint32_t count,uint32_t *idp,dsph_typecode *code,
+                            uint32_t *dcell,double *pos_xyz,float *velrhop_xyzw);
+uint32_t dsph_np(const dsph_ctx *ctx);
+uint32_t dsph_npb(const dsph_ctx *ctx);
+
+/* ---- neighbour list : replaces JSphGpuSingle::RunCellDivide = RunPeriodic + JCellDivGpuSingle::Divide
+ *      + cudiv::PreSortFull/PreSortFluid/Sort/CalcBeginEndCell/SortDataParticles + cusphs::UpdatePosCell
+ *      (S/JSphGpuSingle.cpp:249-417, S/JCellDivGpu_ker.h:40-59, S/JCellDivGpuSingle_ker.h) ---------- */
+int dsph_celldiv_run(dsph_ctx *ctx,int updateperiodic,dsph_divinfo *info);
+/* begin-cell table in the CPU form unsigned[2*nct+6] (S/JCellDivCpu.h:80,141,153); test/inspection */
+int dsph_celldiv_get_begincell(dsph_ctx *ctx,uint32_t *begincell,uint32_t capacity);
+
+/* ---- forces : replaces JSphGpu::PreInteraction_Forces + cusph::Interaction_Forces
+ *      (+cusphNN::Interaction_ForcesNN) + ReduMaxFloat/ComputeAceMax + JSphGpu::DtVariable
+ *      (S/JSphGpu.cpp:811-854, S/JSphGpu_ker.h:200, S/JSphGpuSingle.cpp:435-514, S/JSphGpu.cpp:984) -- */
+int dsph_forces_run(dsph_ctx *ctx,int interstep,dsph_forceres *res);
+/* ace (xyz) and ar of the last evaluation, sorted order; test/inspection */
+int dsph_forces_download(dsph_ctx *ctx,uint32_t first,uint32_t count,float *ace_xyz,float *ar);
+
+/* ---- step update : replaces JSphGpu::ComputeVerlet / ComputeSymplecticPre / ComputeSymplecticCorr
+ *      = cusphs::ComputeStepVerlet|SymplecticPre|SymplecticCor + cusph::ComputeStepPos|Pos2
+ *      + JSphShifting::RunGpu (S/JSphGpu.cpp:874-978, S/JSphGpuSimple_ker.cu:129-445,
+ *      S/JSphGpu_ker.cu:1598-1690) ------------------------------------------------------------- */
+int dsph_step_verlet(dsph_ctx *ctx,double dt);
+int dsph_step_sympre(dsph_ctx *ctx,double dt);
+int dsph_step_symcor(dsph_ctx *ctx,double dt);
+
+/* ---- whole time step : replaces JSphGpuSingle::ComputeStep_Sym / ComputeStep_Ver + the
+ *      RunCellDivide(true) that closes the step (S/JSphGpuSingle.cpp:548-596,853-861).
+ *      Returns the dt used; *res (optional) holds the maxima of the last force evaluation. ------- */
+int dsph_step(dsph_ctx *ctx,double *stepdt,dsph_forceres *res);
+double dsph_symplectic_dtpre(const dsph_ctx *ctx);
+int dsph_set_symplectic_dtpre(dsph_ctx *ctx,double dt);
+int dsph_get_timers(dsph_ctx *ctx,dsph_timers *t,int reset);
+/* pair counters of the last force evaluation (JDsPips, S/JDsPips_ker.cu:66): real & checked pairs
+ * for fluid and boundary particles; used by the roofline byte model. */
+int dsph_pips(dsph_ctx *ctx,uint64_t *fluid_real,uint64_t *fluid_checked,uint64_t *bound_real,uint64_t *bound_checked);
+
+/* ---- case tooling (host only, no GPU): GenCase is a missing blob in the reference, these build the
+ *      synthetic benchmark cases of SURVEY.md 8(d) and read/write Case.xml + Case.bi4 ------------- */
+typedef struct dsph_case {
+  dsph_config cfg;
+  uint32_t np, npb;
+  uint32_t *idp; double *pos_xyz; float *velrhop_xyzw;   /* owned by the library: dsph_case_free */
+  double caseposmin[3], caseposmax[3];
+  char name[64];
+} dsph_case;
+/* kind: "dambreak" (DB(N)), "periodicbox" (PB(N)), "nn2layer" (NN(N)); np_target approximate */
+int dsph_case_make(dsph_case *out,const char *kind,uint64_t np_target,uint32_t seed);
+int dsph_case_free(dsph_case *c);
+int dsph_case_save(const dsph_case *c,const char *dir,const char *casename); /* Case.xml + Case.bi4 */
+int dsph_case_load(dsph_case *out,const char *dir,const char *casename);
+
+/* ---- driver: the JSph/JSphGpuSingle::Run work-alike (S/JSphGpuSingle.cpp:808-883): loads
+ *      <dir>/<casename>.xml+.bi4, runs to TimeMax (or nsteps>0), writes Part_NNNN.bi4, Run.out, Run.csv
+ *      into dirout. ---------------------------------------------------------------------------- */
+int dsph_run_case(const char *dir,const char *casename,const char *dirout,int device,int nsteps,int savepart);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSPH_B200_H */

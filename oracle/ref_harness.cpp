@@ -1,0 +1,214 @@
+// ref_harness.cpp -- TEST INFRASTRUCTURE (never part of the product).
+//
+// Compiled by oracle/Makefile AGAINST THE REFERENCE SOURCES (with -I<reference source dir>) and linked
+// with the reference's own objects.  It subclasses the reference CPU solver JSphCpuSingle (all members
+// used are `protected`, so no reference file is modified or copied) and replays
+// JSphCpuSingle::Run (S/JSphCpuSingle.cpp:1049-1122) while dumping, in binary, the intermediate
+// quantities the parity tests need: cell assignment + sorted order + begin-cell table after
+// RunCellDivide, Ace/Ar/ViscDtMax/AceMax/VelMax/dt after Interaction_Forces, and the state after
+// ComputeSymplecticPre/Corr or ComputeVerlet.  The step sequence below follows
+// JSphCpuSingle::ComputeStep_Sym/_Ver (S/JSphCpuSingle.cpp:674-721) call by call.
+//
+//   ref_harness52 <case> <dirout> -cpu [reference options...] -hdir:<dumpdir> -hsteps:0,1,50 -hnsteps:51
+//
+#include "JSphCpuSingle.h"
+#include "JSphCfgRun.h"
+#include "JCellDivCpuSingle.h"
+#include "JAppInfo.h"
+#include "JLog2.h"
+#include "JException.h"
+#include "JDsTimersCpu.h"
+#include "JArraysCpu.h"
+#include "JSphShifting.h"
+#include "JDsOutputTime.h"
+#include "Functions.h"
+#include "ref_dump.h"
+#include <set>
+#include <string>
+#include <vector>
+#include <cstdlib>
+
+JAppInfo AppInfo("DualSPHysics-refharness","v0","","","");
+
+class RefHarness : public JSphCpuSingle {
+ public:
+  std::string DumpDir;
+  std::set<unsigned> DumpSteps;
+  unsigned NstepsRun=0;
+
+  std::string DumpName(unsigned step,const char *stage)const{
+    return DumpDir+"/"+fun::PrintStr("s%04u_%s.dmp",step,stage);
+  }
+  //-State of particles in current order (after a divide: cell-sorted).
+  void DumpState(unsigned step,const char *stage,bool withcells){
+    RefDumpWriter w(DumpName(step,stage));
+    w.U32("np",Np); w.U32("npb",Npb); w.U32("npbok",NpbOk); w.U32("npbper",NpbPer); w.U32("npfper",NpfPer);
+    w.U32("nstep",Nstep); w.F64("timestep",TimeStep); w.F64("symplecticdtpre",SymplecticDtPre);
+    w.U32("verletstep",VerletStep);
+    w.Add("idp",2,1,Np,Idpc); w.Add("code",1,1,Np,Codec); w.Add("dcell",2,1,Np,Dcellc);
+    w.Add("pos",4,3,Np,Posc); w.Add("velrhop",3,4,Np,Velrhopc);
+    if(TStep==STEP_Verlet && VelrhopM1c)w.Add("velrhopm1",3,4,Np,VelrhopM1c);
+    if(PosPrec)w.Add("pospre",4,3,Np,PosPrec);
+    if(VelrhopPrec)w.Add("velrhoppre",3,4,Np,VelrhopPrec);
+    if(SpsTauc)w.Add("spstau",3,6,Np,SpsTauc);
+    if(withcells){
+      const tuint3 cmin=CellDivSingle->GetCellDomainMin(), cmax=CellDivSingle->GetCellDomainMax();
+      const unsigned cm[6]={cmin.x,cmin.y,cmin.z,cmax.x,cmax.y,cmax.z};
+      w.Add("celldomain",2,6,1,cm);
+      const unsigned nct=CellDivSingle->GetNct();
+      const unsigned nc[4]={CellDivSingle->GetNcx(),CellDivSingle->GetNcy(),CellDivSingle->GetNcz(),nct};
+      w.Add("ncells",2,4,1,nc);
+      w.Add("begincell",2,1,size_t(nct)*2+6,CellDivSingle->GetBeginCell());
+      const unsigned outs[6]={CellDivSingle->GetNpbOut(),CellDivSingle->GetNpfOut(),CellDivSingle->GetNpbIgnore(),
+                              CellDivSingle->GetNpbOutIgnore(),CellDivSingle->GetNpfOutIgnore(),0};
+      w.Add("outcounts",2,6,1,outs);
+      w.U32("domcellcode",DomCellCode);
+      const unsigned dc[3]={DomCells.x,DomCells.y,DomCells.z}; w.Add("domcells",2,3,1,dc);
+      const double dpm[3]={DomPosMin.x,DomPosMin.y,DomPosMin.z}; w.Add("domposmin",4,3,1,dpm);
+      w.F32("scell",Scell);
+    }
+  }
+  void DumpForces(unsigned step,const char *stage,double dt){
+    RefDumpWriter w(DumpName(step,stage));
+    w.U32("np",Np); w.U32("npb",Npb); w.U32("npbok",NpbOk);
+    w.Add("ace",3,3,Np,Acec); w.Add("ar",3,1,Np,Arc);
+    if(ShiftPosfsc)w.Add("shiftposfs",3,4,Np,ShiftPosfsc);
+    if(SpsTauc)w.Add("spstau",3,6,Np,SpsTauc);
+    w.F32("viscdtmax",ViscDtMax); w.F64("acemax",AceMax); w.F64("velmax",VelMax); w.F64("dt",dt);
+  }
+  void DumpConstants(){
+    RefDumpWriter w(DumpDir+"/constants.dmp");
+    w.F32("kernelh",KernelH); w.F32("kernelsize",KernelSize); w.F32("kernelsize2",KernelSize2);
+    w.F32("awen",KWend.awen); w.F32("bwen",KWend.bwen); w.F32("eta2",Eta2); w.F64("cs0",Cs0);
+    w.F32("cteb",CteB); w.F32("gamma",Gamma); w.F32("rhopzero",RhopZero); w.F32("massfluid",MassFluid); w.F32("massbound",MassBound);
+    w.F32("ddtkh",DDTkh); w.F32("ddtgz",DDTgz); w.F32("visco",Visco); w.F32("viscoboundfactor",ViscoBoundFactor);
+    w.F64("dp",Dp); w.F64("cflnumber",CFLnumber); w.F64("dtini",DtIni); w.F64("dtmin",DtMin);
+    w.F32("scell",Scell); w.F32("movlimit",MovLimit); w.U32("scelldiv",unsigned(ScellDiv));
+    const double m[18]={Map_PosMin.x,Map_PosMin.y,Map_PosMin.z,Map_PosMax.x,Map_PosMax.y,Map_PosMax.z,
+      MapRealPosMin.x,MapRealPosMin.y,MapRealPosMin.z,MapRealPosMax.x,MapRealPosMax.y,MapRealPosMax.z,
+      DomPosMin.x,DomPosMin.y,DomPosMin.z,DomPosMax.x,DomPosMax.y,DomPosMax.z};
+    w.Add("maplimits",4,18,1,m);
+    const unsigned mc[3]={Map_Cells.x,Map_Cells.y,Map_Cells.z}; w.Add("mapcells",2,3,1,mc);
+    w.U32("domcellcode",DomCellCode);
+    w.U32("tstep",unsigned(TStep)); w.U32("tkernel",unsigned(TKernel)); w.U32("tvisco",unsigned(TVisco));
+    w.U32("tdensity",unsigned(TDensity)); w.U32("shiftmode",unsigned(ShiftingMode)); w.U32("periactive",unsigned(PeriActive));
+    w.U32("casenp",CaseNp); w.U32("casenfixed",CaseNfixed); w.U32("casenfluid",CaseNfluid);
+    const double pi[9]={PeriXinc.x,PeriXinc.y,PeriXinc.z,PeriYinc.x,PeriYinc.y,PeriYinc.z,PeriZinc.x,PeriZinc.y,PeriZinc.z};
+    w.Add("periinc",4,9,1,pi);
+  }
+
+  //-Same call sequence as JSphCpuSingle::ComputeStep_Sym, with dumps in between.
+  double StepSymDump(unsigned step){
+    const double dt=SymplecticDtPre;
+    Interaction_Forces(INTERSTEP_SymPredictor);
+    const double ddt_p=DtVariable(false);
+    DumpForces(step,"fpre",ddt_p);
+    if(Shifting)RunShifting(dt*.5);
+    ComputeSymplecticPre(dt);
+    PosInteraction_Forces();
+    DumpState(step,"upre",false);
+    RunCellDivide(true);
+    DumpState(step,"div1",true);
+    Interaction_Forces(INTERSTEP_SymCorrector);
+    const double ddt_c=DtVariable(true);
+    DumpForces(step,"fcor",ddt_c);
+    if(Shifting)RunShifting(dt);
+    ComputeSymplecticCorr(dt);
+    PosInteraction_Forces();
+    SymplecticDtPre=std::min(ddt_p,ddt_c);
+    DumpState(step,"ucor",false);
+    return(dt);
+  }
+  //-Same call sequence as JSphCpuSingle::ComputeStep_Ver, with dumps in between.
+  double StepVerDump(unsigned step){
+    Interaction_Forces(INTERSTEP_Verlet);
+    const double dt=DtVariable(true);
+    DumpForces(step,"fver",dt);
+    if(Shifting)RunShifting(dt);
+    ComputeVerlet(dt);
+    PosInteraction_Forces();
+    DumpState(step,"uver",false);
+    return(dt);
+  }
+
+  //-Replays JSphCpuSingle::Run (initialisation and main loop) without PART output bookkeeping.
+  void RunDump(std::string appname,const JSphCfgRun *cfg,JLog2 *log){
+    AppName=appname; Log=log; CfgRun=cfg;
+    Timersc->Config(cfg->SvTimers);
+    Timersc->TmStart(TMC_Init);
+    LoadConfig(cfg);
+    LoadCaseParticles();
+    VisuConfig();
+    ConfigDomain();
+    ConfigRunMode();
+    VisuParticleSummary();
+    InitRunCpu();
+    FreePartsInit();
+    UpdateMaxValues();
+    SaveData();
+    Timersc->ResetTimes();
+    Timersc->TmStop(TMC_Init);
+    PartNstep=-1; Part++;
+    DumpConstants();
+    TimerSim.Start(); TimerPart.Start();
+    while(TimeStep<TimeMax && Nstep<int(NstepsRun)){
+      const unsigned step=unsigned(Nstep);
+      const bool dump=(DumpSteps.count(step)!=0);
+      InterStep=(TStep==STEP_Symplectic? INTERSTEP_SymPredictor: INTERSTEP_Verlet);
+      double stepdt;
+      if(dump){
+        DumpState(step,"div0",true);
+        stepdt=(TStep==STEP_Symplectic? StepSymDump(step): StepVerDump(step));
+      }
+      else stepdt=ComputeStep();
+      RunCellDivide(true);
+      TimeStep+=stepdt;
+      LastDt=stepdt;
+      if(dump){
+        RefDumpWriter w(DumpName(step,"end"));
+        w.F64("stepdt",stepdt); w.F64("timestep",TimeStep); w.F64("symplecticdtpre",SymplecticDtPre);
+        w.U32("np",Np); w.U32("npb",Npb); w.U32("npbok",NpbOk);
+      }
+      Nstep++;
+    }
+    DumpState(unsigned(Nstep),"final",true);
+    TimerSim.Stop(); TimerTot.Stop();
+    log->Printf("refharness: finished %d steps, TimeStep=%.9g",Nstep,TimeStep);
+  }
+};
+
+int main(int argc,char **argv){
+  std::vector<char*> args; RefHarness *sph=new RefHarness();
+  std::string dumpdir="dump";
+  for(int i=0;i<argc;i++){
+    std::string a=argv[i];
+    if(a.compare(0,6,"-hdir:")==0)dumpdir=a.substr(6);
+    else if(a.compare(0,8,"-hsteps:")==0){
+      std::string s=a.substr(8); size_t p=0;
+      while(p<s.size()){ size_t q=s.find(',',p); if(q==std::string::npos)q=s.size(); sph->DumpSteps.insert(unsigned(atoi(s.substr(p,q-p).c_str()))); p=q+1; }
+    }
+    else if(a.compare(0,9,"-hnsteps:")==0)sph->NstepsRun=unsigned(atoi(a.substr(9).c_str()));
+    else args.push_back(argv[i]);
+  }
+  sph->DumpDir=dumpdir;
+  fun::MkdirPath(dumpdir);
+  int errcode=1;
+  AppInfo.ConfigRunPaths(argv[0]);
+  JLog2 *log=NULL;
+  JSphCfgRun cfg;
+  try{
+    cfg.LoadArgv(int(args.size()),args.data());
+    AppInfo.ConfigOutput(cfg.CreateDirs,cfg.CsvSepComa,cfg.DirOut,cfg.DirDataOut);
+    AppInfo.LogInit(AppInfo.GetDirOut()+"/Run.out");
+    log=AppInfo.LogPtr();
+    cfg.Cpu=true;
+    sph->RunDump(AppInfo.GetFullName(),&cfg,log);
+    errcode=0;
+  }
+  catch(const char *cad){ printf("\n*** Exception(chr): %s\n",cad); }
+  catch(const std::string &e){ printf("\n*** Exception(str): %s\n",e.c_str()); }
+  catch(const JException &e){ printf("\n*** JException: %s\n",e.what()); }
+  catch(const std::exception &e){ printf("\n*** Exception(exc): %s\n",e.what()); }
+  printf("refharness finished (code=%d)\n",errcode);
+  return(errcode);
+}
