@@ -1,0 +1,141 @@
+"""dualsphysics_multilayer_b200 -- B200-native per-step particle hot path of DualSPHysics (cell-linked list ->
+Interaction_Forces -> ComputeStep) behind the C ABI of ``include/dsph_b200.h``.
+
+The compute path is hand-written CUDA for sm_100a inside ``libdsph_b200.so`` (built in-tree by
+``__graft_entry__.build()``).  This Python layer is only the test/bench harness view of that C ABI (ctypes); the
+reference is compiled C++, so the host driver that mirrors JSph/JSphGpuSingle lives in ``csrc/host`` (C++).
+There is no CPU fallback: if the library is missing or no CUDA device exists, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .capi import (Case, Config, DivInfo, ForceRes, SphContext, SphError, SphLib, Timers)  # noqa: F401
+from . import capi  # noqa: F401
+
+_PKGDIR = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(_PKGDIR, "libdsph_b200.so")
+_lib = None
+
+
+def lib() -> SphLib:
+    """The product shared library (loaded once).  Raises SphError when it has not been built."""
+    global _lib
+    if _lib is None:
+        L = SphLib(LIBPATH, "dsph_")
+        l = L.lib
+        l.dsph_version.restype = C.c_char_p
+        l.dsph_device_count.restype = C.c_int
+        l.dsph_case_make.restype = C.c_int
+        l.dsph_case_make.argtypes = [C.POINTER(Case), C.c_char_p, C.c_uint64, C.c_uint32]
+        l.dsph_case_free.argtypes = [C.POINTER(Case)]
+        l.dsph_case_load.restype = C.c_int
+        l.dsph_case_load.argtypes = [C.POINTER(Case), C.c_char_p, C.c_char_p]
+        l.dsph_case_save.restype = C.c_int
+        l.dsph_case_save.argtypes = [C.POINTER(Case), C.c_char_p, C.c_char_p]
+        l.dsph_run_case.restype = C.c_int
+        l.dsph_run_case.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
+        l.dsph_get_timers.restype = C.c_int
+        l.dsph_get_timers.argtypes = [C.c_void_p, C.POINTER(Timers), C.c_int]
+        l.dsph_set_force_variant.argtypes = [C.c_void_p, C.c_int]
+        l.dsph_set_verletstep.argtypes = [C.c_void_p, C.c_int]
+        l.dsph_last_force_ms.restype = C.c_double
+        l.dsph_last_force_ms.argtypes = [C.c_void_p]
+        l.dsph_cuda_stream.restype = C.c_void_p
+        l.dsph_cuda_stream.argtypes = [C.c_void_p]
+        l.dsph_constants_upload.restype = C.c_int
+        l.dsph_constants_upload.argtypes = [C.c_void_p, C.POINTER(Config)]
+        _lib = L
+    return _lib
+
+
+def device_count() -> int:
+    return int(lib().lib.dsph_device_count())
+
+
+class CaseData:
+    """Host copy of a case: config + particle arrays (numpy)."""
+
+    def __init__(self, cfg: Config, idp, pos, velrhop, npb, name="Case", caseposmin=None, caseposmax=None,
+                 fluidblocks=None):
+        self.cfg, self.idp, self.pos, self.velrhop, self.npb, self.name = cfg, idp, pos, velrhop, int(npb), name
+        self.caseposmin, self.caseposmax = caseposmin, caseposmax
+        self.fluidblocks = fluidblocks or [int(cfg.casenfluid)]
+
+    @property
+    def np_(self):
+        return int(self.idp.shape[0])
+
+    def codes(self):
+        """typecode per particle: fixed block 0, fluid blocks by rank (JSphMk::GetCodeById)."""
+        code = np.full(self.np_, capi.CODE_TYPE_FIXED, np.uint16)
+        nb = int(self.cfg.casenfixed)
+        start = nb
+        for rank, cnt in enumerate(self.fluidblocks):
+            sel = (self.idp >= start) & (self.idp < start + cnt)
+            code[sel] = capi.CODE_TYPE_FLUID | rank
+            start += cnt
+        return code
+
+
+def _case_from_c(c: Case) -> CaseData:
+    n = int(c.np)
+    idp = np.ctypeslib.as_array(c.idp, shape=(n,)).copy()
+    pos = np.ctypeslib.as_array(c.pos_xyz, shape=(n, 3)).copy()
+    vr = np.ctypeslib.as_array(c.velrhop_xyzw, shape=(n, 4)).copy()
+    nfb = int(c.nfluidblocks)
+    blocks = [int(c.fluidblock_count[i]) for i in range(nfb)] if nfb else None
+    cd = CaseData(c.cfg.copy(), idp, pos, vr, int(c.npb), c.name.decode(), list(c.caseposmin), list(c.caseposmax), blocks)
+    lib().lib.dsph_case_free(C.byref(c))
+    return cd
+
+
+def make_case(kind: str, np_target: int, seed: int = 12345) -> CaseData:
+    """Synthetic benchmark cases of SURVEY.md 8(d): 'dambreak', 'periodicbox', 'nn2layer'."""
+    c = Case()
+    L = lib()
+    L.check(L.lib.dsph_case_make(C.byref(c), kind.encode(), int(np_target), int(seed)))
+    return _case_from_c(c)
+
+
+def load_case(dirname: str, casename: str) -> CaseData:
+    """Reads <dirname>/<casename>.xml + .bi4 (GenCase output format)."""
+    c = Case()
+    L = lib()
+    L.check(L.lib.dsph_case_load(C.byref(c), dirname.encode(), casename.encode()))
+    return _case_from_c(c)
+
+
+def save_case(cd: CaseData, dirname: str, casename: str) -> None:
+    c = Case()
+    c.cfg = cd.cfg
+    c.np, c.npb = cd.np_, cd.npb
+    idp = np.ascontiguousarray(cd.idp, np.uint32)
+    pos = np.ascontiguousarray(cd.pos, np.float64)
+    vr = np.ascontiguousarray(cd.velrhop, np.float32)
+    c.idp = idp.ctypes.data_as(C.POINTER(C.c_uint32))
+    c.pos_xyz = pos.ctypes.data_as(C.POINTER(C.c_double))
+    c.velrhop_xyzw = vr.ctypes.data_as(C.POINTER(C.c_float))
+    for i in range(3):
+        c.caseposmin[i] = cd.caseposmin[i]
+        c.caseposmax[i] = cd.caseposmax[i]
+    c.nfluidblocks = len(cd.fluidblocks)
+    for i, n in enumerate(cd.fluidblocks):
+        c.fluidblock_count[i] = n
+    os.makedirs(dirname, exist_ok=True)
+    L = lib()
+    L.check(L.lib.dsph_case_save(C.byref(c), dirname.encode(), casename.encode()))
+
+
+def create_context(cd_or_cfg, np_capacity: int = 0, device: int = 0) -> SphContext:
+    """GPU context (JSphGpuSingle work-alike).  Raises SphError without a CUDA device."""
+    cfg = cd_or_cfg.cfg if isinstance(cd_or_cfg, CaseData) else cd_or_cfg
+    return SphContext(lib(), cfg, np_capacity, device)
+
+
+def run_case(dirname: str, casename: str, dirout: str, device: int = 0, nsteps: int = 0, savepart: bool = True) -> None:
+    L = lib()
+    L.check(L.lib.dsph_run_case(dirname.encode(), casename.encode(), dirout.encode(), device, nsteps, 1 if savepart else 0))

@@ -1,0 +1,148 @@
+// capi.cu -- extern "C" surface of include/dsph_b200.h (thin: argument checks + exception -> status code).
+#include "../../include/dsph_b200.h"
+#include "engine.h"
+#include "host/casefile.h"
+#include "host/driver.h"
+#include <cstring>
+#include <string>
+#include <new>
+
+using namespace dsph;
+
+struct dsph_ctx { Engine *eng; };
+
+static thread_local std::string g_lasterror;
+
+template<class F> static int Guard(F f){
+  try{ f(); return DSPH_OK; }
+  catch(const EngineError &e){ g_lasterror=e.what(); return e.code; }
+  catch(const std::bad_alloc &){ g_lasterror="Out of host memory."; return DSPH_ERR_STATE; }
+  catch(const std::exception &e){ g_lasterror=e.what(); return DSPH_ERR_STATE; }
+  catch(...){ g_lasterror="Unknown exception."; return DSPH_ERR_STATE; }
+}
+#define NEEDCTX(c) if(!(c)||!(c)->eng){ g_lasterror="Invalid context."; return DSPH_ERR_ARG; }
+
+extern "C" {
+
+const char* dsph_version(void){ return "dsph_b200 0.1 (sm_100a)"; }
+const char* dsph_last_error(void){ return g_lasterror.c_str(); }
+int dsph_device_count(void){ int n=0; if(cudaGetDeviceCount(&n)!=cudaSuccess){ cudaGetLastError(); return 0; } return n; }
+
+int dsph_ctx_create(dsph_ctx **out,int device,const dsph_config *cfg,uint32_t np_capacity){
+  if(!out||!cfg){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  *out=nullptr;
+  return Guard([&]{
+    unsigned capacity=np_capacity;
+    if(!capacity){
+      capacity=cfg->casenp+cfg->casenp/20+1024;                    // reference: Np*(1+over)+128 (S/JSphGpu.cpp:359-429)
+      if(cfg->perix||cfg->periy||cfg->periz)capacity=unsigned(cfg->casenp*1.7)+65536;
+    }
+    Engine *e=new Engine(device,*cfg,capacity);
+    dsph_ctx *c=new dsph_ctx; c->eng=e; *out=c;
+  });
+}
+int dsph_ctx_destroy(dsph_ctx *ctx){
+  if(!ctx)return DSPH_OK;
+  return Guard([&]{ delete ctx->eng; ctx->eng=nullptr; delete ctx; });
+}
+int dsph_constants_upload(dsph_ctx *ctx,const dsph_config *cfg){
+  NEEDCTX(ctx); if(!cfg){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  return Guard([&]{ const double dtpre=ctx->eng->symplecticdtpre; const int vs=ctx->eng->verletstep; ctx->eng->Configure(*cfg); ctx->eng->symplecticdtpre=dtpre; ctx->eng->verletstep=vs; });
+}
+int dsph_particles_upload(dsph_ctx *ctx,uint32_t np,uint32_t npb,const uint32_t *idp,const dsph_typecode *code,const double *pos,const float *velrhop){
+  NEEDCTX(ctx); if(!idp||!pos||!velrhop){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  return Guard([&]{ ctx->eng->Upload(np,npb,idp,code,pos,velrhop); });
+}
+int dsph_particles_set_velrhopm1(dsph_ctx *ctx,const float *v){
+  NEEDCTX(ctx); if(!v){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  return Guard([&]{ ctx->eng->SetVelrhopM1(v); });
+}
+int dsph_particles_set_spstau(dsph_ctx *ctx,const float *t){
+  NEEDCTX(ctx); if(!t){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  return Guard([&]{ ctx->eng->SetSpsTau(t); });
+}
+int dsph_particles_download(dsph_ctx *ctx,uint32_t first,uint32_t count,uint32_t *idp,dsph_typecode *code,uint32_t *dcell,double *pos,float *velrhop){
+  NEEDCTX(ctx);
+  return Guard([&]{ ctx->eng->Download(first,count,idp,code,dcell,pos,velrhop); });
+}
+uint32_t dsph_np(const dsph_ctx *ctx){ return (ctx&&ctx->eng)? ctx->eng->np: 0; }
+uint32_t dsph_npb(const dsph_ctx *ctx){ return (ctx&&ctx->eng)? ctx->eng->npb: 0; }
+
+int dsph_celldiv_run(dsph_ctx *ctx,int updateperiodic,dsph_divinfo *info){
+  NEEDCTX(ctx);
+  return Guard([&]{ ctx->eng->CellDivide(updateperiodic!=0,info); ctx->eng->FlushStepTimer(); });
+}
+int dsph_celldiv_get_begincell(dsph_ctx *ctx,uint32_t *begincell,uint32_t capacity){
+  NEEDCTX(ctx); if(!begincell){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  return Guard([&]{ ctx->eng->GetBeginCell(begincell,capacity); });
+}
+int dsph_forces_run(dsph_ctx *ctx,int interstep,dsph_forceres *res){
+  NEEDCTX(ctx);
+  return Guard([&]{ ctx->eng->Forces(interstep,res); });
+}
+int dsph_forces_download(dsph_ctx *ctx,uint32_t first,uint32_t count,float *ace,float *ar){
+  NEEDCTX(ctx);
+  return Guard([&]{ ctx->eng->ForcesDownload(first,count,ace,ar); });
+}
+int dsph_step_verlet(dsph_ctx *ctx,double dt){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->StepVerlet(dt); }); }
+int dsph_step_sympre(dsph_ctx *ctx,double dt){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->StepSymPre(dt); }); }
+int dsph_step_symcor(dsph_ctx *ctx,double dt){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->StepSymCor(dt); }); }
+int dsph_step(dsph_ctx *ctx,double *stepdt,dsph_forceres *res){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->Step(stepdt,res); }); }
+double dsph_symplectic_dtpre(const dsph_ctx *ctx){ return (ctx&&ctx->eng)? ctx->eng->symplecticdtpre: 0; }
+int dsph_set_symplectic_dtpre(dsph_ctx *ctx,double dt){ NEEDCTX(ctx); ctx->eng->symplecticdtpre=dt; return DSPH_OK; }
+int dsph_set_verletstep(dsph_ctx *ctx,int v){ NEEDCTX(ctx); ctx->eng->verletstep=v; return DSPH_OK; }
+int dsph_set_force_variant(dsph_ctx *ctx,int v){ NEEDCTX(ctx); ctx->eng->forcevariant=v; return DSPH_OK; }
+int dsph_get_timers(dsph_ctx *ctx,dsph_timers *t,int reset){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->GetTimers(t,reset!=0); }); }
+double dsph_last_force_ms(const dsph_ctx *ctx){ return (ctx&&ctx->eng)? ctx->eng->lastforcems: 0; }
+int dsph_pips(dsph_ctx *ctx,uint64_t *fr,uint64_t *fc,uint64_t *br,uint64_t *bc){
+  NEEDCTX(ctx);
+  return Guard([&]{ unsigned long long a,b,c,d; ctx->eng->Pips(&a,&b,&c,&d); if(fr)*fr=a; if(fc)*fc=b; if(br)*br=c; if(bc)*bc=d; });
+}
+void* dsph_cuda_stream(dsph_ctx *ctx){ return (ctx&&ctx->eng)? (void*)ctx->eng->stm: nullptr; }
+
+// ---- case tooling (host only) ----
+static void CaseToC(const CaseData &cd,dsph_case *out){
+  memset(out,0,sizeof(*out));
+  out->cfg=cd.cfg; out->np=cd.np(); out->npb=cd.npb();
+  out->idp=new uint32_t[cd.idp.size()]; out->pos_xyz=new double[cd.pos.size()]; out->velrhop_xyzw=new float[cd.velrhop.size()];
+  memcpy(out->idp,cd.idp.data(),cd.idp.size()*4); memcpy(out->pos_xyz,cd.pos.data(),cd.pos.size()*8); memcpy(out->velrhop_xyzw,cd.velrhop.data(),cd.velrhop.size()*4);
+  memcpy(out->caseposmin,cd.caseposmin,24); memcpy(out->caseposmax,cd.caseposmax,24);
+  strncpy(out->name,cd.name.c_str(),sizeof(out->name)-1);
+  for(auto &b:cd.blocks)if(b.type==3 && out->nfluidblocks<DSPH_MAXPHASES)out->fluidblock_count[out->nfluidblocks++]=b.count;
+}
+int dsph_case_make(dsph_case *out,const char *kind,uint64_t np_target,uint32_t seed){
+  if(!out||!kind){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  return Guard([&]{ CaseData cd; MakeCase(cd,kind,np_target,seed); CaseToC(cd,out); });
+}
+int dsph_case_free(dsph_case *c){
+  if(!c)return DSPH_OK;
+  delete[] c->idp; delete[] c->pos_xyz; delete[] c->velrhop_xyzw; c->idp=nullptr; c->pos_xyz=nullptr; c->velrhop_xyzw=nullptr;
+  return DSPH_OK;
+}
+int dsph_case_load(dsph_case *out,const char *dir,const char *casename){
+  if(!out||!dir||!casename){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  const int r=Guard([&]{ CaseData cd; LoadCase(cd,dir,casename); CaseToC(cd,out); });
+  return r==DSPH_OK? r: DSPH_ERR_IO;
+}
+int dsph_case_save(const dsph_case *c,const char *dir,const char *casename){
+  if(!c||!dir||!casename){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  const int r=Guard([&]{
+    CaseData cd; cd.cfg=c->cfg; cd.name=casename;
+    cd.idp.assign(c->idp,c->idp+c->np); cd.pos.assign(c->pos_xyz,c->pos_xyz+size_t(c->np)*3); cd.velrhop.assign(c->velrhop_xyzw,c->velrhop_xyzw+size_t(c->np)*4);
+    memcpy(cd.caseposmin,c->caseposmin,24); memcpy(cd.caseposmax,c->caseposmax,24);
+    // mk blocks: one fixed block + one fluid block per phase (single block when not multiphase)
+    if(c->cfg.casenfixed)cd.blocks.push_back({0,0,cd.mkboundfirst,0,c->cfg.casenfixed});
+    if(c->nfluidblocks>1){ unsigned beg=c->cfg.casenfixed; for(unsigned b=0;b<c->nfluidblocks;b++){ cd.blocks.push_back({3,b,cd.mkfluidfirst+b,beg,c->fluidblock_count[b]}); beg+=c->fluidblock_count[b]; } }
+    else cd.blocks.push_back({3,0,cd.mkfluidfirst,c->cfg.casenfixed,c->cfg.casenfluid});
+    // keep the simulation domain exactly as configured
+    for(int i=0;i<3;i++){ cd.posmin[i].mode=3; cd.posmin[i].value=c->cfg.maprealposmin[i]; cd.posmax[i].mode=3; cd.posmax[i].value=c->cfg.maprealposmax[i]; }
+    SaveCase(cd,dir,casename);
+  });
+  return r==DSPH_OK? r: DSPH_ERR_IO;
+}
+int dsph_run_case(const char *dir,const char *casename,const char *dirout,int device,int nsteps,int savepart){
+  if(!dir||!casename||!dirout){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  return Guard([&]{ RunOptions o; o.dir=dir; o.casename=casename; o.dirout=dirout; o.device=device; o.nsteps=nsteps; o.savepart=(savepart!=0); RunCase(o); });
+}
+
+} // extern "C"

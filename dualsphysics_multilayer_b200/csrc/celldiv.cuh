@@ -1,0 +1,257 @@
+// celldiv.cuh -- GPU cell-linked list, hand-written for sm_100a.
+//
+//   ker_div_limits    min/max cell of valid particles           (cudiv::LimitsCell, S/JCellDivGpu_ker.cu:343-481;
+//                                                                 CPU: JCellDivCpu::LimitsCellBound/Fluid S/JCellDivCpu.cpp:255-330)
+//   ker_div_prepare   cell domain + special boxes ON THE DEVICE  (JCellDivCpuSingle::CalcCellDomain/MergeMapCellBoundFluid/PrepareNct,
+//                                                                 S/JCellDivCpuSingle.cpp:47-125)
+//   ker_div_presort   sort key per particle                      (KerPreSortFull S/JCellDivGpuSingle_ker.cu:41-72,
+//                                                                 CPU PreSortFull S/JCellDivCpuSingle.cpp:134-162)
+//   RadixSortPairs    stable sort (radixsort.cuh)                (cudiv::Sort)
+//   ker_div_cellmark + suffix-min scan   begin-cell table in the CPU form unsigned[2*nct+6] (S/JCellDivCpu.h:80,141,153)
+//   ker_div_counts    sizes of the special boxes                 (S/JCellDivCpuSingle.cpp:326-337)
+//   ker_div_reorder   ONE fused gather of every particle array + cell-relative position + pressure
+//                     (replaces 6+ KerSortDataParticles launches S/JCellDivGpu_ker.cu:553-642 + cusphs::UpdatePosCell
+//                      S/JSphGpuSimple_ker.cu:41-69 + the per-pair pow() for pressure S/JSphGpu_ker.cu:559)
+#pragma once
+#include "devtypes.h"
+#include "radixsort.cuh"
+#include "../../include/dsph_b200.h"
+
+namespace dsph {
+
+constexpr int DIV_THREADS=256;
+
+__device__ __forceinline__ unsigned DcCellx(unsigned dcc,unsigned cel){ return cel>>((dcc>>10)&31); }
+__device__ __forceinline__ unsigned DcCelly(unsigned dcc,unsigned cel){ return (cel<<(dcc>>25))>>((dcc>>5)&31); }
+__device__ __forceinline__ unsigned DcCellz(unsigned dcc,unsigned cel){ return (cel<<(dcc&31))>>(dcc&31); }
+__device__ __forceinline__ unsigned DcCell(unsigned dcc,unsigned cx,unsigned cy,unsigned cz){ return (cx<<((dcc>>10)&31))|(cy<<((dcc>>15)&31))|cz; }
+
+// limits[0..2]=min (init UINT_MAX), limits[3..5]=max (init 0)
+__global__ void __launch_bounds__(DIV_THREADS) ker_div_limits(unsigned n,unsigned pini,const unsigned* __restrict__ dcell,
+  const typecode* __restrict__ code,unsigned domcellcode,unsigned* __restrict__ limits)
+{
+  unsigned mn[3]={0xffffffffu,0xffffffffu,0xffffffffu}, mx[3]={0,0,0};
+  for(unsigned i=blockIdx.x*blockDim.x+threadIdx.x;i<n;i+=gridDim.x*blockDim.x){
+    const unsigned p=pini+i;
+    if((code[p]&DSPH_CODE_MASKSPECIAL)<DSPH_CODE_OUTIGNORE){
+      const unsigned rcell=dcell[p];
+      const unsigned c[3]={DcCellx(domcellcode,rcell),DcCelly(domcellcode,rcell),DcCellz(domcellcode,rcell)};
+      #pragma unroll
+      for(int k=0;k<3;k++){ mn[k]=min(mn[k],c[k]); mx[k]=max(mx[k],c[k]); }
+    }
+  }
+  #pragma unroll
+  for(int k=0;k<3;k++){
+    mn[k]=__reduce_min_sync(0xffffffffu,mn[k]);
+    mx[k]=__reduce_max_sync(0xffffffffu,mx[k]);
+  }
+  if((threadIdx.x&31)==0){
+    #pragma unroll
+    for(int k=0;k<3;k++){ atomicMin(&limits[k],mn[k]); atomicMax(&limits[3+k],mx[k]); }
+  }
+}
+
+// limb/limf: raw limits of boundary / fluid particles.  useblim: recompute the cached boundary limits.
+__global__ void ker_div_prepare(const unsigned* __restrict__ limb,const unsigned* __restrict__ limf,int useblim,
+  unsigned dcx,unsigned dcy,unsigned dcz,unsigned scelldiv,unsigned nptot,unsigned maxnctt,DivParams* __restrict__ dp)
+{
+  if(threadIdx.x||blockIdx.x)return;
+  const unsigned domcells[3]={dcx,dcy,dcz};
+  unsigned celbmin[3],celbmax[3],celfmin[3],celfmax[3];
+  if(useblim){
+    const bool empty=(limb[0]>limb[3]);
+    for(int i=0;i<3;i++){ celbmin[i]=(empty? domcells[i]: limb[i]); celbmax[i]=(empty? 0: limb[3+i]); dp->blimmin[i]=celbmin[i]; dp->blimmax[i]=celbmax[i]; }
+  }
+  else for(int i=0;i<3;i++){ celbmin[i]=dp->blimmin[i]; celbmax[i]=dp->blimmax[i]; }
+  {
+    const bool empty=(limf[0]>limf[3]);
+    for(int i=0;i<3;i++){ celfmin[i]=(empty? domcells[i]: limf[i]); celfmax[i]=(empty? 0: limf[3+i]); }
+  }
+  unsigned cmin[3],cmax[3];
+  for(int i=0;i<3;i++){
+    cmin[i]=max(min(celbmin[i],celfmin[i]),(celfmin[i]>=scelldiv? celfmin[i]-scelldiv: 0u));
+    cmax[i]=min(max(celbmax[i],celfmax[i]),celfmax[i]+scelldiv);
+    if(cmax[i]>=domcells[i])cmax[i]=domcells[i]-1;
+  }
+  if(cmin[0]>cmax[0]||cmin[1]>cmax[1]||cmin[2]>cmax[2])for(int i=0;i<3;i++)cmin[i]=cmax[i]=0;
+  for(int i=0;i<3;i++){ dp->cellmin[i]=cmin[i]; dp->cellmax[i]=cmax[i]; }
+  const unsigned ncx=cmax[0]-cmin[0]+1, ncy=cmax[1]-cmin[1]+1, ncz=cmax[2]-cmin[2]+1;
+  const unsigned long long nct64=(unsigned long long)(ncx)*ncy*ncz;
+  dp->error=(nct64*2+6>maxnctt? 1u: 0u);
+  const unsigned nct=unsigned(nct64);
+  dp->ncx=ncx; dp->ncy=ncy; dp->ncz=ncz; dp->nsheet=ncx*ncy; dp->nct=nct; dp->nctt=nct*2+6;
+  dp->boxboundignore=nct; dp->boxfluid=nct+1; dp->boxboundout=nct+1+nct; dp->boxfluidout=dp->boxboundout+1;
+  dp->boxboundoutignore=dp->boxfluidout+1; dp->boxfluidoutignore=dp->boxboundoutignore+1;
+  dp->nptot=nptot;
+}
+
+__global__ void __launch_bounds__(DIV_THREADS) ker_div_presort(unsigned n,const unsigned* __restrict__ dcell,const typecode* __restrict__ code,
+  unsigned domcellcode,const DivParams* __restrict__ dpp,unsigned* __restrict__ cellpart)
+{
+  const unsigned p=blockIdx.x*blockDim.x+threadIdx.x;
+  if(p>=n)return;
+  const DivParams &dp=*dpp;
+  const unsigned rcell=dcell[p];
+  const unsigned cx=DcCellx(domcellcode,rcell)-dp.cellmin[0];
+  const unsigned cy=DcCelly(domcellcode,rcell)-dp.cellmin[1];
+  const unsigned cz=DcCellz(domcellcode,rcell)-dp.cellmin[2];
+  const unsigned cellsort=cx+cy*dp.ncx+cz*dp.nsheet;
+  const unsigned rcode=code[p];
+  const unsigned codetype=rcode&DSPH_CODE_MASKTYPE, codeout=rcode&DSPH_CODE_MASKSPECIAL;
+  unsigned box;
+  if(codetype<DSPH_CODE_TYPE_FLOATING)
+    box=(codeout<DSPH_CODE_OUTIGNORE? ((cx<dp.ncx && cy<dp.ncy && cz<dp.ncz)? cellsort: dp.boxboundignore): (codeout==DSPH_CODE_OUTIGNORE? dp.boxboundoutignore: dp.boxboundout));
+  else
+    box=(codeout<=DSPH_CODE_OUTIGNORE? (codeout<DSPH_CODE_OUTIGNORE? dp.boxfluid+cellsort: dp.boxfluidoutignore): (codetype==DSPH_CODE_TYPE_FLOATING? dp.boxboundout: dp.boxfluidout));
+  cellpart[p]=box;
+}
+
+// begin[] pre-filled with 0xffffffff; marks first particle of every non-empty box, begin[nctt-1]=n (sentinel)
+__global__ void __launch_bounds__(DIV_THREADS) ker_div_cellmark(unsigned n,const unsigned* __restrict__ sortedkeys,const DivParams* __restrict__ dpp,unsigned* __restrict__ begin)
+{
+  const unsigned p=blockIdx.x*blockDim.x+threadIdx.x;
+  if(p==0)begin[dpp->nctt-1]=n;
+  if(p>=n)return;
+  const unsigned k=sortedkeys[p];
+  if(p==0 || sortedkeys[p-1]!=k)begin[k]=p;
+}
+
+// suffix-min over begin[0..nctt): empty boxes take the begin of the next non-empty box.  Chunked 3-kernel scan with the
+// number of elements read from the device (host launches for the maximum).
+constexpr int SM_THREADS=256;
+constexpr int SM_ITEMS=8;
+constexpr int SM_CHUNK=SM_THREADS*SM_ITEMS;
+__device__ __forceinline__ unsigned BlockSuffixMinExclusive(unsigned v,unsigned *total){
+  // exclusive min over threads with HIGHER threadIdx (suffix), identity 0xffffffff
+  __shared__ unsigned wmin[SM_THREADS/32];
+  const int lane=threadIdx.x&31, w=threadIdx.x>>5;
+  unsigned inc=v;
+  #pragma unroll
+  for(int o=1;o<32;o<<=1){ const unsigned t=__shfl_down_sync(0xffffffffu,inc,o); if(lane+o<32)inc=min(inc,t); }
+  if(lane==0)wmin[w]=inc;
+  __syncthreads();
+  if(w==0){
+    unsigned s=(lane<SM_THREADS/32? wmin[lane]: 0xffffffffu);
+    #pragma unroll
+    for(int o=1;o<SM_THREADS/32;o<<=1){ const unsigned t=__shfl_down_sync(0xffffffffu,s,o); if(lane+o<SM_THREADS/32)s=min(s,t); }
+    if(lane<SM_THREADS/32)wmin[lane]=s;   // inclusive suffix over warps
+  }
+  __syncthreads();
+  const unsigned wnext=(w+1<SM_THREADS/32? wmin[w+1]: 0xffffffffu);
+  unsigned excl=__shfl_down_sync(0xffffffffu,inc,1); if(lane==31)excl=0xffffffffu;
+  if(total)*total=wmin[0];
+  const unsigned r=min(excl,wnext);
+  __syncthreads();
+  return r;
+}
+__global__ void __launch_bounds__(SM_THREADS) ker_div_sufmin_chunks(unsigned* __restrict__ data,const DivParams* __restrict__ dpp,unsigned* __restrict__ chunkmin)
+{
+  const unsigned n=dpp->nctt;
+  const unsigned base=blockIdx.x*SM_CHUNK+threadIdx.x*SM_ITEMS;
+  if(blockIdx.x*SM_CHUNK>=n){ if(threadIdx.x==0)chunkmin[blockIdx.x]=0xffffffffu; return; }
+  unsigned v[SM_ITEMS]; unsigned s=0xffffffffu;
+  #pragma unroll
+  for(int i=0;i<SM_ITEMS;i++){ v[i]=(base+i<n? data[base+i]: 0xffffffffu); s=min(s,v[i]); }
+  unsigned total;
+  unsigned after=BlockSuffixMinExclusive(s,&total);
+  #pragma unroll
+  for(int i=SM_ITEMS-1;i>=0;i--){ after=min(after,v[i]); if(base+i<n)data[base+i]=after; }
+  if(threadIdx.x==0)chunkmin[blockIdx.x]=total;
+}
+// single block: chunkmin[c] <- min over chunks > c (exclusive suffix), serial over blocks of SM_THREADS from the end
+__global__ void __launch_bounds__(SM_THREADS) ker_div_sufmin_sums(unsigned* __restrict__ chunkmin,unsigned m)
+{
+  __shared__ unsigned carry_s;
+  if(threadIdx.x==0)carry_s=0xffffffffu;
+  __syncthreads();
+  const unsigned nb=(m+SM_THREADS-1)/SM_THREADS;
+  for(unsigned b=nb;b-->0;){
+    const unsigned i=b*SM_THREADS+threadIdx.x;
+    const unsigned v=(i<m? chunkmin[i]: 0xffffffffu);
+    unsigned total;
+    const unsigned carry=carry_s;
+    unsigned ex=BlockSuffixMinExclusive(v,&total);
+    ex=min(ex,carry);
+    if(i<m)chunkmin[i]=ex;
+    __syncthreads();
+    if(threadIdx.x==0)carry_s=min(carry,total);
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(SM_THREADS) ker_div_sufmin_apply(unsigned* __restrict__ data,const DivParams* __restrict__ dpp,const unsigned* __restrict__ chunkmin)
+{
+  const unsigned n=dpp->nctt;
+  const unsigned base=blockIdx.x*SM_CHUNK+threadIdx.x*SM_ITEMS;
+  const unsigned off=chunkmin[blockIdx.x];
+  #pragma unroll
+  for(int i=0;i<SM_ITEMS;i++)if(base+i<n)data[base+i]=min(data[base+i],off);
+}
+
+__global__ void ker_div_counts(const unsigned* __restrict__ begin,unsigned npb12,DivParams* __restrict__ dp)
+{
+  if(threadIdx.x||blockIdx.x)return;
+  dp->npbignore=begin[dp->boxboundignore+1]-begin[dp->boxboundignore];
+  dp->npbout=begin[dp->boxboundout+1]-begin[dp->boxboundout];
+  dp->npfout=begin[dp->boxfluidout+1]-begin[dp->boxfluidout];
+  dp->npboutignore=begin[dp->boxboundoutignore+1]-begin[dp->boxboundoutignore];
+  dp->npfoutignore=begin[dp->boxfluidoutignore+1]-begin[dp->boxfluidoutignore];
+  dp->npfinal=dp->nptot-dp->npbout-dp->npfout-dp->npboutignore-dp->npfoutignore;
+  dp->npbfinal=npb12-dp->npboutignore;
+}
+
+// Every particle array is gathered in ONE pass; optional arrays are null.
+struct ReorderArrays {
+  const unsigned *idp_in; unsigned *idp_out;
+  const typecode *code_in; typecode *code_out;
+  const unsigned *dcell_in; unsigned *dcell_out;
+  const double *pos_in; double *pos_out;            // xyz packed (24 B)
+  const float4 *velrhop_in; float4 *velrhop_out;
+  const float4 *velrhopm1_in; float4 *velrhopm1_out;   // Verlet
+  const double *pospre_in; double *pospre_out;         // Symplectic (mid-step divide)
+  const float4 *velrhoppre_in; float4 *velrhoppre_out;
+  const float *spstau_in; float *spstau_out;           // 6 floats
+  float4 *posp;                                        // out: cell-relative xyz + pressure
+};
+
+__device__ __forceinline__ float PressFromRhop(float rhop,const DevCtes &c){
+  // same rounding points as the reference CPU build (see oracle/sph_oracle.cpp PreInteraction): float product
+  // rhop*(1/rhop0), then pow, -1 and *B in double, one rounding to float.
+  const float x=__fmul_rn(rhop,c.ovrhopzero);
+  return float(c.cteb_d*(pow(double(x),c.gamma_d)-1.0));
+}
+
+__global__ void __launch_bounds__(DIV_THREADS) ker_div_reorder(unsigned n,const unsigned* __restrict__ sortpart,ReorderArrays a,DevCtes c)
+{
+  const unsigned p=blockIdx.x*blockDim.x+threadIdx.x;
+  if(p>=n)return;
+  const unsigned s=sortpart[p];
+  a.idp_out[p]=a.idp_in[s];
+  a.code_out[p]=a.code_in[s];
+  const unsigned rcell=a.dcell_in[s];
+  a.dcell_out[p]=rcell;
+  const double px=a.pos_in[3*size_t(s)], py=a.pos_in[3*size_t(s)+1], pz=a.pos_in[3*size_t(s)+2];
+  a.pos_out[3*size_t(p)]=px; a.pos_out[3*size_t(p)+1]=py; a.pos_out[3*size_t(p)+2]=pz;
+  const float4 vr=a.velrhop_in[s];
+  a.velrhop_out[p]=vr;
+  if(a.velrhopm1_in)a.velrhopm1_out[p]=a.velrhopm1_in[s];
+  if(a.pospre_in){
+    a.pospre_out[3*size_t(p)]=a.pospre_in[3*size_t(s)]; a.pospre_out[3*size_t(p)+1]=a.pospre_in[3*size_t(s)+1]; a.pospre_out[3*size_t(p)+2]=a.pospre_in[3*size_t(s)+2];
+    a.velrhoppre_out[p]=a.velrhoppre_in[s];
+  }
+  if(a.spstau_in){
+    #pragma unroll
+    for(int k=0;k<6;k++)a.spstau_out[6*size_t(p)+k]=a.spstau_in[6*size_t(s)+k];
+  }
+  // cell-relative position (float) + pressure; excluded particles (dcell=0xffffffff) get zeros
+  float4 pp=make_float4(0,0,0,0);
+  if(rcell!=0xffffffffu){
+    const unsigned cx=DcCellx(c.domcellcode,rcell), cy=DcCelly(c.domcellcode,rcell), cz=DcCellz(c.domcellcode,rcell);
+    pp.x=float(px-(c.domposmin[0]+double(cx)*c.scell_d));
+    pp.y=float(py-(c.domposmin[1]+double(cy)*c.scell_d));
+    pp.z=float(pz-(c.domposmin[2]+double(cz)*c.scell_d));
+    pp.w=PressFromRhop(vr.w,c);
+  }
+  a.posp[p]=pp;
+}
+
+} // namespace dsph

@@ -1,0 +1,538 @@
+// engine.cu -- host orchestration of the B200 hot path: the JSphGpuSingle / JCellDivGpuSingle work-alike behind the
+// C ABI of include/dsph_b200.h.  One context = one GPU = one CUDA stream; every kernel is launched on that stream and
+// timed with CUDA events on it.  Sequencing follows JSphGpuSingle::RunCellDivide / Interaction_Forces /
+// ComputeStep_Sym / ComputeStep_Ver (S/JSphGpuSingle.cpp:331-417,435-486,548-596).
+#include "engine.h"
+#include "radixsort.cuh"
+#include "celldiv.cuh"
+#include "forces.cuh"
+#include "forces_v2.cuh"
+#include "step.cuh"
+#include "periodic.cuh"
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <cfloat>
+#include <algorithm>
+
+namespace dsph {
+
+#define CUCHECK(x) do{ cudaError_t e_=(x); if(e_!=cudaSuccess)throw EngineError(DSPH_ERR_CUDA,std::string(#x)+": "+cudaGetErrorString(e_)); }while(0)
+
+template<class T> static void DevAlloc(T *&p,size_t n){ if(p){ cudaFree(p); p=nullptr; } if(n)CUCHECK(cudaMalloc((void**)&p,n*sizeof(T))); }
+template<class T> static void DevFree(T *&p){ if(p){ cudaFree(p); p=nullptr; } }
+
+static int KeyBits(unsigned long long maxkey){ int b=1; while((maxkey>>b)!=0)b++; return b; }
+
+Engine::Engine(int device_,const dsph_config &c,unsigned capacity):device(device_)
+{
+  int ndev=0;
+  if(cudaGetDeviceCount(&ndev)!=cudaSuccess || ndev<=0)throw EngineError(DSPH_ERR_NOGPU,"No CUDA device is available: the B200 hot path has no CPU fallback.");
+  if(device<0 || device>=ndev)throw EngineError(DSPH_ERR_ARG,"Invalid CUDA device index.");
+  CUCHECK(cudaSetDevice(device));
+  CUCHECK(cudaStreamCreateWithFlags(&stm,cudaStreamNonBlocking));
+  for(int i=0;i<NEVENTS;i++)CUCHECK(cudaEventCreate(&ev[i]));
+  CUCHECK(cudaMallocHost((void**)&hpin,sizeof(HostPinned)));
+  memset(hpin,0,sizeof(HostPinned));
+  Configure(c);
+  Allocate(capacity);
+}
+
+Engine::~Engine(){
+  cudaSetDevice(device);
+  FreeAll();
+  for(int i=0;i<NEVENTS;i++)if(ev[i])cudaEventDestroy(ev[i]);
+  if(hpin)cudaFreeHost(hpin);
+  if(stm)cudaStreamDestroy(stm);
+}
+
+void Engine::Configure(const dsph_config &c){
+  cfg=c;
+  DeriveConstants(cfg,k);
+  if(cfg.nn_on)throw EngineError(DSPH_ERR_ARG,"The multiphase non-Newtonian formulation is not available in this build yet.");
+  if(cfg.casenmoving || cfg.casenfloat)throw EngineError(DSPH_ERR_ARG,"Moving and floating particles are outside the hot-path scope.");
+  memset(&dc,0,sizeof(dc));
+  dc.kernelh=cfg.kernelh; dc.ovkernelh=1.f/cfg.kernelh; dc.kernelsize2=k.kernelsize2; dc.eta2=k.eta2; dc.awen=k.awen; dc.bwen=k.bwen;
+  dc.cub_a2=k.cub_a2; dc.cub_a24=k.cub_a24; dc.cub_c1=k.cub_c1; dc.cub_d1=k.cub_d1; dc.cub_c2=k.cub_c2; dc.cub_od_wdeltap=k.cub_od_wdeltap;
+  dc.cteb=cfg.cteb; dc.gamma=cfg.gamma; dc.ovgamma=1.f/cfg.gamma; dc.rhopzero=cfg.rhopzero; dc.ovrhopzero=1.0f/cfg.rhopzero;
+  dc.massfluid=cfg.massfluid; dc.massbound=cfg.massbound; dc.cteb_d=double(cfg.cteb); dc.gamma_d=double(cfg.gamma);
+  dc.cs0=float(k.cs0); dc.visco=cfg.visco; dc.viscobound=cfg.visco*cfg.viscoboundfactor; dc.ddtkh=k.ddtkh; dc.ddtgz=k.ddtgz;
+  dc.spssmag=k.spssmag; dc.spsblin=k.spsblin;
+  { // series of (1+t)^g-1 with g=1/gamma (float, like the reference's 1.f/Gamma), coefficients in double
+    const double g=double(dc.ovgamma); double cf=1;
+    for(int i=0;i<6;i++){ cf*=(g-i)/double(i+1); dc.powc[i]=float(cf); }
+  }
+  dc.scell=k.scell; dc.scelldiv=k.scelldiv; dc.scell_d=double(k.scell);
+  for(int i=0;i<3;i++){
+    dc.domposmin[i]=k.domposmin[i]; dc.domcells[i]=k.domcells[i];
+    dc.maprealposmin[i]=k.maprealposmin[i]; dc.maprealsize[i]=k.maprealsize[i];
+    dc.perixinc[i]=k.perixinc[i]; dc.periyinc[i]=k.periyinc[i]; dc.perizinc[i]=k.perizinc[i];
+    dc.gravity[i]=cfg.gravity[i];
+  }
+  dc.domcellcode=k.domcellcode;
+  dc.perix=cfg.perix; dc.periy=cfg.periy; dc.periz=cfg.periz; dc.periactive=k.periactive;
+  dc.movlimit=k.movlimit;
+  dc.rhopoutmin=cfg.rhopoutmin; dc.rhopoutmax=cfg.rhopoutmax;
+  if(!(dc.rhopoutmin<dc.rhopoutmax)){ dc.rhopoutmin=-FLT_MAX; dc.rhopoutmax=FLT_MAX; }
+  dc.simulate2d=cfg.simulate2d; dc.dtallparticles=cfg.dtallparticles;
+  dc.shiftmode=cfg.shiftmode; dc.shifttfs=cfg.shifttfs;
+  symplecticdtpre=k.dtini; verletstep=0;
+}
+
+void Engine::FreeAll(){
+  for(int b=0;b<2;b++){
+    DevFree(idp[b]); DevFree(code[b]); DevFree(dcell[b]); DevFree(pos[b]); DevFree(velrhop[b]);
+    DevFree(velrhopm1[b]); DevFree(pospre[b]); DevFree(velrhoppre[b]); DevFree(spstau[b]);
+    DevFree(rs.keys[b]); DevFree(rs.vals[b]);
+  }
+  DevFree(posp); DevFree(acear); DevFree(shiftposfs); DevFree(spsgradvel);
+  DevFree(rs.hist); DevFree(rs.chunksum); DevFree(rs.chunksum2);
+  DevFree(begincell); DevFree(sufmin); DevFree(divparams); DevFree(limits); DevFree(fmax); DevFree(perilist); DevFree(pericount);
+}
+
+void Engine::Allocate(unsigned capacity){
+  cap=std::max(capacity,1024u);
+  const bool verlet=(cfg.tstep==DSPH_STEP_VERLET), sympl=(cfg.tstep==DSPH_STEP_SYMPLECTIC), sps=(cfg.tvisco==DSPH_VISCO_LAMINARSPS);
+  for(int b=0;b<2;b++){
+    DevAlloc(idp[b],cap); DevAlloc(code[b],cap); DevAlloc(dcell[b],cap); DevAlloc(pos[b],size_t(cap)*3); DevAlloc(velrhop[b],cap);
+    if(verlet)DevAlloc(velrhopm1[b],cap);
+    if(sympl){ DevAlloc(pospre[b],size_t(cap)*3); DevAlloc(velrhoppre[b],cap); }
+    if(sps)DevAlloc(spstau[b],size_t(cap)*6);
+    DevAlloc(rs.keys[b],cap); DevAlloc(rs.vals[b],cap);
+  }
+  DevAlloc(posp,cap); DevAlloc(acear,cap);
+  if(cfg.shiftmode)DevAlloc(shiftposfs,cap);
+  if(sps)DevAlloc(spsgradvel,size_t(cap)*6);
+  const unsigned ntiles=RsTiles(cap);
+  rs.capacity=cap; rs.histcap=256u*ntiles;
+  DevAlloc(rs.hist,rs.histcap);
+  DevAlloc(rs.chunksum,ScChunks(rs.histcap)+1);
+  DevAlloc(rs.chunksum2,ScChunks(ScChunks(rs.histcap))+1);
+  const unsigned long long nctmax=(unsigned long long)k.domcells[0]*k.domcells[1]*k.domcells[2];
+  if(nctmax*2+6>=0x7fffffffull)throw EngineError(DSPH_ERR_ARG,"The number of cells is too big.");
+  maxnctt=unsigned(nctmax*2+6);
+  keybits=KeyBits(maxnctt);
+  DevAlloc(begincell,size_t(maxnctt)+8);
+  DevAlloc(sufmin,size_t((maxnctt+SM_CHUNK-1)/SM_CHUNK)+8);
+  DevAlloc(divparams,1); DevAlloc(limits,12); DevAlloc(fmax,1);
+  CUCHECK(cudaMemsetAsync(divparams,0,sizeof(DivParams),stm));
+  if(k.periactive){ DevAlloc(perilist,size_t(cap)); DevAlloc(pericount,4); }
+  cur=0;
+}
+
+void Engine::Upload(unsigned np_,unsigned npb_,const unsigned *hidp,const typecode *hcode,const double *hpos,const float *hvelrhop){
+  CUCHECK(cudaSetDevice(device));
+  if(np_>cap)throw EngineError(DSPH_ERR_ARG,"The number of particles exceeds the capacity of the context.");
+  if(npb_>np_)throw EngineError(DSPH_ERR_ARG,"npb > np.");
+  np=np_; npb=npb_; npbok=npb_; npbper=npfper=0; haspre=false; boundchanged=true; blimok=false; divok=false;
+  std::vector<typecode> tmpcode;
+  if(!hcode){
+    tmpcode.resize(np);
+    for(unsigned p=0;p<np;p++)tmpcode[p]=typecode(hidp[p]<cfg.casenfixed? DSPH_CODE_TYPE_FIXED: DSPH_CODE_TYPE_FLUID);
+    hcode=tmpcode.data();
+  }
+  // JSph::LoadDcellParticles (S/JSph.cpp:1690-1711): first cell hash on the host, identical double arithmetic
+  std::vector<unsigned> hdcell(np);
+  for(unsigned p=0;p<np;p++){
+    if((hcode[p]&DSPH_CODE_MASKSPECIAL)<DSPH_CODE_OUTIGNORE){
+      const double x=hpos[3*size_t(p)],y=hpos[3*size_t(p)+1],z=hpos[3*size_t(p)+2];
+      if((hcode[p]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_PERIODIC){   // restart of a state that still holds periodic duplicates
+        unsigned cx=unsigned((x-k.domposmin[0])/k.scell), cy=unsigned((y-k.domposmin[1])/k.scell), cz=unsigned((z-k.domposmin[2])/k.scell);
+        cx=(cx<=k.domcells[0]? cx: k.domcells[0]); cy=(cy<=k.domcells[1]? cy: k.domcells[1]); cz=(cz<=k.domcells[2]? cz: k.domcells[2]);
+        hdcell[p]=DcelCell(k.domcellcode,cx,cy,cz);
+        continue;
+      }
+      const bool in=(x>=k.domrealposmin[0] && y>=k.domrealposmin[1] && z>=k.domrealposmin[2] && x<k.domrealposmax[0] && y<k.domrealposmax[1] && z<k.domrealposmax[2]);
+      if(!in)throw EngineError(DSPH_ERR_PHYSICS,"Found new particles out.");
+      const unsigned cx=unsigned((x-k.domposmin[0])/k.scell), cy=unsigned((y-k.domposmin[1])/k.scell), cz=unsigned((z-k.domposmin[2])/k.scell);
+      hdcell[p]=DcelCell(k.domcellcode,cx,cy,cz);
+    }
+    else hdcell[p]=0xFFFFFFFFu;
+  }
+  CUCHECK(cudaMemcpyAsync(idp[cur],hidp,size_t(np)*4,cudaMemcpyHostToDevice,stm));
+  CUCHECK(cudaMemcpyAsync(code[cur],hcode,size_t(np)*2,cudaMemcpyHostToDevice,stm));
+  CUCHECK(cudaMemcpyAsync(dcell[cur],hdcell.data(),size_t(np)*4,cudaMemcpyHostToDevice,stm));
+  CUCHECK(cudaMemcpyAsync(pos[cur],hpos,size_t(np)*24,cudaMemcpyHostToDevice,stm));
+  CUCHECK(cudaMemcpyAsync(velrhop[cur],hvelrhop,size_t(np)*16,cudaMemcpyHostToDevice,stm));
+  if(cfg.tstep==DSPH_STEP_VERLET)CUCHECK(cudaMemcpyAsync(velrhopm1[cur],hvelrhop,size_t(np)*16,cudaMemcpyHostToDevice,stm));
+  if(cfg.tvisco==DSPH_VISCO_LAMINARSPS)CUCHECK(cudaMemsetAsync(spstau[cur],0,size_t(np)*24,stm));
+  CUCHECK(cudaStreamSynchronize(stm));
+  symplecticdtpre=k.dtini; verletstep=0; forcesok=false;
+}
+
+void Engine::SetVelrhopM1(const float *h){
+  if(cfg.tstep!=DSPH_STEP_VERLET)throw EngineError(DSPH_ERR_STATE,"VelrhopM1 is only used by Verlet.");
+  CUCHECK(cudaMemcpyAsync(velrhopm1[cur],h,size_t(np)*16,cudaMemcpyHostToDevice,stm));
+  CUCHECK(cudaStreamSynchronize(stm));
+}
+
+void Engine::SetSpsTau(const float *h){
+  if(cfg.tvisco!=DSPH_VISCO_LAMINARSPS)throw EngineError(DSPH_ERR_STATE,"SpsTau is only used by Laminar+SPS.");
+  CUCHECK(cudaMemcpyAsync(spstau[cur],h,size_t(np)*24,cudaMemcpyHostToDevice,stm));
+  CUCHECK(cudaStreamSynchronize(stm));
+}
+
+void Engine::Download(unsigned first,unsigned count,unsigned *hidp,typecode *hcode,unsigned *hdcell,double *hpos,float *hvelrhop){
+  if(first+count>np)throw EngineError(DSPH_ERR_ARG,"Range out of particles.");
+  if(hidp)CUCHECK(cudaMemcpyAsync(hidp,idp[cur]+first,size_t(count)*4,cudaMemcpyDeviceToHost,stm));
+  if(hcode)CUCHECK(cudaMemcpyAsync(hcode,code[cur]+first,size_t(count)*2,cudaMemcpyDeviceToHost,stm));
+  if(hdcell)CUCHECK(cudaMemcpyAsync(hdcell,dcell[cur]+first,size_t(count)*4,cudaMemcpyDeviceToHost,stm));
+  if(hpos)CUCHECK(cudaMemcpyAsync(hpos,pos[cur]+size_t(first)*3,size_t(count)*24,cudaMemcpyDeviceToHost,stm));
+  if(hvelrhop)CUCHECK(cudaMemcpyAsync(hvelrhop,velrhop[cur]+first,size_t(count)*16,cudaMemcpyDeviceToHost,stm));
+  CUCHECK(cudaStreamSynchronize(stm));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Periodic duplicates (JSphCpuSingle::RunPeriodic order, S/JSphCpuSingle.cpp:361-431)
+// ------------------------------------------------------------------------------------------------
+void Engine::RunPeriodic(){
+  const int B=256;
+  // mark current periodic particles to be ignored
+  ker_peri_ignore<<<(np+B-1)/B,B,0,stm>>>(np,code[cur]); launches++;
+  const unsigned npb0=npb, npf0=np-npb;
+  npbper=npfper=0; boundchanged=true;
+  for(unsigned ctype=0;ctype<2;ctype++){
+    const unsigned pini=(ctype? npb0: 0), num=(ctype? npf0: npb0);
+    for(unsigned cper=0;cper<3;cper++)if((cper==0&&cfg.perix)||(cper==1&&cfg.periy)||(cper==2&&cfg.periz)){
+      const double *inc=(cper==0? k.perixinc: (cper==1? k.periyinc: k.perizinc));
+      for(unsigned cblock=0;cblock<2;cblock++){
+        const unsigned nper=(ctype? npfper: npbper);
+        const unsigned pini2=(cblock? pini: np-nper), num2=(cblock? num: nper);
+        if(!num2)continue;
+        // ordered list (ascending particle, +inc before -inc) = the CPU list; built with a two-pass count/scan/write
+        PeriArgs pa; pa.n=num2; pa.pini=pini2;
+        for(int i=0;i<3;i++){ pa.inc[i]=inc[i]; pa.mapmin[i]=k.mapposmin[i]; pa.mapmax[i]=k.mapposmax[i]; }
+        pa.code=code[cur]; pa.pos=pos[cur];
+        unsigned *flags=rs.keys[0];   // scratch: count per particle (0..2), scanned in place
+        ker_peri_count<<<(num2+B-1)/B,B,0,stm>>>(pa,flags); launches++;
+        // total = last exclusive offset + last count: keep the last count
+        CUCHECK(cudaMemcpyAsync(&hpin->scratch[0],flags+(num2-1),4,cudaMemcpyDeviceToHost,stm));
+        DeviceExclusiveScan(flags,num2,rs.chunksum,rs.chunksum2,stm,&launches);
+        CUCHECK(cudaMemcpyAsync(&hpin->scratch[1],flags+(num2-1),4,cudaMemcpyDeviceToHost,stm));
+        CUCHECK(cudaStreamSynchronize(stm));
+        const unsigned count=hpin->scratch[0]+hpin->scratch[1];
+        if(!count)continue;
+        if(size_t(np)+count>cap)throw EngineError(DSPH_ERR_STATE,"Periodic particles exceed the capacity of the context (create it with a larger np_capacity).");
+        PeriDupArrays d;
+        d.idp=idp[cur]; d.code=code[cur]; d.dcell=dcell[cur]; d.pos=pos[cur]; d.velrhop=velrhop[cur];
+        d.velrhopm1=(cfg.tstep==DSPH_STEP_VERLET? velrhopm1[cur]: nullptr);
+        d.pospre=(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre? pospre[cur]: nullptr);
+        d.velrhoppre=(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre? velrhoppre[cur]: nullptr);
+        d.spstau=(cfg.tvisco==DSPH_VISCO_LAMINARSPS? spstau[cur]: nullptr);
+        ker_peri_duplicate<<<(num2+B-1)/B,B,0,stm>>>(pa,flags,np,d,dc); launches++;
+        np+=count;
+        if(!ctype)npbper+=count; else npfper+=count;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RunCellDivide
+// ------------------------------------------------------------------------------------------------
+void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
+  CUCHECK(cudaSetDevice(device));
+  const int B=DIV_THREADS;
+  CUCHECK(cudaEventRecord(ev[0],stm));
+  if(updateperiodic && k.periactive)RunPeriodic();
+  CUCHECK(cudaEventRecord(ev[1],stm));
+  const unsigned npb1=npb, npf1=np-npb-npbper-npfper, npb2=npbper, npf2=npfper;
+  const unsigned nptot=np;
+  if(boundchanged || k.periactive){ blimok=false; divok=false; }
+  // ---- limits (one reduction kernel per particle range, results stay on the device)
+  {
+    unsigned init[12]={0xffffffffu,0xffffffffu,0xffffffffu,0,0,0, 0xffffffffu,0xffffffffu,0xffffffffu,0,0,0};
+    memcpy(hpin->limitsinit,init,sizeof(init));
+    CUCHECK(cudaMemcpyAsync(limits,hpin->limitsinit,sizeof(init),cudaMemcpyHostToDevice,stm));
+    const int nsm=148*4;
+    auto lim=[&](unsigned n,unsigned pini,unsigned *dst){ if(n){ ker_div_limits<<<std::min<unsigned>((n+B-1)/B,nsm),B,0,stm>>>(n,pini,dcell[cur],code[cur],k.domcellcode,dst); launches++; } };
+    if(!blimok){ lim(npb1,0,limits); lim(npb2,npb1+npf1,limits); }
+    lim(npf1,npb1,limits+6); lim(npf2,npb1+npf1+npb2,limits+6);
+    ker_div_prepare<<<1,1,0,stm>>>(limits,limits+6,blimok? 0: 1,k.domcells[0],k.domcells[1],k.domcells[2],unsigned(k.scelldiv),nptot,maxnctt,divparams); launches++;
+    blimok=true;
+  }
+  CUCHECK(cudaEventRecord(ev[2],stm));
+  // ---- sort keys
+  if(nptot){ ker_div_presort<<<(nptot+B-1)/B,B,0,stm>>>(nptot,dcell[cur],code[cur],k.domcellcode,divparams,rs.keys[0]); launches++; }
+  CUCHECK(cudaEventRecord(ev[3],stm));
+  const int sidx=RadixSortPairs(rs,nptot,keybits,1,stm,&launches);
+  CUCHECK(cudaEventRecord(ev[4],stm));
+  // ---- begin-cell table
+  CUCHECK(cudaMemsetAsync(begincell,0xff,size_t(maxnctt)*4,stm));
+  {
+    const unsigned nb=std::max(1u,(nptot+B-1)/B);
+    ker_div_cellmark<<<nb,B,0,stm>>>(nptot,rs.keys[sidx],divparams,begincell); launches++;
+    const unsigned nchunks=(maxnctt+SM_CHUNK-1)/SM_CHUNK;
+    ker_div_sufmin_chunks<<<nchunks,SM_THREADS,0,stm>>>(begincell,divparams,sufmin); launches++;
+    if(nchunks>1){
+      ker_div_sufmin_sums<<<1,SM_THREADS,0,stm>>>(sufmin,nchunks); launches++;
+      ker_div_sufmin_apply<<<nchunks,SM_THREADS,0,stm>>>(begincell,divparams,sufmin); launches++;
+    }
+    ker_div_counts<<<1,1,0,stm>>>(begincell,npb1+npb2,divparams); launches++;
+  }
+  CUCHECK(cudaEventRecord(ev[5],stm));
+  // ---- fused reorder of every array (+ cell-relative position and pressure)
+  if(nptot){
+    const int o=cur^1;
+    ReorderArrays a; memset(&a,0,sizeof(a));
+    a.idp_in=idp[cur]; a.idp_out=idp[o]; a.code_in=code[cur]; a.code_out=code[o]; a.dcell_in=dcell[cur]; a.dcell_out=dcell[o];
+    a.pos_in=pos[cur]; a.pos_out=pos[o]; a.velrhop_in=velrhop[cur]; a.velrhop_out=velrhop[o];
+    if(cfg.tstep==DSPH_STEP_VERLET){ a.velrhopm1_in=velrhopm1[cur]; a.velrhopm1_out=velrhopm1[o]; }
+    if(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre){ a.pospre_in=pospre[cur]; a.pospre_out=pospre[o]; a.velrhoppre_in=velrhoppre[cur]; a.velrhoppre_out=velrhoppre[o]; }
+    if(cfg.tvisco==DSPH_VISCO_LAMINARSPS){ a.spstau_in=spstau[cur]; a.spstau_out=spstau[o]; }
+    a.posp=posp;
+    ker_div_reorder<<<(nptot+B-1)/B,B,0,stm>>>(nptot,rs.vals[sidx],a,dc); launches++;
+    cur=o;
+  }
+  CUCHECK(cudaEventRecord(ev[6],stm));
+  // ---- the only device->host transfer of the divide: cell domain + counts (one small async copy + sync)
+  CUCHECK(cudaMemcpyAsync(&hpin->dp,divparams,sizeof(DivParams),cudaMemcpyDeviceToHost,stm));
+  CUCHECK(cudaEventRecord(ev[7],stm));
+  CUCHECK(cudaStreamSynchronize(stm));
+  CUCHECK(cudaGetLastError());
+  dp=hpin->dp;
+  if(dp.error)throw EngineError(DSPH_ERR_STATE,"The number of cells is too big for the allocated cell table.");
+  // DivideFull bookkeeping (S/JCellDivCpuSingle.cpp:299-305); this implementation always sorts every particle,
+  // which yields the same order as the reference's fluid-only sort because the sort is stable.
+  bool same=divok;
+  for(int i=0;i<3;i++)if(lastcellmin[i]!=dp.cellmin[i] || lastcellmax[i]!=dp.cellmax[i])same=false;
+  dividefull=!same;
+  for(int i=0;i<3;i++){ lastcellmin[i]=dp.cellmin[i]; lastcellmax[i]=dp.cellmax[i]; }
+  divok=true;
+  npfout_last=dp.npfout; npout_total+=dp.npfout;
+  np=dp.npfinal; npb=dp.npbfinal; npbok=npb-dp.npbignore;
+  boundchanged=false; forcesok=false;
+  if(dp.npbout)throw EngineError(DSPH_ERR_PHYSICS,"Boundary particles were excluded from the domain (AbortBoundOut, S/JSph.cpp:2477).");
+  AccumTimers(true);
+  if(info){
+    memset(info,0,sizeof(*info));
+    info->np=np; info->npb=npb; info->npbok=npbok; info->npbper=npbper; info->npfper=npfper;
+    info->npbout=dp.npbout; info->npfout=dp.npfout; info->npbignore=dp.npbignore; info->npboutignore=dp.npboutignore; info->npfoutignore=dp.npfoutignore;
+    info->ncx=dp.ncx; info->ncy=dp.ncy; info->ncz=dp.ncz; info->nct=dp.nct; info->nctt=dp.nctt;
+    for(int i=0;i<3;i++){ info->cellmin[i]=dp.cellmin[i]; info->cellmax[i]=dp.cellmax[i]; info->domcells[i]=k.domcells[i]; info->domposmin[i]=k.domposmin[i]; }
+    info->domcellcode=k.domcellcode; info->dividefull=dividefull? 1: 0; info->scell=k.scell;
+  }
+}
+
+void Engine::AccumTimers(bool divide){
+  float ms=0;
+  if(divide){
+    cudaEventElapsedTime(&ms,ev[0],ev[1]); tm.su_periodic+=ms;
+    cudaEventElapsedTime(&ms,ev[1],ev[2]); tm.nl_limits+=ms;
+    cudaEventElapsedTime(&ms,ev[2],ev[3]); tm.nl_presort+=ms;
+    cudaEventElapsedTime(&ms,ev[3],ev[4]); tm.nl_radixsort+=ms;
+    cudaEventElapsedTime(&ms,ev[4],ev[5]); tm.nl_cellbegin+=ms;
+    cudaEventElapsedTime(&ms,ev[5],ev[6]); tm.nl_sortdata+=ms;
+    cudaEventElapsedTime(&ms,ev[6],ev[7]); tm.nl_outcheck+=ms;
+    cudaEventElapsedTime(&ms,ev[0],ev[7]); tm.total+=ms;
+  }
+}
+
+void Engine::GetBeginCell(unsigned *h,unsigned capacity){
+  if(capacity<dp.nctt)throw EngineError(DSPH_ERR_ARG,"begincell capacity too small.");
+  CUCHECK(cudaMemcpyAsync(h,begincell,size_t(dp.nctt)*4,cudaMemcpyDeviceToHost,stm));
+  CUCHECK(cudaStreamSynchronize(stm));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Interaction_Forces
+// ------------------------------------------------------------------------------------------------
+ForceParams Engine::MakeForceParams(){
+  ForceParams t; memset(&t,0,sizeof(t));
+  t.np=np; t.npb=npb; t.npbok=npbok;
+  t.ncx=int(dp.ncx); t.ncy=int(dp.ncy); t.ncz=int(dp.ncz); t.nsheet=int(dp.nsheet);
+  t.cellfluid=dp.nct+1;
+  for(int i=0;i<3;i++)t.cellzero[i]=dp.cellmin[i];
+  t.begincell=begincell; t.dcell=dcell[cur]; t.posp=posp; t.velrhop=velrhop[cur]; t.code=code[cur];
+  t.spstau=spstau[cur]; t.spsgradvel=spsgradvel; t.shiftposfs=shiftposfs; t.acear=acear; t.fmax=fmax;
+  return t;
+}
+
+template<int TKER,int TVISCO,int TDDT,bool SHIFT> static void LaunchFluid(int variant,unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm){
+  if(variant==1){
+    ker_forces_fluid_v1<TKER,TVISCO,TDDT,SHIFT><<<(npf+FORCES_THREADS-1)/FORCES_THREADS,FORCES_THREADS,0,stm>>>(t,c);
+  }
+  else LaunchFluidV2<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm);
+}
+template<int TKER,int TVISCO,int TDDT> static void LaunchFluid3(int variant,bool shift,unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm){
+  if(shift)LaunchFluid<TKER,TVISCO,TDDT,true>(variant,npf,t,c,stm); else LaunchFluid<TKER,TVISCO,TDDT,false>(variant,npf,t,c,stm);
+}
+template<int TKER,int TVISCO> static void LaunchFluid2(int variant,int tddt,bool shift,unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm){
+  switch(tddt){
+    case DSPH_DDT_NONE:     LaunchFluid3<TKER,TVISCO,DSPH_DDT_NONE>(variant,shift,npf,t,c,stm); break;
+    case DSPH_DDT_DDT:      LaunchFluid3<TKER,TVISCO,DSPH_DDT_DDT>(variant,shift,npf,t,c,stm); break;
+    case DSPH_DDT_DDT2:     LaunchFluid3<TKER,TVISCO,DSPH_DDT_DDT2>(variant,shift,npf,t,c,stm); break;
+    case DSPH_DDT_DDT2FULL: LaunchFluid3<TKER,TVISCO,DSPH_DDT_DDT2FULL>(variant,shift,npf,t,c,stm); break;
+    default: throw EngineError(DSPH_ERR_ARG,"Density Diffusion Term mode is not valid.");
+  }
+}
+template<int TKER> static void LaunchFluid1(int variant,int tvisco,int tddt,bool shift,unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm){
+  if(tvisco==DSPH_VISCO_ARTIFICIAL)LaunchFluid2<TKER,DSPH_VISCO_ARTIFICIAL>(variant,tddt,shift,npf,t,c,stm);
+  else if(tvisco==DSPH_VISCO_LAMINARSPS)LaunchFluid2<TKER,DSPH_VISCO_LAMINARSPS>(variant,tddt,shift,npf,t,c,stm);
+  else throw EngineError(DSPH_ERR_ARG,"Viscosity treatment is not valid.");
+}
+
+void Engine::Forces(int interstep,dsph_forceres *res){
+  (void)interstep;
+  CUCHECK(cudaSetDevice(device));
+  if(!divok)throw EngineError(DSPH_ERR_STATE,"dsph_forces_run needs a cell division first (dsph_celldiv_run).");
+  CUCHECK(cudaEventRecord(ev[8],stm));
+  CUCHECK(cudaMemsetAsync(fmax,0,sizeof(ForceMax),stm));
+  CUCHECK(cudaEventRecord(ev[9],stm));
+  const ForceParams t=MakeForceParams();
+  const unsigned npf=np-npb;
+  const bool shift=(cfg.shiftmode!=0);
+  if(npf){
+    if(cfg.tkernel==DSPH_KERNEL_WENDLAND)LaunchFluid1<DSPH_KERNEL_WENDLAND>(forcevariant,cfg.tvisco,cfg.tdensity,shift,npf,t,dc,stm);
+    else if(cfg.tkernel==DSPH_KERNEL_CUBIC)LaunchFluid1<DSPH_KERNEL_CUBIC>(forcevariant,cfg.tvisco,cfg.tdensity,shift,npf,t,dc,stm);
+    else throw EngineError(DSPH_ERR_ARG,"Kernel choice is not valid.");
+    launches++;
+    if(cfg.tvisco==DSPH_VISCO_LAMINARSPS){ ker_sps_tau<<<(npf+255)/256,256,0,stm>>>(npf,npb,velrhop[cur],spsgradvel,spstau[cur],dc); launches++; }
+  }
+  if(npb){
+    const unsigned nb=(npb+FORCES_THREADS-1)/FORCES_THREADS;
+    if(cfg.tkernel==DSPH_KERNEL_WENDLAND)ker_forces_bound_v1<DSPH_KERNEL_WENDLAND><<<nb,FORCES_THREADS,0,stm>>>(t,dc);
+    else ker_forces_bound_v1<DSPH_KERNEL_CUBIC><<<nb,FORCES_THREADS,0,stm>>>(t,dc);
+    launches++;
+  }
+  CUCHECK(cudaEventRecord(ev[10],stm));
+  CUCHECK(cudaMemcpyAsync(&hpin->fmax,fmax,sizeof(ForceMax),cudaMemcpyDeviceToHost,stm));
+  CUCHECK(cudaStreamSynchronize(stm));
+  CUCHECK(cudaGetLastError());
+  { float ms=0; cudaEventElapsedTime(&ms,ev[8],ev[9]); tm.cf_preforces+=ms; cudaEventElapsedTime(&ms,ev[9],ev[10]); tm.cf_forces+=ms; tm.total+=ms; lastforcems=ms; }
+  const ForceMax &m=hpin->fmax;
+  float f; unsigned b;
+  b=m.viscdt_bits; memcpy(&f,&b,4); viscdtmax=f;
+  b=m.ace2_bits; memcpy(&f,&b,4); acemax=sqrt(double(f));
+  b=m.vel2_bits; memcpy(&f,&b,4); velmax=double(sqrtf(f));
+  forcesok=true;
+  if(res)FillForceRes(res);
+}
+
+double Engine::DtVariable(double *pdt1,double *pdt2)const{
+  // JSphGpu::DtVariable S/JSphGpu.cpp:984-1009 (== JSphCpu::DtVariable S/JSphCpu.cpp:1614-1639)
+  const double dt1=(acemax? (sqrt(double(cfg.kernelh)/acemax)): DBL_MAX);
+  const double dt2=double(cfg.kernelh)/(std::max(k.cs0,velmax*10.)+double(cfg.kernelh)*viscdtmax);
+  double dt=cfg.cflnumber*std::min(dt1,dt2);
+  if(cfg.dtfixed_on)dt=cfg.dtfixed;
+  if(dt!=dt || std::isinf(dt))throw EngineError(DSPH_ERR_PHYSICS,"The computed Dt is NaN or infinity.");
+  if(dt<k.dtmin)dt=k.dtmin;
+  if(pdt1)*pdt1=dt1; if(pdt2)*pdt2=dt2;
+  return dt;
+}
+void Engine::FillForceRes(dsph_forceres *res)const{
+  memset(res,0,sizeof(*res));
+  res->viscdtmax=viscdtmax; res->acemax=float(acemax); res->velmax=float(velmax);
+  res->dt=DtVariable(&res->dt1,&res->dt2);
+}
+
+void Engine::ForcesDownload(unsigned first,unsigned count,float *ace,float *ar){
+  if(!forcesok)throw EngineError(DSPH_ERR_STATE,"Forces are not available.");
+  if(first+count>np)throw EngineError(DSPH_ERR_ARG,"Range out of particles.");
+  std::vector<float> h(size_t(count)*4);
+  CUCHECK(cudaMemcpyAsync(h.data(),acear+first,size_t(count)*16,cudaMemcpyDeviceToHost,stm));
+  CUCHECK(cudaStreamSynchronize(stm));
+  for(unsigned i=0;i<count;i++){
+    if(ace){ ace[3*size_t(i)]=h[4*size_t(i)]; ace[3*size_t(i)+1]=h[4*size_t(i)+1]; ace[3*size_t(i)+2]=h[4*size_t(i)+2]; }
+    if(ar)ar[i]=h[4*size_t(i)+3];
+  }
+}
+
+void Engine::Pips(unsigned long long *fr,unsigned long long *fc,unsigned long long *br,unsigned long long *bc){
+  if(!divok)throw EngineError(DSPH_ERR_STATE,"dsph_pips needs a cell division first.");
+  CUCHECK(cudaMemsetAsync(fmax,0,sizeof(ForceMax),stm));
+  const ForceParams t=MakeForceParams();
+  if(np>npb){ ker_pips<<<(np-npb+FORCES_THREADS-1)/FORCES_THREADS,FORCES_THREADS,0,stm>>>(t,dc,npb,np-npb,1); launches++; }
+  if(npbok){ ker_pips<<<(npbok+FORCES_THREADS-1)/FORCES_THREADS,FORCES_THREADS,0,stm>>>(t,dc,0,npbok,0); launches++; }
+  CUCHECK(cudaMemcpyAsync(&hpin->fmax,fmax,sizeof(ForceMax),cudaMemcpyDeviceToHost,stm));
+  CUCHECK(cudaStreamSynchronize(stm));
+  if(fr)*fr=hpin->fmax.pips_fluid_real; if(fc)*fc=hpin->fmax.pips_fluid_checked;
+  if(br)*br=hpin->fmax.pips_bound_real; if(bc)*bc=hpin->fmax.pips_bound_checked;
+  forcesok=false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ComputeStep
+// ------------------------------------------------------------------------------------------------
+StepArrays Engine::MakeStepArrays(){
+  StepArrays a; memset(&a,0,sizeof(a));
+  a.np=np; a.npb=npb; a.pos=pos[cur]; a.dcell=dcell[cur]; a.code=code[cur]; a.velrhop=velrhop[cur];
+  a.velrhopm1=velrhopm1[cur]; a.pospre=pospre[cur]; a.velrhoppre=velrhoppre[cur]; a.acear=acear;
+  a.shiftposfs=(cfg.shiftmode? shiftposfs: nullptr);
+  return a;
+}
+void Engine::ShiftCoefs(double dt,double &coefumagn,double &coeftfs,float &maxdist)const{
+  coefumagn=dt*cfg.shiftcoef*cfg.kernelh;
+  coeftfs=(cfg.simulate2d? 2.0: 3.0)-cfg.shifttfs;
+  maxdist=float(cfg.dp*0.1);
+}
+void Engine::StepSymPre(double dt){
+  if(!forcesok)throw EngineError(DSPH_ERR_STATE,"dsph_step_sympre needs dsph_forces_run first.");
+  if(cfg.tstep!=DSPH_STEP_SYMPLECTIC)throw EngineError(DSPH_ERR_STATE,"The context is not configured for Symplectic.");
+  CUCHECK(cudaEventRecord(ev[11],stm));
+  StepArrays a=MakeStepArrays();
+  ker_step_sympre<<<(np+STEP_THREADS-1)/STEP_THREADS,STEP_THREADS,0,stm>>>(a,dt,dc); launches++;
+  CUCHECK(cudaEventRecord(ev[12],stm));
+  haspre=true; forcesok=false; divok=false; steppending=true;
+}
+void Engine::StepSymCor(double dt){
+  if(!forcesok)throw EngineError(DSPH_ERR_STATE,"dsph_step_symcor needs dsph_forces_run first.");
+  if(!haspre)throw EngineError(DSPH_ERR_STATE,"dsph_step_symcor needs dsph_step_sympre first.");
+  CUCHECK(cudaEventRecord(ev[11],stm));
+  StepArrays a=MakeStepArrays();
+  double cu,ct; float md; ShiftCoefs(dt,cu,ct,md);
+  ker_step_symcor<<<(np+STEP_THREADS-1)/STEP_THREADS,STEP_THREADS,0,stm>>>(a,dt,cu,ct,md,dc); launches++;
+  CUCHECK(cudaEventRecord(ev[12],stm));
+  haspre=false; forcesok=false; divok=false; steppending=true;
+}
+void Engine::StepVerlet(double dt){
+  if(!forcesok)throw EngineError(DSPH_ERR_STATE,"dsph_step_verlet needs dsph_forces_run first.");
+  if(cfg.tstep!=DSPH_STEP_VERLET)throw EngineError(DSPH_ERR_STATE,"The context is not configured for Verlet.");
+  CUCHECK(cudaEventRecord(ev[11],stm));
+  verletstep++;
+  const int euler=(verletstep<cfg.verletsteps? 0: 1);
+  StepArrays a=MakeStepArrays();
+  double cu,ct; float md; ShiftCoefs(dt,cu,ct,md);
+  ker_step_verlet<<<(np+STEP_THREADS-1)/STEP_THREADS,STEP_THREADS,0,stm>>>(a,dt,euler,cu,ct,md,dc); launches++;
+  std::swap(velrhop[cur],velrhopm1[cur]);
+  if(euler)verletstep=0;
+  CUCHECK(cudaEventRecord(ev[12],stm));
+  forcesok=false; divok=false; steppending=true;
+}
+void Engine::FlushStepTimer(){
+  if(steppending){
+    CUCHECK(cudaEventSynchronize(ev[12]));
+    float ms=0; cudaEventElapsedTime(&ms,ev[11],ev[12]); tm.su_computestep+=ms; tm.total+=ms; steppending=false;
+  }
+}
+
+void Engine::Step(double *stepdt,dsph_forceres *res){
+  double dt;
+  if(cfg.tstep==DSPH_STEP_SYMPLECTIC){
+    dt=symplecticdtpre;
+    Forces(DSPH_INTERSTEP_SYMPREDICTOR,nullptr);
+    const double ddt_p=DtVariable(nullptr,nullptr);
+    StepSymPre(dt);
+    CellDivide(true,nullptr); FlushStepTimer();
+    Forces(DSPH_INTERSTEP_SYMCORRECTOR,res);
+    const double ddt_c=DtVariable(nullptr,nullptr);
+    StepSymCor(dt);
+    symplecticdtpre=std::min(ddt_p,ddt_c);
+  }
+  else{
+    Forces(DSPH_INTERSTEP_VERLET,res);
+    dt=DtVariable(nullptr,nullptr);
+    StepVerlet(dt);
+  }
+  CellDivide(true,nullptr); FlushStepTimer();
+  if(stepdt)*stepdt=dt;
+}
+
+void Engine::GetTimers(dsph_timers *t,bool reset){
+  FlushStepTimer();
+  tm.kernel_launches=launches;
+  if(t)*t=tm;
+  if(reset){ memset(&tm,0,sizeof(tm)); launches=0; }
+}
+
+} // namespace dsph

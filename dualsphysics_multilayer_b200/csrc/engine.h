@@ -1,0 +1,87 @@
+// engine.h -- see engine.cu.
+#pragma once
+#include "../../include/dsph_b200.h"
+#include "devtypes.h"
+#include "host/sphconst.h"
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include <stdexcept>
+
+namespace dsph {
+
+struct EngineError : public std::runtime_error {
+  int code;
+  EngineError(int c,const std::string &m):std::runtime_error(m),code(c){}
+};
+
+struct ForceParams; struct StepArrays;
+
+struct HostPinned {
+  DivParams dp;
+  ForceMax fmax;
+  unsigned limitsinit[12];
+  unsigned scratch[8];
+};
+
+class Engine {
+ public:
+  static const int NEVENTS=16;
+  int device;
+  cudaStream_t stm=nullptr;
+  cudaEvent_t ev[NEVENTS]={};
+  HostPinned *hpin=nullptr;
+  dsph_config cfg; SphConst k; DevCtes dc;
+  unsigned cap=0, np=0, npb=0, npbok=0, npbper=0, npfper=0;
+  // particle arrays (double buffered for the reorder; cur = live buffer)
+  int cur=0;
+  unsigned *idp[2]={}, *dcell[2]={}; typecode *code[2]={};
+  double *pos[2]={}; float4 *velrhop[2]={}, *velrhopm1[2]={}, *velrhoppre[2]={}; double *pospre[2]={};
+  float *spstau[2]={};
+  float4 *posp=nullptr, *acear=nullptr, *shiftposfs=nullptr; float *spsgradvel=nullptr;
+  // cell division
+  RadixSortBuffers rs;
+  unsigned *begincell=nullptr, *sufmin=nullptr, *limits=nullptr, *perilist=nullptr, *pericount=nullptr;
+  DivParams *divparams=nullptr; DivParams dp={};
+  unsigned maxnctt=0; int keybits=0;
+  bool boundchanged=true, blimok=false, divok=false, dividefull=false, haspre=false, forcesok=false, steppending=false;
+  unsigned lastcellmin[3]={0,0,0}, lastcellmax[3]={0,0,0};
+  unsigned npfout_last=0; unsigned long long npout_total=0;
+  // forces
+  ForceMax *fmax=nullptr;
+  float viscdtmax=0; double acemax=0, velmax=0; float lastforcems=0;
+  int forcevariant=2;
+  // time stepping
+  double symplecticdtpre=0; int verletstep=0;
+  dsph_timers tm={}; unsigned long long launches=0;
+
+  Engine(int device,const dsph_config &c,unsigned capacity);
+  ~Engine();
+  void Configure(const dsph_config &c);
+  void Allocate(unsigned capacity);
+  void FreeAll();
+  void Upload(unsigned np,unsigned npb,const unsigned *idp,const typecode *code,const double *pos,const float *velrhop);
+  void SetVelrhopM1(const float *h);
+  void SetSpsTau(const float *h);
+  void Download(unsigned first,unsigned count,unsigned *idp,typecode *code,unsigned *dcell,double *pos,float *velrhop);
+  void RunPeriodic();
+  void CellDivide(bool updateperiodic,dsph_divinfo *info);
+  void GetBeginCell(unsigned *h,unsigned capacity);
+  ForceParams MakeForceParams();
+  void Forces(int interstep,dsph_forceres *res);
+  void ForcesDownload(unsigned first,unsigned count,float *ace,float *ar);
+  void Pips(unsigned long long *fr,unsigned long long *fc,unsigned long long *br,unsigned long long *bc);
+  double DtVariable(double *dt1,double *dt2)const;
+  void FillForceRes(dsph_forceres *res)const;
+  StepArrays MakeStepArrays();
+  void ShiftCoefs(double dt,double &coefumagn,double &coeftfs,float &maxdist)const;
+  void StepSymPre(double dt);
+  void StepSymCor(double dt);
+  void StepVerlet(double dt);
+  void Step(double *stepdt,dsph_forceres *res);
+  void FlushStepTimer();
+  void AccumTimers(bool divide);
+  void GetTimers(dsph_timers *t,bool reset);
+};
+
+} // namespace dsph

@@ -1,0 +1,130 @@
+// driver.cpp -- see driver.h.  Host C++ only; every particle operation goes through Engine (CUDA).
+// Loop structure, PART cadence and the values stored in PART headers follow JSphGpuSingle::Run
+// (S/JSphGpuSingle.cpp:808-883), JSph::SavePartData (S/JSph.cpp:2581-2711) and JDsOutputTime::GetNextTime
+// (S/JDsOutputTime.cpp:157-186).
+#include "driver.h"
+#include "casefile.h"
+#include "bi4.h"
+#include "../engine.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdarg>
+#include <cmath>
+#include <vector>
+#include <sys/stat.h>
+
+namespace dsph {
+
+namespace {
+struct Log {
+  FILE *f=nullptr; bool echo=true;
+  void Open(const std::string &file){ f=fopen(file.c_str(),"w"); }
+  void Printf(const char *fmt,...){
+    char tx[2048]; va_list ap; va_start(ap,fmt); vsnprintf(tx,sizeof(tx),fmt,ap); va_end(ap);
+    if(echo){ printf("%s\n",tx); fflush(stdout); }
+    if(f){ fprintf(f,"%s\n",tx); fflush(f); }
+  }
+  ~Log(){ if(f)fclose(f); }
+};
+double NextTime(double t,double tout){
+  unsigned nt=unsigned(t/tout);
+  double next=tout*nt;
+  for(;next<=t;nt++)next=tout*nt;
+  return next;
+}
+}
+
+static void SavePart(Engine &eng,const CaseData &cd,const std::string &dirout,unsigned cpart,double timestep,unsigned step,double runtime,unsigned long long nout,Log &log){
+  const unsigned np=eng.np;
+  std::vector<unsigned> idp(np); std::vector<typecode> code(np); std::vector<double> pos(size_t(np)*3); std::vector<float> vr(size_t(np)*4);
+  eng.Download(0,np,idp.data(),code.data(),nullptr,pos.data(),vr.data());
+  PartHead h; PartData p;
+  const dsph_config &c=cd.cfg;
+  h.casename=cd.name; h.data2d=c.simulate2d!=0; h.data2dposy=c.simulate2dposy;
+  h.casenp=c.casenp; h.casenfixed=c.casenfixed; h.casenmoving=c.casenmoving; h.casenfloat=c.casenfloat; h.casenfluid=c.casenfluid;
+  for(int i=0;i<3;i++){ h.caseposmin[i]=cd.caseposmin[i]; h.caseposmax[i]=cd.caseposmax[i]; h.mapposmin[i]=eng.k.maprealposmin[i]; h.mapposmax[i]=eng.k.maprealposmax[i];
+    h.perixinc[i]=eng.k.perixinc[i]; h.periyinc[i]=eng.k.periyinc[i]; h.perizinc[i]=eng.k.perizinc[i]; }
+  h.perimode=eng.k.periactive;
+  h.dp=c.dp; h.h=c.kernelh; h.b=c.cteb; h.rhop0=c.rhopzero; h.gamma=c.gamma; h.massbound=c.massbound; h.massfluid=c.massfluid;
+  p.cpart=cpart; p.timestep=timestep; p.step=step; p.runtime=runtime; p.nout=unsigned(nout);
+  p.symplecticdtpre=(c.tstep==DSPH_STEP_SYMPLECTIC? eng.symplecticdtpre: 0);
+  for(unsigned q=0;q<np;q++)if((code[q]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL){   // periodic duplicates are not saved (S/JSphGpuSingle.cpp:897)
+    p.idp.push_back(idp[q]);
+    p.pos.push_back(pos[3*size_t(q)]); p.pos.push_back(pos[3*size_t(q)+1]); p.pos.push_back(pos[3*size_t(q)+2]);
+    p.vel.push_back(vr[4*size_t(q)]); p.vel.push_back(vr[4*size_t(q)+1]); p.vel.push_back(vr[4*size_t(q)+2]);
+    p.rhop.push_back(vr[4*size_t(q)+3]);
+  }
+  p.npok=unsigned(p.idp.size());
+  const double sc=eng.k.scell;
+  for(int i=0;i<3;i++){ p.domainmin[i]=eng.k.domposmin[i]+sc*eng.dp.cellmin[i]; p.domainmax[i]=eng.k.domposmin[i]+sc*(eng.dp.cellmax[i]+1); }
+  SavePartFile(dirout+"/"+PartFileName(cpart),h,p,true);
+  log.Printf("Part_%04u  %12.6f  %12u  %10u particles stored",cpart,timestep,step,p.npok);
+}
+
+RunSummary RunCase(const RunOptions &opt){
+  RunSummary sum;
+  mkdir(opt.dirout.c_str(),0755);
+  Log log; log.echo=opt.verbose; log.Open(opt.dirout+"/Run.out");
+  log.Printf("dsph_b200 (B200-native DualSPHysics hot path)  case=%s/%s",opt.dir.c_str(),opt.casename.c_str());
+  CaseData cd; LoadCase(cd,opt.dir,opt.casename);
+  dsph_config &c=cd.cfg;
+  if(opt.timemax>0)c.timemax=opt.timemax;
+  if(opt.timeout>0)c.timeout=opt.timeout;
+  const unsigned np0=cd.np();
+  unsigned capacity=np0+np0/20+1024;
+  if(c.perix||c.periy||c.periz)capacity=unsigned(np0*1.7)+65536;
+  Engine eng(opt.device,c,capacity);
+  if(opt.forcevariant)eng.forcevariant=opt.forcevariant;
+  log.Printf("Particles: np=%u nbound=%u nfluid=%u  dp=%g h=%g cs0=%g  cells(map)=%ux%ux%u",np0,c.casenfixed,c.casenfluid,c.dp,double(c.kernelh),eng.k.cs0,eng.k.mapcells[0],eng.k.mapcells[1],eng.k.mapcells[2]);
+  std::vector<typecode> code(np0); ComputeCodes(cd,np0,cd.idp.data(),code.data());
+  eng.Upload(np0,cd.npb(),cd.idp.data(),code.data(),cd.pos.data(),cd.velrhop.data());
+  dsph_divinfo di; eng.CellDivide(true,&di);
+  double timestep=0; unsigned part=0; unsigned long long nstep=0;
+  const auto t0=std::chrono::steady_clock::now();
+  auto Elapsed=[&]{ return std::chrono::duration<double>(std::chrono::steady_clock::now()-t0).count(); };
+  if(opt.savepart)SavePart(eng,cd,opt.dirout,part,timestep,0,0,0,log);
+  part++;
+  double timepartnext=NextTime(timestep,c.timeout);
+  eng.GetTimers(nullptr,true);
+  const auto tsim0=std::chrono::steady_clock::now();
+  unsigned long long partsteps=0;
+  while(timestep<c.timemax){
+    double dt; dsph_forceres fr;
+    eng.Step(&dt,&fr);
+    partsteps+=eng.np;
+    timestep+=dt; nstep++;
+    const unsigned long long nout=eng.npout_total;
+    const bool partoutstop=(c.partsoutmax_on && double(nout)>double(c.partsoutmax)*double(c.casenfluid)) || !eng.np;
+    if(timestep>=timepartnext || partoutstop){
+      if(opt.savepart)SavePart(eng,cd,opt.dirout,part,timestep,unsigned(nstep),Elapsed(),nout,log);
+      else log.Printf("Part_%04u  %12.6f  %12llu  dt=%.6g  np=%u",part,timestep,nstep,dt,eng.np);
+      part++;
+      timepartnext=NextTime(timestep,c.timeout);
+      if(partoutstop){ log.Printf("Particles OUT limit reached..."); break; }
+    }
+    if(opt.nsteps>0 && nstep>=(unsigned long long)opt.nsteps)break;
+  }
+  const double tsim=std::chrono::duration<double>(std::chrono::steady_clock::now()-tsim0).count();
+  dsph_timers tm; eng.GetTimers(&tm,false);
+  sum.np0=np0; sum.steps=nstep; sum.simtime=timestep; sum.runtime_s=tsim; sum.parts=part; sum.npout=eng.npout_total;
+  sum.mpartsteps_s=(tsim>0? double(partsteps)/tsim/1e6: 0);
+  log.Printf("[Simulation finished]  steps=%llu  TimeStep=%.9g  runtime=%.4f s  %.3f Mparticle-steps/s  excluded=%llu",nstep,timestep,tsim,sum.mpartsteps_s,sum.npout);
+  log.Printf("[GPU Timers] (device ms)");
+  log.Printf("NL-Limits........: %.3f",tm.nl_limits); log.Printf("NL-PreSort.......: %.3f",tm.nl_presort);
+  log.Printf("NL-RadixSort.....: %.3f",tm.nl_radixsort); log.Printf("NL-CellBegin.....: %.3f",tm.nl_cellbegin);
+  log.Printf("NL-SortData......: %.3f",tm.nl_sortdata); log.Printf("NL-OutCheck......: %.3f",tm.nl_outcheck);
+  log.Printf("CF-PreForces.....: %.3f",tm.cf_preforces); log.Printf("CF-Forces........: %.3f",tm.cf_forces);
+  log.Printf("SU-ComputeStep...: %.3f",tm.su_computestep); log.Printf("SU-Periodic......: %.3f",tm.su_periodic);
+  log.Printf("Kernel launches..: %llu",(unsigned long long)tm.kernel_launches);
+  { // Run.csv one-line summary (S/JSph.cpp:2962-3006)
+    FILE *f=fopen((opt.dirout+"/Run.csv").c_str(),"w");
+    if(f){
+      fprintf(f,"#RunName;Np;Steps;TSimul;TimeStep;MPartStepsPerSec;NL-Limits;NL-PreSort;NL-RadixSort;NL-CellBegin;NL-SortData;CF-Forces;SU-ComputeStep\n");
+      fprintf(f,"%s;%u;%llu;%.6f;%.9g;%.4f;%.3f;%.3f;%.3f;%.3f;%.3f;%.3f;%.3f\n",opt.casename.c_str(),np0,nstep,tsim,timestep,sum.mpartsteps_s,tm.nl_limits,tm.nl_presort,tm.nl_radixsort,tm.nl_cellbegin,tm.nl_sortdata,tm.cf_forces,tm.su_computestep);
+      fclose(f);
+    }
+  }
+  return sum;
+}
+
+} // namespace dsph

@@ -1,0 +1,17 @@
+// driver.h -- JSph / JSphGpuSingle::Run work-alike (S/JSphGpuSingle.cpp:808-883): case loading, time loop, PART output.
+#pragma once
+#include <string>
+namespace dsph {
+struct RunOptions {
+  std::string dir=".", casename, dirout="out";
+  int device=0;
+  int nsteps=0;          // >0: stop after nsteps (reference option -nsteps)
+  bool savepart=true;    // false: reference option -sv:none
+  bool verbose=true;
+  double timemax=-1;     // >0 overrides TimeMax (reference option -tmax)
+  double timeout=-1;     // >0 overrides TimeOut (reference option -tout)
+  int forcevariant=0;    // 0: default
+};
+struct RunSummary { unsigned np0=0; unsigned long long steps=0; double simtime=0, runtime_s=0, mpartsteps_s=0; unsigned parts=0; unsigned long long npout=0; };
+RunSummary RunCase(const RunOptions &opt);
+}

@@ -1,0 +1,30 @@
+// dsph_b200 -- command line driver (a subset of the reference's DualSPHysics5.2 options, R/doc/help/DualSPHysics5.2_Help.out):
+//   dsph_b200 <casedir/casename> [dirout] [-gpu[:id]] [-nsteps:N] [-sv:none] [-tmax:T] [-tout:T] [-forcevariant:N]
+#include "../../include/dsph_b200.h"
+#include "host/driver.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+int main(int argc,char **argv){
+  if(argc<2){ printf("usage: dsph_b200 <casedir/casename> [dirout] [-gpu[:id]] [-nsteps:N] [-sv:none] [-tmax:T] [-tout:T]\n"); return 1; }
+  std::string casepath=argv[1], dirout="out"; int device=0,nsteps=0,savepart=1;
+  int narg=0;
+  for(int i=2;i<argc;i++){
+    std::string a=argv[i];
+    if(a[0]!='-'){ if(narg++==0)dirout=a; continue; }
+    if(a.compare(0,5,"-gpu:")==0)device=atoi(a.c_str()+5);
+    else if(a=="-gpu"){}
+    else if(a=="-cpu"){ fprintf(stderr,"dsph_b200: there is no CPU path (use the reference CPU solver).\n"); return 1; }
+    else if(a.compare(0,8,"-nsteps:")==0)nsteps=atoi(a.c_str()+8);
+    else if(a=="-sv:none")savepart=0;
+    else if(a.compare(0,4,"-sv:")==0){}
+    else { fprintf(stderr,"dsph_b200: option ignored: %s\n",a.c_str()); }
+  }
+  std::string dir=".",name=casepath; size_t p=casepath.find_last_of('/');
+  if(p!=std::string::npos){ dir=casepath.substr(0,p); name=casepath.substr(p+1); }
+  const int rc=dsph_run_case(dir.c_str(),name.c_str(),dirout.c_str(),device,nsteps,savepart);
+  if(rc!=DSPH_OK){ fprintf(stderr,"\n*** Exception: %s\nFinished execution (code=1).\n",dsph_last_error()); return 1; }
+  printf("\nFinished execution (code=0).\n");
+  return 0;
+}

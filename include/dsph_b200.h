@@ -160,6 +160,9 @@ int dsph_particles_upload(dsph_ctx *ctx,uint32_t np,uint32_t npb,const uint32_t 
                           const double *pos_xyz,const float *velrhop_xyzw);
 /* optional restart of a mid-state: Verlet VelrhopM1 (NULL -> copy of velrhop, S/JSphGpu.cpp:800) */
 int dsph_particles_set_velrhopm1(dsph_ctx *ctx,const float *velrhopm1_xyzw);
+/* optional restart of a mid-state: SPS stress tensor (xx,xy,xz,yy,yz,zz) per particle, laminar+SPS only
+ * (NULL state = zeros, JSphGpu::InitRunGpu S/JSphGpu.cpp:801) */
+int dsph_particles_set_spstau(dsph_ctx *ctx,const float *tau_6);
 /* downloads in the current (cell-sorted) order; any pointer may be NULL */
 int dsph_particles_download(dsph_ctx *ctx,uint32_t first,uint32_t count,uint32_t *idp,dsph_typecode *code,
                             uint32_t *dcell,double *pos_xyz,float *velrhop_xyzw);
@@ -207,6 +210,8 @@ typedef struct dsph_case {
   uint32_t *idp; double *pos_xyz; float *velrhop_xyzw;   /* owned by the library: dsph_case_free */
   double caseposmin[3], caseposmax[3];
   char name[64];
+  uint32_t nfluidblocks;                       /* fluid mk blocks (= phases in the multiphase fork), in id order */
+  uint32_t fluidblock_count[DSPH_MAXPHASES];
 } dsph_case;
 /* kind: "dambreak" (DB(N)), "periodicbox" (PB(N)), "nn2layer" (NN(N)); np_target approximate */
 int dsph_case_make(dsph_case *out,const char *kind,uint64_t np_target,uint32_t seed);

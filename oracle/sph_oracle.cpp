@@ -1,0 +1,923 @@
+// sph_oracle.cpp -- TEST INFRASTRUCTURE ONLY.  CPU restatement of the reference's per-step particle hot
+// path (JSphCpuSingle / JSphCpu / JCellDivCpuSingle), written from the algorithm, every function citing
+// the reference file:line it follows.  S/ = /root/reference/src/source/.
+//
+// It is the checker for the CUDA path: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline
+// leg may load it.  The product (dualsphysics_multilayer_b200/) never links, imports or calls it.
+// PARITY PIN: the reference ships no golden vectors; this restatement is pinned against
+// dumps of the reference's own JSphCpuSingle produced by oracle/ref_harness.cpp (tests/golden/*.npz,
+// generator tests/golden/make_golden.py) -- see tests/test_oracle_vs_reference.py.
+//
+// The exported C functions mirror include/dsph_b200.h one to one (orc_* instead of dsph_*), so parity tests
+// drive both sides with the same calls.  Arithmetic keeps the reference's float/double rounding points.
+#include "../include/dsph_b200.h"
+#include <cmath>
+#include <cfloat>
+#include <climits>
+#include <cstring>
+#include <cstdio>
+#include <vector>
+#include <string>
+#include <algorithm>
+#include <stdexcept>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+typedef uint16_t typecode;
+struct f3{ float x,y,z; };
+struct f4{ float x,y,z,w; };
+struct d3{ double x,y,z; };
+struct sym3{ float xx,xy,xz,yy,yz,zz; };
+
+// ---- typecode helpers: S/DualSphDef.h:164-226
+inline typecode CodeSpecial(typecode c){ return c&DSPH_CODE_MASKSPECIAL; }
+inline typecode CodeType(typecode c){ return c&DSPH_CODE_MASKTYPE; }
+inline bool CodeIsNormal(typecode c){ return CodeSpecial(c)==DSPH_CODE_NORMAL; }
+inline bool CodeIsPeriodic(typecode c){ return CodeSpecial(c)==DSPH_CODE_PERIODIC; }
+inline bool CodeIsFluid(typecode c){ return CodeType(c)==DSPH_CODE_TYPE_FLUID; }
+inline bool CodeIsFixed(typecode c){ return CodeType(c)==DSPH_CODE_TYPE_FIXED; }
+inline bool CodeIsOutRhop(typecode c){ return CodeSpecial(c)==DSPH_CODE_OUTRHOP; }
+inline typecode CodeSetNormal(typecode c){ return c&(~DSPH_CODE_MASKSPECIAL); }
+
+// ---- dcell bit layout: S/JDsDcellDef.h:33-44
+inline unsigned DcBits(unsigned v,unsigned minbits){ unsigned n=minbits; for(;v>>n;n++); return n; }
+inline unsigned DcCode(unsigned sx,unsigned sy,unsigned sz){ return ((sx+1)<<25)|(sy<<20)|(sz<<15)|((sy+sz)<<10)|((sx+1+sz)<<5)|(sx+1+sy); }
+inline unsigned DcCellx(unsigned dcc,unsigned cel){ return cel>>((dcc>>10)&31); }
+inline unsigned DcCelly(unsigned dcc,unsigned cel){ return (cel<<(dcc>>25))>>((dcc>>5)&31); }
+inline unsigned DcCellz(unsigned dcc,unsigned cel){ return (cel<<(dcc&31))>>(dcc&31); }
+inline unsigned DcCell(unsigned dcc,unsigned cx,unsigned cy,unsigned cz){ return (cx<<((dcc>>10)&31))|(cy<<((dcc>>15)&31))|cz; }
+// JDsDcell::CalcCellDistribution/CalcCellCode: S/JDsDcell.cpp:39-68
+unsigned CalcCellCode(unsigned nx,unsigned ny,unsigned nz){
+  unsigned sx=DcBits(nx,2),sy=DcBits(ny,2),sz=DcBits(nz,2);
+  if(sx+sy+sz>31)return 0;
+  unsigned rest=31-(sx+sy+sz);
+  while(rest){ if(rest){ sx++; rest--; } if(rest){ sy++; rest--; } if(rest){ sz++; rest--; } }
+  return DcCode(sx,sy,sz);
+}
+
+struct Oracle {
+  dsph_config cfg;
+  // ---- derived constants: JSph::ConfigConstants1/2 S/JSph.cpp:1392-1457
+  float KernelH,KernelSize,KernelSize2,Eta2,Awen,Bwen;
+  float CubA1,CubA2,CubAa,CubA24,CubC1,CubD1,CubC2,CubOdWdeltap;
+  float CteB,Gamma,RhopZero,MassFluid,MassBound,Visco,ViscoBoundFactor;
+  float DDTkh,DDTgz,SpsSmag,SpsBlin;
+  f3 Gravity;
+  double Cs0,Dp,CFLnumber,DtIni,DtMin;
+  float RhopOutMin,RhopOutMax;
+  bool Simulate2D,DDTArray;
+  int TKernel,TStep,TVisco,TDensity,ShiftMode,VerletSteps;
+  float ShiftCoef,ShiftTFS;
+  // ---- domain: JSph::LoadCaseParticles S/JSph.cpp:2056-2080, ConfigCellDivision :1772-1779, SelecDomain :1794-1829
+  d3 MapRealPosMin,MapRealPosMax,MapRealSize,Map_PosMin,Map_PosMax,Map_Size;
+  d3 DomPosMin,DomPosMax,DomRealPosMin,DomRealPosMax;
+  d3 PeriXinc,PeriYinc,PeriZinc;
+  bool PeriX,PeriY,PeriZ; int PeriActive;
+  unsigned MapCells[3],DomCells[3],DomCellCode;
+  int ScellDiv; float Scell,MovLimit;
+  // ---- particle state (JSphCpu members S/JSphCpu.h:95-160)
+  unsigned Np=0,Npb=0,NpbOk=0,NpbPer=0,NpfPer=0;
+  std::vector<unsigned> Idp,Dcell; std::vector<typecode> Code;
+  std::vector<d3> Pos,PosPre; std::vector<f4> Velrhop,VelrhopM1,VelrhopPre;
+  bool HasPre=false;
+  std::vector<f3> Ace; std::vector<float> Ar,Delta,Press; std::vector<f4> ShiftPosfs;
+  std::vector<sym3> SpsTau,SpsGradvel;
+  double VelMax=0,AceMax=0; float ViscDtMax=0;
+  double SymplecticDtPre=0; int VerletStep=0;
+  bool BoundChanged=true;
+  // ---- cell division (JCellDivCpu members S/JCellDivCpu.h:44-150)
+  std::vector<unsigned> CellPart,SortPart,PartsInCell,BeginCell;
+  unsigned Ncx=0,Ncy=0,Ncz=0,Nsheet=0,Nct=0,Nctt=0;
+  unsigned BoxBoundIgnore=0,BoxFluid=0,BoxBoundOut=0,BoxFluidOut=0,BoxBoundOutIgnore=0,BoxFluidOutIgnore=0;
+  unsigned CellDomainMin[3]={0,0,0},CellDomainMax[3]={0,0,0};
+  bool BoundLimitOk=false,BoundDivideOk=false,DivideFull=false;
+  unsigned BoundLimitCellMin[3],BoundLimitCellMax[3],BoundDivideCellMin[3],BoundDivideCellMax[3];
+  unsigned Npb1=0,Npf1=0,Npb2=0,Npf2=0,Nptot=0,NpbOut=0,NpfOut=0,NpbOutIgnore=0,NpfOutIgnore=0,NpFinal=0,NpbFinal=0,NpbIgnore=0;
+  unsigned long long PipsFluidReal=0,PipsFluidChecked=0,PipsBoundReal=0,PipsBoundChecked=0;
+  std::string Error;
+
+  void Resize(unsigned n){
+    Idp.resize(n); Dcell.resize(n); Code.resize(n); Pos.resize(n); Velrhop.resize(n);
+    if(TStep==DSPH_STEP_VERLET)VelrhopM1.resize(n);
+    if(TStep==DSPH_STEP_SYMPLECTIC){ PosPre.resize(n); VelrhopPre.resize(n); }
+    if(TVisco==DSPH_VISCO_LAMINARSPS)SpsTau.resize(n);
+  }
+
+  void Configure(const dsph_config &c){
+    cfg=c;
+    TKernel=c.tkernel; TStep=c.tstep; TVisco=c.tvisco; TDensity=c.tdensity; ShiftMode=c.shiftmode; VerletSteps=c.verletsteps;
+    ShiftCoef=c.shiftcoef; ShiftTFS=c.shifttfs;
+    Simulate2D=c.simulate2d!=0;
+    KernelH=c.kernelh; CteB=c.cteb; Gamma=c.gamma; RhopZero=c.rhopzero; MassFluid=c.massfluid; MassBound=c.massbound;
+    Gravity={c.gravity[0],c.gravity[1],c.gravity[2]};
+    Visco=c.visco; ViscoBoundFactor=c.viscoboundfactor; Dp=c.dp; CFLnumber=c.cflnumber;
+    RhopOutMin=c.rhopoutmin; RhopOutMax=c.rhopoutmax;
+    if(!(RhopOutMin<RhopOutMax)){ RhopOutMin=-FLT_MAX; RhopOutMax=FLT_MAX; }   // S/JSph.cpp:862-863
+    // ConfigConstants1 (S/JSph.cpp:1392-1431)
+    const double h=KernelH, kh=h*2.0;
+    KernelSize=float(kh); KernelSize2=KernelSize*KernelSize;
+    if(Simulate2D){ Awen=float(0.557/(h*h)); Bwen=float(-2.7852/(h*h*h)); }          // S/FunSphKernel.h:199-210
+    else          { Awen=float(0.41778/(h*h*h)); Bwen=float(-2.08891/(h*h*h*h)); }
+    {                                                                                // S/FunSphKernel.h:50-80
+      const double PI=3.14159265358979323846;
+      const double a1=(Simulate2D? 10./(PI*7.): 1./PI);
+      const double a2=(Simulate2D? a1/(h*h): a1/(h*h*h));
+      const double aa=(Simulate2D? a1/(h*h*h): a1/(h*h*h*h));
+      const double deltap=1./1.5;
+      const double wdeltap=a2*(1.-1.5*deltap*deltap+0.75*deltap*deltap*deltap);
+      CubOdWdeltap=float(1./wdeltap); CubA1=float(a1); CubA2=float(a2); CubAa=float(aa); CubA24=float(0.25*a2);
+      CubC1=float(-3.*aa); CubD1=float(9.*aa/4.); CubC2=float(-3.*aa/4.);
+    }
+    Cs0=sqrt(double(Gamma)*double(CteB)/double(RhopZero));
+    Eta2=float((h*0.1)*(h*0.1));
+    // ConfigConstants2 (S/JSph.cpp:1437-1457)
+    SpsSmag=SpsBlin=0;
+    if(TVisco==DSPH_VISCO_LAMINARSPS){
+      const double dp_sps=(Simulate2D? sqrt(Dp*Dp*2.)/2.: sqrt(Dp*Dp*3.)/3.);
+      SpsSmag=float(pow((0.12*dp_sps),2)); SpsBlin=float((2./3.)*0.0066*dp_sps*dp_sps);
+    }
+    const float ddtvalue=(TDensity==DSPH_DDT_NONE? 0.f: c.ddtvalue);            // S/JSph.cpp:811
+    DDTkh=KernelSize*ddtvalue;
+    DDTgz=float(double(RhopZero)*double(fabsf(Gravity.z))/double(CteB));
+    DDTArray=(TDensity!=DSPH_DDT_NONE);                                         // Cpu: S/JSph.cpp:814
+    DtIni=(c.dtini>0? c.dtini: double(KernelH)/Cs0);
+    DtMin=(c.dtmin>0? c.dtmin: (double(KernelH)/Cs0)*double(c.coefdtmin));
+    // LoadCaseParticles (S/JSph.cpp:2056-2080)
+    MapRealPosMin={c.maprealposmin[0],c.maprealposmin[1],c.maprealposmin[2]};
+    MapRealPosMax={c.maprealposmax[0],c.maprealposmax[1],c.maprealposmax[2]};
+    MapRealSize={MapRealPosMax.x-MapRealPosMin.x,MapRealPosMax.y-MapRealPosMin.y,MapRealPosMax.z-MapRealPosMin.z};
+    PeriX=c.perix!=0; PeriY=c.periy!=0; PeriZ=c.periz!=0; PeriActive=(PeriX?1:0)|(PeriY?2:0)|(PeriZ?4:0);
+    PeriXinc={c.perixinc[0],c.perixinc[1],c.perixinc[2]}; PeriYinc={c.periyinc[0],c.periyinc[1],c.periyinc[2]}; PeriZinc={c.perizinc[0],c.perizinc[1],c.perizinc[2]};
+    if(PeriX)PeriXinc.x=-MapRealSize.x;
+    if(PeriY)PeriYinc.y=-MapRealSize.y;
+    if(PeriZ)PeriZinc.z=-MapRealSize.z;
+    Map_PosMin=MapRealPosMin; Map_PosMax=MapRealPosMax;
+    if(PeriX){ Map_PosMin.x=Map_PosMin.x-KernelSize; Map_PosMax.x=Map_PosMax.x+KernelSize; }
+    if(PeriY){ Map_PosMin.y=Map_PosMin.y-KernelSize; Map_PosMax.y=Map_PosMax.y+KernelSize; }
+    if(PeriZ){ Map_PosMin.z=Map_PosMin.z-KernelSize; Map_PosMax.z=Map_PosMax.z+KernelSize; }
+    Map_Size={Map_PosMax.x-Map_PosMin.x,Map_PosMax.y-Map_PosMin.y,Map_PosMax.z-Map_PosMin.z};
+    // ConfigCellDivision (S/JSph.cpp:1772-1779)
+    ScellDiv=(c.cellmode==DSPH_CELLMODE_FULL? 1: 2);
+    Scell=KernelSize/ScellDiv; MovLimit=Scell*0.9f;
+    MapCells[0]=unsigned(ceil(Map_Size.x/Scell)); MapCells[1]=unsigned(ceil(Map_Size.y/Scell)); MapCells[2]=unsigned(ceil(Map_Size.z/Scell));
+    // SelecDomain(0,Map_Cells) (S/JSph.cpp:1794-1829)
+    for(int i=0;i<3;i++)DomCells[i]=MapCells[i];
+    DomPosMin=Map_PosMin;
+    DomPosMax.x=Map_PosMin.x+(MapCells[0]*Scell); DomPosMax.y=Map_PosMin.y+(MapCells[1]*Scell); DomPosMax.z=Map_PosMin.z+(MapCells[2]*Scell);
+    if(DomPosMax.x>Map_PosMax.x)DomPosMax.x=Map_PosMax.x;
+    if(DomPosMax.y>Map_PosMax.y)DomPosMax.y=Map_PosMax.y;
+    if(DomPosMax.z>Map_PosMax.z)DomPosMax.z=Map_PosMax.z;
+    DomRealPosMin=DomPosMin; DomRealPosMax=DomPosMax;
+    if(DomRealPosMax.x>MapRealPosMax.x)DomRealPosMax.x=MapRealPosMax.x;
+    if(DomRealPosMax.y>MapRealPosMax.y)DomRealPosMax.y=MapRealPosMax.y;
+    if(DomRealPosMax.z>MapRealPosMax.z)DomRealPosMax.z=MapRealPosMax.z;
+    if(DomRealPosMin.x<MapRealPosMin.x)DomRealPosMin.x=MapRealPosMin.x;
+    if(DomRealPosMin.y<MapRealPosMin.y)DomRealPosMin.y=MapRealPosMin.y;
+    if(DomRealPosMin.z<MapRealPosMin.z)DomRealPosMin.z=MapRealPosMin.z;
+    DomCellCode=CalcCellCode(DomCells[0]+1,DomCells[1]+1,DomCells[2]+1);
+    if(!DomCellCode)throw std::runtime_error("Failed to select a valid CellCode.");
+    SymplecticDtPre=DtIni;                                                        // JSph::InitRun S/JSph.cpp:2090
+    VerletStep=0;
+  }
+
+  // ---- JSph::LoadDcellParticles S/JSph.cpp:1690-1711
+  void LoadDcellParticles(){
+    for(unsigned p=0;p<Np;p++){
+      if(CodeSpecial(Code[p])<DSPH_CODE_OUTIGNORE){
+        const d3 ps=Pos[p];
+        if(CodeIsPeriodic(Code[p])){   // restart of a dumped state that still holds periodic duplicates: PeriodicDuplicatePos rule
+          unsigned cx=unsigned((ps.x-DomPosMin.x)/Scell), cy=unsigned((ps.y-DomPosMin.y)/Scell), cz=unsigned((ps.z-DomPosMin.z)/Scell);
+          cx=(cx<=DomCells[0]? cx: DomCells[0]); cy=(cy<=DomCells[1]? cy: DomCells[1]); cz=(cz<=DomCells[2]? cz: DomCells[2]);
+          Dcell[p]=DcCell(DomCellCode,cx,cy,cz);
+          continue;
+        }
+        const bool in=(ps.x>=DomRealPosMin.x && ps.y>=DomRealPosMin.y && ps.z>=DomRealPosMin.z && ps.x<DomRealPosMax.x && ps.y<DomRealPosMax.y && ps.z<DomRealPosMax.z);
+        if(!in)throw std::runtime_error("Found new particles out.");
+        const double dx=ps.x-DomPosMin.x, dy=ps.y-DomPosMin.y, dz=ps.z-DomPosMin.z;
+        const unsigned cx=unsigned(dx/Scell), cy=unsigned(dy/Scell), cz=unsigned(dz/Scell);
+        Dcell[p]=DcCell(DomCellCode,cx,cy,cz);
+      }
+      else Dcell[p]=0xFFFFFFFFu;
+    }
+  }
+
+  // ---- JSphCpuSingle::RunPeriodic + PeriodicMakeList + PeriodicDuplicate* S/JSphCpuSingle.cpp:182-431
+  void PeriodicDuplicate(unsigned pnew,unsigned rp,const d3 &perinc){
+    const unsigned pcopy=(rp&0x7FFFFFFFu); const bool inverse=(rp>=0x80000000u);
+    d3 ps=Pos[pcopy];
+    ps.x+=(inverse? -perinc.x: perinc.x); ps.y+=(inverse? -perinc.y: perinc.y); ps.z+=(inverse? -perinc.z: perinc.z);
+    unsigned cx=unsigned((ps.x-DomPosMin.x)/Scell), cy=unsigned((ps.y-DomPosMin.y)/Scell), cz=unsigned((ps.z-DomPosMin.z)/Scell);
+    cx=(cx<=DomCells[0]? cx: DomCells[0]); cy=(cy<=DomCells[1]? cy: DomCells[1]); cz=(cz<=DomCells[2]? cz: DomCells[2]);
+    Pos[pnew]=ps; Dcell[pnew]=DcCell(DomCellCode,cx,cy,cz);
+    Idp[pnew]=Idp[pcopy]; Code[pnew]=typecode(CodeSetNormal(Code[pcopy])|DSPH_CODE_PERIODIC);
+    Velrhop[pnew]=Velrhop[pcopy];
+    if(TStep==DSPH_STEP_VERLET)VelrhopM1[pnew]=VelrhopM1[pcopy];
+    if(TStep==DSPH_STEP_SYMPLECTIC && HasPre){ PosPre[pnew]=PosPre[pcopy]; VelrhopPre[pnew]=VelrhopPre[pcopy]; }
+    if(TVisco==DSPH_VISCO_LAMINARSPS)SpsTau[pnew]=SpsTau[pcopy];
+  }
+  void RunPeriodic(){
+    for(unsigned p=0;p<Np;p++){ const typecode rc=Code[p]; if(CodeIsPeriodic(rc))Code[p]=typecode(CodeSetNormal(rc)|DSPH_CODE_OUTIGNORE); }
+    const unsigned npb0=Npb, npf0=Np-Npb;
+    NpbPer=NpfPer=0; BoundChanged=true;
+    for(unsigned ctype=0;ctype<2;ctype++){
+      const unsigned pini=(ctype? npb0: 0), num=(ctype? npf0: npb0);
+      for(unsigned cper=0;cper<3;cper++)if((cper==0&&PeriX)||(cper==1&&PeriY)||(cper==2&&PeriZ)){
+        const d3 perinc=(cper==0? PeriXinc: (cper==1? PeriYinc: PeriZinc));
+        for(unsigned cblock=0;cblock<2;cblock++){
+          const unsigned nper=(ctype? NpfPer: NpbPer);
+          const unsigned pini2=(cblock? pini: Np-nper), num2=(cblock? num: nper);
+          if(!num2)continue;
+          std::vector<unsigned> listp;
+          for(unsigned p=0;p<num2;p++){
+            const unsigned p2=p+pini2;
+            if(CodeSpecial(Code[p2])<=DSPH_CODE_PERIODIC){
+              const d3 ps=Pos[p2];
+              d3 q={ps.x+perinc.x,ps.y+perinc.y,ps.z+perinc.z};
+              if(Map_PosMin.x<=q.x && Map_PosMin.y<=q.y && Map_PosMin.z<=q.z && q.x<Map_PosMax.x && q.y<Map_PosMax.y && q.z<Map_PosMax.z)listp.push_back(p2);
+              q={ps.x-perinc.x,ps.y-perinc.y,ps.z-perinc.z};
+              if(Map_PosMin.x<=q.x && Map_PosMin.y<=q.y && Map_PosMin.z<=q.z && q.x<Map_PosMax.x && q.y<Map_PosMax.y && q.z<Map_PosMax.z)listp.push_back(p2|0x80000000u);
+            }
+          }
+          const unsigned count=unsigned(listp.size());
+          if(Idp.size()<size_t(Np)+count)Resize(Np+count+(Np+count)/20+128);
+          for(unsigned p=0;p<count;p++)PeriodicDuplicate(Np+p,listp[p],perinc);
+          Np+=count;
+          if(!ctype)NpbPer+=count; else NpfPer+=count;
+        }
+      }
+    }
+  }
+
+  // ---- JCellDivCpu::LimitsCellBound/Fluid + CalcCellDomainBound/Fluid S/JCellDivCpu.cpp:255-350
+  void LimitsCell(unsigned n,unsigned pini,unsigned cmin[3],unsigned cmax[3])const{
+    cmin[0]=cmin[1]=cmin[2]=UINT_MAX; cmax[0]=cmax[1]=cmax[2]=0;
+    for(unsigned p=pini;p<pini+n;p++){
+      const unsigned rcell=Dcell[p];
+      const unsigned cx=DcCellx(DomCellCode,rcell),cy=DcCelly(DomCellCode,rcell),cz=DcCellz(DomCellCode,rcell);
+      if(CodeSpecial(Code[p])<DSPH_CODE_OUTIGNORE){
+        if(cmin[0]>cx)cmin[0]=cx; if(cmin[1]>cy)cmin[1]=cy; if(cmin[2]>cz)cmin[2]=cz;
+        if(cmax[0]<cx)cmax[0]=cx; if(cmax[1]<cy)cmax[1]=cy; if(cmax[2]<cz)cmax[2]=cz;
+      }
+    }
+  }
+  void CalcCellDomainRange(unsigned n,unsigned pini,unsigned n2,unsigned pini2,unsigned cellmin[3],unsigned cellmax[3])const{
+    unsigned cmin[3],cmax[3];
+    LimitsCell(n,pini,cmin,cmax);
+    const bool empty=(cmin[0]>cmax[0]);
+    for(int i=0;i<3;i++){ cellmin[i]=(empty? DomCells[i]: cmin[i]); cellmax[i]=(empty? 0: cmax[i]); }
+    if(n2){
+      LimitsCell(n2,pini2,cmin,cmax);
+      const bool empty2=(cmin[0]>cmax[0]);
+      for(int i=0;i<3;i++){
+        const unsigned a=(empty2? DomCells[i]: cmin[i]);
+        // NOTE (reference quirk, S/JCellDivCpu.cpp:295-296): cmin is replaced before cmax is tested, so cmax is only
+        // zeroed when the replaced cmin.x still exceeds cmax.x.
+        cmin[i]=a;
+      }
+      const bool empty3=(cmin[0]>cmax[0]);
+      for(int i=0;i<3;i++){
+        const unsigned b=(empty3? 0: cmax[i]);
+        cellmin[i]=std::min(cellmin[i],cmin[i]); cellmax[i]=std::max(cellmax[i],b);
+      }
+    }
+  }
+  // ---- JCellDivCpuSingle::CalcCellDomain + MergeMapCellBoundFluid S/JCellDivCpuSingle.cpp:47-100
+  void CalcCellDomain(){
+    unsigned celbmin[3],celbmax[3];
+    if(!BoundLimitOk){
+      CalcCellDomainRange(Npb1,0,Npb2,Npb1+Npf1,celbmin,celbmax);
+      BoundLimitOk=true; for(int i=0;i<3;i++){ BoundLimitCellMin[i]=celbmin[i]; BoundLimitCellMax[i]=celbmax[i]; }
+    }
+    else for(int i=0;i<3;i++){ celbmin[i]=BoundLimitCellMin[i]; celbmax[i]=BoundLimitCellMax[i]; }
+    unsigned celfmin[3],celfmax[3];
+    CalcCellDomainRange(Npf1,Npb1,Npf2,Npb1+Npf1+Npb2,celfmin,celfmax);
+    const unsigned sd=unsigned(ScellDiv);
+    for(int i=0;i<3;i++){
+      CellDomainMin[i]=std::max(std::min(celbmin[i],celfmin[i]),(celfmin[i]>=sd? celfmin[i]-sd: 0u));
+      CellDomainMax[i]=std::min(std::max(celbmax[i],celfmax[i]),celfmax[i]+sd);
+      if(CellDomainMax[i]>=DomCells[i])CellDomainMax[i]=DomCells[i]-1;
+    }
+    if(CellDomainMin[0]>CellDomainMax[0]||CellDomainMin[1]>CellDomainMax[1]||CellDomainMin[2]>CellDomainMax[2])
+      for(int i=0;i<3;i++)CellDomainMin[i]=CellDomainMax[i]=0;
+  }
+  // ---- JCellDivCpuSingle::PrepareNct S/JCellDivCpuSingle.cpp:109-125
+  void PrepareNct(){
+    Ncx=CellDomainMax[0]-CellDomainMin[0]+1; Ncy=CellDomainMax[1]-CellDomainMin[1]+1; Ncz=CellDomainMax[2]-CellDomainMin[2]+1;
+    Nsheet=Ncx*Ncy; Nct=Nsheet*Ncz; Nctt=Nct*2+6;   // SizeBeginCell(nct)=nct*2+5+1, S/JCellDivCpu.h:141
+    BoxBoundIgnore=Nct; BoxFluid=BoxBoundIgnore+1; BoxBoundOut=BoxFluid+Nct; BoxFluidOut=BoxBoundOut+1;
+    BoxBoundOutIgnore=BoxFluidOut+1; BoxFluidOutIgnore=BoxBoundOutIgnore+1;
+  }
+  // ---- PreSortFull/PreSortFluid/MakeSortFull/MakeSortFluid S/JCellDivCpuSingle.cpp:134-234
+  unsigned BoxOf(unsigned p,bool fluidonly)const{
+    const unsigned rcell=Dcell[p];
+    const unsigned cx=DcCellx(DomCellCode,rcell)-CellDomainMin[0], cy=DcCelly(DomCellCode,rcell)-CellDomainMin[1], cz=DcCellz(DomCellCode,rcell)-CellDomainMin[2];
+    const unsigned cellsort=cx+cy*Ncx+cz*Nsheet;
+    const typecode rcode=Code[p], codetype=CodeType(rcode), codeout=CodeSpecial(rcode);
+    if(!fluidonly && codetype<DSPH_CODE_TYPE_FLOATING)
+      return (codeout<DSPH_CODE_OUTIGNORE? ((cx<Ncx && cy<Ncy && cz<Ncz)? cellsort: BoxBoundIgnore): (codeout==DSPH_CODE_OUTIGNORE? BoxBoundOutIgnore: BoxBoundOut));
+    return (codeout<=DSPH_CODE_OUTIGNORE? (codeout<DSPH_CODE_OUTIGNORE? BoxFluid+cellsort: BoxFluidOutIgnore): (codetype==DSPH_CODE_TYPE_FLOATING? BoxBoundOut: BoxFluidOut));
+  }
+  void PreSort(){
+    if(DivideFull){
+      std::fill(PartsInCell.begin(),PartsInCell.begin()+(Nctt-1),0u);
+      for(unsigned p=0;p<Nptot;p++){ const unsigned box=BoxOf(p,false); CellPart[p]=box; PartsInCell[box]++; }
+      BeginCell[0]=0;
+      for(unsigned box=0;box<Nctt-1;box++)BeginCell[box+1]=BeginCell[box]+PartsInCell[box];
+      std::fill(PartsInCell.begin(),PartsInCell.begin()+(Nctt-1),0u);
+      for(unsigned p=0;p<Nptot;p++){ const unsigned box=CellPart[p]; SortPart[BeginCell[box]+PartsInCell[box]]=p; PartsInCell[box]++; }
+    }
+    else{
+      std::fill(PartsInCell.begin()+BoxFluid,PartsInCell.begin()+(Nctt-1),0u);
+      for(unsigned p=Npb1;p<Npb1+Npf1;p++){ const unsigned box=BoxOf(p,true); CellPart[p]=box; PartsInCell[box]++; }
+      for(unsigned box=BoxFluid;box<Nctt-1;box++)BeginCell[box+1]=BeginCell[box]+PartsInCell[box];
+      std::fill(PartsInCell.begin()+BoxFluid,PartsInCell.begin()+(Nctt-1),0u);
+      for(unsigned p=Npb1;p<Npb1+Npf1;p++){ const unsigned box=CellPart[p]; SortPart[BeginCell[box]+PartsInCell[box]]=p; PartsInCell[box]++; }
+    }
+  }
+  template<class T> void SortArray(std::vector<T> &v)const{                         // S/JCellDivCpu.cpp:352-450
+    const unsigned ini=(DivideFull? 0: NpbFinal);
+    std::vector<T> tmp(Nptot-ini);
+    for(unsigned p=ini;p<Nptot;p++)tmp[p-ini]=v[SortPart[p]];
+    std::copy(tmp.begin(),tmp.end(),v.begin()+ini);
+  }
+  unsigned CellSize(unsigned box)const{ return BeginCell[box+1]-BeginCell[box]; }
+  // ---- JCellDivCpuSingle::Divide S/JCellDivCpuSingle.cpp:259-345
+  void Divide(bool boundchanged){
+    DivideFull=false;
+    Npb1=Npb; Npf1=Np-Npb-NpbPer-NpfPer; Npb2=NpbPer; Npf2=NpfPer;
+    Nptot=Npb1+Npf1+Npb2+Npf2;
+    NpbOut=NpfOut=NpbOutIgnore=NpfOutIgnore=0; NpFinal=NpbFinal=0; NpbIgnore=0;
+    if(CellPart.size()<Nptot){ CellPart.resize(Nptot+Nptot/20+128); SortPart.resize(CellPart.size()); BoundDivideOk=false; } // CheckMemoryNp -> AllocMemoryNp resets BoundDivideOk
+    if(boundchanged || PeriActive){ BoundLimitOk=BoundDivideOk=false; for(int i=0;i<3;i++)BoundLimitCellMin[i]=BoundLimitCellMax[i]=BoundDivideCellMin[i]=BoundDivideCellMax[i]=0; }
+    CalcCellDomain();
+    PrepareNct();
+    if(BeginCell.size()<Nctt){ BeginCell.assign(Nctt,0u); PartsInCell.assign(Nctt,0u); BoundDivideOk=false; }   // CheckMemoryNct
+    bool same=true; for(int i=0;i<3;i++)if(BoundDivideCellMin[i]!=CellDomainMin[i]||BoundDivideCellMax[i]!=CellDomainMax[i])same=false;
+    if(!BoundDivideOk || !same){
+      DivideFull=true; BoundDivideOk=true;
+      for(int i=0;i<3;i++){ BoundDivideCellMin[i]=CellDomainMin[i]; BoundDivideCellMax[i]=CellDomainMax[i]; }
+    }
+    PreSort();
+    // (the reference also reorders CellPart here, S/JCellDivCpuSingle.cpp:256; it is not used afterwards on the CPU)
+    NpbIgnore=CellSize(BoxBoundIgnore); NpbOut=CellSize(BoxBoundOut); NpfOut=CellSize(BoxFluidOut);
+    NpbOutIgnore=CellSize(BoxBoundOutIgnore); NpfOutIgnore=CellSize(BoxFluidOutIgnore);
+    NpFinal=Nptot-NpbOut-NpfOut-NpbOutIgnore-NpfOutIgnore;
+    NpbFinal=Npb1+Npb2-NpbOutIgnore;
+    if(NpbOut!=0 && DivideFull)NpbFinal=UINT_MAX;
+  }
+  // ---- JSphCpuSingle::RunCellDivide S/JSphCpuSingle.cpp:437-500
+  void RunCellDivide(bool updateperiodic){
+    if(updateperiodic && PeriActive)RunPeriodic();
+    Divide(BoundChanged);
+    SortArray(Idp); SortArray(Code); SortArray(Dcell); SortArray(Pos); SortArray(Velrhop);
+    if(TStep==DSPH_STEP_VERLET)SortArray(VelrhopM1);
+    else if(TStep==DSPH_STEP_SYMPLECTIC && HasPre){ SortArray(PosPre); SortArray(VelrhopPre); }
+    if(TVisco==DSPH_VISCO_LAMINARSPS)SortArray(SpsTau);
+    Np=NpFinal; Npb=NpbFinal; NpbOk=Npb-NpbIgnore;
+    if(NpbOut)throw std::runtime_error("Boundary particles out of the domain (AbortBoundOut).");
+    BoundChanged=false;
+  }
+
+  // ---- kernels: S/FunSphKernel.h:86-151 (cubic), :212-222 (wendland)
+  inline float FacWendland(float rr2)const{
+    const float rad=sqrtf(rr2); const float qq=rad/KernelH; const float wqq1=1.f-0.5f*qq;
+    return Bwen*qq*wqq1*wqq1*wqq1/rad;
+  }
+  inline float WabCubic(float rr2)const{
+    const float rad=sqrtf(rr2); const float qq=rad/KernelH;
+    if(rad>KernelH){ const float wqq1=2.0f-qq; const float wqq2=wqq1*wqq1; return CubA24*(wqq2*wqq1); }
+    const float wqq2=qq*qq; return CubA2*(1.0f+(0.75f*qq-1.5f)*wqq2);
+  }
+  inline float FacCubic(float rr2)const{
+    const float rad=sqrtf(rr2); const float qq=rad/KernelH;
+    if(rad>KernelH){ const float wqq1=2.0f-qq; const float wqq2=wqq1*wqq1; return CubC2*wqq2/rad; }
+    const float wqq2=qq*qq; return (CubC1*qq+CubD1*wqq2)/rad;
+  }
+  inline float TensilCubic(float rr2,float rhopp1,float pressp1,float rhopp2,float pressp2)const{
+    const float wab=WabCubic(rr2); float fab=wab*CubOdWdeltap; fab*=fab; fab*=fab;
+    const float t1=(pressp1/(rhopp1*rhopp1))*(pressp1>0? 0.01f: -0.2f);
+    const float t2=(pressp2/(rhopp2*rhopp2))*(pressp2>0? 0.01f: -0.2f);
+    return fab*(t1+t2);
+  }
+  inline float Fac(float rr2)const{ return TKernel==DSPH_KERNEL_WENDLAND? FacWendland(rr2): FacCubic(rr2); }
+
+  // ---- neighbour search: nsearch::Init / ParticleRange S/JCellSearch_inline.h:33-83
+  struct NgSearch{ int cellinit,cxini,cxfin,yini,yfin,zini,zfin; };
+  inline NgSearch NgInit(unsigned rcell,bool boundp2)const{
+    const int cx=int(DcCellx(DomCellCode,rcell))-int(CellDomainMin[0]);
+    const int cy=int(DcCelly(DomCellCode,rcell))-int(CellDomainMin[1]);
+    const int cz=int(DcCellz(DomCellCode,rcell))-int(CellDomainMin[2]);
+    const int ncx=int(Ncx),ncy=int(Ncy),ncz=int(Ncz),sd=ScellDiv;
+    NgSearch r; r.cellinit=(boundp2? 0: int(Nsheet*Ncz+1));
+    r.cxini=cx-(cx<sd? cx: sd); r.cxfin=cx+(ncx-cx-1<sd? ncx-cx-1: sd)+1;
+    r.yini=cy-(cy<sd? cy: sd);  r.yfin=cy+(ncy-cy-1<sd? ncy-cy-1: sd)+1;
+    r.zini=cz-(cz<sd? cz: sd);  r.zfin=cz+(ncz-cz-1<sd? ncz-cz-1: sd)+1;
+    return r;
+  }
+
+  // ---- JSphCpu::PreInteractionVars_Forces + PreInteraction_Forces S/JSphCpu.cpp:433-479
+  void PreInteraction(){
+    Ar.assign(Np,0.f); Ace.assign(Np,f3{0,0,0});
+    if(DDTArray)Delta.assign(Np,0.f); else Delta.clear();
+    if(ShiftMode)ShiftPosfs.assign(Np,f4{0,0,0,0}); else ShiftPosfs.clear();   // no shifting zones: JSphShifting::InitCpu S/JSphShifting.cpp:345-347
+    if(TVisco==DSPH_VISCO_LAMINARSPS)SpsGradvel.assign(Np,sym3{0,0,0,0,0,0});
+    Press.resize(Np);
+    // fsph::ComputePressMonaghan S/FunSphEos.h:38-40: b*(pow(rhop/rhop0,gamma)-1.0f).  Inside namespace fsph only the C
+    // ::pow(double,double) is visible, so the reference evaluates pow, the -1 and the *b in DOUBLE and rounds to float once;
+    // its -ffast-math build turns rhop/rhop0 into the float product rhop*(1.0f/rhop0) (verified in the disassembly of
+    // JSphCpu::PreInteractionVars_Forces, oracle/_ref/obj52/JSphCpu.o).  Both facts are reproduced here.
+    const float ovrhopzero=1.0f/RhopZero;
+    for(unsigned p=0;p<Np;p++)Press[p]=float(double(CteB)*(pow(double(Velrhop[p].w*ovrhopzero),double(Gamma))-1.0));
+    const unsigned pini=(cfg.dtallparticles? 0: Npb);
+    float vmax=0;
+    for(unsigned p=pini;p<Np;p++){ const f4 v=Velrhop[p]; const float v2=v.x*v.x+v.y*v.y+v.z*v.z; if(vmax<v2)vmax=v2; }
+    VelMax=sqrtf(vmax);                                                        // CalcVelMaxSeq/Omp S/JSphCpu.cpp:485-527 (float sqrt)
+    ViscDtMax=0;
+  }
+
+  // ---- JSphCpu::InteractionForcesFluid S/JSphCpu.cpp:631-822 (FtMode none, no symmetry)
+  void InteractionForcesFluid(bool boundp2,float visco,float &viscdt){
+    const int pinit=int(Npb), pfin=int(Np);
+    const bool shift=(ShiftMode!=0);
+    float vmaxall=viscdt; unsigned long long nreal=0,nchk=0;
+    #pragma omp parallel for schedule(guided) reduction(max:vmaxall) reduction(+:nreal,nchk)
+    for(int p1=pinit;p1<pfin;p1++){
+      float visc=0,arp1=0,deltap1=0; f3 acep1={0,0,0}; sym3 gradvelp1={0,0,0,0,0,0};
+      f4 shiftposfsp1={0,0,0,0}; if(shift)shiftposfsp1=ShiftPosfs[p1];
+      const d3 posp1=Pos[p1]; const f3 velp1={Velrhop[p1].x,Velrhop[p1].y,Velrhop[p1].z};
+      const float rhopp1=Velrhop[p1].w, pressp1=Press[p1];
+      const sym3 taup1=(TVisco==DSPH_VISCO_ARTIFICIAL? gradvelp1: SpsTau[p1]);
+      const NgSearch ngs=NgInit(Dcell[p1],boundp2);
+      for(int z=ngs.zini;z<ngs.zfin;z++)for(int y=ngs.yini;y<ngs.yfin;y++){
+        const int v=int(Nsheet)*z+int(Ncx)*y+ngs.cellinit;
+        const unsigned pini=BeginCell[v+ngs.cxini], pfin2=BeginCell[v+ngs.cxfin];
+        nchk+=pfin2-pini;
+        for(unsigned p2=pini;p2<pfin2;p2++){
+          const float drx=float(posp1.x-Pos[p2].x), dry=float(posp1.y-Pos[p2].y), drz=float(posp1.z-Pos[p2].z);
+          const float rr2=drx*drx+dry*dry+drz*drz;
+          if(rr2<=KernelSize2 && rr2>=1e-18f){
+            nreal++;
+            const float fac=Fac(rr2);
+            const float frx=fac*drx,fry=fac*dry,frz=fac*drz;
+            const float massp2=(boundp2? MassBound: MassFluid);
+            const f4 velrhop2=Velrhop[p2];
+            { //-Momentum
+              const float prs=(pressp1+Press[p2])/(rhopp1*velrhop2.w)+(TKernel==DSPH_KERNEL_CUBIC? TensilCubic(rr2,rhopp1,pressp1,velrhop2.w,Press[p2]): 0);
+              const float p_vpm=-prs*massp2;
+              acep1.x+=p_vpm*frx; acep1.y+=p_vpm*fry; acep1.z+=p_vpm*frz;
+            }
+            //-Continuity
+            const float dvx=velp1.x-velrhop2.x, dvy=velp1.y-velrhop2.y, dvz=velp1.z-velrhop2.z;
+            arp1+=massp2*(dvx*frx+dvy*fry+dvz*frz)*(rhopp1/velrhop2.w);
+            const float cbar=(float)Cs0;
+            if(TDensity==DSPH_DDT_DDT && deltap1!=FLT_MAX){             // Molteni & Colagrossi
+              const float rhop1over2=rhopp1/velrhop2.w;
+              const float visc_densi=DDTkh*cbar*(rhop1over2-1.f)/(rr2+Eta2);
+              const float dot3=(drx*frx+dry*fry+drz*frz);
+              const float delta=visc_densi*dot3*massp2;
+              deltap1=(boundp2? FLT_MAX: deltap1+delta);               // TBoundary==BC_DBC
+            }
+            if((TDensity==DSPH_DDT_DDT2 || (TDensity==DSPH_DDT_DDT2FULL && !boundp2)) && deltap1!=FLT_MAX){   // Fourtakas
+              const float rh=1.f+DDTgz*drz;
+              const float drhop=RhopZero*powf(rh,1.f/Gamma)-RhopZero;
+              const float visc_densi=DDTkh*cbar*((velrhop2.w-rhopp1)-drhop)/(rr2+Eta2);
+              const float dot3=(drx*frx+dry*fry+drz*frz);
+              const float delta=visc_densi*dot3*massp2/velrhop2.w;
+              deltap1=(boundp2? FLT_MAX: deltap1-delta);
+            }
+            if(shift && shiftposfsp1.x!=FLT_MAX){
+              const float massrhop=massp2/velrhop2.w;
+              const bool noshift=(boundp2 && (ShiftMode==DSPH_SHIFT_NOBOUND || (ShiftMode==DSPH_SHIFT_NOFIXED && CodeIsFixed(Code[p2]))));
+              shiftposfsp1.x=(noshift? FLT_MAX: shiftposfsp1.x+massrhop*frx);
+              shiftposfsp1.y+=massrhop*fry; shiftposfsp1.z+=massrhop*frz;
+              shiftposfsp1.w-=massrhop*(drx*frx+dry*fry+drz*frz);
+            }
+            { //-Viscosity
+              const float dot=drx*dvx+dry*dvy+drz*dvz;
+              const float dot_rr2=dot/(rr2+Eta2);
+              visc=std::max(dot_rr2,visc);
+              if(TVisco==DSPH_VISCO_ARTIFICIAL){
+                if(dot<0){
+                  const float amubar=KernelH*dot_rr2;
+                  const float robar=(rhopp1+velrhop2.w)*0.5f;
+                  const float pi_visc=(-visco*cbar*amubar/robar)*massp2;
+                  acep1.x-=pi_visc*frx; acep1.y-=pi_visc*fry; acep1.z-=pi_visc*frz;
+                }
+              }
+              else if(TVisco==DSPH_VISCO_LAMINARSPS){
+                {
+                  const float robar2=(rhopp1+velrhop2.w);
+                  const float temp=4.f*visco/((rr2+Eta2)*robar2);
+                  const float vtemp=massp2*temp*(drx*frx+dry*fry+drz*frz);
+                  acep1.x+=vtemp*dvx; acep1.y+=vtemp*dvy; acep1.z+=vtemp*dvz;
+                }
+                float tau_xx=taup1.xx,tau_xy=taup1.xy,tau_xz=taup1.xz,tau_yy=taup1.yy,tau_yz=taup1.yz,tau_zz=taup1.zz;
+                if(!boundp2){
+                  const sym3 t2=SpsTau[p2];
+                  tau_xx+=t2.xx; tau_xy+=t2.xy; tau_xz+=t2.xz; tau_yy+=t2.yy; tau_yz+=t2.yz; tau_zz+=t2.zz;
+                }
+                acep1.x+=massp2*(tau_xx*frx+tau_xy*fry+tau_xz*frz);
+                acep1.y+=massp2*(tau_xy*frx+tau_yy*fry+tau_yz*frz);
+                acep1.z+=massp2*(tau_xz*frx+tau_yz*fry+tau_zz*frz);
+                const float volp2=-massp2/velrhop2.w;
+                float dv=dvx*volp2; gradvelp1.xx+=dv*frx; gradvelp1.xy+=dv*fry; gradvelp1.xz+=dv*frz;
+                      dv=dvy*volp2; gradvelp1.xy+=dv*frx; gradvelp1.yy+=dv*fry; gradvelp1.yz+=dv*frz;
+                      dv=dvz*volp2; gradvelp1.xz+=dv*frx; gradvelp1.yz+=dv*fry; gradvelp1.zz+=dv*frz;
+              }
+            }
+          }
+        }
+      }
+      if(shift||arp1||acep1.x||acep1.y||acep1.z||visc){
+        if(TDensity!=DSPH_DDT_NONE){
+          if(!Delta.empty())Delta[p1]=(Delta[p1]==FLT_MAX || deltap1==FLT_MAX? FLT_MAX: Delta[p1]+deltap1);
+          else if(deltap1!=FLT_MAX)arp1+=deltap1;
+        }
+        Ar[p1]+=arp1;
+        Ace[p1].x=Ace[p1].x+acep1.x; Ace[p1].y=Ace[p1].y+acep1.y; Ace[p1].z=Ace[p1].z+acep1.z;
+        if(visc>vmaxall)vmaxall=visc;
+        if(TVisco==DSPH_VISCO_LAMINARSPS){
+          sym3 &g=SpsGradvel[p1];
+          g.xx+=gradvelp1.xx; g.xy+=gradvelp1.xy; g.xz+=gradvelp1.xz; g.yy+=gradvelp1.yy; g.yz+=gradvelp1.yz; g.zz+=gradvelp1.zz;
+        }
+        if(shift)ShiftPosfs[p1]=shiftposfsp1;
+      }
+    }
+    viscdt=vmaxall;
+    if(!boundp2){ PipsFluidReal=nreal; PipsFluidChecked=nchk; } else { PipsFluidReal+=nreal; PipsFluidChecked+=nchk; }
+  }
+  // ---- JSphCpu::InteractionForcesBound S/JSphCpu.cpp:548-625
+  void InteractionForcesBound(float &viscdt){
+    const int n=int(NpbOk);
+    float vmaxall=viscdt; unsigned long long nreal=0,nchk=0;
+    #pragma omp parallel for schedule(guided) reduction(max:vmaxall) reduction(+:nreal,nchk)
+    for(int p1=0;p1<n;p1++){
+      float visc=0,arp1=0;
+      const d3 posp1=Pos[p1]; const f4 velrhop1=Velrhop[p1];
+      const NgSearch ngs=NgInit(Dcell[p1],false);
+      for(int z=ngs.zini;z<ngs.zfin;z++)for(int y=ngs.yini;y<ngs.yfin;y++){
+        const int v=int(Nsheet)*z+int(Ncx)*y+ngs.cellinit;
+        const unsigned pini=BeginCell[v+ngs.cxini], pfin2=BeginCell[v+ngs.cxfin];
+        nchk+=pfin2-pini;
+        for(unsigned p2=pini;p2<pfin2;p2++){
+          const float drx=float(posp1.x-Pos[p2].x), dry=float(posp1.y-Pos[p2].y), drz=float(posp1.z-Pos[p2].z);
+          const float rr2=drx*drx+dry*dry+drz*drz;
+          if(rr2<=KernelSize2 && rr2>=1e-18f){
+            nreal++;
+            const float fac=Fac(rr2);
+            const float frx=fac*drx,fry=fac*dry,frz=fac*drz;
+            const float massp2=MassFluid;
+            const f4 velrhop2=Velrhop[p2];
+            const float dvx=velrhop1.x-velrhop2.x, dvy=velrhop1.y-velrhop2.y, dvz=velrhop1.z-velrhop2.z;
+            arp1+=massp2*(dvx*frx+dvy*fry+dvz*frz)*(velrhop1.w/velrhop2.w);
+            const float dot=drx*dvx+dry*dvy+drz*dvz;
+            const float dot_rr2=dot/(rr2+Eta2);
+            visc=std::max(dot_rr2,visc);
+          }
+        }
+      }
+      if(arp1||visc){ Ar[p1]+=arp1; if(visc>vmaxall)vmaxall=visc; }
+    }
+    viscdt=vmaxall; PipsBoundReal=nreal; PipsBoundChecked=nchk;
+  }
+  // ---- JSphCpu::ComputeSpsTau S/JSphCpu.cpp:930-955
+  void ComputeSpsTau(){
+    for(unsigned p=Npb;p<Np;p++){
+      const sym3 g=SpsGradvel[p];
+      const float pow1=g.xx*g.xx+g.yy*g.yy+g.zz*g.zz;
+      const float prr=pow1+pow1+g.xy*g.xy+g.xz*g.xz+g.yz*g.yz;
+      const float visc_sps=SpsSmag*sqrtf(prr);
+      const float div_u=g.xx+g.yy+g.zz;
+      const float sps_k=(2.0f/3.0f)*visc_sps*div_u;
+      const float sps_blin=SpsBlin*prr;
+      const float sumsps=-(sps_k+sps_blin);
+      const float twovisc_sps=(visc_sps+visc_sps);
+      const float one_rho2=1.0f/Velrhop[p].w;
+      sym3 &t=SpsTau[p];
+      t.xx=one_rho2*(twovisc_sps*g.xx+sumsps); t.xy=one_rho2*(visc_sps*g.xy); t.xz=one_rho2*(visc_sps*g.xz);
+      t.yy=one_rho2*(twovisc_sps*g.yy+sumsps); t.yz=one_rho2*(visc_sps*g.yz); t.zz=one_rho2*(twovisc_sps*g.zz+sumsps);
+    }
+  }
+  // ---- JSphCpuSingle::Interaction_Forces S/JSphCpuSingle.cpp:524-567 + Interaction_ForcesCpuT S/JSphCpu.cpp:960-987
+  void InteractionForces(){
+    PreInteraction();
+    float viscdt=0;
+    if(Np>Npb){
+      InteractionForcesFluid(false,Visco,viscdt);
+      InteractionForcesFluid(true,Visco*ViscoBoundFactor,viscdt);
+      if(TVisco==DSPH_VISCO_LAMINARSPS)ComputeSpsTau();
+    }
+    if(NpbOk)InteractionForcesBound(viscdt);
+    if(Simulate2D)for(unsigned p=Npb;p<Np;p++)Ace[p].y=0;
+    if(!Delta.empty())for(unsigned p=Npb;p<Np;p++)if(Delta[p]!=FLT_MAX)Ar[p]+=Delta[p];
+    ViscDtMax=viscdt;
+    // ComputeAceMax S/JSphCpuSingle.cpp:583-636 (periodic particles ignored when PeriActive)
+    float amax=0;
+    for(unsigned p=Npb;p<Np;p++){
+      const bool use=(!PeriActive || CodeIsNormal(Code[p]));
+      const f3 a=(use? Ace[p]: f3{0,0,0});
+      const float a2=a.x*a.x+a.y*a.y+a.z*a.z; if(amax<a2)amax=a2;
+    }
+    AceMax=sqrt(double(amax));
+  }
+  // ---- JSphCpu::DtVariable S/JSphCpu.cpp:1614-1639
+  double DtVariable(double *pdt1,double *pdt2)const{
+    const double dt1=(AceMax? (sqrt(double(KernelH)/AceMax)): DBL_MAX);
+    const double dt2=double(KernelH)/(std::max(Cs0,VelMax*10.)+double(KernelH)*ViscDtMax);
+    double dt=CFLnumber*std::min(dt1,dt2);
+    if(cfg.dtfixed_on)dt=cfg.dtfixed;
+    if(dt!=dt || std::isinf(dt))throw std::runtime_error("The computed Dt is NaN or infinity.");
+    if(dt<DtMin)dt=DtMin;
+    if(pdt1)*pdt1=dt1; if(pdt2)*pdt2=dt2;
+    return dt;
+  }
+  // ---- JSphShifting::RunCpu S/JSphShifting.cpp:387-417
+  void RunShifting(double dt){
+    const double coefumagn=dt*ShiftCoef*KernelH;
+    const double coeftfs=(Simulate2D? 2.0: 3.0)-ShiftTFS;
+    const float maxdist=float(Dp*0.1);
+    for(unsigned p=Npb;p<Np;p++){
+      const f4 rs=ShiftPosfs[p];
+      if(rs.x!=FLT_MAX){
+        const double vx=double(Velrhop[p].x),vy=double(Velrhop[p].y),vz=double(Velrhop[p].z);
+        double umagn=coefumagn*sqrt(vx*vx+vy*vy+vz*vz);
+        if(ShiftTFS){
+          if(rs.w<ShiftTFS)umagn=0;
+          else umagn*=(double(rs.w)-ShiftTFS)/coeftfs;
+        }
+        const float sx=float(double(rs.x)*umagn), sy=float(double(rs.y)*umagn), sz=float(double(rs.z)*umagn);
+        ShiftPosfs[p].x=(fabsf(sx)<maxdist? sx: (sx>=0? maxdist: -maxdist));
+        ShiftPosfs[p].y=(fabsf(sy)<maxdist? sy: (sy>=0? maxdist: -maxdist));
+        ShiftPosfs[p].z=(fabsf(sz)<maxdist? sz: (sz>=0? maxdist: -maxdist));
+      }
+      else ShiftPosfs[p]=f4{0,0,0,0};
+    }
+  }
+  // ---- JSphCpu::UpdatePos S/JSphCpu.cpp:1240-1293
+  void UpdatePos(d3 rpos,double movx,double movy,double movz,bool outrhop,unsigned p){
+    const bool outmove=(fabsf(float(movx))>MovLimit || fabsf(float(movy))>MovLimit || fabsf(float(movz))>MovLimit);
+    rpos.x+=movx; rpos.y+=movy; rpos.z+=movz;
+    double dx=rpos.x-MapRealPosMin.x, dy=rpos.y-MapRealPosMin.y, dz=rpos.z-MapRealPosMin.z;
+    bool out=(dx!=dx||dy!=dy||dz!=dz||dx<0||dy<0||dz<0||dx>=MapRealSize.x||dy>=MapRealSize.y||dz>=MapRealSize.z);
+    if(PeriActive && out){
+      if(PeriX){ if(dx<0){ dx-=PeriXinc.x; dy-=PeriXinc.y; dz-=PeriXinc.z; } if(dx>=MapRealSize.x){ dx+=PeriXinc.x; dy+=PeriXinc.y; dz+=PeriXinc.z; } }
+      if(PeriY){ if(dy<0){ dx-=PeriYinc.x; dy-=PeriYinc.y; dz-=PeriYinc.z; } if(dy>=MapRealSize.y){ dx+=PeriYinc.x; dy+=PeriYinc.y; dz+=PeriYinc.z; } }
+      if(PeriZ){ if(dz<0){ dx-=PeriZinc.x; dy-=PeriZinc.y; dz-=PeriZinc.z; } if(dz>=MapRealSize.z){ dx+=PeriZinc.x; dy+=PeriZinc.y; dz+=PeriZinc.z; } }
+      const bool outx=!PeriX && (dx<0||dx>=MapRealSize.x), outy=!PeriY && (dy<0||dy>=MapRealSize.y), outz=!PeriZ && (dz<0||dz>=MapRealSize.z);
+      out=(outx||outy||outz);
+      rpos={dx+MapRealPosMin.x,dy+MapRealPosMin.y,dz+MapRealPosMin.z};
+    }
+    Pos[p]=rpos;
+    if(outrhop||outmove||out){
+      typecode rcode=Code[p];
+      if(out)rcode=typecode(CodeSetNormal(rcode)|DSPH_CODE_OUTPOS);
+      else if(outrhop)rcode=typecode(CodeSetNormal(rcode)|DSPH_CODE_OUTRHOP);
+      else rcode=typecode(CodeSetNormal(rcode)|DSPH_CODE_OUTMOVE);
+      Code[p]=rcode; Dcell[p]=0xFFFFFFFFu;
+    }
+    else{
+      if(PeriActive){ dx=rpos.x-DomPosMin.x; dy=rpos.y-DomPosMin.y; dz=rpos.z-DomPosMin.z; }
+      const unsigned cx=unsigned(dx/Scell),cy=unsigned(dy/Scell),cz=unsigned(dz/Scell);
+      Dcell[p]=DcCell(DomCellCode,cx,cy,cz);
+    }
+  }
+  // ---- JSphCpu::ComputeVerlet + ComputeVerletVarsFluid + ComputeVelrhopBound S/JSphCpu.cpp:1300-1399
+  void ComputeVerlet(double dt){
+    const bool shift=(ShiftMode!=0);
+    VerletStep++;
+    const bool euler=!(VerletStep<VerletSteps);
+    const double dt2=(euler? dt: dt+dt);
+    const std::vector<f4> &vr2=(euler? Velrhop: VelrhopM1);
+    std::vector<f4> vnew(Np);
+    const double dt205=0.5*dt*dt;
+    const d3 gravity={double(Gravity.x),double(Gravity.y),double(Gravity.z)};
+    for(unsigned p=Npb;p<Np;p++){
+      const float rhopnew=float(double(vr2[p].w)+dt2*Ar[p]);
+      const d3 acegr={double(Ace[p].x)+gravity.x,double(Ace[p].y)+gravity.y,double(Ace[p].z)+gravity.z};
+      double dx=double(Velrhop[p].x)*dt+acegr.x*dt205, dy=double(Velrhop[p].y)*dt+acegr.y*dt205, dz=double(Velrhop[p].z)*dt+acegr.z*dt205;
+      if(shift){ dx+=double(ShiftPosfs[p].x); dy+=double(ShiftPosfs[p].y); dz+=double(ShiftPosfs[p].z); }
+      const bool outrhop=(rhopnew<RhopOutMin || rhopnew>RhopOutMax);
+      const f4 rv={float(double(vr2[p].x)+acegr.x*dt2),float(double(vr2[p].y)+acegr.y*dt2),float(double(vr2[p].z)+acegr.z*dt2),rhopnew};
+      UpdatePos(Pos[p],dx,dy,dz,outrhop,p);
+      vnew[p]=rv;
+    }
+    for(unsigned p=0;p<Npb;p++){
+      const float rhopnew=float(double(vr2[p].w)+dt2*Ar[p]);
+      vnew[p]=f4{0,0,0,(rhopnew<RhopZero? RhopZero: rhopnew)};
+    }
+    // new values computed in VelrhopM1 then swapped (S/JSphCpu.cpp:1385-1398)
+    std::vector<f4> old=Velrhop;
+    for(unsigned p=0;p<Np;p++)Velrhop[p]=vnew[p];
+    for(unsigned p=0;p<Np;p++)VelrhopM1[p]=old[p];
+    if(euler)VerletStep=0;
+  }
+  // ---- JSphCpu::ComputeSymplecticPre S/JSphCpu.cpp:1406-1497
+  void ComputeSymplecticPre(double dt){
+    const double dt05=dt*.5;
+    for(unsigned p=0;p<Np;p++){ PosPre[p]=Pos[p]; VelrhopPre[p]=Velrhop[p]; }
+    HasPre=true;
+    for(unsigned p=0;p<Npb;p++){
+      const f4 vr=VelrhopPre[p];
+      const float rhopnew=float(double(vr.w)+dt05*Ar[p]);
+      Velrhop[p]=f4{vr.x,vr.y,vr.z,(rhopnew<RhopZero? RhopZero: rhopnew)};
+    }
+    std::vector<d3> mov(Np);
+    for(unsigned p=Npb;p<Np;p++){
+      const typecode rcode=Code[p];
+      const float rhopnew=float(double(VelrhopPre[p].w)+dt05*Ar[p]);
+      const double dx=double(VelrhopPre[p].x)*dt05, dy=double(VelrhopPre[p].y)*dt05, dz=double(VelrhopPre[p].z)*dt05;   // predictor never shifts (S/JSphCpu.cpp:1408)
+      const bool outrhop=(rhopnew<RhopOutMin || rhopnew>RhopOutMax);
+      const f4 rv={float(double(VelrhopPre[p].x)+(double(Ace[p].x)+Gravity.x)*dt05),
+                   float(double(VelrhopPre[p].y)+(double(Ace[p].y)+Gravity.y)*dt05),
+                   float(double(VelrhopPre[p].z)+(double(Ace[p].z)+Gravity.z)*dt05),rhopnew};
+      mov[p]={dx,dy,dz}; Velrhop[p]=rv;
+      if(outrhop && CodeIsNormal(rcode))Code[p]=typecode(CodeSetNormal(rcode)|DSPH_CODE_OUTRHOP);
+    }
+    for(unsigned p=Npb;p<Np;p++){
+      const typecode rcode=Code[p];
+      const bool outrhop=CodeIsOutRhop(rcode);
+      const bool normal=(!PeriActive || outrhop || CodeIsNormal(rcode));
+      if(normal){
+        if(CodeIsFluid(rcode))UpdatePos(PosPre[p],mov[p].x,mov[p].y,mov[p].z,outrhop,p);
+        else Pos[p]=PosPre[p];
+      }
+    }
+    for(unsigned p=0;p<Npb;p++)Pos[p]=PosPre[p];
+  }
+  // ---- JSphCpu::ComputeSymplecticCorr S/JSphCpu.cpp:1503-1606
+  void ComputeSymplecticCorr(double dt){
+    const bool shift=(ShiftMode!=0);
+    const double dt05=dt*.5;
+    for(unsigned p=0;p<Npb;p++){
+      const double epsilon_rdot=(-double(Ar[p])/double(Velrhop[p].w))*dt;
+      const float rhopnew=float(double(VelrhopPre[p].w)*(2.-epsilon_rdot)/(2.+epsilon_rdot));
+      Velrhop[p]=f4{0,0,0,(rhopnew<RhopZero? RhopZero: rhopnew)};
+    }
+    std::vector<d3> mov(Np);
+    for(unsigned p=Npb;p<Np;p++){
+      const typecode rcode=Code[p];
+      const double epsilon_rdot=(-double(Ar[p])/double(Velrhop[p].w))*dt;
+      const float rhopnew=float(double(VelrhopPre[p].w)*(2.-epsilon_rdot)/(2.+epsilon_rdot));
+      const f4 rv={float(double(VelrhopPre[p].x)+(double(Ace[p].x)+Gravity.x)*dt),
+                   float(double(VelrhopPre[p].y)+(double(Ace[p].y)+Gravity.y)*dt),
+                   float(double(VelrhopPre[p].z)+(double(Ace[p].z)+Gravity.z)*dt),rhopnew};
+      double dx=(double(VelrhopPre[p].x)+double(rv.x))*dt05, dy=(double(VelrhopPre[p].y)+double(rv.y))*dt05, dz=(double(VelrhopPre[p].z)+double(rv.z))*dt05;
+      if(shift){ dx+=double(ShiftPosfs[p].x); dy+=double(ShiftPosfs[p].y); dz+=double(ShiftPosfs[p].z); }
+      const bool outrhop=(rhopnew<RhopOutMin || rhopnew>RhopOutMax);
+      mov[p]={dx,dy,dz};
+      if(outrhop && CodeIsNormal(rcode))Code[p]=typecode(CodeSetNormal(rcode)|DSPH_CODE_OUTRHOP);
+      Velrhop[p]=rv;
+    }
+    for(unsigned p=Npb;p<Np;p++){
+      const typecode rcode=Code[p];
+      const bool outrhop=CodeIsOutRhop(rcode);
+      const bool normal=(!PeriActive || outrhop || CodeIsNormal(rcode));
+      if(normal){
+        if(CodeIsFluid(rcode))UpdatePos(PosPre[p],mov[p].x,mov[p].y,mov[p].z,outrhop,p);
+        else Pos[p]=PosPre[p];
+      }
+    }
+    HasPre=false;
+  }
+};
+
+thread_local std::string g_err;
+template<class F> int Guard(F f){
+  try{ f(); return DSPH_OK; }
+  catch(const std::exception &e){ g_err=e.what(); return DSPH_ERR_STATE; }
+}
+
+} // namespace
+
+extern "C" {
+
+struct orc_state { Oracle o; };
+
+const char* orc_last_error(void){ return g_err.c_str(); }
+
+int orc_create(orc_state **out,const dsph_config *cfg){
+  return Guard([&]{ orc_state *s=new orc_state(); try{ s->o.Configure(*cfg); }catch(...){ delete s; throw; } *out=s; });
+}
+int orc_destroy(orc_state *s){ delete s; return DSPH_OK; }
+
+int orc_particles_upload(orc_state *s,uint32_t np,uint32_t npb,const uint32_t *idp,const uint16_t *code,const double *pos,const float *velrhop){
+  return Guard([&]{
+    Oracle &o=s->o;
+    o.Np=np; o.Npb=npb; o.NpbOk=npb; o.NpbPer=o.NpfPer=0;
+    o.Resize(np+np/10+1024);
+    for(unsigned p=0;p<np;p++){
+      o.Idp[p]=idp[p];
+      o.Code[p]=(code? code[p]: typecode(idp[p]<o.cfg.casenfixed? DSPH_CODE_TYPE_FIXED: DSPH_CODE_TYPE_FLUID));
+      o.Pos[p]={pos[3*p],pos[3*p+1],pos[3*p+2]};
+      o.Velrhop[p]={velrhop[4*p],velrhop[4*p+1],velrhop[4*p+2],velrhop[4*p+3]};
+    }
+    if(o.TStep==DSPH_STEP_VERLET)for(unsigned p=0;p<np;p++)o.VelrhopM1[p]=o.Velrhop[p];     // InitRunCpu S/JSphCpu.cpp:422
+    if(o.TVisco==DSPH_VISCO_LAMINARSPS)for(unsigned p=0;p<np;p++)o.SpsTau[p]=sym3{0,0,0,0,0,0};
+    o.HasPre=false; o.BoundChanged=true; o.BoundLimitOk=o.BoundDivideOk=false;
+    o.SymplecticDtPre=o.DtIni; o.VerletStep=0;
+    o.LoadDcellParticles();
+  });
+}
+int orc_particles_set_velrhopm1(orc_state *s,const float *v){
+  return Guard([&]{ Oracle &o=s->o; if(o.TStep!=DSPH_STEP_VERLET)throw std::runtime_error("VelrhopM1 is only used by Verlet."); for(unsigned p=0;p<o.Np;p++)o.VelrhopM1[p]={v[4*p],v[4*p+1],v[4*p+2],v[4*p+3]}; });
+}
+int orc_particles_set_spstau(orc_state *s,const float *t){
+  return Guard([&]{ Oracle &o=s->o; if(o.TVisco!=DSPH_VISCO_LAMINARSPS)throw std::runtime_error("SpsTau is only used by Laminar+SPS."); for(unsigned p=0;p<o.Np;p++)o.SpsTau[p]={t[6*p],t[6*p+1],t[6*p+2],t[6*p+3],t[6*p+4],t[6*p+5]}; });
+}
+int orc_particles_download(orc_state *s,uint32_t first,uint32_t count,uint32_t *idp,uint16_t *code,uint32_t *dcell,double *pos,float *velrhop){
+  return Guard([&]{
+    Oracle &o=s->o; if(first+count>o.Np)throw std::runtime_error("range out of particles");
+    for(unsigned i=0;i<count;i++){
+      const unsigned p=first+i;
+      if(idp)idp[i]=o.Idp[p]; if(code)code[i]=o.Code[p]; if(dcell)dcell[i]=o.Dcell[p];
+      if(pos){ pos[3*i]=o.Pos[p].x; pos[3*i+1]=o.Pos[p].y; pos[3*i+2]=o.Pos[p].z; }
+      if(velrhop){ velrhop[4*i]=o.Velrhop[p].x; velrhop[4*i+1]=o.Velrhop[p].y; velrhop[4*i+2]=o.Velrhop[p].z; velrhop[4*i+3]=o.Velrhop[p].w; }
+    }
+  });
+}
+uint32_t orc_np(const orc_state *s){ return s->o.Np; }
+uint32_t orc_npb(const orc_state *s){ return s->o.Npb; }
+
+static void FillDivInfo(const Oracle &o,dsph_divinfo *info){
+  if(!info)return;
+  memset(info,0,sizeof(*info));
+  info->np=o.Np; info->npb=o.Npb; info->npbok=o.NpbOk; info->npbper=o.NpbPer; info->npfper=o.NpfPer;
+  info->npbout=o.NpbOut; info->npfout=o.NpfOut; info->npbignore=o.NpbIgnore; info->npboutignore=o.NpbOutIgnore; info->npfoutignore=o.NpfOutIgnore;
+  info->ncx=o.Ncx; info->ncy=o.Ncy; info->ncz=o.Ncz; info->nct=o.Nct; info->nctt=o.Nctt;
+  for(int i=0;i<3;i++){ info->cellmin[i]=o.CellDomainMin[i]; info->cellmax[i]=o.CellDomainMax[i]; info->domcells[i]=o.DomCells[i]; }
+  info->domcellcode=o.DomCellCode; info->dividefull=o.DivideFull; info->scell=o.Scell;
+  info->domposmin[0]=o.DomPosMin.x; info->domposmin[1]=o.DomPosMin.y; info->domposmin[2]=o.DomPosMin.z;
+}
+int orc_celldiv_run(orc_state *s,int updateperiodic,dsph_divinfo *info){
+  return Guard([&]{ s->o.RunCellDivide(updateperiodic!=0); FillDivInfo(s->o,info); });
+}
+int orc_celldiv_get_begincell(orc_state *s,uint32_t *begincell,uint32_t capacity){
+  return Guard([&]{ const Oracle &o=s->o; if(capacity<o.Nctt)throw std::runtime_error("capacity too small"); memcpy(begincell,o.BeginCell.data(),size_t(o.Nctt)*4); });
+}
+static void FillForceRes(const Oracle &o,dsph_forceres *res){
+  if(!res)return;
+  memset(res,0,sizeof(*res));
+  res->viscdtmax=o.ViscDtMax; res->acemax=float(o.AceMax); res->velmax=float(o.VelMax);
+  res->dt=o.DtVariable(&res->dt1,&res->dt2);
+}
+int orc_forces_run(orc_state *s,int interstep,dsph_forceres *res){
+  (void)interstep;
+  return Guard([&]{ s->o.InteractionForces(); FillForceRes(s->o,res); });
+}
+int orc_forces_download(orc_state *s,uint32_t first,uint32_t count,float *ace,float *ar){
+  return Guard([&]{
+    const Oracle &o=s->o; if(first+count>o.Np || o.Ace.size()<o.Np)throw std::runtime_error("forces are not available");
+    for(unsigned i=0;i<count;i++){ const unsigned p=first+i; if(ace){ ace[3*i]=o.Ace[p].x; ace[3*i+1]=o.Ace[p].y; ace[3*i+2]=o.Ace[p].z; } if(ar)ar[i]=o.Ar[p]; }
+  });
+}
+int orc_step_verlet(orc_state *s,double dt){ return Guard([&]{ Oracle &o=s->o; if(o.ShiftMode)o.RunShifting(dt); o.ComputeVerlet(dt); }); }
+int orc_step_sympre(orc_state *s,double dt){ return Guard([&]{ Oracle &o=s->o; if(o.ShiftMode)o.RunShifting(dt*.5); o.ComputeSymplecticPre(dt); }); }
+int orc_step_symcor(orc_state *s,double dt){ return Guard([&]{ Oracle &o=s->o; if(o.ShiftMode)o.RunShifting(dt); o.ComputeSymplecticCorr(dt); }); }
+
+// JSphCpuSingle::ComputeStep_Sym/_Ver + closing RunCellDivide S/JSphCpuSingle.cpp:674-721,1093-1098
+int orc_step(orc_state *s,double *stepdt,dsph_forceres *res){
+  return Guard([&]{
+    Oracle &o=s->o; double dt;
+    if(o.TStep==DSPH_STEP_SYMPLECTIC){
+      dt=o.SymplecticDtPre;
+      o.InteractionForces();
+      const double ddt_p=o.DtVariable(nullptr,nullptr);
+      if(o.ShiftMode)o.RunShifting(dt*.5);
+      o.ComputeSymplecticPre(dt);
+      o.RunCellDivide(true);
+      o.InteractionForces();
+      const double ddt_c=o.DtVariable(nullptr,nullptr);
+      FillForceRes(o,res);
+      if(o.ShiftMode)o.RunShifting(dt);
+      o.ComputeSymplecticCorr(dt);
+      o.SymplecticDtPre=std::min(ddt_p,ddt_c);
+    }
+    else{
+      o.InteractionForces();
+      dt=o.DtVariable(nullptr,nullptr);
+      FillForceRes(o,res);
+      if(o.ShiftMode)o.RunShifting(dt);
+      o.ComputeVerlet(dt);
+    }
+    o.RunCellDivide(true);
+    if(stepdt)*stepdt=dt;
+  });
+}
+double orc_symplectic_dtpre(const orc_state *s){ return s->o.SymplecticDtPre; }
+int orc_set_symplectic_dtpre(orc_state *s,double dt){ s->o.SymplecticDtPre=dt; return DSPH_OK; }
+int orc_set_verletstep(orc_state *s,int v){ s->o.VerletStep=v; return DSPH_OK; }
+int orc_pips(orc_state *s,uint64_t *fr,uint64_t *fc,uint64_t *br,uint64_t *bc){
+  const Oracle &o=s->o; if(fr)*fr=o.PipsFluidReal; if(fc)*fc=o.PipsFluidChecked; if(br)*br=o.PipsBoundReal; if(bc)*bc=o.PipsBoundChecked; return DSPH_OK;
+}
+int orc_num_threads(void){
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+} // extern "C"

@@ -1,0 +1,33 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(__file__))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    """CPU checker (oracle/liboracle.so); built on demand with the system g++.  Test infrastructure only."""
+    from dualsphysics_multilayer_b200.capi import SphLib
+    so = os.path.join(ROOT, "oracle", "liboracle.so")
+    src = os.path.join(ROOT, "oracle", "sph_oracle.cpp")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
+    return SphLib(so, "orc_")
+
+
+@pytest.fixture(scope="session")
+def gpu_lib():
+    """Product library; the GPU tests fail (not skip) if it is missing or no device is present."""
+    import dualsphysics_multilayer_b200 as dsph
+    L = dsph.lib()
+    assert dsph.device_count() > 0, "no CUDA device: -m gpu tests must run on the B200 box"
+    return L

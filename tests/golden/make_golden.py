@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz from the REFERENCE's own CPU solver (run only where /root/reference exists).
+
+For every case below: the repo's mkcase writes Case.xml + Case.bi4, oracle/_ref/ref_harness52 (the reference
+JSphCpuSingle, subclassed by oracle/ref_harness.cpp) simulates it single-threaded and dumps the intermediate state of
+selected steps; the dumps are packed into one compressed npz together with the raw dsph_config bytes and the case
+arrays.  These files pin the CPU restatement in oracle/ (tests/test_oracle_vs_reference.py) and the CUDA path
+(tests/test_gpu_parity.py).
+
+    python tests/golden/make_golden.py            # (re)generates every fixture
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import dualsphysics_multilayer_b200 as dsph  # noqa: E402
+from dumpio import read_dump  # noqa: E402
+
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness52")
+MKCASE = os.path.join(ROOT, "dualsphysics_multilayer_b200", "bin", "mkcase")
+
+# name, kind, np_target, mkcase options, dumped steps, total steps
+CASES = [
+    ("db_sym_wend_art_ddt2", "dambreak", 3000, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2"], [0, 40], 41),
+    ("db_ver_cubic_art_ddt1_shift", "dambreak", 3000, ["tstep=1", "tkernel=1", "tvisco=1", "visco=0.1", "ddt=1", "shifting=3", "shiftcoef=-2", "shifttfs=2.75", "verletsteps=10"], [0, 9, 25], 26),
+    ("db_sym_wend_lamsps_ddt3", "dambreak", 3000, ["tstep=2", "tkernel=2", "tvisco=2", "visco=0.01", "ddt=3"], [0, 30], 31),
+    ("db_sym_cubic_art_noddt_half", "dambreak", 3000, ["tstep=2", "tkernel=1", "tvisco=1", "visco=0.05", "ddt=0", "cellmode=2", "shifting=1", "shiftcoef=-2"], [20], 21),
+    ("pb_sym_wend_art_ddt1", "periodicbox", 1728, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=1"], [0, 15], 16),
+    ("pb_ver_wend_art_ddt1", "periodicbox", 1728, ["tstep=1", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=1", "verletsteps=5"], [0, 12], 13),
+]
+
+
+def run(name, kind, nptarget, opts, steps, nsteps, outdir):
+    tmp = tempfile.mkdtemp(prefix="golden_")
+    try:
+        subprocess.check_call([MKCASE, kind, str(nptarget), tmp, "Case"] + opts, stdout=subprocess.DEVNULL)
+        cmd = [HARNESS, "Case", "out", "-cpu", "-ompthreads:1", "-sv:none", "-hdir:" + os.path.join(tmp, "dump"),
+               "-hsteps:" + ",".join(str(s) for s in steps), "-hnsteps:%d" % nsteps]
+        cmd += ["-cellmode:half"] if "cellmode=2" in opts else []
+        r = subprocess.run(cmd, cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            print(r.stdout[-3000:])
+            raise RuntimeError("reference harness failed for " + name)
+        cd = dsph.load_case(tmp, "Case")
+        if "cellmode=2" in opts:
+            cd.cfg.cellmode = 2
+        pack = {"config": np.frombuffer(bytes(cd.cfg), np.uint8).copy(), "case/idp": cd.idp, "case/pos": cd.pos,
+                "case/velrhop": cd.velrhop, "case/npb": np.uint32(cd.npb), "steps": np.array(steps, np.uint32),
+                "nsteps": np.uint32(nsteps), "case/caseposmin": np.array(cd.caseposmin), "case/caseposmax": np.array(cd.caseposmax)}
+        for f in sorted(os.listdir(os.path.join(tmp, "dump"))):
+            d = read_dump(os.path.join(tmp, "dump", f))
+            stem = f[:-4]
+            for k, v in d.items():
+                pack[stem + "/" + k] = v
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), **pack)
+        print("%-32s np=%d  %.1f KB" % (name, cd.np_, os.path.getsize(os.path.join(outdir, name + ".npz")) / 1024))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    if not os.path.exists(HARNESS):
+        sys.exit("oracle/_ref/ref_harness52 is missing: run `make -C oracle v52` where /root/reference is mounted")
+    out = os.path.dirname(os.path.abspath(__file__))
+    only = sys.argv[1:]
+    for c in CASES:
+        if not only or c[0] in only:
+            run(*c, outdir=out)

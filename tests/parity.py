@@ -1,0 +1,174 @@
+"""Stage-by-stage parity of one solver (CPU checker or CUDA path) against a golden dump of the reference solver.
+
+Integer/index work (cell assignment, sorted order, begin-cell table, particle codes) must be bit-exact; floating
+point results are compared with a relative L2 norm (north_star: 1e-5 for single-step Ace/Ar/dt in fp32)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from dualsphysics_multilayer_b200 import capi
+from dualsphysics_multilayer_b200.capi import Config, SphContext
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+GOLDEN_CASES = ["db_sym_wend_art_ddt2", "db_ver_cubic_art_ddt1_shift", "db_sym_wend_lamsps_ddt3",
+                "db_sym_cubic_art_noddt_half", "pb_sym_wend_art_ddt1", "pb_ver_wend_art_ddt1"]
+
+
+def rl2(a, b):
+    a = np.asarray(a, np.float64).ravel(); b = np.asarray(b, np.float64).ravel()
+    den = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / den) if den > 0 else float(np.linalg.norm(a - b))
+
+
+class Golden:
+    def __init__(self, name):
+        self.name = name
+        self.z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        self.cfg = Config.from_buffer_copy(self.z["config"].tobytes())
+        self.steps = [int(s) for s in self.z["steps"]]
+        self.nsteps = int(self.z["nsteps"])
+        self.symplectic = (self.cfg.tstep == capi.STEP_SYMPLECTIC)
+        self.periodic = bool(self.cfg.perix or self.cfg.periy or self.cfg.periz)
+
+    def stage(self, step, stage):
+        pre = "s%04d_%s/" % (step, stage)
+        return {k[len(pre):]: self.z[k] for k in self.z.files if k.startswith(pre)}
+
+    def has(self, step, stage):
+        return ("s%04d_%s/np" % (step, stage)) in self.z.files
+
+
+def make_ctx(lib, cfg, capacity=0):
+    return SphContext(lib, cfg, capacity)
+
+
+def upload_state(ctx, st, cfg):
+    """Uploads a dumped (cell-sorted) reference state, periodic duplicates included."""
+    code = st["code"]
+    keep = np.ones(code.shape[0], bool)          # periodic duplicates are kept: the first divide runs with updateperiodic=0
+    npb = int(st["npb"])
+    ctx.upload(st["idp"][keep], st["pos"][keep], st["velrhop"][keep], npb, code[keep])
+    if "velrhopm1" in st:
+        ctx.set_velrhopm1(st["velrhopm1"][keep])
+    if "spstau" in st:
+        ctx.set_spstau(st["spstau"][keep])
+    if cfg.tstep == capi.STEP_SYMPLECTIC:
+        ctx.symplectic_dtpre = float(st["symplecticdtpre"])
+    else:
+        fn = ctx.lib.fn("set_verletstep")
+        fn.argtypes = [C.c_void_p, C.c_int]
+        fn(ctx.h, int(st["verletstep"]))
+    return keep
+
+
+def check_divide(ctx, ref, exact_ints=True):
+    """After ctx.celldiv(): cell domain, counts, sorted order, dcell, codes and begin-cell table must equal the dump."""
+    info = ctx.divinfo
+    res = {}
+    assert int(info.np) == int(ref["np"]), ("np", info.np, ref["np"])
+    assert int(info.npb) == int(ref["npb"]) and int(info.npbok) == int(ref["npbok"])
+    assert list(info.cellmin) + list(info.cellmax) == [int(v) for v in ref["celldomain"]], "cell domain"
+    assert [info.ncx, info.ncy, info.ncz, info.nct] == [int(v) for v in ref["ncells"]]
+    assert int(info.domcellcode) == int(ref["domcellcode"])
+    st = ctx.download()
+    assert np.array_equal(st["idp"], ref["idp"]), "sorted particle order (idp)"
+    assert np.array_equal(st["dcell"], ref["dcell"]), "dcell"
+    assert np.array_equal(st["code"], ref["code"]), "code"
+    # boxes of valid particles: nct boundary cells, BoxBoundIgnore, nct fluid cells, begin of BoxBoundOut (= np).  The
+    # out/ignore boxes after them hold particles the reference dropped in this divide, which a replay does not have.
+    nvalid = 2 * int(info.nct) + 2
+    assert np.array_equal(ctx.begincell()[:nvalid], ref["begincell"][:nvalid]), "begin-cell table"
+    assert np.array_equal(st["pos"], ref["pos"]), "positions must be moved bit-exactly by the reorder"
+    assert np.array_equal(st["velrhop"], ref["velrhop"])
+    return res
+
+
+def check_forces(ctx, ref, cfg, tol, interstep):
+    fr = ctx.forces(interstep)
+    ace, ar = ctx.forces_download()
+    npb = int(ref["npb"])
+    out = dict(ace=rl2(ace[npb:], ref["ace"][npb:]), ar=rl2(ar, ref["ar"]),
+               dt=abs(fr.dt - float(ref["dt"])) / float(ref["dt"]),
+               viscdt=abs(fr.viscdtmax - float(ref["viscdtmax"])) / max(abs(float(ref["viscdtmax"])), 1e-30),
+               acemax=abs(fr.acemax - float(ref["acemax"])) / max(float(ref["acemax"]), 1e-30),
+               velmax=abs(fr.velmax - float(ref["velmax"])) / max(float(ref["velmax"]), 1e-30))
+    for k, v in out.items():
+        assert v <= tol.get(k, tol["default"]), (k, v, out)
+    return fr, out
+
+
+def run_step_stages(lib, g: Golden, step, tol, capacity=0):
+    """Replays one dumped time step stage by stage, re-synchronising with the reference state before each stage."""
+    cfg = g.cfg
+    results = {}
+    ctx = make_ctx(lib, cfg, capacity)
+    s0 = g.stage(step, "div0")
+    upload_state(ctx, s0, cfg)
+    ctx.celldiv(False)                         # the state already holds its periodic duplicates
+    check_divide(ctx, s0)                      # divide of the reference's own state: must reproduce it exactly
+    noisy = (step == 0)                        # at t=0 the density rate is pure rounding noise of the DDT term
+    t2 = dict(tol)
+    if noisy:
+        t2["ar"] = 1.0
+    if g.symplectic:
+        dt = float(s0["symplecticdtpre"])
+        _, results["fpre"] = check_forces(ctx, g.stage(step, "fpre"), cfg, t2, capi.INTERSTEP_SYMPREDICTOR)
+        ctx.step_sympre(dt)
+        u = g.stage(step, "upre")
+        st = ctx.download()
+        normal = (st["code"] & capi.CODE_MASKSPECIAL) != capi.CODE_PERIODIC
+        assert np.array_equal(st["dcell"][normal], u["dcell"][normal]), "dcell after predictor"
+        assert np.array_equal(st["code"], u["code"]), "code after predictor"
+        results["upre_pos"] = float(np.abs(st["pos"][normal] - u["pos"][normal]).max())
+        results["upre_velrhop"] = rl2(st["velrhop"], u["velrhop"])
+        assert results["upre_pos"] <= tol["pos"] and results["upre_velrhop"] <= tol["state"], results
+        ctx.celldiv(True)
+        d1 = g.stage(step, "div1")
+        st = ctx.download()
+        assert np.array_equal(st["idp"], d1["idp"]) and np.array_equal(ctx.begincell(), d1["begincell"]), "mid-step divide"
+        _, results["fcor"] = check_forces(ctx, g.stage(step, "fcor"), cfg, t2 if noisy else tol, capi.INTERSTEP_SYMCORRECTOR)
+        ctx.step_symcor(dt)
+        u = g.stage(step, "ucor")
+    else:
+        fr, results["fver"] = check_forces(ctx, g.stage(step, "fver"), cfg, t2, capi.INTERSTEP_VERLET)
+        ctx.step_verlet(float(g.stage(step, "fver")["dt"]))
+        u = g.stage(step, "uver")
+    st = ctx.download()
+    normal = (st["code"] & capi.CODE_MASKSPECIAL) != capi.CODE_PERIODIC
+    assert np.array_equal(st["code"], u["code"]), "code after update"
+    results["u_pos"] = float(np.abs(st["pos"][normal] - u["pos"][normal]).max())
+    results["u_velrhop"] = rl2(st["velrhop"], u["velrhop"])
+    # the new cell of a particle may differ only if its position differs (cell boundary crossing by rounding)
+    same = np.all(st["pos"] == u["pos"], axis=1) & normal
+    assert np.array_equal(st["dcell"][same], u["dcell"][same]), "dcell after update"
+    assert results["u_pos"] <= tol["pos"] and results["u_velrhop"] <= tol["state"], results
+    ctx.close()
+    return results
+
+
+def run_trajectory(lib, g: Golden, capacity=0):
+    """Whole-step loop from the initial case for g.nsteps steps; returns drift vs the reference's final state."""
+    cfg = g.cfg
+    ctx = make_ctx(lib, cfg, capacity)
+    z = g.z
+    idp = z["case/idp"]; npb = int(z["case/npb"])
+    code = np.where(idp < cfg.casenfixed, capi.CODE_TYPE_FIXED, capi.CODE_TYPE_FLUID).astype(np.uint16)
+    ctx.upload(idp, z["case/pos"], z["case/velrhop"], npb, code)
+    ctx.celldiv(True)
+    t = 0.0
+    for _ in range(g.nsteps):
+        dt, _ = ctx.step()
+        t += dt
+    fin = g.stage(g.nsteps, "final")
+    st = ctx.download()
+    out = dict(time=abs(t - float(fin["timestep"])) / float(fin["timestep"]), np=(ctx.np_, int(fin["np"])))
+    # compare per particle id (order may differ if a particle crossed a cell boundary by rounding)
+    o1 = np.argsort(st["idp"], kind="stable"); o2 = np.argsort(fin["idp"], kind="stable")
+    if ctx.np_ == int(fin["np"]) and np.array_equal(st["idp"][o1], fin["idp"][o2]):
+        normal = (fin["code"][o2] & capi.CODE_MASKSPECIAL) == capi.CODE_NORMAL
+        out["pos"] = float(np.abs(st["pos"][o1][normal] - fin["pos"][o2][normal]).max())
+        out["velrhop"] = rl2(st["velrhop"][o1][normal], fin["velrhop"][o2][normal])
+        out["order_equal"] = bool(np.array_equal(st["idp"], fin["idp"]))
+    ctx.close()
+    return out
