@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the per-step particle hot path (cell list -> Interaction_Forces -> ComputeStep).
+
+    python bench.py --gpus N --steps K --warmup W [--np NP] [--impl reference]
+
+One "step" = one full Symplectic time step (2 force evaluations, 2 ComputeStep updates, 2 neighbour-list builds) of
+the synthetic 3-D dam-break DB(N) of SURVEY.md 8(d) (BASELINE.json configs[1]: 20 M particles on 1 B200).
+Prints ONE JSON line (contract in the task statement): value = M particle-steps/s with the state resident in HBM,
+timed with CUDA events on the solver's stream; e2e = the same metric through the C ABI with HOST buffers (pinned H2D
+of the particle state + D2H of the result inside the timed region); roofline = gather-byte model of the fluid force
+kernel against the measured HBM copy bandwidth; cpu_baseline = the reference's own OpenMP CPU solver
+(oracle/_ref) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mparticle-steps/s (3D dam-break)"
+UNIT = "Mparticle-steps/s"
+REFBIN = os.path.join(ROOT, "oracle", "_ref", "DualSPHysics5.2CPU_linux64")
+MKCASE = os.path.join(ROOT, "dualsphysics_multilayer_b200", "bin", "mkcase")
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.stop_flag, self.sm, self.maxsm, self.reasons = gpu_index, False, [], 0, set()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                if len(f) >= 6:
+                    self.sm.append(float(f[0])); self.maxsm = float(f[1])
+                    for n, v in zip(names, f[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def result(self):
+        sm = sorted(self.sm)
+        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": self.maxsm or None, "reasons": sorted(self.reasons)}
+
+
+def run_reference(np_sample, nsteps, threads):
+    """Times the reference's own CPU implementation (JSphCpuSingle, OpenMP) on DB(np_sample) for nsteps steps."""
+    if not os.path.exists(REFBIN):
+        return None
+    tmp = tempfile.mkdtemp(prefix="bench_ref_")
+    try:
+        subprocess.check_call([MKCASE, "dambreak", str(np_sample), tmp, "Case"], stdout=subprocess.DEVNULL)
+        r = subprocess.run([REFBIN, "Case", "out", "-cpu", "-ompthreads:%d" % threads, "-sv:none", "-svtimers:1",
+                            "-nsteps:%d" % nsteps], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        txt = r.stdout
+        m1 = re.search(r"Simulation Runtime\.*: ([0-9.eE+-]+) sec", txt)
+        m2 = re.search(r"Steps of simulation\.*: (\d+)", txt)
+        m3 = re.search(r"Particles of simulation \(initial\): (\d+)", txt)
+        if not (m1 and m2 and m3):
+            return None
+        t, steps, npart = float(m1.group(1)), int(m2.group(1)), int(m3.group(1))
+        forces = re.search(r"CF-Forces\.*: ([0-9.eE+-]+) sec", txt)
+        return dict(value=npart * steps / t / 1e6, np=npart, steps=steps, seconds=t,
+                    cf_forces_s=(float(forces.group(1)) if forces else None))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def cpu_baseline(sample_seconds=15.0, steps=3):
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)                      # OMP_MAXTHREADS 64, S/OmpDefs.h:39
+    np_sample = int(min(20_000_000, max(200_000, 0.05e6 * threads * sample_seconds / steps)))
+    r = run_reference(np_sample, steps, threads)
+    if r is None:
+        return {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": "oracle/_ref binary unavailable"}
+    return {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": "reference DualSPHysics5.2 CPU (OpenMP, %d threads): dam-break DB(%d), %d Symplectic steps in %.1f s (CF-Forces %.1f s)"
+                      % (threads, r["np"], r["steps"], r["seconds"], r["cf_forces_s"] or -1)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--np", type=int, default=20_000_000, help="particles per GPU (DB(N))")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pre-steps", type=int, default=0, help="untimed steps before warm-up (to leave the initial lattice)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--force-variant", type=int, default=0)
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        cores = os.cpu_count() or 1
+        threads = min(cores, 64)
+        nsteps = max(1, a.steps + a.warmup)
+        np_sample = int(min(a.np, max(200_000, 0.05e6 * threads * 60.0 / nsteps)))
+        t0 = time.time()
+        r = run_reference(np_sample, nsteps, threads)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/DualSPHysics5.2CPU_linux64 is missing (built by oracle/Makefile where /root/reference is mounted)"}))
+            return
+        sample = ("reference DualSPHysics5.2 CPU solver (OpenMP, %d threads) on dam-break DB(%d) = bounded sample of the %d-particle workload, %d steps, %.1f s"
+                  % (threads, r["np"], a.np, r["steps"], r["seconds"]))
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+                          "warmup": a.warmup, "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "3D dam-break DB(N), Symplectic+Wendland+artificial+DDT2", "np_sample": r["np"], "np_workload": a.np},
+                          "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+                          "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "wall_s": time.time() - t0}))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import dualsphysics_multilayer_b200 as dsph
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    L = dsph.lib()
+    l = L.lib
+    l.dsph_timer_start.argtypes = [C.c_void_p]
+    l.dsph_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    l.dsph_fluid_kernel_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
+
+    cd = dsph.make_case("dambreak", a.np)
+    n = cd.np_
+    code = cd.codes()
+    ctx = dsph.create_context(cd, device=local)
+    if a.force_variant:
+        l.dsph_set_force_variant(ctx.h, a.force_variant)
+    ctx.upload(cd.idp, cd.pos, cd.velrhop, cd.npb, code)
+    ctx.celldiv(True)
+    for _ in range(a.pre_steps):
+        ctx.step()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: W warm-up + K timed steps, CUDA events on the solver's stream
+    for _ in range(a.warmup):
+        ctx.step()
+    tm = dsph.Timers()
+    l.dsph_get_timers(ctx.h, C.byref(tm), 1)
+    l.dsph_fluid_kernel_stats(ctx.h, None, None, 1)
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    L.check(l.dsph_timer_start(ctx.h))
+    pstep = 0
+    for _ in range(a.steps):
+        ctx.step()
+        pstep += ctx.np_
+    ms = C.c_double()
+    L.check(l.dsph_timer_stop(ctx.h, C.byref(ms)))
+    barrier()
+    sampler.stop_flag = True; sampler.join(2.0)
+    l.dsph_get_timers(ctx.h, C.byref(tm), 0)
+    fms = C.c_double(); fnl = C.c_uint64()
+    l.dsph_fluid_kernel_stats(ctx.h, C.byref(fms), C.byref(fnl), 0)
+    t_ms = torch.tensor([ms.value], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(pstep)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    value = tot.item() / (t_ms.item() * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (fluid Interaction_Forces): gather-byte model, SURVEY.md 8(d)
+    ctx.celldiv(False)
+    fr_real, fr_chk, br_real, br_chk = ctx.pips()
+    npf = ctx.np_ - ctx.npb
+    bytes_per_launch = 58.0 * npf + 16.0 * (fr_chk + fr_real)
+    k_ms = fms.value / max(1, fnl.value)
+    peak, peaksrc = measured_peak()
+    achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "ker_forces_fluid", "avg_launch_ms": k_ms, "launches": int(fnl.value),
+                "model": "B_gather = 58*Nf + 16*(N_chk+N_real) bytes per launch (SURVEY.md 8d)",
+                "pairs_per_fluid_particle": {"checked": fr_chk / max(npf, 1), "real": fr_real / max(npf, 1)},
+                "fluid_evals_per_s": npf / (k_ms * 1e-3) if k_ms > 0 else 0.0, "peak_source": peaksrc,
+                "share_of_step": fms.value / ms.value if ms.value > 0 else None}
+
+    # ---- end to end through the C ABI with HOST buffers: H2D of the state, one step, D2H of the result, every step
+    e2e = None
+    if not a.no_e2e:
+        st = ctx.download()
+        hid = torch.from_numpy(st["idp"]).pin_memory(); hcode = torch.from_numpy(st["code"].view(np.int16)).pin_memory()
+        hpos = torch.from_numpy(st["pos"]).pin_memory(); hvr = torch.from_numpy(st["velrhop"]).pin_memory()
+        npb = ctx.npb
+        nn = ctx.np_
+        oid = torch.empty(nn, dtype=torch.int32).pin_memory(); ocode = torch.empty(nn, dtype=torch.int16).pin_memory()
+        opos = torch.empty((nn, 3), dtype=torch.float64).pin_memory(); ovr = torch.empty((nn, 4), dtype=torch.float32).pin_memory()
+        up = L.fn("particles_upload"); down = L.fn("particles_download")
+
+        def e2e_step():
+            L.check(up(ctx.h, nn, npb, C.cast(hid.data_ptr(), C.POINTER(C.c_uint32)), C.cast(hcode.data_ptr(), C.POINTER(C.c_uint16)),
+                       C.cast(hpos.data_ptr(), C.POINTER(C.c_double)), C.cast(hvr.data_ptr(), C.POINTER(C.c_float))))
+            ctx.celldiv(True)
+            ctx.step()
+            m = ctx.np_
+            L.check(down(ctx.h, 0, m, C.cast(oid.data_ptr(), C.POINTER(C.c_uint32)), C.cast(ocode.data_ptr(), C.POINTER(C.c_uint16)), None,
+                         C.cast(opos.data_ptr(), C.POINTER(C.c_double)), C.cast(ovr.data_ptr(), C.POINTER(C.c_float))))
+            return m
+        e2e_step()
+        ke = max(2, min(a.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        L.check(l.dsph_timer_start(ctx.h))
+        pe = 0
+        for _ in range(ke):
+            pe += e2e_step()
+        L.check(l.dsph_timer_stop(ctx.h, C.byref(ms)))
+        barrier()
+        wall = time.perf_counter() - t0
+        te = torch.tensor([max(ms.value * 1e-3, wall)], dtype=torch.float64, device="cuda")
+        pt = torch.tensor([float(pe)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX); dist.all_reduce(pt, op=dist.ReduceOp.SUM)
+        e2e = {"value": pt.item() / te.item() / 1e6, "unit": UNIT, "h2d_bytes_per_step": nn * (4 + 2 + 24 + 16),
+               "d2h_bytes_per_step": nn * (4 + 2 + 24 + 16), "steps": ke,
+               "what": "dsph_particles_upload (pinned host -> device) + dsph_celldiv_run + dsph_step + dsph_particles_download per step"}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+               "ms_per_step": t_ms.item() / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "synthetic 3D dam-break DB(N) (SURVEY.md 8d): Symplectic + Wendland + artificial viscosity 0.1 + DDT2 0.1, DBC walls",
+                          "np_per_gpu": n, "nfluid": int(cd.cfg.casenfluid), "pre_steps": a.pre_steps,
+                          "parallelism": ("single GPU" if world == 1 else "%d independent replicas (x-slab halo exchange not in this round)" % world),
+                          "l2": "working set (np*~230 B) is far larger than the 126 MB L2; no flush needed"},
+               "roofline": roofline, "e2e": e2e, "gpu_launches": int(tm.kernel_launches), "clocks": sampler.result(),
+               "timers_ms_per_step": {k: getattr(tm, k) / a.steps for k in ("nl_limits", "nl_presort", "nl_radixsort", "nl_cellbegin", "nl_sortdata",
+                                                                             "cf_preforces", "cf_forces", "su_computestep")}}
+        if not a.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -98,6 +98,23 @@ int dsph_pips(dsph_ctx *ctx,uint64_t *fr,uint64_t *fc,uint64_t *br,uint64_t *bc)
   NEEDCTX(ctx);
   return Guard([&]{ unsigned long long a,b,c,d; ctx->eng->Pips(&a,&b,&c,&d); if(fr)*fr=a; if(fc)*fc=b; if(br)*br=c; if(bc)*bc=d; });
 }
+// CUDA-event stopwatch on the context's stream (bench.py: torch events do not see this stream)
+int dsph_timer_start(dsph_ctx *ctx){ NEEDCTX(ctx); return Guard([&]{ if(cudaEventRecord(ctx->eng->ev[14],ctx->eng->stm)!=cudaSuccess)throw EngineError(DSPH_ERR_CUDA,"cudaEventRecord"); }); }
+int dsph_timer_stop(dsph_ctx *ctx,double *ms){
+  NEEDCTX(ctx);
+  return Guard([&]{
+    Engine *e=ctx->eng; float f=0;
+    if(cudaEventRecord(e->ev[15],e->stm)!=cudaSuccess || cudaEventSynchronize(e->ev[15])!=cudaSuccess || cudaEventElapsedTime(&f,e->ev[14],e->ev[15])!=cudaSuccess)throw EngineError(DSPH_ERR_CUDA,"cuda event timing failed");
+    if(ms)*ms=f;
+  });
+}
+// accumulated device time and launch count of the fluid force kernel (the dominant kernel) since the last reset
+int dsph_fluid_kernel_stats(dsph_ctx *ctx,double *ms_sum,uint64_t *nlaunch,int reset){
+  NEEDCTX(ctx); Engine *e=ctx->eng;
+  if(ms_sum)*ms_sum=e->fluidms_sum; if(nlaunch)*nlaunch=e->fluid_launches;
+  if(reset){ e->fluidms_sum=0; e->fluid_launches=0; }
+  return DSPH_OK;
+}
 void* dsph_cuda_stream(dsph_ctx *ctx){ return (ctx&&ctx->eng)? (void*)ctx->eng->stm: nullptr; }
 
 // ---- case tooling (host only) ----

@@ -26,6 +26,28 @@ __device__ __forceinline__ unsigned DcCelly(unsigned dcc,unsigned cel){ return (
 __device__ __forceinline__ unsigned DcCellz(unsigned dcc,unsigned cel){ return (cel<<(dcc&31))>>(dcc&31); }
 __device__ __forceinline__ unsigned DcCell(unsigned dcc,unsigned cx,unsigned cy,unsigned cz){ return (cx<<((dcc>>10)&31))|(cy<<((dcc>>15)&31))|cz; }
 
+// First cell hash of uploaded particles: JSph::LoadDcellParticles (S/JSph.cpp:1690-1711), periodic duplicates of a
+// restarted state follow PeriodicDuplicatePos (S/JSphCpuSingle.cpp:232-251).  nout counts valid particles out of the domain.
+__global__ void __launch_bounds__(DIV_THREADS) ker_upload_dcell(unsigned n,const double* __restrict__ pos,const typecode* __restrict__ code,
+  unsigned* __restrict__ dcell,unsigned* __restrict__ nout,DevCtes c,double rminx,double rminy,double rminz,double rmaxx,double rmaxy,double rmaxz)
+{
+  const unsigned p=blockIdx.x*blockDim.x+threadIdx.x;
+  if(p>=n)return;
+  const unsigned sp=code[p]&DSPH_CODE_MASKSPECIAL;
+  unsigned cell=0xFFFFFFFFu;
+  if(sp<DSPH_CODE_OUTIGNORE){
+    const double x=pos[3*size_t(p)],y=pos[3*size_t(p)+1],z=pos[3*size_t(p)+2];
+    unsigned cx=unsigned((x-c.domposmin[0])/c.scell_d), cy=unsigned((y-c.domposmin[1])/c.scell_d), cz=unsigned((z-c.domposmin[2])/c.scell_d);
+    if(sp==DSPH_CODE_PERIODIC){
+      cx=(cx<=c.domcells[0]? cx: c.domcells[0]); cy=(cy<=c.domcells[1]? cy: c.domcells[1]); cz=(cz<=c.domcells[2]? cz: c.domcells[2]);
+      cell=DcCell(c.domcellcode,cx,cy,cz);
+    }
+    else if(x>=rminx && y>=rminy && z>=rminz && x<rmaxx && y<rmaxy && z<rmaxz)cell=DcCell(c.domcellcode,cx,cy,cz);
+    else atomicAdd(nout,1u);
+  }
+  dcell[p]=cell;
+}
+
 // limits[0..2]=min (init UINT_MAX), limits[3..5]=max (init 0)
 __global__ void __launch_bounds__(DIV_THREADS) ker_div_limits(unsigned n,unsigned pini,const unsigned* __restrict__ dcell,
   const typecode* __restrict__ code,unsigned domcellcode,unsigned* __restrict__ limits)

@@ -7,6 +7,7 @@
 #include "celldiv.cuh"
 #include "forces.cuh"
 #include "forces_v2.cuh"
+#include "forces_v3.cuh"
 #include "step.cuh"
 #include "periodic.cuh"
 #include <cstdio>
@@ -131,32 +132,20 @@ void Engine::Upload(unsigned np_,unsigned npb_,const unsigned *hidp,const typeco
     for(unsigned p=0;p<np;p++)tmpcode[p]=typecode(hidp[p]<cfg.casenfixed? DSPH_CODE_TYPE_FIXED: DSPH_CODE_TYPE_FLUID);
     hcode=tmpcode.data();
   }
-  // JSph::LoadDcellParticles (S/JSph.cpp:1690-1711): first cell hash on the host, identical double arithmetic
-  std::vector<unsigned> hdcell(np);
-  for(unsigned p=0;p<np;p++){
-    if((hcode[p]&DSPH_CODE_MASKSPECIAL)<DSPH_CODE_OUTIGNORE){
-      const double x=hpos[3*size_t(p)],y=hpos[3*size_t(p)+1],z=hpos[3*size_t(p)+2];
-      if((hcode[p]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_PERIODIC){   // restart of a state that still holds periodic duplicates
-        unsigned cx=unsigned((x-k.domposmin[0])/k.scell), cy=unsigned((y-k.domposmin[1])/k.scell), cz=unsigned((z-k.domposmin[2])/k.scell);
-        cx=(cx<=k.domcells[0]? cx: k.domcells[0]); cy=(cy<=k.domcells[1]? cy: k.domcells[1]); cz=(cz<=k.domcells[2]? cz: k.domcells[2]);
-        hdcell[p]=DcelCell(k.domcellcode,cx,cy,cz);
-        continue;
-      }
-      const bool in=(x>=k.domrealposmin[0] && y>=k.domrealposmin[1] && z>=k.domrealposmin[2] && x<k.domrealposmax[0] && y<k.domrealposmax[1] && z<k.domrealposmax[2]);
-      if(!in)throw EngineError(DSPH_ERR_PHYSICS,"Found new particles out.");
-      const unsigned cx=unsigned((x-k.domposmin[0])/k.scell), cy=unsigned((y-k.domposmin[1])/k.scell), cz=unsigned((z-k.domposmin[2])/k.scell);
-      hdcell[p]=DcelCell(k.domcellcode,cx,cy,cz);
-    }
-    else hdcell[p]=0xFFFFFFFFu;
-  }
   CUCHECK(cudaMemcpyAsync(idp[cur],hidp,size_t(np)*4,cudaMemcpyHostToDevice,stm));
   CUCHECK(cudaMemcpyAsync(code[cur],hcode,size_t(np)*2,cudaMemcpyHostToDevice,stm));
-  CUCHECK(cudaMemcpyAsync(dcell[cur],hdcell.data(),size_t(np)*4,cudaMemcpyHostToDevice,stm));
   CUCHECK(cudaMemcpyAsync(pos[cur],hpos,size_t(np)*24,cudaMemcpyHostToDevice,stm));
   CUCHECK(cudaMemcpyAsync(velrhop[cur],hvelrhop,size_t(np)*16,cudaMemcpyHostToDevice,stm));
   if(cfg.tstep==DSPH_STEP_VERLET)CUCHECK(cudaMemcpyAsync(velrhopm1[cur],hvelrhop,size_t(np)*16,cudaMemcpyHostToDevice,stm));
   if(cfg.tvisco==DSPH_VISCO_LAMINARSPS)CUCHECK(cudaMemsetAsync(spstau[cur],0,size_t(np)*24,stm));
+  // JSph::LoadDcellParticles (S/JSph.cpp:1690-1711): first cell hash, same double arithmetic, on the device
+  CUCHECK(cudaMemsetAsync(limits,0,4,stm));
+  if(np){ ker_upload_dcell<<<(np+255)/256,256,0,stm>>>(np,pos[cur],code[cur],dcell[cur],limits,dc,
+      k.domrealposmin[0],k.domrealposmin[1],k.domrealposmin[2],k.domrealposmax[0],k.domrealposmax[1],k.domrealposmax[2]); launches++; }
+  CUCHECK(cudaMemcpyAsync(&hpin->scratch[0],limits,4,cudaMemcpyDeviceToHost,stm));
   CUCHECK(cudaStreamSynchronize(stm));
+  CUCHECK(cudaGetLastError());
+  if(hpin->scratch[0])throw EngineError(DSPH_ERR_PHYSICS,"Found new particles out.");
   symplecticdtpre=k.dtini; verletstep=0; forcesok=false;
 }
 
@@ -352,7 +341,8 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> static void LaunchFluid(int va
   if(variant==1){
     ker_forces_fluid_v1<TKER,TVISCO,TDDT,SHIFT><<<(npf+FORCES_THREADS-1)/FORCES_THREADS,FORCES_THREADS,0,stm>>>(t,c);
   }
-  else LaunchFluidV2<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm);
+  else if(variant==2)LaunchFluidV2<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm);
+  else LaunchFluidV3<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm);
 }
 template<int TKER,int TVISCO,int TDDT> static void LaunchFluid3(int variant,bool shift,unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm){
   if(shift)LaunchFluid<TKER,TVISCO,TDDT,true>(variant,npf,t,c,stm); else LaunchFluid<TKER,TVISCO,TDDT,false>(variant,npf,t,c,stm);
@@ -389,6 +379,7 @@ void Engine::Forces(int interstep,dsph_forceres *res){
     launches++;
     if(cfg.tvisco==DSPH_VISCO_LAMINARSPS){ ker_sps_tau<<<(npf+255)/256,256,0,stm>>>(npf,npb,velrhop[cur],spsgradvel,spstau[cur],dc); launches++; }
   }
+  CUCHECK(cudaEventRecord(ev[13],stm));
   if(npb){
     const unsigned nb=(npb+FORCES_THREADS-1)/FORCES_THREADS;
     if(cfg.tkernel==DSPH_KERNEL_WENDLAND)ker_forces_bound_v1<DSPH_KERNEL_WENDLAND><<<nb,FORCES_THREADS,0,stm>>>(t,dc);
@@ -399,7 +390,8 @@ void Engine::Forces(int interstep,dsph_forceres *res){
   CUCHECK(cudaMemcpyAsync(&hpin->fmax,fmax,sizeof(ForceMax),cudaMemcpyDeviceToHost,stm));
   CUCHECK(cudaStreamSynchronize(stm));
   CUCHECK(cudaGetLastError());
-  { float ms=0; cudaEventElapsedTime(&ms,ev[8],ev[9]); tm.cf_preforces+=ms; cudaEventElapsedTime(&ms,ev[9],ev[10]); tm.cf_forces+=ms; tm.total+=ms; lastforcems=ms; }
+  { float ms=0; cudaEventElapsedTime(&ms,ev[8],ev[9]); tm.cf_preforces+=ms; cudaEventElapsedTime(&ms,ev[9],ev[10]); tm.cf_forces+=ms; tm.total+=ms; lastforcems=ms;
+    cudaEventElapsedTime(&ms,ev[9],ev[13]); lastfluidms=ms; fluidms_sum+=ms; fluid_launches++; }
   const ForceMax &m=hpin->fmax;
   float f; unsigned b;
   b=m.viscdt_bits; memcpy(&f,&b,4); viscdtmax=f;

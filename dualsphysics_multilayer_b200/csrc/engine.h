@@ -49,8 +49,8 @@ class Engine {
   unsigned npfout_last=0; unsigned long long npout_total=0;
   // forces
   ForceMax *fmax=nullptr;
-  float viscdtmax=0; double acemax=0, velmax=0; float lastforcems=0;
-  int forcevariant=2;
+  float viscdtmax=0; double acemax=0, velmax=0; float lastforcems=0, lastfluidms=0; double fluidms_sum=0; unsigned long long fluid_launches=0;
+  int forcevariant=3;
   // time stepping
   double symplecticdtpre=0; int verletstep=0;
   dsph_timers tm={}; unsigned long long launches=0;

@@ -198,6 +198,15 @@ int dsph_step(dsph_ctx *ctx,double *stepdt,dsph_forceres *res);
 double dsph_symplectic_dtpre(const dsph_ctx *ctx);
 int dsph_set_symplectic_dtpre(dsph_ctx *ctx,double dt);
 int dsph_get_timers(dsph_ctx *ctx,dsph_timers *t,int reset);
+/* CUDA-event stopwatch on the context's own stream (JTimerCuda S/JTimerCuda.h) and statistics of the dominant
+ * kernel (fluid Interaction_Forces): accumulated device ms and number of launches since the last reset. */
+int dsph_timer_start(dsph_ctx *ctx);
+int dsph_timer_stop(dsph_ctx *ctx,double *ms);
+int dsph_fluid_kernel_stats(dsph_ctx *ctx,double *ms_sum,uint64_t *nlaunch,int reset);
+/* selects the force-kernel implementation: 1 plain one-thread-per-particle loop, 2 tuned (default) */
+int dsph_set_force_variant(dsph_ctx *ctx,int variant);
+int dsph_set_verletstep(dsph_ctx *ctx,int verletstep);
+double dsph_last_force_ms(const dsph_ctx *ctx);
 /* pair counters of the last force evaluation (JDsPips, S/JDsPips_ker.cu:66): real & checked pairs
  * for fluid and boundary particles; used by the roofline byte model. */
 int dsph_pips(dsph_ctx *ctx,uint64_t *fluid_real,uint64_t *fluid_checked,uint64_t *bound_real,uint64_t *bound_checked);
