@@ -13,6 +13,7 @@ struct DevCtes {
   // kernel (S/FunSphKernel.h:50-80,199-210)
   float kernelh, ovkernelh, kernelsize2, eta2, awen, bwen;
   float cub_a2, cub_a24, cub_c1, cub_d1, cub_c2, cub_od_wdeltap;
+  float bwen_ovh, cub_c1_ovh, cub_d1_ovh;   // kernel constants divided by h (division-free gradient, forces_v3.cuh)
   // EOS / masses
   float cteb, gamma, ovgamma, rhopzero, ovrhopzero, massfluid, massbound;
   double cteb_d, gamma_d;

@@ -55,6 +55,7 @@ void Engine::Configure(const dsph_config &c){
   memset(&dc,0,sizeof(dc));
   dc.kernelh=cfg.kernelh; dc.ovkernelh=1.f/cfg.kernelh; dc.kernelsize2=k.kernelsize2; dc.eta2=k.eta2; dc.awen=k.awen; dc.bwen=k.bwen;
   dc.cub_a2=k.cub_a2; dc.cub_a24=k.cub_a24; dc.cub_c1=k.cub_c1; dc.cub_d1=k.cub_d1; dc.cub_c2=k.cub_c2; dc.cub_od_wdeltap=k.cub_od_wdeltap;
+  dc.bwen_ovh=float(double(k.bwen)/double(cfg.kernelh)); dc.cub_c1_ovh=float(double(k.cub_c1)/double(cfg.kernelh)); dc.cub_d1_ovh=float(double(k.cub_d1)/double(cfg.kernelh));
   dc.cteb=cfg.cteb; dc.gamma=cfg.gamma; dc.ovgamma=1.f/cfg.gamma; dc.rhopzero=cfg.rhopzero; dc.ovrhopzero=1.0f/cfg.rhopzero;
   dc.massfluid=cfg.massfluid; dc.massbound=cfg.massbound; dc.cteb_d=double(cfg.cteb); dc.gamma_d=double(cfg.gamma);
   dc.cs0=float(k.cs0); dc.visco=cfg.visco; dc.viscobound=cfg.visco*cfg.viscoboundfactor; dc.ddtkh=k.ddtkh; dc.ddtgz=k.ddtgz;
@@ -342,6 +343,7 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> static void LaunchFluid(int va
     ker_forces_fluid_v1<TKER,TVISCO,TDDT,SHIFT><<<(npf+FORCES_THREADS-1)/FORCES_THREADS,FORCES_THREADS,0,stm>>>(t,c);
   }
   else if(variant==2)LaunchFluidV2<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm);
+  else if(variant==4)LaunchFluidV4<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm);
   else LaunchFluidV3<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm);
 }
 template<int TKER,int TVISCO,int TDDT> static void LaunchFluid3(int variant,bool shift,unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm){

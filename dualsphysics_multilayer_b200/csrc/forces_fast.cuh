@@ -1,0 +1,191 @@
+// forces_fast.cuh -- division-free pair body + the production one-thread-per-particle kernel (variant 4).
+//
+// ncu on the plain kernel (profiles/r01_forces.md): issue-bound (81 % issue active), and two thirds of the issued
+// instructions are the eight IEEE divisions + sqrt of the pair body (each a MUFU + Newton + FCHK slow-path sequence,
+// ~17 instructions).  The reference's own CUDA build uses -use_fast_math (S/Makefile:159); here the algebra is
+// rearranged so that one pair needs exactly 1 MUFU.RSQ + 3 MUFU.RCP and no division sequence at all:
+//   fac      = bwen*qq*w^3/rad with qq=rad/h      ->  (bwen/h)*w^3                 (exact algebra, no division)
+//   rad      = sqrt(rr2)                           ->  rr2*rsqrt(rr2)
+//   x/rho2 (3 uses), x/(rr2+eta2) (2 uses), x/robar ->  one reciprocal each, 1/rho1 hoisted per particle
+// Relative error of MUFU.RCP/RSQ is ~1 ulp; the terms are independent per pair, so the effect on Ace/Ar is far below the
+// 1e-5 tolerance (measured in tests/test_gpu_parity.py against the reference dumps).
+#pragma once
+#include "forces.cuh"
+
+namespace dsph {
+
+__device__ __forceinline__ float FastRcp(float x){ float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float FastRsqrt(float x){ float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+struct FastP1 { float4 velrhop; float press, ovrhop; };
+
+// Accumulates one accepted pair.  boundp2 may be a per-lane value (v3) or a literal (v4: constant-folded).
+template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ void PairFast(
+  float drx,float dry,float drz,float rr2,const FastP1 &p1,const float4 &velrhop2,float pressp2,bool boundp2,
+  const float* __restrict__ taup1,const float* __restrict__ taup2,unsigned codep2,const DevCtes &c,PairAcc &a,unsigned &anybound,unsigned &noshiftf)
+{
+  const float massp2=(boundp2? c.massbound: c.massfluid);
+  const float visco=(boundp2? c.viscobound: c.visco);
+  // (a Newton step on the MUFU.RSQ seed was measured: +2 % time, no change of the Ace/Ar difference to the IEEE kernel,
+  //  which is set by the fp32 conditioning of the pressure sum, not by the approximations)
+  const float rinv=FastRsqrt(rr2);
+  const float rad=rr2*rinv;
+  const float qq=rad*c.ovkernelh;
+  float fac;
+  if(TKER==DSPH_KERNEL_WENDLAND){
+    const float wqq1=1.f-0.5f*qq;
+    fac=c.bwen_ovh*(wqq1*wqq1*wqq1);
+  }
+  else{
+    if(rad>c.kernelh){ const float wqq1=2.0f-qq; fac=c.cub_c2*(wqq1*wqq1)*rinv; }
+    else fac=c.cub_c1_ovh+c.cub_d1_ovh*qq;
+  }
+  const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
+  const float rhopp1=p1.velrhop.w;
+  const float ov2=FastRcp(velrhop2.w);
+  {
+    float prs=(p1.press+pressp2)*(p1.ovrhop*ov2);
+    if(TKER==DSPH_KERNEL_CUBIC){
+      float wab;
+      if(rad>c.kernelh){ const float wqq1=2.0f-qq; wab=c.cub_a24*(wqq1*wqq1*wqq1); }
+      else wab=c.cub_a2*(1.0f+(0.75f*qq-1.5f)*(qq*qq));
+      float fab=wab*c.cub_od_wdeltap; fab*=fab; fab*=fab;
+      const float t1=(p1.press*p1.ovrhop*p1.ovrhop)*(p1.press>0? 0.01f: -0.2f);
+      const float t2=(pressp2*ov2*ov2)*(pressp2>0? 0.01f: -0.2f);
+      prs+=fab*(t1+t2);
+    }
+    const float p_vpm=-prs*massp2;
+    a.ax+=p_vpm*frx; a.ay+=p_vpm*fry; a.az+=p_vpm*frz;
+  }
+  const float dvx=p1.velrhop.x-velrhop2.x, dvy=p1.velrhop.y-velrhop2.y, dvz=p1.velrhop.z-velrhop2.z;
+  a.ar+=massp2*(dvx*frx+dvy*fry+dvz*frz)*(rhopp1*ov2);
+  const float ovrr=FastRcp(rr2+c.eta2);
+  const float cbar=c.cs0;
+  if(TDDT==DSPH_DDT_DDT){
+    if(boundp2)anybound=1u;
+    else{
+      // rho1/rho2-1 cancels to ~1e-4: the oracle's value is dominated by the rounding of the IEEE quotient, so this one
+      // division is kept correctly rounded (an approximate reciprocal here changed Ar by 6e-5 in the periodic box).
+      const float visc_densi=c.ddtkh*cbar*(__fdiv_rn(rhopp1,velrhop2.w)-1.f)*ovrr;
+      const float dot3=(drx*frx+dry*fry+drz*frz);
+      a.delta+=visc_densi*dot3*massp2;
+    }
+  }
+  if(TDDT==DSPH_DDT_DDT2 || TDDT==DSPH_DDT_DDT2FULL){
+    if(boundp2){ if(TDDT==DSPH_DDT_DDT2)anybound=1u; }
+    else{
+      const float rh=1.f+c.ddtgz*drz;
+      const float drhop=c.rhopzero*PowNearOne(rh,c)-c.rhopzero;
+      const float visc_densi=c.ddtkh*cbar*((velrhop2.w-rhopp1)-drhop)*ovrr;
+      const float dot3=(drx*frx+dry*fry+drz*frz);
+      a.delta-=visc_densi*dot3*massp2*ov2;
+    }
+  }
+  if(SHIFT){
+    const float massrhop=massp2*ov2;
+    if(boundp2 && (c.shiftmode==DSPH_SHIFT_NOBOUND || (c.shiftmode==DSPH_SHIFT_NOFIXED && (codep2&DSPH_CODE_MASKTYPE)==DSPH_CODE_TYPE_FIXED)))noshiftf=1u;
+    a.shift.x+=massrhop*frx; a.shift.y+=massrhop*fry; a.shift.z+=massrhop*frz;
+    a.shift.w-=massrhop*(drx*frx+dry*fry+drz*frz);
+  }
+  {
+    const float dot=drx*dvx+dry*dvy+drz*dvz;
+    const float dot_rr2=dot*ovrr;
+    a.visc=fmaxf(dot_rr2,a.visc);
+    if(TVISCO==DSPH_VISCO_ARTIFICIAL){
+      if(dot<0){
+        const float amubar=c.kernelh*dot_rr2;
+        const float ovrobar=FastRcp((rhopp1+velrhop2.w)*0.5f);
+        const float pi_visc=(-visco*cbar*amubar*ovrobar)*massp2;
+        a.ax-=pi_visc*frx; a.ay-=pi_visc*fry; a.az-=pi_visc*frz;
+      }
+    }
+    else{
+      {
+        const float temp=4.f*visco*ovrr*FastRcp(rhopp1+velrhop2.w);
+        const float vtemp=massp2*temp*(drx*frx+dry*fry+drz*frz);
+        a.ax+=vtemp*dvx; a.ay+=vtemp*dvy; a.az+=vtemp*dvz;
+      }
+      float tau_xx=taup1[0],tau_xy=taup1[1],tau_xz=taup1[2],tau_yy=taup1[3],tau_yz=taup1[4],tau_zz=taup1[5];
+      if(!boundp2){ tau_xx+=taup2[0]; tau_xy+=taup2[1]; tau_xz+=taup2[2]; tau_yy+=taup2[3]; tau_yz+=taup2[4]; tau_zz+=taup2[5]; }
+      a.ax+=massp2*(tau_xx*frx+tau_xy*fry+tau_xz*frz);
+      a.ay+=massp2*(tau_xy*frx+tau_yy*fry+tau_yz*frz);
+      a.az+=massp2*(tau_xz*frx+tau_yz*fry+tau_zz*frz);
+      const float volp2=-massp2*ov2;
+      float dv=dvx*volp2; a.gxx+=dv*frx; a.gxy+=dv*fry; a.gxz+=dv*frz;
+            dv=dvy*volp2; a.gxy+=dv*frx; a.gyy+=dv*fry; a.gyz+=dv*frz;
+            dv=dvz*volp2; a.gxz+=dv*frx; a.gyz+=dv*fry; a.gzz+=dv*frz;
+    }
+  }
+}
+
+// ---- variant 4: the plain loop structure (oracle pair order) with the division-free body ----
+template<int TKER,int TVISCO,int TDDT,bool SHIFT> __global__ void __launch_bounds__(FORCES_THREADS)
+ker_forces_fluid_v4(ForceParams t,DevCtes c)
+{
+  const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
+  float viscmax=0,ace2=0,vel2=0;
+  if(p1<t.np){
+    const float4 pp1=t.posp[p1];
+    FastP1 q; q.velrhop=t.velrhop[p1]; q.press=pp1.w; q.ovrhop=1.f/q.velrhop.w;
+    float taup1[6]={0,0,0,0,0,0};
+    if(TVISCO==DSPH_VISCO_LAMINARSPS){
+      #pragma unroll
+      for(int k=0;k<6;k++)taup1[k]=t.spstau[6*size_t(p1)+k];
+    }
+    const NgRange ng=NgInit(t.dcell[p1],t,c);
+    PairAcc a; ZeroAcc(a);
+    unsigned anybound=0,noshiftf=0;
+    #pragma unroll 1
+    for(int pass=0;pass<2;pass++){
+      const bool boundp2=(pass==1);
+      const unsigned cellinit=(boundp2? 0u: t.cellfluid);
+      for(int z=ng.zini;z<ng.zfin;z++){
+        const float oz=pp1.z-float(z-ng.cz)*c.scell;
+        for(int y=ng.yini;y<ng.yfin;y++){
+          const float oy=pp1.y-float(y-ng.cy)*c.scell;
+          const unsigned v=unsigned(t.nsheet*z+t.ncx*y)+cellinit;
+          unsigned pini=t.begincell[v+ng.cxini];
+          for(int x=ng.cxini;x<ng.cxfin;x++){
+            const unsigned pfin=t.begincell[v+x+1];
+            const float ox=pp1.x-float(x-ng.cx)*c.scell;
+            for(unsigned p2=pini;p2<pfin;p2++){
+              const float4 pp2=__ldg(&t.posp[p2]);
+              const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
+              const float rr2=drx*drx+dry*dry+drz*drz;
+              if(rr2<=c.kernelsize2 && rr2>=1e-18f){
+                const float4 velrhop2=__ldg(&t.velrhop[p2]);
+                unsigned codep2=0; if(SHIFT && boundp2)codep2=t.code[p2];
+                const float *taup2=(TVISCO==DSPH_VISCO_LAMINARSPS && !boundp2? t.spstau+6*size_t(p2): nullptr);
+                PairFast<TKER,TVISCO,TDDT,SHIFT>(drx,dry,drz,rr2,q,velrhop2,pp2.w,boundp2,taup1,taup2,codep2,c,a,anybound,noshiftf);
+              }
+            }
+            pini=pfin;
+          }
+        }
+      }
+    }
+    float ar=a.ar, ax=a.ax, ay=a.ay, az=a.az;
+    if(c.simulate2d)ay=0;
+    if(TDDT!=DSPH_DDT_NONE && !anybound)ar+=a.delta;
+    t.acear[p1]=make_float4(ax,ay,az,ar);
+    if(SHIFT){ float4 s=a.shift; if(noshiftf)s.x=FLT_MAX; t.shiftposfs[p1]=s; }
+    if(TVISCO==DSPH_VISCO_LAMINARSPS){
+      const float g[6]={a.gxx,a.gxy,a.gxz,a.gyy,a.gyz,a.gzz};
+      #pragma unroll
+      for(int k=0;k<6;k++)t.spsgradvel[6*size_t(p1)+k]=g[k];
+    }
+    viscmax=a.visc;
+    const bool normal=(!c.periactive || (t.code[p1]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
+    if(normal)ace2=ax*ax+ay*ay+az*az;
+    vel2=q.velrhop.x*q.velrhop.x+q.velrhop.y*q.velrhop.y+q.velrhop.z*q.velrhop.z;
+  }
+  WarpMaxToGlobal(viscmax,&t.fmax->viscdt_bits);
+  WarpMaxToGlobal(ace2,&t.fmax->ace2_bits);
+  WarpMaxToGlobal(vel2,&t.fmax->vel2_bits);
+}
+
+template<int TKER,int TVISCO,int TDDT,bool SHIFT> static void LaunchFluidV4(unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm){
+  ker_forces_fluid_v4<TKER,TVISCO,TDDT,SHIFT><<<(npf+FORCES_THREADS-1)/FORCES_THREADS,FORCES_THREADS,0,stm>>>(t,c);
+}
+
+} // namespace dsph
