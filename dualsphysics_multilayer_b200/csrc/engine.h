@@ -50,7 +50,7 @@ class Engine {
   // forces
   ForceMax *fmax=nullptr;
   float viscdtmax=0; double acemax=0, velmax=0; float lastforcems=0, lastfluidms=0; double fluidms_sum=0; unsigned long long fluid_launches=0;
-  int forcevariant=4;
+  int forcevariant=5;
   // time stepping
   double symplecticdtpre=0; int verletstep=0;
   dsph_timers tm={}; unsigned long long launches=0;

@@ -1,0 +1,145 @@
+// forces_v5.cuh -- fluid Interaction_Forces with a deferred pair ring (variant 5).
+//
+// ncu on variant 4 (profiles/r01_forces.md): issue bound, and 68 % of the issue slots go to the pair body executed with only
+// 8.9 of 32 lanes active (a warp's 32 particles fill most of a 2h cell, so a candidate is inside the cut-off of a few
+// lanes only; 620 body executions per warp for 173 accepted pairs per particle).  Here the body is deferred:
+//   TEST   the broadcast candidate loop of variant 4 (one thread per particle, oracle pair order) only tests the distance and
+//          pushes accepted neighbours as 4-byte entries {particle index : 26 bits | neighbour-cell code : 6 bits} into the
+//          lane's own 64-deep ring in shared memory (q[slot][lane]: conflict free, 32 KB per 128-thread block),
+//   PAIR   when some lane's ring is nearly full every lane pops one entry, re-reads posp/velrhop of that neighbour (L1/L2
+//          hits), rebuilds dr with exactly the operations of the test and runs the division-free pair body.
+// A ring of 64 evens out the bursts (tools/simq.py: 227 rounds per warp with 24.5 lanes active instead of 620 with 8.9).
+// The ring is FIFO per lane, so the summation order per particle is the oracle's and the result is bit-identical to
+// variant 4.  Control flow is warp uniform (fixed 3x3x3 cell loops, trip counts by redux.sync) so that the votes are legal.
+// Limits: cells of size 2h (ScellDiv=1) and np < 2^26 per GPU; otherwise variant 4 is used.
+#pragma once
+#include "forces_fast.cuh"
+
+namespace dsph {
+
+constexpr int V5_CH=8;
+constexpr unsigned V5_IDXMASK=(1u<<26)-1u;
+
+template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __device__ __forceinline__ void V5Round(
+  unsigned* __restrict__ q,unsigned &head,unsigned tail,const float4 &pp1,const FastP1 &fp,const float* taup1,bool boundp2,
+  const ForceParams &t,const DevCtes &c,PairAcc &a,unsigned &anyb,unsigned &nosh)
+{
+  if(head!=tail){
+    const unsigned e=q[(head&(V5_Q-1))*FORCES_THREADS];
+    head++;
+    const unsigned p2=e&V5_IDXMASK;
+    const unsigned code=e>>26;
+    const float fdx=float(int(code&3u))-1.f, fdy=float(int((code>>2)&3u))-1.f, fdz=float(int(code>>4))-1.f;
+    const float ox=pp1.x-fdx*c.scell, oy=pp1.y-fdy*c.scell, oz=pp1.z-fdz*c.scell;
+    const float4 pp2=__ldg(&t.posp[p2]);
+    const float4 vr2=__ldg(&t.velrhop[p2]);
+    const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
+    const float rr2=drx*drx+dry*dry+drz*drz;
+    unsigned codep2=0; if(SHIFT && boundp2)codep2=t.code[p2];
+    const float *taup2=(TVISCO==DSPH_VISCO_LAMINARSPS && !boundp2? t.spstau+6*size_t(p2): nullptr);
+    PairFast<TKER,TVISCO,TDDT,SHIFT>(drx,dry,drz,rr2,fp,vr2,pp2.w,boundp2,taup1,taup2,codep2,c,a,anyb,nosh);
+  }
+}
+
+template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __global__ void __launch_bounds__(FORCES_THREADS,(V5_Q>=128? 3: (V5_Q>=64? 6: 8)))
+ker_forces_fluid_v5(ForceParams t,DevCtes c)
+{
+  __shared__ unsigned qsm[V5_Q*FORCES_THREADS];
+  unsigned *q=qsm+threadIdx.x;
+  const unsigned FULL=0xffffffffu;
+  const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
+  const bool active=(p1<t.np);
+  const unsigned p1c=(active? p1: t.np-1);
+  const float4 pp1=t.posp[p1c];
+  FastP1 fp; fp.velrhop=t.velrhop[p1c]; fp.press=pp1.w; fp.ovrhop=1.f/fp.velrhop.w;
+  const unsigned rcell=t.dcell[p1c];
+  const int cx=int(DcCellx(c.domcellcode,rcell))-int(t.cellzero[0]);
+  const int cy=int(DcCelly(c.domcellcode,rcell))-int(t.cellzero[1]);
+  const int cz=int(DcCellz(c.domcellcode,rcell))-int(t.cellzero[2]);
+  float taup1[6]={0,0,0,0,0,0};
+  if(TVISCO==DSPH_VISCO_LAMINARSPS){
+    #pragma unroll
+    for(int k=0;k<6;k++)taup1[k]=t.spstau[6*size_t(p1c)+k];
+  }
+  const unsigned plast=t.np-1;
+  const float ks2=c.kernelsize2, scell=c.scell;
+  PairAcc a; ZeroAcc(a);
+  unsigned anyb=0,nosh=0,head=0,tail=0;
+  #pragma unroll 1
+  for(int pass=0;pass<2;pass++){
+    const bool boundp2=(pass==1);
+    const unsigned cellinit=(boundp2? 0u: t.cellfluid);
+    #pragma unroll 1
+    for(int dz=-1;dz<=1;dz++){
+      const int z=cz+dz;
+      const float oz=pp1.z-float(dz)*scell;
+      #pragma unroll 1
+      for(int dy=-1;dy<=1;dy++){
+        const int y=cy+dy;
+        const float oy=pp1.y-float(dy)*scell;
+        const bool rowok=(active && z>=0 && z<t.ncz && y>=0 && y<t.ncy);
+        #pragma unroll 1
+        for(int dx=-1;dx<=1;dx++){
+          const int x=cx+dx;
+          const float ox=pp1.x-float(dx)*scell;
+          unsigned pini=0,pfin=0;
+          if(rowok && x>=0 && x<t.ncx){
+            const unsigned v=unsigned(t.nsheet*z+t.ncx*y+x)+cellinit;
+            pini=t.begincell[v]; pfin=t.begincell[v+1];
+          }
+          const unsigned nmax=__reduce_max_sync(FULL,pfin-pini);
+          const unsigned codebits=(unsigned(dx+1)|(unsigned(dy+1)<<2)|(unsigned(dz+1)<<4))<<26;
+          for(unsigned i=0;i<nmax;i+=V5_CH){
+            while(__any_sync(FULL,(tail-head)>unsigned(V5_Q-V5_CH)))
+              V5Round<TKER,TVISCO,TDDT,SHIFT,V5_Q>(q,head,tail,pp1,fp,taup1,boundp2,t,c,a,anyb,nosh);
+            #pragma unroll
+            for(int u=0;u<V5_CH;u++){
+              const unsigned p2=pini+i+u;
+              const float4 pp2=__ldg(&t.posp[min(p2,plast)]);
+              const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
+              const float rr2=drx*drx+dry*dry+drz*drz;
+              if(p2<pfin && rr2<=ks2 && rr2>=1e-18f){
+                q[(tail&(V5_Q-1))*FORCES_THREADS]=p2|codebits;
+                tail++;
+              }
+            }
+          }
+        }
+      }
+    }
+    // end of the pass: the boundary pass uses other constants, drain everything
+    while(__any_sync(FULL,head!=tail))
+      V5Round<TKER,TVISCO,TDDT,SHIFT,V5_Q>(q,head,tail,pp1,fp,taup1,boundp2,t,c,a,anyb,nosh);
+  }
+  float viscmax=0,ace2=0,vel2=0;
+  if(active){
+    float ar=a.ar, ax=a.ax, ay=a.ay, az=a.az;
+    if(c.simulate2d)ay=0;
+    if(TDDT!=DSPH_DDT_NONE && !anyb)ar+=a.delta;
+    t.acear[p1]=make_float4(ax,ay,az,ar);
+    if(SHIFT){ float4 s=a.shift; if(nosh)s.x=FLT_MAX; t.shiftposfs[p1]=s; }
+    if(TVISCO==DSPH_VISCO_LAMINARSPS){
+      const float g[6]={a.gxx,a.gxy,a.gxz,a.gyy,a.gyz,a.gzz};
+      #pragma unroll
+      for(int k=0;k<6;k++)t.spsgradvel[6*size_t(p1)+k]=g[k];
+    }
+    viscmax=a.visc;
+    const bool normal=(!c.periactive || (t.code[p1]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
+    if(normal)ace2=ax*ax+ay*ay+az*az;
+    vel2=fp.velrhop.x*fp.velrhop.x+fp.velrhop.y*fp.velrhop.y+fp.velrhop.z*fp.velrhop.z;
+  }
+  WarpMaxToGlobal(viscmax,&t.fmax->viscdt_bits);
+  WarpMaxToGlobal(ace2,&t.fmax->ace2_bits);
+  WarpMaxToGlobal(vel2,&t.fmax->vel2_bits);
+}
+
+template<int TKER,int TVISCO,int TDDT,bool SHIFT> static void LaunchFluidV5(unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm,int qdepth=64){
+  const unsigned nb=(npf+FORCES_THREADS-1)/FORCES_THREADS;
+  if(c.scelldiv==1 && t.np<=V5_IDXMASK){
+    if(qdepth==32)ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,32><<<nb,FORCES_THREADS,0,stm>>>(t,c);
+    else ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,64><<<nb,FORCES_THREADS,0,stm>>>(t,c);
+  }
+  else ker_forces_fluid_v4<TKER,TVISCO,TDDT,SHIFT><<<nb,FORCES_THREADS,0,stm>>>(t,c);
+}
+
+} // namespace dsph
