@@ -158,16 +158,45 @@ def main():
     l.dsph_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     l.dsph_fluid_kernel_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
 
-    cd = dsph.make_case("dambreak", a.np)
-    n = cd.np_
-    code = cd.codes()
-    ctx = dsph.create_context(cd, device=local)
-    if a.force_variant:
-        l.dsph_set_force_variant(ctx.h, a.force_variant)
-    ctx.upload(cd.idp, cd.pos, cd.velrhop, cd.npb, code)
-    ctx.celldiv(True)
+    from dualsphysics_multilayer_b200 import mgpu
+    drv = None
+    if world == 1:
+        cd = dsph.make_case("dambreak", a.np)
+        n = cd.np_
+        code = cd.codes()
+        ctx = dsph.create_context(cd, device=local)
+        if a.force_variant:
+            l.dsph_set_force_variant(ctx.h, a.force_variant)
+        ctx.upload(cd.idp, cd.pos, cd.velrhop, cd.npb, code)
+        ctx.celldiv(True)
+        stepfn = ctx.step
+        nglobal = n
+    else:
+        # weak scaling: DB(world*np) split into x-slabs of balanced particle count; every rank generates only its slab
+        nglobal_target = a.np * world
+        info = dsph.make_case_slab("dambreak", nglobal_target, 0, 0)          # constants + counts of the full case
+        probe = dsph.make_case("dambreak", 300_000)                           # same geometry: column CDF for the cuts
+        from dualsphysics_multilayer_b200.capi import SphContext
+        tmpctx_cfg = info.cfg
+        sc = C.c_double(); pm = (C.c_double * 3)(); dcl = (C.c_uint32 * 3)()
+        L.check(L.fn("domain_info")(C.byref(tmpctx_cfg), C.byref(sc), pm, dcl))
+        ncol = int(dcl[0])
+        frac = np.clip((probe.pos[:, 0] - pm[0]) / (sc.value * ncol), 0, 1 - 1e-12)
+        colcount = np.bincount((frac * ncol).astype(np.int64), minlength=ncol).astype(np.float64)
+        cuts = mgpu.balanced_cuts(colcount, world, 4)
+        cd = dsph.make_case_slab("dambreak", nglobal_target, cuts[rank], cuts[rank + 1])
+        n = cd.np_
+        code = cd.codes()
+        ctx = SphContext(L, cd.cfg, int(n * 1.5) + 200_000, local)
+        if a.force_variant:
+            l.dsph_set_force_variant(ctx.h, a.force_variant)
+        ctx.upload(cd.idp, cd.pos, cd.velrhop, cd.npb, code)
+        drv = mgpu.SlabDriver(ctx, rank, world, cuts, "cuda:%d" % local)
+        drv.celldiv()
+        stepfn = drv.step
+        nglobal = int(info.cfg.casenp)
     for _ in range(a.pre_steps):
-        ctx.step()
+        stepfn()
 
     def barrier():
         if world > 1:
@@ -176,7 +205,7 @@ def main():
 
     # ---- device-resident throughput: W warm-up + K timed steps, CUDA events on the solver's stream
     for _ in range(a.warmup):
-        ctx.step()
+        stepfn()
     tm = dsph.Timers()
     l.dsph_get_timers(ctx.h, C.byref(tm), 1)
     l.dsph_fluid_kernel_stats(ctx.h, None, None, 1)
@@ -185,8 +214,8 @@ def main():
     L.check(l.dsph_timer_start(ctx.h))
     pstep = 0
     for _ in range(a.steps):
-        ctx.step()
-        pstep += ctx.np_
+        stepfn()
+        pstep += (ctx.np_ if drv is None else ctx.np_ - int(ctx.divinfo.npbper) - int(ctx.divinfo.npfper))   # owned particles only
     ms = C.c_double()
     L.check(l.dsph_timer_stop(ctx.h, C.byref(ms)))
     barrier()
@@ -201,9 +230,10 @@ def main():
     value = tot.item() / (t_ms.item() * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel (fluid Interaction_Forces): gather-byte model, SURVEY.md 8(d)
-    ctx.celldiv(False)
+    if drv is None:
+        ctx.celldiv(False)
     fr_real, fr_chk, br_real, br_chk = ctx.pips()
-    npf = ctx.np_ - ctx.npb
+    npf = ctx.np_ - ctx.npb - (0 if drv is None else int(ctx.divinfo.npfper))
     bytes_per_launch = 58.0 * npf + 16.0 * (fr_chk + fr_real)
     k_ms = fms.value / max(1, fnl.value)
     peak, peaksrc = measured_peak()
@@ -218,24 +248,29 @@ def main():
     # ---- end to end through the C ABI with HOST buffers: H2D of the state, one step, D2H of the result, every step
     e2e = None
     if not a.no_e2e:
-        st = ctx.download()
+        st = ctx.download() if drv is None else drv.owned()
         hid = torch.from_numpy(st["idp"]).pin_memory(); hcode = torch.from_numpy(st["code"].view(np.int16)).pin_memory()
         hpos = torch.from_numpy(st["pos"]).pin_memory(); hvr = torch.from_numpy(st["velrhop"]).pin_memory()
-        npb = ctx.npb
-        nn = ctx.np_
-        oid = torch.empty(nn, dtype=torch.int32).pin_memory(); ocode = torch.empty(nn, dtype=torch.int16).pin_memory()
-        opos = torch.empty((nn, 3), dtype=torch.float64).pin_memory(); ovr = torch.empty((nn, 4), dtype=torch.float32).pin_memory()
+        npb = ctx.npb if drv is None else int(np.count_nonzero((st["code"] & 0x1800) != 0x1800))
+        nn = int(st["idp"].shape[0])
+        cap_out = int(nn * 1.3) + 100_000
+        oid = torch.empty(cap_out, dtype=torch.int32).pin_memory(); ocode = torch.empty(cap_out, dtype=torch.int16).pin_memory()
+        opos = torch.empty((cap_out, 3), dtype=torch.float64).pin_memory(); ovr = torch.empty((cap_out, 4), dtype=torch.float32).pin_memory()
         up = L.fn("particles_upload"); down = L.fn("particles_download")
 
         def e2e_step():
             L.check(up(ctx.h, nn, npb, C.cast(hid.data_ptr(), C.POINTER(C.c_uint32)), C.cast(hcode.data_ptr(), C.POINTER(C.c_uint16)),
                        C.cast(hpos.data_ptr(), C.POINTER(C.c_double)), C.cast(hvr.data_ptr(), C.POINTER(C.c_float))))
-            ctx.celldiv(True)
-            ctx.step()
-            m = ctx.np_
+            if drv is None:
+                ctx.celldiv(True)
+                ctx.step()
+            else:
+                drv.celldiv()
+                drv.step()
+            m = min(ctx.np_, cap_out)
             L.check(down(ctx.h, 0, m, C.cast(oid.data_ptr(), C.POINTER(C.c_uint32)), C.cast(ocode.data_ptr(), C.POINTER(C.c_uint16)), None,
                          C.cast(opos.data_ptr(), C.POINTER(C.c_double)), C.cast(ovr.data_ptr(), C.POINTER(C.c_float))))
-            return m
+            return m if drv is None else m - int(ctx.divinfo.npbper) - int(ctx.divinfo.npfper)
         e2e_step()
         ke = max(2, min(a.steps, 5))
         barrier()
@@ -261,7 +296,8 @@ def main():
                "dtype": "f32", "data": "synthetic",
                "config": {"workload": "synthetic 3D dam-break DB(N) (SURVEY.md 8d): Symplectic + Wendland + artificial viscosity 0.1 + DDT2 0.1, DBC walls",
                           "np_per_gpu": n, "nfluid": int(cd.cfg.casenfluid), "pre_steps": a.pre_steps,
-                          "parallelism": ("single GPU" if world == 1 else "%d independent replicas (x-slab halo exchange not in this round)" % world),
+                          "np_global": nglobal,
+                          "parallelism": ("single GPU" if world == 1 else "%d x-slabs of balanced particle count; per divide: NCCL send/recv of migrants + 2h halo copies with <=2 neighbours; per force evaluation: all-reduce(max) of the dt maxima" % world),
                           "l2": "working set (np*~230 B) is far larger than the 126 MB L2; no flush needed"},
                "roofline": roofline, "e2e": e2e, "gpu_launches": int(tm.kernel_launches), "clocks": sampler.result(),
                "timers_ms_per_step": {k: getattr(tm, k) / a.steps for k in ("nl_limits", "nl_presort", "nl_radixsort", "nl_cellbegin", "nl_sortdata",

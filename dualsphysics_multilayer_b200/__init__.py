@@ -31,6 +31,8 @@ def lib() -> SphLib:
         l.dsph_device_count.restype = C.c_int
         l.dsph_case_make.restype = C.c_int
         l.dsph_case_make.argtypes = [C.POINTER(Case), C.c_char_p, C.c_uint64, C.c_uint32]
+        l.dsph_case_make_slab.restype = C.c_int
+        l.dsph_case_make_slab.argtypes = [C.POINTER(Case), C.c_char_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
         l.dsph_case_free.argtypes = [C.POINTER(Case)]
         l.dsph_case_load.restype = C.c_int
         l.dsph_case_load.argtypes = [C.POINTER(Case), C.c_char_p, C.c_char_p]
@@ -98,6 +100,14 @@ def make_case(kind: str, np_target: int, seed: int = 12345) -> CaseData:
     c = Case()
     L = lib()
     L.check(L.lib.dsph_case_make(C.byref(c), kind.encode(), int(np_target), int(seed)))
+    return _case_from_c(c)
+
+
+def make_case_slab(kind: str, np_target: int, cx_lo: int, cx_hi: int, seed: int = 12345) -> CaseData:
+    """The particles of cell columns [cx_lo,cx_hi) of make_case(kind, np_target); cfg/ids are those of the full case."""
+    c = Case()
+    L = lib()
+    L.check(L.lib.dsph_case_make_slab(C.byref(c), kind.encode(), int(np_target), int(seed), int(cx_lo), int(cx_hi)))
     return _case_from_c(c)
 
 

@@ -143,6 +143,16 @@ class SphLib:
         f("symplectic_dtpre", C.c_double, vp)
         f("set_symplectic_dtpre", C.c_int, vp, C.c_double)
         f("pips", C.c_int, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
+        # x-slab multi-GPU
+        f("mgpu_config", C.c_int, vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32)
+        f("mgpu_record_bytes", C.c_uint32)
+        f("mgpu_count", C.c_int, vp, C.POINTER(C.c_uint32))
+        f("mgpu_pack", C.c_int, vp, C.c_void_p, C.c_void_p)
+        f("mgpu_unpack", C.c_int, vp, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p)
+        f("forces_launch", C.c_int, vp, C.c_int)
+        f("forces_maxima_ptr", C.c_void_p, vp)
+        f("forces_finish", C.c_int, vp, C.POINTER(ForceRes))
+        f("domain_info", C.c_int, C.POINTER(Config), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint32))
 
     def _f(self, name, restype, *argtypes):
         fn = getattr(self.lib, self.prefix + name)
@@ -260,6 +270,38 @@ class SphContext:
     @symplectic_dtpre.setter
     def symplectic_dtpre(self, v):
         self.lib.check(self.lib.fn("set_symplectic_dtpre")(self.h, float(v)))
+
+    # -- x-slab multi-GPU (see mgpu.py)
+    def mgpu_config(self, rank, nranks, xlo, xhi):
+        self.lib.check(self.lib.fn("mgpu_config")(self.h, int(rank), int(nranks), int(xlo), int(xhi)))
+
+    def mgpu_count(self):
+        c = (C.c_uint32 * 6)()
+        self.lib.check(self.lib.fn("mgpu_count")(self.h, c))
+        return [int(v) for v in c]
+
+    def mgpu_pack(self, ptr_left, ptr_right):
+        self.lib.check(self.lib.fn("mgpu_pack")(self.h, ptr_left, ptr_right))
+
+    def mgpu_unpack(self, counts, ptr_left, ptr_right):
+        c = (C.c_uint32 * 6)(*[int(v) for v in counts])
+        self.lib.check(self.lib.fn("mgpu_unpack")(self.h, c, ptr_left, ptr_right))
+
+    def forces_launch(self, interstep=INTERSTEP_SYMPREDICTOR):
+        self.lib.check(self.lib.fn("forces_launch")(self.h, interstep))
+
+    def forces_maxima_ptr(self):
+        return int(self.lib.fn("forces_maxima_ptr")(self.h))
+
+    def forces_finish(self) -> ForceRes:
+        r = ForceRes()
+        self.lib.check(self.lib.fn("forces_finish")(self.h, C.byref(r)))
+        return r
+
+    def domain_info(self):
+        sc = C.c_double(); pm = (C.c_double * 3)(); dc = (C.c_uint32 * 3)()
+        self.lib.check(self.lib.fn("domain_info")(C.byref(self.cfg), C.byref(sc), pm, dc))
+        return sc.value, [float(v) for v in pm], [int(v) for v in dc]
 
     def pips(self):
         v = [C.c_uint64() for _ in range(4)]

@@ -117,6 +117,20 @@ int dsph_fluid_kernel_stats(dsph_ctx *ctx,double *ms_sum,uint64_t *nlaunch,int r
 }
 void* dsph_cuda_stream(dsph_ctx *ctx){ return (ctx&&ctx->eng)? (void*)ctx->eng->stm: nullptr; }
 
+// ---- x-slab multi-GPU ----
+int dsph_mgpu_config(dsph_ctx *ctx,int rank,int nranks,uint32_t xlo,uint32_t xhi){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgConfig(rank,nranks,xlo,xhi); }); }
+uint32_t dsph_mgpu_record_bytes(void){ return 96u; }
+int dsph_mgpu_count(dsph_ctx *ctx,uint32_t counts[6]){ NEEDCTX(ctx); return Guard([&]{ unsigned c[6]; ctx->eng->MgCount(c); for(int i=0;i<6;i++)counts[i]=c[i]; }); }
+int dsph_mgpu_pack(dsph_ctx *ctx,void *sl,void *sr){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgPack(sl,sr); }); }
+int dsph_mgpu_unpack(dsph_ctx *ctx,const uint32_t counts[6],const void *rl,const void *rr){ NEEDCTX(ctx); return Guard([&]{ unsigned c[6]; for(int i=0;i<6;i++)c[i]=counts[i]; ctx->eng->MgUnpack(c,rl,rr); }); }
+int dsph_forces_launch(dsph_ctx *ctx,int interstep){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->ForcesLaunch(interstep); }); }
+void* dsph_forces_maxima_ptr(dsph_ctx *ctx){ return (ctx&&ctx->eng)? (void*)ctx->eng->fmax: nullptr; }
+int dsph_forces_finish(dsph_ctx *ctx,dsph_forceres *res){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->ForcesFinish(res); }); }
+int dsph_domain_info(const dsph_config *cfg,double *scell,double domposmin[3],uint32_t domcells[3]){
+  if(!cfg){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  return Guard([&]{ SphConst k; DeriveConstants(*cfg,k); if(scell)*scell=k.scell; for(int i=0;i<3;i++){ if(domposmin)domposmin[i]=k.domposmin[i]; if(domcells)domcells[i]=k.domcells[i]; } });
+}
+
 // ---- case tooling (host only) ----
 static void CaseToC(const CaseData &cd,dsph_case *out){
   memset(out,0,sizeof(*out));
@@ -130,6 +144,14 @@ static void CaseToC(const CaseData &cd,dsph_case *out){
 int dsph_case_make(dsph_case *out,const char *kind,uint64_t np_target,uint32_t seed){
   if(!out||!kind){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
   return Guard([&]{ CaseData cd; MakeCase(cd,kind,np_target,seed); CaseToC(cd,out); });
+}
+int dsph_case_make_slab(dsph_case *out,const char *kind,uint64_t np_target,uint32_t seed,uint32_t cx_lo,uint32_t cx_hi){
+  if(!out||!kind){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  return Guard([&]{
+    CaseData cd; MakeCaseSlab(cd,kind,np_target,seed,cx_lo,cx_hi); CaseToC(cd,out);
+    unsigned nb=0; for(unsigned id:cd.idp)if(id<cd.cfg.casenfixed)nb++;
+    out->npb=nb;   // boundary particles of the slab (cfg.casenfixed keeps the count of the full case)
+  });
 }
 int dsph_case_free(dsph_case *c){
   if(!c)return DSPH_OK;

@@ -30,6 +30,7 @@ struct DevCtes {
   double maprealposmin[3], maprealsize[3];
   double perixinc[3], periyinc[3], perizinc[3];
   int perix, periy, periz, periactive;
+  int ghosts;             // periactive || x-slab multi-GPU: particles with CODE_PERIODIC are neighbour-only copies
   float movlimit, rhopoutmin, rhopoutmax;
   float gravity[3];
   int simulate2d, dtallparticles;

@@ -11,6 +11,7 @@
 #include "forces_v5.cuh"
 #include "step.cuh"
 #include "periodic.cuh"
+#include "mgpu.cuh"
 #include <cstdio>
 #include <cstring>
 #include <cmath>
@@ -73,7 +74,7 @@ void Engine::Configure(const dsph_config &c){
     dc.gravity[i]=cfg.gravity[i];
   }
   dc.domcellcode=k.domcellcode;
-  dc.perix=cfg.perix; dc.periy=cfg.periy; dc.periz=cfg.periz; dc.periactive=k.periactive;
+  dc.perix=cfg.perix; dc.periy=cfg.periy; dc.periz=cfg.periz; dc.periactive=k.periactive; dc.ghosts=(k.periactive||mgpu)? 1: 0;
   dc.movlimit=k.movlimit;
   dc.rhopoutmin=cfg.rhopoutmin; dc.rhopoutmax=cfg.rhopoutmax;
   if(!(dc.rhopoutmin<dc.rhopoutmax)){ dc.rhopoutmin=-FLT_MAX; dc.rhopoutmax=FLT_MAX; }
@@ -225,11 +226,11 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
   CUCHECK(cudaSetDevice(device));
   const int B=DIV_THREADS;
   CUCHECK(cudaEventRecord(ev[0],stm));
-  if(updateperiodic && k.periactive)RunPeriodic();
+  if(updateperiodic && k.periactive && !mgpu)RunPeriodic();
   CUCHECK(cudaEventRecord(ev[1],stm));
   const unsigned npb1=npb, npf1=np-npb-npbper-npfper, npb2=npbper, npf2=npfper;
   const unsigned nptot=np;
-  if(boundchanged || k.periactive){ blimok=false; divok=false; }
+  if(boundchanged || k.periactive || mgpu){ blimok=false; divok=false; }
   // ---- limits (one reduction kernel per particle range, results stay on the device)
   {
     unsigned init[12]={0xffffffffu,0xffffffffu,0xffffffffu,0,0,0, 0xffffffffu,0xffffffffu,0xffffffffu,0,0,0};
@@ -330,7 +331,7 @@ void Engine::GetBeginCell(unsigned *h,unsigned capacity){
 // ------------------------------------------------------------------------------------------------
 ForceParams Engine::MakeForceParams(){
   ForceParams t; memset(&t,0,sizeof(t));
-  t.np=np; t.npb=npb; t.npbok=npbok;
+  t.np=np; t.npb=npb; t.npbok=npbok; t.skipghosts=(mgpu? 1: 0);
   t.ncx=int(dp.ncx); t.ncy=int(dp.ncy); t.ncz=int(dp.ncz); t.nsheet=int(dp.nsheet);
   t.cellfluid=dp.nct+1;
   for(int i=0;i<3;i++)t.cellzero[i]=dp.cellmin[i];
@@ -368,6 +369,12 @@ template<int TKER> static void LaunchFluid1(int variant,int tvisco,int tddt,bool
 }
 
 void Engine::Forces(int interstep,dsph_forceres *res){
+  ForcesLaunch(interstep);
+  ForcesFinish(res);
+}
+
+// kernels only: the three maxima stay on the device (multi-GPU: all-reduce(max) on them before ForcesFinish)
+void Engine::ForcesLaunch(int interstep){
   (void)interstep;
   CUCHECK(cudaSetDevice(device));
   if(!divok)throw EngineError(DSPH_ERR_STATE,"dsph_forces_run needs a cell division first (dsph_celldiv_run).");
@@ -392,6 +399,12 @@ void Engine::Forces(int interstep,dsph_forceres *res){
     launches++;
   }
   CUCHECK(cudaEventRecord(ev[10],stm));
+  forceslaunched=true;
+}
+
+void Engine::ForcesFinish(dsph_forceres *res){
+  if(!forceslaunched)throw EngineError(DSPH_ERR_STATE,"dsph_forces_finish needs dsph_forces_launch first.");
+  forceslaunched=false;
   CUCHECK(cudaMemcpyAsync(&hpin->fmax,fmax,sizeof(ForceMax),cudaMemcpyDeviceToHost,stm));
   CUCHECK(cudaStreamSynchronize(stm));
   CUCHECK(cudaGetLastError());
@@ -523,6 +536,85 @@ void Engine::Step(double *stepdt,dsph_forceres *res){
   }
   CellDivide(true,nullptr); FlushStepTimer();
   if(stepdt)*stepdt=dt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// x-slab multi-GPU: pack / unpack of migrants and halo copies; transport is done by the caller (NCCL)
+// ------------------------------------------------------------------------------------------------
+void Engine::MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi){
+  if(k.periactive)throw EngineError(DSPH_ERR_ARG,"x-slab decomposition cannot be combined with periodic boundaries yet.");
+  if(nranks<1 || rank<0 || rank>=nranks || xlo>=xhi || xhi>k.domcells[0])throw EngineError(DSPH_ERR_ARG,"Invalid slab configuration.");
+  if(nranks>1 && xhi-xlo<2u*unsigned(k.scelldiv)+1u)throw EngineError(DSPH_ERR_ARG,"The slab is narrower than 2 halo widths + 1 cell.");
+  mgpu=(nranks>1); mgrank=rank; mgnranks=nranks; mgxlo=xlo; mgxhi=xhi;
+  dc.ghosts=(k.periactive||mgpu)? 1: 0;
+  if(mgpu)for(int i=0;i<3;i++)DevAlloc(mgscratch[i],size_t(cap));
+}
+void Engine::MgCount(unsigned counts[6]){
+  if(!mgpu)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_count needs dsph_mgpu_config with more than one rank.");
+  const int B=256; const unsigned nb=(np+B-1)/B;
+  CUCHECK(cudaEventRecord(ev[0],stm));
+  // halo copies of the previous divide are dropped by the next sort
+  ker_peri_ignore<<<nb,B,0,stm>>>(np,code[cur]); launches++;
+  MgArgs a; a.np=np; a.npb=npb; a.xlo=mgxlo; a.xhi=mgxhi; a.sd=unsigned(k.scelldiv);
+  a.hasleft=(mgrank>0); a.hasright=(mgrank<mgnranks-1); a.domcellcode=k.domcellcode; a.dcell=dcell[cur]; a.code=code[cur];
+  unsigned *flags=mgscratch[2];
+  unsigned *off[6]={rs.keys[0],rs.keys[1],rs.vals[0],rs.vals[1],mgscratch[0],mgscratch[1]};
+  ker_mg_flags<<<nb,B,0,stm>>>(a,flags); launches++;
+  for(int g=0;g<6;g++){
+    ker_mg_bit<<<nb,B,0,stm>>>(np,flags,g,off[g]); launches++;
+    CUCHECK(cudaMemcpyAsync(&hpin->scratch[g],off[g]+(np-1),4,cudaMemcpyDeviceToHost,stm));     // last flag
+    DeviceExclusiveScan(off[g],np,rs.chunksum,rs.chunksum2,stm,&launches);
+    CUCHECK(cudaMemcpyAsync(&hpin->mgtot[g],off[g]+(np-1),4,cudaMemcpyDeviceToHost,stm));       // last offset
+  }
+  CUCHECK(cudaStreamSynchronize(stm));
+  for(int g=0;g<6;g++){ mgcounts[g]=hpin->scratch[g]+hpin->mgtot[g]; counts[g]=mgcounts[g]; }
+  mgcounted=true;
+}
+void Engine::MgPack(void *sendleft,void *sendright){
+  if(!mgcounted)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_pack needs dsph_mgpu_count first.");
+  mgcounted=false;
+  const int B=256; const unsigned nb=(np+B-1)/B;
+  MgArgs a; a.np=np; a.npb=npb; a.xlo=mgxlo; a.xhi=mgxhi; a.sd=unsigned(k.scelldiv);
+  a.hasleft=(mgrank>0); a.hasright=(mgrank<mgnranks-1); a.domcellcode=k.domcellcode; a.dcell=dcell[cur]; a.code=code[cur];
+  unsigned *flags=mgscratch[2];
+  unsigned *off[6]={rs.keys[0],rs.keys[1],rs.vals[0],rs.vals[1],mgscratch[0],mgscratch[1]};
+  const unsigned *counts=mgcounts;
+  void *sendbuf[2]={sendleft,sendright};
+  MgPackArrays sp; sp.idp=idp[cur]; sp.code=code[cur]; sp.pos=pos[cur]; sp.velrhop=velrhop[cur];
+  sp.pospre=(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre? pospre[cur]: nullptr);
+  sp.aux=(cfg.tstep==DSPH_STEP_SYMPLECTIC? (haspre? velrhoppre[cur]: nullptr): velrhopm1[cur]);
+  for(int d=0;d<2;d++){
+    const unsigned tot=counts[3*d]+counts[3*d+1]+counts[3*d+2];
+    if(tot && !sendbuf[d])throw EngineError(DSPH_ERR_ARG,"Null send buffer.");
+    unsigned base=0;
+    for(int kd=0;kd<3;kd++){
+      const int g=3*d+kd;
+      if(counts[g]){ ker_mg_pack<<<nb,B,0,stm>>>(a,flags,g,off[g],base,sp,(MgRecord*)sendbuf[d]); launches++; }
+      base+=counts[g];
+    }
+  }
+  CUCHECK(cudaStreamSynchronize(stm));
+  CUCHECK(cudaGetLastError());
+}
+void Engine::MgUnpack(const unsigned counts[6],const void *recvleft,const void *recvright){
+  if(!mgpu)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_unpack needs dsph_mgpu_config with more than one rank.");
+  const unsigned bgl=counts[0], fl=counts[1]+counts[2], bgr=counts[3], fr=counts[4]+counts[5];
+  const unsigned total=bgl+fl+bgr+fr;
+  if(size_t(np)+total>cap)throw EngineError(DSPH_ERR_STATE,"Received particles exceed the capacity of the context.");
+  MgUnpackArrays d; d.idp=idp[cur]; d.code=code[cur]; d.dcell=dcell[cur]; d.pos=pos[cur]; d.velrhop=velrhop[cur];
+  d.pospre=(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre? pospre[cur]: nullptr);
+  d.aux=(cfg.tstep==DSPH_STEP_SYMPLECTIC? (haspre? velrhoppre[cur]: nullptr): velrhopm1[cur]);
+  const int B=256;
+  unsigned dst=np;
+  auto up=[&](unsigned n,const MgRecord *src){ if(n){ ker_mg_unpack<<<(n+B-1)/B,B,0,stm>>>(n,src,dst,d,dc); launches++; dst+=n; } };
+  up(bgl,(const MgRecord*)recvleft);
+  up(bgr,(const MgRecord*)recvright);
+  up(fl,(const MgRecord*)recvleft+bgl);
+  up(fr,(const MgRecord*)recvright+bgr);
+  npbper=bgl+bgr; npfper=fl+fr; np+=total;
+  boundchanged=true;
+  CUCHECK(cudaStreamSynchronize(stm));
+  CUCHECK(cudaGetLastError());
 }
 
 void Engine::GetTimers(dsph_timers *t,bool reset){

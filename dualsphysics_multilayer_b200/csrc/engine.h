@@ -22,6 +22,7 @@ struct HostPinned {
   ForceMax fmax;
   unsigned limitsinit[12];
   unsigned scratch[8];
+  unsigned mgtot[8];
 };
 
 class Engine {
@@ -69,6 +70,16 @@ class Engine {
   void GetBeginCell(unsigned *h,unsigned capacity);
   ForceParams MakeForceParams();
   void Forces(int interstep,dsph_forceres *res);
+  void ForcesLaunch(int interstep);
+  void ForcesFinish(dsph_forceres *res);
+  // x-slab multi-GPU
+  bool mgpu=false; int mgrank=0, mgnranks=1; unsigned mgxlo=0, mgxhi=0;
+  unsigned *mgscratch[3]={}; unsigned mgcounts[6]={}; bool mgcounted=false;
+  bool forceslaunched=false;
+  void MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi);
+  void MgCount(unsigned counts[6]);
+  void MgPack(void *sendleft,void *sendright);
+  void MgUnpack(const unsigned counts[6],const void *recvleft,const void *recvright);
   void ForcesDownload(unsigned first,unsigned count,float *ace,float *ar);
   void Pips(unsigned long long *fr,unsigned long long *fc,unsigned long long *br,unsigned long long *bc);
   double DtVariable(double *dt1,double *dt2)const;

@@ -28,6 +28,7 @@ constexpr int FORCES_THREADS=128;
 
 struct ForceParams {
   unsigned np, npb, npbok;
+  int skipghosts;              // multi-GPU: CODE_PERIODIC fluid particles are halo copies, no forces needed
   int ncx, ncy, ncz, nsheet;
   unsigned cellfluid;          // nct+1: offset of the fluid boxes in begincell
   unsigned cellzero[3];        // CellDomainMin
@@ -261,7 +262,7 @@ ker_forces_fluid_v1(ForceParams t,DevCtes c)
       for(int k=0;k<6;k++)t.spsgradvel[6*size_t(p1)+k]=g[k];
     }
     // maxima: AceMax ignores periodic duplicates (S/JSphCpuSingle.cpp:583-636); VelMax takes every fluid particle
-    const bool normal=(!c.periactive || (t.code[p1]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
+    const bool normal=(!c.ghosts || (t.code[p1]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
     if(normal)ace2=ax*ax+ay*ay+az*az;
     vel2=velrhop1.x*velrhop1.x+velrhop1.y*velrhop1.y+velrhop1.z*velrhop1.z;
   }

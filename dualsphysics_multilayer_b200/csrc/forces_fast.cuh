@@ -175,7 +175,7 @@ ker_forces_fluid_v4(ForceParams t,DevCtes c)
       for(int k=0;k<6;k++)t.spsgradvel[6*size_t(p1)+k]=g[k];
     }
     viscmax=a.visc;
-    const bool normal=(!c.periactive || (t.code[p1]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
+    const bool normal=(!c.ghosts || (t.code[p1]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
     if(normal)ace2=ax*ax+ay*ay+az*az;
     vel2=q.velrhop.x*q.velrhop.x+q.velrhop.y*q.velrhop.y+q.velrhop.z*q.velrhop.z;
   }

@@ -125,7 +125,7 @@ ker_forces_fluid_v2(ForceParams t,DevCtes c)
     if(TDDT!=DSPH_DDT_NONE && delta!=FLT_MAX)ar+=delta;
     t.acear[p1]=make_float4(ax,ay,az,ar);
     if(SHIFT)t.shiftposfs[p1]=fb.shift;
-    const bool normal=(!c.periactive || (t.code[p1]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
+    const bool normal=(!c.ghosts || (t.code[p1]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
     if(normal)ace2=ax*ax+ay*ay+az*az;
     vel2=velrhop1.x*velrhop1.x+velrhop1.y*velrhop1.y+velrhop1.z*velrhop1.z;
   }

@@ -142,7 +142,7 @@ template<int TKER,int TDDT,bool SHIFT,int G,int SD> __device__ __forceinline__ v
     if(lane==0){
       t.acear[p1[g]]=make_float4(ax,ay,az,ar);
       if(SHIFT)t.shiftposfs[p1[g]]=sh;
-      const bool normal=(!c.periactive || (t.code[p1[g]]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
+      const bool normal=(!c.ghosts || (t.code[p1[g]]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
       if(normal)ace2max=fmaxf(ace2max,ax*ax+ay*ay+az*az);
       vel2max=fmaxf(vel2max,vr1[g].x*vr1[g].x+vr1[g].y*vr1[g].y+vr1[g].z*vr1[g].z);
       viscmax=fmaxf(viscmax,visc);

@@ -48,8 +48,9 @@ ker_forces_fluid_v5(ForceParams t,DevCtes c)
   unsigned *q=qsm+threadIdx.x;
   const unsigned FULL=0xffffffffu;
   const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
-  const bool active=(p1<t.np);
-  const unsigned p1c=(active? p1: t.np-1);
+  const unsigned p1c=min(p1,t.np-1);
+  // x-slab halo copies are neighbours only: their forces are computed by the owning GPU (skipghosts: multi-GPU mode)
+  const bool active=(p1<t.np && !(t.skipghosts && (t.code[p1c]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_PERIODIC));
   const float4 pp1=t.posp[p1c];
   FastP1 fp; fp.velrhop=t.velrhop[p1c]; fp.press=pp1.w; fp.ovrhop=1.f/fp.velrhop.w;
   const unsigned rcell=t.dcell[p1c];
@@ -124,7 +125,7 @@ ker_forces_fluid_v5(ForceParams t,DevCtes c)
       for(int k=0;k<6;k++)t.spsgradvel[6*size_t(p1)+k]=g[k];
     }
     viscmax=a.visc;
-    const bool normal=(!c.periactive || (t.code[p1]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
+    const bool normal=(!c.ghosts || (t.code[p1]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
     if(normal)ace2=ax*ax+ay*ay+az*az;
     vel2=fp.velrhop.x*fp.velrhop.x+fp.velrhop.y*fp.velrhop.y+fp.velrhop.z*fp.velrhop.z;
   }

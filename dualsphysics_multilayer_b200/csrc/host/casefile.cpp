@@ -2,6 +2,7 @@
 #include "casefile.h"
 #include "bi4.h"
 #include "xmlmini.h"
+#include "sphconst.h"
 #include <cstdio>
 #include <cstring>
 #include <cmath>
@@ -302,6 +303,11 @@ static unsigned long long DamBreakNp(const unsigned n[6]){
   return bottom+sides+(unsigned long long)n[3]*n[4]*n[5];
 }
 
+// Optional x-slab filter (multi-GPU weak scaling): only particles whose cell column lies in [cxlo,cxhi) are stored; ids,
+// counts and constants are those of the full case, so every rank can generate just its own slab.
+struct SlabFilter{ bool on=false; unsigned cxlo=0,cxhi=0; };
+static thread_local SlabFilter g_slab;
+
 static void MakeDamBreak(CaseData &cd,unsigned long long nptarget,bool twolayer){
   dsph_config &c=cd.cfg; ConfigDefaults(c);
   const double a=0.4;
@@ -330,25 +336,34 @@ static void MakeDamBreak(CaseData &cd,unsigned long long nptarget,bool twolayer)
   pos.clear(); vr.clear(); idp.clear();
   const double zsurf=FZ*dp;
   auto rhohyd=[&](double z){ const double dz=zsurf-z; if(dz<=0)return float(rho0); return float(rho0*pow(1.0+rho0*g*dz/B,1.0/gamma)); };
-  auto add=[&](unsigned i,unsigned j,unsigned k,float rho){ pos.push_back(i*dp); pos.push_back(j*dp); pos.push_back(k*dp); vr.push_back(0); vr.push_back(0); vr.push_back(0); vr.push_back(rho); idp.push_back(unsigned(idp.size())); };
+  cd.caseposmin[0]=cd.caseposmin[1]=cd.caseposmin[2]=0;
+  cd.caseposmax[0]=NX*dp; cd.caseposmax[1]=NY*dp; cd.caseposmax[2]=NZ*dp;
+  ComputeMapRealPos(cd);
+  SphConst kc; DeriveConstants(c,kc);
+  unsigned nextid=0;
+  auto add=[&](unsigned i,unsigned j,unsigned k,float rho){
+    const unsigned id=nextid++;
+    if(g_slab.on){ const unsigned cx=unsigned((i*dp-kc.domposmin[0])/kc.scell); if(cx<g_slab.cxlo || cx>=g_slab.cxhi)return; }
+    pos.push_back(i*dp); pos.push_back(j*dp); pos.push_back(k*dp); vr.push_back(0); vr.push_back(0); vr.push_back(0); vr.push_back(rho); idp.push_back(id);
+  };
   for(unsigned k=0;k<=NZ;k++)for(unsigned j=0;j<=NY;j++)for(unsigned i=0;i<=NX;i++){
     const bool wall=(k==0||i==0||i==NX||j==0||j==NY);
     if(wall)add(i,j,k,rhohyd(k*dp));
   }
-  const unsigned nb=unsigned(idp.size());
+  const unsigned nb=nextid;
   unsigned nf0=0,nf1=0;
   if(!twolayer){
     for(unsigned k=1;k<=FZ;k++)for(unsigned j=1;j<=FY;j++)for(unsigned i=1;i<=FX;i++)add(i,j,k,rhohyd(k*dp));
-    nf0=unsigned(idp.size())-nb;
+    nf0=nextid-nb;
   }
   else{
     const unsigned kh=FZ/2;
     for(unsigned k=1;k<=kh;k++)for(unsigned j=1;j<=FY;j++)for(unsigned i=1;i<=FX;i++)add(i,j,k,1500.f);
-    nf0=unsigned(idp.size())-nb;
+    nf0=nextid-nb;
     for(unsigned k=kh+1;k<=FZ;k++)for(unsigned j=1;j<=FY;j++)for(unsigned i=1;i<=FX;i++)add(i,j,k,1000.f);
-    nf1=unsigned(idp.size())-nb-nf0;
+    nf1=nextid-nb-nf0;
   }
-  const unsigned np=unsigned(idp.size());
+  const unsigned np=nextid;
   c.casenp=np; c.casenfixed=nb; c.casenfluid=np-nb;
   cd.mkboundfirst=11; cd.mkfluidfirst=1;
   cd.blocks.clear();
@@ -397,6 +412,13 @@ static void MakePeriodicBox(CaseData &cd,unsigned long long nptarget,unsigned se
   cd.blocks.clear(); cd.blocks.push_back({3,0,cd.mkfluidfirst+0,0,np});
   for(int i=0;i<3;i++){ cd.caseposmin[i]=0.5*dp; cd.caseposmax[i]=(n-0.5)*dp; } // lattice extremes, not jittered positions
   ComputeMapRealPos(cd);
+}
+
+void MakeCaseSlab(CaseData &cd,const std::string &kind,unsigned long long nptarget,unsigned seed,unsigned cxlo,unsigned cxhi){
+  if(kind!="dambreak" && kind!="nn2layer")throw std::runtime_error("Slab generation is available for the dam-break cases only.");
+  g_slab.on=true; g_slab.cxlo=cxlo; g_slab.cxhi=cxhi;
+  try{ MakeCase(cd,kind,nptarget,seed); }catch(...){ g_slab.on=false; throw; }
+  g_slab.on=false;
 }
 
 void MakeCase(CaseData &cd,const std::string &kind,unsigned long long nptarget,unsigned seed){

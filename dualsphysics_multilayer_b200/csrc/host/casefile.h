@@ -38,5 +38,7 @@ void LoadCase(CaseData &cd,const std::string &dir,const std::string &casename);
 
 // kind: "dambreak", "periodicbox", "nn2layer" (DB(N), PB(N), NN(N))
 void MakeCase(CaseData &cd,const std::string &kind,unsigned long long nptarget,unsigned seed);
+// same case, but only the particles of the cell columns [cxlo,cxhi) are generated (ids/counts of the full case)
+void MakeCaseSlab(CaseData &cd,const std::string &kind,unsigned long long nptarget,unsigned seed,unsigned cxlo,unsigned cxhi);
 
 } // namespace dsph

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(STEP_THREADS) ker_step_sympre(StepArrays a,dou
   unsigned code2=rcode;
   if(outrhop && isnormal){ code2=(rcode&(~DSPH_CODE_MASKSPECIAL))|DSPH_CODE_OUTRHOP; a.code[p]=typecode(code2); }
   outrhop=((code2&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_OUTRHOP);
-  const bool normal=(!c.periactive || outrhop || (code2&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
+  const bool normal=(!c.ghosts || outrhop || (code2&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
   if(normal && (code2&DSPH_CODE_MASKTYPE)==DSPH_CODE_TYPE_FLUID)UpdatePos(px,py,pz,dx,dy,dz,outrhop,p,a.pos,a.dcell,a.code,c);
 }
 
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(STEP_THREADS) ker_step_symcor(StepArrays a,dou
   if(outrhop && isnormal){ code2=(rcode&(~DSPH_CODE_MASKSPECIAL))|DSPH_CODE_OUTRHOP; a.code[p]=typecode(code2); }
   a.velrhop[p]=rv;
   outrhop=((code2&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_OUTRHOP);
-  const bool normal=(!c.periactive || outrhop || (code2&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
+  const bool normal=(!c.ghosts || outrhop || (code2&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL);
   if(normal && (code2&DSPH_CODE_MASKTYPE)==DSPH_CODE_TYPE_FLUID){
     const double px=a.pospre[3*size_t(p)], py=a.pospre[3*size_t(p)+1], pz=a.pospre[3*size_t(p)+2];
     UpdatePos(px,py,pz,dx,dy,dz,outrhop,p,a.pos,a.dcell,a.code,c);
@@ -160,6 +160,8 @@ __global__ void __launch_bounds__(STEP_THREADS) ker_step_verlet(StepArrays a,dou
     a.velrhopm1[p]=make_float4(0,0,0,(rhopnew<c.rhopzero? c.rhopzero: rhopnew));
     return;
   }
+  // x-slab halo copies (not the reference's periodic duplicates, which Verlet does update) are never integrated
+  if(c.ghosts && !c.periactive && (a.code[p]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_PERIODIC){ a.velrhopm1[p]=vr1; return; }
   const double dt205=0.5*dt*dt;
   const double agx=double(ac.x)+double(c.gravity[0]), agy=double(ac.y)+double(c.gravity[1]), agz=double(ac.z)+double(c.gravity[2]);
   double dx=double(vr1.x)*dt+agx*dt205, dy=double(vr1.y)*dt+agy*dt205, dz=double(vr1.z)*dt+agz*dt205;

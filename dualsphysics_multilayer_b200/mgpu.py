@@ -1,0 +1,161 @@
+"""x-slab domain decomposition over the GPUs of one box: one process per GPU, torch.distributed for the
+plumbing (NCCL over NVLink on GPUs; gloo on CPU for the tests, where the per-rank engine is the CPU checker).
+
+Per neighbour-list build every rank
+  1. classifies its particles (`mgpu_count`): fluid particles whose cell column left the slab migrate to the neighbour,
+     particles within 2h (ScellDiv cells) of a cut are copied to the neighbour as ghosts (CODE_PERIODIC: neighbours only),
+  2. exchanges the six counts and then the packed 96-byte records with its <=2 neighbours (send/recv),
+  3. appends what it received (`mgpu_unpack`) and runs the ordinary cell division.
+Per force evaluation the three maxima (viscdt, |ace|^2, |vel|^2: uint32 bit patterns of non-negative floats, so integer
+MAX is float MAX) are all-reduced before the time step is derived, so every rank uses the same dt.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import capi
+
+
+def balanced_cuts(colcount: np.ndarray, nranks: int, minwidth: int) -> list:
+    """Cut positions (cell columns) so that every slab owns about the same number of particles; slabs keep at least
+    `minwidth` columns.  Returns nranks+1 increasing column indices, first 0 and last len(colcount)."""
+    ncol = len(colcount)
+    if nranks * minwidth > ncol:
+        raise ValueError("too many ranks for %d cell columns (minimum slab width %d)" % (ncol, minwidth))
+    cum = np.concatenate([[0], np.cumsum(colcount, dtype=np.float64)])
+    cuts = [0]
+    for r in range(1, nranks):
+        target = cum[-1] * r / nranks
+        c = int(np.searchsorted(cum, target))
+        c = max(c, cuts[-1] + minwidth)
+        c = min(c, ncol - (nranks - r) * minwidth)
+        cuts.append(c)
+    cuts.append(ncol)
+    return cuts
+
+
+class _CudaView:
+    """Minimal __cuda_array_interface__ wrapper so torch can view a raw device pointer owned by the C library."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class SlabDriver:
+    def __init__(self, ctx: capi.SphContext, rank: int, world: int, cuts, device: str, group=None):
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        self.device = torch.device(device)
+        self.left = rank - 1 if rank > 0 else None
+        self.right = rank + 1 if rank < world - 1 else None
+        self.cuts = list(cuts)
+        ctx.mgpu_config(rank, world, self.cuts[rank], self.cuts[rank + 1])
+        self.recbytes = int(ctx.lib.fn("mgpu_record_bytes")())
+        self._buf = {}
+        ptr = ctx.forces_maxima_ptr()
+        if self.device.type == "cuda":
+            self.maxima = torch.as_tensor(_CudaView(ptr, 4, "<i4"), device=self.device)
+        else:
+            self.maxima = torch.from_numpy(np.ctypeslib.as_array((C.c_int32 * 4).from_address(ptr)))
+        self.sent_records = 0
+        self.symplectic = (ctx.cfg.tstep == capi.STEP_SYMPLECTIC)
+
+    # ---- buffers -------------------------------------------------------------------------------------------------
+    def _buffer(self, name, nrec):
+        need = max(1, nrec) * self.recbytes
+        b = self._buf.get(name)
+        if b is None or b.numel() < need:
+            b = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8, device=self.device)
+            self._buf[name] = b
+        return b
+
+    # ---- halo + migration exchange ---------------------------------------------------------------------------------
+    def exchange(self):
+        if self.world == 1:
+            return
+        ctx = self.ctx
+        counts = ctx.mgpu_count()                                   # [L: bg, fm, fg, R: bg, fm, fg]
+        mine = torch.tensor(counts, dtype=torch.int64, device=self.device)
+        fromleft = torch.zeros(3, dtype=torch.int64, device=self.device)
+        fromright = torch.zeros(3, dtype=torch.int64, device=self.device)
+        toleft = mine[0:3].contiguous(); toright = mine[3:6].contiguous()
+        ops = []
+        if self.left is not None:
+            ops += [dist.P2POp(dist.isend, toleft, self.left, self.group), dist.P2POp(dist.irecv, fromleft, self.left, self.group)]
+        if self.right is not None:
+            ops += [dist.P2POp(dist.isend, toright, self.right, self.group), dist.P2POp(dist.irecv, fromright, self.right, self.group)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        nl, nr = int(sum(counts[0:3])), int(sum(counts[3:6]))
+        rl = [int(v) for v in fromleft.tolist()]; rr = [int(v) for v in fromright.tolist()]
+        sl, sr = self._buffer("sl", nl), self._buffer("sr", nr)
+        ctx.mgpu_pack(sl.data_ptr(), sr.data_ptr())
+        bl, br = self._buffer("rl", sum(rl)), self._buffer("rr", sum(rr))
+        ops = []
+        if self.left is not None:
+            if nl:
+                ops.append(dist.P2POp(dist.isend, sl[: nl * self.recbytes], self.left, self.group))
+            if sum(rl):
+                ops.append(dist.P2POp(dist.irecv, bl[: sum(rl) * self.recbytes], self.left, self.group))
+        if self.right is not None:
+            if nr:
+                ops.append(dist.P2POp(dist.isend, sr[: nr * self.recbytes], self.right, self.group))
+            if sum(rr):
+                ops.append(dist.P2POp(dist.irecv, br[: sum(rr) * self.recbytes], self.right, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if self.device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        ctx.mgpu_unpack(rl + rr, bl.data_ptr(), br.data_ptr())
+        self.sent_records += nl + nr
+
+    # ---- the step pieces (same sequence as JSphGpuSingle::ComputeStep_Sym/_Ver + closing divide) -------------------
+    def celldiv(self):
+        self.exchange()
+        return self.ctx.celldiv(False)
+
+    def forces(self, interstep):
+        self.ctx.forces_launch(interstep)
+        if self.world > 1:
+            if self.device.type == "cuda":
+                # the library launched on its own stream: make torch's stream wait for it through a device-wide sync
+                torch.cuda.synchronize()
+            dist.all_reduce(self.maxima, op=dist.ReduceOp.MAX, group=self.group)
+            if self.device.type == "cuda":
+                torch.cuda.synchronize()
+        return self.ctx.forces_finish()
+
+    def step(self):
+        ctx = self.ctx
+        if self.symplectic:
+            dt = ctx.symplectic_dtpre
+            rp = self.forces(capi.INTERSTEP_SYMPREDICTOR)
+            ctx.step_sympre(dt)
+            self.celldiv()
+            rc = self.forces(capi.INTERSTEP_SYMCORRECTOR)
+            ctx.step_symcor(dt)
+            ctx.symplectic_dtpre = min(rp.dt, rc.dt)
+            res = rc
+        else:
+            res = self.forces(capi.INTERSTEP_VERLET)
+            dt = res.dt
+            ctx.step_verlet(dt)
+        self.celldiv()
+        return dt, res
+
+    # ---- helpers -------------------------------------------------------------------------------------------------
+    def owned(self):
+        """Particles owned by this rank (ghosts removed), as downloaded arrays."""
+        st = self.ctx.download()
+        keep = (st["code"] & capi.CODE_MASKSPECIAL) == capi.CODE_NORMAL
+        return {k: v[keep] for k, v in st.items()}
+
+
+def slab_select(pos_x: np.ndarray, cuts, rank: int, scell: float, domposmin_x: float):
+    """Boolean mask of the particles whose cell column lies in the slab of `rank` (same arithmetic as the cell hash)."""
+    cx = ((pos_x - domposmin_x) / scell).astype(np.int64)
+    return (cx >= cuts[rank]) & (cx < cuts[rank + 1])

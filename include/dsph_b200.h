@@ -211,6 +211,27 @@ double dsph_last_force_ms(const dsph_ctx *ctx);
  * for fluid and boundary particles; used by the roofline byte model. */
 int dsph_pips(dsph_ctx *ctx,uint64_t *fluid_real,uint64_t *fluid_checked,uint64_t *bound_real,uint64_t *bound_checked);
 
+/* ---- x-slab multi-GPU (new: the reference has no multi-GPU code, only the hooks DCEL_CodeDomLeft/Right
+ *      S/JDsDcellDef.h:30-31 and MGDIV_X S/DualSphDef.h:494-499).  One context per GPU owns the cell columns
+ *      [xcell_lo,xcell_hi) of the domain.  Before every dsph_celldiv_run the caller runs
+ *        dsph_mgpu_count -> exchange counts -> dsph_mgpu_pack -> NCCL send/recv of the records -> dsph_mgpu_unpack
+ *      which moves particles that left the slab to the neighbour (migrants) and appends copies of the neighbour's
+ *      particles within 2h of the cut (ghosts: CODE_PERIODIC, neighbours only, dropped by the next divide), and after
+ *      dsph_forces_launch an all-reduce(max) over dsph_forces_maxima_ptr (4 x uint32 bit patterns of non-negative floats)
+ *      gives every rank the global dt in dsph_forces_finish.  Record = 96 bytes (dsph_mgpu_record_bytes).
+ *      counts[6] = {bound ghosts, fluid migrants, fluid ghosts} for the left neighbour, then for the right one;
+ *      a direction buffer holds its three groups back to back.  Buffers are caller-owned device memory. ---------- */
+int dsph_mgpu_config(dsph_ctx *ctx,int rank,int nranks,uint32_t xcell_lo,uint32_t xcell_hi);
+uint32_t dsph_mgpu_record_bytes(void);
+int dsph_mgpu_count(dsph_ctx *ctx,uint32_t counts[6]);
+int dsph_mgpu_pack(dsph_ctx *ctx,void *send_left,void *send_right);
+int dsph_mgpu_unpack(dsph_ctx *ctx,const uint32_t counts[6],const void *recv_left,const void *recv_right);
+int dsph_forces_launch(dsph_ctx *ctx,int interstep);
+void* dsph_forces_maxima_ptr(dsph_ctx *ctx);
+int dsph_forces_finish(dsph_ctx *ctx,dsph_forceres *res);
+/* domain constants needed to place the cuts: cell size, origin and number of cell columns (JSph::ConfigCellDivision) */
+int dsph_domain_info(const dsph_config *cfg,double *scell,double domposmin[3],uint32_t domcells[3]);
+
 /* ---- case tooling (host only, no GPU): GenCase is a missing blob in the reference, these build the
  *      synthetic benchmark cases of SURVEY.md 8(d) and read/write Case.xml + Case.bi4 ------------- */
 typedef struct dsph_case {
@@ -224,6 +245,9 @@ typedef struct dsph_case {
 } dsph_case;
 /* kind: "dambreak" (DB(N)), "periodicbox" (PB(N)), "nn2layer" (NN(N)); np_target approximate */
 int dsph_case_make(dsph_case *out,const char *kind,uint64_t np_target,uint32_t seed);
+/* same case, but only the particles of the cell columns [cx_lo,cx_hi) are generated (ids, counts and constants are
+ * those of the full case): every rank of a multi-GPU run generates its own x-slab */
+int dsph_case_make_slab(dsph_case *out,const char *kind,uint64_t np_target,uint32_t seed,uint32_t cx_lo,uint32_t cx_hi);
 int dsph_case_free(dsph_case *c);
 int dsph_case_save(const dsph_case *c,const char *dir,const char *casename); /* Case.xml + Case.bi4 */
 int dsph_case_load(dsph_case *out,const char *dir,const char *casename);

@@ -98,6 +98,10 @@ struct Oracle {
   unsigned Npb1=0,Npf1=0,Npb2=0,Npf2=0,Nptot=0,NpbOut=0,NpfOut=0,NpbOutIgnore=0,NpfOutIgnore=0,NpFinal=0,NpbFinal=0,NpbIgnore=0;
   unsigned long long PipsFluidReal=0,PipsFluidChecked=0,PipsBoundReal=0,PipsBoundChecked=0;
   std::string Error;
+  // ---- x-slab decomposition (test twin of csrc/mgpu.cuh; the reference has no multi-GPU code)
+  bool Mgpu=false; int MgRank=0,MgNranks=1; unsigned MgXlo=0,MgXhi=0; unsigned MgCounts[6]={0,0,0,0,0,0};
+  std::vector<unsigned char> MgFlags; unsigned MaxBits[4]={0,0,0,0}; float LastAce2=0,LastVel2=0;
+  bool Ghosts()const{ return PeriActive!=0 || Mgpu; }
 
   void Resize(unsigned n){
     Idp.resize(n); Dcell.resize(n); Code.resize(n); Pos.resize(n); Velrhop.resize(n);
@@ -351,7 +355,7 @@ struct Oracle {
     Nptot=Npb1+Npf1+Npb2+Npf2;
     NpbOut=NpfOut=NpbOutIgnore=NpfOutIgnore=0; NpFinal=NpbFinal=0; NpbIgnore=0;
     if(CellPart.size()<Nptot){ CellPart.resize(Nptot+Nptot/20+128); SortPart.resize(CellPart.size()); BoundDivideOk=false; } // CheckMemoryNp -> AllocMemoryNp resets BoundDivideOk
-    if(boundchanged || PeriActive){ BoundLimitOk=BoundDivideOk=false; for(int i=0;i<3;i++)BoundLimitCellMin[i]=BoundLimitCellMax[i]=BoundDivideCellMin[i]=BoundDivideCellMax[i]=0; }
+    if(boundchanged || PeriActive || Mgpu){ BoundLimitOk=BoundDivideOk=false; for(int i=0;i<3;i++)BoundLimitCellMin[i]=BoundLimitCellMax[i]=BoundDivideCellMin[i]=BoundDivideCellMax[i]=0; }
     CalcCellDomain();
     PrepareNct();
     if(BeginCell.size()<Nctt){ BeginCell.assign(Nctt,0u); PartsInCell.assign(Nctt,0u); BoundDivideOk=false; }   // CheckMemoryNct
@@ -370,7 +374,7 @@ struct Oracle {
   }
   // ---- JSphCpuSingle::RunCellDivide S/JSphCpuSingle.cpp:437-500
   void RunCellDivide(bool updateperiodic){
-    if(updateperiodic && PeriActive)RunPeriodic();
+    if(updateperiodic && PeriActive && !Mgpu)RunPeriodic();
     Divide(BoundChanged);
     SortArray(Idp); SortArray(Code); SortArray(Dcell); SortArray(Pos); SortArray(Velrhop);
     if(TStep==DSPH_STEP_VERLET)SortArray(VelrhopM1);
@@ -434,7 +438,7 @@ struct Oracle {
     const unsigned pini=(cfg.dtallparticles? 0: Npb);
     float vmax=0;
     for(unsigned p=pini;p<Np;p++){ const f4 v=Velrhop[p]; const float v2=v.x*v.x+v.y*v.y+v.z*v.z; if(vmax<v2)vmax=v2; }
-    VelMax=sqrtf(vmax);                                                        // CalcVelMaxSeq/Omp S/JSphCpu.cpp:485-527 (float sqrt)
+    VelMax=sqrtf(vmax); LastVel2=vmax;                                                        // CalcVelMaxSeq/Omp S/JSphCpu.cpp:485-527 (float sqrt)
     ViscDtMax=0;
   }
 
@@ -445,6 +449,7 @@ struct Oracle {
     float vmaxall=viscdt; unsigned long long nreal=0,nchk=0;
     #pragma omp parallel for schedule(guided) reduction(max:vmaxall) reduction(+:nreal,nchk)
     for(int p1=pinit;p1<pfin;p1++){
+      if(Mgpu && CodeIsPeriodic(Code[p1]))continue;   // halo copies: forces are computed by the owning rank
       float visc=0,arp1=0,deltap1=0; f3 acep1={0,0,0}; sym3 gradvelp1={0,0,0,0,0,0};
       f4 shiftposfsp1={0,0,0,0}; if(shift)shiftposfsp1=ShiftPosfs[p1];
       const d3 posp1=Pos[p1]; const f3 velp1={Velrhop[p1].x,Velrhop[p1].y,Velrhop[p1].z};
@@ -617,11 +622,11 @@ struct Oracle {
     // ComputeAceMax S/JSphCpuSingle.cpp:583-636 (periodic particles ignored when PeriActive)
     float amax=0;
     for(unsigned p=Npb;p<Np;p++){
-      const bool use=(!PeriActive || CodeIsNormal(Code[p]));
+      const bool use=(!Ghosts() || CodeIsNormal(Code[p]));
       const f3 a=(use? Ace[p]: f3{0,0,0});
       const float a2=a.x*a.x+a.y*a.y+a.z*a.z; if(amax<a2)amax=a2;
     }
-    AceMax=sqrt(double(amax));
+    AceMax=sqrt(double(amax)); LastAce2=amax;
   }
   // ---- JSphCpu::DtVariable S/JSphCpu.cpp:1614-1639
   double DtVariable(double *pdt1,double *pdt2)const{
@@ -695,6 +700,7 @@ struct Oracle {
     const double dt205=0.5*dt*dt;
     const d3 gravity={double(Gravity.x),double(Gravity.y),double(Gravity.z)};
     for(unsigned p=Npb;p<Np;p++){
+      if(Mgpu && CodeIsPeriodic(Code[p])){ vnew[p]=Velrhop[p]; continue; }
       const float rhopnew=float(double(vr2[p].w)+dt2*Ar[p]);
       const d3 acegr={double(Ace[p].x)+gravity.x,double(Ace[p].y)+gravity.y,double(Ace[p].z)+gravity.z};
       double dx=double(Velrhop[p].x)*dt+acegr.x*dt205, dy=double(Velrhop[p].y)*dt+acegr.y*dt205, dz=double(Velrhop[p].z)*dt+acegr.z*dt205;
@@ -739,7 +745,7 @@ struct Oracle {
     for(unsigned p=Npb;p<Np;p++){
       const typecode rcode=Code[p];
       const bool outrhop=CodeIsOutRhop(rcode);
-      const bool normal=(!PeriActive || outrhop || CodeIsNormal(rcode));
+      const bool normal=(!Ghosts() || outrhop || CodeIsNormal(rcode));
       if(normal){
         if(CodeIsFluid(rcode))UpdatePos(PosPre[p],mov[p].x,mov[p].y,mov[p].z,outrhop,p);
         else Pos[p]=PosPre[p];
@@ -774,13 +780,83 @@ struct Oracle {
     for(unsigned p=Npb;p<Np;p++){
       const typecode rcode=Code[p];
       const bool outrhop=CodeIsOutRhop(rcode);
-      const bool normal=(!PeriActive || outrhop || CodeIsNormal(rcode));
+      const bool normal=(!Ghosts() || outrhop || CodeIsNormal(rcode));
       if(normal){
         if(CodeIsFluid(rcode))UpdatePos(PosPre[p],mov[p].x,mov[p].y,mov[p].z,outrhop,p);
         else Pos[p]=PosPre[p];
       }
     }
     HasPre=false;
+  }
+
+  // ---- x-slab decomposition: same classification / record layout / append order as csrc/mgpu.cuh + Engine::Mg*
+  struct MgRecord{ double pos[3]; f4 velrhop; double pospre[3]; f4 aux; unsigned idp,code; };
+  void MgClassify(unsigned p,int &tl,int &tr)const{
+    tl=tr=-1;
+    const typecode rc=Code[p];
+    if(!CodeIsNormal(rc) || Dcell[p]==0xFFFFFFFFu)return;
+    const unsigned cx=DcCellx(DomCellCode,Dcell[p]); const bool fluid=CodeIsFluid(rc); const unsigned sd=unsigned(ScellDiv);
+    if(MgRank>0){ if(fluid && cx<MgXlo)tl=1; else if(cx<MgXlo+sd && cx>=MgXlo)tl=(fluid? 2: 0); }
+    if(MgRank<MgNranks-1){ if(fluid && cx>=MgXhi)tr=1; else if(cx+sd>=MgXhi && cx<MgXhi)tr=(fluid? 2: 0); }
+  }
+  void MgCount(unsigned counts[6]){
+    for(unsigned p=0;p<Np;p++){ const typecode rc=Code[p]; if(CodeIsPeriodic(rc))Code[p]=typecode(CodeSetNormal(rc)|DSPH_CODE_OUTIGNORE); }
+    MgFlags.assign(Np,0);
+    for(int g=0;g<6;g++)MgCounts[g]=0;
+    for(unsigned p=0;p<Np;p++){
+      int tl,tr; MgClassify(p,tl,tr); unsigned char f=0;
+      if(tl>=0){ f|=(unsigned char)(1u<<tl); MgCounts[tl]++; }
+      if(tr>=0){ f|=(unsigned char)(1u<<(3+tr)); MgCounts[3+tr]++; }
+      MgFlags[p]=f;
+    }
+    for(int g=0;g<6;g++)counts[g]=MgCounts[g];
+  }
+  void MgPack(void *sendleft,void *sendright){
+    MgRecord *out[2]={(MgRecord*)sendleft,(MgRecord*)sendright};
+    const unsigned sd=unsigned(ScellDiv);
+    for(int d=0;d<2;d++){
+      unsigned base=0;
+      for(int kd=0;kd<3;kd++){
+        const int g=3*d+kd; unsigned n=0;
+        for(unsigned p=0;p<Np && MgCounts[g];p++)if((MgFlags[p]>>g)&1u){
+          MgRecord r; memset(&r,0,sizeof(r));
+          r.pos[0]=Pos[p].x; r.pos[1]=Pos[p].y; r.pos[2]=Pos[p].z; r.velrhop=Velrhop[p];
+          if(TStep==DSPH_STEP_SYMPLECTIC && HasPre){ r.pospre[0]=PosPre[p].x; r.pospre[1]=PosPre[p].y; r.pospre[2]=PosPre[p].z; r.aux=VelrhopPre[p]; }
+          if(TStep==DSPH_STEP_VERLET)r.aux=VelrhopM1[p];
+          r.idp=Idp[p];
+          const typecode rc=Code[p];
+          r.code=(kd==1? rc: typecode(CodeSetNormal(rc)|DSPH_CODE_PERIODIC));
+          out[d][base+n]=r; n++;
+          if(kd==1){
+            const unsigned cx=DcCellx(DomCellCode,Dcell[p]);
+            const bool band=(d==0? (cx+sd>=MgXlo): (cx<MgXhi+sd));
+            Code[p]=typecode(CodeSetNormal(rc)|(band? DSPH_CODE_PERIODIC: DSPH_CODE_OUTIGNORE));
+          }
+        }
+        base+=MgCounts[g];
+      }
+    }
+  }
+  void MgUnpack(const unsigned counts[6],const void *recvleft,const void *recvright){
+    const unsigned bgl=counts[0], fl=counts[1]+counts[2], bgr=counts[3], fr=counts[4]+counts[5];
+    const unsigned total=bgl+fl+bgr+fr;
+    if(Idp.size()<size_t(Np)+total)Resize(Np+total+(Np+total)/20+128);
+    unsigned dst=Np;
+    auto up=[&](unsigned n,const MgRecord *src){
+      for(unsigned i=0;i<n;i++){
+        const MgRecord &r=src[i]; const unsigned p=dst+i;
+        Pos[p]={r.pos[0],r.pos[1],r.pos[2]}; Velrhop[p]=r.velrhop;
+        if(TStep==DSPH_STEP_SYMPLECTIC && HasPre){ PosPre[p]={r.pospre[0],r.pospre[1],r.pospre[2]}; VelrhopPre[p]=r.aux; }
+        if(TStep==DSPH_STEP_VERLET)VelrhopM1[p]=r.aux;
+        Idp[p]=r.idp; Code[p]=typecode(r.code);
+        const unsigned cx=unsigned((r.pos[0]-DomPosMin.x)/Scell), cy=unsigned((r.pos[1]-DomPosMin.y)/Scell), cz=unsigned((r.pos[2]-DomPosMin.z)/Scell);
+        Dcell[p]=DcCell(DomCellCode,cx,cy,cz);
+      }
+      dst+=n;
+    };
+    up(bgl,(const MgRecord*)recvleft); up(bgr,(const MgRecord*)recvright);
+    up(fl,(const MgRecord*)recvleft+bgl); up(fr,(const MgRecord*)recvright+bgr);
+    NpbPer=bgl+bgr; NpfPer=fl+fr; Np+=total; BoundChanged=true;
   }
 };
 
@@ -918,6 +994,29 @@ int orc_num_threads(void){
 #else
   return 1;
 #endif
+}
+
+// ---- x-slab decomposition twin (tests/test_mgpu_gloo.py drives two ranks over gloo with this CPU engine) ----
+int orc_mgpu_config(orc_state *s,int rank,int nranks,uint32_t xlo,uint32_t xhi){
+  return Guard([&]{ Oracle &o=s->o; if(o.PeriActive)throw std::runtime_error("x-slab decomposition cannot be combined with periodic boundaries yet.");
+    if(nranks<1||rank<0||rank>=nranks||xlo>=xhi||xhi>o.DomCells[0])throw std::runtime_error("Invalid slab configuration.");
+    o.Mgpu=(nranks>1); o.MgRank=rank; o.MgNranks=nranks; o.MgXlo=xlo; o.MgXhi=xhi; });
+}
+uint32_t orc_mgpu_record_bytes(void){ return 96u; }
+int orc_mgpu_count(orc_state *s,uint32_t counts[6]){ return Guard([&]{ unsigned c[6]; s->o.MgCount(c); for(int i=0;i<6;i++)counts[i]=c[i]; }); }
+int orc_mgpu_pack(orc_state *s,void *sl,void *sr){ return Guard([&]{ s->o.MgPack(sl,sr); }); }
+int orc_mgpu_unpack(orc_state *s,const uint32_t counts[6],const void *rl,const void *rr){ return Guard([&]{ unsigned c[6]; for(int i=0;i<6;i++)c[i]=counts[i]; s->o.MgUnpack(c,rl,rr); }); }
+int orc_forces_launch(orc_state *s,int interstep){
+  (void)interstep;
+  return Guard([&]{ Oracle &o=s->o; o.InteractionForces();
+    float f; f=o.ViscDtMax; memcpy(&o.MaxBits[0],&f,4); f=o.LastAce2; memcpy(&o.MaxBits[1],&f,4); f=o.LastVel2; memcpy(&o.MaxBits[2],&f,4); o.MaxBits[3]=0; });
+}
+void* orc_forces_maxima_ptr(orc_state *s){ return (void*)s->o.MaxBits; }
+int orc_forces_finish(orc_state *s,dsph_forceres *res){
+  return Guard([&]{ Oracle &o=s->o; float f; memcpy(&f,&o.MaxBits[0],4); o.ViscDtMax=f; memcpy(&f,&o.MaxBits[1],4); o.AceMax=sqrt(double(f)); memcpy(&f,&o.MaxBits[2],4); o.VelMax=sqrtf(f); FillForceRes(o,res); });
+}
+int orc_domain_info(const dsph_config *cfg,double *scell,double domposmin[3],uint32_t domcells[3]){
+  return Guard([&]{ Oracle o; o.Configure(*cfg); if(scell)*scell=o.Scell; if(domposmin){ domposmin[0]=o.DomPosMin.x; domposmin[1]=o.DomPosMin.y; domposmin[2]=o.DomPosMin.z; } if(domcells)for(int i=0;i<3;i++)domcells[i]=o.DomCells[i]; });
 }
 
 } // extern "C"

@@ -160,3 +160,15 @@ def test_gpu_large_case_properties(gpu_lib):
     ace, ar = ctx.forces_download()
     assert np.all(np.isfinite(ace)) and np.all(np.isfinite(ar)) and fr.dt > 0
     ctx.close()
+
+
+def test_gpu_two_slabs_equal_single_gpu():
+    """x-slab decomposition over 2 GPUs (NCCL send/recv halos + all-reduce dt) reproduces the single-GPU run."""
+    import subprocess, sys, os, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29531", os.path.join(root, "tests", "mgpu_gpu_check.py"), "200000", "10"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert "MGPU_CHECK PASS" in r.stdout, r.stdout[-3000:]
