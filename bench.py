@@ -150,6 +150,7 @@ def main():
     import dualsphysics_multilayer_b200 as dsph
 
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (no "NCCL version" banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     L = dsph.lib()
@@ -175,14 +176,19 @@ def main():
         # weak scaling: DB(world*np) split into x-slabs of balanced particle count; every rank generates only its slab
         nglobal_target = a.np * world
         info = dsph.make_case_slab("dambreak", nglobal_target, 0, 0)          # constants + counts of the full case
-        probe = dsph.make_case("dambreak", 300_000)                           # same geometry: column CDF for the cuts
-        from dualsphysics_multilayer_b200.capi import SphContext
-        tmpctx_cfg = info.cfg
         sc = C.c_double(); pm = (C.c_double * 3)(); dcl = (C.c_uint32 * 3)()
-        L.check(L.fn("domain_info")(C.byref(tmpctx_cfg), C.byref(sc), pm, dcl))
+        L.check(L.fn("domain_info")(C.byref(info.cfg), C.byref(sc), pm, dcl))
         ncol = int(dcl[0])
-        frac = np.clip((probe.pos[:, 0] - pm[0]) / (sc.value * ncol), 0, 1 - 1e-12)
-        colcount = np.bincount((frac * ncol).astype(np.int64), minlength=ncol).astype(np.float64)
+        # particles per lattice x-index of DB(N) (mkcase geometry: walls at index 0 and NX, bottom at k=0, water column
+        # a x 1.675a x 0.75a at x=0), mapped to cell columns with the arithmetic of the cell hash
+        dp = info.cfg.dp; a_len = 0.4
+        NX, NY, NZ = (int(round(v / dp)) for v in info.caseposmax)
+        FX, FY, FZ = min(int(round(a_len / dp)), NX - 1), NY - 1, min(int(round(0.75 * a_len / dp)), NZ - 1)
+        ii = np.arange(NX + 1)
+        percol = np.where((ii == 0) | (ii == NX), (NY + 1) * (NZ + 1), (NY + 1) + 2 * NZ).astype(np.float64)
+        percol[1:FX + 1] += FY * FZ
+        colidx = ((ii * dp - pm[0]) / sc.value).astype(np.int64)
+        colcount = np.bincount(colidx, weights=percol, minlength=ncol)
         cuts = mgpu.balanced_cuts(colcount, world, 4)
         cd = dsph.make_case_slab("dambreak", nglobal_target, cuts[rank], cuts[rank + 1])
         n = cd.np_

@@ -10,14 +10,15 @@
 
 namespace dsph {
 
-// one record = 96 bytes
+// one record = 88 bytes, 8-byte aligned (plain float arrays: a float4 member would force 16-byte alignment and padding)
 struct MgRecord {
   double pos[3];
-  float4 velrhop;
+  float velrhop[4];
   double pospre[3];
-  float4 aux;          // velrhoppre (Symplectic, mid-step) or velrhopm1 (Verlet)
+  float aux[4];        // velrhoppre (Symplectic, mid-step) or velrhopm1 (Verlet)
   unsigned idp, code;
 };
+static_assert(sizeof(MgRecord)==88,"MgRecord layout is part of the wire format (oracle/sph_oracle.cpp uses the same)");
 
 struct MgArgs {
   unsigned np, npb;
@@ -77,10 +78,10 @@ __global__ void ker_mg_pack(MgArgs a,const unsigned* __restrict__ flags,int bit,
   if(!((flags[p]>>bit)&1u))return;
   MgRecord r;
   r.pos[0]=s.pos[3*size_t(p)]; r.pos[1]=s.pos[3*size_t(p)+1]; r.pos[2]=s.pos[3*size_t(p)+2];
-  r.velrhop=s.velrhop[p];
+  { const float4 v=s.velrhop[p]; r.velrhop[0]=v.x; r.velrhop[1]=v.y; r.velrhop[2]=v.z; r.velrhop[3]=v.w; }
   if(s.pospre){ r.pospre[0]=s.pospre[3*size_t(p)]; r.pospre[1]=s.pospre[3*size_t(p)+1]; r.pospre[2]=s.pospre[3*size_t(p)+2]; }
   else{ r.pospre[0]=r.pospre[1]=r.pospre[2]=0; }
-  r.aux=(s.aux? s.aux[p]: make_float4(0,0,0,0));
+  { const float4 v=(s.aux? s.aux[p]: make_float4(0,0,0,0)); r.aux[0]=v.x; r.aux[1]=v.y; r.aux[2]=v.z; r.aux[3]=v.w; }
   r.idp=s.idp[p];
   const unsigned rc=s.code[p];
   const int kind=bit%3;
@@ -102,9 +103,9 @@ __global__ void ker_mg_unpack(unsigned n,const MgRecord* __restrict__ in,unsigne
   const MgRecord r=in[i];
   const unsigned p=dstbase+i;
   d.pos[3*size_t(p)]=r.pos[0]; d.pos[3*size_t(p)+1]=r.pos[1]; d.pos[3*size_t(p)+2]=r.pos[2];
-  d.velrhop[p]=r.velrhop;
+  d.velrhop[p]=make_float4(r.velrhop[0],r.velrhop[1],r.velrhop[2],r.velrhop[3]);
   if(d.pospre){ d.pospre[3*size_t(p)]=r.pospre[0]; d.pospre[3*size_t(p)+1]=r.pospre[1]; d.pospre[3*size_t(p)+2]=r.pospre[2]; }
-  if(d.aux)d.aux[p]=r.aux;
+  if(d.aux)d.aux[p]=make_float4(r.aux[0],r.aux[1],r.aux[2],r.aux[3]);
   d.idp[p]=r.idp; d.code[p]=typecode(r.code);
   unsigned cx=unsigned((r.pos[0]-c.domposmin[0])/c.scell_d), cy=unsigned((r.pos[1]-c.domposmin[1])/c.scell_d), cz=unsigned((r.pos[2]-c.domposmin[2])/c.scell_d);
   d.dcell[p]=DcCell(c.domcellcode,cx,cy,cz);

@@ -4,7 +4,7 @@ plumbing (NCCL over NVLink on GPUs; gloo on CPU for the tests, where the per-ran
 Per neighbour-list build every rank
   1. classifies its particles (`mgpu_count`): fluid particles whose cell column left the slab migrate to the neighbour,
      particles within 2h (ScellDiv cells) of a cut are copied to the neighbour as ghosts (CODE_PERIODIC: neighbours only),
-  2. exchanges the six counts and then the packed 96-byte records with its <=2 neighbours (send/recv),
+  2. exchanges the six counts and then the packed 88-byte records with its <=2 neighbours (send/recv),
   3. appends what it received (`mgpu_unpack`) and runs the ordinary cell division.
 Per force evaluation the three maxima (viscdt, |ace|^2, |vel|^2: uint32 bit patterns of non-negative floats, so integer
 MAX is float MAX) are all-reduced before the time step is derived, so every rank uses the same dt.

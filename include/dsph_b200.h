@@ -218,7 +218,7 @@ int dsph_pips(dsph_ctx *ctx,uint64_t *fluid_real,uint64_t *fluid_checked,uint64_
  *      which moves particles that left the slab to the neighbour (migrants) and appends copies of the neighbour's
  *      particles within 2h of the cut (ghosts: CODE_PERIODIC, neighbours only, dropped by the next divide), and after
  *      dsph_forces_launch an all-reduce(max) over dsph_forces_maxima_ptr (4 x uint32 bit patterns of non-negative floats)
- *      gives every rank the global dt in dsph_forces_finish.  Record = 96 bytes (dsph_mgpu_record_bytes).
+ *      gives every rank the global dt in dsph_forces_finish.  Record = 88 bytes (dsph_mgpu_record_bytes).
  *      counts[6] = {bound ghosts, fluid migrants, fluid ghosts} for the left neighbour, then for the right one;
  *      a direction buffer holds its three groups back to back.  Buffers are caller-owned device memory. ---------- */
 int dsph_mgpu_config(dsph_ctx *ctx,int rank,int nranks,uint32_t xcell_lo,uint32_t xcell_hi);

@@ -1002,7 +1002,7 @@ int orc_mgpu_config(orc_state *s,int rank,int nranks,uint32_t xlo,uint32_t xhi){
     if(nranks<1||rank<0||rank>=nranks||xlo>=xhi||xhi>o.DomCells[0])throw std::runtime_error("Invalid slab configuration.");
     o.Mgpu=(nranks>1); o.MgRank=rank; o.MgNranks=nranks; o.MgXlo=xlo; o.MgXhi=xhi; });
 }
-uint32_t orc_mgpu_record_bytes(void){ return 96u; }
+uint32_t orc_mgpu_record_bytes(void){ static_assert(sizeof(Oracle::MgRecord)==88,"wire format"); return 88u; }
 int orc_mgpu_count(orc_state *s,uint32_t counts[6]){ return Guard([&]{ unsigned c[6]; s->o.MgCount(c); for(int i=0;i<6;i++)counts[i]=c[i]; }); }
 int orc_mgpu_pack(orc_state *s,void *sl,void *sr){ return Guard([&]{ s->o.MgPack(sl,sr); }); }
 int orc_mgpu_unpack(orc_state *s,const uint32_t counts[6],const void *rl,const void *rr){ return Guard([&]{ unsigned c[6]; for(int i=0;i<6;i++)c[i]=counts[i]; s->o.MgUnpack(c,rl,rr); }); }
