@@ -119,6 +119,15 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--force-variant", type=int, default=0)
     a = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): everything else any library prints (e.g. NCCL's
+    # version banner) goes to stderr; the JSON is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if a.impl == "reference":
@@ -131,11 +140,11 @@ def main():
         t0 = time.time()
         r = run_reference(np_sample, nsteps, threads)
         if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/DualSPHysics5.2CPU_linux64 is missing (built by oracle/Makefile where /root/reference is mounted)"}))
+            emit(({"impl": "reference", "unavailable": "oracle/_ref/DualSPHysics5.2CPU_linux64 is missing (built by oracle/Makefile where /root/reference is mounted)"}))
             return
         sample = ("reference DualSPHysics5.2 CPU solver (OpenMP, %d threads) on dam-break DB(%d) = bounded sample of the %d-particle workload, %d steps, %.1f s"
                   % (threads, r["np"], a.np, r["steps"], r["seconds"]))
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        emit(({"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
                           "warmup": a.warmup, "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": "3D dam-break DB(N), Symplectic+Wendland+artificial+DDT2", "np_sample": r["np"], "np_workload": a.np},
@@ -150,7 +159,6 @@ def main():
     import dualsphysics_multilayer_b200 as dsph
 
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (no "NCCL version" banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     L = dsph.lib()
@@ -193,7 +201,7 @@ def main():
         cd = dsph.make_case_slab("dambreak", nglobal_target, cuts[rank], cuts[rank + 1])
         n = cd.np_
         code = cd.codes()
-        ctx = SphContext(L, cd.cfg, int(n * 1.5) + 200_000, local)
+        ctx = dsph.create_context(cd.cfg, int(n * 1.5) + 200_000, local)
         if a.force_variant:
             l.dsph_set_force_variant(ctx.h, a.force_variant)
         ctx.upload(cd.idp, cd.pos, cd.velrhop, cd.npb, code)
@@ -310,7 +318,7 @@ def main():
                                                                              "cf_preforces", "cf_forces", "su_computestep")}}
         if not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(out))
+        emit(out)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
