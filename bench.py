@@ -118,6 +118,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--force-variant", type=int, default=0)
+    ap.add_argument("--profile-mgpu", action="store_true", help="N>1: 3 extra untimed steps with per-phase host timers (adds syncs)")
+    ap.add_argument("--bound-weight", type=float, default=0.15, help="N>1: cost of a boundary particle relative to a fluid one when balancing the slabs")
     a = ap.parse_args()
     # stdout carries exactly ONE line (the JSON): everything else any library prints (e.g. NCCL's
     # version banner) goes to stderr; the JSON is written to the saved descriptor at the end.
@@ -181,7 +183,7 @@ def main():
         stepfn = ctx.step
         nglobal = n
     else:
-        # weak scaling: DB(world*np) split into x-slabs of balanced particle count; every rank generates only its slab
+        # weak scaling: DB(world*np) split into x-slabs of balanced work (fluid 1, boundary w); every rank generates only its slab
         nglobal_target = a.np * world
         info = dsph.make_case_slab("dambreak", nglobal_target, 0, 0)          # constants + counts of the full case
         sc = C.c_double(); pm = (C.c_double * 3)(); dcl = (C.c_uint32 * 3)()
@@ -193,8 +195,8 @@ def main():
         NX, NY, NZ = (int(round(v / dp)) for v in info.caseposmax)
         FX, FY, FZ = min(int(round(a_len / dp)), NX - 1), NY - 1, min(int(round(0.75 * a_len / dp)), NZ - 1)
         ii = np.arange(NX + 1)
-        percol = np.where((ii == 0) | (ii == NX), (NY + 1) * (NZ + 1), (NY + 1) + 2 * NZ).astype(np.float64)
-        percol[1:FX + 1] += FY * FZ
+        percol = a.bound_weight * np.where((ii == 0) | (ii == NX), (NY + 1) * (NZ + 1), (NY + 1) + 2 * NZ).astype(np.float64)
+        percol[1:FX + 1] += FY * FZ                                     # work-weighted: fluid 1, boundary --bound-weight
         colidx = ((ii * dp - pm[0]) / sc.value).astype(np.int64)
         colcount = np.bincount(colidx, weights=percol, minlength=ncol)
         cuts = mgpu.balanced_cuts(colcount, world, 4)
@@ -304,6 +306,18 @@ def main():
                "d2h_bytes_per_step": nn * (4 + 2 + 24 + 16), "steps": ke,
                "what": "dsph_particles_upload (pinned host -> device) + dsph_celldiv_run + dsph_step + dsph_particles_download per step"}
 
+    phases = None
+    if drv is not None and a.profile_mgpu:
+        drv.prof = {}
+        for _ in range(3):
+            drv.step()
+        mine = {k: 1e3 * v / 3 for k, v in drv.prof.items()}
+        mine["np_owned"] = ctx.np_ - int(ctx.divinfo.npbper) - int(ctx.divinfo.npfper)
+        mine["np_ghost"] = int(ctx.divinfo.npbper) + int(ctx.divinfo.npfper)
+        phases = [None] * world
+        dist.all_gather_object(phases, mine)
+        drv.prof = None
+
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": t_ms.item() / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -311,12 +325,14 @@ def main():
                "config": {"workload": "synthetic 3D dam-break DB(N) (SURVEY.md 8d): Symplectic + Wendland + artificial viscosity 0.1 + DDT2 0.1, DBC walls",
                           "np_per_gpu": n, "nfluid": int(cd.cfg.casenfluid), "pre_steps": a.pre_steps,
                           "np_global": nglobal,
-                          "parallelism": ("single GPU" if world == 1 else "%d x-slabs of balanced particle count; per divide: NCCL send/recv of migrants + 2h halo copies with <=2 neighbours; per force evaluation: all-reduce(max) of the dt maxima" % world),
+                          "parallelism": ("single GPU" if world == 1 else "%d x-slabs of balanced work (fluid 1, boundary %g); per divide: NCCL send/recv of migrants + 2h halo copies with <=2 neighbours; per force evaluation: all-reduce(max) of the dt maxima" % (world, a.bound_weight)),
                           "l2": "working set (np*~230 B) is far larger than the 126 MB L2; no flush needed"},
                "roofline": roofline, "e2e": e2e, "gpu_launches": int(tm.kernel_launches), "clocks": sampler.result(),
                "timers_ms_per_step": {k: getattr(tm, k) / a.steps for k in ("nl_limits", "nl_presort", "nl_radixsort", "nl_cellbegin", "nl_sortdata",
                                                                              "cf_preforces", "cf_forces", "su_computestep")}}
-        if not a.no_cpu_baseline:
+        if phases is not None:
+            out["mgpu_phases_ms_per_step"] = phases
+        if not a.no_cpu_baseline and world == 1:                         # the CPU baseline is reported at N=1 only
             out["cpu_baseline"] = cpu_baseline()
         emit(out)
     ctx.close()

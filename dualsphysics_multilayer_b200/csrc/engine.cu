@@ -547,52 +547,48 @@ void Engine::MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi){
   if(nranks>1 && xhi-xlo<2u*unsigned(k.scelldiv)+1u)throw EngineError(DSPH_ERR_ARG,"The slab is narrower than 2 halo widths + 1 cell.");
   mgpu=(nranks>1); mgrank=rank; mgnranks=nranks; mgxlo=xlo; mgxhi=xhi;
   dc.ghosts=(k.periactive||mgpu)? 1: 0;
-  if(mgpu)for(int i=0;i<3;i++)DevAlloc(mgscratch[i],size_t(cap));
+  for(int i=0;i<3;i++)DevFree(mgscratch[i]);
+  if(mgpu){
+    DevAlloc(mgscratch[0],6*(size_t(cap)+MG_BLOCK-1)/MG_BLOCK+8);   // per-block class counts -> offsets
+    DevAlloc(mgscratch[1],size_t(8));                                // class totals
+    DevAlloc(mgscratch[2],size_t(cap)/4+2);                          // one flag byte per particle
+  }
 }
 void Engine::MgCount(unsigned counts[6]){
   if(!mgpu)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_count needs dsph_mgpu_config with more than one rank.");
-  const int B=256; const unsigned nb=(np+B-1)/B;
-  CUCHECK(cudaEventRecord(ev[0],stm));
-  // halo copies of the previous divide are dropped by the next sort
-  ker_peri_ignore<<<nb,B,0,stm>>>(np,code[cur]); launches++;
+  const unsigned nb=(np+MG_BLOCK-1)/MG_BLOCK;
+  for(int g=0;g<6;g++)mgcounts[g]=counts[g]=0;
+  mgcounted=true;
+  if(!np)return;
   MgArgs a; a.np=np; a.npb=npb; a.xlo=mgxlo; a.xhi=mgxhi; a.sd=unsigned(k.scelldiv);
   a.hasleft=(mgrank>0); a.hasright=(mgrank<mgnranks-1); a.domcellcode=k.domcellcode; a.dcell=dcell[cur]; a.code=code[cur];
-  unsigned *flags=mgscratch[2];
-  unsigned *off[6]={rs.keys[0],rs.keys[1],rs.vals[0],rs.vals[1],mgscratch[0],mgscratch[1]};
-  ker_mg_flags<<<nb,B,0,stm>>>(a,flags); launches++;
-  for(int g=0;g<6;g++){
-    ker_mg_bit<<<nb,B,0,stm>>>(np,flags,g,off[g]); launches++;
-    CUCHECK(cudaMemcpyAsync(&hpin->scratch[g],off[g]+(np-1),4,cudaMemcpyDeviceToHost,stm));     // last flag
-    DeviceExclusiveScan(off[g],np,rs.chunksum,rs.chunksum2,stm,&launches);
-    CUCHECK(cudaMemcpyAsync(&hpin->mgtot[g],off[g]+(np-1),4,cudaMemcpyDeviceToHost,stm));       // last offset
-  }
+  // one pass: retire the halo copies of the previous divide (dropped by the next sort), classify, count per block
+  ker_mg_classify<<<nb,MG_BLOCK,0,stm>>>(a,(unsigned char*)mgscratch[2],mgscratch[0]); launches++;
+  ker_mg_scanblocks<<<6,1024,0,stm>>>(nb,mgscratch[0],mgscratch[1]); launches++;
+  CUCHECK(cudaMemcpyAsync(hpin->mgtot,mgscratch[1],6*sizeof(unsigned),cudaMemcpyDeviceToHost,stm));
   CUCHECK(cudaStreamSynchronize(stm));
-  for(int g=0;g<6;g++){ mgcounts[g]=hpin->scratch[g]+hpin->mgtot[g]; counts[g]=mgcounts[g]; }
-  mgcounted=true;
+  for(int g=0;g<6;g++)mgcounts[g]=counts[g]=hpin->mgtot[g];
 }
 void Engine::MgPack(void *sendleft,void *sendright){
   if(!mgcounted)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_pack needs dsph_mgpu_count first.");
   mgcounted=false;
-  const int B=256; const unsigned nb=(np+B-1)/B;
+  const unsigned nb=(np+MG_BLOCK-1)/MG_BLOCK;
   MgArgs a; a.np=np; a.npb=npb; a.xlo=mgxlo; a.xhi=mgxhi; a.sd=unsigned(k.scelldiv);
   a.hasleft=(mgrank>0); a.hasright=(mgrank<mgnranks-1); a.domcellcode=k.domcellcode; a.dcell=dcell[cur]; a.code=code[cur];
-  unsigned *flags=mgscratch[2];
-  unsigned *off[6]={rs.keys[0],rs.keys[1],rs.vals[0],rs.vals[1],mgscratch[0],mgscratch[1]};
   const unsigned *counts=mgcounts;
   void *sendbuf[2]={sendleft,sendright};
   MgPackArrays sp; sp.idp=idp[cur]; sp.code=code[cur]; sp.pos=pos[cur]; sp.velrhop=velrhop[cur];
   sp.pospre=(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre? pospre[cur]: nullptr);
   sp.aux=(cfg.tstep==DSPH_STEP_SYMPLECTIC? (haspre? velrhoppre[cur]: nullptr): velrhopm1[cur]);
+  MgBases bases; unsigned total=0;
   for(int d=0;d<2;d++){
     const unsigned tot=counts[3*d]+counts[3*d+1]+counts[3*d+2];
     if(tot && !sendbuf[d])throw EngineError(DSPH_ERR_ARG,"Null send buffer.");
     unsigned base=0;
-    for(int kd=0;kd<3;kd++){
-      const int g=3*d+kd;
-      if(counts[g]){ ker_mg_pack<<<nb,B,0,stm>>>(a,flags,g,off[g],base,sp,(MgRecord*)sendbuf[d]); launches++; }
-      base+=counts[g];
-    }
+    for(int kd=0;kd<3;kd++){ bases.v[3*d+kd]=base; base+=counts[3*d+kd]; }
+    total+=tot;
   }
+  if(total){ ker_mg_pack<<<nb,MG_BLOCK,0,stm>>>(a,(const unsigned char*)mgscratch[2],mgscratch[0],bases,sp,(MgRecord*)sendleft,(MgRecord*)sendright); launches++; }
   CUCHECK(cudaStreamSynchronize(stm));
   CUCHECK(cudaGetLastError());
 }

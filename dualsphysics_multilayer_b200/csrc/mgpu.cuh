@@ -47,20 +47,68 @@ __device__ __forceinline__ void MgClassify(unsigned p,const MgArgs &a,int &tolef
   }
 }
 
-// counts[dir*3+kind] per particle are scanned separately: 6 count arrays of np entries would be heavy; instead each
-// particle writes a packed 6 x 1-bit word and six scans run over extracted bits (np is per-GPU, the pass is cheap).
-__global__ void ker_mg_flags(MgArgs a,unsigned* __restrict__ flags){
-  const unsigned p=blockIdx.x*blockDim.x+threadIdx.x;
-  if(p>=a.np)return;
-  int tl,tr; bool ml,mr; MgClassify(p,a,tl,tr,ml,mr);
+// Deterministic (index-ordered) compaction in two passes over one byte per particle:
+//  ker_mg_classify  flags[p] = 6 one-bit classes, per-block class counts (also retires the ghosts of the previous divide)
+//  ker_mg_scanblocks  exclusive scan of the per-block counts of each class (one CTA per class), class totals
+//  ker_mg_pack        rank inside the block by ballot/popc + block offset -> record slot
+#define MG_BLOCK 256
+__global__ void __launch_bounds__(MG_BLOCK) ker_mg_classify(MgArgs a,unsigned char* __restrict__ flags,unsigned* __restrict__ blockcnt){
+  __shared__ unsigned wcnt[6][MG_BLOCK/32];
+  const unsigned p=blockIdx.x*MG_BLOCK+threadIdx.x;
   unsigned f=0;
-  if(tl>=0)f|=1u<<tl;
-  if(tr>=0)f|=1u<<(3+tr);
-  flags[p]=f;
+  if(p<a.np){
+    const unsigned rc=a.code[p];
+    if((rc&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_PERIODIC)a.code[p]=typecode((rc&(~DSPH_CODE_MASKSPECIAL))|DSPH_CODE_OUTIGNORE);
+    int tl,tr; bool ml,mr; MgClassify(p,a,tl,tr,ml,mr);
+    if(tl>=0)f|=1u<<tl;
+    if(tr>=0)f|=1u<<(3+tr);
+    flags[p]=(unsigned char)f;
+  }
+  const unsigned w=threadIdx.x>>5, lane=threadIdx.x&31;
+  #pragma unroll
+  for(int g=0;g<6;g++){
+    const unsigned bal=__ballot_sync(0xffffffffu,(f>>g)&1u);
+    if(lane==0)wcnt[g][w]=__popc(bal);
+  }
+  __syncthreads();
+  if(threadIdx.x<6){
+    unsigned t=0;
+    #pragma unroll
+    for(int i=0;i<MG_BLOCK/32;i++)t+=wcnt[threadIdx.x][i];
+    blockcnt[size_t(threadIdx.x)*gridDim.x+blockIdx.x]=t;
+  }
 }
-__global__ void ker_mg_bit(unsigned n,const unsigned* __restrict__ flags,int bit,unsigned* __restrict__ out){
-  const unsigned p=blockIdx.x*blockDim.x+threadIdx.x;
-  if(p<n)out[p]=(flags[p]>>bit)&1u;
+// grid = 6 CTAs of 1024 threads: in-place exclusive scan of blockcnt[g*nb .. g*nb+nb), total[g]
+__global__ void __launch_bounds__(1024) ker_mg_scanblocks(unsigned nb,unsigned* __restrict__ blockcnt,unsigned* __restrict__ total){
+  __shared__ unsigned wsum[32];
+  __shared__ unsigned carry;
+  unsigned *v=blockcnt+size_t(blockIdx.x)*nb;
+  const unsigned w=threadIdx.x>>5, lane=threadIdx.x&31;
+  if(threadIdx.x==0)carry=0;
+  __syncthreads();
+  for(unsigned base=0;base<nb;base+=1024){
+    const unsigned i=base+threadIdx.x;
+    const unsigned x=(i<nb? v[i]: 0u);
+    unsigned inc=x;
+    #pragma unroll
+    for(int d=1;d<32;d<<=1){ const unsigned y=__shfl_up_sync(0xffffffffu,inc,d); if(lane>=unsigned(d))inc+=y; }
+    if(lane==31)wsum[w]=inc;
+    __syncthreads();
+    if(w==0){
+      unsigned t=wsum[lane];
+      #pragma unroll
+      for(int d=1;d<32;d<<=1){ const unsigned y=__shfl_up_sync(0xffffffffu,t,d); if(lane>=unsigned(d))t+=y; }
+      wsum[lane]=t;
+    }
+    __syncthreads();
+    const unsigned c0=carry;
+    const unsigned excl=c0+(w? wsum[w-1]: 0u)+inc-x;
+    if(i<nb)v[i]=excl;
+    __syncthreads();
+    if(threadIdx.x==1023)carry=c0+wsum[31];
+    __syncthreads();
+  }
+  if(threadIdx.x==0)total[blockIdx.x]=carry;
 }
 
 struct MgPackArrays {
@@ -68,14 +116,26 @@ struct MgPackArrays {
   const double *pospre; const float4 *aux;
 };
 
-// writes the records of one (direction,kind) group; migrants are converted locally: inside the halo band of the
+struct MgBases { unsigned v[6]; };   // first record slot of each class inside its send buffer
+
+// writes the records of all classes; migrants are converted locally: inside the halo band of the
 // neighbour they stay as ghosts (CODE_PERIODIC), otherwise they are dropped by the next sort (CODE_OUTIGNORE)
-__global__ void ker_mg_pack(MgArgs a,const unsigned* __restrict__ flags,int bit,const unsigned* __restrict__ offset,unsigned base,
-  MgPackArrays s,MgRecord* __restrict__ out)
+__global__ void __launch_bounds__(MG_BLOCK) ker_mg_pack(MgArgs a,const unsigned char* __restrict__ flags,const unsigned* __restrict__ blockoff,
+  MgBases bases,MgPackArrays s,MgRecord* __restrict__ outleft,MgRecord* __restrict__ outright)
 {
-  const unsigned p=blockIdx.x*blockDim.x+threadIdx.x;
-  if(p>=a.np)return;
-  if(!((flags[p]>>bit)&1u))return;
+  __shared__ unsigned wcnt[6][MG_BLOCK/32];
+  const unsigned p=blockIdx.x*MG_BLOCK+threadIdx.x;
+  const unsigned f=(p<a.np? flags[p]: 0u);
+  const unsigned w=threadIdx.x>>5, lane=threadIdx.x&31;
+  unsigned rank[6];
+  #pragma unroll
+  for(int g=0;g<6;g++){
+    const unsigned bal=__ballot_sync(0xffffffffu,(f>>g)&1u);
+    rank[g]=__popc(bal&((1u<<lane)-1u));
+    if(lane==0)wcnt[g][w]=__popc(bal);
+  }
+  __syncthreads();
+  if(!f)return;
   MgRecord r;
   r.pos[0]=s.pos[3*size_t(p)]; r.pos[1]=s.pos[3*size_t(p)+1]; r.pos[2]=s.pos[3*size_t(p)+2];
   { const float4 v=s.velrhop[p]; r.velrhop[0]=v.x; r.velrhop[1]=v.y; r.velrhop[2]=v.z; r.velrhop[3]=v.w; }
@@ -84,13 +144,18 @@ __global__ void ker_mg_pack(MgArgs a,const unsigned* __restrict__ flags,int bit,
   { const float4 v=(s.aux? s.aux[p]: make_float4(0,0,0,0)); r.aux[0]=v.x; r.aux[1]=v.y; r.aux[2]=v.z; r.aux[3]=v.w; }
   r.idp=s.idp[p];
   const unsigned rc=s.code[p];
-  const int kind=bit%3;
-  r.code=(kind==1? rc: ((rc&(~DSPH_CODE_MASKSPECIAL))|DSPH_CODE_PERIODIC));   // migrants stay normal, halo copies are ghosts
-  out[base+offset[p]]=r;
-  if(kind==1){ // migrant: local copy becomes a ghost when it is still inside the neighbour's halo band, else it is dropped
-    const unsigned cx=DcCellx(a.domcellcode,a.dcell[p]);
-    const bool band=(bit<3? (cx+a.sd>=a.xlo): (cx<a.xhi+a.sd));
-    s.code[p]=typecode((rc&(~DSPH_CODE_MASKSPECIAL))|(band? DSPH_CODE_PERIODIC: DSPH_CODE_OUTIGNORE));
+  #pragma unroll
+  for(int g=0;g<6;g++)if((f>>g)&1u){
+    unsigned slot=bases.v[g]+blockoff[size_t(g)*gridDim.x+blockIdx.x]+rank[g];
+    for(unsigned i=0;i<w;i++)slot+=wcnt[g][i];
+    const int kind=g%3;
+    r.code=(kind==1? rc: ((rc&(~DSPH_CODE_MASKSPECIAL))|DSPH_CODE_PERIODIC));   // migrants stay normal, halo copies are ghosts
+    (g<3? outleft: outright)[slot]=r;
+    if(kind==1){ // migrant: local copy becomes a ghost when it is still inside the neighbour's halo band, else it is dropped
+      const unsigned cx=DcCellx(a.domcellcode,a.dcell[p]);
+      const bool band=(g<3? (cx+a.sd>=a.xlo): (cx<a.xhi+a.sd));
+      s.code[p]=typecode((rc&(~DSPH_CODE_MASKSPECIAL))|(band? DSPH_CODE_PERIODIC: DSPH_CODE_OUTIGNORE));
+    }
   }
 }
 

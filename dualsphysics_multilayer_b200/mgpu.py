@@ -12,6 +12,7 @@ MAX is float MAX) are all-reduced before the time step is derived, so every rank
 from __future__ import annotations
 
 import ctypes as C
+import time
 
 import numpy as np
 import torch
@@ -61,6 +62,7 @@ class SlabDriver:
         else:
             self.maxima = torch.from_numpy(np.ctypeslib.as_array((C.c_int32 * 4).from_address(ptr)))
         self.sent_records = 0
+        self.prof = None                      # set to {} to accumulate wall seconds per phase (adds device syncs)
         self.symplectic = (ctx.cfg.tstep == capi.STEP_SYMPLECTIC)
 
     # ---- buffers -------------------------------------------------------------------------------------------------
@@ -77,7 +79,9 @@ class SlabDriver:
         if self.world == 1:
             return
         ctx = self.ctx
+        t0 = self._tick()
         counts = ctx.mgpu_count()                                   # [L: bg, fm, fg, R: bg, fm, fg]
+        t0 = self._tick("xch_count", t0)
         mine = torch.tensor(counts, dtype=torch.int64, device=self.device)
         fromleft = torch.zeros(3, dtype=torch.int64, device=self.device)
         fromright = torch.zeros(3, dtype=torch.int64, device=self.device)
@@ -91,8 +95,10 @@ class SlabDriver:
             w.wait()
         nl, nr = int(sum(counts[0:3])), int(sum(counts[3:6]))
         rl = [int(v) for v in fromleft.tolist()]; rr = [int(v) for v in fromright.tolist()]
+        t0 = self._tick("xch_counts_comm", t0)
         sl, sr = self._buffer("sl", nl), self._buffer("sr", nr)
         ctx.mgpu_pack(sl.data_ptr(), sr.data_ptr())
+        t0 = self._tick("xch_pack", t0)
         bl, br = self._buffer("rl", sum(rl)), self._buffer("rr", sum(rr))
         ops = []
         if self.left is not None:
@@ -110,16 +116,33 @@ class SlabDriver:
                 w.wait()
         if self.device.type == "cuda":
             torch.cuda.current_stream().synchronize()
+        t0 = self._tick("xch_records_comm", t0)
         ctx.mgpu_unpack(rl + rr, bl.data_ptr(), br.data_ptr())
+        self._tick("xch_unpack", t0)
         self.sent_records += nl + nr
+
+    def _tick(self, name=None, t0=0.0):
+        if self.prof is None:
+            return 0.0
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+        t = time.perf_counter()
+        if name:
+            self.prof[name] = self.prof.get(name, 0.0) + (t - t0)
+        return t
 
     # ---- the step pieces (same sequence as JSphGpuSingle::ComputeStep_Sym/_Ver + closing divide) -------------------
     def celldiv(self):
         self.exchange()
-        return self.ctx.celldiv(False)
+        t0 = self._tick()
+        r = self.ctx.celldiv(False)
+        self._tick("celldiv", t0)
+        return r
 
     def forces(self, interstep):
+        t0 = self._tick()
         self.ctx.forces_launch(interstep)
+        t0 = self._tick("forces_kernels", t0)
         if self.world > 1:
             if self.device.type == "cuda":
                 # the library launched on its own stream: make torch's stream wait for it through a device-wide sync
@@ -127,6 +150,7 @@ class SlabDriver:
             dist.all_reduce(self.maxima, op=dist.ReduceOp.MAX, group=self.group)
             if self.device.type == "cuda":
                 torch.cuda.synchronize()
+        t0 = self._tick("dt_allreduce", t0)
         return self.ctx.forces_finish()
 
     def step(self):
