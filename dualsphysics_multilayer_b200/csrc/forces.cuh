@@ -114,7 +114,7 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT,bool BOUNDP2> __device__ __forc
   if(TDDT==DSPH_DDT_DDT2 || (TDDT==DSPH_DDT_DDT2FULL && !BOUNDP2)){
     if(a.delta!=FLT_MAX){
       const float rh=1.f+c.ddtgz*drz;
-      const float drhop=c.rhopzero*PowNearOne(rh,c)-c.rhopzero;
+      const float drhop=c.rhopzero*(PowNearOne(rh,c)-1.f);   // the reference's fast-math build evaluates rho0*(pow-1)
       const float visc_densi=c.ddtkh*cbar*((velrhop2.w-rhopp1)-drhop)/(rr2+c.eta2);
       const float dot3=(drx*frx+dry*fry+drz*frz);
       const float delta=visc_densi*dot3*massp2/velrhop2.w;

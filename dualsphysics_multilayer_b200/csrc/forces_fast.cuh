@@ -75,7 +75,7 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ voi
     if(boundp2){ if(TDDT==DSPH_DDT_DDT2)anybound=1u; }
     else{
       const float rh=1.f+c.ddtgz*drz;
-      const float drhop=c.rhopzero*PowNearOne(rh,c)-c.rhopzero;
+      const float drhop=c.rhopzero*(PowNearOne(rh,c)-1.f);   // rho0*(pow-1): the form the reference binary evaluates
       const float visc_densi=c.ddtkh*cbar*((velrhop2.w-rhopp1)-drhop)*ovrr;
       const float dot3=(drx*frx+dry*fry+drz*frz);
       a.delta-=visc_densi*dot3*massp2*ov2;

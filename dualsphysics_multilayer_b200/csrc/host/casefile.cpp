@@ -276,6 +276,15 @@ void LoadCase(CaseData &cd,const std::string &dir,const std::string &casename){
     const unsigned nbound=c.casenfixed+c.casenmoving;
     if(nbound){ unsigned last=0; for(unsigned q=0;q<p.npok;q++)if(cd.idp[q]<nbound && q>last)last=q; if(last+1!=nbound)throw std::runtime_error("Order of boundary (fixed and moving) particles is invalid."); }
   }
+  if(c.nn_on){ // JSph::LoadMultiphaseData M/JSph.cpp:3247-3263: the fluid starts at the rest density of its phase
+    std::vector<dsph_typecode> code(p.npok);
+    ComputeCodes(cd,p.npok,cd.idp.data(),code.data());
+    for(unsigned i=0;i<p.npok;i++)if((code[i]&DSPH_CODE_MASKTYPE)==DSPH_CODE_TYPE_FLUID){
+      const unsigned cp=code[i]&DSPH_CODE_MASKVALUE;
+      if(cp>=unsigned(c.nn_nphases))throw std::runtime_error("Fluid particle without phase information...");
+      cd.velrhop[4*i+3]=c.phases[cp].rho;
+    }
+  }
   const bool mapsizeloaded=(h.mapposmin[0]!=h.mapposmax[0]||h.mapposmin[1]!=h.mapposmax[1]||h.mapposmin[2]!=h.mapposmax[2]);
   if(mapsizeloaded){ memcpy(c.maprealposmin,h.mapposmin,24); memcpy(c.maprealposmax,h.mapposmax,24); }
   else ComputeMapRealPos(cd);

@@ -41,9 +41,9 @@ inline unsigned DcelBits(unsigned v,unsigned minbits){ unsigned n=minbits; for(;
 inline unsigned DcelGetCode(unsigned sx,unsigned sy,unsigned sz){
   return ((sx+1)<<25)|(sy<<20)|(sz<<15)|((sy+sz)<<10)|((sx+1+sz)<<5)|(sx+1+sy);
 }
-inline unsigned CalcCellCode(unsigned ncx,unsigned ncy,unsigned ncz){
+// maxbits: 31 in v5.2 (S/JDsDcell.cpp:39-68); the multiphase fork (v5.0) distributes 32 (M/JSph.cpp:1794-1822)
+inline unsigned CalcCellCode(unsigned ncx,unsigned ncy,unsigned ncz,unsigned maxbits=31){
   unsigned sx=DcelBits(ncx,2), sy=DcelBits(ncy,2), sz=DcelBits(ncz,2);
-  const unsigned maxbits=31;
   if(sx+sy+sz>maxbits)return 0;
   unsigned rest=maxbits-(sx+sy+sz);
   while(rest){
@@ -90,6 +90,7 @@ inline void DeriveConstants(const dsph_config &c,SphConst &k){
   k.ddtgz=float(double(c.rhopzero)*double(fabsf(c.gravity[2]))/double(c.cteb));
   k.dtini=(c.dtini>0? c.dtini: double(c.kernelh)/k.cs0);
   k.dtmin=(c.dtmin>0? c.dtmin: (double(c.kernelh)/k.cs0)*double(c.coefdtmin));
+  if(c.nn_on){ float coefdtmin=c.coefdtmin; coefdtmin*=1.0e-5f; k.dtmin=(c.kernelh/k.cs0)*coefdtmin; }   // JSph::ConfigConstantsMP M/JSph.cpp:3240-3241
   // ---- map limits
   for(int i=0;i<3;i++){ k.maprealposmin[i]=c.maprealposmin[i]; k.maprealposmax[i]=c.maprealposmax[i]; k.maprealsize[i]=k.maprealposmax[i]-k.maprealposmin[i]; }
   for(int i=0;i<3;i++){ k.perixinc[i]=c.perixinc[i]; k.periyinc[i]=c.periyinc[i]; k.perizinc[i]=c.perizinc[i]; }
@@ -120,7 +121,7 @@ inline void DeriveConstants(const dsph_config &c,SphConst &k){
     if(k.domrealposmax[i]>k.maprealposmax[i])k.domrealposmax[i]=k.maprealposmax[i];
     if(k.domrealposmin[i]<k.maprealposmin[i])k.domrealposmin[i]=k.maprealposmin[i];
   }
-  k.domcellcode=CalcCellCode(k.domcells[0]+1,k.domcells[1]+1,k.domcells[2]+1);
+  k.domcellcode=CalcCellCode(k.domcells[0]+1,k.domcells[1]+1,k.domcells[2]+1,(c.nn_on? 32u: 31u));
   if(!k.domcellcode)throw std::runtime_error("Failed to select a valid CellCode for the number of cells.");
 }
 

@@ -17,7 +17,9 @@
 #include "JAppInfo.h"
 #include "JLog2.h"
 #include "JException.h"
+#ifndef HARNESS_NN
 #include "JDsTimersCpu.h"
+#endif
 #include "JArraysCpu.h"
 #include "JSphShifting.h"
 #include "JDsOutputTime.h"
@@ -74,6 +76,13 @@ class RefHarness : public JSphCpuSingle {
     w.Add("ace",3,3,Np,Acec); w.Add("ar",3,1,Np,Arc);
     if(ShiftPosfsc)w.Add("shiftposfs",3,4,Np,ShiftPosfsc);
     if(SpsTauc)w.Add("spstau",3,6,Np,SpsTauc);
+#ifdef HARNESS_NN
+    if(Pressc)w.Add("press",3,1,Np,Pressc);
+    if(Visco_etac)w.Add("visco_eta",3,1,Np,Visco_etac);
+    if(SpsGradvelc)w.Add("gradvel",3,6,Np,SpsGradvelc);
+    if(D_tensorc)w.Add("d_tensor",3,6,Np,D_tensorc);
+    w.F32("viscetadtmax",ViscEtaDtMax);
+#endif
     w.F32("viscdtmax",ViscDtMax); w.F64("acemax",AceMax); w.F64("velmax",VelMax); w.F64("dt",dt);
   }
   void DumpConstants(){
@@ -95,6 +104,18 @@ class RefHarness : public JSphCpuSingle {
     w.U32("casenp",CaseNp); w.U32("casenfixed",CaseNfixed); w.U32("casenfluid",CaseNfluid);
     const double pi[9]={PeriXinc.x,PeriXinc.y,PeriXinc.z,PeriYinc.x,PeriYinc.y,PeriYinc.z,PeriZinc.x,PeriZinc.y,PeriZinc.z};
     w.Add("periinc",4,9,1,pi);
+#ifdef HARNESS_NN
+    w.U32("multiphase",MultiPhase? 1u: 0u); w.U32("tvelgrad",unsigned(TVelGrad)); w.U32("phasecount",PhaseCount); w.F32("lamda",lamda);
+    if(MultiPhase){
+      std::vector<float> ph;
+      for(unsigned c=0;c<PhaseCount;c++){
+        const StPhaseArray &a=PhaseArray[c]; const StPhaseCte &k=PhaseCte[c];
+        const float v[12]={float(k.mkfluid),a.rho,a.mass,a.Cs0,a.CteB,a.Gamma,k.visco,k.tau_yield,k.tau_max,k.Bi_multi,k.m_NN,k.n_NN};
+        ph.insert(ph.end(),v,v+12);
+      }
+      w.Add("phases",3,12,PhaseCount,ph.data());
+    }
+#endif
   }
 
   //-Same call sequence as JSphCpuSingle::ComputeStep_Sym, with dumps in between.
@@ -133,6 +154,24 @@ class RefHarness : public JSphCpuSingle {
 
   //-Replays JSphCpuSingle::Run (initialisation and main loop) without PART output bookkeeping.
   void RunDump(std::string appname,const JSphCfgRun *cfg,JLog2 *log){
+#ifdef HARNESS_NN
+    // M/JSphCpuSingle.cpp:1085-1115
+    AppName=appname; Log=log;
+    TmcCreation(Timers,cfg->SvTimers);
+    TmcStart(Timers,TMC_Init);
+    LoadConfig(const_cast<JSphCfgRun*>(cfg));
+    LoadCaseParticles();
+    VisuConfig();
+    ConfigDomain();
+    ConfigRunMode(cfg);
+    VisuParticleSummary();
+    InitRunCpu();
+    FreePartsInit();
+    UpdateMaxValues();
+    SaveData();
+    TmcResetValues(Timers);
+    TmcStop(Timers,TMC_Init);
+#else
     AppName=appname; Log=log; CfgRun=cfg;
     Timersc->Config(cfg->SvTimers);
     Timersc->TmStart(TMC_Init);
@@ -148,6 +187,7 @@ class RefHarness : public JSphCpuSingle {
     SaveData();
     Timersc->ResetTimes();
     Timersc->TmStop(TMC_Init);
+#endif
     PartNstep=-1; Part++;
     DumpConstants();
     TimerSim.Start(); TimerPart.Start();

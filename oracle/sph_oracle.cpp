@@ -39,6 +39,7 @@ inline bool CodeIsNormal(typecode c){ return CodeSpecial(c)==DSPH_CODE_NORMAL; }
 inline bool CodeIsPeriodic(typecode c){ return CodeSpecial(c)==DSPH_CODE_PERIODIC; }
 inline bool CodeIsFluid(typecode c){ return CodeType(c)==DSPH_CODE_TYPE_FLUID; }
 inline bool CodeIsFixed(typecode c){ return CodeType(c)==DSPH_CODE_TYPE_FIXED; }
+inline unsigned CodeTypeValue(typecode c){ return c&DSPH_CODE_MASKVALUE; }
 inline bool CodeIsOutRhop(typecode c){ return CodeSpecial(c)==DSPH_CODE_OUTRHOP; }
 inline typecode CodeSetNormal(typecode c){ return c&(~DSPH_CODE_MASKSPECIAL); }
 
@@ -50,10 +51,11 @@ inline unsigned DcCelly(unsigned dcc,unsigned cel){ return (cel<<(dcc>>25))>>((d
 inline unsigned DcCellz(unsigned dcc,unsigned cel){ return (cel<<(dcc&31))>>(dcc&31); }
 inline unsigned DcCell(unsigned dcc,unsigned cx,unsigned cy,unsigned cz){ return (cx<<((dcc>>10)&31))|(cy<<((dcc>>15)&31))|cz; }
 // JDsDcell::CalcCellDistribution/CalcCellCode: S/JDsDcell.cpp:39-68
-unsigned CalcCellCode(unsigned nx,unsigned ny,unsigned nz){
+// (the v5.0 multiphase fork distributes 32 bits instead of 31: JSph::CalcCellDistribution M/JSph.cpp:1794-1822)
+unsigned CalcCellCode(unsigned nx,unsigned ny,unsigned nz,unsigned maxbits){
   unsigned sx=DcBits(nx,2),sy=DcBits(ny,2),sz=DcBits(nz,2);
-  if(sx+sy+sz>31)return 0;
-  unsigned rest=31-(sx+sy+sz);
+  if(sx+sy+sz>maxbits)return 0;
+  unsigned rest=maxbits-(sx+sy+sz);
   while(rest){ if(rest){ sx++; rest--; } if(rest){ sy++; rest--; } if(rest){ sz++; rest--; } }
   return DcCode(sx,sy,sz);
 }
@@ -102,6 +104,11 @@ struct Oracle {
   bool Mgpu=false; int MgRank=0,MgNranks=1; unsigned MgXlo=0,MgXhi=0; unsigned MgCounts[6]={0,0,0,0,0,0};
   std::vector<unsigned char> MgFlags; unsigned MaxBits[4]={0,0,0,0}; float LastAce2=0,LastVel2=0;
   bool Ghosts()const{ return PeriActive!=0 || Mgpu; }
+  // ---- multiphase non-Newtonian fork (M/JSph.h:519-531, M/DualSphDef.h StPhaseCte/StPhaseArray, M/JSphCpu.h:363-371)
+  struct Phase{ float rho,mass,cs0,cteb,gamma,visco,tau_yield,tau_max,bi_multi,m_nn,n_nn; };
+  bool MultiPhase=false; int TVelGrad=0; unsigned PhaseCount=0; float Lamda=0.2f; Phase Ph[DSPH_MAXPHASES];
+  std::vector<float> ViscoEta; std::vector<sym3> Dtensor;
+  float ViscEtaDtMax=0;
 
   void Resize(unsigned n){
     Idp.resize(n); Dcell.resize(n); Code.resize(n); Pos.resize(n); Velrhop.resize(n);
@@ -149,6 +156,27 @@ struct Oracle {
     DDTArray=(TDensity!=DSPH_DDT_NONE);                                         // Cpu: S/JSph.cpp:814
     DtIni=(c.dtini>0? c.dtini: double(KernelH)/Cs0);
     DtMin=(c.dtmin>0? c.dtmin: (double(KernelH)/Cs0)*double(c.coefdtmin));
+    // Multiphase: JSph::InitMultiPhase + ConfigConstantsMP M/JSph.cpp:3137-3242 (phases arrive sorted by mkfluid)
+    MultiPhase=(c.nn_on!=0); TVelGrad=c.nn_velgrad; PhaseCount=0; Lamda=c.nn_relaxationdt;
+    if(MultiPhase){
+      if(c.nn_nphases<1 || c.nn_nphases>DSPH_MAXPHASES)throw std::runtime_error("The number of phases is invalid.");
+      if(TVelGrad!=DSPH_VELGRAD_FDA && TVelGrad!=DSPH_VELGRAD_SPH)throw std::runtime_error("Velocity gradient type is not valid.");
+      PhaseCount=unsigned(c.nn_nphases);
+      bool cs0present=true;
+      for(unsigned i=0;i<PhaseCount;i++){
+        const dsph_phase &s=c.phases[i]; Phase &d=Ph[i];
+        d.rho=s.rho; d.cs0=s.cs0; d.gamma=(s.gamma? s.gamma: Gamma);
+        d.cteb=(d.cs0? d.cs0*d.cs0*d.rho/d.gamma: 0.f);
+        d.visco=s.visco; d.tau_yield=s.tau_yield; d.tau_max=s.tau_max; d.bi_multi=(s.tau_max? s.bi_multi: 0.f); d.m_nn=s.m_nn; d.n_nn=s.n_nn;
+        if(!d.cs0)cs0present=false;
+      }
+      for(unsigned i=0;i<PhaseCount;i++){
+        if(!cs0present)Ph[i].cteb=float(Cs0*Cs0*Ph[i].rho/Ph[i].gamma);
+        Ph[i].mass=float(Ph[i].rho*(Simulate2D? Dp*Dp: Dp*Dp*Dp));
+      }
+      float coefdtmin=c.coefdtmin; coefdtmin*=1.0e-5f;
+      DtMin=(KernelH/Cs0)*coefdtmin;                                             // overrides any DtMin of the XML
+    }
     // LoadCaseParticles (S/JSph.cpp:2056-2080)
     MapRealPosMin={c.maprealposmin[0],c.maprealposmin[1],c.maprealposmin[2]};
     MapRealPosMax={c.maprealposmax[0],c.maprealposmax[1],c.maprealposmax[2]};
@@ -181,7 +209,7 @@ struct Oracle {
     if(DomRealPosMin.x<MapRealPosMin.x)DomRealPosMin.x=MapRealPosMin.x;
     if(DomRealPosMin.y<MapRealPosMin.y)DomRealPosMin.y=MapRealPosMin.y;
     if(DomRealPosMin.z<MapRealPosMin.z)DomRealPosMin.z=MapRealPosMin.z;
-    DomCellCode=CalcCellCode(DomCells[0]+1,DomCells[1]+1,DomCells[2]+1);
+    DomCellCode=CalcCellCode(DomCells[0]+1,DomCells[1]+1,DomCells[2]+1,(MultiPhase? 32u: 31u));
     if(!DomCellCode)throw std::runtime_error("Failed to select a valid CellCode.");
     SymplecticDtPre=DtIni;                                                        // JSph::InitRun S/JSph.cpp:2090
     VerletStep=0;
@@ -434,7 +462,19 @@ struct Oracle {
     // its -ffast-math build turns rhop/rhop0 into the float product rhop*(1.0f/rhop0) (verified in the disassembly of
     // JSphCpu::PreInteractionVars_Forces, oracle/_ref/obj52/JSphCpu.o).  Both facts are reproduced here.
     const float ovrhopzero=1.0f/RhopZero;
-    for(unsigned p=0;p<Np;p++)Press[p]=float(double(CteB)*(pow(double(Velrhop[p].w*ovrhopzero),double(Gamma))-1.0));
+    if(!MultiPhase)for(unsigned p=0;p<Np;p++)Press[p]=float(double(CteB)*(pow(double(Velrhop[p].w*ovrhopzero),double(Gamma))-1.0));
+    else{
+      // M/JSphCpu.cpp:516-546 (extra arrays) + JSphCpu::ComputePress_NN M/JSphCpu_Tensors.cpp:47-71 (float pow, per-phase EOS)
+      if(TVisco!=DSPH_VISCO_ARTIFICIAL)SpsGradvel.assign(Np,sym3{0,0,0,0,0,0}); else SpsGradvel.clear();
+      SpsTau.assign(Np,sym3{0,0,0,0,0,0}); Dtensor.assign(Np,sym3{0,0,0,0,0,0}); ViscoEta.assign(Np,0.f);
+      for(unsigned p=0;p<Np;p++){
+        float rhozero=RhopZero,cteb=CteB,gamma=Gamma;
+        if(CodeIsFluid(Code[p])){ const Phase &ph=Ph[CodeTypeValue(Code[p])]; rhozero=ph.rho; cteb=ph.cteb; gamma=ph.gamma; }
+        const float rhop_r0=Velrhop[p].w/rhozero;
+        Press[p]=cteb*(powf(rhop_r0,gamma)-1.0f);
+      }
+      ViscEtaDtMax=0;
+    }
     const unsigned pini=(cfg.dtallparticles? 0: Npb);
     float vmax=0;
     for(unsigned p=pini;p<Np;p++){ const f4 v=Velrhop[p]; const float v2=v.x*v.x+v.y*v.y+v.z*v.z; if(vmax<v2)vmax=v2; }
@@ -487,7 +527,9 @@ struct Oracle {
             }
             if((TDensity==DSPH_DDT_DDT2 || (TDensity==DSPH_DDT_DDT2FULL && !boundp2)) && deltap1!=FLT_MAX){   // Fourtakas
               const float rh=1.f+DDTgz*drz;
-              const float drhop=RhopZero*powf(rh,1.f/Gamma)-RhopZero;
+              // source: RhopZero*pow(rh,1.f/Gamma)-RhopZero; the reference's -ffast-math build factors it as
+              // RhopZero*(pow-1) (pinned by the dumps: Ar agrees to 2e-7 with this form, 3e-6..7e-6 with the literal one)
+              const float drhop=RhopZero*(powf(rh,1.f/Gamma)-1.f);
               const float visc_densi=DDTkh*cbar*((velrhop2.w-rhopp1)-drhop)/(rr2+Eta2);
               const float dot3=(drx*frx+dry*fry+drz*frz);
               const float delta=visc_densi*dot3*massp2/velrhop2.w;
@@ -606,11 +648,319 @@ struct Oracle {
       t.yy=one_rho2*(twovisc_sps*g.yy+sumsps); t.yz=one_rho2*(visc_sps*g.yz); t.zz=one_rho2*(twovisc_sps*g.zz+sumsps);
     }
   }
+  // =====================================================================================================================
+  // Multiphase non-Newtonian formulation (src_mphase fork, CPU path).  FtMode none, no symmetry, DBC boundaries.
+  // =====================================================================================================================
+  // neighbours of p1 in cell order (nsearch::Init/ParticleRange M/JCellSearch_inline.h): f(p2,drx,dry,drz,rr2) for every accepted pair
+  template<class F> inline void ForPairs(unsigned p1,bool boundp2,F &&f)const{
+    const d3 posp1=Pos[p1];
+    const NgSearch ngs=NgInit(Dcell[p1],boundp2);
+    for(int z=ngs.zini;z<ngs.zfin;z++)for(int y=ngs.yini;y<ngs.yfin;y++){
+      const int v=int(Nsheet)*z+int(Ncx)*y+ngs.cellinit;
+      const unsigned pini=BeginCell[v+ngs.cxini], pfin2=BeginCell[v+ngs.cxfin];
+      for(unsigned p2=pini;p2<pfin2;p2++){
+        const float drx=float(posp1.x-Pos[p2].x), dry=float(posp1.y-Pos[p2].y), drz=float(posp1.z-Pos[p2].z);
+        const float rr2=drx*drx+dry*dry+drz*drz;
+        if(rr2<=KernelSize2 && rr2>=1e-18f)f(p2,drx,dry,drz,rr2);
+      }
+    }
+  }
+  // ---- JSphCpu::GetEta_Effective M/JSphCpu_Tensors.cpp:113-141
+  inline float EtaEffective(unsigned ppx,float tau_yield,float dmagn,float visco,float m_nn,float n_nn)const{
+    const Phase &P=Ph[ppx];
+    if(dmagn<=1e-18f)dmagn=1e-18f;
+    float miou_yield=(P.tau_max? P.tau_max/(2.0f*dmagn): tau_yield/(2.0f*dmagn));
+    const bool bi_region=P.tau_max && dmagn<=P.tau_max/(2.f*P.bi_multi*visco);
+    if(bi_region)miou_yield=P.bi_multi*visco;
+    const float miouPap=miou_yield*(1.f-expf(-m_nn*dmagn));
+    const bool capped=(miouPap>m_nn*tau_yield || dmagn==1e-18f);
+    const float term1=(P.tau_max? miou_yield: (capped? m_nn*tau_yield: miouPap));
+    const float miouHB=visco*powf(dmagn,(n_nn-1.0f));
+    const float term2=(bi_region? visco: (capped? visco: miouHB));
+    return term1+term2;
+  }
+  // ---- shared by FDA and SPH-PressGrad: pressure, continuity, DDT and shifting of one pair
+  //      M/JSphCpu_NN_FDA.cpp:205-251 == M/JSphCpu_NN_SPH.cpp:528-581
+  struct NNAcc{ float visc,arp1,deltap1; f3 acep1; f4 shiftposfsp1; };
+  inline void NNPairBasic(bool boundp2,bool shift,unsigned pp1,unsigned pp2,unsigned p2,float massp2,float rhopp1,float pressp1,const f3 &velp1,
+    float drx,float dry,float drz,float rr2,float frx,float fry,float frz,const f4 &velrhop2,float &dvx,float &dvy,float &dvz,NNAcc &a)const
+  {
+    {
+      const float prs=(pressp1+Press[p2])/(rhopp1*velrhop2.w)+(TKernel==DSPH_KERNEL_CUBIC? TensilCubic(rr2,rhopp1,pressp1,velrhop2.w,Press[p2]): 0);
+      const float p_vpm=-prs*massp2;
+      a.acep1.x+=p_vpm*frx; a.acep1.y+=p_vpm*fry; a.acep1.z+=p_vpm*frz;
+    }
+    const float rhop1over2=rhopp1/velrhop2.w;
+    dvx=velp1.x-velrhop2.x; dvy=velp1.y-velrhop2.y; dvz=velp1.z-velrhop2.z;
+    a.arp1+=massp2*(dvx*frx+dvy*fry+dvz*frz)*rhop1over2;
+    const float cbar=Ph[pp2].cs0;                                   // max(Cs0[pp2],Cs0[pp2])
+    if(TDensity==DSPH_DDT_DDT && a.deltap1!=FLT_MAX){
+      const float visc_densi=DDTkh*cbar*(rhop1over2-1.f)/(rr2+Eta2);
+      const float dot3=(drx*frx+dry*fry+drz*frz);
+      const float delta=(pp1==pp2? visc_densi*dot3*massp2: 0);
+      a.deltap1=(boundp2? FLT_MAX: a.deltap1+delta);                // TBoundary==BC_DBC
+    }
+    if((TDensity==DSPH_DDT_DDT2 || (TDensity==DSPH_DDT_DDT2FULL && !boundp2)) && a.deltap1!=FLT_MAX){
+      const float rh=1.f+DDTgz*drz;
+      const float drhop=RhopZero*(powf(rh,1.f/Gamma)-1.f);          // fast-math factoring of RhopZero*pow-RhopZero, as above
+      const float visc_densi=DDTkh*cbar*((velrhop2.w-rhopp1)-drhop)/(rr2+Eta2);
+      const float dot3=(drx*frx+dry*fry+drz*frz);
+      const float delta=(pp1==pp2? visc_densi*dot3*massp2/velrhop2.w: 0);
+      a.deltap1=(boundp2? FLT_MAX: a.deltap1-delta);
+    }
+    if(shift && a.shiftposfsp1.x!=FLT_MAX){
+      const bool heavyphase=(Ph[pp1].mass>Ph[pp2].mass && pp1!=pp2);
+      const float massrhop=massp2/velrhop2.w;
+      const bool noshift=(boundp2 && (ShiftMode==DSPH_SHIFT_NOBOUND || (ShiftMode==DSPH_SHIFT_NOFIXED && CodeIsFixed(Code[p2]))));
+      a.shiftposfsp1.x=(noshift? FLT_MAX: (heavyphase? 0: a.shiftposfsp1.x+massrhop*frx));
+      a.shiftposfsp1.y+=(heavyphase? 0: massrhop*fry);
+      a.shiftposfsp1.z+=(heavyphase? 0: massrhop*frz);
+      a.shiftposfsp1.w-=(heavyphase? 0: massrhop*(drx*frx+dry*fry+drz*frz));
+    }
+  }
+  inline void NNStore(unsigned p1,bool shift,NNAcc &a,float &vmaxall){
+    if(shift||a.arp1||a.acep1.x||a.acep1.y||a.acep1.z||a.visc){
+      if(TDensity!=DSPH_DDT_NONE){
+        if(!Delta.empty())Delta[p1]=(Delta[p1]==FLT_MAX || a.deltap1==FLT_MAX? FLT_MAX: Delta[p1]+a.deltap1);
+        else if(a.deltap1!=FLT_MAX)a.arp1+=a.deltap1;
+      }
+      Ar[p1]+=a.arp1;
+      Ace[p1].x=Ace[p1].x+a.acep1.x; Ace[p1].y=Ace[p1].y+a.acep1.y; Ace[p1].z=Ace[p1].z+a.acep1.z;
+      if(a.visc>vmaxall)vmaxall=a.visc;
+      if(shift)ShiftPosfs[p1]=a.shiftposfsp1;
+    }
+  }
+  // ---- JSphCpu::InteractionForcesFluid_NN_FDA_All M/JSphCpu_NN_FDA.cpp:129-340
+  void NNForcesFluidFDA(bool boundp2,float &viscdt,float &viscetadt){
+    const int pinit=int(Npb), pfin=int(Np);
+    const bool shift=(ShiftMode!=0);
+    float vmaxall=viscdt, etamaxall=viscetadt;
+    #pragma omp parallel for schedule(guided) reduction(max:vmaxall,etamaxall)
+    for(int p1=pinit;p1<pfin;p1++){
+      if(Mgpu && CodeIsPeriodic(Code[p1]))continue;
+      NNAcc a; a.visc=0; a.arp1=0; a.deltap1=0; a.acep1={0,0,0}; a.shiftposfsp1={0,0,0,0};
+      if(shift)a.shiftposfsp1=ShiftPosfs[p1];
+      const f3 velp1={Velrhop[p1].x,Velrhop[p1].y,Velrhop[p1].z};
+      const float rhopp1=Velrhop[p1].w, pressp1=Press[p1];
+      const unsigned pp1=CodeTypeValue(Code[p1]);
+      float visco_etap1=0, visceta=0;
+      ForPairs(unsigned(p1),boundp2,[&](unsigned p2,float drx,float dry,float drz,float rr2){
+        const float fac=Fac(rr2);
+        const float frx=fac*drx,fry=fac*dry,frz=fac*drz;
+        const unsigned pp2=(boundp2? pp1: CodeTypeValue(Code[p2]));
+        const float massp2=(boundp2? MassBound: Ph[pp2].mass);
+        const f4 velrhop2=Velrhop[p2];
+        float dvx,dvy,dvz;
+        NNPairBasic(boundp2,shift,pp1,pp2,p2,massp2,rhopp1,pressp1,velp1,drx,dry,drz,rr2,frx,fry,frz,velrhop2,dvx,dvy,dvz,a);
+        const float cbar=Ph[pp2].cs0;
+        const float dot=drx*dvx+dry*dvy+drz*dvz;
+        const float dot_rr2=dot/(rr2+Eta2);
+        a.visc=std::max(dot_rr2,a.visc);
+        const float visco_NN=Ph[pp2].visco;
+        if(TVisco==DSPH_VISCO_ARTIFICIAL){
+          if(dot<0){
+            const float amubar=KernelH*dot_rr2;
+            const float robar=(rhopp1+velrhop2.w)*0.5f;
+            const float pi_visc=(-visco_NN*cbar*amubar/robar)*massp2;
+            a.acep1.x-=pi_visc*frx; a.acep1.y-=pi_visc*fry; a.acep1.z-=pi_visc*frz;
+          }
+        }
+        else{ // VISCO_LaminarSPS || VISCO_ConstEq
+          if(boundp2){ dvx=2.f*velp1.x; dvy=2.f*velp1.y; dvz=2.f*velp1.z; }        // no-slip
+          // GetVelocityGradients_FDA M/JSphCpu_Tensors.cpp:80-88
+          const float a11=dvx*drx/rr2,a12=dvx*dry/rr2,a13=dvx*drz/rr2;
+          const float a21=dvy*drx/rr2,a22=dvy*dry/rr2,a23=dvy*drz/rr2;
+          const float a31=dvz*drx/rr2,a32=dvz*dry/rr2,a33=dvz*drz/rr2;
+          const float div_vel=(a11+a22+a33)/3.f;
+          // GetStrainRateTensor M/JSphCpu_Tensors.cpp:92-111
+          const float d11=a11-div_vel, d12=0.5f*(a12+a21), d13=0.5f*(a13+a31);
+          const float d21=0.5f*(a21+a12), d22=a22-div_vel, d23=0.5f*(a23+a32);
+          const float d31=0.5f*(a31+a13), d32=0.5f*(a32+a23), d33=a33-div_vel;
+          const float II_D_1=d11*d22+d22*d33+d11*d33;
+          const float II_D_2=d12*d21+d23*d32+d13*d31;
+          const float II_D=II_D_1-II_D_2;
+          const float dmagn=sqrtf(II_D*II_D);
+          visco_etap1=EtaEffective(pp1,Ph[pp2].tau_yield,dmagn,visco_NN,Ph[pp2].m_nn,Ph[pp2].n_nn);
+          visceta=std::max(visco_etap1,visceta);
+          if(TVisco==DSPH_VISCO_LAMINARSPS){                                        // Morris operator
+            const float temp=2.0f*(visco_etap1)/((rr2+Eta2)*velrhop2.w);
+            const float vtemp=massp2*temp*(drx*frx+dry*fry+drz*frz);
+            a.acep1.x+=vtemp*dvx; a.acep1.y+=vtemp*dvy; a.acep1.z+=vtemp*dvz;
+          }
+          else{                                                                     // GetStressTensor :143-164
+            const float t2=2.f*visco_etap1;
+            const float taux=((t2*d11)*frx+(t2*d12)*fry+(t2*d13)*frz)/(velrhop2.w);
+            const float tauy=((t2*d21)*frx+(t2*d22)*fry+(t2*d23)*frz)/(velrhop2.w);
+            const float tauz=((t2*d31)*frx+(t2*d32)*fry+(t2*d33)*frz)/(velrhop2.w);
+            a.acep1.x+=taux*massp2; a.acep1.y+=tauy*massp2; a.acep1.z+=tauz*massp2;
+          }
+        }
+      });
+      const bool stored=(shift||a.arp1||a.acep1.x||a.acep1.y||a.acep1.z||a.visc);
+      NNStore(unsigned(p1),shift,a,vmaxall);
+      if(stored){
+        if(visceta>etamaxall)etamaxall=visceta;
+        if(visco_etap1)ViscoEta[p1]=visco_etap1;
+      }
+    }
+    viscdt=vmaxall; viscetadt=etamaxall;
+  }
+  // ---- JSphCpu::InteractionForcesFluid_NN_SPH_PressGrad M/JSphCpu_NN_SPH.cpp:452-620
+  void NNForcesFluidSPHPressGrad(bool boundp2,float &viscdt){
+    const int pinit=int(Npb), pfin=int(Np);
+    const bool shift=(ShiftMode!=0);
+    float vmaxall=viscdt;
+    #pragma omp parallel for schedule(guided) reduction(max:vmaxall)
+    for(int p1=pinit;p1<pfin;p1++){
+      NNAcc a; a.visc=0; a.arp1=0; a.deltap1=0; a.acep1={0,0,0}; a.shiftposfsp1={0,0,0,0};
+      sym3 g={0,0,0,0,0,0};
+      if(shift)a.shiftposfsp1=ShiftPosfs[p1];
+      const f3 velp1={Velrhop[p1].x,Velrhop[p1].y,Velrhop[p1].z};
+      const float rhopp1=Velrhop[p1].w, pressp1=Press[p1];
+      const unsigned pp1=CodeTypeValue(Code[p1]);
+      ForPairs(unsigned(p1),boundp2,[&](unsigned p2,float drx,float dry,float drz,float rr2){
+        const float fac=Fac(rr2);
+        const float frx=fac*drx,fry=fac*dry,frz=fac*drz;
+        const unsigned pp2=(boundp2? pp1: CodeTypeValue(Code[p2]));
+        const float massp2=(boundp2? MassBound: Ph[pp2].mass);
+        const f4 velrhop2=Velrhop[p2];
+        float dvx,dvy,dvz;
+        NNPairBasic(boundp2,shift,pp1,pp2,p2,massp2,rhopp1,pressp1,velp1,drx,dry,drz,rr2,frx,fry,frz,velrhop2,dvx,dvy,dvz,a);
+        const float dot=drx*dvx+dry*dvy+drz*dvz;
+        const float dot_rr2=dot/(rr2+Eta2);
+        a.visc=std::max(dot_rr2,a.visc);
+        if(TVisco!=DSPH_VISCO_ARTIFICIAL){
+          if(boundp2){ dvx=2.f*velp1.x; dvy=2.f*velp1.y; dvz=2.f*velp1.z; }
+          const float volp2=-massp2/velrhop2.w;                                   // GetVelocityGradients_SPH_tsym M/JSphCpu_Tensors.cpp:171-180
+          float dv=dvx*volp2; g.xx+=dv*frx; g.xy+=dv*fry; g.xz+=dv*frz;
+                dv=dvy*volp2; g.xy+=dv*frx; g.yy+=dv*fry; g.yz+=dv*frz;
+                dv=dvz*volp2; g.xz+=dv*frx; g.yz+=dv*fry; g.zz+=dv*frz;
+        }
+      });
+      const bool stored=(shift||a.arp1||a.acep1.x||a.acep1.y||a.acep1.z||a.visc);
+      NNStore(unsigned(p1),shift,a,vmaxall);
+      if(stored && TVisco!=DSPH_VISCO_ARTIFICIAL){
+        sym3 &t=SpsGradvel[p1];
+        t.xx+=g.xx; t.xy+=g.xy; t.xz+=g.xz; t.yy+=g.yy; t.yz+=g.yz; t.zz+=g.zz;
+      }
+    }
+    viscdt=vmaxall;
+  }
+  // ---- JSphCpu::InteractionForcesFluid_NN_SPH_Visco_eta M/JSphCpu_NN_SPH.cpp:174-228 (+ GetStrainRateTensor_tsym Tensors:184-207)
+  void NNViscoEtaSPH(float &viscetadt){
+    float etamaxall=viscetadt;
+    #pragma omp parallel for schedule(guided) reduction(max:etamaxall)
+    for(int p1=int(Npb);p1<int(Np);p1++){
+      const sym3 gv=SpsGradvel[p1];
+      const unsigned pp1=CodeTypeValue(Code[p1]);
+      const float div_vel=(gv.xx+gv.yy+gv.zz)/3.f;
+      sym3 D; D.xx=gv.xx-div_vel; D.xy=0.5f*(gv.xy); D.xz=0.5f*(gv.xz); D.yy=gv.yy-div_vel; D.yz=0.5f*(gv.yz); D.zz=gv.zz-div_vel;
+      const float II_D_1=D.xx*D.yy+D.yy*D.zz+D.xx*D.zz;
+      const float II_D_2=D.xy*D.xy+D.yz*D.yz+D.xz*D.xz;
+      const float II_D=-II_D_1+II_D_2;
+      const float dmagn=sqrtf(II_D);
+      const float eta=EtaEffective(pp1,Ph[pp1].tau_yield,dmagn,Ph[pp1].visco,Ph[pp1].m_nn,Ph[pp1].n_nn);
+      if(eta)ViscoEta[p1]=eta;
+      if(TVisco!=DSPH_VISCO_ARTIFICIAL)Dtensor[p1]=D;
+      if(eta>etamaxall)etamaxall=eta;
+    }
+    viscetadt=etamaxall;
+  }
+  // ---- JSphCpu::InteractionForcesFluid_NN_SPH_Morris M/JSphCpu_NN_SPH.cpp:337-446
+  void NNForcesFluidSPHMorris(bool boundp2){
+    #pragma omp parallel for schedule(guided)
+    for(int p1=int(Npb);p1<int(Np);p1++){
+      f3 acep1={0,0,0};
+      const f3 velp1={Velrhop[p1].x,Velrhop[p1].y,Velrhop[p1].z};
+      const float rhopp1=Velrhop[p1].w;
+      const float visco_etap1=ViscoEta[p1];
+      const unsigned pp1=CodeTypeValue(Code[p1]);
+      ForPairs(unsigned(p1),boundp2,[&](unsigned p2,float drx,float dry,float drz,float rr2){
+        const float fac=Fac(rr2);
+        const float frx=fac*drx,fry=fac*dry,frz=fac*drz;
+        const unsigned pp2=(boundp2? pp1: CodeTypeValue(Code[p2]));
+        const float massp2=(boundp2? MassBound: Ph[pp2].mass);
+        const f4 velrhop2=Velrhop[p2];
+        float dvx=velp1.x-velrhop2.x,dvy=velp1.y-velrhop2.y,dvz=velp1.z-velrhop2.z;
+        if(boundp2){ dvx=2.f*velp1.x; dvy=2.f*velp1.y; dvz=2.f*velp1.z; }
+        const float cbar=Ph[pp2].cs0;
+        const float dot=drx*dvx+dry*dvy+drz*dvz;
+        const float dot_rr2=dot/(rr2+Eta2);
+        const float visco_NN=Ph[pp2].visco;
+        if(TVisco==DSPH_VISCO_ARTIFICIAL){
+          if(dot<0){
+            const float amubar=KernelH*dot_rr2;
+            const float robar=(rhopp1+velrhop2.w)*0.5f;
+            const float pi_visc=(-visco_NN*cbar*amubar/robar)*massp2;
+            acep1.x-=pi_visc*frx; acep1.y-=pi_visc*fry; acep1.z-=pi_visc*frz;
+          }
+        }
+        else if(TVisco==DSPH_VISCO_LAMINARSPS){
+          float visco_etap2=ViscoEta[p2];
+          if(boundp2)visco_etap2=visco_etap1;
+          const float temp=(visco_etap1+visco_etap2)/((rr2+Eta2)*velrhop2.w);
+          const float vtemp=massp2*temp*(drx*frx+dry*fry+drz*frz);
+          acep1.x+=vtemp*dvx; acep1.y+=vtemp*dvy; acep1.z+=vtemp*dvz;
+        }
+      });
+      if(acep1.x||acep1.y||acep1.z){ Ace[p1].x=Ace[p1].x+acep1.x; Ace[p1].y=Ace[p1].y+acep1.y; Ace[p1].z=Ace[p1].z+acep1.z; }
+    }
+  }
+  // ---- JSphCpu::InteractionForcesFluid_NN_SPH_Visco_Stress_tensor M/JSphCpu_NN_SPH.cpp:128-169 (+ GetStressTensor_sym Tensors:211-231)
+  void NNStressTensorSPH(){
+    for(unsigned p1=Npb;p1<Np;p1++){
+      const float t2=2.f*ViscoEta[p1]; const sym3 D=Dtensor[p1];
+      if(TVisco!=DSPH_VISCO_ARTIFICIAL)SpsTau[p1]=sym3{t2*D.xx,t2*D.xy,t2*D.xz,t2*D.yy,t2*D.yz,t2*D.zz};
+    }
+  }
+  // ---- JSphCpu::InteractionForcesFluid_NN_SPH_ConsEq M/JSphCpu_NN_SPH.cpp:234-331
+  void NNForcesFluidSPHConsEq(bool boundp2){
+    #pragma omp parallel for schedule(guided)
+    for(int p1=int(Npb);p1<int(Np);p1++){
+      f3 acep1={0,0,0};
+      const sym3 tau1=SpsTau[p1];
+      const unsigned pp1=CodeTypeValue(Code[p1]);
+      ForPairs(unsigned(p1),boundp2,[&](unsigned p2,float drx,float dry,float drz,float rr2){
+        const float fac=Fac(rr2);
+        const float frx=fac*drx,fry=fac*dry,frz=fac*drz;
+        const unsigned pp2=(boundp2? pp1: CodeTypeValue(Code[p2]));
+        const float massp2=(boundp2? MassBound: Ph[pp2].mass);
+        const f4 velrhop2=Velrhop[p2];
+        sym3 tau2=SpsTau[p2]; if(boundp2)tau2=tau1;
+        const sym3 ts={tau1.xx+tau2.xx,tau1.xy+tau2.xy,tau1.xz+tau2.xz,tau1.yy+tau2.yy,tau1.yz+tau2.yz,tau1.zz+tau2.zz};
+        const float taux=(ts.xx*frx+ts.xy*fry+ts.xz*frz)/(velrhop2.w);
+        const float tauy=(ts.xy*frx+ts.yy*fry+ts.yz*frz)/(velrhop2.w);
+        const float tauz=(ts.xz*frx+ts.yz*fry+ts.zz*frz)/(velrhop2.w);
+        acep1.x+=taux*massp2; acep1.y+=tauy*massp2; acep1.z+=tauz*massp2;
+      });
+      if(acep1.x||acep1.y||acep1.z){ Ace[p1].x=Ace[p1].x+acep1.x; Ace[p1].y=Ace[p1].y+acep1.y; Ace[p1].z=Ace[p1].z+acep1.z; }
+    }
+  }
+  // ---- Interaction_ForcesCpuT_NN_FDA M/JSphCpu_NN_FDA.cpp:346-379, Interaction_ForcesCpuT_NN_SPH M/JSphCpu_NN_SPH.cpp:654-710
+  //      (InteractionForcesBound_NN_* are the classic boundary pass with MassFluid: M/JSphCpu_NN_FDA.cpp:46-124)
+  void InteractionForcesNN(float &viscdt,float &viscetadt){
+    if(Mgpu && TVelGrad==DSPH_VELGRAD_SPH)throw std::runtime_error("The SPH velocity-gradient approach is not available with x-slab decomposition.");
+    if(Np>Npb){
+      if(TVelGrad==DSPH_VELGRAD_FDA){
+        NNForcesFluidFDA(false,viscdt,viscetadt);
+        NNForcesFluidFDA(true,viscdt,viscetadt);
+      }
+      else{
+        NNForcesFluidSPHPressGrad(false,viscdt);
+        NNForcesFluidSPHPressGrad(true,viscdt);
+        if(TVisco!=DSPH_VISCO_ARTIFICIAL)NNViscoEtaSPH(viscetadt);
+        if(TVisco!=DSPH_VISCO_CONSTEQ){ NNForcesFluidSPHMorris(false); NNForcesFluidSPHMorris(true); }
+        else{ NNStressTensorSPH(); NNForcesFluidSPHConsEq(false); NNForcesFluidSPHConsEq(true); }
+      }
+    }
+  }
+
   // ---- JSphCpuSingle::Interaction_Forces S/JSphCpuSingle.cpp:524-567 + Interaction_ForcesCpuT S/JSphCpu.cpp:960-987
   void InteractionForces(){
     PreInteraction();
     float viscdt=0;
-    if(Np>Npb){
+    if(MultiPhase){ float viscetadt=0; InteractionForcesNN(viscdt,viscetadt); ViscEtaDtMax=viscetadt; }   // M/JSphCpuSingle.cpp:594-636
+    else if(Np>Npb){
       InteractionForcesFluid(false,Visco,viscdt);
       InteractionForcesFluid(true,Visco*ViscoBoundFactor,viscdt);
       if(TVisco==DSPH_VISCO_LAMINARSPS)ComputeSpsTau();
@@ -629,10 +979,13 @@ struct Oracle {
     AceMax=sqrt(double(amax)); LastAce2=amax;
   }
   // ---- JSphCpu::DtVariable S/JSphCpu.cpp:1614-1639
-  double DtVariable(double *pdt1,double *pdt2)const{
+  double DtVariable(double *pdt1,double *pdt2,double *pdt3=nullptr)const{
     const double dt1=(AceMax? (sqrt(double(KernelH)/AceMax)): DBL_MAX);
     const double dt2=double(KernelH)/(std::max(Cs0,VelMax*10.)+double(KernelH)*ViscDtMax);
-    double dt=CFLnumber*std::min(dt1,dt2);
+    // viscous time step of the multiphase fork: M/JSphCpu.cpp:1687-1689
+    const double dt3=(MultiPhase && ViscEtaDtMax*Lamda>0? double(KernelH*KernelH)/double(ViscEtaDtMax*Lamda): DBL_MAX);
+    double dt=CFLnumber*std::min(dt3,std::min(dt1,dt2));
+    if(pdt3)*pdt3=dt3;
     if(cfg.dtfixed_on)dt=cfg.dtfixed;
     if(dt!=dt || std::isinf(dt))throw std::runtime_error("The computed Dt is NaN or infinity.");
     if(dt<DtMin)dt=DtMin;
@@ -654,6 +1007,10 @@ struct Oracle {
           else umagn*=(double(rs.w)-ShiftTFS)/coeftfs;
         }
         const float sx=float(double(rs.x)*umagn), sy=float(double(rs.y)*umagn), sz=float(double(rs.z)*umagn);
+        if(MultiPhase){   // the v5.0 fork clamps one side only: M/JSphShifting.cpp:412-414
+          ShiftPosfs[p].x=(sx<maxdist? sx: maxdist); ShiftPosfs[p].y=(sy<maxdist? sy: maxdist); ShiftPosfs[p].z=(sz<maxdist? sz: maxdist);
+          continue;
+        }
         ShiftPosfs[p].x=(fabsf(sx)<maxdist? sx: (sx>=0? maxdist: -maxdist));
         ShiftPosfs[p].y=(fabsf(sy)<maxdist? sy: (sy>=0? maxdist: -maxdist));
         ShiftPosfs[p].z=(fabsf(sz)<maxdist? sz: (sz>=0? maxdist: -maxdist));
@@ -937,7 +1294,8 @@ static void FillForceRes(const Oracle &o,dsph_forceres *res){
   if(!res)return;
   memset(res,0,sizeof(*res));
   res->viscdtmax=o.ViscDtMax; res->acemax=float(o.AceMax); res->velmax=float(o.VelMax);
-  res->dt=o.DtVariable(&res->dt1,&res->dt2);
+  res->viscetadtmax=o.ViscEtaDtMax;
+  res->dt=o.DtVariable(&res->dt1,&res->dt2,&res->dt3);
 }
 int orc_forces_run(orc_state *s,int interstep,dsph_forceres *res){
   (void)interstep;

@@ -25,6 +25,7 @@ import dualsphysics_multilayer_b200 as dsph  # noqa: E402
 from dumpio import read_dump  # noqa: E402
 
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness52")
+HARNESS_NN = os.path.join(ROOT, "oracle", "_ref", "ref_harnessnn")     # src_mphase fork (v5.0 NNewtonian)
 MKCASE = os.path.join(ROOT, "dualsphysics_multilayer_b200", "bin", "mkcase")
 
 # name, kind, np_target, mkcase options, dumped steps, total steps
@@ -35,6 +36,12 @@ CASES = [
     ("db_sym_cubic_art_noddt_half", "dambreak", 3000, ["tstep=2", "tkernel=1", "tvisco=1", "visco=0.05", "ddt=0", "cellmode=2", "shifting=1", "shiftcoef=-2"], [20], 21),
     ("pb_sym_wend_art_ddt1", "periodicbox", 1728, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=1"], [0, 15], 16),
     ("pb_ver_wend_art_ddt1", "periodicbox", 1728, ["tstep=1", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=1", "verletsteps=5"], [0, 12], 13),
+    # multiphase non-Newtonian fork (two-layer dam break): FDA / SPH velocity gradients, Morris / constitutive-equation operator
+    ("nn_sym_fda_lam_ddt3_shift", "nn2layer", 3000, ["tstep=2", "tkernel=2", "velgrad=1", "tvisco=2", "ddt=3", "shifting=3"], [0, 25], 26),
+    ("nn_ver_sph_lam_ddt1", "nn2layer", 3000, ["tstep=1", "tkernel=2", "velgrad=2", "tvisco=2", "ddt=1", "shifting=0", "verletsteps=10"], [22], 23),
+    ("nn_sym_sph_conseq_ddt2_shift", "nn2layer", 3000, ["tstep=2", "tkernel=2", "velgrad=2", "tvisco=3", "ddt=2", "shifting=3"], [20], 21),
+    ("nn_sym_fda_conseq_cubic", "nn2layer", 3000, ["tstep=2", "tkernel=1", "velgrad=1", "tvisco=3", "ddt=0", "shifting=0"], [20], 21),
+    ("nn_sym_fda_art_ddt1", "nn2layer", 3000, ["tstep=2", "tkernel=2", "velgrad=1", "tvisco=1", "ddt=1", "shifting=1"], [20], 21),
 ]
 
 
@@ -42,7 +49,7 @@ def run(name, kind, nptarget, opts, steps, nsteps, outdir):
     tmp = tempfile.mkdtemp(prefix="golden_")
     try:
         subprocess.check_call([MKCASE, kind, str(nptarget), tmp, "Case"] + opts, stdout=subprocess.DEVNULL)
-        cmd = [HARNESS, "Case", "out", "-cpu", "-ompthreads:1", "-sv:none", "-hdir:" + os.path.join(tmp, "dump"),
+        cmd = [HARNESS_NN if kind == "nn2layer" else HARNESS, "Case", "out", "-cpu", "-ompthreads:1", "-sv:none", "-hdir:" + os.path.join(tmp, "dump"),
                "-hsteps:" + ",".join(str(s) for s in steps), "-hnsteps:%d" % nsteps]
         cmd += ["-cellmode:half"] if "cellmode=2" in opts else []
         r = subprocess.run(cmd, cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -53,7 +60,7 @@ def run(name, kind, nptarget, opts, steps, nsteps, outdir):
         if "cellmode=2" in opts:
             cd.cfg.cellmode = 2
         pack = {"config": np.frombuffer(bytes(cd.cfg), np.uint8).copy(), "case/idp": cd.idp, "case/pos": cd.pos,
-                "case/velrhop": cd.velrhop, "case/npb": np.uint32(cd.npb), "steps": np.array(steps, np.uint32),
+                "case/velrhop": cd.velrhop, "case/code": cd.codes(), "case/npb": np.uint32(cd.npb), "steps": np.array(steps, np.uint32),
                 "nsteps": np.uint32(nsteps), "case/caseposmin": np.array(cd.caseposmin), "case/caseposmax": np.array(cd.caseposmax)}
         for f in sorted(os.listdir(os.path.join(tmp, "dump"))):
             d = read_dump(os.path.join(tmp, "dump", f))

@@ -12,7 +12,10 @@ from dualsphysics_multilayer_b200.capi import Config, SphContext
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 GOLDEN_CASES = ["db_sym_wend_art_ddt2", "db_ver_cubic_art_ddt1_shift", "db_sym_wend_lamsps_ddt3",
-                "db_sym_cubic_art_noddt_half", "pb_sym_wend_art_ddt1", "pb_ver_wend_art_ddt1"]
+                "db_sym_cubic_art_noddt_half", "pb_sym_wend_art_ddt1", "pb_ver_wend_art_ddt1",
+                "nn_sym_fda_lam_ddt3_shift", "nn_ver_sph_lam_ddt1", "nn_sym_sph_conseq_ddt2_shift", "nn_sym_fda_conseq_cubic",
+                "nn_sym_fda_art_ddt1"]
+GPU_PENDING = []                             # cases the CUDA path does not cover yet
 
 
 def rl2(a, b):
@@ -153,7 +156,10 @@ def run_trajectory(lib, g: Golden, capacity=0):
     ctx = make_ctx(lib, cfg, capacity)
     z = g.z
     idp = z["case/idp"]; npb = int(z["case/npb"])
-    code = np.where(idp < cfg.casenfixed, capi.CODE_TYPE_FIXED, capi.CODE_TYPE_FLUID).astype(np.uint16)
+    if "case/code" in z.files:               # multiphase cases: the phase is the type value of the code
+        code = z["case/code"]
+    else:
+        code = np.where(idp < cfg.casenfixed, capi.CODE_TYPE_FIXED, capi.CODE_TYPE_FLUID).astype(np.uint16)
     ctx.upload(idp, z["case/pos"], z["case/velrhop"], npb, code)
     ctx.celldiv(True)
     t = 0.0
