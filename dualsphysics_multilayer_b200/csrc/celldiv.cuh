@@ -242,13 +242,24 @@ __device__ __forceinline__ float PressFromRhop(float rhop,const DevCtes &c){
   return float(c.cteb_d*(pow(double(x),c.gamma_d)-1.0));
 }
 
-__global__ void __launch_bounds__(DIV_THREADS) ker_div_reorder(unsigned n,const unsigned* __restrict__ sortpart,ReorderArrays a,DevCtes c)
+// JSphCpu::ComputePress_NN M/JSphCpu_Tensors.cpp:47-71: EOS of the particle's phase (boundaries: global constants), float
+// arithmetic with powf; the power is taken in double and rounded once = the correctly rounded float power of glibc.
+__device__ __forceinline__ float PressFromRhopNN(float rhop,unsigned rcode,const DevCtes &c,const DevPhases &ph){
+  float rhozero=c.rhopzero, cteb=c.cteb, gamma=c.gamma;
+  if((rcode&DSPH_CODE_MASKTYPE)==DSPH_CODE_TYPE_FLUID){ const DevPhase &p=ph.ph[rcode&DSPH_CODE_MASKVALUE]; rhozero=p.rho; cteb=p.cteb; gamma=p.gamma; }
+  const float rhop_r0=__fdiv_rn(rhop,rhozero);
+  const float pw=float(pow(double(rhop_r0),double(gamma)));
+  return __fmul_rn(cteb,__fsub_rn(pw,1.0f));
+}
+
+template<bool NN> __global__ void __launch_bounds__(DIV_THREADS) ker_div_reorder(unsigned n,const unsigned* __restrict__ sortpart,ReorderArrays a,DevCtes c,DevPhases ph)
 {
   const unsigned p=blockIdx.x*blockDim.x+threadIdx.x;
   if(p>=n)return;
   const unsigned s=sortpart[p];
   a.idp_out[p]=a.idp_in[s];
-  a.code_out[p]=a.code_in[s];
+  const typecode rcode=a.code_in[s];
+  a.code_out[p]=rcode;
   const unsigned rcell=a.dcell_in[s];
   a.dcell_out[p]=rcell;
   const double px=a.pos_in[3*size_t(s)], py=a.pos_in[3*size_t(s)+1], pz=a.pos_in[3*size_t(s)+2];
@@ -271,7 +282,7 @@ __global__ void __launch_bounds__(DIV_THREADS) ker_div_reorder(unsigned n,const 
     pp.x=float(px-(c.domposmin[0]+double(cx)*c.scell_d));
     pp.y=float(py-(c.domposmin[1]+double(cy)*c.scell_d));
     pp.z=float(pz-(c.domposmin[2]+double(cz)*c.scell_d));
-    pp.w=PressFromRhop(vr.w,c);
+    pp.w=(NN? PressFromRhopNN(vr.w,rcode,c,ph): PressFromRhop(vr.w,c));
   }
   a.posp[p]=pp;
 }

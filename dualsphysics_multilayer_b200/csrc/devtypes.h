@@ -36,7 +36,13 @@ struct DevCtes {
   int simulate2d, dtallparticles;
   // shifting (S/JSphShifting.cpp:387-417)
   int shiftmode; float shifttfs;
+  int nn_on;              // multiphase non-Newtonian fork: per-phase EOS, v5.0 shifting clamp
 };
+
+// Phases of the multiphase non-Newtonian fork, passed by value to the kernels that need them (constant bank, indexed
+// by the type value of the particle code).  Replaces the __constant__ PHASECTE/PHASEARRAY[10] of M/JSphGpu_NN_ker.cu:44-47.
+struct DevPhase { float rho, mass, cs0, cteb, gamma, visco, tau_yield, tau_max, bi_multi, m_nn, n_nn, pad; };
+struct DevPhases { int count; int velgrad; float lamda; float pad; DevPhase ph[10]; };
 
 // Cell domain of the current divide; written by ker_div_prepare ON THE DEVICE (no host round trip between the
 // min/max reduction and the key build), copied to the host once per divide together with the counts.

@@ -12,6 +12,7 @@
 #include "step.cuh"
 #include "periodic.cuh"
 #include "mgpu.cuh"
+#include "forces_nn.cuh"
 #include <cstdio>
 #include <cstring>
 #include <cmath>
@@ -52,9 +53,30 @@ Engine::~Engine(){
 void Engine::Configure(const dsph_config &c){
   cfg=c;
   DeriveConstants(cfg,k);
-  if(cfg.nn_on)throw EngineError(DSPH_ERR_ARG,"The multiphase non-Newtonian formulation is not available in this build yet.");
   if(cfg.casenmoving || cfg.casenfloat)throw EngineError(DSPH_ERR_ARG,"Moving and floating particles are outside the hot-path scope.");
-  memset(&dc,0,sizeof(dc));
+  if(cfg.tvisco==DSPH_VISCO_CONSTEQ && !cfg.nn_on)throw EngineError(DSPH_ERR_ARG,"ViscoTreatment 'Constitutive eq.' not valid for Single-phase classic formulation.");
+  sps=(cfg.tvisco==DSPH_VISCO_LAMINARSPS && !cfg.nn_on);
+  memset(&dc,0,sizeof(dc)); memset(&dph,0,sizeof(dph));
+  if(cfg.nn_on){
+    // JSph::InitMultiPhase + ConfigConstantsMP (M/JSph.cpp:3137-3242): per-phase B and particle mass, same rounding points
+    if(cfg.nn_nphases<1 || cfg.nn_nphases>DSPH_MAXPHASES)throw EngineError(DSPH_ERR_ARG,"The number of phases is invalid.");
+    if(cfg.nn_velgrad!=DSPH_VELGRAD_FDA && cfg.nn_velgrad!=DSPH_VELGRAD_SPH)throw EngineError(DSPH_ERR_ARG,"Velocity gradient type is not valid.");
+    dph.count=cfg.nn_nphases; dph.velgrad=cfg.nn_velgrad; dph.lamda=cfg.nn_relaxationdt;
+    bool cs0present=true;
+    for(int i=0;i<dph.count;i++){
+      const dsph_phase &s=cfg.phases[i]; DevPhase &d=dph.ph[i];
+      d.rho=s.rho; d.cs0=s.cs0; d.gamma=(s.gamma? s.gamma: cfg.gamma);
+      d.cteb=(d.cs0? d.cs0*d.cs0*d.rho/d.gamma: 0.f);
+      d.visco=s.visco; d.tau_yield=s.tau_yield; d.tau_max=s.tau_max; d.bi_multi=(s.tau_max? s.bi_multi: 0.f); d.m_nn=s.m_nn; d.n_nn=s.n_nn;
+      if(!d.cs0)cs0present=false;
+    }
+    for(int i=0;i<dph.count;i++){
+      DevPhase &d=dph.ph[i];
+      if(!cs0present)d.cteb=float(k.cs0*k.cs0*d.rho/d.gamma);
+      d.mass=float(d.rho*(cfg.simulate2d? cfg.dp*cfg.dp: cfg.dp*cfg.dp*cfg.dp));
+    }
+  }
+  dc.nn_on=cfg.nn_on;
   dc.kernelh=cfg.kernelh; dc.ovkernelh=1.f/cfg.kernelh; dc.kernelsize2=k.kernelsize2; dc.eta2=k.eta2; dc.awen=k.awen; dc.bwen=k.bwen;
   dc.cub_a2=k.cub_a2; dc.cub_a24=k.cub_a24; dc.cub_c1=k.cub_c1; dc.cub_d1=k.cub_d1; dc.cub_c2=k.cub_c2; dc.cub_od_wdeltap=k.cub_od_wdeltap;
   dc.bwen_ovh=float(double(k.bwen)/double(cfg.kernelh)); dc.cub_c1_ovh=float(double(k.cub_c1)/double(cfg.kernelh)); dc.cub_d1_ovh=float(double(k.cub_d1)/double(cfg.kernelh));
@@ -89,14 +111,18 @@ void Engine::FreeAll(){
     DevFree(velrhopm1[b]); DevFree(pospre[b]); DevFree(velrhoppre[b]); DevFree(spstau[b]);
     DevFree(rs.keys[b]); DevFree(rs.vals[b]);
   }
-  DevFree(posp); DevFree(acear); DevFree(shiftposfs); DevFree(spsgradvel);
+  DevFree(posp); DevFree(acear); DevFree(shiftposfs); DevFree(spsgradvel); DevFree(viscoeta); DevFree(nntau);
   DevFree(rs.hist); DevFree(rs.chunksum); DevFree(rs.chunksum2);
   DevFree(begincell); DevFree(sufmin); DevFree(divparams); DevFree(limits); DevFree(fmax); DevFree(perilist); DevFree(pericount);
 }
 
 void Engine::Allocate(unsigned capacity){
   cap=std::max(capacity,1024u);
-  const bool verlet=(cfg.tstep==DSPH_STEP_VERLET), sympl=(cfg.tstep==DSPH_STEP_SYMPLECTIC), sps=(cfg.tvisco==DSPH_VISCO_LAMINARSPS);
+  const bool verlet=(cfg.tstep==DSPH_STEP_VERLET), sympl=(cfg.tstep==DSPH_STEP_SYMPLECTIC);
+  if(cfg.nn_on && cfg.nn_velgrad==DSPH_VELGRAD_SPH && cfg.tvisco!=DSPH_VISCO_ARTIFICIAL){
+    DevAlloc(viscoeta,cap);
+    if(cfg.tvisco==DSPH_VISCO_CONSTEQ)DevAlloc(nntau,size_t(cap)*6);
+  }
   for(int b=0;b<2;b++){
     DevAlloc(idp[b],cap); DevAlloc(code[b],cap); DevAlloc(dcell[b],cap); DevAlloc(pos[b],size_t(cap)*3); DevAlloc(velrhop[b],cap);
     if(verlet)DevAlloc(velrhopm1[b],cap);
@@ -140,7 +166,7 @@ void Engine::Upload(unsigned np_,unsigned npb_,const unsigned *hidp,const typeco
   CUCHECK(cudaMemcpyAsync(pos[cur],hpos,size_t(np)*24,cudaMemcpyHostToDevice,stm));
   CUCHECK(cudaMemcpyAsync(velrhop[cur],hvelrhop,size_t(np)*16,cudaMemcpyHostToDevice,stm));
   if(cfg.tstep==DSPH_STEP_VERLET)CUCHECK(cudaMemcpyAsync(velrhopm1[cur],hvelrhop,size_t(np)*16,cudaMemcpyHostToDevice,stm));
-  if(cfg.tvisco==DSPH_VISCO_LAMINARSPS)CUCHECK(cudaMemsetAsync(spstau[cur],0,size_t(np)*24,stm));
+  if(sps)CUCHECK(cudaMemsetAsync(spstau[cur],0,size_t(np)*24,stm));
   // JSph::LoadDcellParticles (S/JSph.cpp:1690-1711): first cell hash, same double arithmetic, on the device
   CUCHECK(cudaMemsetAsync(limits,0,4,stm));
   if(np){ ker_upload_dcell<<<(np+255)/256,256,0,stm>>>(np,pos[cur],code[cur],dcell[cur],limits,dc,
@@ -159,7 +185,7 @@ void Engine::SetVelrhopM1(const float *h){
 }
 
 void Engine::SetSpsTau(const float *h){
-  if(cfg.tvisco!=DSPH_VISCO_LAMINARSPS)throw EngineError(DSPH_ERR_STATE,"SpsTau is only used by Laminar+SPS.");
+  if(!sps)throw EngineError(DSPH_ERR_STATE,"SpsTau is only used by Laminar+SPS.");
   CUCHECK(cudaMemcpyAsync(spstau[cur],h,size_t(np)*24,cudaMemcpyHostToDevice,stm));
   CUCHECK(cudaStreamSynchronize(stm));
 }
@@ -210,7 +236,7 @@ void Engine::RunPeriodic(){
         d.velrhopm1=(cfg.tstep==DSPH_STEP_VERLET? velrhopm1[cur]: nullptr);
         d.pospre=(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre? pospre[cur]: nullptr);
         d.velrhoppre=(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre? velrhoppre[cur]: nullptr);
-        d.spstau=(cfg.tvisco==DSPH_VISCO_LAMINARSPS? spstau[cur]: nullptr);
+        d.spstau=(sps? spstau[cur]: nullptr);
         ker_peri_duplicate<<<(num2+B-1)/B,B,0,stm>>>(pa,flags,np,d,dc); launches++;
         np+=count;
         if(!ctype)npbper+=count; else npfper+=count;
@@ -271,9 +297,11 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
     a.pos_in=pos[cur]; a.pos_out=pos[o]; a.velrhop_in=velrhop[cur]; a.velrhop_out=velrhop[o];
     if(cfg.tstep==DSPH_STEP_VERLET){ a.velrhopm1_in=velrhopm1[cur]; a.velrhopm1_out=velrhopm1[o]; }
     if(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre){ a.pospre_in=pospre[cur]; a.pospre_out=pospre[o]; a.velrhoppre_in=velrhoppre[cur]; a.velrhoppre_out=velrhoppre[o]; }
-    if(cfg.tvisco==DSPH_VISCO_LAMINARSPS){ a.spstau_in=spstau[cur]; a.spstau_out=spstau[o]; }
+    if(sps){ a.spstau_in=spstau[cur]; a.spstau_out=spstau[o]; }
     a.posp=posp;
-    ker_div_reorder<<<(nptot+B-1)/B,B,0,stm>>>(nptot,rs.vals[sidx],a,dc); launches++;
+    if(cfg.nn_on)ker_div_reorder<true><<<(nptot+B-1)/B,B,0,stm>>>(nptot,rs.vals[sidx],a,dc,dph);
+    else ker_div_reorder<false><<<(nptot+B-1)/B,B,0,stm>>>(nptot,rs.vals[sidx],a,dc,dph);
+    launches++;
     cur=o;
   }
   CUCHECK(cudaEventRecord(ev[6],stm));
@@ -337,6 +365,7 @@ ForceParams Engine::MakeForceParams(){
   for(int i=0;i<3;i++)t.cellzero[i]=dp.cellmin[i];
   t.begincell=begincell; t.dcell=dcell[cur]; t.posp=posp; t.velrhop=velrhop[cur]; t.code=code[cur];
   t.spstau=spstau[cur]; t.spsgradvel=spsgradvel; t.shiftposfs=shiftposfs; t.acear=acear; t.fmax=fmax;
+  t.viscoeta=viscoeta; t.nntau=nntau;
   return t;
 }
 
@@ -384,12 +413,18 @@ void Engine::ForcesLaunch(int interstep){
   const ForceParams t=MakeForceParams();
   const unsigned npf=np-npb;
   const bool shift=(cfg.shiftmode!=0);
-  if(npf){
+  if(npf && cfg.nn_on){
+    if(mgpu && cfg.nn_velgrad==DSPH_VELGRAD_SPH)throw EngineError(DSPH_ERR_ARG,"The SPH velocity-gradient approach is not available with x-slab decomposition.");
+    const unsigned nl=LaunchForcesNN(cfg.tkernel,cfg.tvisco,cfg.tdensity,shift,t,dc,dph,stm);
+    if(!nl)throw EngineError(DSPH_ERR_ARG,"Kernel / viscosity / DDT choice is not valid for the multiphase formulation.");
+    launches+=nl;
+  }
+  else if(npf){
     if(cfg.tkernel==DSPH_KERNEL_WENDLAND)LaunchFluid1<DSPH_KERNEL_WENDLAND>(forcevariant,cfg.tvisco,cfg.tdensity,shift,npf,t,dc,stm);
     else if(cfg.tkernel==DSPH_KERNEL_CUBIC)LaunchFluid1<DSPH_KERNEL_CUBIC>(forcevariant,cfg.tvisco,cfg.tdensity,shift,npf,t,dc,stm);
     else throw EngineError(DSPH_ERR_ARG,"Kernel choice is not valid.");
     launches++;
-    if(cfg.tvisco==DSPH_VISCO_LAMINARSPS){ ker_sps_tau<<<(npf+255)/256,256,0,stm>>>(npf,npb,velrhop[cur],spsgradvel,spstau[cur],dc); launches++; }
+    if(sps){ ker_sps_tau<<<(npf+255)/256,256,0,stm>>>(npf,npb,velrhop[cur],spsgradvel,spstau[cur],dc); launches++; }
   }
   CUCHECK(cudaEventRecord(ev[13],stm));
   if(npb){
@@ -415,15 +450,19 @@ void Engine::ForcesFinish(dsph_forceres *res){
   b=m.viscdt_bits; memcpy(&f,&b,4); viscdtmax=f;
   b=m.ace2_bits; memcpy(&f,&b,4); acemax=sqrt(double(f));
   b=m.vel2_bits; memcpy(&f,&b,4); velmax=double(sqrtf(f));
+  b=m.visceta_bits; memcpy(&f,&b,4); viscetadtmax=f;
   forcesok=true;
   if(res)FillForceRes(res);
 }
 
-double Engine::DtVariable(double *pdt1,double *pdt2)const{
+double Engine::DtVariable(double *pdt1,double *pdt2,double *pdt3)const{
   // JSphGpu::DtVariable S/JSphGpu.cpp:984-1009 (== JSphCpu::DtVariable S/JSphCpu.cpp:1614-1639)
   const double dt1=(acemax? (sqrt(double(cfg.kernelh)/acemax)): DBL_MAX);
   const double dt2=double(cfg.kernelh)/(std::max(k.cs0,velmax*10.)+double(cfg.kernelh)*viscdtmax);
-  double dt=cfg.cflnumber*std::min(dt1,dt2);
+  // viscous time step of the multiphase fork (M/JSphCpu.cpp:1687-1689, M/JSphGpu.cpp:1075-1078)
+  const double dt3=(cfg.nn_on && viscetadtmax*dph.lamda>0? double(cfg.kernelh*cfg.kernelh)/double(viscetadtmax*dph.lamda): DBL_MAX);
+  if(pdt3)*pdt3=dt3;
+  double dt=cfg.cflnumber*std::min(dt3,std::min(dt1,dt2));
   if(cfg.dtfixed_on)dt=cfg.dtfixed;
   if(dt!=dt || std::isinf(dt))throw EngineError(DSPH_ERR_PHYSICS,"The computed Dt is NaN or infinity.");
   if(dt<k.dtmin)dt=k.dtmin;
@@ -433,7 +472,8 @@ double Engine::DtVariable(double *pdt1,double *pdt2)const{
 void Engine::FillForceRes(dsph_forceres *res)const{
   memset(res,0,sizeof(*res));
   res->viscdtmax=viscdtmax; res->acemax=float(acemax); res->velmax=float(velmax);
-  res->dt=DtVariable(&res->dt1,&res->dt2);
+  res->viscetadtmax=viscetadtmax;
+  res->dt=DtVariable(&res->dt1,&res->dt2,&res->dt3);
 }
 
 void Engine::ForcesDownload(unsigned first,unsigned count,float *ace,float *ar){

@@ -40,6 +40,9 @@ class Engine {
   double *pos[2]={}; float4 *velrhop[2]={}, *velrhopm1[2]={}, *velrhoppre[2]={}; double *pospre[2]={};
   float *spstau[2]={};
   float4 *posp=nullptr, *acear=nullptr, *shiftposfs=nullptr; float *spsgradvel=nullptr;
+  // multiphase non-Newtonian fork (src_mphase): phases + scratch of the SPH velocity-gradient approach
+  DevPhases dph; float *viscoeta=nullptr, *nntau=nullptr; float viscetadtmax=0;
+  bool sps=false;   // Laminar+SPS of the single-phase solver: SpsTau is particle state (sorted, duplicated, exchanged)
   // cell division
   RadixSortBuffers rs;
   unsigned *begincell=nullptr, *sufmin=nullptr, *limits=nullptr, *perilist=nullptr, *pericount=nullptr;
@@ -82,7 +85,7 @@ class Engine {
   void MgUnpack(const unsigned counts[6],const void *recvleft,const void *recvright);
   void ForcesDownload(unsigned first,unsigned count,float *ace,float *ar);
   void Pips(unsigned long long *fr,unsigned long long *fc,unsigned long long *br,unsigned long long *bc);
-  double DtVariable(double *dt1,double *dt2)const;
+  double DtVariable(double *dt1,double *dt2,double *dt3=nullptr)const;
   void FillForceRes(dsph_forceres *res)const;
   StepArrays MakeStepArrays();
   void ShiftCoefs(double dt,double &coefumagn,double &coeftfs,float &maxdist)const;

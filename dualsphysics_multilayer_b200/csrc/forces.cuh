@@ -42,6 +42,8 @@ struct ForceParams {
   float4* __restrict__ shiftposfs;      // OUT (shifting)
   float4* __restrict__ acear;           // OUT
   ForceMax* __restrict__ fmax;
+  float* __restrict__ viscoeta;         // multiphase, SPH velocity gradients: effective viscosity per particle
+  float* __restrict__ nntau;            // multiphase, constitutive equation: stress tensor, 6 floats per particle
 };
 
 __device__ __forceinline__ float PowNearOne(float rh,const DevCtes &c){

@@ -1,0 +1,436 @@
+// forces_nn.cuh -- Interaction_Forces of the multiphase non-Newtonian ("multilayer") fork for sm_100a.
+//
+// Physics of one pair follows the reference CPU kernels, which are the oracle:
+//   FDA approach  JSphCpu::InteractionForcesFluid_NN_FDA_All          M/JSphCpu_NN_FDA.cpp:129-340   (one pass)
+//   SPH approach  InteractionForcesFluid_NN_SPH_PressGrad             M/JSphCpu_NN_SPH.cpp:452-620   (pass 1: pressure, continuity, grad v)
+//                 InteractionForcesFluid_NN_SPH_Visco_eta              :174-228                       (per particle: D, eta_eff)
+//                 InteractionForcesFluid_NN_SPH_Morris                 :337-446                       (pass 2a: Morris operator)
+//                 ..._Visco_Stress_tensor + ..._ConsEq                 :128-169, :234-331             (pass 2b: div(tau))
+//   tensors       JSphCpu_Tensors.cpp (GetVelocityGradients_FDA, GetStrainRateTensor[_tsym], GetEta_Effective, GetStressTensor[_sym])
+// The reference GPU twin is M/JSphGpu_NN_ker.cu:461-1482 (KerInteractionForcesFluid_NN_FDA / _NN_SPH_*), which reads ten
+// phases from __constant__ arrays; here the phases travel as a by-value kernel parameter (DevPhases) and every pair uses
+// the cell-relative float positions + the per-particle pressure written by the reorder kernel (celldiv.cuh).
+//
+// Pair order, the fluid-fluid / fluid-boundary split and the order in which the partial sums are added are the oracle's,
+// so Ace/Ar agree with the CPU restatement to rounding of the pair distance (tests/test_gpu_parity.py, nn_* cases).
+#pragma once
+#include "celldiv.cuh"
+#include "forces.cuh"
+
+namespace dsph {
+
+struct NNAcc { float visc,ar,delta,ax,ay,az; float4 shift; };
+__device__ __forceinline__ void NNZero(NNAcc &a){ a.visc=a.ar=a.delta=a.ax=a.ay=a.az=0; a.shift=make_float4(0,0,0,0); }
+
+// neighbours of one particle in the oracle's order; f(p2,drx,dry,drz,rr2,pressp2) for every accepted pair
+template<bool BOUNDP2,class F> __device__ __forceinline__ void NNForPairs(const NgRange &ng,const float4 &pp1,const ForceParams &t,const DevCtes &c,F &&f)
+{
+  const unsigned cellinit=(BOUNDP2? 0u: t.cellfluid);
+  for(int z=ng.zini;z<ng.zfin;z++){
+    const float oz=pp1.z-float(z-ng.cz)*c.scell;
+    for(int y=ng.yini;y<ng.yfin;y++){
+      const float oy=pp1.y-float(y-ng.cy)*c.scell;
+      const unsigned v=unsigned(t.nsheet*z+t.ncx*y)+cellinit;
+      unsigned pini=t.begincell[v+ng.cxini];
+      for(int x=ng.cxini;x<ng.cxfin;x++){
+        const unsigned pfin=t.begincell[v+x+1];
+        const float ox=pp1.x-float(x-ng.cx)*c.scell;
+        for(unsigned p2=pini;p2<pfin;p2++){
+          const float4 pp2=__ldg(&t.posp[p2]);
+          const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
+          const float rr2=drx*drx+dry*dry+drz*drz;
+          if(rr2<=c.kernelsize2 && rr2>=1e-18f)f(p2,drx,dry,drz,rr2,pp2.w);
+        }
+        pini=pfin;
+      }
+    }
+  }
+}
+
+// JSphCpu::GetEta_Effective M/JSphCpu_Tensors.cpp:113-141 (P: phase of p1; the other arguments come from the phase of p2)
+__device__ __forceinline__ float NNEtaEffective(const DevPhase &P,float tau_yield,float dmagn,float visco,float m_nn,float n_nn){
+  if(dmagn<=1e-18f)dmagn=1e-18f;
+  float miou_yield=(P.tau_max? P.tau_max/(2.0f*dmagn): tau_yield/(2.0f*dmagn));
+  const bool bi_region=(P.tau_max && dmagn<=P.tau_max/(2.f*P.bi_multi*visco));
+  if(bi_region)miou_yield=P.bi_multi*visco;
+  const float miouPap=miou_yield*(1.f-expf(-m_nn*dmagn));
+  const bool capped=(miouPap>m_nn*tau_yield || dmagn==1e-18f);
+  const float term1=(P.tau_max? miou_yield: (capped? m_nn*tau_yield: miouPap));
+  const float miouHB=visco*powf(dmagn,(n_nn-1.0f));
+  const float term2=(bi_region? visco: (capped? visco: miouHB));
+  return term1+term2;
+}
+
+template<int TKER> __device__ __forceinline__ float NNTensil(float rr2,float rhopp1,float pressp1,float rhopp2,float pressp2,const DevCtes &c){
+  if(TKER!=DSPH_KERNEL_CUBIC)return 0.f;
+  const float rad=sqrtf(rr2), qq=rad/c.kernelh;
+  float wab;
+  if(rad>c.kernelh){ const float wqq1=2.0f-qq; const float wqq2=wqq1*wqq1; wab=c.cub_a24*(wqq2*wqq1); }
+  else{ const float wqq2=qq*qq; wab=c.cub_a2*(1.0f+(0.75f*qq-1.5f)*wqq2); }
+  float fab=wab*c.cub_od_wdeltap; fab*=fab; fab*=fab;
+  const float t1=(pressp1/(rhopp1*rhopp1))*(pressp1>0? 0.01f: -0.2f);
+  const float t2=(pressp2/(rhopp2*rhopp2))*(pressp2>0? 0.01f: -0.2f);
+  return fab*(t1+t2);
+}
+
+// pressure, continuity, DDT and shifting of one pair: M/JSphCpu_NN_FDA.cpp:205-251 == M/JSphCpu_NN_SPH.cpp:528-581
+template<int TKER,int TDDT,bool SHIFT,bool BOUNDP2> __device__ __forceinline__ void NNPairBasic(
+  unsigned pp1,unsigned pp2,unsigned codep2,float massp2,const float4 &velrhop1,float pressp1,float pressp2,const float4 &velrhop2,
+  float drx,float dry,float drz,float rr2,float frx,float fry,float frz,float &dvx,float &dvy,float &dvz,
+  const DevCtes &c,const DevPhases &ph,NNAcc &a)
+{
+  const float rhopp1=velrhop1.w;
+  {
+    const float prs=(pressp1+pressp2)/(rhopp1*velrhop2.w)+NNTensil<TKER>(rr2,rhopp1,pressp1,velrhop2.w,pressp2,c);
+    const float p_vpm=-prs*massp2;
+    a.ax+=p_vpm*frx; a.ay+=p_vpm*fry; a.az+=p_vpm*frz;
+  }
+  const float rhop1over2=rhopp1/velrhop2.w;
+  dvx=velrhop1.x-velrhop2.x; dvy=velrhop1.y-velrhop2.y; dvz=velrhop1.z-velrhop2.z;
+  a.ar+=massp2*(dvx*frx+dvy*fry+dvz*frz)*rhop1over2;
+  const float cbar=ph.ph[pp2].cs0;
+  if(TDDT==DSPH_DDT_DDT){
+    if(a.delta!=FLT_MAX){
+      const float visc_densi=c.ddtkh*cbar*(rhop1over2-1.f)/(rr2+c.eta2);
+      const float dot3=(drx*frx+dry*fry+drz*frz);
+      const float delta=(pp1==pp2? visc_densi*dot3*massp2: 0.f);
+      a.delta=(BOUNDP2? FLT_MAX: a.delta+delta);
+    }
+  }
+  if(TDDT==DSPH_DDT_DDT2 || (TDDT==DSPH_DDT_DDT2FULL && !BOUNDP2)){
+    if(a.delta!=FLT_MAX){
+      const float rh=1.f+c.ddtgz*drz;
+      const float drhop=c.rhopzero*(PowNearOne(rh,c)-1.f);
+      const float visc_densi=c.ddtkh*cbar*((velrhop2.w-rhopp1)-drhop)/(rr2+c.eta2);
+      const float dot3=(drx*frx+dry*fry+drz*frz);
+      const float delta=(pp1==pp2? visc_densi*dot3*massp2/velrhop2.w: 0.f);
+      a.delta=(BOUNDP2? FLT_MAX: a.delta-delta);
+    }
+  }
+  if(SHIFT){
+    if(a.shift.x!=FLT_MAX){
+      const bool heavyphase=(ph.ph[pp1].mass>ph.ph[pp2].mass && pp1!=pp2);
+      const float massrhop=massp2/velrhop2.w;
+      const bool noshift=(BOUNDP2 && (c.shiftmode==DSPH_SHIFT_NOBOUND || (c.shiftmode==DSPH_SHIFT_NOFIXED && (codep2&DSPH_CODE_MASKTYPE)==DSPH_CODE_TYPE_FIXED)));
+      a.shift.x=(noshift? FLT_MAX: (heavyphase? 0.f: a.shift.x+massrhop*frx));
+      a.shift.y+=(heavyphase? 0.f: massrhop*fry);
+      a.shift.z+=(heavyphase? 0.f: massrhop*frz);
+      a.shift.w-=(heavyphase? 0.f: massrhop*(drx*frx+dry*fry+drz*frz));
+    }
+  }
+}
+
+// result of the two passes of one particle, combined as the two CPU calls do (store condition of M/JSphCpu_NN_FDA.cpp:317-323)
+struct NNSum { float ar,ax,ay,az,delta,visc; };
+template<int TDDT,bool SHIFT> __device__ __forceinline__ bool NNStore(const NNAcc &a,NNSum &s){
+  if(SHIFT||a.ar||a.ax||a.ay||a.az||a.visc){
+    if(TDDT!=DSPH_DDT_NONE)s.delta=(s.delta==FLT_MAX || a.delta==FLT_MAX? FLT_MAX: s.delta+a.delta);
+    s.ar+=a.ar; s.ax+=a.ax; s.ay+=a.ay; s.az+=a.az;
+    s.visc=fmaxf(s.visc,a.visc);
+    return true;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FDA approach: everything in one pass per neighbour class
+// ---------------------------------------------------------------------------------------------------------------------
+template<int TKER,int TVISCO,int TDDT,bool SHIFT,bool BOUNDP2> __device__ __forceinline__ void NNPassFDA(
+  const NgRange &ng,const float4 &pp1,const float4 &velrhop1,unsigned pp1ph,const ForceParams &t,const DevCtes &c,const DevPhases &ph,
+  NNAcc &a,float &visceta)
+{
+  NNForPairs<BOUNDP2>(ng,pp1,t,c,[&](unsigned p2,float drx,float dry,float drz,float rr2,float pressp2){
+    const float fac=KernelFac<TKER>(rr2,c);
+    const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
+    unsigned codep2=0; if(!BOUNDP2 || SHIFT)codep2=t.code[p2];
+    const unsigned pp2=(BOUNDP2? pp1ph: (codep2&DSPH_CODE_MASKVALUE));
+    const float massp2=(BOUNDP2? c.massbound: ph.ph[pp2].mass);
+    const float4 velrhop2=__ldg(&t.velrhop[p2]);
+    float dvx,dvy,dvz;
+    NNPairBasic<TKER,TDDT,SHIFT,BOUNDP2>(pp1ph,pp2,codep2,massp2,velrhop1,pp1.w,pressp2,velrhop2,drx,dry,drz,rr2,frx,fry,frz,dvx,dvy,dvz,c,ph,a);
+    const float cbar=ph.ph[pp2].cs0;
+    const float dot=drx*dvx+dry*dvy+drz*dvz;
+    const float dot_rr2=dot/(rr2+c.eta2);
+    a.visc=fmaxf(dot_rr2,a.visc);
+    const float visco_NN=ph.ph[pp2].visco;
+    if(TVISCO==DSPH_VISCO_ARTIFICIAL){
+      if(dot<0){
+        const float amubar=c.kernelh*dot_rr2;
+        const float robar=(velrhop1.w+velrhop2.w)*0.5f;
+        const float pi_visc=(-visco_NN*cbar*amubar/robar)*massp2;
+        a.ax-=pi_visc*frx; a.ay-=pi_visc*fry; a.az-=pi_visc*frz;
+      }
+    }
+    else{
+      if(BOUNDP2){ dvx=2.f*velrhop1.x; dvy=2.f*velrhop1.y; dvz=2.f*velrhop1.z; }      // no-slip on the tensor
+      const float a11=dvx*drx/rr2,a12=dvx*dry/rr2,a13=dvx*drz/rr2;
+      const float a21=dvy*drx/rr2,a22=dvy*dry/rr2,a23=dvy*drz/rr2;
+      const float a31=dvz*drx/rr2,a32=dvz*dry/rr2,a33=dvz*drz/rr2;
+      const float div_vel=(a11+a22+a33)/3.f;
+      const float d11=a11-div_vel, d12=0.5f*(a12+a21), d13=0.5f*(a13+a31);
+      const float d21=0.5f*(a21+a12), d22=a22-div_vel, d23=0.5f*(a23+a32);
+      const float d31=0.5f*(a31+a13), d32=0.5f*(a32+a23), d33=a33-div_vel;
+      const float II_D_1=d11*d22+d22*d33+d11*d33;
+      const float II_D_2=d12*d21+d23*d32+d13*d31;
+      const float II_D=II_D_1-II_D_2;
+      const float dmagn=sqrtf(II_D*II_D);
+      const float eta=NNEtaEffective(ph.ph[pp1ph],ph.ph[pp2].tau_yield,dmagn,visco_NN,ph.ph[pp2].m_nn,ph.ph[pp2].n_nn);
+      visceta=fmaxf(eta,visceta);
+      if(TVISCO==DSPH_VISCO_LAMINARSPS){
+        const float temp=2.0f*eta/((rr2+c.eta2)*velrhop2.w);
+        const float vtemp=massp2*temp*(drx*frx+dry*fry+drz*frz);
+        a.ax+=vtemp*dvx; a.ay+=vtemp*dvy; a.az+=vtemp*dvz;
+      }
+      else{
+        const float t2=2.f*eta;
+        const float taux=((t2*d11)*frx+(t2*d12)*fry+(t2*d13)*frz)/(velrhop2.w);
+        const float tauy=((t2*d21)*frx+(t2*d22)*fry+(t2*d23)*frz)/(velrhop2.w);
+        const float tauz=((t2*d31)*frx+(t2*d32)*fry+(t2*d33)*frz)/(velrhop2.w);
+        a.ax+=taux*massp2; a.ay+=tauy*massp2; a.az+=tauz*massp2;
+      }
+    }
+  });
+}
+
+template<int TKER,int TVISCO,int TDDT,bool SHIFT> __global__ void __launch_bounds__(FORCES_THREADS)
+ker_nn_fda(ForceParams t,DevCtes c,DevPhases ph)
+{
+  const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
+  float viscmax=0,ace2=0,vel2=0,etamax=0;
+  if(p1<t.np){
+    const unsigned code1=t.code[p1];
+    const bool ghost=((code1&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_PERIODIC);
+    const float4 velrhop1=t.velrhop[p1];
+    if(!(t.skipghosts && ghost)){
+      const float4 pp1=t.posp[p1];
+      const unsigned pp1ph=code1&DSPH_CODE_MASKVALUE;
+      const NgRange ng=NgInit(t.dcell[p1],t,c);
+      NNSum s; s.ar=s.ax=s.ay=s.az=s.delta=s.visc=0;
+      NNAcc a; NNZero(a);
+      float visceta=0;
+      NNPassFDA<TKER,TVISCO,TDDT,SHIFT,false>(ng,pp1,velrhop1,pp1ph,t,c,ph,a,visceta);
+      if(NNStore<TDDT,SHIFT>(a,s))etamax=fmaxf(etamax,visceta);
+      const float4 shiftff=a.shift;
+      NNZero(a); if(SHIFT)a.shift=shiftff; visceta=0;
+      NNPassFDA<TKER,TVISCO,TDDT,SHIFT,true>(ng,pp1,velrhop1,pp1ph,t,c,ph,a,visceta);
+      if(NNStore<TDDT,SHIFT>(a,s))etamax=fmaxf(etamax,visceta);
+      if(c.simulate2d)s.ay=0;
+      if(TDDT!=DSPH_DDT_NONE && s.delta!=FLT_MAX)s.ar+=s.delta;
+      t.acear[p1]=make_float4(s.ax,s.ay,s.az,s.ar);
+      if(SHIFT)t.shiftposfs[p1]=a.shift;
+      viscmax=s.visc;
+      if(!c.ghosts || !ghost)ace2=s.ax*s.ax+s.ay*s.ay+s.az*s.az;
+    }
+    vel2=velrhop1.x*velrhop1.x+velrhop1.y*velrhop1.y+velrhop1.z*velrhop1.z;
+  }
+  WarpMaxToGlobal(viscmax,&t.fmax->viscdt_bits);
+  WarpMaxToGlobal(ace2,&t.fmax->ace2_bits);
+  WarpMaxToGlobal(vel2,&t.fmax->vel2_bits);
+  WarpMaxToGlobal(etamax,&t.fmax->visceta_bits);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SPH approach, pass 1: pressure, continuity, DDT, shifting + symmetric velocity gradient
+// ---------------------------------------------------------------------------------------------------------------------
+template<int TKER,int TVISCO,int TDDT,bool SHIFT,bool BOUNDP2> __device__ __forceinline__ void NNPassPressGrad(
+  const NgRange &ng,const float4 &pp1,const float4 &velrhop1,unsigned pp1ph,const ForceParams &t,const DevCtes &c,const DevPhases &ph,
+  NNAcc &a,float *g)
+{
+  NNForPairs<BOUNDP2>(ng,pp1,t,c,[&](unsigned p2,float drx,float dry,float drz,float rr2,float pressp2){
+    const float fac=KernelFac<TKER>(rr2,c);
+    const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
+    unsigned codep2=0; if(!BOUNDP2 || SHIFT)codep2=t.code[p2];
+    const unsigned pp2=(BOUNDP2? pp1ph: (codep2&DSPH_CODE_MASKVALUE));
+    const float massp2=(BOUNDP2? c.massbound: ph.ph[pp2].mass);
+    const float4 velrhop2=__ldg(&t.velrhop[p2]);
+    float dvx,dvy,dvz;
+    NNPairBasic<TKER,TDDT,SHIFT,BOUNDP2>(pp1ph,pp2,codep2,massp2,velrhop1,pp1.w,pressp2,velrhop2,drx,dry,drz,rr2,frx,fry,frz,dvx,dvy,dvz,c,ph,a);
+    const float dot=drx*dvx+dry*dvy+drz*dvz;
+    const float dot_rr2=dot/(rr2+c.eta2);
+    a.visc=fmaxf(dot_rr2,a.visc);
+    if(TVISCO!=DSPH_VISCO_ARTIFICIAL){
+      if(BOUNDP2){ dvx=2.f*velrhop1.x; dvy=2.f*velrhop1.y; dvz=2.f*velrhop1.z; }
+      const float volp2=-massp2/velrhop2.w;
+      float dv=dvx*volp2; g[0]+=dv*frx; g[1]+=dv*fry; g[2]+=dv*frz;
+            dv=dvy*volp2; g[1]+=dv*frx; g[3]+=dv*fry; g[4]+=dv*frz;
+            dv=dvz*volp2; g[2]+=dv*frx; g[4]+=dv*fry; g[5]+=dv*frz;
+    }
+  });
+}
+
+// Writes acear (pressure part), shiftposfs, viscdt/vel maxima and, per particle, eta_eff (+ tau for the constitutive eq.)
+template<int TKER,int TVISCO,int TDDT,bool SHIFT> __global__ void __launch_bounds__(FORCES_THREADS)
+ker_nn_sph_pressgrad(ForceParams t,DevCtes c,DevPhases ph)
+{
+  const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
+  float viscmax=0,vel2=0,etamax=0;
+  if(p1<t.np){
+    const unsigned code1=t.code[p1];
+    const float4 velrhop1=t.velrhop[p1];
+    const float4 pp1=t.posp[p1];
+    const unsigned pp1ph=code1&DSPH_CODE_MASKVALUE;
+    const NgRange ng=NgInit(t.dcell[p1],t,c);
+    NNSum s; s.ar=s.ax=s.ay=s.az=s.delta=s.visc=0;
+    float gs[6]={0,0,0,0,0,0};
+    NNAcc a; NNZero(a);
+    float g[6]={0,0,0,0,0,0};
+    NNPassPressGrad<TKER,TVISCO,TDDT,SHIFT,false>(ng,pp1,velrhop1,pp1ph,t,c,ph,a,g);
+    if(NNStore<TDDT,SHIFT>(a,s)){
+      #pragma unroll
+      for(int k=0;k<6;k++)gs[k]+=g[k];
+    }
+    const float4 shiftff=a.shift;
+    NNZero(a); if(SHIFT)a.shift=shiftff;
+    #pragma unroll
+    for(int k=0;k<6;k++)g[k]=0;
+    NNPassPressGrad<TKER,TVISCO,TDDT,SHIFT,true>(ng,pp1,velrhop1,pp1ph,t,c,ph,a,g);
+    if(NNStore<TDDT,SHIFT>(a,s)){
+      #pragma unroll
+      for(int k=0;k<6;k++)gs[k]+=g[k];
+    }
+    if(TDDT!=DSPH_DDT_NONE && s.delta!=FLT_MAX)s.ar+=s.delta;     // Deltac is folded in after all passes; it only touches ar
+    t.acear[p1]=make_float4(s.ax,s.ay,s.az,s.ar);
+    if(SHIFT)t.shiftposfs[p1]=a.shift;
+    viscmax=s.visc;
+    vel2=velrhop1.x*velrhop1.x+velrhop1.y*velrhop1.y+velrhop1.z*velrhop1.z;
+    if(TVISCO!=DSPH_VISCO_ARTIFICIAL){
+      // InteractionForcesFluid_NN_SPH_Visco_eta + GetStrainRateTensor_tsym (M/JSphCpu_NN_SPH.cpp:174-228, Tensors:184-207)
+      const float div_vel=(gs[0]+gs[3]+gs[5])/3.f;
+      const float dxx=gs[0]-div_vel, dxy=0.5f*gs[1], dxz=0.5f*gs[2], dyy=gs[3]-div_vel, dyz=0.5f*gs[4], dzz=gs[5]-div_vel;
+      const float II_D_1=dxx*dyy+dyy*dzz+dxx*dzz;
+      const float II_D_2=dxy*dxy+dyz*dyz+dxz*dxz;
+      const float II_D=-II_D_1+II_D_2;
+      const float dmagn=sqrtf(II_D);
+      const DevPhase &P=ph.ph[pp1ph];
+      const float eta=NNEtaEffective(P,P.tau_yield,dmagn,P.visco,P.m_nn,P.n_nn);
+      t.viscoeta[p1]=eta;
+      etamax=eta;
+      if(TVISCO==DSPH_VISCO_CONSTEQ){          // GetStressTensor_sym (Tensors:211-231)
+        const float t2=2.f*eta;
+        float *tau=t.nntau+6*size_t(p1);
+        tau[0]=t2*dxx; tau[1]=t2*dxy; tau[2]=t2*dxz; tau[3]=t2*dyy; tau[4]=t2*dyz; tau[5]=t2*dzz;
+      }
+    }
+  }
+  WarpMaxToGlobal(viscmax,&t.fmax->viscdt_bits);
+  WarpMaxToGlobal(vel2,&t.fmax->vel2_bits);
+  WarpMaxToGlobal(etamax,&t.fmax->visceta_bits);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SPH approach, pass 2: viscous forces (artificial / Morris operator / divergence of the stress tensor)
+// ---------------------------------------------------------------------------------------------------------------------
+template<int TKER,int TVISCO,bool BOUNDP2> __device__ __forceinline__ void NNPassVisco(
+  const NgRange &ng,const float4 &pp1,const float4 &velrhop1,unsigned pp1ph,float eta1,const float *tau1,
+  const ForceParams &t,const DevCtes &c,const DevPhases &ph,float &ax,float &ay,float &az)
+{
+  NNForPairs<BOUNDP2>(ng,pp1,t,c,[&](unsigned p2,float drx,float dry,float drz,float rr2,float){
+    const float fac=KernelFac<TKER>(rr2,c);
+    const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
+    const unsigned pp2=(BOUNDP2? pp1ph: (t.code[p2]&DSPH_CODE_MASKVALUE));
+    const float massp2=(BOUNDP2? c.massbound: ph.ph[pp2].mass);
+    const float4 velrhop2=__ldg(&t.velrhop[p2]);
+    if(TVISCO==DSPH_VISCO_CONSTEQ){
+      float ts[6];
+      #pragma unroll
+      for(int k=0;k<6;k++)ts[k]=tau1[k]+(BOUNDP2? tau1[k]: t.nntau[6*size_t(p2)+k]);
+      const float taux=(ts[0]*frx+ts[1]*fry+ts[2]*frz)/(velrhop2.w);
+      const float tauy=(ts[1]*frx+ts[3]*fry+ts[4]*frz)/(velrhop2.w);
+      const float tauz=(ts[2]*frx+ts[4]*fry+ts[5]*frz)/(velrhop2.w);
+      ax+=taux*massp2; ay+=tauy*massp2; az+=tauz*massp2;
+    }
+    else{
+      float dvx=velrhop1.x-velrhop2.x, dvy=velrhop1.y-velrhop2.y, dvz=velrhop1.z-velrhop2.z;
+      if(BOUNDP2){ dvx=2.f*velrhop1.x; dvy=2.f*velrhop1.y; dvz=2.f*velrhop1.z; }
+      if(TVISCO==DSPH_VISCO_ARTIFICIAL){
+        const float dot=drx*dvx+dry*dvy+drz*dvz;
+        if(dot<0){
+          const float dot_rr2=dot/(rr2+c.eta2);
+          const float amubar=c.kernelh*dot_rr2;
+          const float robar=(velrhop1.w+velrhop2.w)*0.5f;
+          const float pi_visc=(-ph.ph[pp2].visco*ph.ph[pp2].cs0*amubar/robar)*massp2;
+          ax-=pi_visc*frx; ay-=pi_visc*fry; az-=pi_visc*frz;
+        }
+      }
+      else{
+        const float eta2=(BOUNDP2? eta1: t.viscoeta[p2]);
+        const float temp=(eta1+eta2)/((rr2+c.eta2)*velrhop2.w);
+        const float vtemp=massp2*temp*(drx*frx+dry*fry+drz*frz);
+        ax+=vtemp*dvx; ay+=vtemp*dvy; az+=vtemp*dvz;
+      }
+    }
+  });
+}
+
+template<int TKER,int TVISCO> __global__ void __launch_bounds__(FORCES_THREADS)
+ker_nn_sph_visco(ForceParams t,DevCtes c,DevPhases ph)
+{
+  const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
+  float ace2=0;
+  if(p1<t.np){
+    const unsigned code1=t.code[p1];
+    const float4 velrhop1=t.velrhop[p1];
+    const float4 pp1=t.posp[p1];
+    const unsigned pp1ph=code1&DSPH_CODE_MASKVALUE;
+    const NgRange ng=NgInit(t.dcell[p1],t,c);
+    float eta1=0; float tau1[6]={0,0,0,0,0,0};
+    if(TVISCO==DSPH_VISCO_LAMINARSPS)eta1=t.viscoeta[p1];
+    if(TVISCO==DSPH_VISCO_CONSTEQ){
+      #pragma unroll
+      for(int k=0;k<6;k++)tau1[k]=t.nntau[6*size_t(p1)+k];
+    }
+    float4 acc=t.acear[p1];
+    float ax=0,ay=0,az=0;
+    NNPassVisco<TKER,TVISCO,false>(ng,pp1,velrhop1,pp1ph,eta1,tau1,t,c,ph,ax,ay,az);
+    if(ax||ay||az){ acc.x=acc.x+ax; acc.y=acc.y+ay; acc.z=acc.z+az; }
+    ax=ay=az=0;
+    NNPassVisco<TKER,TVISCO,true>(ng,pp1,velrhop1,pp1ph,eta1,tau1,t,c,ph,ax,ay,az);
+    if(ax||ay||az){ acc.x=acc.x+ax; acc.y=acc.y+ay; acc.z=acc.z+az; }
+    if(c.simulate2d)acc.y=0;
+    t.acear[p1]=acc;
+    const bool ghost=((code1&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_PERIODIC);
+    if(!c.ghosts || !ghost)ace2=acc.x*acc.x+acc.y*acc.y+acc.z*acc.z;
+  }
+  WarpMaxToGlobal(ace2,&t.fmax->ace2_bits);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host dispatch
+// ---------------------------------------------------------------------------------------------------------------------
+template<int TKER,int TVISCO,int TDDT,bool SHIFT> static unsigned LaunchNN4(const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
+  const unsigned npf=t.np-t.npb, nb=(npf+FORCES_THREADS-1)/FORCES_THREADS;
+  if(ph.velgrad==DSPH_VELGRAD_FDA){ ker_nn_fda<TKER,TVISCO,TDDT,SHIFT><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph); return 1; }
+  ker_nn_sph_pressgrad<TKER,TVISCO,TDDT,SHIFT><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
+  ker_nn_sph_visco<TKER,TVISCO><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
+  return 2;
+}
+template<int TKER,int TVISCO,int TDDT> static unsigned LaunchNN3(bool shift,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
+  return shift? LaunchNN4<TKER,TVISCO,TDDT,true>(t,c,ph,stm): LaunchNN4<TKER,TVISCO,TDDT,false>(t,c,ph,stm);
+}
+template<int TKER,int TVISCO> static unsigned LaunchNN2(int tddt,bool shift,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
+  switch(tddt){
+    case DSPH_DDT_NONE:     return LaunchNN3<TKER,TVISCO,DSPH_DDT_NONE>(shift,t,c,ph,stm);
+    case DSPH_DDT_DDT:      return LaunchNN3<TKER,TVISCO,DSPH_DDT_DDT>(shift,t,c,ph,stm);
+    case DSPH_DDT_DDT2:     return LaunchNN3<TKER,TVISCO,DSPH_DDT_DDT2>(shift,t,c,ph,stm);
+    case DSPH_DDT_DDT2FULL: return LaunchNN3<TKER,TVISCO,DSPH_DDT_DDT2FULL>(shift,t,c,ph,stm);
+  }
+  return 0;
+}
+template<int TKER> static unsigned LaunchNN1(int tvisco,int tddt,bool shift,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
+  switch(tvisco){
+    case DSPH_VISCO_ARTIFICIAL: return LaunchNN2<TKER,DSPH_VISCO_ARTIFICIAL>(tddt,shift,t,c,ph,stm);
+    case DSPH_VISCO_LAMINARSPS: return LaunchNN2<TKER,DSPH_VISCO_LAMINARSPS>(tddt,shift,t,c,ph,stm);
+    case DSPH_VISCO_CONSTEQ:    return LaunchNN2<TKER,DSPH_VISCO_CONSTEQ>(tddt,shift,t,c,ph,stm);
+  }
+  return 0;
+}
+// Interaction of the fluid particles for the multiphase fork (cusphNN::Interaction_ForcesNN, M/JSphGpu_NN_ker.h:31-41).
+// Writes acear (+shiftposfs) for [npb,np) and the four maxima of t.fmax; returns the number of kernels launched.
+static unsigned LaunchForcesNN(int tkernel,int tvisco,int tdensity,bool shift,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
+  if(t.np<=t.npb)return 0;
+  if(tkernel==DSPH_KERNEL_WENDLAND)return LaunchNN1<DSPH_KERNEL_WENDLAND>(tvisco,tdensity,shift,t,c,ph,stm);
+  if(tkernel==DSPH_KERNEL_CUBIC)return LaunchNN1<DSPH_KERNEL_CUBIC>(tvisco,tdensity,shift,t,c,ph,stm);
+  return 0;
+}
+
+} // namespace dsph

@@ -61,6 +61,10 @@ __device__ __forceinline__ void ShiftDisp(const float4 rs,const float4 velrhop,d
       else umagn*=(double(rs.w)-c.shifttfs)/coeftfs;
     }
     const float dx=float(double(rs.x)*umagn), dy=float(double(rs.y)*umagn), dz=float(double(rs.z)*umagn);
+    if(c.nn_on){ // the v5.0 multiphase fork clamps one side only (M/JSphShifting.cpp:412-414)
+      sx=double(dx<maxdist? dx: maxdist); sy=double(dy<maxdist? dy: maxdist); sz=double(dz<maxdist? dz: maxdist);
+      return;
+    }
     sx=double(fabsf(dx)<maxdist? dx: (dx>=0? maxdist: -maxdist));
     sy=double(fabsf(dy)<maxdist? dy: (dy>=0? maxdist: -maxdist));
     sz=double(fabsf(dz)<maxdist? dz: (dz>=0? maxdist: -maxdist));

@@ -47,7 +47,7 @@ def _both(gpu_lib, oracle_lib, cd, capacity=0):
     return a, b
 
 
-@pytest.mark.parametrize("kind,n,nsteps", [("dambreak", 60000, 12), ("periodicbox", 27000, 6)])
+@pytest.mark.parametrize("kind,n,nsteps", [("dambreak", 60000, 12), ("periodicbox", 27000, 6), ("nn2layer", 40000, 8)])
 def test_gpu_vs_oracle_steps(gpu_lib, oracle_lib, kind, n, nsteps):
     """Same seeded case, whole steps on both sides: order bit-exact after every divide, forces within tolerance."""
     cd = dsph.make_case(kind, n)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Times the force-kernel variants on a developed dam-break state (device events).  usage: forcebench.py NP PRESTEPS [variants]"""
+"""Times the force-kernel variants on a developed dam-break state (device events).  usage: forcebench.py NP PRESTEPS [variants] [kind] [key=value ...]   (kind: dambreak | nn2layer; e.g. velgrad=2 tvisco=3)"""
 import ctypes as C, sys, os, json
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np
@@ -8,7 +8,12 @@ npart = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
 pre = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1, 2]
 L = dsph.lib(); l = L.lib
-cd = dsph.make_case("dambreak", npart)
+kind = sys.argv[4] if len(sys.argv) > 4 else "dambreak"
+cd = dsph.make_case(kind, npart)
+for kv in sys.argv[5:]:
+    k, v = kv.split("=")
+    k = {"velgrad": "nn_velgrad", "ddt": "tdensity", "shifting": "shiftmode"}.get(k, k)
+    setattr(cd.cfg, k, type(getattr(cd.cfg, k))(float(v)))
 ctx = dsph.create_context(cd)
 ctx.upload(cd.idp, cd.pos, cd.velrhop, cd.npb, cd.codes())
 ctx.celldiv(True)
