@@ -119,6 +119,16 @@ def load_case(dirname: str, casename: str) -> CaseData:
     return _case_from_c(c)
 
 
+def load_part(filename: str):
+    """Reads one PART file (Part_NNNN.bi4 of this driver or of the reference).  Returns (CaseData, timestep, step)."""
+    c = Case()
+    L = lib()
+    t = C.c_double(); st = C.c_uint32()
+    L.lib.dsph_part_load.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
+    L.check(L.lib.dsph_part_load(C.byref(c), filename.encode(), C.byref(t), C.byref(st)))
+    return _case_from_c(c), t.value, st.value
+
+
 def save_case(cd: CaseData, dirname: str, casename: str) -> None:
     c = Case()
     c.cfg = cd.cfg

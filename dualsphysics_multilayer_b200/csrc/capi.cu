@@ -3,6 +3,7 @@
 #include "engine.h"
 #include "host/casefile.h"
 #include "host/driver.h"
+#include "host/bi4.h"
 #include <cstring>
 #include <string>
 #include <new>
@@ -176,6 +177,28 @@ int dsph_case_save(const dsph_case *c,const char *dir,const char *casename){
     // keep the simulation domain exactly as configured
     for(int i=0;i<3;i++){ cd.posmin[i].mode=3; cd.posmin[i].value=c->cfg.maprealposmin[i]; cd.posmax[i].mode=3; cd.posmax[i].value=c->cfg.maprealposmax[i]; }
     SaveCase(cd,dir,casename);
+  });
+  return r==DSPH_OK? r: DSPH_ERR_IO;
+}
+int dsph_part_load(dsph_case *out,const char *file,double *timestep,uint32_t *step){
+  if(!out||!file){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  const int r=Guard([&]{
+    PartHead h; PartData p; LoadPartFile(file,h,p,0);
+    CaseData cd; ConfigDefaults(cd.cfg);
+    cd.cfg.casenp=unsigned(h.casenp); cd.cfg.casenfixed=unsigned(h.casenfixed); cd.cfg.casenmoving=unsigned(h.casenmoving);
+    cd.cfg.casenfloat=unsigned(h.casenfloat); cd.cfg.casenfluid=unsigned(h.casenfluid);
+    cd.cfg.dp=h.dp; cd.cfg.kernelh=float(h.h); cd.cfg.cteb=float(h.b); cd.cfg.rhopzero=float(h.rhop0); cd.cfg.gamma=float(h.gamma);
+    cd.cfg.massbound=float(h.massbound); cd.cfg.massfluid=float(h.massfluid); cd.cfg.simulate2d=(h.data2d? 1: 0);
+    memcpy(cd.caseposmin,h.caseposmin,24); memcpy(cd.caseposmax,h.caseposmax,24);
+    memcpy(cd.cfg.maprealposmin,h.mapposmin,24); memcpy(cd.cfg.maprealposmax,h.mapposmax,24);
+    cd.name=h.casename;
+    cd.idp=p.idp; cd.pos=p.pos; cd.velrhop.resize(size_t(p.npok)*4);
+    for(unsigned i=0;i<p.npok;i++){ cd.velrhop[4*i]=p.vel[3*i]; cd.velrhop[4*i+1]=p.vel[3*i+1]; cd.velrhop[4*i+2]=p.vel[3*i+2]; cd.velrhop[4*i+3]=p.rhop[i]; }
+    CaseToC(cd,out);
+    unsigned nb=0; for(unsigned id:cd.idp)if(id<cd.cfg.casenfixed+cd.cfg.casenmoving)nb++;
+    out->npb=nb;
+    if(timestep)*timestep=p.timestep;
+    if(step)*step=p.step;
   });
   return r==DSPH_OK? r: DSPH_ERR_IO;
 }

@@ -285,6 +285,9 @@ void LoadPartFile(const std::string &file,PartHead &h,PartData &p,unsigned cpart
   h.gamma=root->GetDouble("Gamma"); h.massbound=root->GetDouble("MassBound"); h.massfluid=root->GetDouble("MassFluid");
   char nm[32]; snprintf(nm,sizeof(nm),"PART_%04u",cpart);
   const Bi4Item *part=root->FindItem(nm);
+  if(!part && cpart==0){ // number unknown to the caller: one file holds one PART item (JPartDataBi4::LoadFilePart)
+    for(const auto &it:root->items)if(it->name.compare(0,5,"PART_")==0){ part=it.get(); break; }
+  }
   if(!part)throw std::runtime_error("bi4: PART data is invalid: "+file);
   p.cpart=part->GetUint("Cpart"); p.timestep=part->GetDouble("TimeStep");
   p.npok=part->GetUint("Npok"); p.nout=part->GetUint("Nout",true,0); p.step=part->GetUint("Step",true,0);

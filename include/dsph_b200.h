@@ -251,6 +251,9 @@ int dsph_case_make_slab(dsph_case *out,const char *kind,uint64_t np_target,uint3
 int dsph_case_free(dsph_case *c);
 int dsph_case_save(const dsph_case *c,const char *dir,const char *casename); /* Case.xml + Case.bi4 */
 int dsph_case_load(dsph_case *out,const char *dir,const char *casename);
+/* one PART file (Part_NNNN.bi4 written by this driver or by the reference, JPartDataBi4 S/JPartDataBi4.cpp): particles in
+ * file order (excluded particles are not in it), head constants into cfg; free with dsph_case_free */
+int dsph_part_load(dsph_case *out,const char *file,double *timestep,uint32_t *step);
 
 /* ---- driver: the JSph/JSphGpuSingle::Run work-alike (S/JSphGpuSingle.cpp:808-883): loads
  *      <dir>/<casename>.xml+.bi4, runs to TimeMax (or nsteps>0), writes Part_NNNN.bi4, Run.out, Run.csv
