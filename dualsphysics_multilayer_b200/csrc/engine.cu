@@ -130,7 +130,9 @@ void Engine::Allocate(unsigned capacity){
     if(sps)DevAlloc(spstau[b],size_t(cap)*6);
     DevAlloc(rs.keys[b],cap); DevAlloc(rs.vals[b],cap);
   }
-  DevAlloc(posp,cap); DevAlloc(acear,cap);
+  DevAlloc(posp,size_t(cap)+64);   // padded: the chunked candidate loop of forces_v5.cuh may read a few entries past np
+  CUCHECK(cudaMemsetAsync(posp,0,(size_t(cap)+64)*sizeof(float4),stm));
+  DevAlloc(acear,cap);
   if(cfg.shiftmode)DevAlloc(shiftposfs,cap);
   if(sps)DevAlloc(spsgradvel,size_t(cap)*6);
   const unsigned ntiles=RsTiles(cap);

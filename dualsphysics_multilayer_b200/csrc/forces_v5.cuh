@@ -17,27 +17,43 @@
 
 namespace dsph {
 
-constexpr int V5_CH=8;
+constexpr int V5_CH=8;      // candidates per unrolled chunk (4 was measured: 1.7 % slower at Q=32, 9 % slower at Q=64)
 constexpr unsigned V5_IDXMASK=(1u<<26)-1u;
 
+// Ring slots are addressed with 32-bit shared-window addresses and explicit ld/st.shared: through a generic pointer the
+// compiler rebuilt the shared base (S2R SR_CgaCtaId + 4 integer instructions) for every push and pop (ncu source page).
+constexpr unsigned V5_STRIDE=FORCES_THREADS*4u;    // bytes between consecutive slots of one lane
+// head and tail count in BYTES of the lane's ring (slot k lives at k*V5_STRIDE), so a slot address is one AND + one ADD
+__device__ __forceinline__ void V5Push(unsigned qaddr,unsigned byteoff,unsigned v){
+  asm volatile("st.shared.u32 [%0], %1;" :: "r"(qaddr+byteoff), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned V5Pop(unsigned qaddr,unsigned byteoff){
+  unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(qaddr+byteoff) : "memory"); return v;
+}
+// not movable: keeps the velrhop load next to the posp load instead of behind the ALMOSTZERO branch (two serial latencies)
+__device__ __forceinline__ float4 V5LoadNc(const float4 *p){
+  float4 v; asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x),"=f"(v.y),"=f"(v.z),"=f"(v.w) : "l"(p)); return v;
+}
+
 template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __device__ __forceinline__ void V5Round(
-  unsigned* __restrict__ q,unsigned &head,unsigned tail,const float4 &pp1,const FastP1 &fp,const float* taup1,bool boundp2,
+  unsigned q,unsigned &head,unsigned tail,const float4 &pp1,const FastP1 &fp,const float* taup1,bool boundp2,
   const ForceParams &t,const DevCtes &c,PairAcc &a,unsigned &anyb,unsigned &nosh)
 {
   if(head!=tail){
-    const unsigned e=q[(head&(V5_Q-1))*FORCES_THREADS];
-    head++;
+    const unsigned e=V5Pop(q,head&((V5_Q-1)*V5_STRIDE));
+    head+=V5_STRIDE;
     const unsigned p2=e&V5_IDXMASK;
     const unsigned code=e>>26;
     const float fdx=float(int(code&3u))-1.f, fdy=float(int((code>>2)&3u))-1.f, fdz=float(int(code>>4))-1.f;
     const float ox=pp1.x-fdx*c.scell, oy=pp1.y-fdy*c.scell, oz=pp1.z-fdz*c.scell;
     const float4 pp2=__ldg(&t.posp[p2]);
-    const float4 vr2=__ldg(&t.velrhop[p2]);
+    const float4 vr2=V5LoadNc(t.velrhop+p2);
     const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
     const float rr2=drx*drx+dry*dry+drz*drz;
     unsigned codep2=0; if(SHIFT && boundp2)codep2=t.code[p2];
     const float *taup2=(TVISCO==DSPH_VISCO_LAMINARSPS && !boundp2? t.spstau+6*size_t(p2): nullptr);
-    PairFast<TKER,TVISCO,TDDT,SHIFT>(drx,dry,drz,rr2,fp,vr2,pp2.w,boundp2,taup1,taup2,codep2,c,a,anyb,nosh);
+    // the ALMOSTZERO exclusion (the particle itself, coincident particles) is applied here, not in the candidate test
+    if(rr2>=1e-18f)PairFast<TKER,TVISCO,TDDT,SHIFT>(drx,dry,drz,rr2,fp,vr2,pp2.w,boundp2,taup1,taup2,codep2,c,a,anyb,nosh);
   }
 }
 
@@ -45,7 +61,7 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __global__ void __lau
 ker_forces_fluid_v5(ForceParams t,DevCtes c)
 {
   __shared__ unsigned qsm[V5_Q*FORCES_THREADS];
-  unsigned *q=qsm+threadIdx.x;
+  const unsigned q=unsigned(__cvta_generic_to_shared(qsm))+threadIdx.x*4u;
   const unsigned FULL=0xffffffffu;
   const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
   const unsigned p1c=min(p1,t.np-1);
@@ -62,7 +78,6 @@ ker_forces_fluid_v5(ForceParams t,DevCtes c)
     #pragma unroll
     for(int k=0;k<6;k++)taup1[k]=t.spstau[6*size_t(p1c)+k];
   }
-  const unsigned plast=t.np-1;
   const float ks2=c.kernelsize2, scell=c.scell;
   PairAcc a; ZeroAcc(a);
   unsigned anyb=0,nosh=0,head=0,tail=0;
@@ -91,17 +106,33 @@ ker_forces_fluid_v5(ForceParams t,DevCtes c)
           const unsigned nmax=__reduce_max_sync(FULL,pfin-pini);
           const unsigned codebits=(unsigned(dx+1)|(unsigned(dy+1)<<2)|(unsigned(dz+1)<<4))<<26;
           for(unsigned i=0;i<nmax;i+=V5_CH){
-            while(__any_sync(FULL,(tail-head)>unsigned(V5_Q-V5_CH)))
+            while(__any_sync(FULL,(tail-head)>unsigned(V5_Q-V5_CH)*V5_STRIDE))
               V5Round<TKER,TVISCO,TDDT,SHIFT,V5_Q>(q,head,tail,pp1,fp,taup1,boundp2,t,c,a,anyb,nosh);
-            #pragma unroll
-            for(int u=0;u<V5_CH;u++){
-              const unsigned p2=pini+i+u;
-              const float4 pp2=__ldg(&t.posp[min(p2,plast)]);
-              const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
-              const float rr2=drx*drx+dry*dry+drz*drz;
-              if(p2<pfin && rr2<=ks2 && rr2>=1e-18f){
-                q[(tail&(V5_Q-1))*FORCES_THREADS]=p2|codebits;
-                tail++;
+            // posp is padded (engine.cu): a chunk may read up to V5_CH-1 entries past the range without a clamp
+            const unsigned pb=pini+i;
+            const float4* __restrict__ ppb=t.posp+pb;
+            if(__all_sync(FULL,pb+V5_CH<=pfin)){      // every lane has a full chunk: no per-candidate range check
+              #pragma unroll
+              for(int u=0;u<V5_CH;u++){
+                const float4 pp2=__ldg(ppb+u);
+                const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
+                const float rr2=drx*drx+dry*dry+drz*drz;
+                if(rr2<=ks2){
+                  V5Push(q,tail&((V5_Q-1)*V5_STRIDE),(pb+u)|codebits);
+                  tail+=V5_STRIDE;
+                }
+              }
+            }
+            else{
+              #pragma unroll
+              for(int u=0;u<V5_CH;u++){
+                const float4 pp2=__ldg(ppb+u);
+                const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
+                const float rr2=drx*drx+dry*dry+drz*drz;
+                if(pb+u<pfin && rr2<=ks2){
+                  V5Push(q,tail&((V5_Q-1)*V5_STRIDE),(pb+u)|codebits);
+                  tail+=V5_STRIDE;
+                }
               }
             }
           }
