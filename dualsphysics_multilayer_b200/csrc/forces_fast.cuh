@@ -22,9 +22,13 @@ struct FastP1 { float4 velrhop; float press, ovrhop; };
 // Accumulates one accepted pair.  boundp2 may be a per-lane value (v3) or a literal (v4: constant-folded).
 template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ void PairFast(
   float drx,float dry,float drz,float rr2,const FastP1 &p1,const float4 &velrhop2,float pressp2,bool boundp2,
-  const float* __restrict__ taup1,const float* __restrict__ taup2,unsigned codep2,const DevCtes &c,PairAcc &a,unsigned &anybound,unsigned &noshiftf)
+  const float* __restrict__ taup1,const float* __restrict__ taup2,unsigned codep2,const DevCtes &c,PairAcc &a,unsigned &anybound,unsigned &noshiftf,
+  bool valid=true)
 {
-  const float massp2=(boundp2? c.massbound: c.massfluid);
+  // valid=false (v5: the particle itself or a coincident one, rr2 clamped by the caller): the pair runs with zero mass and sets
+  // no flag, so that every term is exactly 0 and no branch separates the two neighbour loads of the caller
+  const float massp2=(valid? (boundp2? c.massbound: c.massfluid): 0.f);
+  const bool boundflag=(boundp2 && valid);
   const float visco=(boundp2? c.viscobound: c.visco);
   // (a Newton step on the MUFU.RSQ seed was measured: +2 % time, no change of the Ace/Ar difference to the IEEE kernel,
   //  which is set by the fp32 conditioning of the pressure sum, not by the approximations)
@@ -62,8 +66,8 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ voi
   const float ovrr=FastRcp(rr2+c.eta2);
   const float cbar=c.cs0;
   if(TDDT==DSPH_DDT_DDT){
-    if(boundp2)anybound=1u;
-    else{
+    if(boundflag)anybound=1u;
+    if(!boundp2){
       // rho1/rho2-1 cancels to ~1e-4: the oracle's value is dominated by the rounding of the IEEE quotient, so this one
       // division is kept correctly rounded (an approximate reciprocal here changed Ar by 6e-5 in the periodic box).
       const float visc_densi=c.ddtkh*cbar*(__fdiv_rn(rhopp1,velrhop2.w)-1.f)*ovrr;
@@ -72,8 +76,8 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ voi
     }
   }
   if(TDDT==DSPH_DDT_DDT2 || TDDT==DSPH_DDT_DDT2FULL){
-    if(boundp2){ if(TDDT==DSPH_DDT_DDT2)anybound=1u; }
-    else{
+    if(boundflag && TDDT==DSPH_DDT_DDT2)anybound=1u;
+    if(!boundp2){
       const float rh=1.f+c.ddtgz*drz;
       const float drhop=c.rhopzero*(PowNearOne(rh,c)-1.f);   // rho0*(pow-1): the form the reference binary evaluates
       const float visc_densi=c.ddtkh*cbar*((velrhop2.w-rhopp1)-drhop)*ovrr;
@@ -83,7 +87,7 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ voi
   }
   if(SHIFT){
     const float massrhop=massp2*ov2;
-    if(boundp2 && (c.shiftmode==DSPH_SHIFT_NOBOUND || (c.shiftmode==DSPH_SHIFT_NOFIXED && (codep2&DSPH_CODE_MASKTYPE)==DSPH_CODE_TYPE_FIXED)))noshiftf=1u;
+    if(boundflag && (c.shiftmode==DSPH_SHIFT_NOBOUND || (c.shiftmode==DSPH_SHIFT_NOFIXED && (codep2&DSPH_CODE_MASKTYPE)==DSPH_CODE_TYPE_FIXED)))noshiftf=1u;
     a.shift.x+=massrhop*frx; a.shift.y+=massrhop*fry; a.shift.z+=massrhop*frz;
     a.shift.w-=massrhop*(drx*frx+dry*fry+drz*frz);
   }

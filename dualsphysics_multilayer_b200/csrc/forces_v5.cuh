@@ -30,10 +30,6 @@ __device__ __forceinline__ void V5Push(unsigned qaddr,unsigned byteoff,unsigned 
 __device__ __forceinline__ unsigned V5Pop(unsigned qaddr,unsigned byteoff){
   unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(qaddr+byteoff) : "memory"); return v;
 }
-// not movable: keeps the velrhop load next to the posp load instead of behind the ALMOSTZERO branch (two serial latencies)
-__device__ __forceinline__ float4 V5LoadNc(const float4 *p){
-  float4 v; asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x),"=f"(v.y),"=f"(v.z),"=f"(v.w) : "l"(p)); return v;
-}
 
 template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __device__ __forceinline__ void V5Round(
   unsigned q,unsigned &head,unsigned tail,const float4 &pp1,const FastP1 &fp,const float* taup1,bool boundp2,
@@ -47,13 +43,14 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __device__ __forceinl
     const float fdx=float(int(code&3u))-1.f, fdy=float(int((code>>2)&3u))-1.f, fdz=float(int(code>>4))-1.f;
     const float ox=pp1.x-fdx*c.scell, oy=pp1.y-fdy*c.scell, oz=pp1.z-fdz*c.scell;
     const float4 pp2=__ldg(&t.posp[p2]);
-    const float4 vr2=V5LoadNc(t.velrhop+p2);
+    const float4 vr2=__ldg(&t.velrhop[p2]);
     const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
     const float rr2=drx*drx+dry*dry+drz*drz;
     unsigned codep2=0; if(SHIFT && boundp2)codep2=t.code[p2];
     const float *taup2=(TVISCO==DSPH_VISCO_LAMINARSPS && !boundp2? t.spstau+6*size_t(p2): nullptr);
-    // the ALMOSTZERO exclusion (the particle itself, coincident particles) is applied here, not in the candidate test
-    if(rr2>=1e-18f)PairFast<TKER,TVISCO,TDDT,SHIFT>(drx,dry,drz,rr2,fp,vr2,pp2.w,boundp2,taup1,taup2,codep2,c,a,anyb,nosh);
+    // the ALMOSTZERO exclusion (the particle itself, coincident particles) is applied here, not in the candidate test, and
+    // without a branch: such a pair runs with rr2 clamped and zero mass (every contribution is exactly 0, no flag is set)
+    PairFast<TKER,TVISCO,TDDT,SHIFT>(drx,dry,drz,fmaxf(rr2,1e-18f),fp,vr2,pp2.w,boundp2,taup1,taup2,codep2,c,a,anyb,nosh,rr2>=1e-18f);
   }
 }
 
