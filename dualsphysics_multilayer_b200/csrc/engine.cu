@@ -26,6 +26,18 @@ namespace dsph {
 template<class T> static void DevAlloc(T *&p,size_t n){ if(p){ cudaFree(p); p=nullptr; } if(n)CUCHECK(cudaMalloc((void**)&p,n*sizeof(T))); }
 template<class T> static void DevFree(T *&p){ if(p){ cudaFree(p); p=nullptr; } }
 
+// Small host<->device transfers (cell domain, maxima, counters: 4..120 bytes) are done by a one-warp kernel through the
+// mapped pinned block instead of cudaMemcpyAsync: a DMA engine serves its queue in order, so a 4-byte copy of one context
+// would wait behind a 0.9 GB particle upload/download of another context (measured: the end-to-end pipeline of bench.py
+// lost 25 ms per step to that).  The kernel runs on the context's stream like any other kernel.
+__global__ void ker_small_copy(unsigned *dst,const unsigned *src,unsigned nwords){
+  for(unsigned i=threadIdx.x;i<nwords;i+=blockDim.x)dst[i]=src[i];
+  __threadfence_system();
+}
+static void SmallCopy(void *dst,const void *src,size_t bytes,cudaStream_t stm){
+  ker_small_copy<<<1,32,0,stm>>>((unsigned*)dst,(const unsigned*)src,unsigned(bytes/4));
+}
+
 static int KeyBits(unsigned long long maxkey){ int b=1; while((maxkey>>b)!=0)b++; return b; }
 
 Engine::Engine(int device_,const dsph_config &c,unsigned capacity):device(device_)
@@ -36,7 +48,8 @@ Engine::Engine(int device_,const dsph_config &c,unsigned capacity):device(device
   CUCHECK(cudaSetDevice(device));
   CUCHECK(cudaStreamCreateWithFlags(&stm,cudaStreamNonBlocking));
   for(int i=0;i<NEVENTS;i++)CUCHECK(cudaEventCreate(&ev[i]));
-  CUCHECK(cudaMallocHost((void**)&hpin,sizeof(HostPinned)));
+  CUCHECK(cudaHostAlloc((void**)&hpin,sizeof(HostPinned),cudaHostAllocMapped|cudaHostAllocPortable));
+  CUCHECK(cudaHostGetDevicePointer((void**)&hpind,hpin,0));
   memset(hpin,0,sizeof(HostPinned));
   Configure(c);
   Allocate(capacity);
@@ -169,15 +182,25 @@ void Engine::Upload(unsigned np_,unsigned npb_,const unsigned *hidp,const typeco
   CUCHECK(cudaMemcpyAsync(velrhop[cur],hvelrhop,size_t(np)*16,cudaMemcpyHostToDevice,stm));
   if(cfg.tstep==DSPH_STEP_VERLET)CUCHECK(cudaMemcpyAsync(velrhopm1[cur],hvelrhop,size_t(np)*16,cudaMemcpyHostToDevice,stm));
   if(sps)CUCHECK(cudaMemsetAsync(spstau[cur],0,size_t(np)*24,stm));
-  // JSph::LoadDcellParticles (S/JSph.cpp:1690-1711): first cell hash, same double arithmetic, on the device
+  // the upload itself is copies only (pure DMA: it overlaps the kernels of other contexts); the first cell hash runs with
+  // the first consumer of dcell (EnsureDcell)
+  CUCHECK(cudaStreamSynchronize(stm));
+  CUCHECK(cudaGetLastError());
+  dcellpending=true;
+  symplecticdtpre=k.dtini; verletstep=0; forcesok=false;
+}
+
+// JSph::LoadDcellParticles (S/JSph.cpp:1690-1711): first cell hash, same double arithmetic, on the device
+void Engine::EnsureDcell(){
+  if(!dcellpending)return;
+  dcellpending=false;
   CUCHECK(cudaMemsetAsync(limits,0,4,stm));
   if(np){ ker_upload_dcell<<<(np+255)/256,256,0,stm>>>(np,pos[cur],code[cur],dcell[cur],limits,dc,
       k.domrealposmin[0],k.domrealposmin[1],k.domrealposmin[2],k.domrealposmax[0],k.domrealposmax[1],k.domrealposmax[2]); launches++; }
-  CUCHECK(cudaMemcpyAsync(&hpin->scratch[0],limits,4,cudaMemcpyDeviceToHost,stm));
+  SmallCopy(&hpind->scratch[0],limits,4,stm);
   CUCHECK(cudaStreamSynchronize(stm));
   CUCHECK(cudaGetLastError());
   if(hpin->scratch[0])throw EngineError(DSPH_ERR_PHYSICS,"Found new particles out.");
-  symplecticdtpre=k.dtini; verletstep=0; forcesok=false;
 }
 
 void Engine::SetVelrhopM1(const float *h){
@@ -194,6 +217,7 @@ void Engine::SetSpsTau(const float *h){
 
 void Engine::Download(unsigned first,unsigned count,unsigned *hidp,typecode *hcode,unsigned *hdcell,double *hpos,float *hvelrhop){
   if(first+count>np)throw EngineError(DSPH_ERR_ARG,"Range out of particles.");
+  if(hdcell)EnsureDcell();
   if(hidp)CUCHECK(cudaMemcpyAsync(hidp,idp[cur]+first,size_t(count)*4,cudaMemcpyDeviceToHost,stm));
   if(hcode)CUCHECK(cudaMemcpyAsync(hcode,code[cur]+first,size_t(count)*2,cudaMemcpyDeviceToHost,stm));
   if(hdcell)CUCHECK(cudaMemcpyAsync(hdcell,dcell[cur]+first,size_t(count)*4,cudaMemcpyDeviceToHost,stm));
@@ -226,9 +250,9 @@ void Engine::RunPeriodic(){
         unsigned *flags=rs.keys[0];   // scratch: count per particle (0..2), scanned in place
         ker_peri_count<<<(num2+B-1)/B,B,0,stm>>>(pa,flags); launches++;
         // total = last exclusive offset + last count: keep the last count
-        CUCHECK(cudaMemcpyAsync(&hpin->scratch[0],flags+(num2-1),4,cudaMemcpyDeviceToHost,stm));
+        SmallCopy(&hpind->scratch[0],flags+(num2-1),4,stm);
         DeviceExclusiveScan(flags,num2,rs.chunksum,rs.chunksum2,stm,&launches);
-        CUCHECK(cudaMemcpyAsync(&hpin->scratch[1],flags+(num2-1),4,cudaMemcpyDeviceToHost,stm));
+        SmallCopy(&hpind->scratch[1],flags+(num2-1),4,stm);
         CUCHECK(cudaStreamSynchronize(stm));
         const unsigned count=hpin->scratch[0]+hpin->scratch[1];
         if(!count)continue;
@@ -252,6 +276,7 @@ void Engine::RunPeriodic(){
 // ------------------------------------------------------------------------------------------------
 void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
   CUCHECK(cudaSetDevice(device));
+  EnsureDcell();
   const int B=DIV_THREADS;
   CUCHECK(cudaEventRecord(ev[0],stm));
   if(updateperiodic && k.periactive && !mgpu)RunPeriodic();
@@ -263,7 +288,7 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
   {
     unsigned init[12]={0xffffffffu,0xffffffffu,0xffffffffu,0,0,0, 0xffffffffu,0xffffffffu,0xffffffffu,0,0,0};
     memcpy(hpin->limitsinit,init,sizeof(init));
-    CUCHECK(cudaMemcpyAsync(limits,hpin->limitsinit,sizeof(init),cudaMemcpyHostToDevice,stm));
+    SmallCopy(limits,hpind->limitsinit,sizeof(init),stm);
     const int nsm=148*4;
     auto lim=[&](unsigned n,unsigned pini,unsigned *dst){ if(n){ ker_div_limits<<<std::min<unsigned>((n+B-1)/B,nsm),B,0,stm>>>(n,pini,dcell[cur],code[cur],k.domcellcode,dst); launches++; } };
     if(!blimok){ lim(npb1,0,limits); lim(npb2,npb1+npf1,limits); }
@@ -308,7 +333,7 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
   }
   CUCHECK(cudaEventRecord(ev[6],stm));
   // ---- the only device->host transfer of the divide: cell domain + counts (one small async copy + sync)
-  CUCHECK(cudaMemcpyAsync(&hpin->dp,divparams,sizeof(DivParams),cudaMemcpyDeviceToHost,stm));
+  SmallCopy(&hpind->dp,divparams,sizeof(DivParams),stm);
   CUCHECK(cudaEventRecord(ev[7],stm));
   CUCHECK(cudaStreamSynchronize(stm));
   CUCHECK(cudaGetLastError());
@@ -442,7 +467,7 @@ void Engine::ForcesLaunch(int interstep){
 void Engine::ForcesFinish(dsph_forceres *res){
   if(!forceslaunched)throw EngineError(DSPH_ERR_STATE,"dsph_forces_finish needs dsph_forces_launch first.");
   forceslaunched=false;
-  CUCHECK(cudaMemcpyAsync(&hpin->fmax,fmax,sizeof(ForceMax),cudaMemcpyDeviceToHost,stm));
+  SmallCopy(&hpind->fmax,fmax,sizeof(ForceMax),stm);
   CUCHECK(cudaStreamSynchronize(stm));
   CUCHECK(cudaGetLastError());
   { float ms=0; cudaEventElapsedTime(&ms,ev[8],ev[9]); tm.cf_preforces+=ms; cudaEventElapsedTime(&ms,ev[9],ev[10]); tm.cf_forces+=ms; tm.total+=ms; lastforcems=ms;
@@ -496,7 +521,7 @@ void Engine::Pips(unsigned long long *fr,unsigned long long *fc,unsigned long lo
   const ForceParams t=MakeForceParams();
   if(np>npb){ ker_pips<<<(np-npb+FORCES_THREADS-1)/FORCES_THREADS,FORCES_THREADS,0,stm>>>(t,dc,npb,np-npb,1); launches++; }
   if(npbok){ ker_pips<<<(npbok+FORCES_THREADS-1)/FORCES_THREADS,FORCES_THREADS,0,stm>>>(t,dc,0,npbok,0); launches++; }
-  CUCHECK(cudaMemcpyAsync(&hpin->fmax,fmax,sizeof(ForceMax),cudaMemcpyDeviceToHost,stm));
+  SmallCopy(&hpind->fmax,fmax,sizeof(ForceMax),stm);
   CUCHECK(cudaStreamSynchronize(stm));
   if(fr)*fr=hpin->fmax.pips_fluid_real; if(fc)*fc=hpin->fmax.pips_fluid_checked;
   if(br)*br=hpin->fmax.pips_bound_real; if(bc)*bc=hpin->fmax.pips_bound_checked;
@@ -598,6 +623,7 @@ void Engine::MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi){
 }
 void Engine::MgCount(unsigned counts[6]){
   if(!mgpu)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_count needs dsph_mgpu_config with more than one rank.");
+  EnsureDcell();
   const unsigned nb=(np+MG_BLOCK-1)/MG_BLOCK;
   for(int g=0;g<6;g++)mgcounts[g]=counts[g]=0;
   mgcounted=true;
@@ -607,7 +633,7 @@ void Engine::MgCount(unsigned counts[6]){
   // one pass: retire the halo copies of the previous divide (dropped by the next sort), classify, count per block
   ker_mg_classify<<<nb,MG_BLOCK,0,stm>>>(a,(unsigned char*)mgscratch[2],mgscratch[0]); launches++;
   ker_mg_scanblocks<<<6,1024,0,stm>>>(nb,mgscratch[0],mgscratch[1]); launches++;
-  CUCHECK(cudaMemcpyAsync(hpin->mgtot,mgscratch[1],6*sizeof(unsigned),cudaMemcpyDeviceToHost,stm));
+  SmallCopy(hpind->mgtot,mgscratch[1],6*sizeof(unsigned),stm);
   CUCHECK(cudaStreamSynchronize(stm));
   for(int g=0;g<6;g++)mgcounts[g]=counts[g]=hpin->mgtot[g];
 }

@@ -31,7 +31,7 @@ class Engine {
   int device;
   cudaStream_t stm=nullptr;
   cudaEvent_t ev[NEVENTS]={};
-  HostPinned *hpin=nullptr;
+  HostPinned *hpin=nullptr, *hpind=nullptr;   // mapped pinned block: host view and device alias
   dsph_config cfg; SphConst k; DevCtes dc;
   unsigned cap=0, np=0, npb=0, npbok=0, npbper=0, npfper=0;
   // particle arrays (double buffered for the reorder; cur = live buffer)
@@ -65,6 +65,8 @@ class Engine {
   void Allocate(unsigned capacity);
   void FreeAll();
   void Upload(unsigned np,unsigned npb,const unsigned *idp,const typecode *code,const double *pos,const float *velrhop);
+  bool dcellpending=false;   // set by Upload: the first cell hash runs with the first consumer (EnsureDcell)
+  void EnsureDcell();
   void SetVelrhopM1(const float *h);
   void SetSpsTau(const float *h);
   void Download(unsigned first,unsigned count,unsigned *idp,typecode *code,unsigned *dcell,double *pos,float *velrhop);
