@@ -72,14 +72,22 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": self.maxsm or None, "reasons": sorted(self.reasons)}
 
 
-def run_reference(np_sample, nsteps, threads):
-    """Times the reference's own CPU implementation (JSphCpuSingle, OpenMP) on DB(np_sample) for nsteps steps."""
-    if not os.path.exists(REFBIN):
+WORKLOADS = {
+    "dambreak": ("3D dam-break", "synthetic 3D dam-break DB(N) (SURVEY.md 8d): Symplectic + Wendland + artificial viscosity 0.1 + DDT2 0.1, DBC walls"),
+    "periodicbox": ("3D periodic box", "synthetic periodic fluid box PB(N) (SURVEY.md 8d): Taylor-Green field, Symplectic + Wendland + artificial viscosity + DDT1, periodic in x, y, z"),
+    "nn2layer": ("two-layer non-Newtonian dam-break", "synthetic two-layer multiphase dam-break NN(N) (SURVEY.md 8d): FDA velocity gradients, Morris operator, DDT3, shifting"),
+}
+
+
+def run_reference(np_sample, nsteps, threads, kind="dambreak"):
+    """Times the reference's own CPU implementation (JSphCpuSingle, OpenMP) on the workload at np_sample for nsteps steps."""
+    refbin = REFBIN if kind != "nn2layer" else os.path.join(os.path.dirname(REFBIN), "DualSPHysics5.0_NNewtonianCPU_linux64")
+    if not os.path.exists(refbin):
         return None
     tmp = tempfile.mkdtemp(prefix="bench_ref_")
     try:
-        subprocess.check_call([MKCASE, "dambreak", str(np_sample), tmp, "Case"], stdout=subprocess.DEVNULL)
-        r = subprocess.run([REFBIN, "Case", "out", "-cpu", "-ompthreads:%d" % threads, "-sv:none", "-svtimers:1",
+        subprocess.check_call([MKCASE, kind, str(np_sample), tmp, "Case"], stdout=subprocess.DEVNULL)
+        r = subprocess.run([refbin, "Case", "out", "-cpu", "-ompthreads:%d" % threads, "-sv:none", "-svtimers:1",
                             "-nsteps:%d" % nsteps], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         txt = r.stdout
         m1 = re.search(r"Simulation Runtime\.*: ([0-9.eE+-]+) sec", txt)
@@ -95,16 +103,16 @@ def run_reference(np_sample, nsteps, threads):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
-def cpu_baseline(sample_seconds=15.0, steps=3):
+def cpu_baseline(sample_seconds=15.0, steps=3, kind="dambreak"):
     cores = os.cpu_count() or 1
     threads = min(cores, 64)                      # OMP_MAXTHREADS 64, S/OmpDefs.h:39
     np_sample = int(min(20_000_000, max(200_000, 0.05e6 * threads * sample_seconds / steps)))
-    r = run_reference(np_sample, steps, threads)
+    r = run_reference(np_sample, steps, threads, kind)
     if r is None:
         return {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": "oracle/_ref binary unavailable"}
     return {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference",
-            "sample": "reference DualSPHysics5.2 CPU (OpenMP, %d threads): dam-break DB(%d), %d Symplectic steps in %.1f s (CF-Forces %.1f s)"
-                      % (threads, r["np"], r["steps"], r["seconds"], r["cf_forces_s"] or -1)}
+            "sample": "reference DualSPHysics CPU solver (OpenMP, %d threads): %s at %d particles, %d steps in %.1f s (CF-Forces %.1f s)"
+                      % (threads, WORKLOADS[kind][0], r["np"], r["steps"], r["seconds"], r["cf_forces_s"] or -1)}
 
 
 def main():
@@ -118,6 +126,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--force-variant", type=int, default=0)
+    ap.add_argument("--workload", default="dambreak", choices=["dambreak", "periodicbox", "nn2layer"],
+                    help="DB(N) is the headline (BASELINE.json); PB(N) and NN(N) are the other single-GPU configs of SURVEY.md 8(d)")
     ap.add_argument("--profile-mgpu", action="store_true", help="N>1: 3 extra untimed steps with per-phase host timers (adds syncs)")
     ap.add_argument("--bound-weight", type=float, default=0.15, help="N>1: cost of a boundary particle relative to a fluid one when balancing the slabs")
     a = ap.parse_args()
@@ -140,16 +150,16 @@ def main():
         nsteps = max(1, a.steps + a.warmup)
         np_sample = int(min(a.np, max(200_000, 0.05e6 * threads * 60.0 / nsteps)))
         t0 = time.time()
-        r = run_reference(np_sample, nsteps, threads)
+        r = run_reference(np_sample, nsteps, threads, a.workload)
         if r is None:
             emit(({"impl": "reference", "unavailable": "oracle/_ref/DualSPHysics5.2CPU_linux64 is missing (built by oracle/Makefile where /root/reference is mounted)"}))
             return
         sample = ("reference DualSPHysics5.2 CPU solver (OpenMP, %d threads) on dam-break DB(%d) = bounded sample of the %d-particle workload, %d steps, %.1f s"
                   % (threads, r["np"], a.np, r["steps"], r["seconds"]))
-        emit(({"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        emit(({"impl": "reference", "metric": METRIC.replace("3D dam-break", WORKLOADS[a.workload][0]), "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
                           "warmup": a.warmup, "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": "3D dam-break DB(N), Symplectic+Wendland+artificial+DDT2", "np_sample": r["np"], "np_workload": a.np},
+                          "config": {"workload": WORKLOADS[a.workload][1], "np_sample": r["np"], "np_workload": a.np},
                           "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
                           "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "wall_s": time.time() - t0}))
@@ -160,6 +170,8 @@ def main():
     import torch.distributed as dist
     import dualsphysics_multilayer_b200 as dsph
 
+    if world > 1 and a.workload != "dambreak":
+        raise SystemExit("bench.py: the x-slab runs use the dam-break workload")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
@@ -172,7 +184,7 @@ def main():
     from dualsphysics_multilayer_b200 import mgpu
     drv = None
     if world == 1:
-        cd = dsph.make_case("dambreak", a.np)
+        cd = dsph.make_case(a.workload, a.np)
         n = cd.np_
         code = cd.codes()
         ctx = dsph.create_context(cd, device=local)
@@ -250,7 +262,7 @@ def main():
         ctx.celldiv(False)
     fr_real, fr_chk, br_real, br_chk = ctx.pips()
     npf = ctx.np_ - ctx.npb - (0 if drv is None else int(ctx.divinfo.npfper))
-    bytes_per_launch = 58.0 * npf + 16.0 * (fr_chk + fr_real)
+    bytes_per_launch = 58.0 * npf + 16.0 * (fr_chk + fr_real) + (2.0 * fr_real if a.workload == "nn2layer" else 0.0)   # + code[p2]: phase of the neighbour
     k_ms = fms.value / max(1, fnl.value)
     peak, peaksrc = measured_peak()
     achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
@@ -360,10 +372,10 @@ def main():
         drv.prof = None
 
     if rank == 0:
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        out = {"metric": METRIC.replace("3D dam-break", WORKLOADS[a.workload][0]), "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": t_ms.item() / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic",
-               "config": {"workload": "synthetic 3D dam-break DB(N) (SURVEY.md 8d): Symplectic + Wendland + artificial viscosity 0.1 + DDT2 0.1, DBC walls",
+               "config": {"workload": WORKLOADS[a.workload][1],
                           "np_per_gpu": n, "nfluid": int(cd.cfg.casenfluid), "pre_steps": a.pre_steps,
                           "np_global": nglobal,
                           "parallelism": ("single GPU" if world == 1 else "%d x-slabs of balanced work (fluid 1, boundary %g); per divide: NCCL send/recv of migrants + 2h halo copies with <=2 neighbours; per force evaluation: all-reduce(max) of the dt maxima" % (world, a.bound_weight)),
@@ -374,7 +386,7 @@ def main():
         if phases is not None:
             out["mgpu_phases_ms_per_step"] = phases
         if not a.no_cpu_baseline and world == 1:                         # the CPU baseline is reported at N=1 only
-            out["cpu_baseline"] = cpu_baseline()
+            out["cpu_baseline"] = cpu_baseline(kind=a.workload)
         emit(out)
     ctx.close()
     if world > 1:

@@ -442,7 +442,7 @@ void Engine::ForcesLaunch(int interstep){
   const bool shift=(cfg.shiftmode!=0);
   if(npf && cfg.nn_on){
     if(mgpu && cfg.nn_velgrad==DSPH_VELGRAD_SPH)throw EngineError(DSPH_ERR_ARG,"The SPH velocity-gradient approach is not available with x-slab decomposition.");
-    const unsigned nl=LaunchForcesNN(cfg.tkernel,cfg.tvisco,cfg.tdensity,shift,t,dc,dph,stm);
+    const unsigned nl=LaunchForcesNN(forcevariant,cfg.tkernel,cfg.tvisco,cfg.tdensity,shift,t,dc,dph,stm);
     if(!nl)throw EngineError(DSPH_ERR_ARG,"Kernel / viscosity / DDT choice is not valid for the multiphase formulation.");
     launches+=nl;
   }

@@ -16,6 +16,7 @@
 #pragma once
 #include "celldiv.cuh"
 #include "forces.cuh"
+#include "forces_v5.cuh"
 
 namespace dsph {
 
@@ -395,41 +396,279 @@ ker_nn_sph_visco(ForceParams t,DevCtes c,DevPhases ph)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// FDA approach, production kernel: the deferred-ring structure of forces_v5.cuh (candidate test -> per-lane ring in shared
+// memory -> pair rounds at full lane occupancy) with a division-free multiphase pair body.  Same pair order as the plain
+// kernel above (which stays as the IEEE cross-check, variant 1); differs from it only by the rounding of MUFU.RCP/RSQ/EX2.
+// ---------------------------------------------------------------------------------------------------------------------
+struct NNFastP1 { float4 velrhop; float press, ovrhop; unsigned ph; float tau_max, bi_multi, mass; };
+struct NNFastAcc { float ax,ay,az,ar,delta,visc,visceta; float4 shift; };
+
+__device__ __forceinline__ float NNEtaFast(float tau_max1,float bi_multi1,float tau_yield,float dmagn,float visco,float m_nn,float n_nn){
+  const float dm=fmaxf(dmagn,1e-18f);
+  const float ov2d=FastRcp(2.0f*dm);
+  float miou_yield=(tau_max1? tau_max1: tau_yield)*ov2d;
+  bool bi_region=false;
+  if(tau_max1){ bi_region=(dm<=tau_max1*FastRcp(2.f*bi_multi1*visco)); if(bi_region)miou_yield=bi_multi1*visco; }
+  const float miouPap=miou_yield*(1.f-__expf(-m_nn*dm));
+  const bool capped=(miouPap>m_nn*tau_yield || dm==1e-18f);
+  const float term1=(tau_max1? miou_yield: (capped? m_nn*tau_yield: miouPap));
+  const float miouHB=(n_nn==1.0f? visco: visco*__powf(dm,(n_nn-1.0f)));
+  const float term2=(bi_region? visco: (capped? visco: miouHB));
+  return term1+term2;
+}
+
+template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ void NNPairFast(
+  float drx,float dry,float drz,float rr2,const NNFastP1 &p1,const float4 &velrhop2,float pressp2,bool boundp2,unsigned codep2,bool valid,
+  const DevCtes &c,const DevPhases &ph,NNFastAcc &a,unsigned &anybound,unsigned &noshiftf)
+{
+  const unsigned pp2=(boundp2? p1.ph: (codep2&DSPH_CODE_MASKVALUE));
+  const DevPhase &P2=ph.ph[pp2];
+  const float massp2=(valid? (boundp2? c.massbound: P2.mass): 0.f);
+  const bool boundflag=(boundp2 && valid);
+  const float rinv=FastRsqrt(rr2);
+  const float rad=rr2*rinv;
+  const float qq=rad*c.ovkernelh;
+  float fac;
+  if(TKER==DSPH_KERNEL_WENDLAND){ const float wqq1=1.f-0.5f*qq; fac=c.bwen_ovh*(wqq1*wqq1*wqq1); }
+  else{
+    if(rad>c.kernelh){ const float wqq1=2.0f-qq; fac=c.cub_c2*(wqq1*wqq1)*rinv; }
+    else fac=c.cub_c1_ovh+c.cub_d1_ovh*qq;
+  }
+  const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
+  const float rhopp1=p1.velrhop.w;
+  const float ov2=FastRcp(velrhop2.w);
+  {
+    float prs=(p1.press+pressp2)*(p1.ovrhop*ov2);
+    if(TKER==DSPH_KERNEL_CUBIC){
+      float wab;
+      if(rad>c.kernelh){ const float wqq1=2.0f-qq; wab=c.cub_a24*(wqq1*wqq1*wqq1); }
+      else wab=c.cub_a2*(1.0f+(0.75f*qq-1.5f)*(qq*qq));
+      float fab=wab*c.cub_od_wdeltap; fab*=fab; fab*=fab;
+      const float t1=(p1.press*p1.ovrhop*p1.ovrhop)*(p1.press>0? 0.01f: -0.2f);
+      const float t2=(pressp2*ov2*ov2)*(pressp2>0? 0.01f: -0.2f);
+      prs+=fab*(t1+t2);
+    }
+    const float p_vpm=-prs*massp2;
+    a.ax+=p_vpm*frx; a.ay+=p_vpm*fry; a.az+=p_vpm*frz;
+  }
+  float dvx=p1.velrhop.x-velrhop2.x, dvy=p1.velrhop.y-velrhop2.y, dvz=p1.velrhop.z-velrhop2.z;
+  a.ar+=massp2*(dvx*frx+dvy*fry+dvz*frz)*(rhopp1*ov2);
+  const float ovrr=FastRcp(rr2+c.eta2);
+  const float cbar=P2.cs0;
+  const float dot3=(drx*frx+dry*fry+drz*frz);
+  const bool samephase=(p1.ph==pp2);
+  if(TDDT==DSPH_DDT_DDT){
+    if(boundflag)anybound=1u;
+    if(!boundp2 && samephase){
+      const float visc_densi=c.ddtkh*cbar*(__fdiv_rn(rhopp1,velrhop2.w)-1.f)*ovrr;
+      a.delta+=visc_densi*dot3*massp2;
+    }
+  }
+  if(TDDT==DSPH_DDT_DDT2 || TDDT==DSPH_DDT_DDT2FULL){
+    if(boundflag && TDDT==DSPH_DDT_DDT2)anybound=1u;
+    if(!boundp2 && samephase){
+      const float rh=1.f+c.ddtgz*drz;
+      const float drhop=c.rhopzero*(PowNearOne(rh,c)-1.f);
+      const float visc_densi=c.ddtkh*cbar*((velrhop2.w-rhopp1)-drhop)*ovrr;
+      a.delta-=visc_densi*dot3*massp2*ov2;
+    }
+  }
+  if(SHIFT){
+    if(boundflag && (c.shiftmode==DSPH_SHIFT_NOBOUND || (c.shiftmode==DSPH_SHIFT_NOFIXED && (codep2&DSPH_CODE_MASKTYPE)==DSPH_CODE_TYPE_FIXED)))noshiftf=1u;
+    // a heavier particle next to a lighter phase resets the x accumulator and skips the rest (M/JSphCpu_NN_FDA.cpp:244-250)
+    const bool heavyphase=(valid && p1.mass>P2.mass && !samephase);
+    const float massrhop=massp2*ov2;
+    a.shift.x=(heavyphase? 0.f: a.shift.x+massrhop*frx);
+    if(!heavyphase){ a.shift.y+=massrhop*fry; a.shift.z+=massrhop*frz; a.shift.w-=massrhop*dot3; }
+  }
+  {
+    const float dot=drx*dvx+dry*dvy+drz*dvz;
+    const float dot_rr2=dot*ovrr;
+    a.visc=fmaxf(dot_rr2,a.visc);
+    const float visco_NN=P2.visco;
+    if(TVISCO==DSPH_VISCO_ARTIFICIAL){
+      if(dot<0){
+        const float amubar=c.kernelh*dot_rr2;
+        const float ovrobar=FastRcp((rhopp1+velrhop2.w)*0.5f);
+        const float pi_visc=(-visco_NN*cbar*amubar*ovrobar)*massp2;
+        a.ax-=pi_visc*frx; a.ay-=pi_visc*fry; a.az-=pi_visc*frz;
+      }
+    }
+    else{
+      if(boundp2){ dvx=2.f*p1.velrhop.x; dvy=2.f*p1.velrhop.y; dvz=2.f*p1.velrhop.z; }
+      const float ovr2=rinv*rinv;
+      const float sx=drx*ovr2, sy=dry*ovr2, sz=drz*ovr2;
+      const float a11=dvx*sx,a12=dvx*sy,a13=dvx*sz;
+      const float a21=dvy*sx,a22=dvy*sy,a23=dvy*sz;
+      const float a31=dvz*sx,a32=dvz*sy,a33=dvz*sz;
+      const float div_vel=(a11+a22+a33)*(1.f/3.f);
+      const float d11=a11-div_vel, d22=a22-div_vel, d33=a33-div_vel;
+      const float d12=0.5f*(a12+a21), d13=0.5f*(a13+a31), d23=0.5f*(a23+a32);
+      const float II_D=(d11*d22+d22*d33+d11*d33)-(d12*d12+d23*d23+d13*d13);
+      const float dmagn=fabsf(II_D);
+      const float eta=NNEtaFast(p1.tau_max,p1.bi_multi,P2.tau_yield,dmagn,visco_NN,P2.m_nn,P2.n_nn);
+      if(valid)a.visceta=fmaxf(eta,a.visceta);
+      if(TVISCO==DSPH_VISCO_LAMINARSPS){
+        const float temp=2.0f*eta*ovrr*ov2;
+        const float vtemp=massp2*temp*dot3;
+        a.ax+=vtemp*dvx; a.ay+=vtemp*dvy; a.az+=vtemp*dvz;
+      }
+      else{
+        const float t2=2.f*eta*ov2*massp2;
+        a.ax+=t2*(d11*frx+d12*fry+d13*frz);
+        a.ay+=t2*(d12*frx+d22*fry+d23*frz);
+        a.az+=t2*(d13*frx+d23*fry+d33*frz);
+      }
+    }
+  }
+}
+
+template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __device__ __forceinline__ void NNRound(
+  unsigned q,unsigned &head,unsigned tail,const float4 &pp1,const NNFastP1 &fp,bool boundp2,
+  const ForceParams &t,const DevCtes &c,const DevPhases &ph,NNFastAcc &a,unsigned &anyb,unsigned &nosh)
+{
+  if(head!=tail){
+    const unsigned e=V5Pop(q,head&((V5_Q-1)*V5_STRIDE));
+    head+=V5_STRIDE;
+    const unsigned p2=e&V5_IDXMASK;
+    const unsigned code=e>>26;
+    const float fdx=float(int(code&3u))-1.f, fdy=float(int((code>>2)&3u))-1.f, fdz=float(int(code>>4))-1.f;
+    const float ox=pp1.x-fdx*c.scell, oy=pp1.y-fdy*c.scell, oz=pp1.z-fdz*c.scell;
+    const float4 pp2=__ldg(&t.posp[p2]);
+    const float4 vr2=__ldg(&t.velrhop[p2]);
+    unsigned codep2=0; if(!boundp2 || SHIFT)codep2=t.code[p2];
+    const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
+    const float rr2=drx*drx+dry*dry+drz*drz;
+    NNPairFast<TKER,TVISCO,TDDT,SHIFT>(drx,dry,drz,fmaxf(rr2,1e-18f),fp,vr2,pp2.w,boundp2,codep2,rr2>=1e-18f,c,ph,a,anyb,nosh);
+  }
+}
+
+template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __global__ void __launch_bounds__(FORCES_THREADS,6)
+ker_nn_fda_ring(ForceParams t,DevCtes c,DevPhases ph)
+{
+  __shared__ unsigned qsm[V5_Q*FORCES_THREADS];
+  const unsigned q=unsigned(__cvta_generic_to_shared(qsm))+threadIdx.x*4u;
+  const unsigned FULL=0xffffffffu;
+  const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
+  const unsigned p1c=min(p1,t.np-1);
+  const unsigned code1=t.code[p1c];
+  const bool ghost=((code1&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_PERIODIC);
+  const bool active=(p1<t.np && !(t.skipghosts && ghost));
+  const float4 pp1=t.posp[p1c];
+  NNFastP1 fp; fp.velrhop=t.velrhop[p1c]; fp.press=pp1.w; fp.ovrhop=1.f/fp.velrhop.w;
+  fp.ph=code1&DSPH_CODE_MASKVALUE; if(fp.ph>=unsigned(ph.count))fp.ph=0;
+  fp.tau_max=ph.ph[fp.ph].tau_max; fp.bi_multi=ph.ph[fp.ph].bi_multi; fp.mass=ph.ph[fp.ph].mass;
+  const unsigned rcell=t.dcell[p1c];
+  const int cx=int(DcCellx(c.domcellcode,rcell))-int(t.cellzero[0]);
+  const int cy=int(DcCelly(c.domcellcode,rcell))-int(t.cellzero[1]);
+  const int cz=int(DcCellz(c.domcellcode,rcell))-int(t.cellzero[2]);
+  const float ks2=c.kernelsize2, scell=c.scell;
+  NNFastAcc a; a.ax=a.ay=a.az=a.ar=a.delta=a.visc=a.visceta=0; a.shift=make_float4(0,0,0,0);
+  unsigned anyb=0,nosh=0,head=0,tail=0;
+  #pragma unroll 1
+  for(int pass=0;pass<2;pass++){
+    const bool boundp2=(pass==1);
+    const unsigned cellinit=(boundp2? 0u: t.cellfluid);
+    #pragma unroll 1
+    for(int dz=-1;dz<=1;dz++){
+      const int z=cz+dz;
+      const float oz=pp1.z-float(dz)*scell;
+      #pragma unroll 1
+      for(int dy=-1;dy<=1;dy++){
+        const int y=cy+dy;
+        const float oy=pp1.y-float(dy)*scell;
+        const bool rowok=(active && z>=0 && z<t.ncz && y>=0 && y<t.ncy);
+        #pragma unroll 1
+        for(int dx=-1;dx<=1;dx++){
+          const int x=cx+dx;
+          const float ox=pp1.x-float(dx)*scell;
+          unsigned pini=0,pfin=0;
+          if(rowok && x>=0 && x<t.ncx){
+            const unsigned v=unsigned(t.nsheet*z+t.ncx*y+x)+cellinit;
+            pini=t.begincell[v]; pfin=t.begincell[v+1];
+          }
+          const unsigned nmax=__reduce_max_sync(FULL,pfin-pini);
+          const unsigned codebits=(unsigned(dx+1)|(unsigned(dy+1)<<2)|(unsigned(dz+1)<<4))<<26;
+          for(unsigned i=0;i<nmax;i+=V5_CH){
+            while(__any_sync(FULL,(tail-head)>unsigned(V5_Q-V5_CH)*V5_STRIDE))
+              NNRound<TKER,TVISCO,TDDT,SHIFT,V5_Q>(q,head,tail,pp1,fp,boundp2,t,c,ph,a,anyb,nosh);
+            const unsigned pb=pini+i;
+            const float4* __restrict__ ppb=t.posp+pb;
+            #pragma unroll
+            for(int u=0;u<V5_CH;u++){
+              const float4 pp2=__ldg(ppb+u);
+              const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
+              const float rr2=drx*drx+dry*dry+drz*drz;
+              if(pb+u<pfin && rr2<=ks2){
+                V5Push(q,tail&((V5_Q-1)*V5_STRIDE),(pb+u)|codebits);
+                tail+=V5_STRIDE;
+              }
+            }
+          }
+        }
+      }
+    }
+    while(__any_sync(FULL,head!=tail))
+      NNRound<TKER,TVISCO,TDDT,SHIFT,V5_Q>(q,head,tail,pp1,fp,boundp2,t,c,ph,a,anyb,nosh);
+  }
+  float viscmax=0,ace2=0,vel2=0,etamax=0;
+  if(active){
+    float ar=a.ar, ax=a.ax, ay=a.ay, az=a.az;
+    if(c.simulate2d)ay=0;
+    if(TDDT!=DSPH_DDT_NONE && !anyb)ar+=a.delta;
+    t.acear[p1]=make_float4(ax,ay,az,ar);
+    if(SHIFT){ float4 s=a.shift; if(nosh)s.x=FLT_MAX; t.shiftposfs[p1]=s; }
+    viscmax=a.visc; etamax=a.visceta;
+    if(!c.ghosts || !ghost)ace2=ax*ax+ay*ay+az*az;
+  }
+  if(p1<t.np)vel2=fp.velrhop.x*fp.velrhop.x+fp.velrhop.y*fp.velrhop.y+fp.velrhop.z*fp.velrhop.z;
+  WarpMaxToGlobal(viscmax,&t.fmax->viscdt_bits);
+  WarpMaxToGlobal(ace2,&t.fmax->ace2_bits);
+  WarpMaxToGlobal(vel2,&t.fmax->vel2_bits);
+  WarpMaxToGlobal(etamax,&t.fmax->visceta_bits);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // host dispatch
 // ---------------------------------------------------------------------------------------------------------------------
-template<int TKER,int TVISCO,int TDDT,bool SHIFT> static unsigned LaunchNN4(const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
+template<int TKER,int TVISCO,int TDDT,bool SHIFT> static unsigned LaunchNN4(int variant,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
   const unsigned npf=t.np-t.npb, nb=(npf+FORCES_THREADS-1)/FORCES_THREADS;
-  if(ph.velgrad==DSPH_VELGRAD_FDA){ ker_nn_fda<TKER,TVISCO,TDDT,SHIFT><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph); return 1; }
+  if(ph.velgrad==DSPH_VELGRAD_FDA){
+    // variant 1: plain IEEE loop (cross-check); otherwise the ring kernel (needs cells of 2h and np < 2^26 like forces_v5.cuh)
+    if(variant!=1 && c.scelldiv==1 && t.np<=V5_IDXMASK)ker_nn_fda_ring<TKER,TVISCO,TDDT,SHIFT,32><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
+    else ker_nn_fda<TKER,TVISCO,TDDT,SHIFT><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
+    return 1;
+  }
   ker_nn_sph_pressgrad<TKER,TVISCO,TDDT,SHIFT><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
   ker_nn_sph_visco<TKER,TVISCO><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
   return 2;
 }
-template<int TKER,int TVISCO,int TDDT> static unsigned LaunchNN3(bool shift,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
-  return shift? LaunchNN4<TKER,TVISCO,TDDT,true>(t,c,ph,stm): LaunchNN4<TKER,TVISCO,TDDT,false>(t,c,ph,stm);
+template<int TKER,int TVISCO,int TDDT> static unsigned LaunchNN3(int variant,bool shift,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
+  return shift? LaunchNN4<TKER,TVISCO,TDDT,true>(variant,t,c,ph,stm): LaunchNN4<TKER,TVISCO,TDDT,false>(variant,t,c,ph,stm);
 }
-template<int TKER,int TVISCO> static unsigned LaunchNN2(int tddt,bool shift,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
+template<int TKER,int TVISCO> static unsigned LaunchNN2(int variant,int tddt,bool shift,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
   switch(tddt){
-    case DSPH_DDT_NONE:     return LaunchNN3<TKER,TVISCO,DSPH_DDT_NONE>(shift,t,c,ph,stm);
-    case DSPH_DDT_DDT:      return LaunchNN3<TKER,TVISCO,DSPH_DDT_DDT>(shift,t,c,ph,stm);
-    case DSPH_DDT_DDT2:     return LaunchNN3<TKER,TVISCO,DSPH_DDT_DDT2>(shift,t,c,ph,stm);
-    case DSPH_DDT_DDT2FULL: return LaunchNN3<TKER,TVISCO,DSPH_DDT_DDT2FULL>(shift,t,c,ph,stm);
+    case DSPH_DDT_NONE:     return LaunchNN3<TKER,TVISCO,DSPH_DDT_NONE>(variant,shift,t,c,ph,stm);
+    case DSPH_DDT_DDT:      return LaunchNN3<TKER,TVISCO,DSPH_DDT_DDT>(variant,shift,t,c,ph,stm);
+    case DSPH_DDT_DDT2:     return LaunchNN3<TKER,TVISCO,DSPH_DDT_DDT2>(variant,shift,t,c,ph,stm);
+    case DSPH_DDT_DDT2FULL: return LaunchNN3<TKER,TVISCO,DSPH_DDT_DDT2FULL>(variant,shift,t,c,ph,stm);
   }
   return 0;
 }
-template<int TKER> static unsigned LaunchNN1(int tvisco,int tddt,bool shift,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
+template<int TKER> static unsigned LaunchNN1(int variant,int tvisco,int tddt,bool shift,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
   switch(tvisco){
-    case DSPH_VISCO_ARTIFICIAL: return LaunchNN2<TKER,DSPH_VISCO_ARTIFICIAL>(tddt,shift,t,c,ph,stm);
-    case DSPH_VISCO_LAMINARSPS: return LaunchNN2<TKER,DSPH_VISCO_LAMINARSPS>(tddt,shift,t,c,ph,stm);
-    case DSPH_VISCO_CONSTEQ:    return LaunchNN2<TKER,DSPH_VISCO_CONSTEQ>(tddt,shift,t,c,ph,stm);
+    case DSPH_VISCO_ARTIFICIAL: return LaunchNN2<TKER,DSPH_VISCO_ARTIFICIAL>(variant,tddt,shift,t,c,ph,stm);
+    case DSPH_VISCO_LAMINARSPS: return LaunchNN2<TKER,DSPH_VISCO_LAMINARSPS>(variant,tddt,shift,t,c,ph,stm);
+    case DSPH_VISCO_CONSTEQ:    return LaunchNN2<TKER,DSPH_VISCO_CONSTEQ>(variant,tddt,shift,t,c,ph,stm);
   }
   return 0;
 }
 // Interaction of the fluid particles for the multiphase fork (cusphNN::Interaction_ForcesNN, M/JSphGpu_NN_ker.h:31-41).
 // Writes acear (+shiftposfs) for [npb,np) and the four maxima of t.fmax; returns the number of kernels launched.
-static unsigned LaunchForcesNN(int tkernel,int tvisco,int tdensity,bool shift,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
+static unsigned LaunchForcesNN(int variant,int tkernel,int tvisco,int tdensity,bool shift,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
   if(t.np<=t.npb)return 0;
-  if(tkernel==DSPH_KERNEL_WENDLAND)return LaunchNN1<DSPH_KERNEL_WENDLAND>(tvisco,tdensity,shift,t,c,ph,stm);
-  if(tkernel==DSPH_KERNEL_CUBIC)return LaunchNN1<DSPH_KERNEL_CUBIC>(tvisco,tdensity,shift,t,c,ph,stm);
+  if(tkernel==DSPH_KERNEL_WENDLAND)return LaunchNN1<DSPH_KERNEL_WENDLAND>(variant,tvisco,tdensity,shift,t,c,ph,stm);
+  if(tkernel==DSPH_KERNEL_CUBIC)return LaunchNN1<DSPH_KERNEL_CUBIC>(variant,tvisco,tdensity,shift,t,c,ph,stm);
   return 0;
 }
 

@@ -126,6 +126,30 @@ def test_gpu_force_variants_agree(gpu_lib):
         assert rl2(ace, ace1) < 5e-6 and rl2(ar, ar1) < 5e-6 and abs(f1.dt - f.dt) / f1.dt < 1e-6, (v, rl2(ace, ace1), rl2(ar, ar1))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("opts", [dict(), dict(tvisco=3), dict(tvisco=1, tdensity=1, tkernel=1)])
+def test_gpu_nn_ring_kernel_matches_plain_loop(gpu_lib, opts):
+    """Multiphase FDA: the production ring kernel (division-free body) against the plain IEEE loop (variant 1)."""
+    cd = dsph.make_case("nn2layer", 60000)
+    for k, v in opts.items():
+        setattr(cd.cfg, k, v)
+    ctx = dsph.create_context(cd)
+    ctx.upload(cd.idp, cd.pos, cd.velrhop, cd.npb, cd.codes())
+    ctx.celldiv(True)
+    for _ in range(8):
+        ctx.step()
+    res = {}
+    for variant in (1, 6):
+        gpu_lib.lib.dsph_set_force_variant(ctx.h, variant)
+        ctx.celldiv(False)
+        fr = ctx.forces()
+        res[variant] = (ctx.forces_download(), fr)
+    (ace1, ar1), f1 = res[1]; (ace6, ar6), f6 = res[6]
+    npb = ctx.npb
+    assert rl2(ace6[npb:], ace1[npb:]) < 5e-6 and rl2(ar6, ar1) < 5e-6, (rl2(ace6[npb:], ace1[npb:]), rl2(ar6, ar1))
+    assert abs(f1.dt - f6.dt) / f1.dt < 1e-5 and abs(f1.viscetadtmax - f6.viscetadtmax) <= 1e-5 * abs(f1.viscetadtmax)
+
+
 def test_gpu_large_case_properties(gpu_lib):
     """Full-size properties (no CPU oracle at this size): sortedness, permutation, begin-cell consistency, idempotence."""
     cd = dsph.make_case("dambreak", 2_000_000)
