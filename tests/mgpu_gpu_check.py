@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""torchrun --nproc-per-node N tests/mgpu_gpu_check.py [np] [steps]: N x-slabs on N GPUs (NCCL) must reproduce the
+"""torchrun --nproc-per-node N tests/mgpu_gpu_check.py [np] [steps] [kind]: N x-slabs on N GPUs (NCCL) must reproduce the
 single-GPU run: identical particle set, same dt, positions/velocities within single-step tolerance."""
 import os, sys
 import numpy as np
@@ -15,7 +15,8 @@ def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cd = dsph.make_case("dambreak", npart)
+    kind = sys.argv[3] if len(sys.argv) > 3 else "dambreak"     # dambreak | nn2layer (multiphase, FDA)
+    cd = dsph.make_case(kind, npart)
     code = cd.codes()
     ctx = dsph.create_context(cd, np_capacity=cd.np_ + 200000, device=local)
     scell, dmin, dcells = ctx.domain_info()

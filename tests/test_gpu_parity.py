@@ -188,13 +188,14 @@ def test_gpu_large_case_properties(gpu_lib):
     ctx.close()
 
 
-def test_gpu_two_slabs_equal_single_gpu():
+@pytest.mark.parametrize("kind", ["dambreak", "nn2layer"])
+def test_gpu_two_slabs_equal_single_gpu(kind):
     """x-slab decomposition over 2 GPUs (NCCL send/recv halos + all-reduce dt) reproduces the single-GPU run."""
     import subprocess, sys, os, torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29531", os.path.join(root, "tests", "mgpu_gpu_check.py"), "200000", "10"],
+                        "--master-port", "29531", os.path.join(root, "tests", "mgpu_gpu_check.py"), "200000", "10", kind],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert "MGPU_CHECK PASS" in r.stdout, r.stdout[-3000:]
