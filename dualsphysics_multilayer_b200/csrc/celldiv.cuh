@@ -235,10 +235,11 @@ struct ReorderArrays {
   float4 *posp;                                        // out: cell-relative xyz + pressure
 };
 
-__device__ __forceinline__ float PressFromRhop(float rhop,const DevCtes &c){
+__device__ __forceinline__ float PressFromRhop(float rhop,const DevCtes &c,bool tail){
   // same rounding points as the reference CPU build (see oracle/sph_oracle.cpp PreInteraction): float product
-  // rhop*(1/rhop0), then pow, -1 and *B in double, one rounding to float.
-  const float x=__fmul_rn(rhop,c.ovrhopzero);
+  // rhop*(1/rhop0), then pow, -1 and *B in double, one rounding to float.  tail: the last Np-4*((Np-1)/4) particles, for
+  // which the reference binary's scalar loop epilogue keeps the true division (1 ulp = 0.13 Pa at the free surface).
+  const float x=(tail? __fdiv_rn(rhop,c.rhopzero): __fmul_rn(rhop,c.ovrhopzero));
   return float(c.cteb_d*(pow(double(x),c.gamma_d)-1.0));
 }
 
@@ -252,10 +253,13 @@ __device__ __forceinline__ float PressFromRhopNN(float rhop,unsigned rcode,const
   return __fmul_rn(cteb,__fsub_rn(pw,1.0f));
 }
 
-template<bool NN> __global__ void __launch_bounds__(DIV_THREADS) ker_div_reorder(unsigned n,const unsigned* __restrict__ sortpart,ReorderArrays a,DevCtes c,DevPhases ph)
+template<bool NN> __global__ void __launch_bounds__(DIV_THREADS) ker_div_reorder(unsigned n,const unsigned* __restrict__ sortpart,ReorderArrays a,DevCtes c,DevPhases ph,
+  const DivParams* __restrict__ divp)
 {
   const unsigned p=blockIdx.x*blockDim.x+threadIdx.x;
   if(p>=n)return;
+  const unsigned npfin=divp->npfinal;                              // particles that stay after this divide (set by ker_div_counts)
+  const unsigned npfinal_vec=(npfin? ((npfin-1u)/4u)*4u: 0u);      // see PressFromRhop
   const unsigned s=sortpart[p];
   a.idp_out[p]=a.idp_in[s];
   const typecode rcode=a.code_in[s];
@@ -282,7 +286,7 @@ template<bool NN> __global__ void __launch_bounds__(DIV_THREADS) ker_div_reorder
     pp.x=float(px-(c.domposmin[0]+double(cx)*c.scell_d));
     pp.y=float(py-(c.domposmin[1]+double(cy)*c.scell_d));
     pp.z=float(pz-(c.domposmin[2]+double(cz)*c.scell_d));
-    pp.w=(NN? PressFromRhopNN(vr.w,rcode,c,ph): PressFromRhop(vr.w,c));
+    pp.w=(NN? PressFromRhopNN(vr.w,rcode,c,ph): PressFromRhop(vr.w,c,p>=npfinal_vec));
   }
   a.posp[p]=pp;
 }

@@ -326,8 +326,8 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
     if(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre){ a.pospre_in=pospre[cur]; a.pospre_out=pospre[o]; a.velrhoppre_in=velrhoppre[cur]; a.velrhoppre_out=velrhoppre[o]; }
     if(sps){ a.spstau_in=spstau[cur]; a.spstau_out=spstau[o]; }
     a.posp=posp;
-    if(cfg.nn_on)ker_div_reorder<true><<<(nptot+B-1)/B,B,0,stm>>>(nptot,rs.vals[sidx],a,dc,dph);
-    else ker_div_reorder<false><<<(nptot+B-1)/B,B,0,stm>>>(nptot,rs.vals[sidx],a,dc,dph);
+    if(cfg.nn_on)ker_div_reorder<true><<<(nptot+B-1)/B,B,0,stm>>>(nptot,rs.vals[sidx],a,dc,dph,divparams);
+    else ker_div_reorder<false><<<(nptot+B-1)/B,B,0,stm>>>(nptot,rs.vals[sidx],a,dc,dph,divparams);
     launches++;
     cur=o;
   }

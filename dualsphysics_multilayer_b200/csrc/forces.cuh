@@ -106,7 +106,8 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT,bool BOUNDP2> __device__ __forc
   const float cbar=c.cs0;
   if(TDDT==DSPH_DDT_DDT){
     if(a.delta!=FLT_MAX){
-      const float rhop1over2=rhopp1/velrhop2.w;
+      // the reference binary evaluates rho1*(1/rho2) for cubic + laminar/SPS and the true quotient otherwise (oracle/sph_oracle.cpp)
+      const float rhop1over2=(TKER==DSPH_KERNEL_CUBIC && TVISCO==DSPH_VISCO_LAMINARSPS? __fmul_rn(rhopp1,__frcp_rn(velrhop2.w)): __fdiv_rn(rhopp1,velrhop2.w));
       const float visc_densi=c.ddtkh*cbar*(rhop1over2-1.f)/(rr2+c.eta2);
       const float dot3=(drx*frx+dry*fry+drz*frz);
       const float delta=visc_densi*dot3*massp2;

@@ -70,7 +70,9 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ voi
     if(!boundp2){
       // rho1/rho2-1 cancels to ~1e-4: the oracle's value is dominated by the rounding of the IEEE quotient, so this one
       // division is kept correctly rounded (an approximate reciprocal here changed Ar by 6e-5 in the periodic box).
-      const float visc_densi=c.ddtkh*cbar*(__fdiv_rn(rhopp1,velrhop2.w)-1.f)*ovrr;
+      // (cubic + laminar/SPS: the reference binary multiplies by the rounded reciprocal instead, see forces.cuh)
+      const float rhop1over2=(TKER==DSPH_KERNEL_CUBIC && TVISCO==DSPH_VISCO_LAMINARSPS? __fmul_rn(rhopp1,__frcp_rn(velrhop2.w)): __fdiv_rn(rhopp1,velrhop2.w));
+      const float visc_densi=c.ddtkh*cbar*(rhop1over2-1.f)*ovrr;
       const float dot3=(drx*frx+dry*fry+drz*frz);
       a.delta+=visc_densi*dot3*massp2;
     }

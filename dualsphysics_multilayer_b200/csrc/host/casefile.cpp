@@ -305,8 +305,9 @@ static void DamBreakCounts(double dp,double a,unsigned n[6]){
   if(n[3]>n[0]-1)n[3]=n[0]-1;
   if(n[5]>n[2]-1)n[5]=n[2]-1;
 }
-static unsigned long long DamBreakNp(const unsigned n[6]){
+static unsigned long long DamBreakNp(const unsigned n[6],bool twod=false){
   const unsigned long long NX=n[0],NY=n[1],NZ=n[2];
+  if(twod)return (NX+1)+2*NZ+(unsigned long long)n[3]*n[5];   // x-z plane: bed + two side walls + water column
   const unsigned long long bottom=(NX+1)*(NY+1);
   const unsigned long long sides=((NX+1)*(NY+1)-(NX-1)*(NY-1))*NZ;
   return bottom+sides+(unsigned long long)n[3]*n[4]*n[5];
@@ -317,23 +318,26 @@ static unsigned long long DamBreakNp(const unsigned n[6]){
 struct SlabFilter{ bool on=false; unsigned cxlo=0,cxhi=0; };
 static thread_local SlabFilter g_slab;
 
-static void MakeDamBreak(CaseData &cd,unsigned long long nptarget,bool twolayer){
+// twod: the x-z section at y=0 as a 2-D simulation (data2d: h=coefh*sqrt(2)*dp, mass=rho0*dp^2, no walls in y)
+static void MakeDamBreak(CaseData &cd,unsigned long long nptarget,bool twolayer,bool twod=false){
   dsph_config &c=cd.cfg; ConfigDefaults(c);
   const double a=0.4;
   // bisection on dp for the particle count
   double lo=1e-5,hi=0.2; unsigned n[6];
   for(int it=0;it<200;it++){
     const double mid=sqrt(lo*hi); DamBreakCounts(mid,a,n);
-    if(n[0]<4||n[1]<3||n[2]<3){ hi=mid; continue; }
-    if(DamBreakNp(n)>nptarget)lo=mid; else hi=mid;
+    if(n[0]<4||(!twod && n[1]<3)||n[2]<3){ hi=mid; continue; }
+    if(DamBreakNp(n,twod)>nptarget)lo=mid; else hi=mid;
   }
   const double dp=hi; DamBreakCounts(dp,a,n);
-  const unsigned NX=n[0],NY=n[1],NZ=n[2],FX=n[3],FY=n[4],FZ=n[5];
+  const unsigned NX=n[0],NY=(twod? 0u: n[1]),NZ=n[2],FX=n[3],FY=(twod? 0u: n[4]),FZ=n[5];
+  const unsigned JF0=(twod? 0u: 1u);       // first y index of the fluid block (2-D: the single layer j=0)
   const double g=9.81, rho0=1000, gamma=7, coefsound=20, coefh=1.0;
   const double hswl=FZ*dp;
   const double cs0=coefsound*sqrt(g*hswl), B=cs0*cs0*rho0/gamma;
-  c.dp=dp; c.kernelh=float(coefh*sqrt(3.0*dp*dp)); c.cteb=float(B); c.gamma=float(gamma); c.rhopzero=float(rho0);
-  c.massfluid=float(rho0*dp*dp*dp); c.massbound=c.massfluid;
+  c.dp=dp; c.kernelh=float(coefh*sqrt((twod? 2.0: 3.0)*dp*dp)); c.cteb=float(B); c.gamma=float(gamma); c.rhopzero=float(rho0);
+  c.massfluid=float(twod? rho0*dp*dp: rho0*dp*dp*dp); c.massbound=c.massfluid;
+  c.simulate2d=(twod? 1: 0); c.simulate2dposy=0;
   c.gravity[0]=0; c.gravity[1]=0; c.gravity[2]=float(-g);
   c.cflnumber=0.2; c.tstep=DSPH_STEP_SYMPLECTIC; c.tkernel=DSPH_KERNEL_WENDLAND;
   c.tvisco=DSPH_VISCO_ARTIFICIAL; c.visco=0.1f; c.viscoboundfactor=1.f;
@@ -356,20 +360,20 @@ static void MakeDamBreak(CaseData &cd,unsigned long long nptarget,bool twolayer)
     pos.push_back(i*dp); pos.push_back(j*dp); pos.push_back(k*dp); vr.push_back(0); vr.push_back(0); vr.push_back(0); vr.push_back(rho); idp.push_back(id);
   };
   for(unsigned k=0;k<=NZ;k++)for(unsigned j=0;j<=NY;j++)for(unsigned i=0;i<=NX;i++){
-    const bool wall=(k==0||i==0||i==NX||j==0||j==NY);
+    const bool wall=(k==0||i==0||i==NX||(!twod && (j==0||j==NY)));
     if(wall)add(i,j,k,rhohyd(k*dp));
   }
   const unsigned nb=nextid;
   unsigned nf0=0,nf1=0;
   if(!twolayer){
-    for(unsigned k=1;k<=FZ;k++)for(unsigned j=1;j<=FY;j++)for(unsigned i=1;i<=FX;i++)add(i,j,k,rhohyd(k*dp));
+    for(unsigned k=1;k<=FZ;k++)for(unsigned j=JF0;j<=FY;j++)for(unsigned i=1;i<=FX;i++)add(i,j,k,rhohyd(k*dp));
     nf0=nextid-nb;
   }
   else{
     const unsigned kh=FZ/2;
-    for(unsigned k=1;k<=kh;k++)for(unsigned j=1;j<=FY;j++)for(unsigned i=1;i<=FX;i++)add(i,j,k,1500.f);
+    for(unsigned k=1;k<=kh;k++)for(unsigned j=JF0;j<=FY;j++)for(unsigned i=1;i<=FX;i++)add(i,j,k,1500.f);
     nf0=nextid-nb;
-    for(unsigned k=kh+1;k<=FZ;k++)for(unsigned j=1;j<=FY;j++)for(unsigned i=1;i<=FX;i++)add(i,j,k,1000.f);
+    for(unsigned k=kh+1;k<=FZ;k++)for(unsigned j=JF0;j<=FY;j++)for(unsigned i=1;i<=FX;i++)add(i,j,k,1000.f);
     nf1=nextid-nb-nf0;
   }
   const unsigned np=nextid;
@@ -434,8 +438,10 @@ void MakeCase(CaseData &cd,const std::string &kind,unsigned long long nptarget,u
   cd=CaseData();
   if(kind=="dambreak"){ MakeDamBreak(cd,nptarget,false); cd.name="DamBreak"; }
   else if(kind=="nn2layer"){ MakeDamBreak(cd,nptarget,true); cd.name="DamBreakNN"; }
+  else if(kind=="dambreak2d"){ MakeDamBreak(cd,nptarget,false,true); cd.name="DamBreak2D"; }
+  else if(kind=="nn2layer2d"){ MakeDamBreak(cd,nptarget,true,true); cd.name="DamBreakNN2D"; }
   else if(kind=="periodicbox"){ MakePeriodicBox(cd,nptarget,seed); cd.name="PeriodicBox"; }
-  else throw std::runtime_error("Unknown case kind: "+kind+" (dambreak | periodicbox | nn2layer)");
+  else throw std::runtime_error("Unknown case kind: "+kind+" (dambreak | periodicbox | nn2layer | dambreak2d | nn2layer2d)");
 }
 
 } // namespace dsph

@@ -76,8 +76,8 @@ class RefHarness : public JSphCpuSingle {
     w.Add("ace",3,3,Np,Acec); w.Add("ar",3,1,Np,Arc);
     if(ShiftPosfsc)w.Add("shiftposfs",3,4,Np,ShiftPosfsc);
     if(SpsTauc)w.Add("spstau",3,6,Np,SpsTauc);
-#ifdef HARNESS_NN
     if(Pressc)w.Add("press",3,1,Np,Pressc);
+#ifdef HARNESS_NN
     if(Visco_etac)w.Add("visco_eta",3,1,Np,Visco_etac);
     if(SpsGradvelc)w.Add("gradvel",3,6,Np,SpsGradvelc);
     if(D_tensorc)w.Add("d_tensor",3,6,Np,D_tensorc);

@@ -462,7 +462,14 @@ struct Oracle {
     // its -ffast-math build turns rhop/rhop0 into the float product rhop*(1.0f/rhop0) (verified in the disassembly of
     // JSphCpu::PreInteractionVars_Forces, oracle/_ref/obj52/JSphCpu.o).  Both facts are reproduced here.
     const float ovrhopzero=1.0f/RhopZero;
-    if(!MultiPhase)for(unsigned p=0;p<Np;p++)Press[p]=float(double(CteB)*(pow(double(Velrhop[p].w*ovrhopzero),double(Gamma))-1.0));
+    // One more fact of the binary, pinned by the pressure dumps of oracle/ref_harness.cpp: the loop is vectorised 4-wide with a
+    // scalar epilogue ("peeling for gaps" of the strided .w load) that handles the last Np-4*((Np-1)/4) particles, and the
+    // epilogue keeps the true division rhop/rhop0.  One ulp of that quotient is 0.13 Pa, visible in Ace of free-surface particles.
+    const unsigned nvec=(Np? ((Np-1)/4)*4: 0);
+    if(!MultiPhase)for(unsigned p=0;p<Np;p++){
+      const float x=(p<nvec? Velrhop[p].w*ovrhopzero: Velrhop[p].w/RhopZero);
+      Press[p]=float(double(CteB)*(pow(double(x),double(Gamma))-1.0));
+    }
     else{
       // M/JSphCpu.cpp:516-546 (extra arrays) + JSphCpu::ComputePress_NN M/JSphCpu_Tensors.cpp:47-71 (float pow, per-phase EOS)
       if(TVisco!=DSPH_VISCO_ARTIFICIAL)SpsGradvel.assign(Np,sym3{0,0,0,0,0,0}); else SpsGradvel.clear();
@@ -519,7 +526,11 @@ struct Oracle {
             arp1+=massp2*(dvx*frx+dvy*fry+dvz*frz)*(rhopp1/velrhop2.w);
             const float cbar=(float)Cs0;
             if(TDensity==DSPH_DDT_DDT && deltap1!=FLT_MAX){             // Molteni & Colagrossi
-              const float rhop1over2=rhopp1/velrhop2.w;
+              // rho1/rho2-1 cancels to ~1e-4, so one ulp of the quotient is visible in Ar (5e-6 .. 5e-5).  The reference binary
+              // (-ffast-math: reciprocal-math) evaluates rho1*(1/rho2) in exactly one template instantiation family, cubic kernel +
+              // laminar/SPS (3 divisions by rho2 there), and the true quotient in all others: measured on 16 instantiations
+              // (kernel x viscosity x shifting x step algorithm), Ar agrees to 1.5e-7 with the matching form and 5e-6 with the other.
+              const float rhop1over2=(TKernel==DSPH_KERNEL_CUBIC && TVisco==DSPH_VISCO_LAMINARSPS? rhopp1*(1.0f/velrhop2.w): rhopp1/velrhop2.w);
               const float visc_densi=DDTkh*cbar*(rhop1over2-1.f)/(rr2+Eta2);
               const float dot3=(drx*frx+dry*fry+drz*frz);
               const float delta=visc_densi*dot3*massp2;

@@ -42,6 +42,11 @@ CASES = [
     ("nn_sym_sph_conseq_ddt2_shift", "nn2layer", 3000, ["tstep=2", "tkernel=2", "velgrad=2", "tvisco=3", "ddt=2", "shifting=3"], [20], 21),
     ("nn_sym_fda_conseq_cubic", "nn2layer", 3000, ["tstep=2", "tkernel=1", "velgrad=1", "tvisco=3", "ddt=0", "shifting=0"], [20], 21),
     ("nn_sym_fda_art_ddt1", "nn2layer", 3000, ["tstep=2", "tkernel=2", "velgrad=1", "tvisco=1", "ddt=1", "shifting=1"], [20], 21),
+    # 2-D simulations (x-z plane): Simulate2D kernel constants, masses, cell domain with one cell in y, Ace.y = 0
+    ("db2d_sym_wend_art_ddt2_shift", "dambreak2d", 3000, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2", "shifting=3", "shiftcoef=-2", "shifttfs=1.5"], [0, 30], 31),
+    ("db2d_ver_cubic_lamsps_ddt1", "dambreak2d", 3000, ["tstep=1", "tkernel=1", "tvisco=2", "visco=0.01", "ddt=1", "verletsteps=10"], [25], 26),
+    ("nn2d_sym_sph_lam_ddt3_shift", "nn2layer2d", 3000, ["tstep=2", "tkernel=2", "velgrad=2", "tvisco=2", "ddt=3", "shifting=3"], [25], 26),
+    ("nn2d_sym_fda_conseq_ddt2", "nn2layer2d", 3000, ["tstep=2", "tkernel=2", "velgrad=1", "tvisco=3", "ddt=2", "shifting=0"], [25], 26),
 ]
 
 
@@ -49,7 +54,7 @@ def run(name, kind, nptarget, opts, steps, nsteps, outdir):
     tmp = tempfile.mkdtemp(prefix="golden_")
     try:
         subprocess.check_call([MKCASE, kind, str(nptarget), tmp, "Case"] + opts, stdout=subprocess.DEVNULL)
-        cmd = [HARNESS_NN if kind == "nn2layer" else HARNESS, "Case", "out", "-cpu", "-ompthreads:1", "-sv:none", "-hdir:" + os.path.join(tmp, "dump"),
+        cmd = [HARNESS_NN if kind.startswith("nn2layer") else HARNESS, "Case", "out", "-cpu", "-ompthreads:1", "-sv:none", "-hdir:" + os.path.join(tmp, "dump"),
                "-hsteps:" + ",".join(str(s) for s in steps), "-hnsteps:%d" % nsteps]
         cmd += ["-cellmode:half"] if "cellmode=2" in opts else []
         r = subprocess.run(cmd, cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -14,7 +14,8 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 GOLDEN_CASES = ["db_sym_wend_art_ddt2", "db_ver_cubic_art_ddt1_shift", "db_sym_wend_lamsps_ddt3",
                 "db_sym_cubic_art_noddt_half", "pb_sym_wend_art_ddt1", "pb_ver_wend_art_ddt1",
                 "nn_sym_fda_lam_ddt3_shift", "nn_ver_sph_lam_ddt1", "nn_sym_sph_conseq_ddt2_shift", "nn_sym_fda_conseq_cubic",
-                "nn_sym_fda_art_ddt1"]
+                "nn_sym_fda_art_ddt1", "db2d_sym_wend_art_ddt2_shift", "db2d_ver_cubic_lamsps_ddt1", "nn2d_sym_sph_lam_ddt3_shift",
+                "nn2d_sym_fda_conseq_ddt2"]
 GPU_PENDING = []                             # cases the CUDA path does not cover yet
 
 

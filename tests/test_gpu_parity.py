@@ -13,7 +13,10 @@ pytestmark = pytest.mark.gpu
 
 # north_star: cell assignment and sorted order bit-exact; single-step Ace/Ar/dt within 1e-5 relative L2 (fp32)
 TOL = dict(default=2e-5, ace=1e-5, ar=1e-5, dt=1e-5, viscdt=1e-5, acemax=1e-5, velmax=1e-6, pos=1e-8, state=1e-6)
-TOL_PB = dict(TOL, ace=1e-4)      # see tests/test_oracle_vs_reference.py: noise floor of the quiescent periodic box
+# Periodic box: the case starts from exactly uniform density, so in the corrector of step 0 the pressure field is nothing but the
+# float quantisation of rho/rho0 (steps of 0.13 Pa) and Ace is its residue: the production kernel measures 3.7e-5 there (the CPU
+# checker 1.8e-7 by doing the same roundings term by term).  At step 15 of the same case the production kernel is at 4.2e-7.
+TOL_PB = dict(TOL, ace=1e-4)
 
 
 def tol_for(name):

@@ -7,15 +7,16 @@ import pytest
 import parity
 from parity import Golden
 
-# the reference is built with -ffast-math, the checker is not: ~2e-6 of relative L2 is the reference's own noise floor
-TOL = dict(default=2e-5, ace=1e-5, ar=1e-5, dt=1e-6, viscdt=1e-5, acemax=1e-5, velmax=1e-6, pos=1e-8, state=1e-6)
-# periodic box: uniform density, Mach 0.01 -> |ace| ~ 1e-2 m/s^2 is the residue of pressure terms that cancel to ~1e-5
-# of their magnitude, so the fast-math/strict-math difference of the two CPU builds already reaches ~1e-5 relative L2.
-TOL_PB = dict(TOL, ace=1e-4)
+# The reference is built with -O3 -ffast-math, the checker with strict IEEE arithmetic.  Three facts of the reference binary are
+# reproduced by the checker (each pinned by these dumps, see oracle/sph_oracle.cpp): pressure in double from the float product
+# rho*(1/rho0) -- except in the scalar epilogue of the vectorised loop, which divides --, the factored DDT2 term rho0*(pow-1), and
+# the reciprocal form of the DDT1 quotient in the cubic + laminar/SPS instantiations.  With them the measured maxima over all 15
+# cases are Ace 1.5e-6, Ar 4.3e-7, dt 1.5e-8 (before: 1.3e-5 in the periodic box, which was the epilogue artefact, not noise).
+TOL = dict(default=5e-6, ace=5e-6, ar=2e-6, dt=1e-6, viscdt=2e-6, acemax=2e-6, velmax=1e-6, pos=1e-8, state=1e-6)
 
 
 def tol_for(name):
-    return TOL_PB if name.startswith("pb_") else TOL
+    return TOL
 
 
 @pytest.mark.parametrize("name", parity.GOLDEN_CASES)
