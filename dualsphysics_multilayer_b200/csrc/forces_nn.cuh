@@ -629,6 +629,264 @@ ker_nn_fda_ring(ForceParams t,DevCtes c,DevPhases ph)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// SPH approach on the ring structure.  RingTraverse is the skeleton of forces_v5.cuh (cell loops, chunked candidate test,
+// per-lane ring, rounds at full lane occupancy) with the pair body passed in: pair(p2,drx,dry,drz,rr2,pressp2,boundp2,valid).
+// ---------------------------------------------------------------------------------------------------------------------
+template<int V5_Q,class PAIR> __device__ __forceinline__ void RingTraverse(const ForceParams &t,const DevCtes &c,bool active,const float4 &pp1,unsigned rcell,
+  unsigned q,PAIR &&pair)
+{
+  const unsigned FULL=0xffffffffu;
+  const int cx=int(DcCellx(c.domcellcode,rcell))-int(t.cellzero[0]);
+  const int cy=int(DcCelly(c.domcellcode,rcell))-int(t.cellzero[1]);
+  const int cz=int(DcCellz(c.domcellcode,rcell))-int(t.cellzero[2]);
+  const float ks2=c.kernelsize2, scell=c.scell;
+  unsigned head=0,tail=0;
+  auto round=[&](bool boundp2){
+    if(head!=tail){
+      const unsigned e=V5Pop(q,head&((V5_Q-1)*V5_STRIDE));
+      head+=V5_STRIDE;
+      const unsigned p2=e&V5_IDXMASK;
+      const unsigned code=e>>26;
+      const float fdx=float(int(code&3u))-1.f, fdy=float(int((code>>2)&3u))-1.f, fdz=float(int(code>>4))-1.f;
+      const float ox=pp1.x-fdx*scell, oy=pp1.y-fdy*scell, oz=pp1.z-fdz*scell;
+      const float4 pp2=__ldg(&t.posp[p2]);
+      const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
+      const float rr2=drx*drx+dry*dry+drz*drz;
+      pair(p2,drx,dry,drz,fmaxf(rr2,1e-18f),pp2.w,boundp2,rr2>=1e-18f);
+    }
+  };
+  #pragma unroll 1
+  for(int pass=0;pass<2;pass++){
+    const bool boundp2=(pass==1);
+    const unsigned cellinit=(boundp2? 0u: t.cellfluid);
+    #pragma unroll 1
+    for(int dz=-1;dz<=1;dz++){
+      const int z=cz+dz;
+      const float oz=pp1.z-float(dz)*scell;
+      #pragma unroll 1
+      for(int dy=-1;dy<=1;dy++){
+        const int y=cy+dy;
+        const float oy=pp1.y-float(dy)*scell;
+        const bool rowok=(active && z>=0 && z<t.ncz && y>=0 && y<t.ncy);
+        #pragma unroll 1
+        for(int dx=-1;dx<=1;dx++){
+          const int x=cx+dx;
+          const float ox=pp1.x-float(dx)*scell;
+          unsigned pini=0,pfin=0;
+          if(rowok && x>=0 && x<t.ncx){
+            const unsigned v=unsigned(t.nsheet*z+t.ncx*y+x)+cellinit;
+            pini=t.begincell[v]; pfin=t.begincell[v+1];
+          }
+          const unsigned nmax=__reduce_max_sync(FULL,pfin-pini);
+          const unsigned codebits=(unsigned(dx+1)|(unsigned(dy+1)<<2)|(unsigned(dz+1)<<4))<<26;
+          for(unsigned i=0;i<nmax;i+=V5_CH){
+            while(__any_sync(FULL,(tail-head)>unsigned(V5_Q-V5_CH)*V5_STRIDE))round(boundp2);
+            const unsigned pb=pini+i;
+            const float4* __restrict__ ppb=t.posp+pb;
+            #pragma unroll
+            for(int u=0;u<V5_CH;u++){
+              const float4 pp2=__ldg(ppb+u);
+              const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
+              const float rr2=drx*drx+dry*dry+drz*drz;
+              if(pb+u<pfin && rr2<=ks2){
+                V5Push(q,tail&((V5_Q-1)*V5_STRIDE),(pb+u)|codebits);
+                tail+=V5_STRIDE;
+              }
+            }
+          }
+        }
+      }
+    }
+    while(__any_sync(FULL,head!=tail))round(boundp2);
+  }
+}
+
+template<int TKER> __device__ __forceinline__ float NNFacFast(float rr2,const DevCtes &c,float &rinv,float &rad,float &qq){
+  rinv=FastRsqrt(rr2); rad=rr2*rinv; qq=rad*c.ovkernelh;
+  if(TKER==DSPH_KERNEL_WENDLAND){ const float wqq1=1.f-0.5f*qq; return c.bwen_ovh*(wqq1*wqq1*wqq1); }
+  if(rad>c.kernelh){ const float wqq1=2.0f-qq; return c.cub_c2*(wqq1*wqq1)*rinv; }
+  return c.cub_c1_ovh+c.cub_d1_ovh*qq;
+}
+
+// pass 1: pressure, continuity, DDT, shifting, viscdt + symmetric velocity gradient; epilogue: D, eta_eff (+ tau)
+template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __global__ void __launch_bounds__(FORCES_THREADS,6)
+ker_nn_sph_pressgrad_ring(ForceParams t,DevCtes c,DevPhases ph)
+{
+  __shared__ unsigned qsm[V5_Q*FORCES_THREADS];
+  const unsigned q=unsigned(__cvta_generic_to_shared(qsm))+threadIdx.x*4u;
+  const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
+  const unsigned p1c=min(p1,t.np-1);
+  const bool active=(p1<t.np);
+  const unsigned code1=t.code[p1c];
+  const float4 pp1=t.posp[p1c];
+  NNFastP1 fp; fp.velrhop=t.velrhop[p1c]; fp.press=pp1.w; fp.ovrhop=1.f/fp.velrhop.w;
+  fp.ph=code1&DSPH_CODE_MASKVALUE; if(fp.ph>=unsigned(ph.count))fp.ph=0;
+  fp.tau_max=ph.ph[fp.ph].tau_max; fp.bi_multi=ph.ph[fp.ph].bi_multi; fp.mass=ph.ph[fp.ph].mass;
+  NNFastAcc a; a.ax=a.ay=a.az=a.ar=a.delta=a.visc=a.visceta=0; a.shift=make_float4(0,0,0,0);
+  float g0=0,g1=0,g2=0,g3=0,g4=0,g5=0;
+  unsigned anyb=0,nosh=0;
+  RingTraverse<V5_Q>(t,c,active,pp1,t.dcell[p1c],q,[&](unsigned p2,float drx,float dry,float drz,float rr2,float pressp2,bool boundp2,bool valid){
+    const float4 velrhop2=__ldg(&t.velrhop[p2]);
+    unsigned codep2=0; if(!boundp2 || SHIFT)codep2=t.code[p2];
+    const unsigned pp2=(boundp2? fp.ph: (codep2&DSPH_CODE_MASKVALUE));
+    const DevPhase &P2=ph.ph[pp2];
+    const float massp2=(valid? (boundp2? c.massbound: P2.mass): 0.f);
+    const bool boundflag=(boundp2 && valid);
+    float rinv,rad,qq; const float fac=NNFacFast<TKER>(rr2,c,rinv,rad,qq);
+    const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
+    const float rhopp1=fp.velrhop.w;
+    const float ov2=FastRcp(velrhop2.w);
+    {
+      float prs=(fp.press+pressp2)*(fp.ovrhop*ov2);
+      if(TKER==DSPH_KERNEL_CUBIC){
+        float wab;
+        if(rad>c.kernelh){ const float wqq1=2.0f-qq; wab=c.cub_a24*(wqq1*wqq1*wqq1); }
+        else wab=c.cub_a2*(1.0f+(0.75f*qq-1.5f)*(qq*qq));
+        float fab=wab*c.cub_od_wdeltap; fab*=fab; fab*=fab;
+        const float t1=(fp.press*fp.ovrhop*fp.ovrhop)*(fp.press>0? 0.01f: -0.2f);
+        const float t2=(pressp2*ov2*ov2)*(pressp2>0? 0.01f: -0.2f);
+        prs+=fab*(t1+t2);
+      }
+      const float p_vpm=-prs*massp2;
+      a.ax+=p_vpm*frx; a.ay+=p_vpm*fry; a.az+=p_vpm*frz;
+    }
+    float dvx=fp.velrhop.x-velrhop2.x, dvy=fp.velrhop.y-velrhop2.y, dvz=fp.velrhop.z-velrhop2.z;
+    a.ar+=massp2*(dvx*frx+dvy*fry+dvz*frz)*(rhopp1*ov2);
+    const float ovrr=FastRcp(rr2+c.eta2);
+    const float cbar=P2.cs0;
+    const float dot3=(drx*frx+dry*fry+drz*frz);
+    const bool samephase=(fp.ph==pp2);
+    if(TDDT==DSPH_DDT_DDT){
+      if(boundflag)anyb=1u;
+      if(!boundp2 && samephase){
+        const float visc_densi=c.ddtkh*cbar*(__fdiv_rn(rhopp1,velrhop2.w)-1.f)*ovrr;
+        a.delta+=visc_densi*dot3*massp2;
+      }
+    }
+    if(TDDT==DSPH_DDT_DDT2 || TDDT==DSPH_DDT_DDT2FULL){
+      if(boundflag && TDDT==DSPH_DDT_DDT2)anyb=1u;
+      if(!boundp2 && samephase){
+        const float rh=1.f+c.ddtgz*drz;
+        const float drhop=c.rhopzero*(PowNearOne(rh,c)-1.f);
+        const float visc_densi=c.ddtkh*cbar*((velrhop2.w-rhopp1)-drhop)*ovrr;
+        a.delta-=visc_densi*dot3*massp2*ov2;
+      }
+    }
+    if(SHIFT){
+      if(boundflag && (c.shiftmode==DSPH_SHIFT_NOBOUND || (c.shiftmode==DSPH_SHIFT_NOFIXED && (codep2&DSPH_CODE_MASKTYPE)==DSPH_CODE_TYPE_FIXED)))nosh=1u;
+      const bool heavyphase=(valid && fp.mass>P2.mass && !samephase);
+      const float massrhop=massp2*ov2;
+      a.shift.x=(heavyphase? 0.f: a.shift.x+massrhop*frx);
+      if(!heavyphase){ a.shift.y+=massrhop*fry; a.shift.z+=massrhop*frz; a.shift.w-=massrhop*dot3; }
+    }
+    const float dot=drx*dvx+dry*dvy+drz*dvz;
+    a.visc=fmaxf(dot*ovrr,a.visc);
+    if(TVISCO!=DSPH_VISCO_ARTIFICIAL){
+      if(boundp2){ dvx=2.f*fp.velrhop.x; dvy=2.f*fp.velrhop.y; dvz=2.f*fp.velrhop.z; }
+      const float volp2=-massp2*ov2;
+      float dv=dvx*volp2; g0+=dv*frx; g1+=dv*fry; g2+=dv*frz;
+            dv=dvy*volp2; g1+=dv*frx; g3+=dv*fry; g4+=dv*frz;
+            dv=dvz*volp2; g2+=dv*frx; g4+=dv*fry; g5+=dv*frz;
+    }
+  });
+  float viscmax=0,vel2=0,etamax=0;
+  if(active){
+    float ar=a.ar;
+    if(TDDT!=DSPH_DDT_NONE && !anyb)ar+=a.delta;
+    t.acear[p1]=make_float4(a.ax,a.ay,a.az,ar);
+    if(SHIFT){ float4 s=a.shift; if(nosh)s.x=FLT_MAX; t.shiftposfs[p1]=s; }
+    viscmax=a.visc;
+    vel2=fp.velrhop.x*fp.velrhop.x+fp.velrhop.y*fp.velrhop.y+fp.velrhop.z*fp.velrhop.z;
+    if(TVISCO!=DSPH_VISCO_ARTIFICIAL){
+      const float div_vel=(g0+g3+g5)/3.f;
+      const float dxx=g0-div_vel, dxy=0.5f*g1, dxz=0.5f*g2, dyy=g3-div_vel, dyz=0.5f*g4, dzz=g5-div_vel;
+      const float II_D=-(dxx*dyy+dyy*dzz+dxx*dzz)+(dxy*dxy+dyz*dyz+dxz*dxz);
+      const float dmagn=sqrtf(II_D);
+      const DevPhase &P=ph.ph[fp.ph];
+      const float eta=NNEtaEffective(P,P.tau_yield,dmagn,P.visco,P.m_nn,P.n_nn);     // per particle: IEEE version
+      t.viscoeta[p1]=eta; etamax=eta;
+      if(TVISCO==DSPH_VISCO_CONSTEQ){
+        const float t2=2.f*eta; float *tau=t.nntau+6*size_t(p1);
+        tau[0]=t2*dxx; tau[1]=t2*dxy; tau[2]=t2*dxz; tau[3]=t2*dyy; tau[4]=t2*dyz; tau[5]=t2*dzz;
+      }
+    }
+  }
+  WarpMaxToGlobal(viscmax,&t.fmax->viscdt_bits);
+  WarpMaxToGlobal(vel2,&t.fmax->vel2_bits);
+  WarpMaxToGlobal(etamax,&t.fmax->visceta_bits);
+}
+
+// pass 2: viscous forces (artificial / Morris with eta1+eta2 / divergence of tau1+tau2), added to acear
+template<int TKER,int TVISCO,int V5_Q> __global__ void __launch_bounds__(FORCES_THREADS,6)
+ker_nn_sph_visco_ring(ForceParams t,DevCtes c,DevPhases ph)
+{
+  __shared__ unsigned qsm[V5_Q*FORCES_THREADS];
+  const unsigned q=unsigned(__cvta_generic_to_shared(qsm))+threadIdx.x*4u;
+  const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
+  const unsigned p1c=min(p1,t.np-1);
+  const bool active=(p1<t.np);
+  const unsigned code1=t.code[p1c];
+  const float4 pp1=t.posp[p1c];
+  const float4 velrhop1=t.velrhop[p1c];
+  unsigned ph1=code1&DSPH_CODE_MASKVALUE; if(ph1>=unsigned(ph.count))ph1=0;
+  float eta1=0; float tau1[6]={0,0,0,0,0,0};
+  if(TVISCO==DSPH_VISCO_LAMINARSPS)eta1=t.viscoeta[p1c];
+  if(TVISCO==DSPH_VISCO_CONSTEQ){
+    #pragma unroll
+    for(int k=0;k<6;k++)tau1[k]=t.nntau[6*size_t(p1c)+k];
+  }
+  float ax=0,ay=0,az=0;
+  RingTraverse<V5_Q>(t,c,active,pp1,t.dcell[p1c],q,[&](unsigned p2,float drx,float dry,float drz,float rr2,float,bool boundp2,bool valid){
+    const float4 velrhop2=__ldg(&t.velrhop[p2]);
+    const unsigned pp2=(boundp2? ph1: (unsigned(t.code[p2])&DSPH_CODE_MASKVALUE));
+    const DevPhase &P2=ph.ph[pp2];
+    const float massp2=(valid? (boundp2? c.massbound: P2.mass): 0.f);
+    float rinv,rad,qq; const float fac=NNFacFast<TKER>(rr2,c,rinv,rad,qq);
+    const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
+    const float ov2=FastRcp(velrhop2.w);
+    if(TVISCO==DSPH_VISCO_CONSTEQ){
+      float ts[6];
+      #pragma unroll
+      for(int k=0;k<6;k++)ts[k]=tau1[k]+(boundp2? tau1[k]: t.nntau[6*size_t(p2)+k]);
+      const float m2=massp2*ov2;
+      ax+=m2*(ts[0]*frx+ts[1]*fry+ts[2]*frz);
+      ay+=m2*(ts[1]*frx+ts[3]*fry+ts[4]*frz);
+      az+=m2*(ts[2]*frx+ts[4]*fry+ts[5]*frz);
+    }
+    else{
+      float dvx=velrhop1.x-velrhop2.x, dvy=velrhop1.y-velrhop2.y, dvz=velrhop1.z-velrhop2.z;
+      if(boundp2){ dvx=2.f*velrhop1.x; dvy=2.f*velrhop1.y; dvz=2.f*velrhop1.z; }
+      const float ovrr=FastRcp(rr2+c.eta2);
+      if(TVISCO==DSPH_VISCO_ARTIFICIAL){
+        const float dot=drx*dvx+dry*dvy+drz*dvz;
+        if(dot<0){
+          const float amubar=c.kernelh*(dot*ovrr);
+          const float ovrobar=FastRcp((velrhop1.w+velrhop2.w)*0.5f);
+          const float pi_visc=(-P2.visco*P2.cs0*amubar*ovrobar)*massp2;
+          ax-=pi_visc*frx; ay-=pi_visc*fry; az-=pi_visc*frz;
+        }
+      }
+      else{
+        const float eta2=(boundp2? eta1: t.viscoeta[p2]);
+        const float temp=(eta1+eta2)*ovrr*ov2;
+        const float vtemp=massp2*temp*(drx*frx+dry*fry+drz*frz);
+        ax+=vtemp*dvx; ay+=vtemp*dvy; az+=vtemp*dvz;
+      }
+    }
+  });
+  float ace2=0;
+  if(active){
+    float4 acc=t.acear[p1];
+    acc.x+=ax; acc.y+=ay; acc.z+=az;
+    if(c.simulate2d)acc.y=0;
+    t.acear[p1]=acc;
+    const bool ghost=((code1&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_PERIODIC);
+    if(!c.ghosts || !ghost)ace2=acc.x*acc.x+acc.y*acc.y+acc.z*acc.z;
+  }
+  WarpMaxToGlobal(ace2,&t.fmax->ace2_bits);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // host dispatch
 // ---------------------------------------------------------------------------------------------------------------------
 template<int TKER,int TVISCO,int TDDT,bool SHIFT> static unsigned LaunchNN4(int variant,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
@@ -639,8 +897,14 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> static unsigned LaunchNN4(int 
     else ker_nn_fda<TKER,TVISCO,TDDT,SHIFT><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
     return 1;
   }
-  ker_nn_sph_pressgrad<TKER,TVISCO,TDDT,SHIFT><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
-  ker_nn_sph_visco<TKER,TVISCO><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
+  if(variant!=1 && c.scelldiv==1 && t.np<=V5_IDXMASK){
+    ker_nn_sph_pressgrad_ring<TKER,TVISCO,TDDT,SHIFT,32><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
+    ker_nn_sph_visco_ring<TKER,TVISCO,32><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
+  }
+  else{
+    ker_nn_sph_pressgrad<TKER,TVISCO,TDDT,SHIFT><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
+    ker_nn_sph_visco<TKER,TVISCO><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
+  }
   return 2;
 }
 template<int TKER,int TVISCO,int TDDT> static unsigned LaunchNN3(int variant,bool shift,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){

@@ -130,9 +130,10 @@ def test_gpu_force_variants_agree(gpu_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("opts", [dict(), dict(tvisco=3), dict(tvisco=1, tdensity=1, tkernel=1)])
+@pytest.mark.parametrize("opts", [dict(), dict(tvisco=3), dict(tvisco=1, tdensity=1, tkernel=1),
+                                  dict(nn_velgrad=2), dict(nn_velgrad=2, tvisco=3, tkernel=1), dict(nn_velgrad=2, tvisco=1, tdensity=2)])
 def test_gpu_nn_ring_kernel_matches_plain_loop(gpu_lib, opts):
-    """Multiphase FDA: the production ring kernel (division-free body) against the plain IEEE loop (variant 1)."""
+    """Multiphase FDA and SPH approaches: the production ring kernels (division-free body) against the plain IEEE loops (variant 1)."""
     cd = dsph.make_case("nn2layer", 60000)
     for k, v in opts.items():
         setattr(cd.cfg, k, v)
