@@ -129,7 +129,7 @@ def main():
     ap.add_argument("--workload", default="dambreak", choices=["dambreak", "periodicbox", "nn2layer"],
                     help="DB(N) is the headline (BASELINE.json); PB(N) and NN(N) are the other single-GPU configs of SURVEY.md 8(d)")
     ap.add_argument("--profile-mgpu", action="store_true", help="N>1: 3 extra untimed steps with per-phase host timers (adds syncs)")
-    ap.add_argument("--bound-weight", type=float, default=0.15, help="N>1: cost of a boundary particle relative to a fluid one when balancing the slabs")
+    ap.add_argument("--bound-weight", type=float, default=0.05, help="N>1: cost of a boundary particle relative to a fluid one when balancing the slabs")
     a = ap.parse_args()
     # stdout carries exactly ONE line (the JSON): everything else any library prints (e.g. NCCL's
     # version banner) goes to stderr; the JSON is written to the saved descriptor at the end.
