@@ -68,7 +68,9 @@ def test_two_slabs_equal_single_domain(tmp_path, oracle_lib, kind, npart, nsteps
     assert len(idp) == len(st["idp"]) and len(np.unique(idp)) == len(idp), "every particle must be owned by exactly one rank"
     o1 = np.argsort(idp); o2 = np.argsort(st["idp"])
     assert np.array_equal(idp[o1], st["idp"][o2])
-    assert np.abs(pos[o1] - st["pos"][o2]).max() < 1e-9
+    # not bit-identical any more: the reference's scalar-epilogue pressure quotient (oracle/sph_oracle.cpp PreInteraction) applies to
+    # the last <=4 particles of EACH domain, so a slab run differs from the single domain by one ulp of pressure on those particles
+    assert np.abs(pos[o1] - st["pos"][o2]).max() < 1e-7
     den = np.linalg.norm(st["velrhop"][o2].astype(np.float64))
     assert np.linalg.norm((vr[o1] - st["velrhop"][o2]).astype(np.float64)) / den < 1e-6
     assert sum(int(p["sent"]) for p in parts) > 0, "the slabs must have exchanged halo particles"
