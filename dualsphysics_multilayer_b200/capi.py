@@ -145,7 +145,7 @@ class SphLib:
         f("pips", C.c_int, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
         # x-slab multi-GPU
         f("mgpu_config", C.c_int, vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32)
-        f("mgpu_record_bytes", C.c_uint32)
+        f("mgpu_record_bytes", C.c_uint32, vp)
         f("mgpu_count", C.c_int, vp, C.POINTER(C.c_uint32))
         f("mgpu_pack", C.c_int, vp, C.c_void_p, C.c_void_p)
         f("mgpu_unpack", C.c_int, vp, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p)

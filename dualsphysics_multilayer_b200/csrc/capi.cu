@@ -120,7 +120,7 @@ void* dsph_cuda_stream(dsph_ctx *ctx){ return (ctx&&ctx->eng)? (void*)ctx->eng->
 
 // ---- x-slab multi-GPU ----
 int dsph_mgpu_config(dsph_ctx *ctx,int rank,int nranks,uint32_t xlo,uint32_t xhi){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgConfig(rank,nranks,xlo,xhi); }); }
-uint32_t dsph_mgpu_record_bytes(void){ return 88u; }
+uint32_t dsph_mgpu_record_bytes(const dsph_ctx *ctx){ return (ctx && ctx->eng)? ctx->eng->MgRecordBytes(): 88u; }
 int dsph_mgpu_count(dsph_ctx *ctx,uint32_t counts[6]){ NEEDCTX(ctx); return Guard([&]{ unsigned c[6]; ctx->eng->MgCount(c); for(int i=0;i<6;i++)counts[i]=c[i]; }); }
 int dsph_mgpu_pack(dsph_ctx *ctx,void *sl,void *sr){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgPack(sl,sr); }); }
 int dsph_mgpu_unpack(dsph_ctx *ctx,const uint32_t counts[6],const void *rl,const void *rr){ NEEDCTX(ctx); return Guard([&]{ unsigned c[6]; for(int i=0;i<6;i++)c[i]=counts[i]; ctx->eng->MgUnpack(c,rl,rr); }); }

@@ -648,6 +648,7 @@ void Engine::MgPack(void *sendleft,void *sendright){
   MgPackArrays sp; sp.idp=idp[cur]; sp.code=code[cur]; sp.pos=pos[cur]; sp.velrhop=velrhop[cur];
   sp.pospre=(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre? pospre[cur]: nullptr);
   sp.aux=(cfg.tstep==DSPH_STEP_SYMPLECTIC? (haspre? velrhoppre[cur]: nullptr): velrhopm1[cur]);
+  sp.spstau=(sps? spstau[cur]: nullptr); sp.recbytes=MgRecordBytes();
   MgBases bases; unsigned total=0;
   for(int d=0;d<2;d++){
     const unsigned tot=counts[3*d]+counts[3*d+1]+counts[3*d+2];
@@ -656,7 +657,7 @@ void Engine::MgPack(void *sendleft,void *sendright){
     for(int kd=0;kd<3;kd++){ bases.v[3*d+kd]=base; base+=counts[3*d+kd]; }
     total+=tot;
   }
-  if(total){ ker_mg_pack<<<nb,MG_BLOCK,0,stm>>>(a,(const unsigned char*)mgscratch[2],mgscratch[0],bases,sp,(MgRecord*)sendleft,(MgRecord*)sendright); launches++; }
+  if(total){ ker_mg_pack<<<nb,MG_BLOCK,0,stm>>>(a,(const unsigned char*)mgscratch[2],mgscratch[0],bases,sp,(char*)sendleft,(char*)sendright); launches++; }
   CUCHECK(cudaStreamSynchronize(stm));
   CUCHECK(cudaGetLastError());
 }
@@ -668,13 +669,14 @@ void Engine::MgUnpack(const unsigned counts[6],const void *recvleft,const void *
   MgUnpackArrays d; d.idp=idp[cur]; d.code=code[cur]; d.dcell=dcell[cur]; d.pos=pos[cur]; d.velrhop=velrhop[cur];
   d.pospre=(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre? pospre[cur]: nullptr);
   d.aux=(cfg.tstep==DSPH_STEP_SYMPLECTIC? (haspre? velrhoppre[cur]: nullptr): velrhopm1[cur]);
+  d.spstau=(sps? spstau[cur]: nullptr); d.recbytes=MgRecordBytes();
   const int B=256;
   unsigned dst=np;
-  auto up=[&](unsigned n,const MgRecord *src){ if(n){ ker_mg_unpack<<<(n+B-1)/B,B,0,stm>>>(n,src,dst,d,dc); launches++; dst+=n; } };
-  up(bgl,(const MgRecord*)recvleft);
-  up(bgr,(const MgRecord*)recvright);
-  up(fl,(const MgRecord*)recvleft+bgl);
-  up(fr,(const MgRecord*)recvright+bgr);
+  auto up=[&](unsigned n,const char *src){ if(n){ ker_mg_unpack<<<(n+B-1)/B,B,0,stm>>>(n,src,dst,d,dc); launches++; dst+=n; } };
+  up(bgl,(const char*)recvleft);
+  up(bgr,(const char*)recvright);
+  up(fl,(const char*)recvleft+size_t(bgl)*d.recbytes);
+  up(fr,(const char*)recvright+size_t(bgr)*d.recbytes);
   npbper=bgl+bgr; npfper=fl+fr; np+=total;
   boundchanged=true;
   CUCHECK(cudaStreamSynchronize(stm));

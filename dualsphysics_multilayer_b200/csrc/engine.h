@@ -82,6 +82,7 @@ class Engine {
   unsigned *mgscratch[3]={}; unsigned mgcounts[6]={}; bool mgcounted=false;
   bool forceslaunched=false;
   void MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi);
+  unsigned MgRecordBytes()const{ return sps? 112u: 88u; }   // pos 24, velrhop 16, pospre 24, velrhoppre|velrhopm1 16, idp 4, code 4 [+ SpsTau 24]
   void MgCount(unsigned counts[6]);
   void MgPack(void *sendleft,void *sendright);
   void MgUnpack(const unsigned counts[6],const void *recvleft,const void *recvright);

@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(1024) ker_mg_scanblocks(unsigned nb,unsigned* 
 struct MgPackArrays {
   const unsigned *idp; typecode *code; const double *pos; const float4 *velrhop;
   const double *pospre; const float4 *aux;
+  const float *spstau;      // laminar+SPS: 6 floats per particle appended to the record (record = 88 + 24 bytes)
+  unsigned recbytes;        // 88 or 112
 };
 
 struct MgBases { unsigned v[6]; };   // first record slot of each class inside its send buffer
@@ -121,7 +123,7 @@ struct MgBases { unsigned v[6]; };   // first record slot of each class inside i
 // writes the records of all classes; migrants are converted locally: inside the halo band of the
 // neighbour they stay as ghosts (CODE_PERIODIC), otherwise they are dropped by the next sort (CODE_OUTIGNORE)
 __global__ void __launch_bounds__(MG_BLOCK) ker_mg_pack(MgArgs a,const unsigned char* __restrict__ flags,const unsigned* __restrict__ blockoff,
-  MgBases bases,MgPackArrays s,MgRecord* __restrict__ outleft,MgRecord* __restrict__ outright)
+  MgBases bases,MgPackArrays s,char* __restrict__ outleft,char* __restrict__ outright)
 {
   __shared__ unsigned wcnt[6][MG_BLOCK/32];
   const unsigned p=blockIdx.x*MG_BLOCK+threadIdx.x;
@@ -150,7 +152,13 @@ __global__ void __launch_bounds__(MG_BLOCK) ker_mg_pack(MgArgs a,const unsigned 
     for(unsigned i=0;i<w;i++)slot+=wcnt[g][i];
     const int kind=g%3;
     r.code=(kind==1? rc: ((rc&(~DSPH_CODE_MASKSPECIAL))|DSPH_CODE_PERIODIC));   // migrants stay normal, halo copies are ghosts
-    (g<3? outleft: outright)[slot]=r;
+    char *dst=(g<3? outleft: outright)+size_t(slot)*s.recbytes;
+    *reinterpret_cast<MgRecord*>(dst)=r;
+    if(s.spstau){
+      float *tau=reinterpret_cast<float*>(dst+sizeof(MgRecord));
+      #pragma unroll
+      for(int k=0;k<6;k++)tau[k]=s.spstau[6*size_t(p)+k];
+    }
     if(kind==1){ // migrant: local copy becomes a ghost when it is still inside the neighbour's halo band, else it is dropped
       const unsigned cx=DcCellx(a.domcellcode,a.dcell[p]);
       const bool band=(g<3? (cx+a.sd>=a.xlo): (cx<a.xhi+a.sd));
@@ -161,11 +169,18 @@ __global__ void __launch_bounds__(MG_BLOCK) ker_mg_pack(MgArgs a,const unsigned 
 
 struct MgUnpackArrays {
   unsigned *idp; typecode *code; unsigned *dcell; double *pos; float4 *velrhop; double *pospre; float4 *aux;
+  float *spstau; unsigned recbytes;
 };
-__global__ void ker_mg_unpack(unsigned n,const MgRecord* __restrict__ in,unsigned dstbase,MgUnpackArrays d,DevCtes c){
+__global__ void ker_mg_unpack(unsigned n,const char* __restrict__ in,unsigned dstbase,MgUnpackArrays d,DevCtes c){
   const unsigned i=blockIdx.x*blockDim.x+threadIdx.x;
   if(i>=n)return;
-  const MgRecord r=in[i];
+  const char *src=in+size_t(i)*d.recbytes;
+  const MgRecord r=*reinterpret_cast<const MgRecord*>(src);
+  if(d.spstau){
+    const float *tau=reinterpret_cast<const float*>(src+sizeof(MgRecord));
+    #pragma unroll
+    for(int k=0;k<6;k++)d.spstau[6*size_t(dstbase+i)+k]=tau[k];
+  }
   const unsigned p=dstbase+i;
   d.pos[3*size_t(p)]=r.pos[0]; d.pos[3*size_t(p)+1]=r.pos[1]; d.pos[3*size_t(p)+2]=r.pos[2];
   d.velrhop[p]=make_float4(r.velrhop[0],r.velrhop[1],r.velrhop[2],r.velrhop[3]);

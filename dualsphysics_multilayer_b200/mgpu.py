@@ -54,7 +54,7 @@ class SlabDriver:
         self.right = rank + 1 if rank < world - 1 else None
         self.cuts = list(cuts)
         ctx.mgpu_config(rank, world, self.cuts[rank], self.cuts[rank + 1])
-        self.recbytes = int(ctx.lib.fn("mgpu_record_bytes")())
+        self.recbytes = int(ctx.lib.fn("mgpu_record_bytes")(ctx.h))
         self._buf = {}
         ptr = ctx.forces_maxima_ptr()
         if self.device.type == "cuda":

@@ -1179,9 +1179,11 @@ struct Oracle {
     }
     for(int g=0;g<6;g++)counts[g]=MgCounts[g];
   }
+  bool MgSps()const{ return TVisco==DSPH_VISCO_LAMINARSPS && !MultiPhase; }     // SpsTau is particle state: it travels with the record
+  unsigned MgRecordBytes()const{ return unsigned(sizeof(MgRecord))+(MgSps()? 24u: 0u); }
   void MgPack(void *sendleft,void *sendright){
-    MgRecord *out[2]={(MgRecord*)sendleft,(MgRecord*)sendright};
-    const unsigned sd=unsigned(ScellDiv);
+    char *out[2]={(char*)sendleft,(char*)sendright};
+    const unsigned sd=unsigned(ScellDiv), rb=MgRecordBytes();
     for(int d=0;d<2;d++){
       unsigned base=0;
       for(int kd=0;kd<3;kd++){
@@ -1194,7 +1196,10 @@ struct Oracle {
           r.idp=Idp[p];
           const typecode rc=Code[p];
           r.code=(kd==1? rc: typecode(CodeSetNormal(rc)|DSPH_CODE_PERIODIC));
-          out[d][base+n]=r; n++;
+          char *dstp=out[d]+size_t(base+n)*rb;
+          memcpy(dstp,&r,sizeof(r));
+          if(MgSps())memcpy(dstp+sizeof(r),&SpsTau[p],24);
+          n++;
           if(kd==1){
             const unsigned cx=DcCellx(DomCellCode,Dcell[p]);
             const bool band=(d==0? (cx+sd>=MgXlo): (cx<MgXhi+sd));
@@ -1210,9 +1215,11 @@ struct Oracle {
     const unsigned total=bgl+fl+bgr+fr;
     if(Idp.size()<size_t(Np)+total)Resize(Np+total+(Np+total)/20+128);
     unsigned dst=Np;
-    auto up=[&](unsigned n,const MgRecord *src){
+    const unsigned rb=MgRecordBytes();
+    auto up=[&](unsigned n,const char *src){
       for(unsigned i=0;i<n;i++){
-        const MgRecord &r=src[i]; const unsigned p=dst+i;
+        MgRecord r; memcpy(&r,src+size_t(i)*rb,sizeof(r)); const unsigned p=dst+i;
+        if(MgSps())memcpy(&SpsTau[p],src+size_t(i)*rb+sizeof(r),24);
         Pos[p]={r.pos[0],r.pos[1],r.pos[2]}; Velrhop[p]=r.velrhop;
         if(TStep==DSPH_STEP_SYMPLECTIC && HasPre){ PosPre[p]={r.pospre[0],r.pospre[1],r.pospre[2]}; VelrhopPre[p]=r.aux; }
         if(TStep==DSPH_STEP_VERLET)VelrhopM1[p]=r.aux;
@@ -1222,8 +1229,8 @@ struct Oracle {
       }
       dst+=n;
     };
-    up(bgl,(const MgRecord*)recvleft); up(bgr,(const MgRecord*)recvright);
-    up(fl,(const MgRecord*)recvleft+bgl); up(fr,(const MgRecord*)recvright+bgr);
+    up(bgl,(const char*)recvleft); up(bgr,(const char*)recvright);
+    up(fl,(const char*)recvleft+size_t(bgl)*rb); up(fr,(const char*)recvright+size_t(bgr)*rb);
     NpbPer=bgl+bgr; NpfPer=fl+fr; Np+=total; BoundChanged=true;
   }
 };
@@ -1371,7 +1378,7 @@ int orc_mgpu_config(orc_state *s,int rank,int nranks,uint32_t xlo,uint32_t xhi){
     if(nranks<1||rank<0||rank>=nranks||xlo>=xhi||xhi>o.DomCells[0])throw std::runtime_error("Invalid slab configuration.");
     o.Mgpu=(nranks>1); o.MgRank=rank; o.MgNranks=nranks; o.MgXlo=xlo; o.MgXhi=xhi; });
 }
-uint32_t orc_mgpu_record_bytes(void){ static_assert(sizeof(Oracle::MgRecord)==88,"wire format"); return 88u; }
+uint32_t orc_mgpu_record_bytes(const orc_state *s){ static_assert(sizeof(Oracle::MgRecord)==88,"wire format"); return s? s->o.MgRecordBytes(): 88u; }
 int orc_mgpu_count(orc_state *s,uint32_t counts[6]){ return Guard([&]{ unsigned c[6]; s->o.MgCount(c); for(int i=0;i<6;i++)counts[i]=c[i]; }); }
 int orc_mgpu_pack(orc_state *s,void *sl,void *sr){ return Guard([&]{ s->o.MgPack(sl,sr); }); }
 int orc_mgpu_unpack(orc_state *s,const uint32_t counts[6],const void *rl,const void *rr){ return Guard([&]{ unsigned c[6]; for(int i=0;i<6;i++)c[i]=counts[i]; s->o.MgUnpack(c,rl,rr); }); }

@@ -15,8 +15,12 @@ def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    kind = sys.argv[3] if len(sys.argv) > 3 else "dambreak"     # dambreak | nn2layer (multiphase, FDA)
-    cd = dsph.make_case(kind, npart)
+    kind = sys.argv[3] if len(sys.argv) > 3 else "dambreak"     # dambreak | nn2layer (multiphase, FDA) [":key=value,..."]
+    base, _, opts = kind.partition(":")
+    cd = dsph.make_case(base, npart)
+    for kv in filter(None, opts.split(",")):
+        k, v = kv.split("=")
+        setattr(cd.cfg, k, type(getattr(cd.cfg, k))(float(v)))
     code = cd.codes()
     ctx = dsph.create_context(cd, np_capacity=cd.np_ + 200000, device=local)
     scell, dmin, dcells = ctx.domain_info()

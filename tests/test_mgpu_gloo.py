@@ -19,6 +19,17 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
+def _make(kind, npart):
+    """kind may carry options: 'dambreak:tstep=1,shiftmode=3' (Verlet + shifting), 'nn2layer' (multiphase FDA)."""
+    import dualsphysics_multilayer_b200 as dsph
+    base, _, opts = kind.partition(":")
+    cd = dsph.make_case(base, npart)
+    for kv in filter(None, opts.split(",")):
+        k, v = kv.split("=")
+        setattr(cd.cfg, k, type(getattr(cd.cfg, k))(float(v)))
+    return cd
+
+
 def _worker(rank, world, port, kind, npart, nsteps, outdir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -26,7 +37,7 @@ def _worker(rank, world, port, kind, npart, nsteps, outdir):
     from dualsphysics_multilayer_b200 import capi, mgpu
     from dualsphysics_multilayer_b200.capi import SphContext, SphLib
     orc = SphLib(os.path.join(ROOT, "oracle", "liboracle.so"), "orc_")
-    cd = dsph.make_case(kind, npart)
+    cd = _make(kind, npart)
     code = cd.codes()
     ctx = SphContext(orc, cd.cfg)
     scell, dmin, dcells = ctx.domain_info()
@@ -46,14 +57,15 @@ def _worker(rank, world, port, kind, npart, nsteps, outdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind,npart,nsteps", [("dambreak", 6000, 12)])
+@pytest.mark.parametrize("kind,npart,nsteps", [("dambreak", 6000, 12), ("dambreak:tstep=1,verletsteps=5,shiftmode=3,shiftcoef=-2,tvisco=2,visco=0.01", 6000, 12),
+                                               ("nn2layer", 6000, 10)])
 def test_two_slabs_equal_single_domain(tmp_path, oracle_lib, kind, npart, nsteps):
     world = 2
     port = _free_port()
     mp.spawn(_worker, args=(world, port, kind, npart, nsteps, str(tmp_path)), nprocs=world, join=True)
     import dualsphysics_multilayer_b200 as dsph
     from dualsphysics_multilayer_b200.capi import SphContext
-    cd = dsph.make_case(kind, npart)
+    cd = _make(kind, npart)
     ref = SphContext(oracle_lib, cd.cfg)
     ref.upload(cd.idp, cd.pos, cd.velrhop, cd.npb, cd.codes())
     ref.celldiv(True)
