@@ -276,15 +276,24 @@ class SphContext:
         self.lib.check(self.lib.fn("mgpu_config")(self.h, int(rank), int(nranks), int(xlo), int(xhi)))
 
     def mgpu_count(self):
-        c = (C.c_uint32 * 6)()
+        """[left: bound ghosts, bound migrants, fluid migrants, fluid ghosts, right: the same four]"""
+        c = (C.c_uint32 * 8)()
         self.lib.check(self.lib.fn("mgpu_count")(self.h, c))
         return [int(v) for v in c]
+
+    def mgpu_column_counts(self, ncol):
+        """Owned particles per cell column (fluid, boundary): input of the slab re-balancing."""
+        f = np.zeros(ncol, np.uint32); b = np.zeros(ncol, np.uint32)
+        fn = self.lib.fn("mgpu_column_counts")
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32]
+        self.lib.check(fn(self.h, f.ctypes.data_as(C.POINTER(C.c_uint32)), b.ctypes.data_as(C.POINTER(C.c_uint32)), int(ncol)))
+        return f, b
 
     def mgpu_pack(self, ptr_left, ptr_right):
         self.lib.check(self.lib.fn("mgpu_pack")(self.h, ptr_left, ptr_right))
 
     def mgpu_unpack(self, counts, ptr_left, ptr_right):
-        c = (C.c_uint32 * 6)(*[int(v) for v in counts])
+        c = (C.c_uint32 * 8)(*[int(v) for v in counts])
         self.lib.check(self.lib.fn("mgpu_unpack")(self.h, c, ptr_left, ptr_right))
 
     def forces_launch(self, interstep=INTERSTEP_SYMPREDICTOR):

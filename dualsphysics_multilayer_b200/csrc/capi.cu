@@ -121,9 +121,10 @@ void* dsph_cuda_stream(dsph_ctx *ctx){ return (ctx&&ctx->eng)? (void*)ctx->eng->
 // ---- x-slab multi-GPU ----
 int dsph_mgpu_config(dsph_ctx *ctx,int rank,int nranks,uint32_t xlo,uint32_t xhi){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgConfig(rank,nranks,xlo,xhi); }); }
 uint32_t dsph_mgpu_record_bytes(const dsph_ctx *ctx){ return (ctx && ctx->eng)? ctx->eng->MgRecordBytes(): 88u; }
-int dsph_mgpu_count(dsph_ctx *ctx,uint32_t counts[6]){ NEEDCTX(ctx); return Guard([&]{ unsigned c[6]; ctx->eng->MgCount(c); for(int i=0;i<6;i++)counts[i]=c[i]; }); }
+int dsph_mgpu_count(dsph_ctx *ctx,uint32_t counts[8]){ NEEDCTX(ctx); return Guard([&]{ unsigned c[8]; ctx->eng->MgCount(c); for(int i=0;i<8;i++)counts[i]=c[i]; }); }
+int dsph_mgpu_column_counts(dsph_ctx *ctx,uint32_t *fluid,uint32_t *bound,uint32_t ncol){ NEEDCTX(ctx); if(!fluid||!bound){ g_lasterror="Null argument."; return DSPH_ERR_ARG; } return Guard([&]{ ctx->eng->MgColumnCounts(fluid,bound,ncol); }); }
 int dsph_mgpu_pack(dsph_ctx *ctx,void *sl,void *sr){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgPack(sl,sr); }); }
-int dsph_mgpu_unpack(dsph_ctx *ctx,const uint32_t counts[6],const void *rl,const void *rr){ NEEDCTX(ctx); return Guard([&]{ unsigned c[6]; for(int i=0;i<6;i++)c[i]=counts[i]; ctx->eng->MgUnpack(c,rl,rr); }); }
+int dsph_mgpu_unpack(dsph_ctx *ctx,const uint32_t counts[8],const void *rl,const void *rr){ NEEDCTX(ctx); return Guard([&]{ unsigned c[8]; for(int i=0;i<8;i++)c[i]=counts[i]; ctx->eng->MgUnpack(c,rl,rr); }); }
 int dsph_forces_launch(dsph_ctx *ctx,int interstep){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->ForcesLaunch(interstep); }); }
 void* dsph_forces_maxima_ptr(dsph_ctx *ctx){ return (ctx&&ctx->eng)? (void*)ctx->eng->fmax: nullptr; }
 int dsph_forces_finish(dsph_ctx *ctx,dsph_forceres *res){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->ForcesFinish(res); }); }

@@ -614,28 +614,39 @@ void Engine::MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi){
   if(nranks>1 && xhi-xlo<2u*unsigned(k.scelldiv)+1u)throw EngineError(DSPH_ERR_ARG,"The slab is narrower than 2 halo widths + 1 cell.");
   mgpu=(nranks>1); mgrank=rank; mgnranks=nranks; mgxlo=xlo; mgxhi=xhi;
   dc.ghosts=(k.periactive||mgpu)? 1: 0;
-  for(int i=0;i<3;i++)DevFree(mgscratch[i]);
-  if(mgpu){
-    DevAlloc(mgscratch[0],6*(size_t(cap)+MG_BLOCK-1)/MG_BLOCK+8);   // per-block class counts -> offsets
-    DevAlloc(mgscratch[1],size_t(8));                                // class totals
+  if(!mgpu)for(int i=0;i<3;i++)DevFree(mgscratch[i]);
+  else if(!mgscratch[0]){                                            // (re-balancing calls MgConfig again: keep the scratch)
+    DevAlloc(mgscratch[0],MG_CLASSES*((size_t(cap)+MG_BLOCK-1)/MG_BLOCK)+8);   // per-block class counts -> offsets
+    DevAlloc(mgscratch[1],size_t(2*k.domcells[0]+16));               // class totals; column histograms (fluid, boundary)
     DevAlloc(mgscratch[2],size_t(cap)/4+2);                          // one flag byte per particle
   }
 }
-void Engine::MgCount(unsigned counts[6]){
+void Engine::MgColumnCounts(unsigned *fluid,unsigned *bound,unsigned ncol){
+  if(!mgpu)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_column_counts needs dsph_mgpu_config with more than one rank.");
+  if(ncol!=k.domcells[0])throw EngineError(DSPH_ERR_ARG,"ncol must be the number of cell columns of the domain (dsph_domain_info).");
+  EnsureDcell();
+  unsigned *d=mgscratch[1]+16;
+  CUCHECK(cudaMemsetAsync(d,0,size_t(2*ncol)*4,stm));
+  if(np){ ker_mg_column_counts<<<(np+255)/256,256,0,stm>>>(np,dcell[cur],code[cur],k.domcellcode,ncol,d,d+ncol); launches++; }
+  CUCHECK(cudaMemcpyAsync(fluid,d,size_t(ncol)*4,cudaMemcpyDeviceToHost,stm));
+  CUCHECK(cudaMemcpyAsync(bound,d+ncol,size_t(ncol)*4,cudaMemcpyDeviceToHost,stm));
+  CUCHECK(cudaStreamSynchronize(stm));
+}
+void Engine::MgCount(unsigned counts[8]){
   if(!mgpu)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_count needs dsph_mgpu_config with more than one rank.");
   EnsureDcell();
   const unsigned nb=(np+MG_BLOCK-1)/MG_BLOCK;
-  for(int g=0;g<6;g++)mgcounts[g]=counts[g]=0;
+  for(int g=0;g<MG_CLASSES;g++)mgcounts[g]=counts[g]=0;
   mgcounted=true;
   if(!np)return;
   MgArgs a; a.np=np; a.npb=npb; a.xlo=mgxlo; a.xhi=mgxhi; a.sd=unsigned(k.scelldiv);
   a.hasleft=(mgrank>0); a.hasright=(mgrank<mgnranks-1); a.domcellcode=k.domcellcode; a.dcell=dcell[cur]; a.code=code[cur];
   // one pass: retire the halo copies of the previous divide (dropped by the next sort), classify, count per block
   ker_mg_classify<<<nb,MG_BLOCK,0,stm>>>(a,(unsigned char*)mgscratch[2],mgscratch[0]); launches++;
-  ker_mg_scanblocks<<<6,1024,0,stm>>>(nb,mgscratch[0],mgscratch[1]); launches++;
-  SmallCopy(hpind->mgtot,mgscratch[1],6*sizeof(unsigned),stm);
+  ker_mg_scanblocks<<<MG_CLASSES,1024,0,stm>>>(nb,mgscratch[0],mgscratch[1]); launches++;
+  SmallCopy(hpind->mgtot,mgscratch[1],MG_CLASSES*sizeof(unsigned),stm);
   CUCHECK(cudaStreamSynchronize(stm));
-  for(int g=0;g<6;g++)mgcounts[g]=counts[g]=hpin->mgtot[g];
+  for(int g=0;g<MG_CLASSES;g++)mgcounts[g]=counts[g]=hpin->mgtot[g];
 }
 void Engine::MgPack(void *sendleft,void *sendright){
   if(!mgcounted)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_pack needs dsph_mgpu_count first.");
@@ -651,19 +662,19 @@ void Engine::MgPack(void *sendleft,void *sendright){
   sp.spstau=(sps? spstau[cur]: nullptr); sp.recbytes=MgRecordBytes();
   MgBases bases; unsigned total=0;
   for(int d=0;d<2;d++){
-    const unsigned tot=counts[3*d]+counts[3*d+1]+counts[3*d+2];
-    if(tot && !sendbuf[d])throw EngineError(DSPH_ERR_ARG,"Null send buffer.");
     unsigned base=0;
-    for(int kd=0;kd<3;kd++){ bases.v[3*d+kd]=base; base+=counts[3*d+kd]; }
-    total+=tot;
+    for(int kd=0;kd<4;kd++){ bases.v[4*d+kd]=base; base+=counts[4*d+kd]; }
+    if(base && !sendbuf[d])throw EngineError(DSPH_ERR_ARG,"Null send buffer.");
+    total+=base;
   }
   if(total){ ker_mg_pack<<<nb,MG_BLOCK,0,stm>>>(a,(const unsigned char*)mgscratch[2],mgscratch[0],bases,sp,(char*)sendleft,(char*)sendright); launches++; }
   CUCHECK(cudaStreamSynchronize(stm));
   CUCHECK(cudaGetLastError());
 }
-void Engine::MgUnpack(const unsigned counts[6],const void *recvleft,const void *recvright){
+void Engine::MgUnpack(const unsigned counts[8],const void *recvleft,const void *recvright){
   if(!mgpu)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_unpack needs dsph_mgpu_config with more than one rank.");
-  const unsigned bgl=counts[0], fl=counts[1]+counts[2], bgr=counts[3], fr=counts[4]+counts[5];
+  // per side: boundary block (ghosts, migrants) then fluid block (migrants, ghosts)
+  const unsigned bgl=counts[0]+counts[1], fl=counts[2]+counts[3], bgr=counts[4]+counts[5], fr=counts[6]+counts[7];
   const unsigned total=bgl+fl+bgr+fr;
   if(size_t(np)+total>cap)throw EngineError(DSPH_ERR_STATE,"Received particles exceed the capacity of the context.");
   MgUnpackArrays d; d.idp=idp[cur]; d.code=code[cur]; d.dcell=dcell[cur]; d.pos=pos[cur]; d.velrhop=velrhop[cur];

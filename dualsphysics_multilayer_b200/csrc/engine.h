@@ -79,13 +79,14 @@ class Engine {
   void ForcesFinish(dsph_forceres *res);
   // x-slab multi-GPU
   bool mgpu=false; int mgrank=0, mgnranks=1; unsigned mgxlo=0, mgxhi=0;
-  unsigned *mgscratch[3]={}; unsigned mgcounts[6]={}; bool mgcounted=false;
+  unsigned *mgscratch[3]={}; unsigned mgcounts[8]={}; bool mgcounted=false;
   bool forceslaunched=false;
   void MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi);
   unsigned MgRecordBytes()const{ return sps? 112u: 88u; }   // pos 24, velrhop 16, pospre 24, velrhoppre|velrhopm1 16, idp 4, code 4 [+ SpsTau 24]
-  void MgCount(unsigned counts[6]);
+  void MgCount(unsigned counts[8]);
+  void MgColumnCounts(unsigned *fluid,unsigned *bound,unsigned ncol);
   void MgPack(void *sendleft,void *sendright);
-  void MgUnpack(const unsigned counts[6],const void *recvleft,const void *recvright);
+  void MgUnpack(const unsigned counts[8],const void *recvleft,const void *recvright);
   void ForcesDownload(unsigned first,unsigned count,float *ace,float *ar);
   void Pips(unsigned long long *fr,unsigned long long *fc,unsigned long long *br,unsigned long long *bc);
   double DtVariable(double *dt1,double *dt2,double *dt3=nullptr)const;

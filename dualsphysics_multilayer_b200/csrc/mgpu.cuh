@@ -28,9 +28,11 @@ struct MgArgs {
   const unsigned *dcell; typecode *code;
 };
 
-// classes per particle and direction: bit0 send-left, bit1 send-right; kind: 0 bound ghost, 1 fluid migrant, 2 fluid ghost
-__device__ __forceinline__ void MgClassify(unsigned p,const MgArgs &a,int &toleft,int &toright,bool &migl,bool &migr){
-  toleft=toright=-1; migl=migr=false;
+// classes per particle and direction; kind: 0 boundary ghost, 1 boundary migrant (only after the cuts moved: re-balancing),
+// 2 fluid migrant, 3 fluid ghost.  Class g = 4*direction + kind (direction 0 = left neighbour, 1 = right neighbour).
+constexpr int MG_CLASSES=8;
+__device__ __forceinline__ void MgClassify(unsigned p,const MgArgs &a,int &toleft,int &toright){
+  toleft=toright=-1;
   const unsigned rc=a.code[p];
   if((rc&DSPH_CODE_MASKSPECIAL)!=DSPH_CODE_NORMAL)return;
   const unsigned cel=a.dcell[p];
@@ -38,12 +40,12 @@ __device__ __forceinline__ void MgClassify(unsigned p,const MgArgs &a,int &tolef
   const unsigned cx=DcCellx(a.domcellcode,cel);
   const bool fluid=((rc&DSPH_CODE_MASKTYPE)==DSPH_CODE_TYPE_FLUID);
   if(a.hasleft){
-    if(fluid && cx<a.xlo){ toleft=1; migl=true; }
-    else if(cx<a.xlo+a.sd && cx>=a.xlo)toleft=(fluid? 2: 0);
+    if(cx<a.xlo)toleft=(fluid? 2: 1);
+    else if(cx<a.xlo+a.sd)toleft=(fluid? 3: 0);
   }
   if(a.hasright){
-    if(fluid && cx>=a.xhi){ toright=1; migr=true; }
-    else if(cx+a.sd>=a.xhi && cx<a.xhi)toright=(fluid? 2: 0);
+    if(cx>=a.xhi)toright=(fluid? 2: 1);
+    else if(cx+a.sd>=a.xhi)toright=(fluid? 3: 0);
   }
 }
 
@@ -53,32 +55,32 @@ __device__ __forceinline__ void MgClassify(unsigned p,const MgArgs &a,int &tolef
 //  ker_mg_pack        rank inside the block by ballot/popc + block offset -> record slot
 #define MG_BLOCK 256
 __global__ void __launch_bounds__(MG_BLOCK) ker_mg_classify(MgArgs a,unsigned char* __restrict__ flags,unsigned* __restrict__ blockcnt){
-  __shared__ unsigned wcnt[6][MG_BLOCK/32];
+  __shared__ unsigned wcnt[MG_CLASSES][MG_BLOCK/32];
   const unsigned p=blockIdx.x*MG_BLOCK+threadIdx.x;
   unsigned f=0;
   if(p<a.np){
     const unsigned rc=a.code[p];
     if((rc&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_PERIODIC)a.code[p]=typecode((rc&(~DSPH_CODE_MASKSPECIAL))|DSPH_CODE_OUTIGNORE);
-    int tl,tr; bool ml,mr; MgClassify(p,a,tl,tr,ml,mr);
+    int tl,tr; MgClassify(p,a,tl,tr);
     if(tl>=0)f|=1u<<tl;
-    if(tr>=0)f|=1u<<(3+tr);
+    if(tr>=0)f|=1u<<(4+tr);
     flags[p]=(unsigned char)f;
   }
   const unsigned w=threadIdx.x>>5, lane=threadIdx.x&31;
   #pragma unroll
-  for(int g=0;g<6;g++){
+  for(int g=0;g<MG_CLASSES;g++){
     const unsigned bal=__ballot_sync(0xffffffffu,(f>>g)&1u);
     if(lane==0)wcnt[g][w]=__popc(bal);
   }
   __syncthreads();
-  if(threadIdx.x<6){
+  if(threadIdx.x<MG_CLASSES){
     unsigned t=0;
     #pragma unroll
     for(int i=0;i<MG_BLOCK/32;i++)t+=wcnt[threadIdx.x][i];
     blockcnt[size_t(threadIdx.x)*gridDim.x+blockIdx.x]=t;
   }
 }
-// grid = 6 CTAs of 1024 threads: in-place exclusive scan of blockcnt[g*nb .. g*nb+nb), total[g]
+// grid = MG_CLASSES CTAs of 1024 threads: in-place exclusive scan of blockcnt[g*nb .. g*nb+nb), total[g]
 __global__ void __launch_bounds__(1024) ker_mg_scanblocks(unsigned nb,unsigned* __restrict__ blockcnt,unsigned* __restrict__ total){
   __shared__ unsigned wsum[32];
   __shared__ unsigned carry;
@@ -111,6 +113,18 @@ __global__ void __launch_bounds__(1024) ker_mg_scanblocks(unsigned nb,unsigned* 
   if(threadIdx.x==0)total[blockIdx.x]=carry;
 }
 
+// owned (normal) particles per cell column, fluid and boundary separately: input of the slab re-balancing
+__global__ void ker_mg_column_counts(unsigned n,const unsigned* __restrict__ dcell,const typecode* __restrict__ code,unsigned domcellcode,
+  unsigned ncol,unsigned* __restrict__ fluid,unsigned* __restrict__ bound)
+{
+  const unsigned p=blockIdx.x*blockDim.x+threadIdx.x;
+  if(p>=n)return;
+  const unsigned rc=code[p], cel=dcell[p];
+  if((rc&DSPH_CODE_MASKSPECIAL)!=DSPH_CODE_NORMAL || cel==0xFFFFFFFFu)return;
+  const unsigned cx=DcCellx(domcellcode,cel);
+  if(cx<ncol)atomicAdd(((rc&DSPH_CODE_MASKTYPE)==DSPH_CODE_TYPE_FLUID? fluid: bound)+cx,1u);
+}
+
 struct MgPackArrays {
   const unsigned *idp; typecode *code; const double *pos; const float4 *velrhop;
   const double *pospre; const float4 *aux;
@@ -118,20 +132,20 @@ struct MgPackArrays {
   unsigned recbytes;        // 88 or 112
 };
 
-struct MgBases { unsigned v[6]; };   // first record slot of each class inside its send buffer
+struct MgBases { unsigned v[MG_CLASSES]; };   // first record slot of each class inside its send buffer
 
 // writes the records of all classes; migrants are converted locally: inside the halo band of the
 // neighbour they stay as ghosts (CODE_PERIODIC), otherwise they are dropped by the next sort (CODE_OUTIGNORE)
 __global__ void __launch_bounds__(MG_BLOCK) ker_mg_pack(MgArgs a,const unsigned char* __restrict__ flags,const unsigned* __restrict__ blockoff,
   MgBases bases,MgPackArrays s,char* __restrict__ outleft,char* __restrict__ outright)
 {
-  __shared__ unsigned wcnt[6][MG_BLOCK/32];
+  __shared__ unsigned wcnt[MG_CLASSES][MG_BLOCK/32];
   const unsigned p=blockIdx.x*MG_BLOCK+threadIdx.x;
   const unsigned f=(p<a.np? flags[p]: 0u);
   const unsigned w=threadIdx.x>>5, lane=threadIdx.x&31;
-  unsigned rank[6];
+  unsigned rank[MG_CLASSES];
   #pragma unroll
-  for(int g=0;g<6;g++){
+  for(int g=0;g<MG_CLASSES;g++){
     const unsigned bal=__ballot_sync(0xffffffffu,(f>>g)&1u);
     rank[g]=__popc(bal&((1u<<lane)-1u));
     if(lane==0)wcnt[g][w]=__popc(bal);
@@ -147,21 +161,22 @@ __global__ void __launch_bounds__(MG_BLOCK) ker_mg_pack(MgArgs a,const unsigned 
   r.idp=s.idp[p];
   const unsigned rc=s.code[p];
   #pragma unroll
-  for(int g=0;g<6;g++)if((f>>g)&1u){
+  for(int g=0;g<MG_CLASSES;g++)if((f>>g)&1u){
     unsigned slot=bases.v[g]+blockoff[size_t(g)*gridDim.x+blockIdx.x]+rank[g];
     for(unsigned i=0;i<w;i++)slot+=wcnt[g][i];
-    const int kind=g%3;
-    r.code=(kind==1? rc: ((rc&(~DSPH_CODE_MASKSPECIAL))|DSPH_CODE_PERIODIC));   // migrants stay normal, halo copies are ghosts
-    char *dst=(g<3? outleft: outright)+size_t(slot)*s.recbytes;
+    const int kind=g&3;
+    const bool migrant=(kind==1 || kind==2);
+    r.code=(migrant? rc: ((rc&(~DSPH_CODE_MASKSPECIAL))|DSPH_CODE_PERIODIC));   // migrants stay normal, halo copies are ghosts
+    char *dst=(g<4? outleft: outright)+size_t(slot)*s.recbytes;
     *reinterpret_cast<MgRecord*>(dst)=r;
     if(s.spstau){
       float *tau=reinterpret_cast<float*>(dst+sizeof(MgRecord));
       #pragma unroll
       for(int k=0;k<6;k++)tau[k]=s.spstau[6*size_t(p)+k];
     }
-    if(kind==1){ // migrant: local copy becomes a ghost when it is still inside the neighbour's halo band, else it is dropped
+    if(migrant){ // local copy becomes a ghost when it is still inside the neighbour's halo band, else it is dropped
       const unsigned cx=DcCellx(a.domcellcode,a.dcell[p]);
-      const bool band=(g<3? (cx+a.sd>=a.xlo): (cx<a.xhi+a.sd));
+      const bool band=(g<4? (cx+a.sd>=a.xlo): (cx<a.xhi+a.sd));
       s.code[p]=typecode((rc&(~DSPH_CODE_MASKSPECIAL))|(band? DSPH_CODE_PERIODIC: DSPH_CODE_OUTIGNORE));
     }
   }

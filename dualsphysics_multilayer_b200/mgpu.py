@@ -80,12 +80,12 @@ class SlabDriver:
             return
         ctx = self.ctx
         t0 = self._tick()
-        counts = ctx.mgpu_count()                                   # [L: bg, fm, fg, R: bg, fm, fg]
+        counts = ctx.mgpu_count()                                   # [L: bg, bm, fm, fg, R: bg, bm, fm, fg]
         t0 = self._tick("xch_count", t0)
         mine = torch.tensor(counts, dtype=torch.int64, device=self.device)
-        fromleft = torch.zeros(3, dtype=torch.int64, device=self.device)
-        fromright = torch.zeros(3, dtype=torch.int64, device=self.device)
-        toleft = mine[0:3].contiguous(); toright = mine[3:6].contiguous()
+        fromleft = torch.zeros(4, dtype=torch.int64, device=self.device)
+        fromright = torch.zeros(4, dtype=torch.int64, device=self.device)
+        toleft = mine[0:4].contiguous(); toright = mine[4:8].contiguous()
         ops = []
         if self.left is not None:
             ops += [dist.P2POp(dist.isend, toleft, self.left, self.group), dist.P2POp(dist.irecv, fromleft, self.left, self.group)]
@@ -93,7 +93,7 @@ class SlabDriver:
             ops += [dist.P2POp(dist.isend, toright, self.right, self.group), dist.P2POp(dist.irecv, fromright, self.right, self.group)]
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-        nl, nr = int(sum(counts[0:3])), int(sum(counts[3:6]))
+        nl, nr = int(sum(counts[0:4])), int(sum(counts[4:8]))
         rl = [int(v) for v in fromleft.tolist()]; rr = [int(v) for v in fromright.tolist()]
         t0 = self._tick("xch_counts_comm", t0)
         sl, sr = self._buffer("sl", nl), self._buffer("sr", nr)
@@ -130,6 +130,38 @@ class SlabDriver:
         if name:
             self.prof[name] = self.prof.get(name, 0.0) + (t - t0)
         return t
+
+    # ---- re-balancing: move the cuts to the current particle distribution ------------------------------------------
+    def rebalance(self, bound_weight=0.05, minwidth=None):
+        """Collective.  New cuts from the global per-column histogram of owned particles (fluid 1, boundary bound_weight).
+        A cut moves by less than the width of the narrower of its two slabs, so every particle changes owner by at most
+        one rank; the next exchange migrates fluid AND boundary particles that are outside the new range and rebuilds the
+        halos.  Returns True when the cuts changed."""
+        if self.world == 1:
+            return False
+        ctx = self.ctx
+        ncol = int(ctx.domain_info()[2][0])
+        fl, bd = ctx.mgpu_column_counts(ncol)
+        w = torch.from_numpy(fl.astype(np.float64) + bound_weight * bd.astype(np.float64)).to(self.device)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM, group=self.group)
+        hist = w.cpu().numpy()
+        sd = 2 if int(ctx.cfg.cellmode) == 2 else 1          # DSPH_CELLMODE_HALF: cells of h, halo = 2 cells
+        if minwidth is None:
+            minwidth = 2 * sd + 1
+        target = balanced_cuts(hist, self.world, minwidth)
+        new = list(self.cuts)
+        for r in range(1, self.world):
+            room = min(self.cuts[r] - self.cuts[r - 1], self.cuts[r + 1] - self.cuts[r]) - 1
+            new[r] = int(min(max(target[r], self.cuts[r] - room), self.cuts[r] + room))
+        for r in range(1, self.world):                                 # keep every slab at least minwidth wide
+            new[r] = max(new[r], new[r - 1] + minwidth)
+        for r in range(self.world - 1, 0, -1):
+            new[r] = min(new[r], new[r + 1] - minwidth)
+        if new == self.cuts:
+            return False
+        self.cuts = new
+        ctx.mgpu_config(self.rank, self.world, new[self.rank], new[self.rank + 1])
+        return True
 
     # ---- the step pieces (same sequence as JSphGpuSingle::ComputeStep_Sym/_Ver + closing divide) -------------------
     def celldiv(self):

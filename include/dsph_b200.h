@@ -219,15 +219,20 @@ int dsph_pips(dsph_ctx *ctx,uint64_t *fluid_real,uint64_t *fluid_checked,uint64_
  *      particles within 2h of the cut (ghosts: CODE_PERIODIC, neighbours only, dropped by the next divide), and after
  *      dsph_forces_launch an all-reduce(max) over dsph_forces_maxima_ptr (4 x uint32 bit patterns of non-negative floats)
  *      gives every rank the global dt in dsph_forces_finish.  Record = 88 or 112 bytes (dsph_mgpu_record_bytes).
- *      counts[6] = {bound ghosts, fluid migrants, fluid ghosts} for the left neighbour, then for the right one;
- *      a direction buffer holds its three groups back to back.  Buffers are caller-owned device memory. ---------- */
+ *      counts[8] = {boundary ghosts, boundary migrants, fluid migrants, fluid ghosts} for the left neighbour, then for
+ *      the right one; a direction buffer holds its four groups back to back.  Buffers are caller-owned device memory.
+ *      Re-balancing: dsph_mgpu_column_counts gives the owned particles per cell column; after an all-reduce the caller
+ *      picks new cuts (each cut moves by less than the width of its two slabs) and calls dsph_mgpu_config again: the next
+ *      count/pack/unpack migrates the fluid AND boundary particles that are outside the new range. ------------------ */
 int dsph_mgpu_config(dsph_ctx *ctx,int rank,int nranks,uint32_t xcell_lo,uint32_t xcell_hi);
 /* bytes of one record for this context: 88 = pos 24 + velrhop 16 + pospre 24 + velrhoppre|velrhopm1 16 + idp 4 + code 4,
  * + 24 (SpsTau) when the context runs laminar+SPS viscosity (single-phase), whose stress tensor is particle state */
 uint32_t dsph_mgpu_record_bytes(const dsph_ctx *ctx);
-int dsph_mgpu_count(dsph_ctx *ctx,uint32_t counts[6]);
+int dsph_mgpu_count(dsph_ctx *ctx,uint32_t counts[8]);
 int dsph_mgpu_pack(dsph_ctx *ctx,void *send_left,void *send_right);
-int dsph_mgpu_unpack(dsph_ctx *ctx,const uint32_t counts[6],const void *recv_left,const void *recv_right);
+int dsph_mgpu_unpack(dsph_ctx *ctx,const uint32_t counts[8],const void *recv_left,const void *recv_right);
+/* owned (CODE_NORMAL) particles per cell column of the domain, fluid and boundary separately; ncol = domcells[0] */
+int dsph_mgpu_column_counts(dsph_ctx *ctx,uint32_t *fluid,uint32_t *bound,uint32_t ncol);
 int dsph_forces_launch(dsph_ctx *ctx,int interstep);
 void* dsph_forces_maxima_ptr(dsph_ctx *ctx);
 int dsph_forces_finish(dsph_ctx *ctx,dsph_forceres *res);

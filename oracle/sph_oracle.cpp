@@ -101,7 +101,7 @@ struct Oracle {
   unsigned long long PipsFluidReal=0,PipsFluidChecked=0,PipsBoundReal=0,PipsBoundChecked=0;
   std::string Error;
   // ---- x-slab decomposition (test twin of csrc/mgpu.cuh; the reference has no multi-GPU code)
-  bool Mgpu=false; int MgRank=0,MgNranks=1; unsigned MgXlo=0,MgXhi=0; unsigned MgCounts[6]={0,0,0,0,0,0};
+  bool Mgpu=false; int MgRank=0,MgNranks=1; unsigned MgXlo=0,MgXhi=0; unsigned MgCounts[8]={0,0,0,0,0,0,0,0};
   std::vector<unsigned char> MgFlags; unsigned MaxBits[4]={0,0,0,0}; float LastAce2=0,LastVel2=0;
   bool Ghosts()const{ return PeriActive!=0 || Mgpu; }
   // ---- multiphase non-Newtonian fork (M/JSph.h:519-531, M/DualSphDef.h StPhaseCte/StPhaseArray, M/JSphCpu.h:363-371)
@@ -1164,20 +1164,31 @@ struct Oracle {
     const typecode rc=Code[p];
     if(!CodeIsNormal(rc) || Dcell[p]==0xFFFFFFFFu)return;
     const unsigned cx=DcCellx(DomCellCode,Dcell[p]); const bool fluid=CodeIsFluid(rc); const unsigned sd=unsigned(ScellDiv);
-    if(MgRank>0){ if(fluid && cx<MgXlo)tl=1; else if(cx<MgXlo+sd && cx>=MgXlo)tl=(fluid? 2: 0); }
-    if(MgRank<MgNranks-1){ if(fluid && cx>=MgXhi)tr=1; else if(cx+sd>=MgXhi && cx<MgXhi)tr=(fluid? 2: 0); }
+    // kinds: 0 boundary ghost, 1 boundary migrant (only after the cuts moved: re-balancing), 2 fluid migrant, 3 fluid ghost
+    if(MgRank>0){ if(cx<MgXlo)tl=(fluid? 2: 1); else if(cx<MgXlo+sd)tl=(fluid? 3: 0); }
+    if(MgRank<MgNranks-1){ if(cx>=MgXhi)tr=(fluid? 2: 1); else if(cx+sd>=MgXhi)tr=(fluid? 3: 0); }
   }
-  void MgCount(unsigned counts[6]){
+  void MgCount(unsigned counts[8]){
     for(unsigned p=0;p<Np;p++){ const typecode rc=Code[p]; if(CodeIsPeriodic(rc))Code[p]=typecode(CodeSetNormal(rc)|DSPH_CODE_OUTIGNORE); }
     MgFlags.assign(Np,0);
-    for(int g=0;g<6;g++)MgCounts[g]=0;
+    for(int g=0;g<8;g++)MgCounts[g]=0;
     for(unsigned p=0;p<Np;p++){
       int tl,tr; MgClassify(p,tl,tr); unsigned char f=0;
       if(tl>=0){ f|=(unsigned char)(1u<<tl); MgCounts[tl]++; }
-      if(tr>=0){ f|=(unsigned char)(1u<<(3+tr)); MgCounts[3+tr]++; }
+      if(tr>=0){ f|=(unsigned char)(1u<<(4+tr)); MgCounts[4+tr]++; }
       MgFlags[p]=f;
     }
-    for(int g=0;g<6;g++)counts[g]=MgCounts[g];
+    for(int g=0;g<8;g++)counts[g]=MgCounts[g];
+  }
+  // owned (normal) particles per cell column, fluid and boundary separately: input of the slab re-balancing
+  void MgColumnCounts(unsigned *fluid,unsigned *bound,unsigned ncol)const{
+    for(unsigned c=0;c<ncol;c++)fluid[c]=bound[c]=0;
+    for(unsigned p=0;p<Np;p++){
+      const typecode rc=Code[p];
+      if(!CodeIsNormal(rc) || Dcell[p]==0xFFFFFFFFu)continue;
+      const unsigned cx=DcCellx(DomCellCode,Dcell[p]);
+      if(cx<ncol){ if(CodeIsFluid(rc))fluid[cx]++; else bound[cx]++; }
+    }
   }
   bool MgSps()const{ return TVisco==DSPH_VISCO_LAMINARSPS && !MultiPhase; }     // SpsTau is particle state: it travels with the record
   unsigned MgRecordBytes()const{ return unsigned(sizeof(MgRecord))+(MgSps()? 24u: 0u); }
@@ -1186,8 +1197,8 @@ struct Oracle {
     const unsigned sd=unsigned(ScellDiv), rb=MgRecordBytes();
     for(int d=0;d<2;d++){
       unsigned base=0;
-      for(int kd=0;kd<3;kd++){
-        const int g=3*d+kd; unsigned n=0;
+      for(int kd=0;kd<4;kd++){
+        const int g=4*d+kd; unsigned n=0; const bool migrant=(kd==1 || kd==2);
         for(unsigned p=0;p<Np && MgCounts[g];p++)if((MgFlags[p]>>g)&1u){
           MgRecord r; memset(&r,0,sizeof(r));
           r.pos[0]=Pos[p].x; r.pos[1]=Pos[p].y; r.pos[2]=Pos[p].z; r.velrhop=Velrhop[p];
@@ -1195,12 +1206,12 @@ struct Oracle {
           if(TStep==DSPH_STEP_VERLET)r.aux=VelrhopM1[p];
           r.idp=Idp[p];
           const typecode rc=Code[p];
-          r.code=(kd==1? rc: typecode(CodeSetNormal(rc)|DSPH_CODE_PERIODIC));
+          r.code=(migrant? rc: typecode(CodeSetNormal(rc)|DSPH_CODE_PERIODIC));
           char *dstp=out[d]+size_t(base+n)*rb;
           memcpy(dstp,&r,sizeof(r));
           if(MgSps())memcpy(dstp+sizeof(r),&SpsTau[p],24);
           n++;
-          if(kd==1){
+          if(migrant){
             const unsigned cx=DcCellx(DomCellCode,Dcell[p]);
             const bool band=(d==0? (cx+sd>=MgXlo): (cx<MgXhi+sd));
             Code[p]=typecode(CodeSetNormal(rc)|(band? DSPH_CODE_PERIODIC: DSPH_CODE_OUTIGNORE));
@@ -1210,8 +1221,8 @@ struct Oracle {
       }
     }
   }
-  void MgUnpack(const unsigned counts[6],const void *recvleft,const void *recvright){
-    const unsigned bgl=counts[0], fl=counts[1]+counts[2], bgr=counts[3], fr=counts[4]+counts[5];
+  void MgUnpack(const unsigned counts[8],const void *recvleft,const void *recvright){
+    const unsigned bgl=counts[0]+counts[1], fl=counts[2]+counts[3], bgr=counts[4]+counts[5], fr=counts[6]+counts[7];   // boundary | fluid per side
     const unsigned total=bgl+fl+bgr+fr;
     if(Idp.size()<size_t(Np)+total)Resize(Np+total+(Np+total)/20+128);
     unsigned dst=Np;
@@ -1379,9 +1390,10 @@ int orc_mgpu_config(orc_state *s,int rank,int nranks,uint32_t xlo,uint32_t xhi){
     o.Mgpu=(nranks>1); o.MgRank=rank; o.MgNranks=nranks; o.MgXlo=xlo; o.MgXhi=xhi; });
 }
 uint32_t orc_mgpu_record_bytes(const orc_state *s){ static_assert(sizeof(Oracle::MgRecord)==88,"wire format"); return s? s->o.MgRecordBytes(): 88u; }
-int orc_mgpu_count(orc_state *s,uint32_t counts[6]){ return Guard([&]{ unsigned c[6]; s->o.MgCount(c); for(int i=0;i<6;i++)counts[i]=c[i]; }); }
+int orc_mgpu_count(orc_state *s,uint32_t counts[8]){ return Guard([&]{ unsigned c[8]; s->o.MgCount(c); for(int i=0;i<8;i++)counts[i]=c[i]; }); }
+int orc_mgpu_column_counts(orc_state *s,uint32_t *fluid,uint32_t *bound,uint32_t ncol){ return Guard([&]{ s->o.MgColumnCounts(fluid,bound,ncol); }); }
 int orc_mgpu_pack(orc_state *s,void *sl,void *sr){ return Guard([&]{ s->o.MgPack(sl,sr); }); }
-int orc_mgpu_unpack(orc_state *s,const uint32_t counts[6],const void *rl,const void *rr){ return Guard([&]{ unsigned c[6]; for(int i=0;i<6;i++)c[i]=counts[i]; s->o.MgUnpack(c,rl,rr); }); }
+int orc_mgpu_unpack(orc_state *s,const uint32_t counts[8],const void *rl,const void *rr){ return Guard([&]{ unsigned c[8]; for(int i=0;i<8;i++)c[i]=counts[i]; s->o.MgUnpack(c,rl,rr); }); }
 int orc_forces_launch(orc_state *s,int interstep){
   (void)interstep;
   return Guard([&]{ Oracle &o=s->o; o.InteractionForces();

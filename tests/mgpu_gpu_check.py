@@ -16,7 +16,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     kind = sys.argv[3] if len(sys.argv) > 3 else "dambreak"     # dambreak | nn2layer (multiphase, FDA) [":key=value,..."]
-    base, _, opts = kind.partition(":")
+    rebalance = kind.endswith("@rebalance")          # start from bad cuts and let SlabDriver.rebalance() walk them back
+    base, _, opts = kind.replace("@rebalance", "").partition(":")
     cd = dsph.make_case(base, npart)
     for kv in filter(None, opts.split(",")):
         k, v = kv.split("=")
@@ -26,14 +27,23 @@ def main():
     scell, dmin, dcells = ctx.domain_info()
     cx = ((cd.pos[:, 0] - dmin[0]) / scell).astype(np.int64)
     cuts = mgpu.balanced_cuts(np.bincount(cx, minlength=dcells[0]), world, 3)
+    if rebalance:
+        cuts = [cuts[0]] + [min(c + 4, dcells[0] - 3 * (world - i)) for i, c in enumerate(cuts[1:-1], 1)] + [cuts[-1]]
     sel = mgpu.slab_select(cd.pos[:, 0], cuts, rank, scell, dmin[0])
     ctx.upload(cd.idp[sel], cd.pos[sel], cd.velrhop[sel], int(np.count_nonzero(sel[: cd.npb])), code[sel])
     drv = mgpu.SlabDriver(ctx, rank, world, cuts, "cuda:%d" % local)
     drv.celldiv()
     t = 0.0
-    for _ in range(nsteps):
+    moved = 0
+    for s in range(nsteps):
+        if rebalance and s % 3 == 2 and drv.rebalance(bound_weight=0.3):
+            moved += 1
+            drv.celldiv()
         dt, _ = drv.step()
         t += dt
+    if rebalance and moved == 0:
+        print("MGPU_CHECK FAIL: the cuts did not move")
+        sys.exit(1)
     own = drv.owned()
     gathered = [None] * world
     dist.all_gather_object(gathered, dict(t=t, idp=own["idp"], pos=own["pos"], velrhop=own["velrhop"], sent=drv.sent_records))
