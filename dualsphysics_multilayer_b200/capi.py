@@ -272,6 +272,17 @@ class SphContext:
         self.lib.check(self.lib.fn("set_symplectic_dtpre")(self.h, float(v)))
 
     # -- x-slab multi-GPU (see mgpu.py)
+    def measure_points(self, points):
+        """Pressure, velocity and kernel sum at `points` [k,3] (Shepard-corrected interpolation over the fluid particles)."""
+        pts = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+        n = pts.shape[0]
+        press = np.zeros(n, np.float32); vel = np.zeros((n, 3), np.float32); kc = np.zeros(n, np.float32)
+        fn = self.lib.fn("measure_points")
+        fn.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        self.lib.check(fn(self.h, n, pts.ctypes.data_as(C.POINTER(C.c_double)), press.ctypes.data_as(C.POINTER(C.c_float)),
+                          vel.ctypes.data_as(C.POINTER(C.c_float)), kc.ctypes.data_as(C.POINTER(C.c_float))))
+        return press, vel, kc
+
     def mgpu_config(self, rank, nranks, xlo, xhi):
         self.lib.check(self.lib.fn("mgpu_config")(self.h, int(rank), int(nranks), int(xlo), int(xhi)))
 

@@ -99,6 +99,10 @@ int dsph_pips(dsph_ctx *ctx,uint64_t *fr,uint64_t *fc,uint64_t *br,uint64_t *bc)
   NEEDCTX(ctx);
   return Guard([&]{ unsigned long long a,b,c,d; ctx->eng->Pips(&a,&b,&c,&d); if(fr)*fr=a; if(fc)*fc=b; if(br)*br=c; if(bc)*bc=d; });
 }
+int dsph_measure_points(dsph_ctx *ctx,uint32_t npoints,const double *points_xyz,float *press,float *vel_xyz,float *kcorr){
+  NEEDCTX(ctx); if(npoints && !points_xyz){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  return Guard([&]{ ctx->eng->MeasurePoints(npoints,points_xyz,press,vel_xyz,kcorr); });
+}
 // CUDA-event stopwatch on the context's stream (bench.py: torch events do not see this stream)
 int dsph_timer_start(dsph_ctx *ctx){ NEEDCTX(ctx); return Guard([&]{ if(cudaEventRecord(ctx->eng->ev[14],ctx->eng->stm)!=cudaSuccess)throw EngineError(DSPH_ERR_CUDA,"cudaEventRecord"); }); }
 int dsph_timer_stop(dsph_ctx *ctx,double *ms){

@@ -13,6 +13,7 @@
 #include "periodic.cuh"
 #include "mgpu.cuh"
 #include "forces_nn.cuh"
+#include "measure.cuh"
 #include <cstdio>
 #include <cstring>
 #include <cmath>
@@ -513,6 +514,32 @@ void Engine::ForcesDownload(unsigned first,unsigned count,float *ace,float *ar){
     if(ace){ ace[3*size_t(i)]=h[4*size_t(i)]; ace[3*size_t(i)+1]=h[4*size_t(i)+1]; ace[3*size_t(i)+2]=h[4*size_t(i)+2]; }
     if(ar)ar[i]=h[4*size_t(i)+3];
   }
+}
+
+// Probes: pressure / velocity / kernel sum at n points from the current cell list (measure.cuh)
+void Engine::MeasurePoints(unsigned n,const double *hpoints,float *hpress,float *hvel,float *hkcorr){
+  if(!divok)throw EngineError(DSPH_ERR_STATE,"dsph_measure_points needs a cell division first (dsph_celldiv_run).");
+  if(!n)return;
+  double *dpts=nullptr; float *dout=nullptr;
+  CUCHECK(cudaMalloc((void**)&dpts,size_t(n)*24));
+  if(cudaMalloc((void**)&dout,size_t(n)*20)!=cudaSuccess){ cudaFree(dpts); throw EngineError(DSPH_ERR_CUDA,"cudaMalloc failed (probe results)."); }
+  try{
+    CUCHECK(cudaMemcpyAsync(dpts,hpoints,size_t(n)*24,cudaMemcpyHostToDevice,stm));
+    MeasureArgs m; m.npoints=n; m.points=dpts; m.pos=pos[cur]; m.press=dout; m.vel=dout+n; m.kcorr=dout+size_t(n)*4;
+    const ForceParams t=MakeForceParams();
+    const unsigned nb=(n+127)/128;
+    const bool wend=(cfg.tkernel==DSPH_KERNEL_WENDLAND);
+    if(cfg.nn_on){ if(wend)ker_measure_points<DSPH_KERNEL_WENDLAND,true><<<nb,128,0,stm>>>(m,t,dc,dph); else ker_measure_points<DSPH_KERNEL_CUBIC,true><<<nb,128,0,stm>>>(m,t,dc,dph); }
+    else{ if(wend)ker_measure_points<DSPH_KERNEL_WENDLAND,false><<<nb,128,0,stm>>>(m,t,dc,dph); else ker_measure_points<DSPH_KERNEL_CUBIC,false><<<nb,128,0,stm>>>(m,t,dc,dph); }
+    launches++;
+    if(hpress)CUCHECK(cudaMemcpyAsync(hpress,dout,size_t(n)*4,cudaMemcpyDeviceToHost,stm));
+    if(hvel)CUCHECK(cudaMemcpyAsync(hvel,dout+n,size_t(n)*12,cudaMemcpyDeviceToHost,stm));
+    if(hkcorr)CUCHECK(cudaMemcpyAsync(hkcorr,dout+size_t(n)*4,size_t(n)*4,cudaMemcpyDeviceToHost,stm));
+    CUCHECK(cudaStreamSynchronize(stm));
+    CUCHECK(cudaGetLastError());
+  }
+  catch(...){ cudaFree(dpts); cudaFree(dout); throw; }
+  cudaFree(dpts); cudaFree(dout);
 }
 
 void Engine::Pips(unsigned long long *fr,unsigned long long *fc,unsigned long long *br,unsigned long long *bc){

@@ -88,6 +88,7 @@ class Engine {
   void MgPack(void *sendleft,void *sendright);
   void MgUnpack(const unsigned counts[8],const void *recvleft,const void *recvright);
   void ForcesDownload(unsigned first,unsigned count,float *ace,float *ar);
+  void MeasurePoints(unsigned n,const double *points,float *press,float *vel,float *kcorr);
   void Pips(unsigned long long *fr,unsigned long long *fc,unsigned long long *br,unsigned long long *bc);
   double DtVariable(double *dt1,double *dt2,double *dt3=nullptr)const;
   void FillForceRes(dsph_forceres *res)const;

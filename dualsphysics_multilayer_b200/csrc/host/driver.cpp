@@ -61,6 +61,37 @@ static void SavePart(Engine &eng,const CaseData &cd,const std::string &dirout,un
   log.Printf("Part_%04u  %12.6f  %12u  %10u particles stored",cpart,timestep,step,p.npok);
 }
 
+// Probe points: <dir>/<casename>_Points.txt, one "x y z" per line (separators blank , ;  comments #), the file format of the
+// reference examples' CaseDambreak_Points*.txt lists for MeasureTool.  Results go to <dirout>/MeasurePoints.csv, one row per
+// PART and point: pressure, velocity and kernel sum from dsph_measure_points' kernel (measure.cuh).
+static std::vector<double> LoadPoints(const std::string &file){
+  std::vector<double> pts;
+  FILE *f=fopen(file.c_str(),"r");
+  if(!f)return pts;
+  char line[512];
+  while(fgets(line,sizeof(line),f)){
+    for(char *q=line;*q;q++)if(*q==','||*q==';'||*q=='\t')*q=' ';
+    if(line[0]=='#')continue;
+    double x,y,z;
+    if(sscanf(line,"%lf %lf %lf",&x,&y,&z)==3){ pts.push_back(x); pts.push_back(y); pts.push_back(z); }
+  }
+  fclose(f);
+  return pts;
+}
+static void SaveProbes(Engine &eng,const std::vector<double> &pts,const std::string &dirout,unsigned cpart,double timestep){
+  const unsigned n=unsigned(pts.size()/3);
+  if(!n)return;
+  std::vector<float> press(n),vel(size_t(n)*3),kc(n);
+  eng.MeasurePoints(n,pts.data(),press.data(),vel.data(),kc.data());
+  const std::string file=dirout+"/MeasurePoints.csv";
+  FILE *f=fopen(file.c_str(),cpart? "a": "w");
+  if(!f)return;
+  if(!cpart)fprintf(f,"Part;Time [s];Point;PosX [m];PosY [m];PosZ [m];Press [Pa];VelX [m/s];VelY [m/s];VelZ [m/s];Kcorr\n");
+  for(unsigned i=0;i<n;i++)fprintf(f,"%u;%.9g;%u;%.9g;%.9g;%.9g;%.7g;%.7g;%.7g;%.7g;%.7g\n",cpart,timestep,i,pts[3*i],pts[3*i+1],pts[3*i+2],
+    press[i],vel[3*i],vel[3*i+1],vel[3*i+2],kc[i]);
+  fclose(f);
+}
+
 RunSummary RunCase(const RunOptions &opt){
   RunSummary sum;
   mkdir(opt.dirout.c_str(),0755);
@@ -82,7 +113,10 @@ RunSummary RunCase(const RunOptions &opt){
   double timestep=0; unsigned part=0; unsigned long long nstep=0;
   const auto t0=std::chrono::steady_clock::now();
   auto Elapsed=[&]{ return std::chrono::duration<double>(std::chrono::steady_clock::now()-t0).count(); };
+  const std::vector<double> probes=LoadPoints(opt.dir+"/"+opt.casename+"_Points.txt");
+  if(!probes.empty())log.Printf("Probe points: %u (%s_Points.txt) -> MeasurePoints.csv",unsigned(probes.size()/3),opt.casename.c_str());
   if(opt.savepart)SavePart(eng,cd,opt.dirout,part,timestep,0,0,0,log);
+  SaveProbes(eng,probes,opt.dirout,part,timestep);
   part++;
   double timepartnext=NextTime(timestep,c.timeout);
   eng.GetTimers(nullptr,true);
@@ -98,6 +132,7 @@ RunSummary RunCase(const RunOptions &opt){
     if(timestep>=timepartnext || partoutstop){
       if(opt.savepart)SavePart(eng,cd,opt.dirout,part,timestep,unsigned(nstep),Elapsed(),nout,log);
       else log.Printf("Part_%04u  %12.6f  %12llu  dt=%.6g  np=%u",part,timestep,nstep,dt,eng.np);
+      SaveProbes(eng,probes,opt.dirout,part,timestep);
       part++;
       timepartnext=NextTime(timestep,c.timeout);
       if(partoutstop){ log.Printf("Particles OUT limit reached..."); break; }

@@ -211,6 +211,13 @@ double dsph_last_force_ms(const dsph_ctx *ctx);
  * for fluid and boundary particles; used by the roofline byte model. */
 int dsph_pips(dsph_ctx *ctx,uint64_t *fluid_real,uint64_t *fluid_checked,uint64_t *bound_real,uint64_t *bound_checked);
 
+/* ---- probes: pressure, velocity and kernel sum at arbitrary points, Shepard-corrected SPH interpolation
+ *      over the fluid particles of the current cell list (needs dsph_celldiv_run).  Stand-in for the reference's MeasureTool
+ *      post-processing (-points <file> -vars:+press,+vel,+kcorr; binary only in the reference) with the interpolation of the
+ *      in-solver velocity gauge (JGaugeVelocity::CalculeCpuT S/JDsGaugeItem.cpp:325-367) divided by the kernel sum.
+ *      Any output pointer may be NULL.  Points outside the cell domain give zeros. ----------------------------------- */
+int dsph_measure_points(dsph_ctx *ctx,uint32_t npoints,const double *points_xyz,float *press,float *vel_xyz,float *kcorr);
+
 /* ---- x-slab multi-GPU (new: the reference has no multi-GPU code, only the hooks DCEL_CodeDomLeft/Right
  *      S/JDsDcellDef.h:30-31 and MGDIV_X S/DualSphDef.h:494-499).  One context per GPU owns the cell columns
  *      [xcell_lo,xcell_hi) of the domain.  Before every dsph_celldiv_run the caller runs

@@ -29,6 +29,21 @@ def gauge_pressure(points, pos, rhop, h, cteb, rhop0, gamma, mass):
     return out, ksum
 
 
+def gauge_velocity(points, pos, vel, rhop, h, mass):
+    """Shepard-corrected velocity at `points` [k,3] from fluid particles (JGaugeVelocity interpolation / kernel sum)."""
+    out = np.zeros((len(points), 3))
+    for k, pt in enumerate(np.asarray(points, np.float64)):
+        d = pos - pt
+        near = np.all(np.abs(d) <= 2.0 * h, axis=1)
+        if not near.any():
+            continue
+        r = np.sqrt((d[near] ** 2).sum(axis=1))
+        w = wendland(r / h, h) * (mass / rhop[near])
+        if w.sum() > 0:
+            out[k] = (w[:, None] * vel[near]).sum(axis=0) / w.sum()
+    return out
+
+
 def surge_front(pos_fluid, zmax):
     """x of the advancing front along the bed: the 99.5th percentile of x of the fluid particles below zmax."""
     sel = pos_fluid[:, 2] <= zmax

@@ -154,6 +154,53 @@ def test_gpu_nn_ring_kernel_matches_plain_loop(gpu_lib, opts):
     assert abs(f1.dt - f6.dt) / f1.dt < 1e-5 and abs(f1.viscetadtmax - f6.viscetadtmax) <= 1e-5 * abs(f1.viscetadtmax)
 
 
+@pytest.mark.parametrize("kind", ["dambreak", "nn2layer"])
+def test_gpu_measure_points_match_numpy(gpu_lib, kind):
+    """dsph_measure_points (device probes: pressure, velocity, kernel sum) against the numpy interpolation of tests/measure.py."""
+    import measure
+    cd = dsph.make_case(kind, 60000)
+    ctx = dsph.create_context(cd)
+    ctx.upload(cd.idp, cd.pos, cd.velrhop, cd.npb, cd.codes())
+    ctx.celldiv(True)
+    for _ in range(20):
+        ctx.step()
+    st = ctx.download()
+    rng = np.random.default_rng(7)
+    lo = np.array(cd.caseposmin); hi = np.array(cd.caseposmax)
+    pts = np.vstack([lo + rng.random((60, 3)) * (np.array([0.42, hi[1], 0.32]) - lo),       # inside and around the water column
+                     lo + rng.random((10, 3)) * (hi - lo), [[-1.0, 0.1, 0.1], [0.2, 0.3, 5.0]]])  # anywhere in the tank, outside the domain
+    press, vel, kc = ctx.measure_points(pts)
+    fl = (st["code"] & capi.CODE_MASKTYPE) == capi.CODE_TYPE_FLUID
+    pf = st["pos"][fl]; rf = st["velrhop"][fl, 3]; vf = st["velrhop"][fl, :3]
+    cfg = cd.cfg
+    if kind == "nn2layer":        # per-phase EOS and mass
+        ph = (st["code"][fl] & 0x7ff).astype(int)
+        rho0 = np.array([cfg.phases[k].rho for k in range(cfg.nn_nphases)])[ph]
+        cs0 = np.array([cfg.phases[k].cs0 for k in range(cfg.nn_nphases)])[ph]
+        gam = np.array([cfg.phases[k].gamma for k in range(cfg.nn_nphases)])[ph]
+        pj = (cs0 ** 2 * rho0 / gam) * ((rf.astype(np.float64) / rho0) ** gam - 1.0)
+        mass = rho0 * cfg.dp ** 3
+    else:
+        pj = float(cfg.cteb) * ((rf.astype(np.float64) / float(cfg.rhopzero)) ** float(cfg.gamma) - 1.0)
+        mass = np.full(len(rf), float(cfg.massfluid))
+    h = float(cfg.kernelh)
+    refp = np.zeros(len(pts)); refv = np.zeros((len(pts), 3)); refk = np.zeros(len(pts))
+    for k, pt in enumerate(pts):
+        d = pf - pt; near = np.all(np.abs(d) <= 2 * h, axis=1)
+        if near.any():
+            r = np.sqrt((d[near] ** 2).sum(axis=1)); w = measure.wendland(r / h, h) * (mass[near] / rf[near])
+            refk[k] = w.sum()
+            if refk[k] > 0:
+                refp[k] = (w * pj[near]).sum() / refk[k]; refv[k] = (w[:, None] * vf[near]).sum(axis=0) / refk[k]
+    assert np.count_nonzero(refk > 0.5) > 30, "most probes must lie inside the fluid"
+    assert kc[-1] == 0 and kc[-2] == 0 and press[-1] == 0
+    pscale = max(np.abs(refp).max(), 1.0); vscale = max(np.abs(refv).max(), 1e-6)
+    assert np.max(np.abs(kc - refk)) <= 2e-5 * max(refk.max(), 1.0), np.max(np.abs(kc - refk))
+    assert np.max(np.abs(press - refp)) <= 1e-4 * pscale, (np.max(np.abs(press - refp)), pscale)
+    assert np.max(np.abs(vel - refv)) <= 1e-4 * vscale, (np.max(np.abs(vel - refv)), vscale)
+    ctx.close()
+
+
 def test_gpu_large_case_properties(gpu_lib):
     """Full-size properties (no CPU oracle at this size): sortedness, permutation, begin-cell consistency, idempotence."""
     cd = dsph.make_case("dambreak", 2_000_000)

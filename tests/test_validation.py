@@ -71,8 +71,15 @@ def test_gpu_dambreak_1s_front_and_gauges_within_1_percent(gpu_lib, tmp_path):
     z = np.load(GOLD)
     cd = _case(tmp_path, z)
     out = tmp_path / "out"
+    np.savetxt(str(tmp_path / "Case_Points.txt"), np.array(gauges_for(cd)), header="probe points (x y z)")   # driver: device-side probes
     dsph.run_case(str(tmp_path), "Case", str(out), device=0, nsteps=0, savepart=True)
     ours = series_from_parts(str(out), cd)
+    # the driver's own probe output (dsph_measure_points kernel) must agree with the numpy measurement of its PART files
+    csv = np.genfromtxt(str(out / "MeasurePoints.csv"), delimiter=";", skip_header=1)
+    pcsv = csv[:, 6].reshape(-1, 4)
+    assert pcsv.shape[0] == len(ours)
+    scale0 = float(cd.cfg.rhopzero) * 9.81 * 0.3
+    assert np.max(np.abs(pcsv - ours[:, 5:9])) <= 2e-4 * scale0, np.max(np.abs(pcsv - ours[:, 5:9]))
     ref = z["series"]
     assert len(ours) == len(ref) == 21, (len(ours), len(ref))
     assert np.all(ours[:, COL["np"]] == ref[:, COL["np"]]), "no particle may be lost that the reference keeps"
