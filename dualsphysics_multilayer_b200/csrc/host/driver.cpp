@@ -11,6 +11,11 @@
 #include <cstdarg>
 #include <cmath>
 #include <vector>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <memory>
+#include <stdexcept>
 #include <sys/stat.h>
 
 namespace dsph {
@@ -34,11 +39,57 @@ double NextTime(double t,double tout){
 }
 }
 
-static void SavePart(Engine &eng,const CaseData &cd,const std::string &dirout,unsigned cpart,double timestep,unsigned step,double runtime,unsigned long long nout,Log &log){
+// PART output: the state is copied off the device by the time loop (one D2H per array), everything else --
+// dropping the halo/periodic copies, building the bi4 container and writing it -- runs on a writer thread while the
+// simulation goes on.  One job in flight: a new PART waits for the previous file to be complete.
+struct PartJob {
+  std::string file; PartHead h; PartData p;
+  std::vector<unsigned> idp; std::vector<typecode> code; std::vector<double> pos; std::vector<float> vr;
+};
+class PartWriter {
+  std::thread th; std::mutex mx; std::condition_variable cv;
+  std::unique_ptr<PartJob> job; bool stop=false; std::string error;
+  static void Write(PartJob &j){
+    PartData &p=j.p; const size_t np=j.idp.size();
+    p.idp.reserve(np); p.pos.reserve(np*3); p.vel.reserve(np*3); p.rhop.reserve(np);
+    for(size_t q=0;q<np;q++)if((j.code[q]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL){   // periodic / halo copies are not saved (S/JSphGpuSingle.cpp:897)
+      p.idp.push_back(j.idp[q]);
+      p.pos.push_back(j.pos[3*q]); p.pos.push_back(j.pos[3*q+1]); p.pos.push_back(j.pos[3*q+2]);
+      p.vel.push_back(j.vr[4*q]); p.vel.push_back(j.vr[4*q+1]); p.vel.push_back(j.vr[4*q+2]);
+      p.rhop.push_back(j.vr[4*q+3]);
+    }
+    p.npok=unsigned(p.idp.size());
+    SavePartFile(j.file,j.h,p,true);
+  }
+  void Loop(){
+    for(;;){
+      std::unique_ptr<PartJob> j;
+      { std::unique_lock<std::mutex> lk(mx); cv.wait(lk,[&]{ return job || stop; }); if(!job && stop)return; j=std::move(job); }
+      try{ Write(*j); }catch(const std::exception &e){ std::lock_guard<std::mutex> lk(mx); error=e.what(); }
+      { std::lock_guard<std::mutex> lk(mx); busy=false; }
+      cv.notify_all();
+    }
+  }
+  bool busy=false;
+ public:
+  PartWriter(){ th=std::thread([this]{ Loop(); }); }
+  ~PartWriter(){ try{ Finish(); }catch(...){} { std::lock_guard<std::mutex> lk(mx); stop=true; } cv.notify_all(); if(th.joinable())th.join(); }
+  void Submit(std::unique_ptr<PartJob> j){
+    std::unique_lock<std::mutex> lk(mx);
+    cv.wait(lk,[&]{ return !busy; });
+    if(!error.empty())throw std::runtime_error("PART output failed: "+error);
+    job=std::move(j); busy=true;
+    lk.unlock(); cv.notify_all();
+  }
+  void Finish(){ std::unique_lock<std::mutex> lk(mx); cv.wait(lk,[&]{ return !busy; }); if(!error.empty()){ std::string e=error; error.clear(); throw std::runtime_error("PART output failed: "+e); } }
+};
+
+static void SavePart(Engine &eng,const CaseData &cd,const std::string &dirout,unsigned cpart,double timestep,unsigned step,double runtime,unsigned long long nout,Log &log,PartWriter &writer){
   const unsigned np=eng.np;
-  std::vector<unsigned> idp(np); std::vector<typecode> code(np); std::vector<double> pos(size_t(np)*3); std::vector<float> vr(size_t(np)*4);
-  eng.Download(0,np,idp.data(),code.data(),nullptr,pos.data(),vr.data());
-  PartHead h; PartData p;
+  std::unique_ptr<PartJob> j(new PartJob);
+  j->idp.resize(np); j->code.resize(np); j->pos.resize(size_t(np)*3); j->vr.resize(size_t(np)*4);
+  eng.Download(0,np,j->idp.data(),j->code.data(),nullptr,j->pos.data(),j->vr.data());
+  PartHead &h=j->h; PartData &p=j->p;
   const dsph_config &c=cd.cfg;
   h.casename=cd.name; h.data2d=c.simulate2d!=0; h.data2dposy=c.simulate2dposy;
   h.casenp=c.casenp; h.casenfixed=c.casenfixed; h.casenmoving=c.casenmoving; h.casenfloat=c.casenfloat; h.casenfluid=c.casenfluid;
@@ -48,17 +99,12 @@ static void SavePart(Engine &eng,const CaseData &cd,const std::string &dirout,un
   h.dp=c.dp; h.h=c.kernelh; h.b=c.cteb; h.rhop0=c.rhopzero; h.gamma=c.gamma; h.massbound=c.massbound; h.massfluid=c.massfluid;
   p.cpart=cpart; p.timestep=timestep; p.step=step; p.runtime=runtime; p.nout=unsigned(nout);
   p.symplecticdtpre=(c.tstep==DSPH_STEP_SYMPLECTIC? eng.symplecticdtpre: 0);
-  for(unsigned q=0;q<np;q++)if((code[q]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL){   // periodic duplicates are not saved (S/JSphGpuSingle.cpp:897)
-    p.idp.push_back(idp[q]);
-    p.pos.push_back(pos[3*size_t(q)]); p.pos.push_back(pos[3*size_t(q)+1]); p.pos.push_back(pos[3*size_t(q)+2]);
-    p.vel.push_back(vr[4*size_t(q)]); p.vel.push_back(vr[4*size_t(q)+1]); p.vel.push_back(vr[4*size_t(q)+2]);
-    p.rhop.push_back(vr[4*size_t(q)+3]);
-  }
-  p.npok=unsigned(p.idp.size());
   const double sc=eng.k.scell;
   for(int i=0;i<3;i++){ p.domainmin[i]=eng.k.domposmin[i]+sc*eng.dp.cellmin[i]; p.domainmax[i]=eng.k.domposmin[i]+sc*(eng.dp.cellmax[i]+1); }
-  SavePartFile(dirout+"/"+PartFileName(cpart),h,p,true);
-  log.Printf("Part_%04u  %12.6f  %12u  %10u particles stored",cpart,timestep,step,p.npok);
+  j->file=dirout+"/"+PartFileName(cpart);
+  const unsigned nsave=np-eng.npbper-eng.npfper;
+  writer.Submit(std::move(j));
+  log.Printf("Part_%04u  %12.6f  %12u  %10u particles stored",cpart,timestep,step,nsave);
 }
 
 // Probe points: <dir>/<casename>_Points.txt, one "x y z" per line (separators blank , ;  comments #), the file format of the
@@ -115,7 +161,8 @@ RunSummary RunCase(const RunOptions &opt){
   auto Elapsed=[&]{ return std::chrono::duration<double>(std::chrono::steady_clock::now()-t0).count(); };
   const std::vector<double> probes=LoadPoints(opt.dir+"/"+opt.casename+"_Points.txt");
   if(!probes.empty())log.Printf("Probe points: %u (%s_Points.txt) -> MeasurePoints.csv",unsigned(probes.size()/3),opt.casename.c_str());
-  if(opt.savepart)SavePart(eng,cd,opt.dirout,part,timestep,0,0,0,log);
+  PartWriter writer;
+  if(opt.savepart)SavePart(eng,cd,opt.dirout,part,timestep,0,0,0,log,writer);
   SaveProbes(eng,probes,opt.dirout,part,timestep);
   part++;
   double timepartnext=NextTime(timestep,c.timeout);
@@ -130,7 +177,7 @@ RunSummary RunCase(const RunOptions &opt){
     const unsigned long long nout=eng.npout_total;
     const bool partoutstop=(c.partsoutmax_on && double(nout)>double(c.partsoutmax)*double(c.casenfluid)) || !eng.np;
     if(timestep>=timepartnext || partoutstop){
-      if(opt.savepart)SavePart(eng,cd,opt.dirout,part,timestep,unsigned(nstep),Elapsed(),nout,log);
+      if(opt.savepart)SavePart(eng,cd,opt.dirout,part,timestep,unsigned(nstep),Elapsed(),nout,log,writer);
       else log.Printf("Part_%04u  %12.6f  %12llu  dt=%.6g  np=%u",part,timestep,nstep,dt,eng.np);
       SaveProbes(eng,probes,opt.dirout,part,timestep);
       part++;
@@ -140,6 +187,7 @@ RunSummary RunCase(const RunOptions &opt){
     if(opt.nsteps>0 && nstep>=(unsigned long long)opt.nsteps)break;
   }
   const double tsim=std::chrono::duration<double>(std::chrono::steady_clock::now()-tsim0).count();
+  writer.Finish();                                   // the last PART file must be complete before the run reports success
   dsph_timers tm; eng.GetTimers(&tm,false);
   sum.np0=np0; sum.steps=nstep; sum.simtime=timestep; sum.runtime_s=tsim; sum.parts=part; sum.npout=eng.npout_total;
   sum.mpartsteps_s=(tsim>0? double(partsteps)/tsim/1e6: 0);
