@@ -103,7 +103,40 @@ def run_reference(np_sample, nsteps, threads, kind="dambreak"):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
-def cpu_baseline(sample_seconds=15.0, steps=3, kind="dambreak"):
+REFGPU = os.path.join(os.path.dirname(REFBIN), "DualSPHysics5.2_linux64")
+
+
+def reference_gpu_baseline(npart, kind="dambreak", steps_a=8, steps_b=28):
+    """The reference's OWN GPU solver (JSphGpuSingle + its CUDA kernels, S/Makefile flags) recompiled for sm_100 by
+    `make -C oracle gpu52`, run on this GPU on the same workload: steady-state rate from two runs of different length (their
+    difference removes initialisation and first-launch effects).  A reported baseline: what the unmodified reference kernels
+    deliver on a B200."""
+    if kind == "nn2layer" or not os.path.exists(REFGPU):
+        return None
+    tmp = tempfile.mkdtemp(prefix="bench_refgpu_")
+    try:
+        subprocess.check_call([MKCASE, kind, str(npart), tmp, "Case"], stdout=subprocess.DEVNULL)
+        res = []
+        for ns in (steps_a, steps_b):
+            r = subprocess.run([REFGPU, "Case", "out", "-gpu", "-sv:none", "-svtimers:0", "-nsteps:%d" % ns], cwd=tmp,
+                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            m1 = re.search(r"Simulation Runtime\.*: ([0-9.eE+-]+) sec", r.stdout)
+            m2 = re.search(r"Steps of simulation\.*: (\d+)", r.stdout)
+            m3 = re.search(r"Particles of simulation \(initial\): (\d+)", r.stdout)
+            if not (m1 and m2 and m3):
+                return {"value": None, "unit": UNIT, "what": "reference GPU solver failed: " + r.stdout[-200:].replace("\n", " ")}
+            res.append((float(m1.group(1)), int(m2.group(1)), int(m3.group(1))))
+        (ta, na, npa), (tb, nb, _) = res
+        rate = npa * (nb - na) / (tb - ta) / 1e6 if tb > ta and nb > na else None
+        return {"value": rate, "unit": UNIT, "np": npa, "ms_per_step": 1e3 * (tb - ta) / (nb - na) if nb > na else None,
+                "what": "reference DualSPHysics5.2 GPU solver (its own CUDA kernels, nvcc 12.9 -O3 -use_fast_math, sm_100) on this GPU, "
+                        "%s at %d particles: steps %d..%d of two runs (%.2f s and %.2f s of Simulation Runtime)"
+                        % (WORKLOADS[kind][0], npa, na, nb, ta, tb)}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def cpu_baseline(sample_seconds=25.0, steps=3, kind="dambreak"):
     cores = os.cpu_count() or 1
     threads = min(cores, 64)                      # OMP_MAXTHREADS 64, S/OmpDefs.h:39
     np_sample = int(min(20_000_000, max(200_000, 0.05e6 * threads * sample_seconds / steps)))
@@ -125,6 +158,7 @@ def main():
     ap.add_argument("--pre-steps", type=int, default=0, help="untimed steps before warm-up (to leave the initial lattice)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the run of the reference's own GPU solver (oracle/_ref/DualSPHysics5.2_linux64)")
     ap.add_argument("--force-variant", type=int, default=0)
     ap.add_argument("--workload", default="dambreak", choices=["dambreak", "periodicbox", "nn2layer"],
                     help="DB(N) is the headline (BASELINE.json); PB(N) and NN(N) are the other single-GPU configs of SURVEY.md 8(d)")
@@ -387,6 +421,9 @@ def main():
             out["mgpu_phases_ms_per_step"] = phases
         if not a.no_cpu_baseline and world == 1:                         # the CPU baseline is reported at N=1 only
             out["cpu_baseline"] = cpu_baseline(kind=a.workload)
+            if not a.no_reference_gpu:
+                ctx.close()                                              # free the device before the reference solver allocates
+                out["reference_gpu"] = reference_gpu_baseline(a.np, a.workload)
         emit(out)
     ctx.close()
     if world > 1:
