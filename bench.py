@@ -128,7 +128,16 @@ def reference_gpu_baseline(npart, kind="dambreak", steps_a=8, steps_b=28):
             res.append((float(m1.group(1)), int(m2.group(1)), int(m3.group(1))))
         (ta, na, npa), (tb, nb, _) = res
         rate = npa * (nb - na) / (tb - ta) / 1e6 if tb > ta and nb > na else None
+        # one more short run with the reference's synchronising timers on, only for its own split of the step
+        r = subprocess.run([REFGPU, "Case", "out", "-gpu", "-sv:none", "-svtimers:1", "-nsteps:%d" % steps_b], cwd=tmp,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        split = {}
+        for key in ("NL-Limits", "NL-PreSort", "NL-RadixSort", "NL-CellBegin", "NL-SortData", "CF-Forces", "SU-ComputeStep"):
+            m = re.search(re.escape(key) + r"\.*: ([0-9.eE+-]+) sec", r.stdout)
+            if m:
+                split[key] = 1e3 * float(m.group(1)) / steps_b
         return {"value": rate, "unit": UNIT, "np": npa, "ms_per_step": 1e3 * (tb - ta) / (nb - na) if nb > na else None,
+                "its_own_timers_ms_per_step": split,
                 "what": "reference DualSPHysics5.2 GPU solver (its own CUDA kernels, nvcc 12.9 -O3 -use_fast_math, sm_100) on this GPU, "
                         "%s at %d particles: steps %d..%d of two runs (%.2f s and %.2f s of Simulation Runtime)"
                         % (WORKLOADS[kind][0], npa, na, nb, ta, tb)}
