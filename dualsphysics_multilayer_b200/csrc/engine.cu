@@ -442,7 +442,6 @@ void Engine::ForcesLaunch(int interstep){
   const unsigned npf=np-npb;
   const bool shift=(cfg.shiftmode!=0);
   if(npf && cfg.nn_on){
-    if(mgpu && cfg.nn_velgrad==DSPH_VELGRAD_SPH)throw EngineError(DSPH_ERR_ARG,"The SPH velocity-gradient approach is not available with x-slab decomposition.");
     const unsigned nl=LaunchForcesNN(forcevariant,cfg.tkernel,cfg.tvisco,cfg.tdensity,shift,t,dc,dph,stm);
     if(!nl)throw EngineError(DSPH_ERR_ARG,"Kernel / viscosity / DDT choice is not valid for the multiphase formulation.");
     launches+=nl;
@@ -638,7 +637,7 @@ void Engine::Step(double *stepdt,dsph_forceres *res){
 void Engine::MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi){
   if(k.periactive)throw EngineError(DSPH_ERR_ARG,"x-slab decomposition cannot be combined with periodic boundaries yet.");
   if(nranks<1 || rank<0 || rank>=nranks || xlo>=xhi || xhi>k.domcells[0])throw EngineError(DSPH_ERR_ARG,"Invalid slab configuration.");
-  if(nranks>1 && xhi-xlo<2u*unsigned(k.scelldiv)+1u)throw EngineError(DSPH_ERR_ARG,"The slab is narrower than 2 halo widths + 1 cell.");
+  if(nranks>1 && xhi-xlo<2u*MgHalo()+1u)throw EngineError(DSPH_ERR_ARG,"The slab is narrower than 2 halo widths + 1 cell.");
   mgpu=(nranks>1); mgrank=rank; mgnranks=nranks; mgxlo=xlo; mgxhi=xhi;
   dc.ghosts=(k.periactive||mgpu)? 1: 0;
   if(!mgpu)for(int i=0;i<3;i++)DevFree(mgscratch[i]);
@@ -666,7 +665,7 @@ void Engine::MgCount(unsigned counts[8]){
   for(int g=0;g<MG_CLASSES;g++)mgcounts[g]=counts[g]=0;
   mgcounted=true;
   if(!np)return;
-  MgArgs a; a.np=np; a.npb=npb; a.xlo=mgxlo; a.xhi=mgxhi; a.sd=unsigned(k.scelldiv);
+  MgArgs a; a.np=np; a.npb=npb; a.xlo=mgxlo; a.xhi=mgxhi; a.sd=MgHalo();
   a.hasleft=(mgrank>0); a.hasright=(mgrank<mgnranks-1); a.domcellcode=k.domcellcode; a.dcell=dcell[cur]; a.code=code[cur];
   // one pass: retire the halo copies of the previous divide (dropped by the next sort), classify, count per block
   ker_mg_classify<<<nb,MG_BLOCK,0,stm>>>(a,(unsigned char*)mgscratch[2],mgscratch[0]); launches++;
@@ -679,7 +678,7 @@ void Engine::MgPack(void *sendleft,void *sendright){
   if(!mgcounted)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_pack needs dsph_mgpu_count first.");
   mgcounted=false;
   const unsigned nb=(np+MG_BLOCK-1)/MG_BLOCK;
-  MgArgs a; a.np=np; a.npb=npb; a.xlo=mgxlo; a.xhi=mgxhi; a.sd=unsigned(k.scelldiv);
+  MgArgs a; a.np=np; a.npb=npb; a.xlo=mgxlo; a.xhi=mgxhi; a.sd=MgHalo();
   a.hasleft=(mgrank>0); a.hasright=(mgrank<mgnranks-1); a.domcellcode=k.domcellcode; a.dcell=dcell[cur]; a.code=code[cur];
   const unsigned *counts=mgcounts;
   void *sendbuf[2]={sendleft,sendright};

@@ -82,6 +82,9 @@ class Engine {
   unsigned *mgscratch[3]={}; unsigned mgcounts[8]={}; bool mgcounted=false;
   bool forceslaunched=false;
   void MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi);
+  // halo width in cells: 2h; 4h for the SPH velocity-gradient approach of the multiphase fork (its second pair pass reads eta_eff / tau of
+  // the neighbours: with a double halo the first pass is complete for the inner ghost layer, so no second exchange is needed)
+  unsigned MgHalo()const{ return unsigned(k.scelldiv)*(cfg.nn_on && cfg.nn_velgrad==DSPH_VELGRAD_SPH && cfg.tvisco!=DSPH_VISCO_ARTIFICIAL? 2u: 1u); }
   unsigned MgRecordBytes()const{ return sps? 112u: 88u; }   // pos 24, velrhop 16, pospre 24, velrhoppre|velrhopm1 16, idp 4, code 4 [+ SpsTau 24]
   void MgCount(unsigned counts[8]);
   void MgColumnCounts(unsigned *fluid,unsigned *bound,unsigned ncol);

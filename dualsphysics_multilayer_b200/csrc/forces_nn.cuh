@@ -292,7 +292,9 @@ ker_nn_sph_pressgrad(ForceParams t,DevCtes c,DevPhases ph)
     if(TDDT!=DSPH_DDT_NONE && s.delta!=FLT_MAX)s.ar+=s.delta;     // Deltac is folded in after all passes; it only touches ar
     t.acear[p1]=make_float4(s.ax,s.ay,s.az,s.ar);
     if(SHIFT)t.shiftposfs[p1]=a.shift;
-    viscmax=s.visc;
+    // x-slab halo copies (their neighbourhood is complete only for the inner layer) take no part in the maxima
+    const bool halo=(t.skipghosts && (code1&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_PERIODIC);
+    if(!halo)viscmax=s.visc;
     vel2=velrhop1.x*velrhop1.x+velrhop1.y*velrhop1.y+velrhop1.z*velrhop1.z;
     if(TVISCO!=DSPH_VISCO_ARTIFICIAL){
       // InteractionForcesFluid_NN_SPH_Visco_eta + GetStrainRateTensor_tsym (M/JSphCpu_NN_SPH.cpp:174-228, Tensors:184-207)
@@ -305,7 +307,7 @@ ker_nn_sph_pressgrad(ForceParams t,DevCtes c,DevPhases ph)
       const DevPhase &P=ph.ph[pp1ph];
       const float eta=NNEtaEffective(P,P.tau_yield,dmagn,P.visco,P.m_nn,P.n_nn);
       t.viscoeta[p1]=eta;
-      etamax=eta;
+      if(!halo)etamax=eta;
       if(TVISCO==DSPH_VISCO_CONSTEQ){          // GetStressTensor_sym (Tensors:211-231)
         const float t2=2.f*eta;
         float *tau=t.nntau+6*size_t(p1);
@@ -795,7 +797,8 @@ ker_nn_sph_pressgrad_ring(ForceParams t,DevCtes c,DevPhases ph)
     if(TDDT!=DSPH_DDT_NONE && !anyb)ar+=a.delta;
     t.acear[p1]=make_float4(a.ax,a.ay,a.az,ar);
     if(SHIFT){ float4 s=a.shift; if(nosh)s.x=FLT_MAX; t.shiftposfs[p1]=s; }
-    viscmax=a.visc;
+    const bool halo=(t.skipghosts && (code1&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_PERIODIC);   // x-slab halo copy: no part in the maxima
+    if(!halo)viscmax=a.visc;
     vel2=fp.velrhop.x*fp.velrhop.x+fp.velrhop.y*fp.velrhop.y+fp.velrhop.z*fp.velrhop.z;
     if(TVISCO!=DSPH_VISCO_ARTIFICIAL){
       const float div_vel=(g0+g3+g5)/3.f;
@@ -804,7 +807,7 @@ ker_nn_sph_pressgrad_ring(ForceParams t,DevCtes c,DevPhases ph)
       const float dmagn=sqrtf(II_D);
       const DevPhase &P=ph.ph[fp.ph];
       const float eta=NNEtaEffective(P,P.tau_yield,dmagn,P.visco,P.m_nn,P.n_nn);     // per particle: IEEE version
-      t.viscoeta[p1]=eta; etamax=eta;
+      t.viscoeta[p1]=eta; if(!halo)etamax=eta;
       if(TVISCO==DSPH_VISCO_CONSTEQ){
         const float t2=2.f*eta; float *tau=t.nntau+6*size_t(p1);
         tau[0]=t2*dxx; tau[1]=t2*dxy; tau[2]=t2*dxz; tau[3]=t2*dyy; tau[4]=t2*dyz; tau[5]=t2*dzz;

@@ -849,7 +849,8 @@ struct Oracle {
         }
       });
       const bool stored=(shift||a.arp1||a.acep1.x||a.acep1.y||a.acep1.z||a.visc);
-      NNStore(unsigned(p1),shift,a,vmaxall);
+      float vdummy=0;
+      NNStore(unsigned(p1),shift,a,(Mgpu && CodeIsPeriodic(Code[p1])? vdummy: vmaxall));   // halo copies do not take part in the maxima
       if(stored && TVisco!=DSPH_VISCO_ARTIFICIAL){
         sym3 &t=SpsGradvel[p1];
         t.xx+=g.xx; t.xy+=g.xy; t.xz+=g.xz; t.yy+=g.yy; t.yz+=g.yz; t.zz+=g.zz;
@@ -873,7 +874,7 @@ struct Oracle {
       const float eta=EtaEffective(pp1,Ph[pp1].tau_yield,dmagn,Ph[pp1].visco,Ph[pp1].m_nn,Ph[pp1].n_nn);
       if(eta)ViscoEta[p1]=eta;
       if(TVisco!=DSPH_VISCO_ARTIFICIAL)Dtensor[p1]=D;
-      if(eta>etamaxall)etamaxall=eta;
+      if(eta>etamaxall && !(Mgpu && CodeIsPeriodic(Code[p1])))etamaxall=eta;
     }
     viscetadt=etamaxall;
   }
@@ -950,7 +951,6 @@ struct Oracle {
   // ---- Interaction_ForcesCpuT_NN_FDA M/JSphCpu_NN_FDA.cpp:346-379, Interaction_ForcesCpuT_NN_SPH M/JSphCpu_NN_SPH.cpp:654-710
   //      (InteractionForcesBound_NN_* are the classic boundary pass with MassFluid: M/JSphCpu_NN_FDA.cpp:46-124)
   void InteractionForcesNN(float &viscdt,float &viscetadt){
-    if(Mgpu && TVelGrad==DSPH_VELGRAD_SPH)throw std::runtime_error("The SPH velocity-gradient approach is not available with x-slab decomposition.");
     if(Np>Npb){
       if(TVelGrad==DSPH_VELGRAD_FDA){
         NNForcesFluidFDA(false,viscdt,viscetadt);
@@ -1163,7 +1163,7 @@ struct Oracle {
     tl=tr=-1;
     const typecode rc=Code[p];
     if(!CodeIsNormal(rc) || Dcell[p]==0xFFFFFFFFu)return;
-    const unsigned cx=DcCellx(DomCellCode,Dcell[p]); const bool fluid=CodeIsFluid(rc); const unsigned sd=unsigned(ScellDiv);
+    const unsigned cx=DcCellx(DomCellCode,Dcell[p]); const bool fluid=CodeIsFluid(rc); const unsigned sd=MgHalo();
     // kinds: 0 boundary ghost, 1 boundary migrant (only after the cuts moved: re-balancing), 2 fluid migrant, 3 fluid ghost
     if(MgRank>0){ if(cx<MgXlo)tl=(fluid? 2: 1); else if(cx<MgXlo+sd)tl=(fluid? 3: 0); }
     if(MgRank<MgNranks-1){ if(cx>=MgXhi)tr=(fluid? 2: 1); else if(cx+sd>=MgXhi)tr=(fluid? 3: 0); }
@@ -1190,11 +1190,14 @@ struct Oracle {
       if(cx<ncol){ if(CodeIsFluid(rc))fluid[cx]++; else bound[cx]++; }
     }
   }
+  // halo width in cells: 2h, or 4h for the SPH velocity-gradient approach of the multiphase fork, whose second pair pass reads
+  // eta_eff / tau of the neighbours: with a double halo the first pass is complete for the inner ghost layer (no second exchange)
+  unsigned MgHalo()const{ return unsigned(ScellDiv)*(MultiPhase && TVelGrad==DSPH_VELGRAD_SPH && TVisco!=DSPH_VISCO_ARTIFICIAL? 2u: 1u); }
   bool MgSps()const{ return TVisco==DSPH_VISCO_LAMINARSPS && !MultiPhase; }     // SpsTau is particle state: it travels with the record
   unsigned MgRecordBytes()const{ return unsigned(sizeof(MgRecord))+(MgSps()? 24u: 0u); }
   void MgPack(void *sendleft,void *sendright){
     char *out[2]={(char*)sendleft,(char*)sendright};
-    const unsigned sd=unsigned(ScellDiv), rb=MgRecordBytes();
+    const unsigned sd=MgHalo(), rb=MgRecordBytes();
     for(int d=0;d<2;d++){
       unsigned base=0;
       for(int kd=0;kd<4;kd++){

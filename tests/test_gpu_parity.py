@@ -240,7 +240,7 @@ def test_gpu_large_case_properties(gpu_lib):
 
 
 @pytest.mark.parametrize("kind", ["dambreak", "nn2layer", "dambreak:tstep=1,verletsteps=5,tvisco=2,visco=0.01,shiftmode=3,shiftcoef=-2",
-                                  "dambreak@rebalance", "nn2layer@rebalance"])
+                                  "dambreak@rebalance", "nn2layer@rebalance", "nn2layer:nn_velgrad=2", "nn2layer:nn_velgrad=2,tvisco=3"])
 def test_gpu_two_slabs_equal_single_gpu(kind):
     """x-slab decomposition over 2 GPUs (NCCL send/recv halos + all-reduce dt) reproduces the single-GPU run."""
     import subprocess, sys, os, torch

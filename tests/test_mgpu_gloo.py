@@ -67,7 +67,8 @@ def _worker(rank, world, port, kind, npart, nsteps, outdir):
 
 
 @pytest.mark.parametrize("kind,npart,nsteps", [("dambreak", 6000, 12), ("dambreak:tstep=1,verletsteps=5,shiftmode=3,shiftcoef=-2,tvisco=2,visco=0.01", 6000, 12),
-                                               ("nn2layer", 6000, 10), ("dambreak@rebalance", 6000, 12),
+                                               ("nn2layer", 6000, 10), ("nn2layer:nn_velgrad=2", 6000, 10), ("nn2layer:nn_velgrad=2,tvisco=3", 6000, 10),
+                                               ("dambreak@rebalance", 6000, 12),
                                                ("dambreak:tstep=1,verletsteps=5,tvisco=2,visco=0.01@rebalance", 6000, 12)])
 def test_two_slabs_equal_single_domain(tmp_path, oracle_lib, kind, npart, nsteps):
     world = 2
