@@ -156,6 +156,18 @@ def create_context(cd_or_cfg, np_capacity: int = 0, device: int = 0) -> SphConte
     return SphContext(lib(), cfg, np_capacity, device)
 
 
-def run_case(dirname: str, casename: str, dirout: str, device: int = 0, nsteps: int = 0, savepart: bool = True) -> None:
+class _RunOpts(C.Structure):
+    _fields_ = [("dir", C.c_char_p), ("casename", C.c_char_p), ("dirout", C.c_char_p),
+                ("device", C.c_int32), ("nsteps", C.c_int32), ("savepart", C.c_int32), ("forcevariant", C.c_int32),
+                ("timemax", C.c_double), ("timeout", C.c_double), ("restart", C.c_int32), ("partbegin", C.c_int32),
+                ("partbegindir", C.c_char_p)]
+
+
+def run_case(dirname: str, casename: str, dirout: str, device: int = 0, nsteps: int = 0, savepart: bool = True,
+             timemax: float = -1.0, timeout: float = -1.0, partbegin: int = -1, partbegindir: str = None) -> None:
+    """The stand-alone driver (dsph_run_case_ex): Case.xml + Case.bi4 in, Part_NNNN.bi4 / Run.out / Run.csv out."""
     L = lib()
-    L.check(L.lib.dsph_run_case(dirname.encode(), casename.encode(), dirout.encode(), device, nsteps, 1 if savepart else 0))
+    o = _RunOpts(dirname.encode(), casename.encode(), dirout.encode(), device, nsteps, 1 if savepart else 0, 0,
+                 timemax, timeout, 1 if partbegin >= 0 else 0, max(partbegin, 0), partbegindir.encode() if partbegindir else None)
+    L.lib.dsph_run_case_ex.argtypes = [C.POINTER(_RunOpts)]
+    L.check(L.lib.dsph_run_case_ex(C.byref(o)))

@@ -207,6 +207,15 @@ int dsph_part_load(dsph_case *out,const char *file,double *timestep,uint32_t *st
   });
   return r==DSPH_OK? r: DSPH_ERR_IO;
 }
+int dsph_run_case_ex(const dsph_runopts *r){
+  if(!r||!r->dir||!r->casename||!r->dirout){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  return Guard([&]{
+    RunOptions o; o.dir=r->dir; o.casename=r->casename; o.dirout=r->dirout; o.device=r->device; o.nsteps=r->nsteps; o.savepart=(r->savepart!=0);
+    o.timemax=r->timemax; o.timeout=r->timeout; o.forcevariant=r->forcevariant;
+    o.partbegin=(r->restart? r->partbegin: -1); if(r->partbegindir)o.partbegindir=r->partbegindir;
+    RunCase(o);
+  });
+}
 int dsph_run_case(const char *dir,const char *casename,const char *dirout,int device,int nsteps,int savepart){
   if(!dir||!casename||!dirout){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
   return Guard([&]{ RunOptions o; o.dir=dir; o.casename=casename; o.dirout=dirout; o.device=device; o.nsteps=nsteps; o.savepart=(savepart!=0); RunCase(o); });

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <cmath>
+#include <algorithm>
 #include <vector>
 #include <thread>
 #include <mutex>
@@ -147,23 +148,40 @@ RunSummary RunCase(const RunOptions &opt){
   dsph_config &c=cd.cfg;
   if(opt.timemax>0)c.timemax=opt.timemax;
   if(opt.timeout>0)c.timeout=opt.timeout;
+  double timestep=0; unsigned part=0; double restartdtpre=0;
+  if(opt.partbegin>=0){
+    // restart: particle state, time and the Symplectic dt of the next step come from a PART file of a previous run
+    // (JPartsLoad4::LoadParticles with partbegin + JSph::RestartCheckData, S/JSph.cpp:2005-2040); excluded particles stay excluded
+    PartHead ph; PartData pd;
+    const std::string dirb=(opt.partbegindir.empty()? opt.dirout: opt.partbegindir);
+    LoadPartFile(dirb+"/"+PartFileName(unsigned(opt.partbegin)),ph,pd,unsigned(opt.partbegin));
+    if(ph.casenp!=c.casenp || ph.casenfixed!=c.casenfixed || ph.casenfluid!=c.casenfluid)throw std::runtime_error("The PART file of -partbegin does not belong to this case.");
+    cd.idp=pd.idp; cd.pos=pd.pos; cd.velrhop.resize(size_t(pd.npok)*4);
+    for(unsigned i=0;i<pd.npok;i++){ cd.velrhop[4*i]=pd.vel[3*i]; cd.velrhop[4*i+1]=pd.vel[3*i+1]; cd.velrhop[4*i+2]=pd.vel[3*i+2]; cd.velrhop[4*i+3]=pd.rhop[i]; }
+    timestep=pd.timestep; part=unsigned(opt.partbegin); restartdtpre=pd.symplecticdtpre;
+    log.Printf("Restart from %s/%s: TimeStep=%.9g  np=%u",dirb.c_str(),PartFileName(part).c_str(),timestep,pd.npok);
+  }
   const unsigned np0=cd.np();
-  unsigned capacity=np0+np0/20+1024;
+  unsigned capacity=std::max(np0,c.casenp)+c.casenp/20+1024;
   if(c.perix||c.periy||c.periz)capacity=unsigned(np0*1.7)+65536;
   Engine eng(opt.device,c,capacity);
   if(opt.forcevariant)eng.forcevariant=opt.forcevariant;
   log.Printf("Particles: np=%u nbound=%u nfluid=%u  dp=%g h=%g cs0=%g  cells(map)=%ux%ux%u",np0,c.casenfixed,c.casenfluid,c.dp,double(c.kernelh),eng.k.cs0,eng.k.mapcells[0],eng.k.mapcells[1],eng.k.mapcells[2]);
   std::vector<typecode> code(np0); ComputeCodes(cd,np0,cd.idp.data(),code.data());
-  eng.Upload(np0,cd.npb(),cd.idp.data(),code.data(),cd.pos.data(),cd.velrhop.data());
+  unsigned npb0=0; for(unsigned i=0;i<np0;i++)if(cd.idp[i]<c.casenfixed+c.casenmoving)npb0++;     // boundary ids come first (CheckSortParticles)
+  eng.Upload(np0,npb0,cd.idp.data(),code.data(),cd.pos.data(),cd.velrhop.data());
+  if(restartdtpre>0)eng.symplecticdtpre=restartdtpre;
   dsph_divinfo di; eng.CellDivide(true,&di);
-  double timestep=0; unsigned part=0; unsigned long long nstep=0;
+  unsigned long long nstep=0;
   const auto t0=std::chrono::steady_clock::now();
   auto Elapsed=[&]{ return std::chrono::duration<double>(std::chrono::steady_clock::now()-t0).count(); };
   const std::vector<double> probes=LoadPoints(opt.dir+"/"+opt.casename+"_Points.txt");
   if(!probes.empty())log.Printf("Probe points: %u (%s_Points.txt) -> MeasurePoints.csv",unsigned(probes.size()/3),opt.casename.c_str());
   PartWriter writer;
-  if(opt.savepart)SavePart(eng,cd,opt.dirout,part,timestep,0,0,0,log,writer);
-  SaveProbes(eng,probes,opt.dirout,part,timestep);
+  if(opt.partbegin<0){
+    if(opt.savepart)SavePart(eng,cd,opt.dirout,part,timestep,0,0,0,log,writer);
+    SaveProbes(eng,probes,opt.dirout,part,timestep);
+  }
   part++;
   double timepartnext=NextTime(timestep,c.timeout);
   eng.GetTimers(nullptr,true);

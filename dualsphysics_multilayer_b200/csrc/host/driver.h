@@ -11,6 +11,8 @@ struct RunOptions {
   double timemax=-1;     // >0 overrides TimeMax (reference option -tmax)
   double timeout=-1;     // >0 overrides TimeOut (reference option -tout)
   int forcevariant=0;    // 0: default
+  int partbegin=-1;      // >=0: restart from <partbegindir>/Part_NNNN.bi4 (reference option -partbegin:N dir, S/JSph.cpp:2005-2040)
+  std::string partbegindir;
 };
 struct RunSummary { unsigned np0=0; unsigned long long steps=0; double simtime=0, runtime_s=0, mpartsteps_s=0; unsigned parts=0; unsigned long long npout=0; };
 RunSummary RunCase(const RunOptions &opt);

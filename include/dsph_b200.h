@@ -273,6 +273,18 @@ int dsph_part_load(dsph_case *out,const char *file,double *timestep,uint32_t *st
  *      <dir>/<casename>.xml+.bi4, runs to TimeMax (or nsteps>0), writes Part_NNNN.bi4, Run.out, Run.csv
  *      into dirout. ---------------------------------------------------------------------------- */
 int dsph_run_case(const char *dir,const char *casename,const char *dirout,int device,int nsteps,int savepart);
+/* the same with the remaining command-line options of the reference that concern this path (R/doc/help/DualSPHysics5.2_Help.out):
+ * -tmax, -tout, -partbegin:N dir (restart from dir/Part_NNNN.bi4: particle state, time and the Symplectic dt of the next
+ * step, S/JSph.cpp:2005-2040).  Zero-initialise, then set what is needed: timemax/timeout <= 0 keep the XML values,
+ * restart = 0 starts from Case.bi4 (partbegin is ignored), partbegindir NULL = dirout. */
+typedef struct dsph_runopts {
+  const char *dir, *casename, *dirout;
+  int32_t device, nsteps, savepart, forcevariant;
+  double timemax, timeout;
+  int32_t restart, partbegin;
+  const char *partbegindir;
+} dsph_runopts;
+int dsph_run_case_ex(const dsph_runopts *opts);
 
 #ifdef __cplusplus
 }
