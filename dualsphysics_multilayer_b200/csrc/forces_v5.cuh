@@ -8,10 +8,14 @@
 //          lane's own 64-deep ring in shared memory (q[slot][lane]: conflict free, 32 KB per 128-thread block),
 //   PAIR   when some lane's ring is nearly full every lane pops one entry, re-reads posp/velrhop of that neighbour (L1/L2
 //          hits), rebuilds dr with exactly the operations of the test and runs the division-free pair body.
-// A ring of 64 evens out the bursts (tools/simq.py: 227 rounds per warp with 24.5 lanes active instead of 620 with 8.9).
+// The ring evens out the bursts (tools/simq.py: 227 rounds per warp with 24.5 lanes active at 64 slots, 282 at 32 slots, instead of
+// 620 immediate executions with 8.9 lanes).  Production is the 32-slot ring (variant 6): 16 KB of shared memory per CTA lets 8
+// CTAs (32 warps) share an SM, which is worth more than the deeper ring once the candidate test is lean (profiles/r01_forces.md).
 // The ring is FIFO per lane, so the summation order per particle is the oracle's and the result is bit-identical to
 // variant 4.  Control flow is warp uniform (fixed 3x3x3 cell loops, trip counts by redux.sync) so that the votes are legal.
-// Limits: cells of size 2h (ScellDiv=1) and np < 2^26 per GPU; otherwise variant 4 is used.
+// Candidate test: chunks of 8 unrolled loads from the padded posp array (no index clamp); when every lane has a full chunk the
+// range check is skipped; the ALMOSTZERO exclusion lives in the pair body as a zero-mass pair (no branch between the two
+// neighbour loads).  Limits: cells of size 2h (ScellDiv=1) and np < 2^26 per GPU; otherwise variant 4 is used.
 #pragma once
 #include "forces_fast.cuh"
 
