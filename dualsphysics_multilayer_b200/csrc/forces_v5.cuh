@@ -5,7 +5,7 @@
 // lanes only; 620 body executions per warp for 173 accepted pairs per particle).  Here the body is deferred:
 //   TEST   the broadcast candidate loop of variant 4 (one thread per particle, oracle pair order) only tests the distance and
 //          pushes accepted neighbours as 4-byte entries {particle index : 26 bits | neighbour-cell code : 6 bits} into the
-//          lane's own 64-deep ring in shared memory (q[slot][lane]: conflict free, 32 KB per 128-thread block),
+//          lane's own ring in shared memory (q[slot][lane]: conflict free; 32 or 64 slots = 16 or 32 KB per 128-thread block),
 //   PAIR   when some lane's ring is nearly full every lane pops one entry, re-reads posp/velrhop of that neighbour (L1/L2
 //          hits), rebuilds dr with exactly the operations of the test and runs the division-free pair body.
 // The ring evens out the bursts (tools/simq.py: 227 rounds per warp with 24.5 lanes active at 64 slots, 282 at 32 slots, instead of
