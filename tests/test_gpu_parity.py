@@ -302,3 +302,35 @@ def test_gpu_option_matrix_vs_oracle(gpu_lib, oracle_lib, kind, opts):
     assert rl2(acea[npb:], aceb[npb:]) <= 1e-5 and rl2(ara, arb) <= 1e-5, (rl2(acea[npb:], aceb[npb:]), rl2(ara, arb))
     assert abs(fa.dt - fb.dt) <= 1e-5 * fb.dt
     a.close(); b.close(); b2.close()
+
+
+@pytest.mark.parametrize("tstep", [capi.STEP_SYMPLECTIC, capi.STEP_VERLET])
+def test_gpu_excluded_particles_match_oracle(gpu_lib, oracle_lib, tstep):
+    """Particles that leave: displacement above MovLimit (OUTMOVE), density outside RhopOut (OUTRHOP), position outside the map
+    (OUTPOS).  The divide must drop the same particles on both sides (S/JSphCpu.cpp:1240-1293, S/JCellDivCpuSingle.cpp:134-194)."""
+    cd = dsph.make_case("dambreak", 6000)
+    cd.cfg.tstep = tstep
+    a, b = _both(gpu_lib, oracle_lib, cd)
+    a.celldiv(True); b.celldiv(True)
+    for _ in range(2):
+        a.step(); b.step()
+    st = b.download()
+    fl = np.nonzero((st["code"] & capi.CODE_MASKTYPE) == capi.CODE_TYPE_FLUID)[0]
+    vr = st["velrhop"].copy(); pos = st["pos"].copy()
+    vr[fl[10], 0] = 5.0e4                                  # moves more than 0.9*Scell in one step
+    vr[fl[200], 3] = 5000.0                                # density out of [700,1300]
+    zmax = float(cd.cfg.maprealposmax[2])
+    pos[fl[400], 2] = zmax - 1e-7; vr[fl[400], 2] = 80.0   # crosses the top of the map
+    for c in (a, b):
+        c.upload(st["idp"], pos, vr, b.npb, st["code"])
+        c.celldiv(True)
+    n0 = b.np_
+    for s in range(3):
+        a.step(); b.step()
+        sa, sb = a.download(), b.download()
+        assert a.np_ == b.np_, ("np after step %d" % s, a.np_, b.np_)
+        assert np.array_equal(sa["idp"], sb["idp"]) and np.array_equal(sa["code"], sb["code"])
+    assert n0 - b.np_ >= 3, (n0, b.np_)          # the three tagged particles (and whatever the density spike blew away) are gone
+    gone = set(st["idp"][[fl[10], fl[200], fl[400]]].tolist())
+    assert gone.isdisjoint(set(sb["idp"].tolist()))
+    a.close(); b.close()
