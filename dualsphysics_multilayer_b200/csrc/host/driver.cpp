@@ -162,6 +162,11 @@ RunSummary RunCase(const RunOptions &opt){
     log.Printf("Restart from %s/%s: TimeStep=%.9g  np=%u",dirb.c_str(),PartFileName(part).c_str(),timestep,pd.npok);
   }
   const unsigned np0=cd.np();
+  // JSph::CheckRhopLimits (S/JSph.cpp:2021-2030): the initial density of every fluid particle must be inside RhopOut
+  if(c.rhopoutmin<c.rhopoutmax)for(unsigned i=0;i<np0;i++)if(cd.idp[i]>=c.casenfixed+c.casenmoving+c.casenfloat){
+    const float r=cd.velrhop[4*size_t(i)+3];
+    if(r<c.rhopoutmin || c.rhopoutmax<r)throw std::runtime_error("Initial fluid density is out of limits. *** To change the limits modify the value of 'RhopOutMin' and 'RhopOutMax' in the XML file (parameters section).");
+  }
   unsigned capacity=std::max(np0,c.casenp)+c.casenp/20+1024;
   if(c.perix||c.periy||c.periz)capacity=unsigned(np0*1.7)+65536;
   Engine eng(opt.device,c,capacity);

@@ -47,13 +47,26 @@ CASES = [
     ("db2d_ver_cubic_lamsps_ddt1", "dambreak2d", 3000, ["tstep=1", "tkernel=1", "tvisco=2", "visco=0.01", "ddt=1", "verletsteps=10"], [25], 26),
     ("nn2d_sym_sph_lam_ddt3_shift", "nn2layer2d", 3000, ["tstep=2", "tkernel=2", "velgrad=2", "tvisco=2", "ddt=3", "shifting=3"], [25], 26),
     ("nn2d_sym_fda_conseq_ddt2", "nn2layer2d", 3000, ["tstep=2", "tkernel=2", "velgrad=1", "tvisco=3", "ddt=2", "shifting=0"], [25], 26),
+    # particles leaving: a RhopOut window just above the initial hydrostatic maximum excludes 4 / 20 / 146 particles by steps 10 / 20 / 40 (OUTRHOP marking in
+    # the step update, special boxes of the divide, NpfOut bookkeeping); options after "xml:" patch <parameter> values of Case.xml
+    ("db_sym_wend_art_ddt2_rhopout", "dambreak", 3000, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2", "xml:RhopOutMax=1002.14", "xml:RhopOutMin=999.2"], [10, 20, 40], 41),
+    ("db_ver_wend_art_ddt1_rhopout", "dambreak", 3000, ["tstep=1", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=1", "verletsteps=3", "xml:RhopOutMax=1002.14", "xml:RhopOutMin=999.2"], [12, 30], 31),
 ]
 
 
 def run(name, kind, nptarget, opts, steps, nsteps, outdir):
     tmp = tempfile.mkdtemp(prefix="golden_")
     try:
-        subprocess.check_call([MKCASE, kind, str(nptarget), tmp, "Case"] + opts, stdout=subprocess.DEVNULL)
+        subprocess.check_call([MKCASE, kind, str(nptarget), tmp, "Case"] + [o for o in opts if not o.startswith("xml:")], stdout=subprocess.DEVNULL)
+        xmlfile = os.path.join(tmp, "Case.xml")
+        xml = open(xmlfile).read()
+        for o in opts:
+            if o.startswith("xml:"):
+                k, v = o[4:].split("=")
+                import re
+                xml, n = re.subn(r'(<parameter key="%s" value=")[^"]*(")' % k, r"\g<1>%s\g<2>" % v, xml)
+                assert n == 1, "parameter %s not found in Case.xml" % k
+        open(xmlfile, "w").write(xml)
         cmd = [HARNESS_NN if kind.startswith("nn2layer") else HARNESS, "Case", "out", "-cpu", "-ompthreads:1", "-sv:none", "-hdir:" + os.path.join(tmp, "dump"),
                "-hsteps:" + ",".join(str(s) for s in steps), "-hnsteps:%d" % nsteps]
         cmd += ["-cellmode:half"] if "cellmode=2" in opts else []
