@@ -242,6 +242,9 @@ int dsph_mgpu_unpack(dsph_ctx *ctx,const uint32_t counts[8],const void *recv_lef
 int dsph_mgpu_column_counts(dsph_ctx *ctx,uint32_t *fluid,uint32_t *bound,uint32_t ncol);
 int dsph_forces_launch(dsph_ctx *ctx,int interstep);
 void* dsph_forces_maxima_ptr(dsph_ctx *ctx);
+/* the CUDA stream (cudaStream_t) every kernel of this context is launched on: lets the caller order its collective after
+ * dsph_forces_launch and before dsph_forces_finish with stream waits instead of a device-wide synchronisation */
+void* dsph_cuda_stream(dsph_ctx *ctx);
 int dsph_forces_finish(dsph_ctx *ctx,dsph_forceres *res);
 /* domain constants needed to place the cuts: cell size, origin and number of cell columns (JSph::ConfigCellDivision) */
 int dsph_domain_info(const dsph_config *cfg,double *scell,double domposmin[3],uint32_t domcells[3]);
