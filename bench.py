@@ -162,7 +162,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--np", type=int, default=20_000_000, help="particles per GPU (DB(N))")
+    ap.add_argument("--np", "--particles", dest="np", type=int, default=20_000_000, help="particles per GPU (DB(N))")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pre-steps", type=int, default=0, help="untimed steps before warm-up (to leave the initial lattice)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -173,6 +173,7 @@ def main():
                     help="DB(N) is the headline (BASELINE.json); PB(N) and NN(N) are the other single-GPU configs of SURVEY.md 8(d)")
     ap.add_argument("--profile-mgpu", action="store_true", help="N>1: 3 extra untimed steps with per-phase host timers (adds syncs)")
     ap.add_argument("--bound-weight", type=float, default=0.05, help="N>1: cost of a boundary particle relative to a fluid one when balancing the slabs")
+    ap.add_argument("--balance-steps", type=int, default=3, help="N>1: untimed steps before warm-up, each followed by SlabDriver.rebalance with the measured per-rank kernel time")
     a = ap.parse_args()
     # stdout carries exactly ONE line (the JSON): everything else any library prints (e.g. NCCL's
     # version banner) goes to stderr; the JSON is written to the saved descriptor at the end.
@@ -268,6 +269,15 @@ def main():
         nglobal = int(info.cfg.casenp)
     for _ in range(a.pre_steps):
         stepfn()
+    cuts_initial = list(drv.cuts) if drv is not None else None
+    if drv is not None:
+        # dynamic load balance (setup, untimed): the static weights cannot know that free-surface and wall particles have fewer
+        # neighbours; move the cuts with the measured device time of every rank's own kernels, as a production run does every k steps
+        for _ in range(a.balance_steps):
+            drv.measured_cost()
+            stepfn()
+            if drv.rebalance(bound_weight=a.bound_weight, rank_cost=drv.measured_cost()):
+                drv.celldiv()
 
     def barrier():
         if world > 1:
@@ -421,7 +431,7 @@ def main():
                "config": {"workload": WORKLOADS[a.workload][1],
                           "np_per_gpu": n, "nfluid": int(cd.cfg.casenfluid), "pre_steps": a.pre_steps,
                           "np_global": nglobal,
-                          "parallelism": ("single GPU" if world == 1 else "%d x-slabs of balanced work (fluid 1, boundary %g); per divide: NCCL send/recv of migrants + 2h halo copies with <=2 neighbours; per force evaluation: all-reduce(max) of the dt maxima" % (world, a.bound_weight)),
+                          "parallelism": ("single GPU" if world == 1 else "%d x-slabs of balanced work (fluid 1, boundary %g); per divide: NCCL send/recv of migrants + 2h halo copies with <=2 neighbours; per force evaluation: all-reduce(max) of the dt maxima; cuts re-balanced %d times with the measured kernel time per rank before warm-up (%s -> %s)" % (world, a.bound_weight, a.balance_steps, cuts_initial, list(drv.cuts))),
                           "l2": "working set (np*~230 B) is far larger than the 126 MB L2; no flush needed"},
                "roofline": roofline, "e2e": e2e, "gpu_launches": int(tm.kernel_launches), "clocks": sampler.result(),
                "timers_ms_per_step": {k: getattr(tm, k) / a.steps for k in ("nl_limits", "nl_presort", "nl_radixsort", "nl_cellbegin", "nl_sortdata",

@@ -59,6 +59,7 @@ class SlabDriver:
         ptr = ctx.forces_maxima_ptr()
         if self.device.type == "cuda":
             self.maxima = torch.as_tensor(_CudaView(ptr, 4, "<i4"), device=self.device)
+            self._libstream = torch.cuda.ExternalStream(int(ctx.lib.lib.dsph_cuda_stream(ctx.h)), device=self.device)
         else:
             self.maxima = torch.from_numpy(np.ctypeslib.as_array((C.c_int32 * 4).from_address(ptr)))
         self.sent_records = 0
@@ -132,11 +133,15 @@ class SlabDriver:
         return t
 
     # ---- re-balancing: move the cuts to the current particle distribution ------------------------------------------
-    def rebalance(self, bound_weight=0.05, minwidth=None):
+    def rebalance(self, bound_weight=0.05, minwidth=None, rank_cost=None):
         """Collective.  New cuts from the global per-column histogram of owned particles (fluid 1, boundary bound_weight).
         A cut moves by less than the width of the narrower of its two slabs, so every particle changes owner by at most
         one rank; the next exchange migrates fluid AND boundary particles that are outside the new range and rebuilds the
-        halos.  Returns True when the cuts changed."""
+        halos.  Returns True when the cuts changed.
+        rank_cost (optional, one number per call and rank, e.g. `measured_cost()`): the measured cost of this rank's own
+        work since the last call.  The columns of every slab are then scaled so that they add up to the slab's measured
+        cost: the particle histogram only distributes the cost inside a slab, the measurement decides between slabs
+        (free-surface and wall particles have fewer neighbours than interior ones, which no static weight captures)."""
         if self.world == 1:
             return False
         ctx = self.ctx
@@ -145,6 +150,17 @@ class SlabDriver:
         w = torch.from_numpy(fl.astype(np.float64) + bound_weight * bd.astype(np.float64)).to(self.device)
         dist.all_reduce(w, op=dist.ReduceOp.SUM, group=self.group)
         hist = w.cpu().numpy()
+        if rank_cost is not None:
+            costs = torch.zeros(self.world, dtype=torch.float64, device=self.device)
+            costs[self.rank] = float(rank_cost)
+            dist.all_reduce(costs, op=dist.ReduceOp.SUM, group=self.group)
+            costs = costs.cpu().numpy()
+            if np.all(costs > 0):
+                for r in range(self.world):
+                    seg = hist[self.cuts[r]:self.cuts[r + 1]]
+                    tot = seg.sum()
+                    if tot > 0:
+                        seg *= costs[r] / tot
         sd = 2 if int(ctx.cfg.cellmode) == 2 else 1          # DSPH_CELLMODE_HALF: cells of h, halo = 2 cells
         if minwidth is None:
             minwidth = 2 * sd + 1
@@ -163,6 +179,14 @@ class SlabDriver:
         ctx.mgpu_config(self.rank, self.world, new[self.rank], new[self.rank + 1])
         return True
 
+    def measured_cost(self):
+        """Device milliseconds of this rank's own kernels (cell division, forces, updates: the CUDA-event timers of the
+        context) since the last call; waiting for the neighbours is not part of it."""
+        tm = capi.Timers()
+        self.ctx.lib.lib.dsph_get_timers(self.ctx.h, C.byref(tm), 1)
+        return (tm.nl_limits + tm.nl_presort + tm.nl_radixsort + tm.nl_cellbegin + tm.nl_sortdata + tm.nl_outcheck +
+                tm.cf_preforces + tm.cf_forces + tm.su_computestep + tm.su_periodic + tm.su_shifting)
+
     # ---- the step pieces (same sequence as JSphGpuSingle::ComputeStep_Sym/_Ver + closing divide) -------------------
     def celldiv(self):
         self.exchange()
@@ -177,11 +201,14 @@ class SlabDriver:
         t0 = self._tick("forces_kernels", t0)
         if self.world > 1:
             if self.device.type == "cuda":
-                # the library launched on its own stream: make torch's stream wait for it through a device-wide sync
-                torch.cuda.synchronize()
-            dist.all_reduce(self.maxima, op=dist.ReduceOp.MAX, group=self.group)
-            if self.device.type == "cuda":
-                torch.cuda.synchronize()
+                # the library launched on its own stream (dsph_cuda_stream): order the collective after the force kernels and
+                # the read-back of dsph_forces_finish after the collective with stream waits, no device-wide synchronisation
+                cur = torch.cuda.current_stream(self.device)
+                cur.wait_stream(self._libstream)
+                dist.all_reduce(self.maxima, op=dist.ReduceOp.MAX, group=self.group)
+                self._libstream.wait_stream(cur)
+            else:
+                dist.all_reduce(self.maxima, op=dist.ReduceOp.MAX, group=self.group)
         t0 = self._tick("dt_allreduce", t0)
         return self.ctx.forces_finish()
 

@@ -22,7 +22,7 @@ def _free_port():
 def _make(kind, npart):
     """kind may carry options: 'dambreak:tstep=1,shiftmode=3' (Verlet + shifting), 'nn2layer' (multiphase FDA)."""
     import dualsphysics_multilayer_b200 as dsph
-    base, _, opts = kind.replace("@rebalance", "").partition(":")
+    base, _, opts = kind.replace("@rebalancecost", "").replace("@rebalance", "").partition(":")
     cd = dsph.make_case(base, npart)
     for kv in filter(None, opts.split(",")):
         k, v = kv.split("=")
@@ -43,7 +43,8 @@ def _worker(rank, world, port, kind, npart, nsteps, outdir):
     scell, dmin, dcells = ctx.domain_info()
     cx = ((cd.pos[:, 0] - dmin[0]) / scell).astype(np.int64)
     cuts = mgpu.balanced_cuts(np.bincount(cx, minlength=dcells[0]), world, 3)
-    rebalance = kind.endswith("@rebalance")
+    rebalance = kind.endswith("@rebalance") or kind.endswith("@rebalancecost")
+    withcost = kind.endswith("@rebalancecost")
     if rebalance:                                   # start from deliberately bad cuts; rebalance() must walk them back
         cuts = [cuts[0]] + [min(c + 4, dcells[0] - 3 * (world - i)) for i, c in enumerate(cuts[1:-1], 1)] + [cuts[-1]]
     sel = mgpu.slab_select(cd.pos[:, 0], cuts, rank, scell, dmin[0])
@@ -56,7 +57,9 @@ def _worker(rank, world, port, kind, npart, nsteps, outdir):
     for s in range(nsteps):
         if rebalance and s % 3 == 2:
             # between two steps the last divide is done: move the cuts, exchange (migrates fluid + boundary), divide again
-            if drv.rebalance(bound_weight=0.3):
+            # @rebalancecost: a measured cost per rank (here synthetic: rank 1 pays twice as much per particle) scales the histogram
+            cost = (ctx.np_ * (1.0 + rank)) if withcost else None
+            if drv.rebalance(bound_weight=0.3, rank_cost=cost):
                 moved += 1
                 drv.celldiv()
         dt, _ = drv.step()
@@ -68,7 +71,7 @@ def _worker(rank, world, port, kind, npart, nsteps, outdir):
 
 @pytest.mark.parametrize("kind,npart,nsteps", [("dambreak", 6000, 12), ("dambreak:tstep=1,verletsteps=5,shiftmode=3,shiftcoef=-2,tvisco=2,visco=0.01", 6000, 12),
                                                ("nn2layer", 6000, 10), ("nn2layer:nn_velgrad=2", 6000, 10), ("nn2layer:nn_velgrad=2,tvisco=3", 6000, 10),
-                                               ("dambreak@rebalance", 6000, 12),
+                                               ("dambreak@rebalance", 6000, 12), ("dambreak@rebalancecost", 6000, 12),
                                                ("dambreak:tstep=1,verletsteps=5,tvisco=2,visco=0.01@rebalance", 6000, 12)])
 def test_two_slabs_equal_single_domain(tmp_path, oracle_lib, kind, npart, nsteps):
     world = 2
@@ -97,7 +100,7 @@ def test_two_slabs_equal_single_domain(tmp_path, oracle_lib, kind, npart, nsteps
     den = np.linalg.norm(st["velrhop"][o2].astype(np.float64))
     assert np.linalg.norm((vr[o1] - st["velrhop"][o2]).astype(np.float64)) / den < 1e-6
     assert sum(int(p["sent"]) for p in parts) > 0, "the slabs must have exchanged halo particles"
-    if kind.endswith("@rebalance"):
+    if "@rebalance" in kind:
         assert all(int(p["moved"]) > 0 for p in parts), "the cuts must have moved"
         print("cuts after re-balancing:", parts[0]["cuts"])
 
