@@ -9,13 +9,18 @@
 //   PAIR   when some lane's ring is nearly full every lane pops one entry, re-reads posp/velrhop of that neighbour (L1/L2
 //          hits), rebuilds dr with exactly the operations of the test and runs the division-free pair body.
 // The ring evens out the bursts (tools/simq.py: 227 rounds per warp with 24.5 lanes active at 64 slots, 282 at 32 slots, instead of
-// 620 immediate executions with 8.9 lanes).  Production is the 32-slot ring (variant 6): 16 KB of shared memory per CTA lets 8
+// 620 immediate executions with 8.9 lanes).  Production is the 32-slot ring (variants 6 and 7): 16 KB of shared memory per CTA lets 8
 // CTAs (32 warps) share an SM, which is worth more than the deeper ring once the candidate test is lean (profiles/r01_forces.md).
 // The ring is FIFO per lane, so the summation order per particle is the oracle's and the result is bit-identical to
 // variant 4.  Control flow is warp uniform (fixed 3x3x3 cell loops, trip counts by redux.sync) so that the votes are legal.
 // Candidate test: chunks of 8 unrolled loads from the padded posp array (no index clamp); when every lane has a full chunk the
 // range check is skipped; the ALMOSTZERO exclusion lives in the pair body as a zero-mass pair (no branch between the two
 // neighbour loads).  Limits: cells of size 2h (ScellDiv=1) and np < 2^26 per GPU; otherwise variant 4 is used.
+// Variant 7 (OPT=1, production) is variant 6 with fewer issue slots around the same arithmetic (37.07 -> 34.12 ms at 20 M, bit-identical):
+// ring slots addressed by one LOP3 (OR instead of AND+ADD, the ring base folded into the ld/st offset), the pushed word kept as a
+// loop variable (index | cell code, +u per candidate), the neighbour-cell offsets of the pair body read from a 1 KB shared table
+// (LDS.128 + 3 FADD instead of 13 shift/convert instructions), the lane's ring offset pinned in a register, and the full chunks of
+// a cell counted once (CREDUX.MIN) instead of a vote per chunk.
 #pragma once
 #include "forces_fast.cuh"
 
@@ -35,17 +40,64 @@ __device__ __forceinline__ unsigned V5Pop(unsigned qaddr,unsigned byteoff){
   unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(qaddr+byteoff) : "memory"); return v;
 }
 
-template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __device__ __forceinline__ void V5Round(
+// OPT=1 (variant 7).  The ring of a CTA is the only static shared array besides the 1 KB offset table behind it, so it starts
+// at V5_SMEM0 (the first byte after the 1 KB the system reserves per CTA; checked at kernel entry, trap otherwise) and is
+// 16 KB-aligned relative to that: slot address = ((tail & mask) | lane part) + V5_SMEM0 = ONE LOP3 with the constant folded
+// into the ld/st.shared offset, instead of AND + ADD.
+constexpr unsigned V5_SMEM0=0x400u;
+template<int V5_Q> __device__ __forceinline__ void V5PushOr(unsigned qrel,unsigned tail,unsigned v){
+  const unsigned a=(tail&((V5_Q-1)*V5_STRIDE))|qrel;
+  asm volatile("st.shared.u32 [%0+1024], %1;" :: "r"(a), "r"(v) : "memory");
+}
+template<int V5_Q> __device__ __forceinline__ unsigned V5PopOr(unsigned qrel,unsigned head){
+  const unsigned a=(head&((V5_Q-1)*V5_STRIDE))|qrel;
+  unsigned v; asm volatile("ld.shared.u32 %0, [%1+1024];" : "=r"(v) : "r"(a) : "memory"); return v;
+}
+// entry e = {index:26 | cell code:6}: table slot of the code = ((e>>22)&0x3f0) | window base, table right behind the ring
+template<int V5_Q> __device__ __forceinline__ float4 V5OffTab(unsigned e,unsigned ubase){
+  float4 r;
+  const unsigned a=((e>>22)&0x3f0u); (void)ubase;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(r.x),"=f"(r.y),"=f"(r.z),"=f"(r.w) : "r"(a), "n"(V5_SMEM0+V5_Q*V5_STRIDE) : "memory");
+  return r;
+}
+
+// one chunk of V5_CH candidates of variant 7: vb = first index | cell code (index < 2^26, so vb+u carries index+u), vfin = end | code
+template<int V5_Q,bool CHECK> __device__ __forceinline__ void V5Chunk(const float4* __restrict__ posp,unsigned vb,unsigned vfin,
+  float ox,float oy,float oz,float ks2,unsigned q,unsigned &tail)
+{
+  const float4* __restrict__ ppb=posp+(vb&V5_IDXMASK);     // posp is padded: a chunk may read up to V5_CH-1 entries past the range
+  #pragma unroll
+  for(int u=0;u<V5_CH;u++){
+    const float4 pp2=__ldg(ppb+u);
+    const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
+    const float rr2=drx*drx+dry*dry+drz*drz;
+    if((!CHECK || vb+u<vfin) && rr2<=ks2){
+      V5PushOr<V5_Q>(q,tail,vb+u);
+      tail+=V5_STRIDE;
+    }
+  }
+}
+
+template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q,int OPT> __device__ __forceinline__ void V5Round(
   unsigned q,unsigned &head,unsigned tail,const float4 &pp1,const FastP1 &fp,const float* taup1,bool boundp2,
   const ForceParams &t,const DevCtes &c,PairAcc &a,unsigned &anyb,unsigned &nosh)
 {
   if(head!=tail){
-    const unsigned e=V5Pop(q,head&((V5_Q-1)*V5_STRIDE));
+    const unsigned e=(OPT? V5PopOr<V5_Q>(q,head): V5Pop(q,head&((V5_Q-1)*V5_STRIDE)));
     head+=V5_STRIDE;
     const unsigned p2=e&V5_IDXMASK;
     const unsigned code=e>>26;
-    const float fdx=float(int(code&3u))-1.f, fdy=float(int((code>>2)&3u))-1.f, fdz=float(int(code>>4))-1.f;
-    const float ox=pp1.x-fdx*c.scell, oy=pp1.y-fdy*c.scell, oz=pp1.z-fdz*c.scell;
+    float ox,oy,oz;
+    if(OPT){
+      // cell-origin offsets of the 27 neighbour cells from a 1 KB table in shared memory (one LDS.128 + 3 FADD instead of
+      // 13 integer/convert instructions; fd*scell is exact, so pp1 - table entry rounds like the FFMA of the candidate test)
+      const float4 off=V5OffTab<V5_Q>(e,q&0xff000000u);
+      ox=pp1.x-off.x; oy=pp1.y-off.y; oz=pp1.z-off.z;
+    }
+    else{
+      const float fdx=float(int(code&3u))-1.f, fdy=float(int((code>>2)&3u))-1.f, fdz=float(int(code>>4))-1.f;
+      ox=pp1.x-fdx*c.scell; oy=pp1.y-fdy*c.scell; oz=pp1.z-fdz*c.scell;
+    }
     const float4 pp2=__ldg(&t.posp[p2]);
     const float4 vr2=__ldg(&t.velrhop[p2]);
     const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
@@ -58,12 +110,24 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __device__ __forceinl
   }
 }
 
-template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __global__ void __launch_bounds__(FORCES_THREADS,(V5_Q>=128? 3: (V5_Q>=64? 6: 8)))
+template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q,int OPT> __global__ void __launch_bounds__(FORCES_THREADS,(V5_Q>=128? 3: (V5_Q>=64? 6: 8)))
 ker_forces_fluid_v5(ForceParams t,DevCtes c)
 {
-  __shared__ unsigned qsm[V5_Q*FORCES_THREADS];
-  const unsigned q=unsigned(__cvta_generic_to_shared(qsm))+threadIdx.x*4u;
+  __shared__ __align__(16) unsigned qsm[V5_Q*FORCES_THREADS+(OPT? 64*4: 0)];   // ring [+ 64 x float4 cell-offset table]
   const unsigned FULL=0xffffffffu;
+  unsigned q=unsigned(__cvta_generic_to_shared(qsm));
+  if(OPT){
+    if(q!=V5_SMEM0)__trap();                      // the OR-addressing needs the ring at the first usable byte of the CTA's window (no cluster launch)
+    if(threadIdx.x<64){
+      const unsigned k=threadIdx.x;
+      float4* tab=reinterpret_cast<float4*>(qsm+V5_Q*FORCES_THREADS);
+      tab[k]=make_float4((float(int(k&3u))-1.f)*c.scell,(float(int((k>>2)&3u))-1.f)*c.scell,(float(int(k>>4))-1.f)*c.scell,0.f);
+    }
+    __syncthreads();
+    q=threadIdx.x*4u;                            // lane part; slots are OR-ed in, V5_SMEM0 is an immediate of the ld/st
+    asm volatile("" : "+r"(q));                  // keep it in a register (the compiler re-derived it from SR_TID in every chunk)
+  }
+  else q+=threadIdx.x*4u;
   const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
   const unsigned p1c=min(p1,t.np-1);
   // x-slab halo copies are neighbours only: their forces are computed by the owning GPU (skipghosts: multi-GPU mode)
@@ -106,9 +170,29 @@ ker_forces_fluid_v5(ForceParams t,DevCtes c)
           }
           const unsigned nmax=__reduce_max_sync(FULL,pfin-pini);
           const unsigned codebits=(unsigned(dx+1)|(unsigned(dy+1)<<2)|(unsigned(dz+1)<<4))<<26;
+          if(OPT){
+            // variant 7: the chunk loop runs on vb = index | cell code (what is pushed), split into the chunks every lane has in
+            // full (one CREDUX.MIN per cell instead of a vote per chunk) and the ragged rest
+            const unsigned n=pfin-pini;
+            const unsigned ifull=(__reduce_min_sync(FULL,n)/V5_CH)*V5_CH;
+            unsigned vb=pini|codebits;
+            const unsigned vfin=pfin|codebits;
+            unsigned i=0;
+            for(;i<ifull;i+=V5_CH,vb+=V5_CH){
+              while(__any_sync(FULL,(tail-head)>unsigned(V5_Q-V5_CH)*V5_STRIDE))
+                V5Round<TKER,TVISCO,TDDT,SHIFT,V5_Q,OPT>(q,head,tail,pp1,fp,taup1,boundp2,t,c,a,anyb,nosh);
+              V5Chunk<V5_Q,false>(t.posp,vb,vfin,ox,oy,oz,ks2,q,tail);
+            }
+            for(;i<nmax;i+=V5_CH,vb+=V5_CH){
+              while(__any_sync(FULL,(tail-head)>unsigned(V5_Q-V5_CH)*V5_STRIDE))
+                V5Round<TKER,TVISCO,TDDT,SHIFT,V5_Q,OPT>(q,head,tail,pp1,fp,taup1,boundp2,t,c,a,anyb,nosh);
+              V5Chunk<V5_Q,true>(t.posp,vb,vfin,ox,oy,oz,ks2,q,tail);
+            }
+          }
+          else
           for(unsigned i=0;i<nmax;i+=V5_CH){
             while(__any_sync(FULL,(tail-head)>unsigned(V5_Q-V5_CH)*V5_STRIDE))
-              V5Round<TKER,TVISCO,TDDT,SHIFT,V5_Q>(q,head,tail,pp1,fp,taup1,boundp2,t,c,a,anyb,nosh);
+              V5Round<TKER,TVISCO,TDDT,SHIFT,V5_Q,OPT>(q,head,tail,pp1,fp,taup1,boundp2,t,c,a,anyb,nosh);
             // posp is padded (engine.cu): a chunk may read up to V5_CH-1 entries past the range without a clamp
             const unsigned pb=pini+i;
             const float4* __restrict__ ppb=t.posp+pb;
@@ -142,7 +226,7 @@ ker_forces_fluid_v5(ForceParams t,DevCtes c)
     }
     // end of the pass: the boundary pass uses other constants, drain everything
     while(__any_sync(FULL,head!=tail))
-      V5Round<TKER,TVISCO,TDDT,SHIFT,V5_Q>(q,head,tail,pp1,fp,taup1,boundp2,t,c,a,anyb,nosh);
+      V5Round<TKER,TVISCO,TDDT,SHIFT,V5_Q,OPT>(q,head,tail,pp1,fp,taup1,boundp2,t,c,a,anyb,nosh);
   }
   float viscmax=0,ace2=0,vel2=0;
   if(active){
@@ -166,11 +250,12 @@ ker_forces_fluid_v5(ForceParams t,DevCtes c)
   WarpMaxToGlobal(vel2,&t.fmax->vel2_bits);
 }
 
-template<int TKER,int TVISCO,int TDDT,bool SHIFT> static void LaunchFluidV5(unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm,int qdepth=64){
+template<int TKER,int TVISCO,int TDDT,bool SHIFT> static void LaunchFluidV5(unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm,int qdepth=64,int opt=0){
   const unsigned nb=(npf+FORCES_THREADS-1)/FORCES_THREADS;
   if(c.scelldiv==1 && t.np<=V5_IDXMASK){
-    if(qdepth==32)ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,32><<<nb,FORCES_THREADS,0,stm>>>(t,c);
-    else ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,64><<<nb,FORCES_THREADS,0,stm>>>(t,c);
+    if(qdepth==32 && opt)ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,32,1><<<nb,FORCES_THREADS,0,stm>>>(t,c);
+    else if(qdepth==32)ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,32,0><<<nb,FORCES_THREADS,0,stm>>>(t,c);
+    else ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,64,0><<<nb,FORCES_THREADS,0,stm>>>(t,c);
   }
   else ker_forces_fluid_v4<TKER,TVISCO,TDDT,SHIFT><<<nb,FORCES_THREADS,0,stm>>>(t,c);
 }

@@ -104,7 +104,8 @@ def test_gpu_pips_match_oracle(gpu_lib, oracle_lib):
 
 def test_gpu_force_variants_agree(gpu_lib):
     """Kernel variants: 1 plain IEEE loop (reference structure), 2 lane FIFO (bit-identical to 1), 3 warp-cooperative,
-    4 division-free body, 5/6 = 4 + deferred pair ring of 64/32 slots (6 is production; both bit-identical to 4).  3 and 4 differ from 1 only by rounding (fp32 conditioning of the pressure sum)."""
+    4 division-free body, 5/6 = 4 + deferred pair ring of 64/32 slots, 7 = 6 with OR-addressed ring slots, table-driven cell offsets and
+    a leaner chunk loop (5, 6, 7 bit-identical to 4).  3 and 4 differ from 1 only by rounding (fp32 conditioning of the pressure sum)."""
     cd = dsph.make_case("dambreak", 80000)
     ctx = dsph.create_context(cd)
     ctx.upload(cd.idp, cd.pos, cd.velrhop, cd.npb, cd.codes())
@@ -112,7 +113,7 @@ def test_gpu_force_variants_agree(gpu_lib):
     for _ in range(5):
         ctx.step()
     res = {}
-    for variant in (1, 2, 3, 4, 5, 6):
+    for variant in (1, 2, 3, 4, 5, 6, 7):
         gpu_lib.lib.dsph_set_force_variant(ctx.h, variant)
         ctx.celldiv(False)
         fr = ctx.forces()
@@ -124,6 +125,8 @@ def test_gpu_force_variants_agree(gpu_lib):
     assert np.array_equal(ace5, ace4) and np.array_equal(ar5, ar4) and f4.dt == f5.dt, "v5 (deferred ring) must be bit-identical to v4"
     (ace6, ar6), f6 = res[6]
     assert np.array_equal(ace6, ace4) and np.array_equal(ar6, ar4) and f4.dt == f6.dt, "v6 (32-slot ring) must be bit-identical to v4"
+    (ace7, ar7), f7 = res[7]
+    assert np.array_equal(ace7, ace4) and np.array_equal(ar7, ar4) and f4.dt == f7.dt, "v7 must be bit-identical to v4"
     for v in (3, 4):
         (ace, ar), f = res[v]
         assert rl2(ace, ace1) < 5e-6 and rl2(ar, ar1) < 5e-6 and abs(f1.dt - f.dt) / f1.dt < 1e-6, (v, rl2(ace, ace1), rl2(ar, ar1))
