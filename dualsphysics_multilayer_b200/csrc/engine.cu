@@ -406,6 +406,7 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> static void LaunchFluid(int va
   else if(variant==5)LaunchFluidV5<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm,64);
   else if(variant==6)LaunchFluidV5<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm,32);
   else if(variant==7)LaunchFluidV5<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm,32,1);
+  else if(variant==8)LaunchFluidV5<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm,32,2);
   else LaunchFluidV3<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm);
 }
 template<int TKER,int TVISCO,int TDDT> static void LaunchFluid3(int variant,bool shift,unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm){

@@ -19,8 +19,18 @@ __device__ __forceinline__ float FastRsqrt(float x){ float r; asm("rsqrt.approx.
 
 struct FastP1 { float4 velrhop; float press, ovrhop; };
 
+// packed fp32x2 arithmetic of sm_100 (FADD2/FMUL2/FFMA2: two IEEE fp32 operations per issue slot, same rounding as the scalar forms)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 Pk(float a,float b){ f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void Upk(f32x2 v,float &a,float &b){ asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 Sub2(f32x2 a,f32x2 b){ f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 Mul2(f32x2 a,f32x2 b){ f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 Fma2(f32x2 a,f32x2 b,f32x2 c){ f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 // Accumulates one accepted pair.  boundp2 may be a per-lane value (v3) or a literal (v4: constant-folded).
-template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ void PairFast(
+// NOBRANCH (variant 8): the artificial-viscosity term of receding pairs is selected to zero instead of branched around (the
+// branch diverges in nearly every round: BSSY + BRA + BSYNC cost more issue slots than the select).
+template<int TKER,int TVISCO,int TDDT,bool SHIFT,bool NOBRANCH=false> __device__ __forceinline__ void PairFast(
   float drx,float dry,float drz,float rr2,const FastP1 &p1,const float4 &velrhop2,float pressp2,bool boundp2,
   const float* __restrict__ taup1,const float* __restrict__ taup2,unsigned codep2,const DevCtes &c,PairAcc &a,unsigned &anybound,unsigned &noshiftf,
   bool valid=true)
@@ -44,7 +54,8 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ voi
     if(rad>c.kernelh){ const float wqq1=2.0f-qq; fac=c.cub_c2*(wqq1*wqq1)*rinv; }
     else fac=c.cub_c1_ovh+c.cub_d1_ovh*qq;
   }
-  const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
+  float frx,fry; const float frz=fac*drz;
+  if(NOBRANCH)Upk(Mul2(Pk(fac,fac),Pk(drx,dry)),frx,fry); else{ frx=fac*drx; fry=fac*dry; }
   const float rhopp1=p1.velrhop.w;
   const float ov2=FastRcp(velrhop2.w);
   {
@@ -59,9 +70,11 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ voi
       prs+=fab*(t1+t2);
     }
     const float p_vpm=-prs*massp2;
-    a.ax+=p_vpm*frx; a.ay+=p_vpm*fry; a.az+=p_vpm*frz;
+    if(NOBRANCH)Upk(Fma2(Pk(p_vpm,p_vpm),Pk(frx,fry),Pk(a.ax,a.ay)),a.ax,a.ay); else{ a.ax+=p_vpm*frx; a.ay+=p_vpm*fry; }
+    a.az+=p_vpm*frz;
   }
-  const float dvx=p1.velrhop.x-velrhop2.x, dvy=p1.velrhop.y-velrhop2.y, dvz=p1.velrhop.z-velrhop2.z;
+  float dvx,dvy; const float dvz=p1.velrhop.z-velrhop2.z;
+  if(NOBRANCH)Upk(Sub2(Pk(p1.velrhop.x,p1.velrhop.y),Pk(velrhop2.x,velrhop2.y)),dvx,dvy); else{ dvx=p1.velrhop.x-velrhop2.x; dvy=p1.velrhop.y-velrhop2.y; }
   a.ar+=massp2*(dvx*frx+dvy*fry+dvz*frz)*(rhopp1*ov2);
   const float ovrr=FastRcp(rr2+c.eta2);
   const float cbar=c.cs0;
@@ -97,7 +110,15 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ voi
     const float dot=drx*dvx+dry*dvy+drz*dvz;
     const float dot_rr2=dot*ovrr;
     a.visc=fmaxf(dot_rr2,a.visc);
-    if(TVISCO==DSPH_VISCO_ARTIFICIAL){
+    if(TVISCO==DSPH_VISCO_ARTIFICIAL && NOBRANCH){
+      const float amubar=c.kernelh*dot_rr2;
+      const float ovrobar=FastRcp((rhopp1+velrhop2.w)*0.5f);
+      float pi_visc=(-visco*cbar*amubar*ovrobar)*massp2;
+      pi_visc=(dot<0? -pi_visc: 0.f);                // x + 0*fr == x: identical sums
+      Upk(Fma2(Pk(pi_visc,pi_visc),Pk(frx,fry),Pk(a.ax,a.ay)),a.ax,a.ay);
+      a.az+=pi_visc*frz;
+    }
+    else if(TVISCO==DSPH_VISCO_ARTIFICIAL){
       if(dot<0){
         const float amubar=c.kernelh*dot_rr2;
         const float ovrobar=FastRcp((rhopp1+velrhop2.w)*0.5f);

@@ -525,32 +525,11 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ voi
   }
 }
 
-template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __device__ __forceinline__ void NNRound(
-  unsigned q,unsigned &head,unsigned tail,const float4 &pp1,const NNFastP1 &fp,bool boundp2,
-  const ForceParams &t,const DevCtes &c,const DevPhases &ph,NNFastAcc &a,unsigned &anyb,unsigned &nosh)
-{
-  if(head!=tail){
-    const unsigned e=V5Pop(q,head&((V5_Q-1)*V5_STRIDE));
-    head+=V5_STRIDE;
-    const unsigned p2=e&V5_IDXMASK;
-    const unsigned code=e>>26;
-    const float fdx=float(int(code&3u))-1.f, fdy=float(int((code>>2)&3u))-1.f, fdz=float(int(code>>4))-1.f;
-    const float ox=pp1.x-fdx*c.scell, oy=pp1.y-fdy*c.scell, oz=pp1.z-fdz*c.scell;
-    const float4 pp2=__ldg(&t.posp[p2]);
-    const float4 vr2=__ldg(&t.velrhop[p2]);
-    unsigned codep2=0; if(!boundp2 || SHIFT)codep2=t.code[p2];
-    const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
-    const float rr2=drx*drx+dry*dry+drz*drz;
-    NNPairFast<TKER,TVISCO,TDDT,SHIFT>(drx,dry,drz,fmaxf(rr2,1e-18f),fp,vr2,pp2.w,boundp2,codep2,rr2>=1e-18f,c,ph,a,anyb,nosh);
-  }
-}
-
 template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __global__ void __launch_bounds__(FORCES_THREADS,6)
 ker_nn_fda_ring(ForceParams t,DevCtes c,DevPhases ph)
 {
-  __shared__ unsigned qsm[V5_Q*FORCES_THREADS];
-  const unsigned q=unsigned(__cvta_generic_to_shared(qsm))+threadIdx.x*4u;
-  const unsigned FULL=0xffffffffu;
+  __shared__ __align__(16) V8Smem<V5_Q> qsm;
+  const unsigned q=V8Setup<V5_Q>(qsm.w,c.scell);
   const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
   const unsigned p1c=min(p1,t.np-1);
   const unsigned code1=t.code[p1c];
@@ -560,59 +539,13 @@ ker_nn_fda_ring(ForceParams t,DevCtes c,DevPhases ph)
   NNFastP1 fp; fp.velrhop=t.velrhop[p1c]; fp.press=pp1.w; fp.ovrhop=1.f/fp.velrhop.w;
   fp.ph=code1&DSPH_CODE_MASKVALUE; if(fp.ph>=unsigned(ph.count))fp.ph=0;
   fp.tau_max=ph.ph[fp.ph].tau_max; fp.bi_multi=ph.ph[fp.ph].bi_multi; fp.mass=ph.ph[fp.ph].mass;
-  const unsigned rcell=t.dcell[p1c];
-  const int cx=int(DcCellx(c.domcellcode,rcell))-int(t.cellzero[0]);
-  const int cy=int(DcCelly(c.domcellcode,rcell))-int(t.cellzero[1]);
-  const int cz=int(DcCellz(c.domcellcode,rcell))-int(t.cellzero[2]);
-  const float ks2=c.kernelsize2, scell=c.scell;
   NNFastAcc a; a.ax=a.ay=a.az=a.ar=a.delta=a.visc=a.visceta=0; a.shift=make_float4(0,0,0,0);
-  unsigned anyb=0,nosh=0,head=0,tail=0;
-  #pragma unroll 1
-  for(int pass=0;pass<2;pass++){
-    const bool boundp2=(pass==1);
-    const unsigned cellinit=(boundp2? 0u: t.cellfluid);
-    #pragma unroll 1
-    for(int dz=-1;dz<=1;dz++){
-      const int z=cz+dz;
-      const float oz=pp1.z-float(dz)*scell;
-      #pragma unroll 1
-      for(int dy=-1;dy<=1;dy++){
-        const int y=cy+dy;
-        const float oy=pp1.y-float(dy)*scell;
-        const bool rowok=(active && z>=0 && z<t.ncz && y>=0 && y<t.ncy);
-        #pragma unroll 1
-        for(int dx=-1;dx<=1;dx++){
-          const int x=cx+dx;
-          const float ox=pp1.x-float(dx)*scell;
-          unsigned pini=0,pfin=0;
-          if(rowok && x>=0 && x<t.ncx){
-            const unsigned v=unsigned(t.nsheet*z+t.ncx*y+x)+cellinit;
-            pini=t.begincell[v]; pfin=t.begincell[v+1];
-          }
-          const unsigned nmax=__reduce_max_sync(FULL,pfin-pini);
-          const unsigned codebits=(unsigned(dx+1)|(unsigned(dy+1)<<2)|(unsigned(dz+1)<<4))<<26;
-          for(unsigned i=0;i<nmax;i+=V5_CH){
-            while(__any_sync(FULL,(tail-head)>unsigned(V5_Q-V5_CH)*V5_STRIDE))
-              NNRound<TKER,TVISCO,TDDT,SHIFT,V5_Q>(q,head,tail,pp1,fp,boundp2,t,c,ph,a,anyb,nosh);
-            const unsigned pb=pini+i;
-            const float4* __restrict__ ppb=t.posp+pb;
-            #pragma unroll
-            for(int u=0;u<V5_CH;u++){
-              const float4 pp2=__ldg(ppb+u);
-              const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
-              const float rr2=drx*drx+dry*dry+drz*drz;
-              if(pb+u<pfin && rr2<=ks2){
-                V5Push(q,tail&((V5_Q-1)*V5_STRIDE),(pb+u)|codebits);
-                tail+=V5_STRIDE;
-              }
-            }
-          }
-        }
-      }
-    }
-    while(__any_sync(FULL,head!=tail))
-      NNRound<TKER,TVISCO,TDDT,SHIFT,V5_Q>(q,head,tail,pp1,fp,boundp2,t,c,ph,a,anyb,nosh);
-  }
+  unsigned anyb=0,nosh=0;
+  V8Traverse<V5_Q>(t,c,active,pp1,t.dcell[p1c],q,[&](unsigned p2,float drx,float dry,float drz,float rr2,float pressp2,bool boundp2,bool valid){
+    const float4 vr2=__ldg(&t.velrhop[p2]);
+    unsigned codep2=0; if(!boundp2 || SHIFT)codep2=t.code[p2];
+    NNPairFast<TKER,TVISCO,TDDT,SHIFT>(drx,dry,drz,rr2,fp,vr2,pressp2,boundp2,codep2,valid,c,ph,a,anyb,nosh);
+  });
   float viscmax=0,ace2=0,vel2=0,etamax=0;
   if(active){
     float ar=a.ar, ax=a.ax, ay=a.ay, az=a.az;
@@ -637,70 +570,7 @@ ker_nn_fda_ring(ForceParams t,DevCtes c,DevPhases ph)
 template<int V5_Q,class PAIR> __device__ __forceinline__ void RingTraverse(const ForceParams &t,const DevCtes &c,bool active,const float4 &pp1,unsigned rcell,
   unsigned q,PAIR &&pair)
 {
-  const unsigned FULL=0xffffffffu;
-  const int cx=int(DcCellx(c.domcellcode,rcell))-int(t.cellzero[0]);
-  const int cy=int(DcCelly(c.domcellcode,rcell))-int(t.cellzero[1]);
-  const int cz=int(DcCellz(c.domcellcode,rcell))-int(t.cellzero[2]);
-  const float ks2=c.kernelsize2, scell=c.scell;
-  unsigned head=0,tail=0;
-  auto round=[&](bool boundp2){
-    if(head!=tail){
-      const unsigned e=V5Pop(q,head&((V5_Q-1)*V5_STRIDE));
-      head+=V5_STRIDE;
-      const unsigned p2=e&V5_IDXMASK;
-      const unsigned code=e>>26;
-      const float fdx=float(int(code&3u))-1.f, fdy=float(int((code>>2)&3u))-1.f, fdz=float(int(code>>4))-1.f;
-      const float ox=pp1.x-fdx*scell, oy=pp1.y-fdy*scell, oz=pp1.z-fdz*scell;
-      const float4 pp2=__ldg(&t.posp[p2]);
-      const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
-      const float rr2=drx*drx+dry*dry+drz*drz;
-      pair(p2,drx,dry,drz,fmaxf(rr2,1e-18f),pp2.w,boundp2,rr2>=1e-18f);
-    }
-  };
-  #pragma unroll 1
-  for(int pass=0;pass<2;pass++){
-    const bool boundp2=(pass==1);
-    const unsigned cellinit=(boundp2? 0u: t.cellfluid);
-    #pragma unroll 1
-    for(int dz=-1;dz<=1;dz++){
-      const int z=cz+dz;
-      const float oz=pp1.z-float(dz)*scell;
-      #pragma unroll 1
-      for(int dy=-1;dy<=1;dy++){
-        const int y=cy+dy;
-        const float oy=pp1.y-float(dy)*scell;
-        const bool rowok=(active && z>=0 && z<t.ncz && y>=0 && y<t.ncy);
-        #pragma unroll 1
-        for(int dx=-1;dx<=1;dx++){
-          const int x=cx+dx;
-          const float ox=pp1.x-float(dx)*scell;
-          unsigned pini=0,pfin=0;
-          if(rowok && x>=0 && x<t.ncx){
-            const unsigned v=unsigned(t.nsheet*z+t.ncx*y+x)+cellinit;
-            pini=t.begincell[v]; pfin=t.begincell[v+1];
-          }
-          const unsigned nmax=__reduce_max_sync(FULL,pfin-pini);
-          const unsigned codebits=(unsigned(dx+1)|(unsigned(dy+1)<<2)|(unsigned(dz+1)<<4))<<26;
-          for(unsigned i=0;i<nmax;i+=V5_CH){
-            while(__any_sync(FULL,(tail-head)>unsigned(V5_Q-V5_CH)*V5_STRIDE))round(boundp2);
-            const unsigned pb=pini+i;
-            const float4* __restrict__ ppb=t.posp+pb;
-            #pragma unroll
-            for(int u=0;u<V5_CH;u++){
-              const float4 pp2=__ldg(ppb+u);
-              const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
-              const float rr2=drx*drx+dry*dry+drz*drz;
-              if(pb+u<pfin && rr2<=ks2){
-                V5Push(q,tail&((V5_Q-1)*V5_STRIDE),(pb+u)|codebits);
-                tail+=V5_STRIDE;
-              }
-            }
-          }
-        }
-      }
-    }
-    while(__any_sync(FULL,head!=tail))round(boundp2);
-  }
+  V8Traverse<V5_Q>(t,c,active,pp1,rcell,q,pair);      // forces_v5.cuh: the skeleton of the production single-phase kernel (variant 8)
 }
 
 template<int TKER> __device__ __forceinline__ float NNFacFast(float rr2,const DevCtes &c,float &rinv,float &rad,float &qq){
@@ -714,8 +584,8 @@ template<int TKER> __device__ __forceinline__ float NNFacFast(float rr2,const De
 template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __global__ void __launch_bounds__(FORCES_THREADS,6)
 ker_nn_sph_pressgrad_ring(ForceParams t,DevCtes c,DevPhases ph)
 {
-  __shared__ unsigned qsm[V5_Q*FORCES_THREADS];
-  const unsigned q=unsigned(__cvta_generic_to_shared(qsm))+threadIdx.x*4u;
+  __shared__ __align__(16) V8Smem<V5_Q> qsm;
+  const unsigned q=V8Setup<V5_Q>(qsm.w,c.scell);
   const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
   const unsigned p1c=min(p1,t.np-1);
   const bool active=(p1<t.np);
@@ -823,8 +693,8 @@ ker_nn_sph_pressgrad_ring(ForceParams t,DevCtes c,DevPhases ph)
 template<int TKER,int TVISCO,int V5_Q> __global__ void __launch_bounds__(FORCES_THREADS,6)
 ker_nn_sph_visco_ring(ForceParams t,DevCtes c,DevPhases ph)
 {
-  __shared__ unsigned qsm[V5_Q*FORCES_THREADS];
-  const unsigned q=unsigned(__cvta_generic_to_shared(qsm))+threadIdx.x*4u;
+  __shared__ __align__(16) V8Smem<V5_Q> qsm;
+  const unsigned q=V8Setup<V5_Q>(qsm.w,c.scell);
   const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
   const unsigned p1c=min(p1,t.np-1);
   const bool active=(p1<t.np);

@@ -21,6 +21,11 @@
 // loop variable (index | cell code, +u per candidate), the neighbour-cell offsets of the pair body read from a 1 KB shared table
 // (LDS.128 + 3 FADD instead of 13 shift/convert instructions), the lane's ring offset pinned in a register, and the full chunks of
 // a cell counted once (CREDUX.MIN) instead of a vote per chunk.
+// Variant 8 (OPT=2, production, 31.73 ms) adds the packed fp32x2 instructions of sm_100 (FADD2/FMUL2/FFMA2: two IEEE operations per
+// issue slot, bit-identical to the scalar forms) for the x,y components of dr, dv, fr and the ace accumulation in the pair body and
+// of dr in the candidate test, selects the artificial-viscosity term of receding pairs to zero instead of branching around it, and is
+// compiled for 7 resident CTAs per SM (72 registers, no spills: __launch_bounds__(128,6); 8 CTAs = 64 registers spill 20 bytes and
+// measure 32.9 ms, 6 CTAs with 78 registers 33.2 ms).
 #pragma once
 #include "forces_fast.cuh"
 
@@ -62,14 +67,16 @@ template<int V5_Q> __device__ __forceinline__ float4 V5OffTab(unsigned e,unsigne
 }
 
 // one chunk of V5_CH candidates of variant 7: vb = first index | cell code (index < 2^26, so vb+u carries index+u), vfin = end | code
-template<int V5_Q,bool CHECK> __device__ __forceinline__ void V5Chunk(const float4* __restrict__ posp,unsigned vb,unsigned vfin,
+template<int V5_Q,bool CHECK,bool PACKED> __device__ __forceinline__ void V5Chunk(const float4* __restrict__ posp,unsigned vb,unsigned vfin,
   float ox,float oy,float oz,float ks2,unsigned q,unsigned &tail)
 {
   const float4* __restrict__ ppb=posp+(vb&V5_IDXMASK);     // posp is padded: a chunk may read up to V5_CH-1 entries past the range
+  const f32x2 oxy=Pk(ox,oy);
   #pragma unroll
   for(int u=0;u<V5_CH;u++){
     const float4 pp2=__ldg(ppb+u);
-    const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
+    float drx,dry; const float drz=oz-pp2.z;
+    if(PACKED)Upk(Sub2(oxy,Pk(pp2.x,pp2.y)),drx,dry); else{ drx=ox-pp2.x; dry=oy-pp2.y; }   // FADD2: same rounding, one issue slot
     const float rr2=drx*drx+dry*dry+drz*drz;
     if((!CHECK || vb+u<vfin) && rr2<=ks2){
       V5PushOr<V5_Q>(q,tail,vb+u);
@@ -88,7 +95,12 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q,int OPT> __device__ __
     const unsigned p2=e&V5_IDXMASK;
     const unsigned code=e>>26;
     float ox,oy,oz;
-    if(OPT){
+    f32x2 oxy=0;
+    if(OPT>=2){
+      const float4 off=V5OffTab<V5_Q>(e,q&0xff000000u);
+      oxy=Sub2(Pk(pp1.x,pp1.y),Pk(off.x,off.y)); oz=pp1.z-off.z; ox=oy=0;
+    }
+    else if(OPT){
       // cell-origin offsets of the 27 neighbour cells from a 1 KB table in shared memory (one LDS.128 + 3 FADD instead of
       // 13 integer/convert instructions; fd*scell is exact, so pp1 - table entry rounds like the FFMA of the candidate test)
       const float4 off=V5OffTab<V5_Q>(e,q&0xff000000u);
@@ -100,17 +112,18 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q,int OPT> __device__ __
     }
     const float4 pp2=__ldg(&t.posp[p2]);
     const float4 vr2=__ldg(&t.velrhop[p2]);
-    const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
+    float drx,dry; const float drz=oz-pp2.z;
+    if(OPT>=2)Upk(Sub2(oxy,Pk(pp2.x,pp2.y)),drx,dry); else{ drx=ox-pp2.x; dry=oy-pp2.y; }
     const float rr2=drx*drx+dry*dry+drz*drz;
     unsigned codep2=0; if(SHIFT && boundp2)codep2=t.code[p2];
     const float *taup2=(TVISCO==DSPH_VISCO_LAMINARSPS && !boundp2? t.spstau+6*size_t(p2): nullptr);
     // the ALMOSTZERO exclusion (the particle itself, coincident particles) is applied here, not in the candidate test, and
     // without a branch: such a pair runs with rr2 clamped and zero mass (every contribution is exactly 0, no flag is set)
-    PairFast<TKER,TVISCO,TDDT,SHIFT>(drx,dry,drz,fmaxf(rr2,1e-18f),fp,vr2,pp2.w,boundp2,taup1,taup2,codep2,c,a,anyb,nosh,rr2>=1e-18f);
+    PairFast<TKER,TVISCO,TDDT,SHIFT,(OPT>=2)>(drx,dry,drz,fmaxf(rr2,1e-18f),fp,vr2,pp2.w,boundp2,taup1,taup2,codep2,c,a,anyb,nosh,rr2>=1e-18f);
   }
 }
 
-template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q,int OPT> __global__ void __launch_bounds__(FORCES_THREADS,(V5_Q>=128? 3: (V5_Q>=64? 6: 8)))
+template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q,int OPT,int MINB=(V5_Q>=128? 3: (V5_Q>=64? 6: 8))> __global__ void __launch_bounds__(FORCES_THREADS,MINB)
 ker_forces_fluid_v5(ForceParams t,DevCtes c)
 {
   __shared__ __align__(16) unsigned qsm[V5_Q*FORCES_THREADS+(OPT? 64*4: 0)];   // ring [+ 64 x float4 cell-offset table]
@@ -181,12 +194,12 @@ ker_forces_fluid_v5(ForceParams t,DevCtes c)
             for(;i<ifull;i+=V5_CH,vb+=V5_CH){
               while(__any_sync(FULL,(tail-head)>unsigned(V5_Q-V5_CH)*V5_STRIDE))
                 V5Round<TKER,TVISCO,TDDT,SHIFT,V5_Q,OPT>(q,head,tail,pp1,fp,taup1,boundp2,t,c,a,anyb,nosh);
-              V5Chunk<V5_Q,false>(t.posp,vb,vfin,ox,oy,oz,ks2,q,tail);
+              V5Chunk<V5_Q,false,(OPT>=2)>(t.posp,vb,vfin,ox,oy,oz,ks2,q,tail);
             }
             for(;i<nmax;i+=V5_CH,vb+=V5_CH){
               while(__any_sync(FULL,(tail-head)>unsigned(V5_Q-V5_CH)*V5_STRIDE))
                 V5Round<TKER,TVISCO,TDDT,SHIFT,V5_Q,OPT>(q,head,tail,pp1,fp,taup1,boundp2,t,c,a,anyb,nosh);
-              V5Chunk<V5_Q,true>(t.posp,vb,vfin,ox,oy,oz,ks2,q,tail);
+              V5Chunk<V5_Q,true,(OPT>=2)>(t.posp,vb,vfin,ox,oy,oz,ks2,q,tail);
             }
           }
           else
@@ -250,10 +263,96 @@ ker_forces_fluid_v5(ForceParams t,DevCtes c)
   WarpMaxToGlobal(vel2,&t.fmax->vel2_bits);
 }
 
+// ---- the variant-8 skeleton for other pair bodies (multiphase kernels of forces_nn.cuh) ----
+// Shared memory of a CTA: V5_Q*FORCES_THREADS ring words + 64 float4 of cell offsets; must be the kernel's only static shared array.
+template<int V5_Q> struct V8Smem { unsigned w[V5_Q*FORCES_THREADS+64*4]; };
+
+// fills the offset table, checks the ring's place in the shared window and returns the lane's (pinned) ring offset
+template<int V5_Q> __device__ __forceinline__ unsigned V8Setup(unsigned* qsm,float scell){
+  if(unsigned(__cvta_generic_to_shared(qsm))!=V5_SMEM0)__trap();
+  if(threadIdx.x<64){
+    const unsigned k=threadIdx.x;
+    reinterpret_cast<float4*>(qsm+V5_Q*FORCES_THREADS)[k]=make_float4((float(int(k&3u))-1.f)*scell,(float(int((k>>2)&3u))-1.f)*scell,(float(int(k>>4))-1.f)*scell,0.f);
+  }
+  __syncthreads();
+  unsigned q=threadIdx.x*4u;
+  asm volatile("" : "+r"(q));
+  return q;
+}
+
+// pair(p2,drx,dry,drz,rr2 clamped,press of p2,boundp2,valid) is called for every accepted neighbour in the oracle's order per particle
+template<int V5_Q,class PAIR> __device__ __forceinline__ void V8Traverse(const ForceParams &t,const DevCtes &c,bool active,const float4 &pp1,unsigned rcell,
+  unsigned q,PAIR &&pair)
+{
+  const unsigned FULL=0xffffffffu;
+  const int cx=int(DcCellx(c.domcellcode,rcell))-int(t.cellzero[0]);
+  const int cy=int(DcCelly(c.domcellcode,rcell))-int(t.cellzero[1]);
+  const int cz=int(DcCellz(c.domcellcode,rcell))-int(t.cellzero[2]);
+  const float ks2=c.kernelsize2, scell=c.scell;
+  unsigned head=0,tail=0;
+  auto round=[&](bool boundp2){
+    if(head!=tail){
+      const unsigned e=V5PopOr<V5_Q>(q,head);
+      head+=V5_STRIDE;
+      const unsigned p2=e&V5_IDXMASK;
+      const float4 off=V5OffTab<V5_Q>(e,0u);
+      const float4 pp2=__ldg(&t.posp[p2]);
+      float drx,dry;
+      Upk(Sub2(Sub2(Pk(pp1.x,pp1.y),Pk(off.x,off.y)),Pk(pp2.x,pp2.y)),drx,dry);
+      const float drz=(pp1.z-off.z)-pp2.z;
+      const float rr2=drx*drx+dry*dry+drz*drz;
+      pair(p2,drx,dry,drz,fmaxf(rr2,1e-18f),pp2.w,boundp2,rr2>=1e-18f);
+    }
+  };
+  #pragma unroll 1
+  for(int pass=0;pass<2;pass++){
+    const bool boundp2=(pass==1);
+    const unsigned cellinit=(boundp2? 0u: t.cellfluid);
+    #pragma unroll 1
+    for(int dz=-1;dz<=1;dz++){
+      const int z=cz+dz;
+      const float oz=pp1.z-float(dz)*scell;
+      #pragma unroll 1
+      for(int dy=-1;dy<=1;dy++){
+        const int y=cy+dy;
+        const float oy=pp1.y-float(dy)*scell;
+        const bool rowok=(active && z>=0 && z<t.ncz && y>=0 && y<t.ncy);
+        #pragma unroll 1
+        for(int dx=-1;dx<=1;dx++){
+          const int x=cx+dx;
+          const float ox=pp1.x-float(dx)*scell;
+          unsigned pini=0,pfin=0;
+          if(rowok && x>=0 && x<t.ncx){
+            const unsigned v=unsigned(t.nsheet*z+t.ncx*y+x)+cellinit;
+            pini=t.begincell[v]; pfin=t.begincell[v+1];
+          }
+          const unsigned n=pfin-pini;
+          const unsigned nmax=__reduce_max_sync(FULL,n);
+          const unsigned ifull=(__reduce_min_sync(FULL,n)/V5_CH)*V5_CH;
+          const unsigned codebits=(unsigned(dx+1)|(unsigned(dy+1)<<2)|(unsigned(dz+1)<<4))<<26;
+          unsigned vb=pini|codebits;
+          const unsigned vfin=pfin|codebits;
+          unsigned i=0;
+          for(;i<ifull;i+=V5_CH,vb+=V5_CH){
+            while(__any_sync(FULL,(tail-head)>unsigned(V5_Q-V5_CH)*V5_STRIDE))round(boundp2);
+            V5Chunk<V5_Q,false,true>(t.posp,vb,vfin,ox,oy,oz,ks2,q,tail);
+          }
+          for(;i<nmax;i+=V5_CH,vb+=V5_CH){
+            while(__any_sync(FULL,(tail-head)>unsigned(V5_Q-V5_CH)*V5_STRIDE))round(boundp2);
+            V5Chunk<V5_Q,true,true>(t.posp,vb,vfin,ox,oy,oz,ks2,q,tail);
+          }
+        }
+      }
+    }
+    while(__any_sync(FULL,head!=tail))round(boundp2);
+  }
+}
+
 template<int TKER,int TVISCO,int TDDT,bool SHIFT> static void LaunchFluidV5(unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm,int qdepth=64,int opt=0){
   const unsigned nb=(npf+FORCES_THREADS-1)/FORCES_THREADS;
   if(c.scelldiv==1 && t.np<=V5_IDXMASK){
-    if(qdepth==32 && opt)ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,32,1><<<nb,FORCES_THREADS,0,stm>>>(t,c);
+    if(qdepth==32 && opt==2)ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,32,2,6><<<nb,FORCES_THREADS,0,stm>>>(t,c);
+    else if(qdepth==32 && opt)ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,32,1><<<nb,FORCES_THREADS,0,stm>>>(t,c);
     else if(qdepth==32)ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,32,0><<<nb,FORCES_THREADS,0,stm>>>(t,c);
     else ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,64,0><<<nb,FORCES_THREADS,0,stm>>>(t,c);
   }

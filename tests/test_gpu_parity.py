@@ -113,7 +113,7 @@ def test_gpu_force_variants_agree(gpu_lib):
     for _ in range(5):
         ctx.step()
     res = {}
-    for variant in (1, 2, 3, 4, 5, 6, 7):
+    for variant in (1, 2, 3, 4, 5, 6, 7, 8):
         gpu_lib.lib.dsph_set_force_variant(ctx.h, variant)
         ctx.celldiv(False)
         fr = ctx.forces()
@@ -127,6 +127,8 @@ def test_gpu_force_variants_agree(gpu_lib):
     assert np.array_equal(ace6, ace4) and np.array_equal(ar6, ar4) and f4.dt == f6.dt, "v6 (32-slot ring) must be bit-identical to v4"
     (ace7, ar7), f7 = res[7]
     assert np.array_equal(ace7, ace4) and np.array_equal(ar7, ar4) and f4.dt == f7.dt, "v7 must be bit-identical to v4"
+    (ace8, ar8), f8 = res[8]
+    assert np.array_equal(ace8, ace4) and np.array_equal(ar8, ar4) and f4.dt == f8.dt, "v8 (packed fp32x2) must be bit-identical to v4"
     for v in (3, 4):
         (ace, ar), f = res[v]
         assert rl2(ace, ace1) < 5e-6 and rl2(ar, ar1) < 5e-6 and abs(f1.dt - f.dt) / f1.dt < 1e-6, (v, rl2(ace, ace1), rl2(ar, ar1))
