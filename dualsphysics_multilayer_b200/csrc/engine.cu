@@ -54,6 +54,11 @@ Engine::Engine(int device_,const dsph_config &c,unsigned capacity):device(device
   memset(hpin,0,sizeof(HostPinned));
   Configure(c);
   Allocate(capacity);
+  // variants 7/8 address their ring relative to the start of the CTA's shared window: check the assumption once
+  ker_v8_probe<<<1,32,0,stm>>>(&hpind->probe);
+  CUCHECK(cudaStreamSynchronize(stm));
+  ringbase_ok=(hpin->probe==V5_SMEM0);
+  if(!ringbase_ok)forcevariant=6;
 }
 
 Engine::~Engine(){
@@ -444,13 +449,14 @@ void Engine::ForcesLaunch(int interstep){
   const unsigned npf=np-npb;
   const bool shift=(cfg.shiftmode!=0);
   if(npf && cfg.nn_on){
-    const unsigned nl=LaunchForcesNN(forcevariant,cfg.tkernel,cfg.tvisco,cfg.tdensity,shift,t,dc,dph,stm);
+    const unsigned nl=LaunchForcesNN((ringbase_ok? forcevariant: 1),cfg.tkernel,cfg.tvisco,cfg.tdensity,shift,t,dc,dph,stm);
     if(!nl)throw EngineError(DSPH_ERR_ARG,"Kernel / viscosity / DDT choice is not valid for the multiphase formulation.");
     launches+=nl;
   }
   else if(npf){
-    if(cfg.tkernel==DSPH_KERNEL_WENDLAND)LaunchFluid1<DSPH_KERNEL_WENDLAND>(forcevariant,cfg.tvisco,cfg.tdensity,shift,npf,t,dc,stm);
-    else if(cfg.tkernel==DSPH_KERNEL_CUBIC)LaunchFluid1<DSPH_KERNEL_CUBIC>(forcevariant,cfg.tvisco,cfg.tdensity,shift,npf,t,dc,stm);
+    const int fv=(!ringbase_ok && forcevariant>=7? 6: forcevariant);
+    if(cfg.tkernel==DSPH_KERNEL_WENDLAND)LaunchFluid1<DSPH_KERNEL_WENDLAND>(fv,cfg.tvisco,cfg.tdensity,shift,npf,t,dc,stm);
+    else if(cfg.tkernel==DSPH_KERNEL_CUBIC)LaunchFluid1<DSPH_KERNEL_CUBIC>(fv,cfg.tvisco,cfg.tdensity,shift,npf,t,dc,stm);
     else throw EngineError(DSPH_ERR_ARG,"Kernel choice is not valid.");
     launches++;
     if(sps){ ker_sps_tau<<<(npf+255)/256,256,0,stm>>>(npf,npb,velrhop[cur],spsgradvel,spstau[cur],dc); launches++; }

@@ -348,6 +348,13 @@ template<int V5_Q,class PAIR> __device__ __forceinline__ void V8Traverse(const F
   }
 }
 
+// Where does the first static shared array of a kernel start in the CTA's shared window?  Variants 7/8 fold V5_SMEM0 into their
+// ld/st.shared offsets; the engine asks once per context and falls back to variant 6 (multiphase: the plain loop) if it differs.
+__global__ void ker_v8_probe(unsigned *out){
+  __shared__ __align__(16) V8Smem<32> qsm;
+  if(threadIdx.x==0)*out=unsigned(__cvta_generic_to_shared(qsm.w));
+}
+
 template<int TKER,int TVISCO,int TDDT,bool SHIFT> static void LaunchFluidV5(unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm,int qdepth=64,int opt=0){
   const unsigned nb=(npf+FORCES_THREADS-1)/FORCES_THREADS;
   if(c.scelldiv==1 && t.np<=V5_IDXMASK){
