@@ -5,7 +5,7 @@ from dualsphysics_multilayer_b200 import capi
 L=dsph.lib()
 for name in ('pb_sym_wend_art_ddt1','db_sym_wend_art_ddt2','db2d_sym_wend_art_ddt2_shift'):
     g=parity.Golden(name)
-    for variant in (1,4,6):
+    for variant in (1,4,6,8):
         ctx=parity.make_ctx(L,g.cfg,20000)
         L.lib.dsph_set_force_variant(ctx.h,variant)
         step=g.steps[-1]
