@@ -412,6 +412,7 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> static void LaunchFluid(int va
   else if(variant==6)LaunchFluidV5<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm,32);
   else if(variant==7)LaunchFluidV5<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm,32,1);
   else if(variant==8)LaunchFluidV5<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm,32,2);
+  else if(variant==9)LaunchFluidV5<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm,32,3);
   else LaunchFluidV3<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm);
 }
 template<int TKER,int TVISCO,int TDDT> static void LaunchFluid3(int variant,bool shift,unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm){
@@ -454,7 +455,7 @@ void Engine::ForcesLaunch(int interstep){
     launches+=nl;
   }
   else if(npf){
-    const int fv=(!ringbase_ok && forcevariant>=7? 6: forcevariant);
+    const int fv=(!ringbase_ok && forcevariant>=7? 6: forcevariant);   // 7, 8, 9 need the ring at the start of the shared window
     if(cfg.tkernel==DSPH_KERNEL_WENDLAND)LaunchFluid1<DSPH_KERNEL_WENDLAND>(fv,cfg.tvisco,cfg.tdensity,shift,npf,t,dc,stm);
     else if(cfg.tkernel==DSPH_KERNEL_CUBIC)LaunchFluid1<DSPH_KERNEL_CUBIC>(fv,cfg.tvisco,cfg.tdensity,shift,npf,t,dc,stm);
     else throw EngineError(DSPH_ERR_ARG,"Kernel choice is not valid.");

@@ -56,7 +56,7 @@ class Engine {
   ForceMax *fmax=nullptr;
   float viscdtmax=0; double acemax=0, velmax=0; float lastforcems=0, lastfluidms=0; double fluidms_sum=0; unsigned long long fluid_launches=0;
   bool ringbase_ok=true;  // the shared-window assumption of variants 7/8 holds on this device/driver (probed at creation)
-  int forcevariant=8;   // 8 = 7 + packed fp32x2 arithmetic, 7 CTAs/SM; 7 = deferred ring, 32 slots (8 CTAs/SM), OR-addressed slots + offset table; 6 = same ring, first version; 5 = 64 slots; 4 = no ring; 1 = IEEE reference structure
+  int forcevariant=9;   // 9 = 8 with opposite rows of cells visited back to back (summation order differs from the oracle's); 8 = 7 + packed fp32x2 arithmetic, 7 CTAs/SM; 7 = deferred ring, 32 slots (8 CTAs/SM), OR-addressed slots + offset table; 6 = same ring, first version; 5 = 64 slots; 4 = no ring; 1 = IEEE reference structure
   // time stepping
   double symplecticdtpre=0; int verletstep=0;
   dsph_timers tm={}; unsigned long long launches=0;

@@ -50,6 +50,12 @@ __device__ __forceinline__ unsigned V5Pop(unsigned qaddr,unsigned byteoff){
 // 16 KB-aligned relative to that: slot address = ((tail & mask) | lane part) + V5_SMEM0 = ONE LOP3 with the constant folded
 // into the ld/st.shared offset, instead of AND + ADD.
 constexpr unsigned V5_SMEM0=0x400u;
+// row order of variant 9, two bits per row (value+1): (dz,dy) = (-1,-1),(1,1),(-1,1),(1,-1),(-1,0),(1,0),(0,-1),(0,1),(0,0)
+constexpr unsigned V5RowPack(int a0,int a1,int a2,int a3,int a4,int a5,int a6,int a7,int a8){
+  return unsigned(a0+1)|(unsigned(a1+1)<<2)|(unsigned(a2+1)<<4)|(unsigned(a3+1)<<6)|(unsigned(a4+1)<<8)|(unsigned(a5+1)<<10)|(unsigned(a6+1)<<12)|(unsigned(a7+1)<<14)|(unsigned(a8+1)<<16);
+}
+constexpr unsigned V5_ROWDZ=V5RowPack(-1,1,-1,1,-1,1,0,0,0);
+constexpr unsigned V5_ROWDY=V5RowPack(-1,1,1,-1,0,0,-1,1,0);
 template<int V5_Q> __device__ __forceinline__ void V5PushOr(unsigned qrel,unsigned tail,unsigned v){
   const unsigned a=(tail&((V5_Q-1)*V5_STRIDE))|qrel;
   asm volatile("st.shared.u32 [%0+1024], %1;" :: "r"(a), "r"(v) : "memory");
@@ -164,11 +170,14 @@ ker_forces_fluid_v5(ForceParams t,DevCtes c)
     const bool boundp2=(pass==1);
     const unsigned cellinit=(boundp2? 0u: t.cellfluid);
     #pragma unroll 1
-    for(int dz=-1;dz<=1;dz++){
-      const int z=cz+dz;
-      const float oz=pp1.z-float(dz)*scell;
-      #pragma unroll 1
-      for(int dy=-1;dy<=1;dy++){
+    for(int r=0;r<9;r++){
+      {
+        // rows (dz,dy) of three cells: z,y ascending = the oracle's order, or (OPT>=3, variant 9) opposite rows back to back, which
+        // evens out the arrival of accepted pairs between the lanes of a warp (tools/simq.py: 284 -> 250 pair rounds per warp)
+        const int dz=(OPT>=3? int((V5_ROWDZ>>(2*r))&3u)-1: r/3-1);
+        const int dy=(OPT>=3? int((V5_ROWDY>>(2*r))&3u)-1: r%3-1);
+        const int z=cz+dz;
+        const float oz=pp1.z-float(dz)*scell;
         const int y=cy+dy;
         const float oy=pp1.y-float(dy)*scell;
         const bool rowok=(active && z>=0 && z<t.ncz && y>=0 && y<t.ncy);
@@ -280,7 +289,8 @@ template<int V5_Q> __device__ __forceinline__ unsigned V8Setup(unsigned* qsm,flo
   return q;
 }
 
-// pair(p2,drx,dry,drz,rr2 clamped,press of p2,boundp2,valid) is called for every accepted neighbour in the oracle's order per particle
+// pair(p2,drx,dry,drz,rr2 clamped,press of p2,boundp2,valid) is called for every accepted neighbour (fluid pass, then boundary pass;
+// rows in the order of variant 9, cells and particles ascending inside a row)
 template<int V5_Q,class PAIR> __device__ __forceinline__ void V8Traverse(const ForceParams &t,const DevCtes &c,bool active,const float4 &pp1,unsigned rcell,
   unsigned q,PAIR &&pair)
 {
@@ -309,11 +319,13 @@ template<int V5_Q,class PAIR> __device__ __forceinline__ void V8Traverse(const F
     const bool boundp2=(pass==1);
     const unsigned cellinit=(boundp2? 0u: t.cellfluid);
     #pragma unroll 1
-    for(int dz=-1;dz<=1;dz++){
-      const int z=cz+dz;
-      const float oz=pp1.z-float(dz)*scell;
-      #pragma unroll 1
-      for(int dy=-1;dy<=1;dy++){
+    for(int r=0;r<9;r++){
+      {
+        // rows of three cells in the order of variant 9 (opposite rows back to back)
+        const int dz=int((V5_ROWDZ>>(2*r))&3u)-1;
+        const int dy=int((V5_ROWDY>>(2*r))&3u)-1;
+        const int z=cz+dz;
+        const float oz=pp1.z-float(dz)*scell;
         const int y=cy+dy;
         const float oy=pp1.y-float(dy)*scell;
         const bool rowok=(active && z>=0 && z<t.ncz && y>=0 && y<t.ncy);
@@ -359,6 +371,7 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> static void LaunchFluidV5(unsi
   const unsigned nb=(npf+FORCES_THREADS-1)/FORCES_THREADS;
   if(c.scelldiv==1 && t.np<=V5_IDXMASK){
     if(qdepth==32 && opt==2)ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,32,2,6><<<nb,FORCES_THREADS,0,stm>>>(t,c);
+    else if(qdepth==32 && opt==3)ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,32,3,6><<<nb,FORCES_THREADS,0,stm>>>(t,c);
     else if(qdepth==32 && opt)ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,32,1><<<nb,FORCES_THREADS,0,stm>>>(t,c);
     else if(qdepth==32)ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,32,0><<<nb,FORCES_THREADS,0,stm>>>(t,c);
     else ker_forces_fluid_v5<TKER,TVISCO,TDDT,SHIFT,64,0><<<nb,FORCES_THREADS,0,stm>>>(t,c);
