@@ -321,10 +321,10 @@ def main():
     achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture of this very workload (profiles/)
     traffic, traffic_src = None, None
-    tfile = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01c_forces_v8_20m_summary.json")
+    tfile = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01d_forces_v9_20m_summary.json")
     if world == 1 and a.np == 20_000_000 and not a.force_variant and os.path.exists(tfile):
         traffic = json.load(open(tfile))["dram_bytes_per_launch"]
-        traffic_src = "profiles/r01c_forces_v8_20m_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+        traffic_src = "profiles/r01d_forces_v9_20m_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "kernel": "ker_forces_fluid", "avg_launch_ms": k_ms, "launches": int(fnl.value),
