@@ -105,7 +105,7 @@ def test_gpu_pips_match_oracle(gpu_lib, oracle_lib):
 def test_gpu_force_variants_agree(gpu_lib):
     """Kernel variants: 1 plain IEEE loop (reference structure), 2 lane FIFO (bit-identical to 1), 3 warp-cooperative,
     4 division-free body, 5/6 = 4 + deferred pair ring of 64/32 slots, 7 = 6 with OR-addressed ring slots, table-driven cell offsets and
-    a leaner chunk loop (5, 6, 7 bit-identical to 4).  3 and 4 differ from 1 only by rounding (fp32 conditioning of the pressure sum)."""
+    a leaner chunk loop, 8 = 7 + packed fp32x2 arithmetic (5-8 bit-identical to 4), 9 = 8 with another order of the rows of cells (production).  3 and 4 differ from 1 only by rounding (fp32 conditioning of the pressure sum)."""
     cd = dsph.make_case("dambreak", 80000)
     ctx = dsph.create_context(cd)
     ctx.upload(cd.idp, cd.pos, cd.velrhop, cd.npb, cd.codes())
@@ -113,7 +113,7 @@ def test_gpu_force_variants_agree(gpu_lib):
     for _ in range(5):
         ctx.step()
     res = {}
-    for variant in (1, 2, 3, 4, 5, 6, 7, 8):
+    for variant in (1, 2, 3, 4, 5, 6, 7, 8, 9):
         gpu_lib.lib.dsph_set_force_variant(ctx.h, variant)
         ctx.celldiv(False)
         fr = ctx.forces()
@@ -129,6 +129,9 @@ def test_gpu_force_variants_agree(gpu_lib):
     assert np.array_equal(ace7, ace4) and np.array_equal(ar7, ar4) and f4.dt == f7.dt, "v7 must be bit-identical to v4"
     (ace8, ar8), f8 = res[8]
     assert np.array_equal(ace8, ace4) and np.array_equal(ar8, ar4) and f4.dt == f8.dt, "v8 (packed fp32x2) must be bit-identical to v4"
+    # 9 (production) visits the rows of cells in another order: rounding-level difference to 4-8
+    (ace9, ar9), f9 = res[9]
+    assert rl2(ace9, ace4) < 5e-6 and rl2(ar9, ar4) < 5e-6 and abs(f9.dt - f4.dt) / f4.dt < 1e-6, (rl2(ace9, ace4), rl2(ar9, ar4))
     for v in (3, 4):
         (ace, ar), f = res[v]
         assert rl2(ace, ace1) < 5e-6 and rl2(ar, ar1) < 5e-6 and abs(f1.dt - f.dt) / f1.dt < 1e-6, (v, rl2(ace, ace1), rl2(ar, ar1))
