@@ -322,8 +322,10 @@ def main():
     # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture of this very workload (profiles/)
     traffic, traffic_src = None, None
     tfile = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01d_forces_v9_20m_summary.json")
+    ncu_summary = None
     if world == 1 and a.np == 20_000_000 and not a.force_variant and os.path.exists(tfile):
-        traffic = json.load(open(tfile))["dram_bytes_per_launch"]
+        ncu_summary = json.load(open(tfile))
+        traffic = ncu_summary["dram_bytes_per_launch"]
         traffic_src = "profiles/r01d_forces_v9_20m_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_per_launch,
@@ -332,6 +334,14 @@ def main():
                 "pairs_per_fluid_particle": {"checked": fr_chk / max(npf, 1), "real": fr_real / max(npf, 1)},
                 "fluid_evals_per_s": npf / (k_ms * 1e-3) if k_ms > 0 else 0.0, "peak_source": peaksrc,
                 "share_of_step": fms.value / ms.value if ms.value > 0 else None}
+    if ncu_summary is not None:
+        # what actually limits the kernel (from the same committed capture): the gather bytes are served by L1/L2, DRAM only sees `traffic`
+        m = ncu_summary["metrics"]
+        roofline["limiter"] = {"what": "instruction issue", "smsp__issue_active_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"].split()[0]),
+                               "warp_instructions_per_launch": float(m["smsp__inst_executed.sum"].split()[0]),
+                               "threads_per_instruction": float(m["smsp__thread_inst_executed_per_inst_executed.ratio"].split()[0]),
+                               "l1_hit_pct": float(m["l1tex__t_sector_hit_rate.pct"].split()[0]), "l2_hit_pct": float(m["lts__t_sector_hit_rate.pct"].split()[0]),
+                               "dram_gbs": traffic / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None}
 
     # ---- end to end through the C ABI with HOST buffers: H2D of the state, one step, D2H of the result, every step
     e2e = None

@@ -436,7 +436,8 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ voi
     if(rad>c.kernelh){ const float wqq1=2.0f-qq; fac=c.cub_c2*(wqq1*wqq1)*rinv; }
     else fac=c.cub_c1_ovh+c.cub_d1_ovh*qq;
   }
-  const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
+  float frx,fry; const float frz=fac*drz;
+  Upk(Mul2(Pk(fac,fac),Pk(drx,dry)),frx,fry);          // packed fp32x2 (forces_fast.cuh): same rounding, one issue slot
   const float rhopp1=p1.velrhop.w;
   const float ov2=FastRcp(velrhop2.w);
   {
@@ -451,9 +452,11 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ voi
       prs+=fab*(t1+t2);
     }
     const float p_vpm=-prs*massp2;
-    a.ax+=p_vpm*frx; a.ay+=p_vpm*fry; a.az+=p_vpm*frz;
+    Upk(Fma2(Pk(p_vpm,p_vpm),Pk(frx,fry),Pk(a.ax,a.ay)),a.ax,a.ay);
+    a.az+=p_vpm*frz;
   }
-  float dvx=p1.velrhop.x-velrhop2.x, dvy=p1.velrhop.y-velrhop2.y, dvz=p1.velrhop.z-velrhop2.z;
+  float dvx,dvy,dvz=p1.velrhop.z-velrhop2.z;
+  Upk(Sub2(Pk(p1.velrhop.x,p1.velrhop.y),Pk(velrhop2.x,velrhop2.y)),dvx,dvy);
   a.ar+=massp2*(dvx*frx+dvy*fry+dvz*frz)*(rhopp1*ov2);
   const float ovrr=FastRcp(rr2+c.eta2);
   const float cbar=P2.cs0;
@@ -513,7 +516,8 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ voi
       if(TVISCO==DSPH_VISCO_LAMINARSPS){
         const float temp=2.0f*eta*ovrr*ov2;
         const float vtemp=massp2*temp*dot3;
-        a.ax+=vtemp*dvx; a.ay+=vtemp*dvy; a.az+=vtemp*dvz;
+        Upk(Fma2(Pk(vtemp,vtemp),Pk(dvx,dvy),Pk(a.ax,a.ay)),a.ax,a.ay);
+        a.az+=vtemp*dvz;
       }
       else{
         const float t2=2.f*eta*ov2*massp2;

@@ -203,7 +203,11 @@ int dsph_get_timers(dsph_ctx *ctx,dsph_timers *t,int reset);
 int dsph_timer_start(dsph_ctx *ctx);
 int dsph_timer_stop(dsph_ctx *ctx,double *ms);
 int dsph_fluid_kernel_stats(dsph_ctx *ctx,double *ms_sum,uint64_t *nlaunch,int reset);
-/* selects the force-kernel implementation: 1 plain one-thread-per-particle loop, 2 tuned (default) */
+/* selects the fluid force-kernel implementation (profiles/r01_forces.md): 1 plain one-thread-per-particle IEEE loop (the reference's
+ * structure and pair order), 2 lane FIFO, 3 warp-cooperative, 4 division-free body, 5/6 deferred pair ring of 64/32 slots, 7 = 6 with
+ * OR-addressed ring slots and table-driven cell offsets, 8 = 7 + packed fp32x2 arithmetic (1,2 and 4-8: the oracle's summation order;
+ * 4-8 bit-identical to each other), 9 = 8 with opposite rows of neighbour cells visited back to back (default; rounding-level
+ * difference to 8).  Multiphase runs: 1 = plain loop, anything else = ring kernels. */
 int dsph_set_force_variant(dsph_ctx *ctx,int variant);
 int dsph_set_verletstep(dsph_ctx *ctx,int verletstep);
 double dsph_last_force_ms(const dsph_ctx *ctx);
