@@ -50,7 +50,9 @@ def _both(gpu_lib, oracle_lib, cd, capacity=0):
     return a, b
 
 
-@pytest.mark.parametrize("kind,n,nsteps", [("dambreak", 60000, 12), ("periodicbox", 27000, 6), ("nn2layer", 40000, 8)])
+@pytest.mark.parametrize("kind,n,nsteps", [("dambreak", 60000, 12), ("periodicbox", 27000, 6), ("nn2layer", 40000, 8),
+                                           # tiny inputs: a single partly filled CTA (30 fluid particles), a few CTAs, a fluid-only box of 8^3
+                                           ("dambreak", 300, 6), ("dambreak", 2500, 6), ("periodicbox", 343, 4), ("nn2layer", 1500, 4)])
 def test_gpu_vs_oracle_steps(gpu_lib, oracle_lib, kind, n, nsteps):
     """Same seeded case, whole steps on both sides: order bit-exact after every divide, forces within tolerance."""
     cd = dsph.make_case(kind, n)
