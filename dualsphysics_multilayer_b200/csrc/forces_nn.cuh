@@ -529,7 +529,7 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ voi
   }
 }
 
-template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __global__ void __launch_bounds__(FORCES_THREADS,6)
+template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __global__ void __launch_bounds__(FORCES_THREADS,7)
 ker_nn_fda_ring(ForceParams t,DevCtes c,DevPhases ph)
 {
   __shared__ __align__(16) V8Smem<V5_Q> qsm;
@@ -694,7 +694,7 @@ ker_nn_sph_pressgrad_ring(ForceParams t,DevCtes c,DevPhases ph)
 }
 
 // pass 2: viscous forces (artificial / Morris with eta1+eta2 / divergence of tau1+tau2), added to acear
-template<int TKER,int TVISCO,int V5_Q> __global__ void __launch_bounds__(FORCES_THREADS,6)
+template<int TKER,int TVISCO,int V5_Q> __global__ void __launch_bounds__(FORCES_THREADS,7)
 ker_nn_sph_visco_ring(ForceParams t,DevCtes c,DevPhases ph)
 {
   __shared__ __align__(16) V8Smem<V5_Q> qsm;
