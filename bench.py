@@ -106,43 +106,142 @@ def run_reference(np_sample, nsteps, threads, kind="dambreak"):
 REFGPU = os.path.join(os.path.dirname(REFBIN), "DualSPHysics5.2_linux64")
 
 
-def reference_gpu_baseline(npart, kind="dambreak", steps_a=8, steps_b=28):
+GPU_TIMER_KEYS = ("NL-Limits", "NL-PreSort", "NL-RadixSort", "NL-CellBegin", "NL-SortData", "NL-OutCheck", "CF-PreForces", "CF-Forces",
+                  "SU-Shifting", "SU-ComputeStep", "SU-Floating", "SU-Motion", "SU-Periodic", "SU-ResizeNp", "SU-DownData", "SU-SavePart", "SU-Chrono",
+                  "SU-Moorings", "SU-InOut", "SU-Gauges")
+
+
+def _lsq_slope(xs, ys):
+    """Least-squares line y = a + b x: returns (b, a, rms residual)."""
+    n = float(len(xs)); sx = sum(xs); sy = sum(ys); sxx = sum(x * x for x in xs); sxy = sum(x * y for x, y in zip(xs, ys))
+    den = n * sxx - sx * sx
+    if den == 0:
+        return None, None, None
+    b = (n * sxy - sx * sy) / den; a0 = (sy - b * sx) / n
+    res = (sum((y - (a0 + b * x)) ** 2 for x, y in zip(xs, ys)) / n) ** 0.5
+    return b, a0, res
+
+
+def _run_refgpu(tmp, nsteps, svtimers):
+    r = subprocess.run([REFGPU, "Case", "out", "-gpu", "-sv:none", "-svtimers:%d" % (1 if svtimers else 0), "-nsteps:%d" % nsteps], cwd=tmp,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    m1 = re.search(r"Simulation Runtime\.*: ([0-9.eE+-]+) sec", r.stdout)
+    m2 = re.search(r"Steps of simulation\.*: (\d+)", r.stdout)
+    m3 = re.search(r"Particles of simulation \(initial\): (\d+)", r.stdout)
+    if not (m1 and m2 and m3):
+        raise RuntimeError("reference GPU solver failed: " + r.stdout[-300:].replace("\n", " "))
+    tim = {}
+    for key in GPU_TIMER_KEYS:
+        m = re.search(re.escape(key) + r"\.*: ([0-9.eE+-]+) sec", r.stdout)
+        if m:
+            tim[key] = float(m.group(1))
+    return float(m1.group(1)), int(m2.group(1)), int(m3.group(1)), tim
+
+
+def reference_gpu_baseline(npart, kind="dambreak", lengths=(20, 60, 120), repeats=3):
     """The reference's OWN GPU solver (JSphGpuSingle + its CUDA kernels, S/Makefile flags) recompiled for sm_100 by
-    `make -C oracle gpu52`, run on this GPU on the same workload: steady-state rate from two runs of different length (their
-    difference removes initialisation and first-launch effects).  A reported baseline: what the unmodified reference kernels
-    deliver on a B200."""
+    `make -C oracle gpu52`, run on this GPU on the same workload.  Method: one discarded warm-up process
+    (driver/context start-up, module load, file cache), then `repeats` series of runs of `lengths` steps each; the per-step
+    cost is the least-squares SLOPE of "Simulation Runtime" over the number of steps (initialisation and first-launch effects
+    live in the intercept), computed per series and over all points.  A third series with the reference's synchronising
+    timers on (-svtimers:1) gives the slope of every [GPU Timers] line; the sum of those slopes must agree with the slope of
+    that series' Simulation Runtime.  The result is flagged unreliable when the two repeats differ by more than 5 %."""
     if kind == "nn2layer" or not os.path.exists(REFGPU):
         return None
     tmp = tempfile.mkdtemp(prefix="bench_refgpu_")
     try:
         subprocess.check_call([MKCASE, kind, str(npart), tmp, "Case"], stdout=subprocess.DEVNULL)
-        res = []
-        for ns in (steps_a, steps_b):
-            r = subprocess.run([REFGPU, "Case", "out", "-gpu", "-sv:none", "-svtimers:0", "-nsteps:%d" % ns], cwd=tmp,
-                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-            m1 = re.search(r"Simulation Runtime\.*: ([0-9.eE+-]+) sec", r.stdout)
-            m2 = re.search(r"Steps of simulation\.*: (\d+)", r.stdout)
-            m3 = re.search(r"Particles of simulation \(initial\): (\d+)", r.stdout)
-            if not (m1 and m2 and m3):
-                return {"value": None, "unit": UNIT, "what": "reference GPU solver failed: " + r.stdout[-200:].replace("\n", " ")}
-            res.append((float(m1.group(1)), int(m2.group(1)), int(m3.group(1))))
-        (ta, na, npa), (tb, nb, _) = res
-        rate = npa * (nb - na) / (tb - ta) / 1e6 if tb > ta and nb > na else None
-        # one more short run with the reference's synchronising timers on, only for its own split of the step
-        r = subprocess.run([REFGPU, "Case", "out", "-gpu", "-sv:none", "-svtimers:1", "-nsteps:%d" % steps_b], cwd=tmp,
-                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        t0 = time.time()
+        try:
+            _, _, npa, _ = _run_refgpu(tmp, 5, False)                      # warm-up process, discarded
+            series = []
+            for rep in range(repeats):
+                pts = [_run_refgpu(tmp, ns, False) for ns in lengths]
+                b, a0, res = _lsq_slope([p[1] for p in pts], [p[0] for p in pts])
+                series.append({"steps": [p[1] for p in pts], "runtime_s": [p[0] for p in pts], "ms_per_step": 1e3 * b, "intercept_s": a0, "rms_residual_s": res})
+            tpts = [_run_refgpu(tmp, ns, True) for ns in lengths]          # synchronising timers on
+        except RuntimeError as e:
+            return {"value": None, "unit": UNIT, "what": str(e)}
+        # Disturbances of a run (its thrust sort allocates and frees temporaries in every call, the first touch of 4 GB of pool
+        # memory, other tenants of the host) only ADD time, and they hit single runs (measured: one 60-step run of 17.0 s between
+        # repeats of 8.8 s).  The per-step cost is therefore the slope through the FASTEST run of every length; the slopes of the
+        # individual series and of the -svtimers:1 series are reported next to it, and the result is flagged unreliable when the
+        # fastest-run line does not fit (residual > 5 % of the span) or disagrees with the timer series by more than 10 %.
+        nlen = len(lengths)
+        best = [min(sr["runtime_s"][i] for sr in series) for i in range(nlen)]
+        b_all, a_all, res_all = _lsq_slope(list(lengths), best)
+        slopes = [sr["ms_per_step"] for sr in series]
+        spread = (max(slopes) - min(slopes)) / (sum(slopes) / len(slopes))
+        bt, _, rest = _lsq_slope([p[1] for p in tpts], [p[0] for p in tpts])
         split = {}
-        for key in ("NL-Limits", "NL-PreSort", "NL-RadixSort", "NL-CellBegin", "NL-SortData", "CF-Forces", "SU-ComputeStep"):
-            m = re.search(re.escape(key) + r"\.*: ([0-9.eE+-]+) sec", r.stdout)
-            if m:
-                split[key] = 1e3 * float(m.group(1)) / steps_b
-        return {"value": rate, "unit": UNIT, "np": npa, "ms_per_step": 1e3 * (tb - ta) / (nb - na) if nb > na else None,
-                "its_own_timers_ms_per_step": split,
-                "what": "reference DualSPHysics5.2 GPU solver (its own CUDA kernels, nvcc 12.9 -O3 -use_fast_math, sm_100) on this GPU, "
-                        "%s at %d particles: steps %d..%d of two runs (%.2f s and %.2f s of Simulation Runtime)"
-                        % (WORKLOADS[kind][0], npa, na, nb, ta, tb)}
+        for key in GPU_TIMER_KEYS:
+            if all(key in p[3] for p in tpts):
+                bk, _, _ = _lsq_slope([p[1] for p in tpts], [p[3][key] for p in tpts])
+                if bk is not None and abs(bk) > 1e-7:
+                    split[key] = 1e3 * bk
+        tsum = sum(split.values())
+        span = max(best) - min(best)
+        fit_ok = bool(b_all and b_all > 0 and res_all <= 0.05 * span)
+        agree = bool(bt and b_all and abs(bt - b_all) <= 0.10 * b_all)
+        return {"value": npa / b_all / 1e6 if b_all and b_all > 0 else None, "unit": UNIT, "np": npa, "ms_per_step": 1e3 * b_all,
+                "rms_residual_ms": 1e3 * res_all, "fastest_runtime_s": best, "series": series, "series_slope_spread": spread,
+                "reliable": bool(fit_ok and agree), "fit_ok": fit_ok, "agrees_with_timer_series": agree,
+                "with_sync_timers": {"ms_per_step": 1e3 * bt, "rms_residual_ms": 1e3 * rest, "timers_ms_per_step": split, "timers_sum_ms_per_step": tsum,
+                                     "timers_sum_over_runtime": (tsum / (1e3 * bt) if bt else None)},
+                "wall_s": time.time() - t0,
+                "what": "reference DualSPHysics5.2 GPU solver (its own CUDA kernels + thrust sort, nvcc 12.9 -O3 -use_fast_math, sm_100) on this GPU, %s at %d "
+                        "particles: least-squares slope of its 'Simulation Runtime' over the fastest of %d runs of each of %s steps, after one discarded warm-up process; "
+                        "timer split from a third series with -svtimers:1" % (WORKLOADS[kind][0], npa, repeats, "/".join(str(v) for v in lengths))}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+NCU_METRICS = ("dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio,"
+               "smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,l1tex__t_sector_hit_rate.pct,"
+               "lts__t_sector_hit_rate.pct,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,gpu__time_duration.sum")
+
+
+def ncu_one_launch(a):
+    """Counters of ONE launch of the fluid force kernel on this workload, captured now (child process = this script with
+    --ncu-child under `ncu -k regex:ker_forces_fluid -s 2 -c 1`).  Only counters are taken from it (bytes, instructions, ratios);
+    durations under the profiler are never reported as bench values."""
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return {"unavailable": "ncu not found"}
+    cmd = [ncu, "--metrics", NCU_METRICS, "--clock-control", "none", "-k", "regex:ker_forces_fluid", "-s", "2", "-c", "1", "--csv",
+           sys.executable, os.path.abspath(__file__), "--ncu-child", "--np", str(a.np), "--workload", a.workload, "--no-e2e", "--no-cpu-baseline"]
+    if a.force_variant:
+        cmd += ["--force-variant", str(a.force_variant)]
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    except Exception as e:                                              # noqa: BLE001
+        return {"unavailable": "ncu child failed: %r" % (e,)}
+    vals, kname = {}, None
+    import csv
+    rows = [ln for ln in r.stdout.splitlines() if ln.startswith('"')]
+    if len(rows) >= 2:
+        rd = list(csv.reader(rows))
+        hdr = rd[0]
+        try:
+            ik, im, iv = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value")
+            for row in rd[1:]:
+                kname = row[ik]
+                try:
+                    vals[row[im]] = float(row[iv].replace(",", ""))
+                except ValueError:
+                    pass
+        except ValueError:
+            pass
+    if "dram__bytes_read.sum" not in vals:
+        return {"unavailable": "no counters in the ncu output (rc %d): %s" % (r.returncode, (r.stderr or r.stdout)[-300:].replace("\n", " "))}
+    return {"kernel": (kname or "")[:120], "dram_bytes_per_launch": vals["dram__bytes_read.sum"] + vals.get("dram__bytes_write.sum", 0.0),
+            "warp_instructions_per_launch": vals.get("smsp__inst_executed.sum"),
+            "threads_per_instruction": vals.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
+            "smsp__issue_active_pct": vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "sm__warps_active_pct": vals.get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+            "fma_pipe_pct": vals.get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+            "l1_hit_pct": vals.get("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": vals.get("lts__t_sector_hit_rate.pct"),
+            "what": "ncu --metrics ... -k regex:ker_forces_fluid -s 2 -c 1 on `bench.py --ncu-child` (same workload and size, state after 2 steps)"}
 
 
 def cpu_baseline(sample_seconds=25.0, steps=3, kind="dambreak"):
@@ -165,6 +264,10 @@ def main():
     ap.add_argument("--np", "--particles", dest="np", type=int, default=20_000_000, help="particles per GPU (DB(N))")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pre-steps", type=int, default=0, help="untimed steps before warm-up (to leave the initial lattice)")
+    ap.add_argument("--ref-seconds", type=float, default=900.0, help="--impl reference: time limit for the CPU run; the particle count is reduced only when the full workload would exceed it")
+    ap.add_argument("--developed-step", type=int, default=200, help="step number at which the second (developed-state) window starts (SURVEY.md 8d: steps 200-400); 0 = only the initial window")
+    ap.add_argument("--no-ncu", action="store_true", help="skip the in-run one-launch ncu capture (dram bytes, instructions, issue-active) of the fluid force kernel")
+    ap.add_argument("--ncu-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the run of the reference's own GPU solver (oracle/_ref/DualSPHysics5.2_linux64)")
@@ -192,18 +295,24 @@ def main():
         cores = os.cpu_count() or 1
         threads = min(cores, 64)
         nsteps = max(1, a.steps + a.warmup)
-        np_sample = int(min(a.np, max(200_000, 0.05e6 * threads * 60.0 / nsteps)))
+        # the SAME configuration as the B200 arm whenever it fits the arm's time limit: the reference CPU solver
+        # does ~0.085 M particle-steps/s per thread on these boxes (1.36-1.43 M on 16 threads, 2.56 M on 32), so DB(20 M) x 25 steps
+        # is ~6 min on 16 threads.  Only when the estimate exceeds --ref-seconds is the particle count reduced (and said so).
+        est_rate = 0.085e6 * threads
+        np_sample = int(a.np if a.np * nsteps / est_rate <= a.ref_seconds else max(200_000, est_rate * a.ref_seconds / nsteps))
         t0 = time.time()
         r = run_reference(np_sample, nsteps, threads, a.workload)
         if r is None:
             emit(({"impl": "reference", "unavailable": "oracle/_ref/DualSPHysics5.2CPU_linux64 is missing (built by oracle/Makefile where /root/reference is mounted)"}))
             return
-        sample = ("reference DualSPHysics5.2 CPU solver (OpenMP, %d threads) on dam-break DB(%d) = bounded sample of the %d-particle workload, %d steps, %.1f s"
-                  % (threads, r["np"], a.np, r["steps"], r["seconds"]))
+        same = abs(r["np"] - a.np) <= 0.02 * a.np
+        sample = ("reference DualSPHysics5.2 CPU solver (OpenMP, %d threads) on %s at %d particles (%s), %d steps, %.1f s"
+                  % (threads, WORKLOADS[a.workload][0], r["np"], "the full workload of the B200 arm" if same else "bounded sample of the %d-particle workload" % a.np,
+                     r["steps"], r["seconds"]))
         emit(({"impl": "reference", "metric": METRIC.replace("3D dam-break", WORKLOADS[a.workload][0]), "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
                           "warmup": a.warmup, "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": WORKLOADS[a.workload][1], "np_sample": r["np"], "np_workload": a.np},
+                          "config": {"workload": WORKLOADS[a.workload][1], "np_sample": r["np"], "np_workload": a.np, "same_config": bool(same)},
                           "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
                           "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "wall_s": time.time() - t0}))
@@ -284,64 +393,104 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput: W warm-up + K timed steps, CUDA events on the solver's stream
-    for _ in range(a.warmup):
-        stepfn()
-    tm = dsph.Timers()
-    l.dsph_get_timers(ctx.h, C.byref(tm), 1)
-    l.dsph_fluid_kernel_stats(ctx.h, None, None, 1)
-    sampler = ClockSampler(local); sampler.start()
-    barrier()
-    L.check(l.dsph_timer_start(ctx.h))
-    pstep = 0
-    for _ in range(a.steps):
-        stepfn()
-        pstep += (ctx.np_ if drv is None else ctx.np_ - int(ctx.divinfo.npbper) - int(ctx.divinfo.npfper))   # owned particles only
-    ms = C.c_double()
-    L.check(l.dsph_timer_stop(ctx.h, C.byref(ms)))
-    barrier()
-    sampler.stop_flag = True; sampler.join(2.0)
-    l.dsph_get_timers(ctx.h, C.byref(tm), 0)
-    fms = C.c_double(); fnl = C.c_uint64()
-    l.dsph_fluid_kernel_stats(ctx.h, C.byref(fms), C.byref(fnl), 0)
-    t_ms = torch.tensor([ms.value], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(pstep)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    value = tot.item() / (t_ms.item() * 1e-3) / 1e6
+    # ---- in-run ncu child: build the same state, run a few force evaluations and exit (the parent runs this under ncu -k ... -c 1)
+    if a.ncu_child:
+        for _ in range(2):
+            stepfn()
+        ctx.close()
+        emit({"ncu_child": True})
+        return
 
-    # ---- roofline of the dominant kernel (fluid Interaction_Forces): gather-byte model, SURVEY.md 8(d)
+    # ---- device-resident throughput: W warm-up + K timed steps, CUDA events on the solver's stream, for two windows of the run
+    # (SURVEY.md 8d): the compact initial block (steps W..W+K) and the state after --developed-step steps (headline).
+    stepno = [a.pre_steps]
+
+    def run_steps(k):
+        for _ in range(k):
+            stepfn()
+        stepno[0] += k
+
+    def owned_now():
+        return ctx.np_ if drv is None else ctx.np_ - int(ctx.divinfo.npbper) - int(ctx.divinfo.npfper)
+
+    def timed_window(with_clocks):
+        tmw = dsph.Timers()
+        l.dsph_get_timers(ctx.h, C.byref(tmw), 1)
+        l.dsph_fluid_kernel_stats(ctx.h, None, None, 1)
+        smp = None
+        if with_clocks:
+            smp = ClockSampler(local); smp.start()
+        barrier()
+        L.check(l.dsph_timer_start(ctx.h))
+        pstep = 0
+        first = stepno[0]
+        for _ in range(a.steps):
+            stepfn()
+            pstep += owned_now()                                           # owned particles only
+        stepno[0] += a.steps
+        msw = C.c_double()
+        L.check(l.dsph_timer_stop(ctx.h, C.byref(msw)))
+        barrier()
+        if smp is not None:
+            smp.stop_flag = True; smp.join(2.0)
+        l.dsph_get_timers(ctx.h, C.byref(tmw), 0)
+        fmsw = C.c_double(); fnlw = C.c_uint64()
+        l.dsph_fluid_kernel_stats(ctx.h, C.byref(fmsw), C.byref(fnlw), 0)
+        t_ms = torch.tensor([msw.value], dtype=torch.float64, device="cuda")
+        tot = torch.tensor([float(pstep)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        return {"first_step": first, "value": tot.item() / (t_ms.item() * 1e-3) / 1e6, "ms_total": t_ms.item(), "ms_local": msw.value,
+                "fluid_ms": fmsw.value, "fluid_launches": int(fnlw.value), "timers": tmw, "clocks": (smp.result() if smp is not None else None)}
+
+    run_steps(a.warmup)
+    win_initial = timed_window(a.developed_step <= 0)
+    win = win_initial
+    if a.developed_step > 0:
+        run_steps(max(0, a.developed_step - stepno[0]))
+        if stepno[0] == a.pre_steps + a.warmup + a.steps:                 # nothing ran in between: still warm
+            pass
+        win = timed_window(True)
+    value = win["value"]; t_ms_total = win["ms_total"]; tm = win["timers"]; ms_local = win["ms_local"]
+    fms_value, fnl_value = win["fluid_ms"], win["fluid_launches"]
+
+    # ---- roofline of the dominant kernel (fluid Interaction_Forces).  SURVEY.md 8(d) + ncu: the kernel is NOT HBM bound (DRAM
+    # traffic = the compulsory ~58 B per fluid particle, served at <1 % of the HBM peak); its roof is fp32 instruction issue.
+    #   achieved = (11*N_chk + 85*N_real) flop per fluid particle (SURVEY.md 8d flop model; pair counts from ker_pips on this very state)
+    #              / average launch duration of the fluid kernel (CUDA events on the solver's stream inside the timed region)
+    #   peak     = 148 SMs x 128 fp32 lanes x 2 flop (FMA) x sm_max_mhz  (non-tensor fp32; MEASURED_PEAKS.json only holds HBM and bf16
+    #              tensor peaks, so this roof is derived from the measured maximum SM clock, and said so in peak_source)
     if drv is None:
         ctx.celldiv(False)
     fr_real, fr_chk, br_real, br_chk = ctx.pips()
     npf = ctx.np_ - ctx.npb - (0 if drv is None else int(ctx.divinfo.npfper))
-    bytes_per_launch = 58.0 * npf + 16.0 * (fr_chk + fr_real) + (2.0 * fr_real if a.workload == "nn2layer" else 0.0)   # + code[p2]: phase of the neighbour
-    k_ms = fms.value / max(1, fnl.value)
-    peak, peaksrc = measured_peak()
-    achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture of this very workload (profiles/)
-    traffic, traffic_src = None, None
-    tfile = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01d_forces_v9_20m_summary.json")
-    ncu_summary = None
-    if world == 1 and a.np == 20_000_000 and not a.force_variant and os.path.exists(tfile):
-        ncu_summary = json.load(open(tfile))
-        traffic = ncu_summary["dram_bytes_per_launch"]
-        traffic_src = "profiles/r01d_forces_v9_20m_summary.json (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                "kernel": "ker_forces_fluid", "avg_launch_ms": k_ms, "launches": int(fnl.value),
-                "model": "B_gather = 58*Nf + 16*(N_chk+N_real) bytes per launch (SURVEY.md 8d)",
+    k_ms = fms_value / max(1, fnl_value)
+    hbm_peak, hbm_src = measured_peak()
+    sm_mhz = 1965.0
+    try:
+        sm_mhz = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"])
+    except Exception:
+        pass
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    pair_flop = {"dambreak": 85.0, "periodicbox": 75.0, "nn2layer": 145.0}[a.workload]      # 85 (Wendland+artificial+DDT2); DDT1 instead of DDT2 -13+3; NN-FDA +60
+    flop_per_launch = 11.0 * fr_chk + pair_flop * fr_real
+    tflops = flop_per_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    gather_bytes = 58.0 * npf + 16.0 * (fr_chk + fr_real) + (2.0 * fr_real if a.workload == "nn2layer" else 0.0)   # + code[p2]: phase of the neighbour
+    gather_gbs = gather_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    roofline = {"bound": "fp32-issue", "achieved": tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tflops / fp32_peak, "traffic": None,
+                "kernel": "ker_forces_fluid (production variant %d)" % (a.force_variant or L.lib.dsph_get_force_variant(ctx.h)),
+                "avg_launch_ms": k_ms, "launches": int(fnl_value),
+                "algorithmic_flop_per_launch": flop_per_launch,
+                "model": "flop = 11*N_chk + %g*N_real per launch (SURVEY.md 8d flop model; N_chk/N_real counted by ker_pips on the timed state)" % pair_flop,
+                "peak_source": "derived: 148 SMs x 128 fp32 lanes x 2 flop x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json); non-tensor fp32 issue peak, not a measured number" % sm_mhz,
                 "pairs_per_fluid_particle": {"checked": fr_chk / max(npf, 1), "real": fr_real / max(npf, 1)},
-                "fluid_evals_per_s": npf / (k_ms * 1e-3) if k_ms > 0 else 0.0, "peak_source": peaksrc,
-                "share_of_step": fms.value / ms.value if ms.value > 0 else None}
-    if ncu_summary is not None:
-        # what actually limits the kernel (from the same committed capture): the gather bytes are served by L1/L2, DRAM only sees `traffic`
-        m = ncu_summary["metrics"]
-        roofline["limiter"] = {"what": "instruction issue", "smsp__issue_active_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"].split()[0]),
-                               "warp_instructions_per_launch": float(m["smsp__inst_executed.sum"].split()[0]),
-                               "threads_per_instruction": float(m["smsp__thread_inst_executed_per_inst_executed.ratio"].split()[0]),
-                               "l1_hit_pct": float(m["l1tex__t_sector_hit_rate.pct"].split()[0]), "l2_hit_pct": float(m["lts__t_sector_hit_rate.pct"].split()[0]),
-                               "dram_gbs": traffic / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None}
+                "fluid_evals_per_s": npf / (k_ms * 1e-3) if k_ms > 0 else 0.0,
+                "share_of_step": fms_value / ms_local if ms_local > 0 else None,
+                "why_not_hbm": "DRAM traffic of one launch is the compulsory ~58 B per fluid particle (see dram below when ncu ran): <1 % of the HBM peak; "
+                               "the gather bytes of the SURVEY model are served by L1/L2",
+                "gather_model_secondary": {"what": "B_gather = 58*Nf + 16*(N_chk+N_real) bytes moved to the SMs per launch (SURVEY.md 8d); NOT DRAM traffic, may exceed the HBM peak",
+                                           "bytes_per_launch": gather_bytes, "gbs": gather_gbs, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+                                           "ratio_to_hbm_peak": gather_gbs / hbm_peak}}
 
     # ---- end to end through the C ABI with HOST buffers: H2D of the state, one step, D2H of the result, every step
     e2e = None
@@ -436,22 +585,40 @@ def main():
 
     if rank == 0:
         out = {"metric": METRIC.replace("3D dam-break", WORKLOADS[a.workload][0]), "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-               "ms_per_step": t_ms.item() / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "ms_per_step": t_ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic",
                "config": {"workload": WORKLOADS[a.workload][1],
-                          "np_per_gpu": n, "nfluid": int(cd.cfg.casenfluid), "pre_steps": a.pre_steps,
+                          "np_per_gpu": n, "nfluid": int(cd.cfg.casenfluid), "pre_steps": a.pre_steps, "timed_steps": [win["first_step"], win["first_step"] + a.steps],
                           "np_global": nglobal,
                           "parallelism": ("single GPU" if world == 1 else "%d x-slabs of balanced work (fluid 1, boundary %g); per divide: NCCL send/recv of migrants + 2h halo copies with <=2 neighbours; per force evaluation: all-reduce(max) of the dt maxima; cuts re-balanced %d times with the measured kernel time per rank before warm-up (%s -> %s)" % (world, a.bound_weight, a.balance_steps, cuts_initial, list(drv.cuts))),
                           "l2": "working set (np*~230 B) is far larger than the 126 MB L2; no flush needed"},
-               "roofline": roofline, "e2e": e2e, "gpu_launches": int(tm.kernel_launches), "clocks": sampler.result(),
+               "roofline": roofline, "e2e": e2e, "gpu_launches": int(tm.kernel_launches), "clocks": win["clocks"],
                "timers_ms_per_step": {k: getattr(tm, k) / a.steps for k in ("nl_limits", "nl_presort", "nl_radixsort", "nl_cellbegin", "nl_sortdata",
                                                                              "cf_preforces", "cf_forces", "su_computestep")}}
+        tsteps = ("nl_limits", "nl_presort", "nl_radixsort", "nl_cellbegin", "nl_sortdata", "cf_preforces", "cf_forces", "su_computestep")
+        out["windows"] = {"what": "two timed windows of the same run (SURVEY.md 8d): the compact initial block and the state after --developed-step steps; "
+                                  "the headline value/ms_per_step/roofline/timers are those of the LAST window",
+                          "initial": {"steps": [win_initial["first_step"], win_initial["first_step"] + a.steps], "value": win_initial["value"],
+                                      "ms_per_step": win_initial["ms_total"] / a.steps,
+                                      "fluid_kernel_ms": win_initial["fluid_ms"] / max(1, win_initial["fluid_launches"]),
+                                      "timers_ms_per_step": {k: getattr(win_initial["timers"], k) / a.steps for k in tsteps}},
+                          "developed": {"steps": [win["first_step"], win["first_step"] + a.steps], "value": win["value"], "ms_per_step": win["ms_total"] / a.steps,
+                                        "fluid_kernel_ms": win["fluid_ms"] / max(1, win["fluid_launches"])}}
         if phases is not None:
             out["mgpu_phases_ms_per_step"] = phases
+        if world == 1:
+            ctx.close()                                                  # free the device before the child processes allocate
+            if not a.no_ncu:
+                ncu = ncu_one_launch(a)
+                out["roofline"]["ncu"] = ncu
+                if ncu.get("dram_bytes_per_launch"):
+                    out["roofline"]["traffic"] = ncu["dram_bytes_per_launch"]
+                    out["roofline"]["traffic_source"] = "measured in this run: one-launch ncu capture of the fluid force kernel on the same workload (child process, see roofline.ncu)"
+                    out["roofline"]["dram_gbs"] = ncu["dram_bytes_per_launch"] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+                    out["roofline"]["dram_frac_of_hbm_peak"] = out["roofline"]["dram_gbs"] / hbm_peak if k_ms > 0 else None
         if not a.no_cpu_baseline and world == 1:                         # the CPU baseline is reported at N=1 only
             out["cpu_baseline"] = cpu_baseline(kind=a.workload)
             if not a.no_reference_gpu:
-                ctx.close()                                              # free the device before the reference solver allocates
                 out["reference_gpu"] = reference_gpu_baseline(a.np, a.workload)
         emit(out)
     ctx.close()

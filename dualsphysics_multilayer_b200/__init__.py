@@ -44,6 +44,8 @@ def lib() -> SphLib:
         l.dsph_get_timers.argtypes = [C.c_void_p, C.POINTER(Timers), C.c_int]
         l.dsph_set_force_variant.argtypes = [C.c_void_p, C.c_int]
         l.dsph_set_verletstep.argtypes = [C.c_void_p, C.c_int]
+        l.dsph_get_force_variant.restype = C.c_int
+        l.dsph_get_force_variant.argtypes = [C.c_void_p]
         l.dsph_last_force_ms.restype = C.c_double
         l.dsph_last_force_ms.argtypes = [C.c_void_p]
         l.dsph_cuda_stream.restype = C.c_void_p

@@ -48,7 +48,7 @@ int dsph_ctx_destroy(dsph_ctx *ctx){
 }
 int dsph_constants_upload(dsph_ctx *ctx,const dsph_config *cfg){
   NEEDCTX(ctx); if(!cfg){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
-  return Guard([&]{ const double dtpre=ctx->eng->symplecticdtpre; const int vs=ctx->eng->verletstep; ctx->eng->Configure(*cfg); ctx->eng->symplecticdtpre=dtpre; ctx->eng->verletstep=vs; });
+  return Guard([&]{ ctx->eng->Reconfigure(*cfg); });
 }
 int dsph_particles_upload(dsph_ctx *ctx,uint32_t np,uint32_t npb,const uint32_t *idp,const dsph_typecode *code,const double *pos,const float *velrhop){
   NEEDCTX(ctx); if(!idp||!pos||!velrhop){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
@@ -93,6 +93,8 @@ double dsph_symplectic_dtpre(const dsph_ctx *ctx){ return (ctx&&ctx->eng)? ctx->
 int dsph_set_symplectic_dtpre(dsph_ctx *ctx,double dt){ NEEDCTX(ctx); ctx->eng->symplecticdtpre=dt; return DSPH_OK; }
 int dsph_set_verletstep(dsph_ctx *ctx,int v){ NEEDCTX(ctx); ctx->eng->verletstep=v; return DSPH_OK; }
 int dsph_set_force_variant(dsph_ctx *ctx,int v){ NEEDCTX(ctx); ctx->eng->forcevariant=v; return DSPH_OK; }
+int dsph_set_refbinary_tail(dsph_ctx *ctx,int on){ NEEDCTX(ctx); ctx->eng->reftail=(on!=0); ctx->eng->dc.reftail=(on? 1: 0); ctx->eng->divok=false; return DSPH_OK; }
+int dsph_get_force_variant(const dsph_ctx *ctx){ return (ctx&&ctx->eng)? ctx->eng->EffectiveForceVariant(): 0; }
 int dsph_get_timers(dsph_ctx *ctx,dsph_timers *t,int reset){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->GetTimers(t,reset!=0); }); }
 double dsph_last_force_ms(const dsph_ctx *ctx){ return (ctx&&ctx->eng)? ctx->eng->lastforcems: 0; }
 int dsph_pips(dsph_ctx *ctx,uint64_t *fr,uint64_t *fc,uint64_t *br,uint64_t *bc){

@@ -15,16 +15,13 @@
 #pragma once
 #include "devtypes.h"
 #include "radixsort.cuh"
+#include <cuda_fp16.h>
 #include "../../include/dsph_b200.h"
 
 namespace dsph {
 
 constexpr int DIV_THREADS=256;
 
-__device__ __forceinline__ unsigned DcCellx(unsigned dcc,unsigned cel){ return cel>>((dcc>>10)&31); }
-__device__ __forceinline__ unsigned DcCelly(unsigned dcc,unsigned cel){ return (cel<<(dcc>>25))>>((dcc>>5)&31); }
-__device__ __forceinline__ unsigned DcCellz(unsigned dcc,unsigned cel){ return (cel<<(dcc&31))>>(dcc&31); }
-__device__ __forceinline__ unsigned DcCell(unsigned dcc,unsigned cx,unsigned cy,unsigned cz){ return (cx<<((dcc>>10)&31))|(cy<<((dcc>>15)&31))|cz; }
 
 // First cell hash of uploaded particles: JSph::LoadDcellParticles (S/JSph.cpp:1690-1711), periodic duplicates of a
 // restarted state follow PeriodicDuplicatePos (S/JSphCpuSingle.cpp:232-251).  nout counts valid particles out of the domain.
@@ -104,7 +101,7 @@ __global__ void ker_div_prepare(const unsigned* __restrict__ limb,const unsigned
   dp->ncx=ncx; dp->ncy=ncy; dp->ncz=ncz; dp->nsheet=ncx*ncy; dp->nct=nct; dp->nctt=nct*2+6;
   dp->boxboundignore=nct; dp->boxfluid=nct+1; dp->boxboundout=nct+1+nct; dp->boxfluidout=dp->boxboundout+1;
   dp->boxboundoutignore=dp->boxfluidout+1; dp->boxfluidoutignore=dp->boxboundoutignore+1;
-  dp->nptot=nptot;
+  dp->nptot=nptot; dp->maxcellpop=0;
 }
 
 __global__ void __launch_bounds__(DIV_THREADS) ker_div_presort(unsigned n,const unsigned* __restrict__ dcell,const typecode* __restrict__ code,
@@ -209,6 +206,18 @@ __global__ void __launch_bounds__(SM_THREADS) ker_div_sufmin_apply(unsigned* __r
   for(int i=0;i<SM_ITEMS;i++)if(base+i<n)data[base+i]=min(data[base+i],off);
 }
 
+// largest population of a cell (boundary and fluid cells; the special boxes are never neighbours): the chunked candidate loops
+// of the ring force kernels read past a lane's own cell by up to that many entries (the arrays are padded, engine.h POSP_PAD)
+__global__ void __launch_bounds__(256) ker_div_maxpop(const unsigned* __restrict__ begin,DivParams* __restrict__ dp)
+{
+  const unsigned c=blockIdx.x*blockDim.x+threadIdx.x;
+  const unsigned nct=dp->nct;
+  unsigned v=0;
+  if(c<2u*nct+1u && c!=nct)v=begin[c+1]-begin[c];
+  v=__reduce_max_sync(0xffffffffu,v);
+  if((threadIdx.x&31)==0 && v>dp->maxcellpop)atomicMax(&dp->maxcellpop,v);
+}
+
 __global__ void ker_div_counts(const unsigned* __restrict__ begin,unsigned npb12,DivParams* __restrict__ dp)
 {
   if(threadIdx.x||blockIdx.x)return;
@@ -233,12 +242,16 @@ struct ReorderArrays {
   const float4 *velrhoppre_in; float4 *velrhoppre_out;
   const float *spstau_in; float *spstau_out;           // 6 floats
   float4 *posp;                                        // out: cell-relative xyz + pressure
+  uint4 *posh;                                         // out: packed-half culling copy (forces_v10.cuh), one uint4 per 2 particles
 };
 
 __device__ __forceinline__ float PressFromRhop(float rhop,const DevCtes &c,bool tail){
   // same rounding points as the reference CPU build (see oracle/sph_oracle.cpp PreInteraction): float product
-  // rhop*(1/rhop0), then pow, -1 and *B in double, one rounding to float.  tail: the last Np-4*((Np-1)/4) particles, for
-  // which the reference binary's scalar loop epilogue keeps the true division (1 ulp = 0.13 Pa at the free surface).
+  // rhop*(1/rhop0), then pow, -1 and *B in double, one rounding to float.
+  // tail: the reference BINARY vectorises this loop 4-wide and its scalar epilogue keeps the true division for the last
+  // Np-4*((Np-1)/4) particles (1 ulp of the quotient = 0.13 Pa).  That index-dependent artefact is NOT part of the product
+  // path (one rule for every particle, so a single domain and x-slabs round alike); it is reproduced only when a test asks for
+  // it (dsph_set_refbinary_tail) to compare with dumps of that binary at the 1e-5 level on 2-3 k particle cases.
   const float x=(tail? __fdiv_rn(rhop,c.rhopzero): __fmul_rn(rhop,c.ovrhopzero));
   return float(c.cteb_d*(pow(double(x),c.gamma_d)-1.0));
 }
@@ -253,42 +266,61 @@ __device__ __forceinline__ float PressFromRhopNN(float rhop,unsigned rcode,const
   return __fmul_rn(cteb,__fsub_rn(pw,1.0f));
 }
 
-template<bool NN> __global__ void __launch_bounds__(DIV_THREADS) ker_div_reorder(unsigned n,const unsigned* __restrict__ sortpart,ReorderArrays a,DevCtes c,DevPhases ph,
-  const DivParams* __restrict__ divp)
+template<bool NN> __global__ void __launch_bounds__(DIV_THREADS) ker_div_reorder(unsigned n,const unsigned* __restrict__ sortpart,ReorderArrays a,DevCtes c,DevPhases ph,const DivParams* __restrict__ divp)
 {
   const unsigned p=blockIdx.x*blockDim.x+threadIdx.x;
-  if(p>=n)return;
-  const unsigned npfin=divp->npfinal;                              // particles that stay after this divide (set by ker_div_counts)
-  const unsigned npfinal_vec=(npfin? ((npfin-1u)/4u)*4u: 0u);      // see PressFromRhop
-  const unsigned s=sortpart[p];
-  a.idp_out[p]=a.idp_in[s];
-  const typecode rcode=a.code_in[s];
-  a.code_out[p]=rcode;
-  const unsigned rcell=a.dcell_in[s];
-  a.dcell_out[p]=rcell;
-  const double px=a.pos_in[3*size_t(s)], py=a.pos_in[3*size_t(s)+1], pz=a.pos_in[3*size_t(s)+2];
-  a.pos_out[3*size_t(p)]=px; a.pos_out[3*size_t(p)+1]=py; a.pos_out[3*size_t(p)+2]=pz;
-  const float4 vr=a.velrhop_in[s];
-  a.velrhop_out[p]=vr;
-  if(a.velrhopm1_in)a.velrhopm1_out[p]=a.velrhopm1_in[s];
-  if(a.pospre_in){
-    a.pospre_out[3*size_t(p)]=a.pospre_in[3*size_t(s)]; a.pospre_out[3*size_t(p)+1]=a.pospre_in[3*size_t(s)+1]; a.pospre_out[3*size_t(p)+2]=a.pospre_in[3*size_t(s)+2];
-    a.velrhoppre_out[p]=a.velrhoppre_in[s];
-  }
-  if(a.spstau_in){
-    #pragma unroll
-    for(int k=0;k<6;k++)a.spstau_out[6*size_t(p)+k]=a.spstau_in[6*size_t(s)+k];
-  }
-  // cell-relative position (float) + pressure; excluded particles (dcell=0xffffffff) get zeros
+  const bool ok=(p<n);
+  unsigned npfinal_vec=0xffffffffu;                                // first particle of the reference binary's scalar epilogue (test switch)
+  if(c.reftail){ const unsigned npfin=divp->npfinal; npfinal_vec=(npfin? ((npfin-1u)/4u)*4u: 0u); }
   float4 pp=make_float4(0,0,0,0);
-  if(rcell!=0xffffffffu){
-    const unsigned cx=DcCellx(c.domcellcode,rcell), cy=DcCelly(c.domcellcode,rcell), cz=DcCellz(c.domcellcode,rcell);
-    pp.x=float(px-(c.domposmin[0]+double(cx)*c.scell_d));
-    pp.y=float(py-(c.domposmin[1]+double(cy)*c.scell_d));
-    pp.z=float(pz-(c.domposmin[2]+double(cz)*c.scell_d));
-    pp.w=(NN? PressFromRhopNN(vr.w,rcode,c,ph): PressFromRhop(vr.w,c,p>=npfinal_vec));
+  unsigned rcell=0xffffffffu;
+  if(ok){
+    const unsigned s=sortpart[p];
+    a.idp_out[p]=a.idp_in[s];
+    const typecode rcode=a.code_in[s];
+    a.code_out[p]=rcode;
+    rcell=a.dcell_in[s];
+    a.dcell_out[p]=rcell;
+    const double px=a.pos_in[3*size_t(s)], py=a.pos_in[3*size_t(s)+1], pz=a.pos_in[3*size_t(s)+2];
+    a.pos_out[3*size_t(p)]=px; a.pos_out[3*size_t(p)+1]=py; a.pos_out[3*size_t(p)+2]=pz;
+    const float4 vr=a.velrhop_in[s];
+    a.velrhop_out[p]=vr;
+    if(a.velrhopm1_in)a.velrhopm1_out[p]=a.velrhopm1_in[s];
+    if(a.pospre_in){
+      a.pospre_out[3*size_t(p)]=a.pospre_in[3*size_t(s)]; a.pospre_out[3*size_t(p)+1]=a.pospre_in[3*size_t(s)+1]; a.pospre_out[3*size_t(p)+2]=a.pospre_in[3*size_t(s)+2];
+      a.velrhoppre_out[p]=a.velrhoppre_in[s];
+    }
+    if(a.spstau_in){
+      #pragma unroll
+      for(int k=0;k<6;k++)a.spstau_out[6*size_t(p)+k]=a.spstau_in[6*size_t(s)+k];
+    }
+    // cell-relative position (float) + pressure; excluded particles (dcell=0xffffffff) get zeros
+    if(rcell!=0xffffffffu){
+      const unsigned cx=DcCellx(c.domcellcode,rcell), cy=DcCelly(c.domcellcode,rcell), cz=DcCellz(c.domcellcode,rcell);
+      pp.x=float(px-(c.domposmin[0]+double(cx)*c.scell_d));
+      pp.y=float(py-(c.domposmin[1]+double(cy)*c.scell_d));
+      pp.z=float(pz-(c.domposmin[2]+double(cz)*c.scell_d));
+      pp.w=(NN? PressFromRhopNN(vr.w,rcode,c,ph): PressFromRhop(vr.w,c,p>=npfinal_vec));
+    }
+    a.posp[p]=pp;
   }
-  a.posp[p]=pp;
+  // packed-half culling copy (forces_v10.cuh): centre-relative coordinates in units of half a cell, n = |rounded xyz|^2;
+  // the even lane of each pair of particles writes one uint4 {x0 x1, y0 y1, z0 z1, n0 n1}.  Particles past n or excluded ones
+  // are parked far away (never inside anybody's cut-off).
+  {
+    const bool in=(ok && rcell!=0xffffffffu);
+    const __half hx=__float2half_rn(in? pp.x*c.hscale-1.f: 100.f), hy=__float2half_rn(in? pp.y*c.hscale-1.f: 100.f), hz=__float2half_rn(in? pp.z*c.hscale-1.f: 100.f);
+    const float fx=__half2float(hx), fy=__half2float(hy), fz=__half2float(hz);
+    const __half hn=__float2half_rn(fx*fx+fy*fy+fz*fz);
+    const unsigned wx=__half_as_ushort(hx), wy=__half_as_ushort(hy), wz=__half_as_ushort(hz), wn=__half_as_ushort(hn);
+    const unsigned lo=wx|(wy<<16), hi=wz|(wn<<16);
+    const unsigned lo2=__shfl_down_sync(0xffffffffu,lo,1), hi2=__shfl_down_sync(0xffffffffu,hi,1);   // DIV_THREADS is even: the partner is in the warp
+    if(!(p&1u) && p<n+1u){
+      uint4 v;
+      v.x=(lo&0xffffu)|(lo2<<16); v.y=(lo>>16)|(lo2&0xffff0000u); v.z=(hi&0xffffu)|(hi2<<16); v.w=(hi>>16)|(hi2&0xffff0000u);
+      a.posh[p>>1]=v;
+    }
+  }
 }
 
 } // namespace dsph

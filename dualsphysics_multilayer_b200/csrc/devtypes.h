@@ -22,6 +22,7 @@ struct DevCtes {
   float powc[6];          // series of (1+t)^(1/gamma)-1 = t*(c0+t*(c1+...)) used by DDT2/3 (see PowNearOne)
   // cells
   float scell; int scelldiv;
+  float hscale;           // 2/scell: scale of the half-precision culling frame of forces_v10.cuh (cell = [-1,1]^3)
   double scell_d;
   double domposmin[3];
   unsigned domcellcode;
@@ -37,7 +38,16 @@ struct DevCtes {
   // shifting (S/JSphShifting.cpp:387-417)
   int shiftmode; float shifttfs;
   int nn_on;              // multiphase non-Newtonian fork: per-phase EOS, v5.0 shifting clamp
+  int reftail;            // test switch (dsph_set_refbinary_tail): reproduce the pressure rounding of the reference BINARY's loop epilogue
 };
+
+#ifdef __CUDACC__
+// cell code of a particle (S/JDsDcellDef.h:33-44): bit fields chosen by JDsDcell::CalcCellCode
+__device__ __forceinline__ unsigned DcCellx(unsigned dcc,unsigned cel){ return cel>>((dcc>>10)&31); }
+__device__ __forceinline__ unsigned DcCelly(unsigned dcc,unsigned cel){ return (cel<<(dcc>>25))>>((dcc>>5)&31); }
+__device__ __forceinline__ unsigned DcCellz(unsigned dcc,unsigned cel){ return (cel<<(dcc&31))>>(dcc&31); }
+__device__ __forceinline__ unsigned DcCell(unsigned dcc,unsigned cx,unsigned cy,unsigned cz){ return (cx<<((dcc>>10)&31))|(cy<<((dcc>>15)&31))|cz; }
+#endif
 
 // Phases of the multiphase non-Newtonian fork, passed by value to the kernels that need them (constant bank, indexed
 // by the type value of the particle code).  Replaces the __constant__ PHASECTE/PHASEARRAY[10] of M/JSphGpu_NN_ker.cu:44-47.
@@ -55,6 +65,7 @@ struct DivParams {
   unsigned nptot, npfinal, npbfinal;
   unsigned blimmin[3], blimmax[3];   // cached boundary cell limits (BoundLimitCellMin/Max)
   unsigned error;                    // !=0: nct overflow
+  unsigned maxcellpop;               // largest population of a (boundary or fluid) cell of this divide
 };
 
 // Maxima of one force evaluation, as order-preserving uint bit patterns of non-negative floats.
@@ -67,7 +78,7 @@ struct ForceMax {
 struct RadixSortBuffers {
   uint32_t *keys[2]={nullptr,nullptr}, *vals[2]={nullptr,nullptr};
   uint32_t *hist=nullptr, *chunksum=nullptr, *chunksum2=nullptr;
-  uint32_t capacity=0, histcap=0;
+  uint32_t capacity=0, histcap=0, chunksumcap=0, chunksum2cap=0;   // chunksum*: scan scratch (entries), sized for max(histogram, particle count)
 };
 
 } // namespace dsph

@@ -5,14 +5,10 @@
 #include "engine.h"
 #include "radixsort.cuh"
 #include "celldiv.cuh"
-#include "forces.cuh"
-#include "forces_v2.cuh"
-#include "forces_v3.cuh"
-#include "forces_v5.cuh"
+#include "forces_api.h"
 #include "step.cuh"
 #include "periodic.cuh"
 #include "mgpu.cuh"
-#include "forces_nn.cuh"
 #include "measure.cuh"
 #include <cstdio>
 #include <cstring>
@@ -54,11 +50,12 @@ Engine::Engine(int device_,const dsph_config &c,unsigned capacity):device(device
   memset(hpin,0,sizeof(HostPinned));
   Configure(c);
   Allocate(capacity);
-  // variants 7/8 address their ring relative to the start of the CTA's shared window: check the assumption once
-  ker_v8_probe<<<1,32,0,stm>>>(&hpind->probe);
+  // the ring kernels (variants 9, 10, multiphase) address their ring relative to the start of the CTA's shared window:
+  // check the assumption once per context; without it the plain kernels run (variant 4 / multiphase variant 1), a perf
+  // cliff that the driver reports in Run.out (dsph_ringbase_ok)
+  LaunchRingBaseProbe(&hpind->probe,stm);
   CUCHECK(cudaStreamSynchronize(stm));
-  ringbase_ok=(hpin->probe==V5_SMEM0);
-  if(!ringbase_ok)forcevariant=6;
+  ringbase_ok=(hpin->probe==RingBaseExpected());
 }
 
 Engine::~Engine(){
@@ -107,7 +104,7 @@ void Engine::Configure(const dsph_config &c){
     const double g=double(dc.ovgamma); double cf=1;
     for(int i=0;i<6;i++){ cf*=(g-i)/double(i+1); dc.powc[i]=float(cf); }
   }
-  dc.scell=k.scell; dc.scelldiv=k.scelldiv; dc.scell_d=double(k.scell);
+  dc.scell=k.scell; dc.scelldiv=k.scelldiv; dc.scell_d=double(k.scell); dc.hscale=2.f/k.scell;
   for(int i=0;i<3;i++){
     dc.domposmin[i]=k.domposmin[i]; dc.domcells[i]=k.domcells[i];
     dc.maprealposmin[i]=k.maprealposmin[i]; dc.maprealsize[i]=k.maprealsize[i];
@@ -121,7 +118,25 @@ void Engine::Configure(const dsph_config &c){
   if(!(dc.rhopoutmin<dc.rhopoutmax)){ dc.rhopoutmin=-FLT_MAX; dc.rhopoutmax=FLT_MAX; }
   dc.simulate2d=cfg.simulate2d; dc.dtallparticles=cfg.dtallparticles;
   dc.shiftmode=cfg.shiftmode; dc.shifttfs=cfg.shifttfs;
+  dc.reftail=(reftail? 1: 0);
   symplecticdtpre=k.dtini; verletstep=0;
+}
+
+// dsph_constants_upload on a live context (the reference re-uploads StCteInteraction when the DDT ramp changes a constant,
+// S/JSphGpuSingle.cpp:520-539).  Everything that decides which arrays exist or how cells are laid out must stay as it was
+// at creation: those fields are compared and the call is rejected with DSPH_ERR_ARG, the context stays untouched.
+void Engine::Reconfigure(const dsph_config &c){
+  SphConst k2; DeriveConstants(c,k2);
+  bool same=(c.tstep==cfg.tstep && c.shiftmode==cfg.shiftmode && c.tvisco==cfg.tvisco && c.tkernel==cfg.tkernel && c.nn_on==cfg.nn_on &&
+    c.nn_velgrad==cfg.nn_velgrad && c.nn_nphases==cfg.nn_nphases && c.perix==cfg.perix && c.periy==cfg.periy && c.periz==cfg.periz &&
+    c.simulate2d==cfg.simulate2d && c.cellmode==cfg.cellmode && c.casenfixed==cfg.casenfixed && c.casenmoving==cfg.casenmoving &&
+    c.casenfloat==cfg.casenfloat && k2.scell==k.scell && k2.scelldiv==k.scelldiv && k2.domcellcode==k.domcellcode && k2.periactive==k.periactive);
+  for(int i=0;i<3 && same;i++)same=(k2.domcells[i]==k.domcells[i] && k2.domposmin[i]==k.domposmin[i] && k2.maprealposmin[i]==k.maprealposmin[i] && k2.maprealsize[i]==k.maprealsize[i]);
+  if(!same)throw EngineError(DSPH_ERR_ARG,"dsph_constants_upload: the formulation (step algorithm, viscosity, shifting, kernel, phases, periodicity) and the cell domain are fixed at dsph_ctx_create; create a new context to change them.");
+  const double dtpre=symplecticdtpre; const int vs=verletstep;
+  Configure(c);
+  symplecticdtpre=dtpre; verletstep=vs;
+  forcesok=false;    // forces computed with the previous constants must not feed an update
 }
 
 void Engine::FreeAll(){
@@ -130,7 +145,7 @@ void Engine::FreeAll(){
     DevFree(velrhopm1[b]); DevFree(pospre[b]); DevFree(velrhoppre[b]); DevFree(spstau[b]);
     DevFree(rs.keys[b]); DevFree(rs.vals[b]);
   }
-  DevFree(posp); DevFree(acear); DevFree(shiftposfs); DevFree(spsgradvel); DevFree(viscoeta); DevFree(nntau);
+  DevFree(posp); DevFree(posh); DevFree(acear); DevFree(shiftposfs); DevFree(spsgradvel); DevFree(viscoeta); DevFree(nntau);
   DevFree(rs.hist); DevFree(rs.chunksum); DevFree(rs.chunksum2);
   DevFree(begincell); DevFree(sufmin); DevFree(divparams); DevFree(limits); DevFree(fmax); DevFree(perilist); DevFree(pericount);
 }
@@ -149,16 +164,23 @@ void Engine::Allocate(unsigned capacity){
     if(sps)DevAlloc(spstau[b],size_t(cap)*6);
     DevAlloc(rs.keys[b],cap); DevAlloc(rs.vals[b],cap);
   }
-  DevAlloc(posp,size_t(cap)+64);   // padded: the chunked candidate loop of forces_v5.cuh may read a few entries past np
-  CUCHECK(cudaMemsetAsync(posp,0,(size_t(cap)+64)*sizeof(float4),stm));
+  // padded: the chunked candidate loops of the ring kernels read past a lane's own cell range (forces_ring.cuh: up to the
+  // largest cell population among the lanes of a warp + 7 entries; forces_v10.cuh: 16 entries); POSP_PAD bounds the cell
+  // population the ring kernels accept (checked per divide: dp.maxcellpop), denser states run variant 4
+  DevAlloc(posp,size_t(cap)+POSP_PAD);
+  CUCHECK(cudaMemsetAsync(posp,0,(size_t(cap)+POSP_PAD)*sizeof(float4),stm));
+  DevAlloc(posh,(size_t(cap)+POSP_PAD)/2+1);
+  CUCHECK(cudaMemsetAsync(posh,0,((size_t(cap)+POSP_PAD)/2+1)*sizeof(uint4),stm));
   DevAlloc(acear,cap);
   if(cfg.shiftmode)DevAlloc(shiftposfs,cap);
   if(sps)DevAlloc(spsgradvel,size_t(cap)*6);
   const unsigned ntiles=RsTiles(cap);
   rs.capacity=cap; rs.histcap=256u*ntiles;
   DevAlloc(rs.hist,rs.histcap);
-  DevAlloc(rs.chunksum,ScChunks(rs.histcap)+1);
-  DevAlloc(rs.chunksum2,ScChunks(ScChunks(rs.histcap))+1);
+  // scan scratch: used for the digit histograms (histcap entries) AND for the per-particle periodic counts (up to cap entries)
+  rs.chunksumcap=ScChunks(std::max(rs.histcap,cap))+1; rs.chunksum2cap=ScChunks(rs.chunksumcap)+1;
+  DevAlloc(rs.chunksum,rs.chunksumcap);
+  DevAlloc(rs.chunksum2,rs.chunksum2cap);
   const unsigned long long nctmax=(unsigned long long)k.domcells[0]*k.domcells[1]*k.domcells[2];
   if(nctmax*2+6>=0x7fffffffull)throw EngineError(DSPH_ERR_ARG,"The number of cells is too big.");
   maxnctt=unsigned(nctmax*2+6);
@@ -257,7 +279,8 @@ void Engine::RunPeriodic(){
         ker_peri_count<<<(num2+B-1)/B,B,0,stm>>>(pa,flags); launches++;
         // total = last exclusive offset + last count: keep the last count
         SmallCopy(&hpind->scratch[0],flags+(num2-1),4,stm);
-        DeviceExclusiveScan(flags,num2,rs.chunksum,rs.chunksum2,stm,&launches);
+        if(DeviceExclusiveScan(flags,num2,rs.chunksum,rs.chunksumcap,rs.chunksum2,rs.chunksum2cap,stm,&launches)<0)
+          throw EngineError(DSPH_ERR_STATE,"Scan scratch too small for the periodic pass.");
         SmallCopy(&hpind->scratch[1],flags+(num2-1),4,stm);
         CUCHECK(cudaStreamSynchronize(stm));
         const unsigned count=hpin->scratch[0]+hpin->scratch[1];
@@ -319,6 +342,7 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
       ker_div_sufmin_sums<<<1,SM_THREADS,0,stm>>>(sufmin,nchunks); launches++;
       ker_div_sufmin_apply<<<nchunks,SM_THREADS,0,stm>>>(begincell,divparams,sufmin); launches++;
     }
+    ker_div_maxpop<<<(maxnctt+255)/256,256,0,stm>>>(begincell,divparams); launches++;
     ker_div_counts<<<1,1,0,stm>>>(begincell,npb1+npb2,divparams); launches++;
   }
   CUCHECK(cudaEventRecord(ev[5],stm));
@@ -331,7 +355,7 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
     if(cfg.tstep==DSPH_STEP_VERLET){ a.velrhopm1_in=velrhopm1[cur]; a.velrhopm1_out=velrhopm1[o]; }
     if(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre){ a.pospre_in=pospre[cur]; a.pospre_out=pospre[o]; a.velrhoppre_in=velrhoppre[cur]; a.velrhoppre_out=velrhoppre[o]; }
     if(sps){ a.spstau_in=spstau[cur]; a.spstau_out=spstau[o]; }
-    a.posp=posp;
+    a.posp=posp; a.posh=posh;
     if(cfg.nn_on)ker_div_reorder<true><<<(nptot+B-1)/B,B,0,stm>>>(nptot,rs.vals[sidx],a,dc,dph,divparams);
     else ker_div_reorder<false><<<(nptot+B-1)/B,B,0,stm>>>(nptot,rs.vals[sidx],a,dc,dph,divparams);
     launches++;
@@ -396,41 +420,16 @@ ForceParams Engine::MakeForceParams(){
   t.ncx=int(dp.ncx); t.ncy=int(dp.ncy); t.ncz=int(dp.ncz); t.nsheet=int(dp.nsheet);
   t.cellfluid=dp.nct+1;
   for(int i=0;i<3;i++)t.cellzero[i]=dp.cellmin[i];
-  t.begincell=begincell; t.dcell=dcell[cur]; t.posp=posp; t.velrhop=velrhop[cur]; t.code=code[cur];
+  t.begincell=begincell; t.dcell=dcell[cur]; t.posp=posp; t.posh=posh; t.velrhop=velrhop[cur]; t.code=code[cur];
   t.spstau=spstau[cur]; t.spsgradvel=spsgradvel; t.shiftposfs=shiftposfs; t.acear=acear; t.fmax=fmax;
   t.viscoeta=viscoeta; t.nntau=nntau;
   return t;
 }
 
-template<int TKER,int TVISCO,int TDDT,bool SHIFT> static void LaunchFluid(int variant,unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm){
-  if(variant==1){
-    ker_forces_fluid_v1<TKER,TVISCO,TDDT,SHIFT><<<(npf+FORCES_THREADS-1)/FORCES_THREADS,FORCES_THREADS,0,stm>>>(t,c);
-  }
-  else if(variant==2)LaunchFluidV2<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm);
-  else if(variant==4)LaunchFluidV4<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm);
-  else if(variant==5)LaunchFluidV5<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm,64);
-  else if(variant==6)LaunchFluidV5<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm,32);
-  else if(variant==7)LaunchFluidV5<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm,32,1);
-  else if(variant==8)LaunchFluidV5<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm,32,2);
-  else if(variant==9)LaunchFluidV5<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm,32,3);
-  else LaunchFluidV3<TKER,TVISCO,TDDT,SHIFT>(npf,t,c,stm);
-}
-template<int TKER,int TVISCO,int TDDT> static void LaunchFluid3(int variant,bool shift,unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm){
-  if(shift)LaunchFluid<TKER,TVISCO,TDDT,true>(variant,npf,t,c,stm); else LaunchFluid<TKER,TVISCO,TDDT,false>(variant,npf,t,c,stm);
-}
-template<int TKER,int TVISCO> static void LaunchFluid2(int variant,int tddt,bool shift,unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm){
-  switch(tddt){
-    case DSPH_DDT_NONE:     LaunchFluid3<TKER,TVISCO,DSPH_DDT_NONE>(variant,shift,npf,t,c,stm); break;
-    case DSPH_DDT_DDT:      LaunchFluid3<TKER,TVISCO,DSPH_DDT_DDT>(variant,shift,npf,t,c,stm); break;
-    case DSPH_DDT_DDT2:     LaunchFluid3<TKER,TVISCO,DSPH_DDT_DDT2>(variant,shift,npf,t,c,stm); break;
-    case DSPH_DDT_DDT2FULL: LaunchFluid3<TKER,TVISCO,DSPH_DDT_DDT2FULL>(variant,shift,npf,t,c,stm); break;
-    default: throw EngineError(DSPH_ERR_ARG,"Density Diffusion Term mode is not valid.");
-  }
-}
-template<int TKER> static void LaunchFluid1(int variant,int tvisco,int tddt,bool shift,unsigned npf,const ForceParams &t,const DevCtes &c,cudaStream_t stm){
-  if(tvisco==DSPH_VISCO_ARTIFICIAL)LaunchFluid2<TKER,DSPH_VISCO_ARTIFICIAL>(variant,tddt,shift,npf,t,c,stm);
-  else if(tvisco==DSPH_VISCO_LAMINARSPS)LaunchFluid2<TKER,DSPH_VISCO_LAMINARSPS>(variant,tddt,shift,npf,t,c,stm);
-  else throw EngineError(DSPH_ERR_ARG,"Viscosity treatment is not valid.");
+int Engine::EffectiveForceVariant()const{
+  if(cfg.nn_on)return (ringbase_ok && RingVariant()!=4 && RingVariant()!=1 && k.scelldiv==1? RingVariant(): 1);
+  ForceParams t; memset(&t,0,sizeof(t)); t.np=np;
+  return EffectiveFluidVariant(RingVariant(),ringbase_ok,t,dc);
 }
 
 void Engine::Forces(int interstep,dsph_forceres *res){
@@ -450,25 +449,19 @@ void Engine::ForcesLaunch(int interstep){
   const unsigned npf=np-npb;
   const bool shift=(cfg.shiftmode!=0);
   if(npf && cfg.nn_on){
-    const unsigned nl=LaunchForcesNN((ringbase_ok? forcevariant: 1),cfg.tkernel,cfg.tvisco,cfg.tdensity,shift,t,dc,dph,stm);
+    const unsigned nl=LaunchForcesNN((ringbase_ok && RingVariant()!=4? RingVariant(): 1),cfg.tkernel,cfg.tvisco,cfg.tdensity,shift,t,dc,dph,stm);
     if(!nl)throw EngineError(DSPH_ERR_ARG,"Kernel / viscosity / DDT choice is not valid for the multiphase formulation.");
     launches+=nl;
   }
   else if(npf){
-    const int fv=(!ringbase_ok && forcevariant>=7? 6: forcevariant);   // 7, 8, 9 need the ring at the start of the shared window
-    if(cfg.tkernel==DSPH_KERNEL_WENDLAND)LaunchFluid1<DSPH_KERNEL_WENDLAND>(fv,cfg.tvisco,cfg.tdensity,shift,npf,t,dc,stm);
-    else if(cfg.tkernel==DSPH_KERNEL_CUBIC)LaunchFluid1<DSPH_KERNEL_CUBIC>(fv,cfg.tvisco,cfg.tdensity,shift,npf,t,dc,stm);
-    else throw EngineError(DSPH_ERR_ARG,"Kernel choice is not valid.");
+    if(cfg.tkernel!=DSPH_KERNEL_WENDLAND && cfg.tkernel!=DSPH_KERNEL_CUBIC)throw EngineError(DSPH_ERR_ARG,"Kernel choice is not valid.");
+    if(cfg.tvisco!=DSPH_VISCO_ARTIFICIAL && cfg.tvisco!=DSPH_VISCO_LAMINARSPS)throw EngineError(DSPH_ERR_ARG,"Viscosity treatment is not valid.");
+    if(!LaunchForcesFluid(RingVariant(),ringbase_ok,cfg.tkernel,cfg.tvisco,cfg.tdensity,shift,t,dc,stm))throw EngineError(DSPH_ERR_ARG,"Density Diffusion Term mode is not valid.");
     launches++;
-    if(sps){ ker_sps_tau<<<(npf+255)/256,256,0,stm>>>(npf,npb,velrhop[cur],spsgradvel,spstau[cur],dc); launches++; }
+    if(sps){ LaunchSpsTau(npf,npb,velrhop[cur],spsgradvel,spstau[cur],dc,stm); launches++; }
   }
   CUCHECK(cudaEventRecord(ev[13],stm));
-  if(npb){
-    const unsigned nb=(npb+FORCES_THREADS-1)/FORCES_THREADS;
-    if(cfg.tkernel==DSPH_KERNEL_WENDLAND)ker_forces_bound_v1<DSPH_KERNEL_WENDLAND><<<nb,FORCES_THREADS,0,stm>>>(t,dc);
-    else ker_forces_bound_v1<DSPH_KERNEL_CUBIC><<<nb,FORCES_THREADS,0,stm>>>(t,dc);
-    launches++;
-  }
+  if(npb){ LaunchForcesBound(cfg.tkernel,t,dc,stm); launches++; }
   CUCHECK(cudaEventRecord(ev[10],stm));
   forceslaunched=true;
 }
@@ -554,8 +547,8 @@ void Engine::Pips(unsigned long long *fr,unsigned long long *fc,unsigned long lo
   if(!divok)throw EngineError(DSPH_ERR_STATE,"dsph_pips needs a cell division first.");
   CUCHECK(cudaMemsetAsync(fmax,0,sizeof(ForceMax),stm));
   const ForceParams t=MakeForceParams();
-  if(np>npb){ ker_pips<<<(np-npb+FORCES_THREADS-1)/FORCES_THREADS,FORCES_THREADS,0,stm>>>(t,dc,npb,np-npb,1); launches++; }
-  if(npbok){ ker_pips<<<(npbok+FORCES_THREADS-1)/FORCES_THREADS,FORCES_THREADS,0,stm>>>(t,dc,0,npbok,0); launches++; }
+  if(np>npb){ LaunchPips(t,dc,npb,np-npb,1,stm); launches++; }
+  if(npbok){ LaunchPips(t,dc,0,npbok,0,stm); launches++; }
   SmallCopy(&hpind->fmax,fmax,sizeof(ForceMax),stm);
   CUCHECK(cudaStreamSynchronize(stm));
   if(fr)*fr=hpin->fmax.pips_fluid_real; if(fc)*fc=hpin->fmax.pips_fluid_checked;

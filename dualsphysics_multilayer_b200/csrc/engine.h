@@ -40,9 +40,11 @@ class Engine {
   unsigned *idp[2]={}, *dcell[2]={}; typecode *code[2]={};
   double *pos[2]={}; float4 *velrhop[2]={}, *velrhopm1[2]={}, *velrhoppre[2]={}; double *pospre[2]={};
   float *spstau[2]={};
-  float4 *posp=nullptr, *acear=nullptr, *shiftposfs=nullptr; float *spsgradvel=nullptr;
+  static const unsigned POSP_PAD=512;
+  float4 *posp=nullptr; uint4 *posh=nullptr; float4 *acear=nullptr, *shiftposfs=nullptr; float *spsgradvel=nullptr;
   // multiphase non-Newtonian fork (src_mphase): phases + scratch of the SPH velocity-gradient approach
   DevPhases dph; float *viscoeta=nullptr, *nntau=nullptr; float viscetadtmax=0;
+  bool reftail=false;   // test switch, see celldiv.cuh PressFromRhop
   bool sps=false;   // Laminar+SPS of the single-phase solver: SpsTau is particle state (sorted, duplicated, exchanged)
   // cell division
   RadixSortBuffers rs;
@@ -55,8 +57,14 @@ class Engine {
   // forces
   ForceMax *fmax=nullptr;
   float viscdtmax=0; double acemax=0, velmax=0; float lastforcems=0, lastfluidms=0; double fluidms_sum=0; unsigned long long fluid_launches=0;
-  bool ringbase_ok=true;  // the shared-window assumption of variants 7/8 holds on this device/driver (probed at creation)
-  int forcevariant=9;   // 9 = 8 with opposite rows of cells visited back to back (summation order differs from the oracle's); 8 = 7 + packed fp32x2 arithmetic, 7 CTAs/SM; 7 = deferred ring, 32 slots (8 CTAs/SM), OR-addressed slots + offset table; 6 = same ring, first version; 5 = 64 slots; 4 = no ring; 1 = IEEE reference structure
+  bool ringbase_ok=true;  // the shared-window assumption of the ring kernels holds on this device/driver (probed at creation)
+  // fluid force kernel (forces_api.h): 10 = packed-half culling + hit-mask ring (production), 9 = deferred pair ring with fp32 candidate
+  // test (bit-identical results to 10), 4 = plain loop with the division-free body (any cell mode), 1 = IEEE loop in the reference's
+  // structure and pair order (cross-check).  Multiphase: 1 = plain IEEE loops, anything else = ring kernels.
+  int forcevariant=10;
+  // cells denser than the padding of posp/posh allows (POSP_PAD) must not run the unclamped chunk loops of the ring kernels
+  int RingVariant()const{ return (dp.maxcellpop+64u<=POSP_PAD || forcevariant==1)? forcevariant: 4; }
+  int EffectiveForceVariant()const;
   // time stepping
   double symplecticdtpre=0; int verletstep=0;
   dsph_timers tm={}; unsigned long long launches=0;
@@ -64,6 +72,7 @@ class Engine {
   Engine(int device,const dsph_config &c,unsigned capacity);
   ~Engine();
   void Configure(const dsph_config &c);
+  void Reconfigure(const dsph_config &c);   // dsph_constants_upload on a live context: constants only, layout-changing fields are rejected
   void Allocate(unsigned capacity);
   void FreeAll();
   void Upload(unsigned np,unsigned npb,const unsigned *idp,const typecode *code,const double *pos,const float *velrhop);

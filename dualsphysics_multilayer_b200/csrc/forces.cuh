@@ -18,33 +18,10 @@
 // ViscDt / |ace|^2 / |vel|^2 maxima are reduced with warp shuffles and one atomicMax per warp on the float bit
 // pattern (all values >= 0), so no reduction passes and no extra arrays.
 #pragma once
-#include "devtypes.h"
-#include "../../include/dsph_b200.h"
+#include "forceparams.h"
 #include <cfloat>
 
 namespace dsph {
-
-constexpr int FORCES_THREADS=128;
-
-struct ForceParams {
-  unsigned np, npb, npbok;
-  int skipghosts;              // multi-GPU: CODE_PERIODIC fluid particles are halo copies, no forces needed
-  int ncx, ncy, ncz, nsheet;
-  unsigned cellfluid;          // nct+1: offset of the fluid boxes in begincell
-  unsigned cellzero[3];        // CellDomainMin
-  const unsigned* __restrict__ begincell;
-  const unsigned* __restrict__ dcell;
-  const float4* __restrict__ posp;
-  const float4* __restrict__ velrhop;
-  const typecode* __restrict__ code;
-  const float* __restrict__ spstau;     // 6 floats per particle (laminar+SPS)
-  float* __restrict__ spsgradvel;       // 6 floats per particle, OUT
-  float4* __restrict__ shiftposfs;      // OUT (shifting)
-  float4* __restrict__ acear;           // OUT
-  ForceMax* __restrict__ fmax;
-  float* __restrict__ viscoeta;         // multiphase, SPH velocity gradients: effective viscosity per particle
-  float* __restrict__ nntau;            // multiphase, constitutive equation: stress tensor, 6 floats per particle
-};
 
 __device__ __forceinline__ float PowNearOne(float rh,const DevCtes &c){
   // rh^(1/gamma) for the DDT2/3 hydrostatic term (S/JSphCpu.cpp:729-731).  rh=1+ddtgz*drz is within ~1e-2 of 1, where
@@ -170,20 +147,6 @@ __device__ __forceinline__ void WarpMaxToGlobal(float v,unsigned *dst){
   unsigned b=__float_as_uint(v);
   b=__reduce_max_sync(0xffffffffu,b);
   if((threadIdx.x&31)==0 && b)atomicMax(dst,b);
-}
-
-struct NgRange { int cxini,cxfin,yini,yfin,zini,zfin,cx,cy,cz; };
-__device__ __forceinline__ NgRange NgInit(unsigned rcell,const ForceParams &t,const DevCtes &c){
-  // nsearch::Init S/JCellSearch_inline.h:33-52
-  NgRange r;
-  r.cx=int(DcCellx(c.domcellcode,rcell))-int(t.cellzero[0]);
-  r.cy=int(DcCelly(c.domcellcode,rcell))-int(t.cellzero[1]);
-  r.cz=int(DcCellz(c.domcellcode,rcell))-int(t.cellzero[2]);
-  const int sd=c.scelldiv;
-  r.cxini=r.cx-min(r.cx,sd); r.cxfin=r.cx+min(t.ncx-r.cx-1,sd)+1;
-  r.yini=r.cy-min(r.cy,sd);  r.yfin=r.cy+min(t.ncy-r.cy-1,sd)+1;
-  r.zini=r.cz-min(r.cz,sd);  r.zfin=r.cz+min(t.ncz-r.cz-1,sd)+1;
-  return r;
 }
 
 // ---- v1: one thread per fluid particle, direct loop (reference structure; the tuned variants must reproduce it) ----
@@ -323,7 +286,7 @@ template<int TKER> __global__ void __launch_bounds__(FORCES_THREADS) ker_forces_
 }
 
 // ---- SPS stress tensor from the velocity gradient (S/JSphCpu.cpp:930-955) ----
-__global__ void __launch_bounds__(256) ker_sps_tau(unsigned n,unsigned pini,const float4* __restrict__ velrhop,const float* __restrict__ gradvel,float* __restrict__ tau,DevCtes c)
+static __global__ void __launch_bounds__(256) ker_sps_tau(unsigned n,unsigned pini,const float4* __restrict__ velrhop,const float* __restrict__ gradvel,float* __restrict__ tau,DevCtes c)
 {
   const unsigned i=blockIdx.x*blockDim.x+threadIdx.x;
   if(i>=n)return;
@@ -343,7 +306,7 @@ __global__ void __launch_bounds__(256) ker_sps_tau(unsigned n,unsigned pini,cons
 }
 
 // ---- pair counters (JDsPips, S/JDsPips_ker.cu:66): real and checked pairs per particle class ----
-__global__ void __launch_bounds__(FORCES_THREADS) ker_pips(ForceParams t,DevCtes c,unsigned pini1,unsigned n1,int fluid)
+static __global__ void __launch_bounds__(FORCES_THREADS) ker_pips(ForceParams t,DevCtes c,unsigned pini1,unsigned n1,int fluid)
 {
   const unsigned i=blockIdx.x*blockDim.x+threadIdx.x;
   const unsigned p1=pini1+i;

@@ -114,7 +114,7 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT,bool NOBRANCH=false> __device__
   {
     const float dot=drx*dvx+dry*dvy+drz*dvz;
     const float dot_rr2=dot*ovrr;
-    a.visc=fmaxf(dot_rr2,a.visc);
+    a.visc=fmaxf((valid? dot_rr2: 0.f),a.visc);      // rejected pair (variant 10: false positive of the half-precision culling): no effect
     if(TVISCO==DSPH_VISCO_ARTIFICIAL && NOBRANCH){
       const float amubar=c.kernelh*dot_rr2;
       const float ovrobar=FastRcp((rhopp1+velrhop2.w)*0.5f);

@@ -14,9 +14,8 @@
 // Pair order, the fluid-fluid / fluid-boundary split and the order in which the partial sums are added are the oracle's,
 // so Ace/Ar agree with the CPU restatement to rounding of the pair distance (tests/test_gpu_parity.py, nn_* cases).
 #pragma once
-#include "celldiv.cuh"
 #include "forces.cuh"
-#include "forces_v5.cuh"
+#include "forces_ring.cuh"
 
 namespace dsph {
 
@@ -398,7 +397,7 @@ ker_nn_sph_visco(ForceParams t,DevCtes c,DevPhases ph)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// FDA approach, production kernel: the deferred-ring structure of forces_v5.cuh (candidate test -> per-lane ring in shared
+// FDA approach, production kernel: the deferred-ring structure of forces_ring.cuh (candidate test -> per-lane ring in shared
 // memory -> pair rounds at full lane occupancy) with a division-free multiphase pair body.  Same pair order as the plain
 // kernel above (which stays as the IEEE cross-check, variant 1); differs from it only by the rounding of MUFU.RCP/RSQ/EX2.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -529,11 +528,11 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> __device__ __forceinline__ voi
   }
 }
 
-template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __global__ void __launch_bounds__(FORCES_THREADS,7)
+template<int TKER,int TVISCO,int TDDT,bool SHIFT> __global__ void __launch_bounds__(FORCES_THREADS,7)
 ker_nn_fda_ring(ForceParams t,DevCtes c,DevPhases ph)
 {
-  __shared__ __align__(16) V8Smem<V5_Q> qsm;
-  const unsigned q=V8Setup<V5_Q>(qsm.w,c.scell);
+  __shared__ __align__(16) V8Smem qsm;
+  const unsigned q=V8Setup(qsm.w,c.scell);
   const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
   const unsigned p1c=min(p1,t.np-1);
   const unsigned code1=t.code[p1c];
@@ -545,7 +544,7 @@ ker_nn_fda_ring(ForceParams t,DevCtes c,DevPhases ph)
   fp.tau_max=ph.ph[fp.ph].tau_max; fp.bi_multi=ph.ph[fp.ph].bi_multi; fp.mass=ph.ph[fp.ph].mass;
   NNFastAcc a; a.ax=a.ay=a.az=a.ar=a.delta=a.visc=a.visceta=0; a.shift=make_float4(0,0,0,0);
   unsigned anyb=0,nosh=0;
-  V8Traverse<V5_Q>(t,c,active,pp1,t.dcell[p1c],q,[&](unsigned p2,float drx,float dry,float drz,float rr2,float pressp2,bool boundp2,bool valid){
+  V8Traverse(t,c,active,pp1,t.dcell[p1c],q,[&](unsigned p2,float drx,float dry,float drz,float rr2,float pressp2,bool boundp2,bool valid){
     const float4 vr2=__ldg(&t.velrhop[p2]);
     unsigned codep2=0; if(!boundp2 || SHIFT)codep2=t.code[p2];
     NNPairFast<TKER,TVISCO,TDDT,SHIFT>(drx,dry,drz,rr2,fp,vr2,pressp2,boundp2,codep2,valid,c,ph,a,anyb,nosh);
@@ -568,13 +567,13 @@ ker_nn_fda_ring(ForceParams t,DevCtes c,DevPhases ph)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// SPH approach on the ring structure.  RingTraverse is the skeleton of forces_v5.cuh (cell loops, chunked candidate test,
+// SPH approach on the ring structure.  RingTraverse is the skeleton of forces_ring.cuh (cell loops, chunked candidate test,
 // per-lane ring, rounds at full lane occupancy) with the pair body passed in: pair(p2,drx,dry,drz,rr2,pressp2,boundp2,valid).
 // ---------------------------------------------------------------------------------------------------------------------
-template<int V5_Q,class PAIR> __device__ __forceinline__ void RingTraverse(const ForceParams &t,const DevCtes &c,bool active,const float4 &pp1,unsigned rcell,
+template<class PAIR> __device__ __forceinline__ void RingTraverse(const ForceParams &t,const DevCtes &c,bool active,const float4 &pp1,unsigned rcell,
   unsigned q,PAIR &&pair)
 {
-  V8Traverse<V5_Q>(t,c,active,pp1,rcell,q,pair);      // forces_v5.cuh: the skeleton of the production single-phase kernel (variant 8)
+  V8Traverse(t,c,active,pp1,rcell,q,pair);      // forces_ring.cuh: the skeleton of the production single-phase kernel (variant 8)
 }
 
 template<int TKER> __device__ __forceinline__ float NNFacFast(float rr2,const DevCtes &c,float &rinv,float &rad,float &qq){
@@ -585,11 +584,11 @@ template<int TKER> __device__ __forceinline__ float NNFacFast(float rr2,const De
 }
 
 // pass 1: pressure, continuity, DDT, shifting, viscdt + symmetric velocity gradient; epilogue: D, eta_eff (+ tau)
-template<int TKER,int TVISCO,int TDDT,bool SHIFT,int V5_Q> __global__ void __launch_bounds__(FORCES_THREADS,6)
+template<int TKER,int TVISCO,int TDDT,bool SHIFT> __global__ void __launch_bounds__(FORCES_THREADS,6)
 ker_nn_sph_pressgrad_ring(ForceParams t,DevCtes c,DevPhases ph)
 {
-  __shared__ __align__(16) V8Smem<V5_Q> qsm;
-  const unsigned q=V8Setup<V5_Q>(qsm.w,c.scell);
+  __shared__ __align__(16) V8Smem qsm;
+  const unsigned q=V8Setup(qsm.w,c.scell);
   const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
   const unsigned p1c=min(p1,t.np-1);
   const bool active=(p1<t.np);
@@ -601,7 +600,7 @@ ker_nn_sph_pressgrad_ring(ForceParams t,DevCtes c,DevPhases ph)
   NNFastAcc a; a.ax=a.ay=a.az=a.ar=a.delta=a.visc=a.visceta=0; a.shift=make_float4(0,0,0,0);
   float g0=0,g1=0,g2=0,g3=0,g4=0,g5=0;
   unsigned anyb=0,nosh=0;
-  RingTraverse<V5_Q>(t,c,active,pp1,t.dcell[p1c],q,[&](unsigned p2,float drx,float dry,float drz,float rr2,float pressp2,bool boundp2,bool valid){
+  RingTraverse(t,c,active,pp1,t.dcell[p1c],q,[&](unsigned p2,float drx,float dry,float drz,float rr2,float pressp2,bool boundp2,bool valid){
     const float4 velrhop2=__ldg(&t.velrhop[p2]);
     unsigned codep2=0; if(!boundp2 || SHIFT)codep2=t.code[p2];
     const unsigned pp2=(boundp2? fp.ph: (codep2&DSPH_CODE_MASKVALUE));
@@ -694,11 +693,11 @@ ker_nn_sph_pressgrad_ring(ForceParams t,DevCtes c,DevPhases ph)
 }
 
 // pass 2: viscous forces (artificial / Morris with eta1+eta2 / divergence of tau1+tau2), added to acear
-template<int TKER,int TVISCO,int V5_Q> __global__ void __launch_bounds__(FORCES_THREADS,7)
+template<int TKER,int TVISCO> __global__ void __launch_bounds__(FORCES_THREADS,7)
 ker_nn_sph_visco_ring(ForceParams t,DevCtes c,DevPhases ph)
 {
-  __shared__ __align__(16) V8Smem<V5_Q> qsm;
-  const unsigned q=V8Setup<V5_Q>(qsm.w,c.scell);
+  __shared__ __align__(16) V8Smem qsm;
+  const unsigned q=V8Setup(qsm.w,c.scell);
   const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
   const unsigned p1c=min(p1,t.np-1);
   const bool active=(p1<t.np);
@@ -713,7 +712,7 @@ ker_nn_sph_visco_ring(ForceParams t,DevCtes c,DevPhases ph)
     for(int k=0;k<6;k++)tau1[k]=t.nntau[6*size_t(p1c)+k];
   }
   float ax=0,ay=0,az=0;
-  RingTraverse<V5_Q>(t,c,active,pp1,t.dcell[p1c],q,[&](unsigned p2,float drx,float dry,float drz,float rr2,float,bool boundp2,bool valid){
+  RingTraverse(t,c,active,pp1,t.dcell[p1c],q,[&](unsigned p2,float drx,float dry,float drz,float rr2,float,bool boundp2,bool valid){
     const float4 velrhop2=__ldg(&t.velrhop[p2]);
     const unsigned pp2=(boundp2? ph1: (unsigned(t.code[p2])&DSPH_CODE_MASKVALUE));
     const DevPhase &P2=ph.ph[pp2];
@@ -769,14 +768,14 @@ ker_nn_sph_visco_ring(ForceParams t,DevCtes c,DevPhases ph)
 template<int TKER,int TVISCO,int TDDT,bool SHIFT> static unsigned LaunchNN4(int variant,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
   const unsigned npf=t.np-t.npb, nb=(npf+FORCES_THREADS-1)/FORCES_THREADS;
   if(ph.velgrad==DSPH_VELGRAD_FDA){
-    // variant 1: plain IEEE loop (cross-check); otherwise the ring kernel (needs cells of 2h and np < 2^26 like forces_v5.cuh)
-    if(variant!=1 && c.scelldiv==1 && t.np<=V5_IDXMASK)ker_nn_fda_ring<TKER,TVISCO,TDDT,SHIFT,32><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
+    // variant 1: plain IEEE loop (cross-check); otherwise the ring kernel (needs cells of 2h and np < 2^26 like forces_ring.cuh)
+    if(variant!=1 && c.scelldiv==1 && t.np<=V5_IDXMASK)ker_nn_fda_ring<TKER,TVISCO,TDDT,SHIFT><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
     else ker_nn_fda<TKER,TVISCO,TDDT,SHIFT><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
     return 1;
   }
   if(variant!=1 && c.scelldiv==1 && t.np<=V5_IDXMASK){
-    ker_nn_sph_pressgrad_ring<TKER,TVISCO,TDDT,SHIFT,32><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
-    ker_nn_sph_visco_ring<TKER,TVISCO,32><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
+    ker_nn_sph_pressgrad_ring<TKER,TVISCO,TDDT,SHIFT><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
+    ker_nn_sph_visco_ring<TKER,TVISCO><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
   }
   else{
     ker_nn_sph_pressgrad<TKER,TVISCO,TDDT,SHIFT><<<nb,FORCES_THREADS,0,stm>>>(t,c,ph);
@@ -806,7 +805,7 @@ template<int TKER> static unsigned LaunchNN1(int variant,int tvisco,int tddt,boo
 }
 // Interaction of the fluid particles for the multiphase fork (cusphNN::Interaction_ForcesNN, M/JSphGpu_NN_ker.h:31-41).
 // Writes acear (+shiftposfs) for [npb,np) and the four maxima of t.fmax; returns the number of kernels launched.
-static unsigned LaunchForcesNN(int variant,int tkernel,int tvisco,int tdensity,bool shift,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
+unsigned LaunchForcesNN(int variant,int tkernel,int tvisco,int tdensity,bool shift,const ForceParams &t,const DevCtes &c,const DevPhases &ph,cudaStream_t stm){
   if(t.np<=t.npb)return 0;
   if(tkernel==DSPH_KERNEL_WENDLAND)return LaunchNN1<DSPH_KERNEL_WENDLAND>(variant,tvisco,tdensity,shift,t,c,ph,stm);
   if(tkernel==DSPH_KERNEL_CUBIC)return LaunchNN1<DSPH_KERNEL_CUBIC>(variant,tvisco,tdensity,shift,t,c,ph,stm);

@@ -5,8 +5,7 @@
 // (JGaugeVelocity::CalculeCpuT, S/JDsGaugeItem.cpp:325-367: sum over fluid neighbours of W_ab * m/rho_b * f_b) divided by the
 // kernel sum.  One thread per probe point; positions are the double-precision ones (no cell-relative trick needed here).
 #pragma once
-#include "forces.cuh"
-#include "celldiv.cuh"
+#include "forceparams.h"
 
 namespace dsph {
 

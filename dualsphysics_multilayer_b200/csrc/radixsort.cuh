@@ -149,10 +149,12 @@ __global__ void __launch_bounds__(RS_THREADS) ker_rs_scatter(const uint32_t* __r
 inline uint32_t RsTiles(uint32_t n){ return (n+RS_TILE-1)/RS_TILE; }
 inline uint32_t ScChunks(uint32_t m){ return (m+SC_CHUNK-1)/SC_CHUNK; }
 
-// exclusive scan of data[0..m) in place; tmp1 >= ScChunks(m) entries, tmp2 >= ScChunks(ScChunks(m)) entries
-inline int DeviceExclusiveScan(uint32_t *data,uint32_t m,uint32_t *tmp1,uint32_t *tmp2,cudaStream_t stm,unsigned long long *launches){
+// exclusive scan of data[0..m) in place; tmp1 holds tmp1cap >= ScChunks(m) entries, tmp2 >= ScChunks(ScChunks(m)) entries.
+// Returns -1 (nothing launched) when the scratch is too small for m.
+inline int DeviceExclusiveScan(uint32_t *data,uint32_t m,uint32_t *tmp1,uint32_t tmp1cap,uint32_t *tmp2,uint32_t tmp2cap,cudaStream_t stm,unsigned long long *launches){
   if(!m)return 0;
   const uint32_t c1=ScChunks(m);
+  if(c1>tmp1cap || ScChunks(c1)>tmp2cap)return -1;
   ker_scan_chunks<<<c1,SC_THREADS,0,stm>>>(data,m,tmp1); (*launches)++;
   if(c1>1){
     if(c1<=SC_CHUNK*64){ ker_scan_sums<<<1,SC_THREADS,0,stm>>>(tmp1,c1); (*launches)++; }
@@ -177,7 +179,7 @@ inline int RadixSortPairs(RadixSortBuffers &b,uint32_t n,int keybits,int iotaval
   for(int pass=0;pass<npass;pass++){
     const int shift=pass*8;
     ker_rs_hist<<<ntiles,RS_THREADS,0,stm>>>(b.keys[cur],n,shift,ntiles,b.hist); (*launches)++;
-    DeviceExclusiveScan(b.hist,256u*ntiles,b.chunksum,b.chunksum2,stm,launches);
+    DeviceExclusiveScan(b.hist,256u*ntiles,b.chunksum,b.chunksumcap,b.chunksum2,b.chunksum2cap,stm,launches);
     ker_rs_scatter<<<ntiles,RS_THREADS,0,stm>>>(b.keys[cur],b.vals[cur],n,shift,ntiles,b.hist,b.keys[cur^1],b.vals[cur^1],(pass==0 && iotavals)?1:0); (*launches)++;
     cur^=1;
   }

@@ -209,6 +209,12 @@ int dsph_fluid_kernel_stats(dsph_ctx *ctx,double *ms_sum,uint64_t *nlaunch,int r
  * 4-8 bit-identical to each other), 9 = 8 with opposite rows of neighbour cells visited back to back (default; rounding-level
  * difference to 8).  Multiphase runs: 1 = plain loop, anything else = ring kernels. */
 int dsph_set_force_variant(dsph_ctx *ctx,int variant);
+int dsph_get_force_variant(const dsph_ctx *ctx);
+/* TEST SWITCH, off by default.  The reference CPU binary (g++ -O3 -ffast-math) evaluates the pressure of its last Np-4*((Np-1)/4)
+ * particles with rhop/rhop0 and of all others with rhop*(1/rhop0) (scalar epilogue of a vectorised loop, JSphCpu::PreInteractionVars_Forces
+ * S/JSphCpu.cpp:430-470).  on=1 reproduces that index-dependent rounding so that dumps of that binary can be compared at the 1e-5
+ * level on cases of a few thousand particles; the product path keeps one rounding rule for every particle. */
+int dsph_set_refbinary_tail(dsph_ctx *ctx,int on);   /* the variant the next dsph_forces_run will launch (after device-capability fallbacks) */
 int dsph_set_verletstep(dsph_ctx *ctx,int verletstep);
 double dsph_last_force_ms(const dsph_ctx *ctx);
 /* pair counters of the last force evaluation (JDsPips, S/JDsPips_ker.cu:66): real & checked pairs

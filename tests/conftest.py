@@ -29,5 +29,8 @@ def gpu_lib():
     """Product library; the GPU tests fail (not skip) if it is missing or no device is present."""
     import dualsphysics_multilayer_b200 as dsph
     L = dsph.lib()
+    # the CPU checker reproduces an index-dependent rounding artefact of the reference BINARY (oracle/sph_oracle.cpp: scalar epilogue
+    # of the vectorised pressure loop) that the product deliberately does not copy: off when the checker is compared with the CUDA path
+    os.environ["ORC_REFBINARY_TAIL"] = "0"
     assert dsph.device_count() > 0, "no CUDA device: -m gpu tests must run on the B200 box"
     return L

@@ -44,7 +44,14 @@ class Golden:
 
 
 def make_ctx(lib, cfg, capacity=0):
-    return SphContext(lib, cfg, capacity)
+    """Context for a comparison with dumps of the reference BINARY: the CUDA library is asked to reproduce that binary's
+    index-dependent pressure rounding (dsph_set_refbinary_tail, off in production); the CPU checker does it by default."""
+    ctx = SphContext(lib, cfg, capacity)
+    if lib.prefix == "dsph_":
+        fn = lib.lib.dsph_set_refbinary_tail
+        fn.argtypes = [C.c_void_p, C.c_int]
+        fn(ctx.h, 1)
+    return ctx
 
 
 def upload_state(ctx, st, cfg):

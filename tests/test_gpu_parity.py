@@ -104,39 +104,37 @@ def test_gpu_pips_match_oracle(gpu_lib, oracle_lib):
     assert abs(pa[0] - pb[0]) <= 1e-3 * pb[0] and abs(pa[2] - pb[2]) <= 1e-3 * max(pb[2], 1)
 
 
-def test_gpu_force_variants_agree(gpu_lib):
-    """Kernel variants: 1 plain IEEE loop (reference structure), 2 lane FIFO (bit-identical to 1), 3 warp-cooperative,
-    4 division-free body, 5/6 = 4 + deferred pair ring of 64/32 slots, 7 = 6 with OR-addressed ring slots, table-driven cell offsets and
-    a leaner chunk loop, 8 = 7 + packed fp32x2 arithmetic (5-8 bit-identical to 4), 9 = 8 with another order of the rows of cells (production).  3 and 4 differ from 1 only by rounding (fp32 conditioning of the pressure sum)."""
+@pytest.mark.parametrize("opts", [dict(), dict(tkernel=1, tvisco=2, visco=0.01, tdensity=1, shiftmode=3, shiftcoef=-2.0), dict(tdensity=3, shiftmode=1, shiftcoef=-2.0),
+                                  dict(tkernel=1, tdensity=0)])
+def test_gpu_force_variants_agree(gpu_lib, opts):
+    """Kernel variants: 1 plain IEEE loop (reference structure and pair order), 4 division-free body in the same loop, 9 deferred pair
+    ring with the fp32 candidate test (rows of cells in another order), 10 = production: packed-half candidate culling + hit-mask ring.
+    10 accepts exactly the pairs of 9 in the same order with the same arithmetic: BIT-IDENTICAL.  4 and 9 differ from 1 by rounding."""
     cd = dsph.make_case("dambreak", 80000)
+    for k, v in opts.items():
+        setattr(cd.cfg, k, type(getattr(cd.cfg, k))(v))
     ctx = dsph.create_context(cd)
+    assert gpu_lib.lib.dsph_get_force_variant(ctx.h) == 10, "production variant must be the default on this device"
     ctx.upload(cd.idp, cd.pos, cd.velrhop, cd.npb, cd.codes())
     ctx.celldiv(True)
     for _ in range(5):
         ctx.step()
     res = {}
-    for variant in (1, 2, 3, 4, 5, 6, 7, 8, 9):
+    for variant in (1, 4, 9, 10):
         gpu_lib.lib.dsph_set_force_variant(ctx.h, variant)
+        assert gpu_lib.lib.dsph_get_force_variant(ctx.h) == variant
         ctx.celldiv(False)
         fr = ctx.forces()
         res[variant] = (ctx.forces_download(), fr)
     (ace1, ar1), f1 = res[1]
-    (ace2, ar2), f2 = res[2]
-    assert np.array_equal(ace2, ace1) and np.array_equal(ar2, ar1) and f1.dt == f2.dt
-    (ace4, ar4), f4 = res[4]; (ace5, ar5), f5 = res[5]
-    assert np.array_equal(ace5, ace4) and np.array_equal(ar5, ar4) and f4.dt == f5.dt, "v5 (deferred ring) must be bit-identical to v4"
-    (ace6, ar6), f6 = res[6]
-    assert np.array_equal(ace6, ace4) and np.array_equal(ar6, ar4) and f4.dt == f6.dt, "v6 (32-slot ring) must be bit-identical to v4"
-    (ace7, ar7), f7 = res[7]
-    assert np.array_equal(ace7, ace4) and np.array_equal(ar7, ar4) and f4.dt == f7.dt, "v7 must be bit-identical to v4"
-    (ace8, ar8), f8 = res[8]
-    assert np.array_equal(ace8, ace4) and np.array_equal(ar8, ar4) and f4.dt == f8.dt, "v8 (packed fp32x2) must be bit-identical to v4"
-    # 9 (production) visits the rows of cells in another order: rounding-level difference to 4-8
     (ace9, ar9), f9 = res[9]
-    assert rl2(ace9, ace4) < 5e-6 and rl2(ar9, ar4) < 5e-6 and abs(f9.dt - f4.dt) / f4.dt < 1e-6, (rl2(ace9, ace4), rl2(ar9, ar4))
-    for v in (3, 4):
+    (ace10, ar10), f10 = res[10]
+    assert np.array_equal(ace10, ace9) and np.array_equal(ar10, ar9), "v10 (packed-half culling) must be bit-identical to v9"
+    assert f10.dt == f9.dt and f10.viscdtmax == f9.viscdtmax and f10.acemax == f9.acemax
+    for v in (4, 9):
         (ace, ar), f = res[v]
         assert rl2(ace, ace1) < 5e-6 and rl2(ar, ar1) < 5e-6 and abs(f1.dt - f.dt) / f1.dt < 1e-6, (v, rl2(ace, ace1), rl2(ar, ar1))
+    ctx.close()
 
 
 @pytest.mark.gpu
