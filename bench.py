@@ -275,6 +275,7 @@ def main():
     ap.add_argument("--workload", default="dambreak", choices=["dambreak", "periodicbox", "nn2layer"],
                     help="DB(N) is the headline (BASELINE.json); PB(N) and NN(N) are the other single-GPU configs of SURVEY.md 8(d)")
     ap.add_argument("--profile-mgpu", action="store_true", help="N>1: 3 extra untimed steps with per-phase host timers (adds syncs)")
+    ap.add_argument("--python-mgpu", action="store_true", help="N>1: round 1's Python/torch.distributed exchange instead of the library's native NCCL transport")
     ap.add_argument("--bound-weight", type=float, default=0.05, help="N>1: cost of a boundary particle relative to a fluid one when balancing the slabs")
     ap.add_argument("--balance-steps", type=int, default=3, help="N>1: untimed steps before warm-up, each followed by SlabDriver.rebalance with the measured per-rank kernel time")
     a = ap.parse_args()
@@ -372,9 +373,17 @@ def main():
         if a.force_variant:
             l.dsph_set_force_variant(ctx.h, a.force_variant)
         ctx.upload(cd.idp, cd.pos, cd.velrhop, cd.npb, code)
-        drv = mgpu.SlabDriver(ctx, rank, world, cuts, "cuda:%d" % local)
+        # native transport (csrc/mgpu_comm.cu): exchange, dt all-reduce and step sequencing inside the library; --python-mgpu keeps
+        # round 1's torch.distributed-driven exchange for comparison
+        drv = (mgpu.SlabDriver(ctx, rank, world, cuts, "cuda:%d" % local) if a.python_mgpu else mgpu.NativeSlabDriver(ctx, rank, world, cuts))
         drv.celldiv()
-        stepfn = drv.step
+        if a.python_mgpu:
+            stepfn = drv.step
+        else:
+            def stepfn():
+                r = drv.step()
+                drv.update_divinfo()
+                return r
         nglobal = int(info.cfg.casenp)
     for _ in range(a.pre_steps):
         stepfn()
@@ -522,6 +531,8 @@ def main():
             else:
                 dr.celldiv()
                 dr.step()
+                if hasattr(dr, "update_divinfo"):
+                    dr.update_divinfo()
             m = min(cx.np_, cap_out)
             L.check(down(cx.h, 0, m, C.cast(oid.data_ptr(), C.POINTER(C.c_uint32)), C.cast(ocode.data_ptr(), C.POINTER(C.c_uint16)), None,
                          C.cast(opos.data_ptr(), C.POINTER(C.c_double)), C.cast(ovr.data_ptr(), C.POINTER(C.c_float))))
@@ -573,15 +584,23 @@ def main():
 
     phases = None
     if drv is not None and a.profile_mgpu:
-        drv.prof = {}
-        for _ in range(3):
-            drv.step()
-        mine = {k: 1e3 * v / 3 for k, v in drv.prof.items()}
+        if a.python_mgpu:
+            drv.prof = {}
+            for _ in range(3):
+                drv.step()
+            mine = {k: 1e3 * v / 3 for k, v in drv.prof.items()}
+        else:
+            drv.profile(True)
+            for _ in range(3):
+                stepfn()
+            ph, _sent = drv.profile(False)
+            mine = {k: v / 3 for k, v in zip(("xch_classify", "xch_totals_comm_and_host_wait", "xch_pack", "xch_records_comm", "xch_unpack", "dt_allreduce"), ph)}
         mine["np_owned"] = ctx.np_ - int(ctx.divinfo.npbper) - int(ctx.divinfo.npfper)
         mine["np_ghost"] = int(ctx.divinfo.npbper) + int(ctx.divinfo.npfper)
         phases = [None] * world
         dist.all_gather_object(phases, mine)
-        drv.prof = None
+        if a.python_mgpu:
+            drv.prof = None
 
     if rank == 0:
         out = {"metric": METRIC.replace("3D dam-break", WORKLOADS[a.workload][0]), "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -590,7 +609,7 @@ def main():
                "config": {"workload": WORKLOADS[a.workload][1],
                           "np_per_gpu": n, "nfluid": int(cd.cfg.casenfluid), "pre_steps": a.pre_steps, "timed_steps": [win["first_step"], win["first_step"] + a.steps],
                           "np_global": nglobal,
-                          "parallelism": ("single GPU" if world == 1 else "%d x-slabs of balanced work (fluid 1, boundary %g); per divide: NCCL send/recv of migrants + 2h halo copies with <=2 neighbours; per force evaluation: all-reduce(max) of the dt maxima; cuts re-balanced %d times with the measured kernel time per rank before warm-up (%s -> %s)" % (world, a.bound_weight, a.balance_steps, cuts_initial, list(drv.cuts))),
+                          "parallelism": ("single GPU" if world == 1 else "%d x-slabs of balanced work (fluid 1, boundary %g); per divide: ncclSend/ncclRecv of migrants + 2h halo copies with <=2 neighbours; per force evaluation: ncclAllReduce(max) of the dt maxima, both issued by the library on its own stream (%s); cuts re-balanced %d times with the measured kernel time per rank before warm-up (%s -> %s)" % (world, a.bound_weight, "python/torch.distributed exchange" if a.python_mgpu else "native transport, dsph_mgpu_step", a.balance_steps, cuts_initial, list(drv.cuts))),
                           "l2": "working set (np*~230 B) is far larger than the 126 MB L2; no flush needed"},
                "roofline": roofline, "e2e": e2e, "gpu_launches": int(tm.kernel_launches), "clocks": win["clocks"],
                "timers_ms_per_step": {k: getattr(tm, k) / a.steps for k in ("nl_limits", "nl_presort", "nl_radixsort", "nl_cellbegin", "nl_sortdata",

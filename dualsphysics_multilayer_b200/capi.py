@@ -149,6 +149,22 @@ class SphLib:
         f("mgpu_count", C.c_int, vp, C.POINTER(C.c_uint32))
         f("mgpu_pack", C.c_int, vp, C.c_void_p, C.c_void_p)
         f("mgpu_unpack", C.c_int, vp, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p)
+        if prefix == "dsph_":                                   # native transport (NCCL inside the library, mgpu_comm.cu)
+            f("mgpu_unique_id", C.c_int, C.c_void_p)
+            f("mgpu_nccl_version", C.c_int)
+            f("mgpu_comm_init", C.c_int, vp, C.c_void_p, C.c_int, C.c_int)
+            f("mgpu_comm_attach", C.c_int, vp, C.c_void_p, C.c_int, C.c_int)
+            f("mgpu_config_cuts", C.c_int, vp, C.c_int, C.c_int, C.POINTER(C.c_uint32))
+            f("mgpu_halo_cells", C.c_uint32, vp)
+            f("mgpu_exchange", C.c_int, vp)
+            f("mgpu_celldiv", C.c_int, vp, C.POINTER(DivInfo))
+            f("mgpu_forces", C.c_int, vp, C.c_int, C.POINTER(ForceRes))
+            f("mgpu_step", C.c_int, vp, C.POINTER(C.c_double), C.POINTER(ForceRes))
+            f("mgpu_rebalance", C.c_int, vp, C.c_double, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_uint32))
+            f("mgpu_measured_cost", C.c_double, vp)
+            f("mgpu_profile", C.c_int, vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64))
+            f("mgpu_sent_records", C.c_int, vp, C.POINTER(C.c_uint64))
+            f("celldiv_last_info", C.c_int, vp, C.POINTER(DivInfo))
         f("forces_launch", C.c_int, vp, C.c_int)
         f("forces_maxima_ptr", C.c_void_p, vp)
         f("forces_finish", C.c_int, vp, C.POINTER(ForceRes))

@@ -131,6 +131,33 @@ int dsph_mgpu_count(dsph_ctx *ctx,uint32_t counts[8]){ NEEDCTX(ctx); return Guar
 int dsph_mgpu_column_counts(dsph_ctx *ctx,uint32_t *fluid,uint32_t *bound,uint32_t ncol){ NEEDCTX(ctx); if(!fluid||!bound){ g_lasterror="Null argument."; return DSPH_ERR_ARG; } return Guard([&]{ ctx->eng->MgColumnCounts(fluid,bound,ncol); }); }
 int dsph_mgpu_pack(dsph_ctx *ctx,void *sl,void *sr){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgPack(sl,sr); }); }
 int dsph_mgpu_unpack(dsph_ctx *ctx,const uint32_t counts[8],const void *rl,const void *rr){ NEEDCTX(ctx); return Guard([&]{ unsigned c[8]; for(int i=0;i<8;i++)c[i]=counts[i]; ctx->eng->MgUnpack(c,rl,rr); }); }
+// native NCCL transport (mgpu_comm.cu)
+int dsph_mgpu_unique_id(void *id128){ if(!id128){ g_lasterror="Null argument."; return DSPH_ERR_ARG; } return Guard([&]{ dsph::MgUniqueId(id128); }); }
+int dsph_mgpu_nccl_version(void){ return dsph::MgNcclVersion(); }
+int dsph_mgpu_comm_init(dsph_ctx *ctx,const void *id128,int rank,int nranks){ NEEDCTX(ctx); if(!id128){ g_lasterror="Null argument."; return DSPH_ERR_ARG; } return Guard([&]{ ctx->eng->MgCommInit(id128,rank,nranks); }); }
+int dsph_mgpu_comm_attach(dsph_ctx *ctx,void *ncclcomm,int rank,int nranks){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgCommAttach(ncclcomm,rank,nranks); }); }
+int dsph_mgpu_config_cuts(dsph_ctx *ctx,int rank,int nranks,const uint32_t *cuts){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgConfigCuts(rank,nranks,cuts); }); }
+uint32_t dsph_mgpu_halo_cells(const dsph_ctx *ctx){ return (ctx&&ctx->eng)? ctx->eng->MgHalo(): 0u; }
+int dsph_mgpu_exchange(dsph_ctx *ctx){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgExchange(); }); }
+int dsph_celldiv_last_info(dsph_ctx *ctx,dsph_divinfo *info){ NEEDCTX(ctx); if(!info){ g_lasterror="Null argument."; return DSPH_ERR_ARG; } return Guard([&]{ ctx->eng->LastDivInfo(info); }); }
+int dsph_mgpu_sent_records(dsph_ctx *ctx,uint64_t *sent){ NEEDCTX(ctx); if(sent)*sent=ctx->eng->mgsentrecords; return DSPH_OK; }
+int dsph_mgpu_celldiv(dsph_ctx *ctx,dsph_divinfo *info){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgCellDivide(info); ctx->eng->FlushStepTimer(); }); }
+int dsph_mgpu_forces(dsph_ctx *ctx,int interstep,dsph_forceres *res){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgForces(interstep,res); }); }
+int dsph_mgpu_step(dsph_ctx *ctx,double *stepdt,dsph_forceres *res){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgStep(stepdt,res); }); }
+int dsph_mgpu_rebalance(dsph_ctx *ctx,double bound_weight,double rank_cost,int *changed,uint32_t *cuts_out){
+  NEEDCTX(ctx);
+  return Guard([&]{ const bool ch=ctx->eng->MgRebalance(bound_weight,rank_cost,cuts_out); if(changed)*changed=(ch? 1: 0); });
+}
+double dsph_mgpu_measured_cost(dsph_ctx *ctx){ return (ctx&&ctx->eng)? ctx->eng->MgMeasuredCost(): 0; }
+int dsph_mgpu_profile(dsph_ctx *ctx,int on,double phases_ms[6],uint64_t *sent_records){
+  NEEDCTX(ctx); Engine *e=ctx->eng;
+  if(phases_ms)for(int i=0;i<6;i++)phases_ms[i]=e->mgphase_ms[i];
+  if(sent_records)*sent_records=e->mgsentrecords;
+  for(int i=0;i<6;i++)e->mgphase_ms[i]=0;
+  e->mgprofile=(on!=0);
+  return DSPH_OK;
+}
+int dsph_ringbase_ok(const dsph_ctx *ctx){ return (ctx&&ctx->eng && ctx->eng->ringbase_ok)? 1: 0; }
 int dsph_forces_launch(dsph_ctx *ctx,int interstep){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->ForcesLaunch(interstep); }); }
 void* dsph_forces_maxima_ptr(dsph_ctx *ctx){ return (ctx&&ctx->eng)? (void*)ctx->eng->fmax: nullptr; }
 int dsph_forces_finish(dsph_ctx *ctx,dsph_forceres *res){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->ForcesFinish(res); }); }

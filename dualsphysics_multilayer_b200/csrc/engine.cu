@@ -35,6 +35,8 @@ static void SmallCopy(void *dst,const void *src,size_t bytes,cudaStream_t stm){
   ker_small_copy<<<1,32,0,stm>>>((unsigned*)dst,(const unsigned*)src,unsigned(bytes/4));
 }
 
+void Engine::SmallCopyAsync(void *dst,const void *src,size_t bytes){ SmallCopy(dst,src,bytes,stm); }
+
 static int KeyBits(unsigned long long maxkey){ int b=1; while((maxkey>>b)!=0)b++; return b; }
 
 Engine::Engine(int device_,const dsph_config &c,unsigned capacity):device(device_)
@@ -60,6 +62,7 @@ Engine::Engine(int device_,const dsph_config &c,unsigned capacity):device(device
 
 Engine::~Engine(){
   cudaSetDevice(device);
+  MgCommDestroy();
   FreeAll();
   for(int i=0;i<NEVENTS;i++)if(ev[i])cudaEventDestroy(ev[i]);
   if(hpin)cudaFreeHost(hpin);
@@ -381,7 +384,11 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
   boundchanged=false; forcesok=false;
   if(dp.npbout)throw EngineError(DSPH_ERR_PHYSICS,"Boundary particles were excluded from the domain (AbortBoundOut, S/JSph.cpp:2477).");
   AccumTimers(true);
-  if(info){
+  if(info)LastDivInfo(info);
+}
+
+void Engine::LastDivInfo(dsph_divinfo *info)const{
+  {
     memset(info,0,sizeof(*info));
     info->np=np; info->npb=npb; info->npbok=npbok; info->npbper=npbper; info->npfper=npfper;
     info->npbout=dp.npbout; info->npfout=dp.npfout; info->npbignore=dp.npbignore; info->npboutignore=dp.npboutignore; info->npfoutignore=dp.npfoutignore;
@@ -660,23 +667,29 @@ void Engine::MgColumnCounts(unsigned *fluid,unsigned *bound,unsigned ncol){
   CUCHECK(cudaMemcpyAsync(bound,d+ncol,size_t(ncol)*4,cudaMemcpyDeviceToHost,stm));
   CUCHECK(cudaStreamSynchronize(stm));
 }
-void Engine::MgCount(unsigned counts[8]){
+// classification + per-class totals on the stream, no host synchronisation: totals land in mgscratch[1][0..7]
+void Engine::MgClassifyAsync(){
   if(!mgpu)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_count needs dsph_mgpu_config with more than one rank.");
   EnsureDcell();
   const unsigned nb=(np+MG_BLOCK-1)/MG_BLOCK;
-  for(int g=0;g<MG_CLASSES;g++)mgcounts[g]=counts[g]=0;
-  mgcounted=true;
-  if(!np)return;
+  if(!np){ CUCHECK(cudaMemsetAsync(mgscratch[1],0,MG_CLASSES*sizeof(unsigned),stm)); return; }
   MgArgs a; a.np=np; a.npb=npb; a.xlo=mgxlo; a.xhi=mgxhi; a.sd=MgHalo();
   a.hasleft=(mgrank>0); a.hasright=(mgrank<mgnranks-1); a.domcellcode=k.domcellcode; a.dcell=dcell[cur]; a.code=code[cur];
   // one pass: retire the halo copies of the previous divide (dropped by the next sort), classify, count per block
   ker_mg_classify<<<nb,MG_BLOCK,0,stm>>>(a,(unsigned char*)mgscratch[2],mgscratch[0]); launches++;
   ker_mg_scanblocks<<<MG_CLASSES,1024,0,stm>>>(nb,mgscratch[0],mgscratch[1]); launches++;
+}
+void Engine::MgCount(unsigned counts[8]){
+  for(int g=0;g<MG_CLASSES;g++)mgcounts[g]=counts[g]=0;
+  MgClassifyAsync();
+  mgcounted=true;
+  if(!np)return;
   SmallCopy(hpind->mgtot,mgscratch[1],MG_CLASSES*sizeof(unsigned),stm);
   CUCHECK(cudaStreamSynchronize(stm));
   for(int g=0;g<MG_CLASSES;g++)mgcounts[g]=counts[g]=hpin->mgtot[g];
 }
-void Engine::MgPack(void *sendleft,void *sendright){
+// pack kernel on the stream (counts of the classification in mgcounts[])
+void Engine::MgPackAsync(void *sendleft,void *sendright){
   if(!mgcounted)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_pack needs dsph_mgpu_count first.");
   mgcounted=false;
   const unsigned nb=(np+MG_BLOCK-1)/MG_BLOCK;
@@ -696,10 +709,13 @@ void Engine::MgPack(void *sendleft,void *sendright){
     total+=base;
   }
   if(total){ ker_mg_pack<<<nb,MG_BLOCK,0,stm>>>(a,(const unsigned char*)mgscratch[2],mgscratch[0],bases,sp,(char*)sendleft,(char*)sendright); launches++; }
+}
+void Engine::MgPack(void *sendleft,void *sendright){
+  MgPackAsync(sendleft,sendright);
   CUCHECK(cudaStreamSynchronize(stm));
   CUCHECK(cudaGetLastError());
 }
-void Engine::MgUnpack(const unsigned counts[8],const void *recvleft,const void *recvright){
+void Engine::MgUnpackAsync(const unsigned counts[8],const void *recvleft,const void *recvright){
   if(!mgpu)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_unpack needs dsph_mgpu_config with more than one rank.");
   // per side: boundary block (ghosts, migrants) then fluid block (migrants, ghosts)
   const unsigned bgl=counts[0]+counts[1], fl=counts[2]+counts[3], bgr=counts[4]+counts[5], fr=counts[6]+counts[7];
@@ -718,15 +734,25 @@ void Engine::MgUnpack(const unsigned counts[8],const void *recvleft,const void *
   up(fr,(const char*)recvright+size_t(bgr)*d.recbytes);
   npbper=bgl+bgr; npfper=fl+fr; np+=total;
   boundchanged=true;
+}
+void Engine::MgUnpack(const unsigned counts[8],const void *recvleft,const void *recvright){
+  MgUnpackAsync(counts,recvleft,recvright);
   CUCHECK(cudaStreamSynchronize(stm));
   CUCHECK(cudaGetLastError());
+}
+// device ms of this rank's own kernels since the last call (the event timers of the context; waiting for neighbours is not in them)
+double Engine::MgMeasuredCost(){
+  FlushStepTimer();
+  const double c=tm.nl_limits+tm.nl_presort+tm.nl_radixsort+tm.nl_cellbegin+tm.nl_sortdata+tm.nl_outcheck+tm.cf_preforces+tm.cf_forces+tm.su_computestep+tm.su_periodic+tm.su_shifting;
+  const double r=c-mgcostmark; mgcostmark=c;
+  return r;
 }
 
 void Engine::GetTimers(dsph_timers *t,bool reset){
   FlushStepTimer();
   tm.kernel_launches=launches;
   if(t)*t=tm;
-  if(reset){ memset(&tm,0,sizeof(tm)); launches=0; }
+  if(reset){ memset(&tm,0,sizeof(tm)); launches=0; mgcostmark=0; }
 }
 
 } // namespace dsph

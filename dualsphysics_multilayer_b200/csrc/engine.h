@@ -22,7 +22,7 @@ struct HostPinned {
   ForceMax fmax;
   unsigned limitsinit[12];
   unsigned scratch[8];
-  unsigned mgtot[8];
+  unsigned mgtot[16];   // class totals of the slab exchange: [0..7] own (to left, to right), [8..15] announced by the neighbours
   unsigned probe;
 };
 
@@ -83,6 +83,7 @@ class Engine {
   void Download(unsigned first,unsigned count,unsigned *idp,typecode *code,unsigned *dcell,double *pos,float *velrhop);
   void RunPeriodic();
   void CellDivide(bool updateperiodic,dsph_divinfo *info);
+  void LastDivInfo(dsph_divinfo *info)const;
   void GetBeginCell(unsigned *h,unsigned capacity);
   ForceParams MakeForceParams();
   void Forces(int interstep,dsph_forceres *res);
@@ -98,6 +99,24 @@ class Engine {
   unsigned MgHalo()const{ return unsigned(k.scelldiv)*(cfg.nn_on && cfg.nn_velgrad==DSPH_VELGRAD_SPH && cfg.tvisco!=DSPH_VISCO_ARTIFICIAL? 2u: 1u); }
   unsigned MgRecordBytes()const{ return sps? 112u: 88u; }   // pos 24, velrhop 16, pospre 24, velrhoppre|velrhopm1 16, idp 4, code 4 [+ SpsTau 24]
   void MgCount(unsigned counts[8]);
+  void MgClassifyAsync(); void MgPackAsync(void *sendleft,void *sendright); void MgUnpackAsync(const unsigned counts[8],const void *recvleft,const void *recvright);
+  double mgcostmark=0; double MgMeasuredCost();
+  // native transport (mgpu_comm.cu): NCCL communicator of the slab group, exchange buffers, whole-step sequencing
+  void *mgcomm=nullptr; bool mgcomm_own=false;
+  char *mgsend[2]={nullptr,nullptr}, *mgrecv[2]={nullptr,nullptr}; size_t mgsendcap[2]={0,0}, mgrecvcap[2]={0,0};
+  unsigned *mgcntdev=nullptr; double *mghistdev=nullptr; unsigned mghistcap=0;
+  std::vector<unsigned> mgcuts;             // cell columns of all the cuts (nranks+1), needed by the re-balancing
+  unsigned long long mgsentrecords=0; double mgphase_ms[6]={0,0,0,0,0,0}; bool mgprofile=false;
+  void SmallCopyAsync(void *dst,const void *src,size_t bytes);   // 4..128-byte transfers through a one-warp kernel (see engine.cu)
+  void MgCommInit(const void *uid128,int rank,int nranks);
+  void MgCommAttach(void *ncclcomm,int rank,int nranks);
+  void MgCommDestroy();
+  void MgConfigCuts(int rank,int nranks,const unsigned *cuts);
+  void MgExchange();
+  void MgCellDivide(dsph_divinfo *info);
+  void MgForces(int interstep,dsph_forceres *res);
+  void MgStep(double *stepdt,dsph_forceres *res);
+  bool MgRebalance(double bound_weight,double rank_cost,unsigned *cuts_out);
   void MgColumnCounts(unsigned *fluid,unsigned *bound,unsigned ncol);
   void MgPack(void *sendleft,void *sendright);
   void MgUnpack(const unsigned counts[8],const void *recvleft,const void *recvright);
@@ -116,5 +135,8 @@ class Engine {
   void AccumTimers(bool divide);
   void GetTimers(dsph_timers *t,bool reset);
 };
+
+void MgUniqueId(void *id128);   // ncclGetUniqueId (mgpu_comm.cu)
+int MgNcclVersion();
 
 } // namespace dsph

@@ -73,7 +73,11 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT,int Q> __device__ __forceinline
   }
 }
 
-template<int TKER,int TVISCO,int TDDT,bool SHIFT,int MINB=6,int Q=V10_Q> __global__ void __launch_bounds__(FORCES_THREADS,MINB)
+// resident CTAs per SM the kernel is compiled for: 8 (64 registers, <= 12 bytes of spills, 23.33 ms at DB(20 M); 7 CTAs 23.62 ms, 6 CTAs 24.17 ms) for the
+// light instantiations; laminar+SPS and shifting carry 6-10 more accumulators and would spill 30-150 bytes at 64 registers: 6 CTAs (80 registers)
+constexpr int V10MinBlocks(int tvisco,bool shift){ return (tvisco==DSPH_VISCO_ARTIFICIAL && !shift)? 8: 6; }
+
+template<int TKER,int TVISCO,int TDDT,bool SHIFT,int MINB=V10MinBlocks(TVISCO,SHIFT),int Q=V10_Q> __global__ void __launch_bounds__(FORCES_THREADS,MINB)
 ker_forces_fluid_v10(ForceParams t,DevCtes c)
 {
   __shared__ __align__(16) unsigned qsm[Q*FORCES_THREADS*2+64*4];   // ring (8-byte entries) + 64 x float4 cell-offset table

@@ -1,0 +1,268 @@
+// mgpu_comm.cu -- native transport of the x-slab decomposition: the halo / migrant exchange,
+// the all-reduce of the dt maxima, the whole-step sequencing and the re-balancing of the cuts run inside the library on the
+// context's own CUDA stream with NCCL send/recv/all-reduce, one process per GPU.  The reference is single-GPU (vestigial hooks
+// S/DualSphDef.h:494-499, S/JDsDcellDef.h:30-31); the sequence is JSphGpuSingle::ComputeStep_Sym/_Ver (S/JSphGpuSingle.cpp:548-596)
+// with an exchange in front of every RunCellDivide and an all-reduce(max) between the force kernels and DtVariable.
+//
+// Per exchange (one neighbour-list build):
+//   classify + scan (2 kernels)  ->  ncclSend/Recv of the 4+4 class totals with the <= 2 neighbours (device to device)
+//   -> ONE host synchronisation (own + announced totals through the mapped pinned block)
+//   -> pack kernel -> ncclSend/Recv of the records -> unpack kernels, all enqueued on the stream without further host waits.
+// (round 1 drove the same kernels from Python through torch.distributed: 4 stream synchronisations, two P2P rounds with host
+//  waits and ~4.7 ms per step at 8 GPUs.)
+//
+// NCCL is resolved at run time (dlopen: the copy already loaded in the process, e.g. by torch, else the system libnccl.so.2), so the
+// library has no link-time dependency on it and single-GPU users never load it.
+#include "engine.h"
+#include <nccl.h>
+#include <dlfcn.h>
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+#include <cmath>
+#include <chrono>
+
+namespace dsph {
+
+namespace {
+struct NcclApi {
+  void *handle=nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*)=nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*,int,ncclUniqueId,int)=nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t)=nullptr;
+  ncclResult_t (*Send)(const void*,size_t,ncclDataType_t,int,ncclComm_t,cudaStream_t)=nullptr;
+  ncclResult_t (*Recv)(void*,size_t,ncclDataType_t,int,ncclComm_t,cudaStream_t)=nullptr;
+  ncclResult_t (*AllReduce)(const void*,void*,size_t,ncclDataType_t,ncclRedOp_t,ncclComm_t,cudaStream_t)=nullptr;
+  ncclResult_t (*GroupStart)()=nullptr;
+  ncclResult_t (*GroupEnd)()=nullptr;
+  const char* (*GetErrorString)(ncclResult_t)=nullptr;
+  ncclResult_t (*GetVersion)(int*)=nullptr;
+  std::string error;
+  bool Load(){
+    if(handle)return true;
+    const char *names[]={"libnccl.so.2","libnccl.so"};
+    for(const char *n:names){ handle=dlopen(n,RTLD_NOW|RTLD_NOLOAD|RTLD_GLOBAL); if(handle)break; }      // a copy already in the process (torch's)
+    if(!handle)for(const char *n:names){ handle=dlopen(n,RTLD_NOW|RTLD_GLOBAL); if(handle)break; }
+    if(!handle){ error=std::string("NCCL library not found (libnccl.so.2): ")+(dlerror()? dlerror(): ""); return false; }
+    bool ok=true;
+    auto sym=[&](const char *name){ void *p=dlsym(handle,name); if(!p){ ok=false; error=std::string("NCCL symbol missing: ")+name; } return p; };
+    GetUniqueId=(decltype(GetUniqueId))sym("ncclGetUniqueId");
+    CommInitRank=(decltype(CommInitRank))sym("ncclCommInitRank");
+    CommDestroy=(decltype(CommDestroy))sym("ncclCommDestroy");
+    Send=(decltype(Send))sym("ncclSend"); Recv=(decltype(Recv))sym("ncclRecv");
+    AllReduce=(decltype(AllReduce))sym("ncclAllReduce");
+    GroupStart=(decltype(GroupStart))sym("ncclGroupStart"); GroupEnd=(decltype(GroupEnd))sym("ncclGroupEnd");
+    GetErrorString=(decltype(GetErrorString))sym("ncclGetErrorString");
+    GetVersion=(decltype(GetVersion))sym("ncclGetVersion");
+    if(!ok){ handle=nullptr; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+NcclApi& Nccl(){ if(!g_nccl.Load())throw EngineError(DSPH_ERR_STATE,g_nccl.error); return g_nccl; }
+
+#define NCCLCHECK(x) do{ ncclResult_t r_=(x); if(r_!=ncclSuccess)throw EngineError(DSPH_ERR_CUDA,std::string(#x)+": "+Nccl().GetErrorString(r_)); }while(0)
+#define CUCHECK2(x) do{ cudaError_t e_=(x); if(e_!=cudaSuccess)throw EngineError(DSPH_ERR_CUDA,std::string(#x)+": "+cudaGetErrorString(e_)); }while(0)
+
+void GrowBuffer(char *&p,size_t &cap,size_t need){
+  if(need<=cap)return;
+  if(p){ cudaFree(p); p=nullptr; cap=0; }
+  const size_t n=need+need/4+65536;
+  CUCHECK2(cudaMalloc((void**)&p,n));
+  cap=n;
+}
+struct Stopwatch {
+  std::chrono::steady_clock::time_point t0; bool on; cudaStream_t stm;
+  Stopwatch(bool on_,cudaStream_t s):on(on_),stm(s){ if(on){ cudaStreamSynchronize(stm); t0=std::chrono::steady_clock::now(); } }
+  void Lap(double &acc){ if(on){ cudaStreamSynchronize(stm); const auto t=std::chrono::steady_clock::now(); acc+=std::chrono::duration<double,std::milli>(t-t0).count(); t0=t; } }
+};
+} // namespace
+
+void MgUniqueId(void *id128){
+  ncclUniqueId id; NCCLCHECK(Nccl().GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId)==128,"ncclUniqueId is 128 bytes");
+  memcpy(id128,&id,sizeof(id));
+}
+int MgNcclVersion(){ int v=0; if(g_nccl.Load() && g_nccl.GetVersion)g_nccl.GetVersion(&v); return v; }
+
+void Engine::MgCommInit(const void *uid128,int rank,int nranks){
+  if(nranks<1 || rank<0 || rank>=nranks)throw EngineError(DSPH_ERR_ARG,"Invalid rank / number of ranks.");
+  MgCommDestroy();
+  CUCHECK2(cudaSetDevice(device));
+  ncclUniqueId id; memcpy(&id,uid128,sizeof(id));
+  ncclComm_t comm=nullptr;
+  NCCLCHECK(Nccl().CommInitRank(&comm,nranks,id,rank));
+  mgcomm=comm; mgcomm_own=true;
+  if(!mgcntdev)CUCHECK2(cudaMalloc((void**)&mgcntdev,32*sizeof(unsigned)));
+  CUCHECK2(cudaMemsetAsync(mgcntdev,0,32*sizeof(unsigned),stm));
+}
+void Engine::MgCommAttach(void *ncclcomm,int rank,int nranks){
+  if(!ncclcomm || nranks<1 || rank<0 || rank>=nranks)throw EngineError(DSPH_ERR_ARG,"Invalid communicator / rank.");
+  Nccl();
+  MgCommDestroy();
+  CUCHECK2(cudaSetDevice(device));
+  mgcomm=ncclcomm; mgcomm_own=false;
+  if(!mgcntdev)CUCHECK2(cudaMalloc((void**)&mgcntdev,32*sizeof(unsigned)));
+  CUCHECK2(cudaMemsetAsync(mgcntdev,0,32*sizeof(unsigned),stm));
+}
+void Engine::MgCommDestroy(){
+  if(mgcomm && mgcomm_own && g_nccl.handle){ cudaStreamSynchronize(stm); g_nccl.CommDestroy((ncclComm_t)mgcomm); }
+  mgcomm=nullptr; mgcomm_own=false;
+  for(int d=0;d<2;d++){ if(mgsend[d]){ cudaFree(mgsend[d]); mgsend[d]=nullptr; mgsendcap[d]=0; } if(mgrecv[d]){ cudaFree(mgrecv[d]); mgrecv[d]=nullptr; mgrecvcap[d]=0; } }
+  if(mgcntdev){ cudaFree(mgcntdev); mgcntdev=nullptr; }
+  if(mghistdev){ cudaFree(mghistdev); mghistdev=nullptr; mghistcap=0; }
+}
+
+void Engine::MgConfigCuts(int rank,int nranks,const unsigned *cuts){
+  if(nranks<1 || rank<0 || rank>=nranks || !cuts)throw EngineError(DSPH_ERR_ARG,"Invalid slab configuration.");
+  for(int r=0;r<nranks;r++)if(cuts[r]>=cuts[r+1])throw EngineError(DSPH_ERR_ARG,"The cuts must be increasing cell columns.");
+  MgConfig(rank,nranks,cuts[rank],cuts[rank+1]);
+  mgcuts.assign(cuts,cuts+nranks+1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// halo + migrant exchange, one host synchronisation
+// ------------------------------------------------------------------------------------------------
+void Engine::MgExchange(){
+  if(!mgpu)return;
+  if(!mgcomm)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_exchange needs dsph_mgpu_comm_init (or dsph_mgpu_comm_attach) first.");
+  CUCHECK2(cudaSetDevice(device));
+  NcclApi &N=Nccl();
+  ncclComm_t comm=(ncclComm_t)mgcomm;
+  const int left=(mgrank>0? mgrank-1: -1), right=(mgrank<mgnranks-1? mgrank+1: -1);
+  Stopwatch sw(mgprofile,stm);
+  // 1. classify, class totals -> mgscratch[1][0..7] (to left: 0..3, to right: 4..7)
+  MgClassifyAsync();
+  sw.Lap(mgphase_ms[0]);
+  // 2. totals to the neighbours, theirs into mgcntdev[8..15] (from left: 8..11, from right: 12..15; zero without neighbour)
+  NCCLCHECK(N.GroupStart());
+  if(left>=0){  NCCLCHECK(N.Send(mgscratch[1],4,ncclUint32,left,comm,stm));    NCCLCHECK(N.Recv(mgcntdev+8,4,ncclUint32,left,comm,stm)); }
+  if(right>=0){ NCCLCHECK(N.Send(mgscratch[1]+4,4,ncclUint32,right,comm,stm)); NCCLCHECK(N.Recv(mgcntdev+12,4,ncclUint32,right,comm,stm)); }
+  NCCLCHECK(N.GroupEnd());
+  SmallCopyAsync(hpind->mgtot,mgscratch[1],8*sizeof(unsigned));
+  SmallCopyAsync(hpind->mgtot+8,mgcntdev+8,8*sizeof(unsigned));
+  CUCHECK2(cudaStreamSynchronize(stm));                           // the only host wait of the exchange
+  unsigned rcv[8];
+  for(int g=0;g<8;g++){ mgcounts[g]=hpin->mgtot[g]; rcv[g]=hpin->mgtot[8+g]; }
+  if(!np)for(int g=0;g<8;g++)mgcounts[g]=0;
+  mgcounted=true;
+  sw.Lap(mgphase_ms[1]);
+  const size_t rb=MgRecordBytes();
+  const size_t nsend[2]={size_t(mgcounts[0])+mgcounts[1]+mgcounts[2]+mgcounts[3],size_t(mgcounts[4])+mgcounts[5]+mgcounts[6]+mgcounts[7]};
+  const size_t nrecv[2]={size_t(rcv[0])+rcv[1]+rcv[2]+rcv[3],size_t(rcv[4])+rcv[5]+rcv[6]+rcv[7]};
+  for(int d=0;d<2;d++){ GrowBuffer(mgsend[d],mgsendcap[d],std::max<size_t>(nsend[d],1)*rb); GrowBuffer(mgrecv[d],mgrecvcap[d],std::max<size_t>(nrecv[d],1)*rb); }
+  // 3. pack -> records to the neighbours -> unpack, all on the stream
+  MgPackAsync(mgsend[0],mgsend[1]);
+  sw.Lap(mgphase_ms[2]);
+  NCCLCHECK(N.GroupStart());
+  if(left>=0){  if(nsend[0])NCCLCHECK(N.Send(mgsend[0],nsend[0]*rb,ncclUint8,left,comm,stm));   if(nrecv[0])NCCLCHECK(N.Recv(mgrecv[0],nrecv[0]*rb,ncclUint8,left,comm,stm)); }
+  if(right>=0){ if(nsend[1])NCCLCHECK(N.Send(mgsend[1],nsend[1]*rb,ncclUint8,right,comm,stm));  if(nrecv[1])NCCLCHECK(N.Recv(mgrecv[1],nrecv[1]*rb,ncclUint8,right,comm,stm)); }
+  NCCLCHECK(N.GroupEnd());
+  sw.Lap(mgphase_ms[3]);
+  MgUnpackAsync(rcv,mgrecv[0],mgrecv[1]);
+  sw.Lap(mgphase_ms[4]);
+  mgsentrecords+=nsend[0]+nsend[1];
+}
+
+void Engine::MgCellDivide(dsph_divinfo *info){
+  MgExchange();
+  CellDivide(false,info);
+}
+
+// force kernels, all-reduce(max) of the maxima (uint bit patterns of non-negative floats: integer max = float max), dt
+void Engine::MgForces(int interstep,dsph_forceres *res){
+  ForcesLaunch(interstep);
+  if(mgpu){
+    if(!mgcomm)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_step needs dsph_mgpu_comm_init first.");
+    Stopwatch sw(mgprofile,stm);
+    NCCLCHECK(Nccl().AllReduce(fmax,fmax,4,ncclUint32,ncclMax,(ncclComm_t)mgcomm,stm));
+    sw.Lap(mgphase_ms[5]);
+  }
+  ForcesFinish(res);
+}
+
+void Engine::MgStep(double *stepdt,dsph_forceres *res){
+  double dt;
+  if(cfg.tstep==DSPH_STEP_SYMPLECTIC){
+    dt=symplecticdtpre;
+    MgForces(DSPH_INTERSTEP_SYMPREDICTOR,nullptr);
+    const double ddt_p=DtVariable(nullptr,nullptr);
+    StepSymPre(dt);
+    MgCellDivide(nullptr); FlushStepTimer();
+    MgForces(DSPH_INTERSTEP_SYMCORRECTOR,res);
+    const double ddt_c=DtVariable(nullptr,nullptr);
+    StepSymCor(dt);
+    symplecticdtpre=std::min(ddt_p,ddt_c);
+  }
+  else{
+    MgForces(DSPH_INTERSTEP_VERLET,res);
+    dt=DtVariable(nullptr,nullptr);
+    StepVerlet(dt);
+  }
+  MgCellDivide(nullptr); FlushStepTimer();
+  if(stepdt)*stepdt=dt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// re-balancing (collective): new cuts from the global per-column histogram of owned particles (fluid 1, boundary bound_weight),
+// scaled per slab to the measured cost of its rank when rank_cost>0 on every rank.  A cut moves by less than the width of the
+// narrower of its two slabs, so a particle changes owner by at most one rank; the next exchange migrates fluid AND boundary
+// particles that are outside the new range.  Returns true when the cuts changed (the caller then runs dsph_mgpu_celldiv).
+// ------------------------------------------------------------------------------------------------
+static std::vector<unsigned> BalancedCuts(const std::vector<double> &col,int nranks,unsigned minwidth){
+  const unsigned ncol=unsigned(col.size());
+  std::vector<double> cum(ncol+1,0.0);
+  for(unsigned i=0;i<ncol;i++)cum[i+1]=cum[i]+col[i];
+  std::vector<unsigned> cuts(1,0u);
+  for(int r=1;r<nranks;r++){
+    const double target=cum[ncol]*r/nranks;
+    unsigned c=unsigned(std::lower_bound(cum.begin(),cum.end(),target)-cum.begin());
+    c=std::max(c,cuts.back()+minwidth);
+    c=std::min(c,ncol-unsigned(nranks-r)*minwidth);
+    cuts.push_back(c);
+  }
+  cuts.push_back(ncol);
+  return cuts;
+}
+
+bool Engine::MgRebalance(double bound_weight,double rank_cost,unsigned *cuts_out){
+  if(!mgpu)return false;
+  if(!mgcomm || int(mgcuts.size())!=mgnranks+1)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_rebalance needs dsph_mgpu_comm_init and dsph_mgpu_config_cuts first.");
+  CUCHECK2(cudaSetDevice(device));
+  const unsigned ncol=k.domcells[0];
+  const unsigned minwidth=2u*MgHalo()+1u;
+  if(unsigned(mgnranks)*minwidth>ncol)throw EngineError(DSPH_ERR_ARG,"Too many ranks for the cell columns of the domain.");
+  std::vector<unsigned> fl(ncol),bd(ncol);
+  MgColumnCounts(fl.data(),bd.data(),ncol);
+  const unsigned nval=ncol+unsigned(mgnranks);
+  if(mghistcap<nval){ if(mghistdev)cudaFree(mghistdev); CUCHECK2(cudaMalloc((void**)&mghistdev,size_t(nval)*sizeof(double))); mghistcap=nval; }
+  std::vector<double> h(nval,0.0);
+  for(unsigned i=0;i<ncol;i++)h[i]=double(fl[i])+bound_weight*double(bd[i]);
+  h[ncol+mgrank]=rank_cost;
+  CUCHECK2(cudaMemcpyAsync(mghistdev,h.data(),size_t(nval)*sizeof(double),cudaMemcpyHostToDevice,stm));
+  NCCLCHECK(Nccl().AllReduce(mghistdev,mghistdev,nval,ncclDouble,ncclSum,(ncclComm_t)mgcomm,stm));
+  CUCHECK2(cudaMemcpyAsync(h.data(),mghistdev,size_t(nval)*sizeof(double),cudaMemcpyDeviceToHost,stm));
+  CUCHECK2(cudaStreamSynchronize(stm));
+  std::vector<double> hist(h.begin(),h.begin()+ncol);
+  bool costs_ok=true;
+  for(int r=0;r<mgnranks;r++)if(!(h[ncol+r]>0))costs_ok=false;
+  if(costs_ok)for(int r=0;r<mgnranks;r++){
+    double tot=0; for(unsigned i=mgcuts[r];i<mgcuts[r+1];i++)tot+=hist[i];
+    if(tot>0){ const double f=h[ncol+r]/tot; for(unsigned i=mgcuts[r];i<mgcuts[r+1];i++)hist[i]*=f; }
+  }
+  const std::vector<unsigned> target=BalancedCuts(hist,mgnranks,minwidth);
+  std::vector<unsigned> nw(mgcuts);
+  for(int r=1;r<mgnranks;r++){
+    const long long room=(long long)std::min(mgcuts[r]-mgcuts[r-1],mgcuts[r+1]-mgcuts[r])-1;
+    const long long lo=(long long)mgcuts[r]-room, hi=(long long)mgcuts[r]+room;
+    nw[r]=unsigned(std::min(std::max((long long)target[r],lo),hi));
+  }
+  for(int r=1;r<mgnranks;r++)nw[r]=std::max(nw[r],nw[r-1]+minwidth);        // keep every slab at least minwidth wide
+  for(int r=mgnranks-1;r>0;r--)nw[r]=std::min(nw[r],nw[r+1]-minwidth);
+  if(cuts_out)for(int r=0;r<=mgnranks;r++)cuts_out[r]=nw[r];
+  if(nw==mgcuts)return false;
+  MgConfigCuts(mgrank,mgnranks,nw.data());
+  return true;
+}
+
+} // namespace dsph

@@ -238,6 +238,87 @@ class SlabDriver:
         return {k: v[keep] for k, v in st.items()}
 
 
+class NativeSlabDriver:
+    """The same interface as SlabDriver over the library's native transport (csrc/mgpu_comm.cu): the exchange, the dt all-reduce,
+    the step sequencing and the re-balancing run inside libdsph_b200.so with NCCL on the context's own stream -- this class only
+    forwards.  torch.distributed is used once, to hand rank 0's 128-byte ncclUniqueId to the other ranks (any channel would do:
+    bin/dsph_b200 -mgpu uses threads of one process)."""
+
+    def __init__(self, ctx: capi.SphContext, rank: int, world: int, cuts, device: str = None, group=None, uid: bytes = None):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        lib = ctx.lib
+        if uid is None:
+            box = [None]
+            if rank == 0:
+                buf = C.create_string_buffer(128)
+                lib.check(lib.fn("mgpu_unique_id")(buf))
+                box[0] = bytes(buf.raw)
+            dist.broadcast_object_list(box, src=0, group=group)
+            uid = box[0]
+        self.cuts = [int(c) for c in cuts]
+        lib.check(lib.fn("mgpu_comm_init")(ctx.h, C.c_char_p(uid), rank, world))
+        self._set_cuts(self.cuts)
+        self.recbytes = int(lib.fn("mgpu_record_bytes")(ctx.h))
+        self.halo = int(lib.fn("mgpu_halo_cells")(ctx.h))
+        self._prof_on = False
+
+    def _set_cuts(self, cuts):
+        arr = (C.c_uint32 * (self.world + 1))(*cuts)
+        self.ctx.lib.check(self.ctx.lib.fn("mgpu_config_cuts")(self.ctx.h, self.rank, self.world, arr))
+
+    def exchange(self):
+        self.ctx.lib.check(self.ctx.lib.fn("mgpu_exchange")(self.ctx.h))
+
+    def celldiv(self):
+        info = capi.DivInfo()
+        self.ctx.lib.check(self.ctx.lib.fn("mgpu_celldiv")(self.ctx.h, C.byref(info)))
+        self.ctx.divinfo = info
+        return info
+
+    def forces(self, interstep):
+        r = capi.ForceRes()
+        self.ctx.lib.check(self.ctx.lib.fn("mgpu_forces")(self.ctx.h, interstep, C.byref(r)))
+        return r
+
+    def step(self):
+        dt = C.c_double(); r = capi.ForceRes()
+        self.ctx.lib.check(self.ctx.lib.fn("mgpu_step")(self.ctx.h, C.byref(dt), C.byref(r)))
+        return dt.value, r
+
+    def rebalance(self, bound_weight=0.05, minwidth=None, rank_cost=None):
+        ch = C.c_int(0); out = (C.c_uint32 * (self.world + 1))()
+        self.ctx.lib.check(self.ctx.lib.fn("mgpu_rebalance")(self.ctx.h, float(bound_weight), float(-1.0 if rank_cost is None else rank_cost), C.byref(ch), out))
+        self.cuts = [int(v) for v in out]
+        return bool(ch.value)
+
+    def measured_cost(self):
+        return float(self.ctx.lib.fn("mgpu_measured_cost")(self.ctx.h))
+
+    def profile(self, on):
+        """Switch the per-phase host timers on/off; returns (phases_ms[6], sent_records) accumulated since the last call."""
+        ph = (C.c_double * 6)(); sent = C.c_uint64()
+        self.ctx.lib.check(self.ctx.lib.fn("mgpu_profile")(self.ctx.h, 1 if on else 0, ph, C.byref(sent)))
+        return list(ph), int(sent.value)
+
+    @property
+    def sent_records(self):
+        sent = C.c_uint64()
+        self.ctx.lib.check(self.ctx.lib.fn("mgpu_sent_records")(self.ctx.h, C.byref(sent)))
+        return int(sent.value)
+
+    def update_divinfo(self):
+        """DivInfo of the last divide (dsph_mgpu_step runs its own divides)."""
+        info = capi.DivInfo()
+        self.ctx.lib.check(self.ctx.lib.fn("celldiv_last_info")(self.ctx.h, C.byref(info)))
+        self.ctx.divinfo = info
+        return info
+
+    def owned(self):
+        st = self.ctx.download()
+        keep = (st["code"] & capi.CODE_MASKSPECIAL) == capi.CODE_NORMAL
+        return {k: v[keep] for k, v in st.items()}
+
+
 def slab_select(pos_x: np.ndarray, cuts, rank: int, scell: float, domposmin_x: float):
     """Boolean mask of the particles whose cell column lies in the slab of `rank` (same arithmetic as the cell hash)."""
     cx = ((pos_x - domposmin_x) / scell).astype(np.int64)

@@ -250,6 +250,41 @@ int dsph_mgpu_pack(dsph_ctx *ctx,void *send_left,void *send_right);
 int dsph_mgpu_unpack(dsph_ctx *ctx,const uint32_t counts[8],const void *recv_left,const void *recv_right);
 /* owned (CODE_NORMAL) particles per cell column of the domain, fluid and boundary separately; ncol = domcells[0] */
 int dsph_mgpu_column_counts(dsph_ctx *ctx,uint32_t *fluid,uint32_t *bound,uint32_t ncol);
+
+/* ---- 5b. native transport (NCCL inside the library, no Python / torch on the path).  SURVEY.md 8b asked for
+ *      dsph_ctx_create(device, ncclComm*), dsph_halo_exchange, dsph_migrate: here the communicator is attached to a context after
+ *      creation (dsph_mgpu_comm_attach: a ncclComm_t the host application owns; or dsph_mgpu_comm_init: the library creates it from
+ *      a 128-byte ncclUniqueId that rank 0 obtained with dsph_mgpu_unique_id and distributed by any means), halo exchange and
+ *      migration are one call (dsph_mgpu_exchange: classify -> class totals to the neighbours -> ONE host wait -> pack ->
+ *      ncclSend/ncclRecv of the records -> unpack, all on the context's stream), and
+ *        dsph_mgpu_celldiv = dsph_mgpu_exchange + dsph_celldiv_run(updateperiodic=0)
+ *        dsph_mgpu_forces  = dsph_forces_launch + ncclAllReduce(max) of the four maxima + dsph_forces_finish
+ *        dsph_mgpu_step    = dsph_step with those two in place of RunCellDivide / Interaction_Forces (S/JSphGpuSingle.cpp:548-596)
+ *      dsph_mgpu_rebalance (collective) moves the cuts to the measured load: per-column histogram of owned particles (fluid 1,
+ *      boundary bound_weight) all-reduced, scaled per slab by rank_cost (e.g. dsph_mgpu_measured_cost: device ms of this rank's own
+ *      kernels since the last call; <=0 on any rank = histogram only); *changed=1 -> call dsph_mgpu_celldiv next.  cuts_out (optional)
+ *      receives the nranks+1 cut columns.  NCCL is loaded with dlopen at the first of these calls. ------- */
+int dsph_mgpu_unique_id(void *id128);
+int dsph_mgpu_nccl_version(void);
+int dsph_mgpu_comm_init(dsph_ctx *ctx,const void *id128,int rank,int nranks);
+int dsph_mgpu_comm_attach(dsph_ctx *ctx,void *ncclcomm,int rank,int nranks);
+int dsph_mgpu_config_cuts(dsph_ctx *ctx,int rank,int nranks,const uint32_t *cuts);   /* = dsph_mgpu_config with all nranks+1 cut columns known */
+uint32_t dsph_mgpu_halo_cells(const dsph_ctx *ctx);                                    /* halo width in cells; a slab must be >= 2*halo+1 columns wide */
+int dsph_mgpu_exchange(dsph_ctx *ctx);
+int dsph_mgpu_celldiv(dsph_ctx *ctx,dsph_divinfo *info);
+int dsph_mgpu_forces(dsph_ctx *ctx,int interstep,dsph_forceres *res);
+int dsph_mgpu_step(dsph_ctx *ctx,double *stepdt,dsph_forceres *res);
+int dsph_mgpu_rebalance(dsph_ctx *ctx,double bound_weight,double rank_cost,int *changed,uint32_t *cuts_out);
+double dsph_mgpu_measured_cost(dsph_ctx *ctx);
+/* per-phase host timers of the exchange (adds stream synchronisations while on): classify, totals exchange + host wait, pack,
+ * records send/recv, unpack, dt all-reduce [ms accumulated since the last call]; records sent so far */
+int dsph_mgpu_profile(dsph_ctx *ctx,int on,double phases_ms[6],uint64_t *sent_records);
+int dsph_mgpu_sent_records(dsph_ctx *ctx,uint64_t *sent_records);
+/* the dsph_divinfo of the most recent divide (dsph_step / dsph_mgpu_step run their own divides) */
+int dsph_celldiv_last_info(dsph_ctx *ctx,dsph_divinfo *info);
+/* 1 when the ring kernels (variants 9, 10, multiphase ring) can run on this device/driver (shared-window probe at creation);
+ * 0 = the plain kernels run instead, a large performance cliff that the driver reports in Run.out */
+int dsph_ringbase_ok(const dsph_ctx *ctx);
 int dsph_forces_launch(dsph_ctx *ctx,int interstep);
 void* dsph_forces_maxima_ptr(dsph_ctx *ctx);
 /* the CUDA stream (cudaStream_t) every kernel of this context is launched on: lets the caller order its collective after

@@ -31,7 +31,8 @@ def main():
         cuts = [cuts[0]] + [min(c + 4, dcells[0] - 3 * (world - i)) for i, c in enumerate(cuts[1:-1], 1)] + [cuts[-1]]
     sel = mgpu.slab_select(cd.pos[:, 0], cuts, rank, scell, dmin[0])
     ctx.upload(cd.idp[sel], cd.pos[sel], cd.velrhop[sel], int(np.count_nonzero(sel[: cd.npb])), code[sel])
-    drv = mgpu.SlabDriver(ctx, rank, world, cuts, "cuda:%d" % local)
+    native = os.environ.get("DSPH_MGPU_DRIVER", "native") == "native"      # native = NCCL inside libdsph_b200.so (dsph_mgpu_step)
+    drv = mgpu.NativeSlabDriver(ctx, rank, world, cuts) if native else mgpu.SlabDriver(ctx, rank, world, cuts, "cuda:%d" % local)
     drv.celldiv()
     t = 0.0
     moved = 0
