@@ -131,6 +131,59 @@ def load_part(filename: str):
     return _case_from_c(c), t.value, st.value
 
 
+def _case_to_c(cd: CaseData):
+    """ctypes view of a CaseData (the numpy arrays are returned too: they must outlive the call)."""
+    c = Case()
+    c.cfg = cd.cfg
+    c.np, c.npb = cd.np_, cd.npb
+    idp = np.ascontiguousarray(cd.idp, np.uint32)
+    pos = np.ascontiguousarray(cd.pos, np.float64)
+    vr = np.ascontiguousarray(cd.velrhop, np.float32)
+    c.idp = idp.ctypes.data_as(C.POINTER(C.c_uint32))
+    c.pos_xyz = pos.ctypes.data_as(C.POINTER(C.c_double))
+    c.velrhop_xyzw = vr.ctypes.data_as(C.POINTER(C.c_float))
+    for i in range(3):
+        c.caseposmin[i] = cd.caseposmin[i]
+        c.caseposmax[i] = cd.caseposmax[i]
+    c.name = cd.name.encode()
+    c.nfluidblocks = len(cd.fluidblocks)
+    for i, n in enumerate(cd.fluidblocks):
+        c.fluidblock_count[i] = n
+    return c, (idp, pos, vr)
+
+
+def save_partset(cd: CaseData, dirout: str, cpart: int, timestep: float, step: int = 0, symplecticdtpre: float = 0.0, piecemax: int = 0,
+                 out=None) -> None:
+    """Host only: the PART output set of one instant (Part_Head.ibi4, Part_NNNN.bi4 or its pieces, PartInfo.ibi4, PartOut_000.obi4).
+    out = (idp, pos[n,3], velrhop[n,4], motive) of the excluded particles, or None."""
+    c, keep = _case_to_c(cd)
+    os.makedirs(dirout, exist_ok=True)
+    L = lib()
+    fn = L.lib.dsph_partset_save
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(Case), C.c_char_p, C.c_uint32, C.c_double, C.c_uint32, C.c_double, C.c_uint32, C.c_uint32,
+                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    if out is None:
+        L.check(fn(C.byref(c), dirout.encode(), cpart, timestep, step, symplecticdtpre, piecemax, 0, None, None, None, None))
+    else:
+        oid = np.ascontiguousarray(out[0], np.uint32); opos = np.ascontiguousarray(out[1], np.float64)
+        ovr = np.ascontiguousarray(out[2], np.float32); omo = np.ascontiguousarray(out[3], np.uint8)
+        L.check(fn(C.byref(c), dirout.encode(), cpart, timestep, step, symplecticdtpre, piecemax, len(oid),
+                   oid.ctypes.data, opos.ctypes.data, ovr.ctypes.data, omo.ctypes.data))
+
+
+def load_partset(dirname: str, cpart: int):
+    """Every piece of PART `cpart` in `dirname`, concatenated.  Returns (CaseData, timestep, step, npiece)."""
+    c = Case()
+    L = lib()
+    t = C.c_double(); st = C.c_uint32(); npc = C.c_uint32()
+    fn = L.lib.dsph_partset_load
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.check(fn(C.byref(c), dirname.encode(), cpart, C.byref(t), C.byref(st), C.byref(npc)))
+    return _case_from_c(c), t.value, st.value, npc.value
+
+
 def save_case(cd: CaseData, dirname: str, casename: str) -> None:
     c = Case()
     c.cfg = cd.cfg
@@ -162,14 +215,18 @@ class _RunOpts(C.Structure):
     _fields_ = [("dir", C.c_char_p), ("casename", C.c_char_p), ("dirout", C.c_char_p),
                 ("device", C.c_int32), ("nsteps", C.c_int32), ("savepart", C.c_int32), ("forcevariant", C.c_int32),
                 ("timemax", C.c_double), ("timeout", C.c_double), ("restart", C.c_int32), ("partbegin", C.c_int32),
-                ("partbegindir", C.c_char_p)]
+                ("partbegindir", C.c_char_p), ("mgpu", C.c_int32), ("rebalancesteps", C.c_int32), ("boundweight", C.c_double),
+                ("piecemax", C.c_uint32), ("reserved_", C.c_uint32)]
 
 
 def run_case(dirname: str, casename: str, dirout: str, device: int = 0, nsteps: int = 0, savepart: bool = True,
-             timemax: float = -1.0, timeout: float = -1.0, partbegin: int = -1, partbegindir: str = None) -> None:
-    """The stand-alone driver (dsph_run_case_ex): Case.xml + Case.bi4 in, Part_NNNN.bi4 / Run.out / Run.csv out."""
+             timemax: float = -1.0, timeout: float = -1.0, partbegin: int = -1, partbegindir: str = None,
+             mgpu: int = 0, rebalancesteps: int = 0, piecemax: int = 0) -> None:
+    """The stand-alone driver (dsph_run_case_ex): Case.xml + Case.bi4 in, Part_Head.ibi4 / Part_NNNN.bi4 (or pieces) /
+    PartInfo.ibi4 / PartOut_000.obi4 / Run.out / Run.csv out.  mgpu > 1: x-slab run on that many GPUs of this process."""
     L = lib()
     o = _RunOpts(dirname.encode(), casename.encode(), dirout.encode(), device, nsteps, 1 if savepart else 0, 0,
-                 timemax, timeout, 1 if partbegin >= 0 else 0, max(partbegin, 0), partbegindir.encode() if partbegindir else None)
+                 timemax, timeout, 1 if partbegin >= 0 else 0, max(partbegin, 0), partbegindir.encode() if partbegindir else None,
+                 mgpu, rebalancesteps, 0.0, piecemax, 0)
     L.lib.dsph_run_case_ex.argtypes = [C.POINTER(_RunOpts)]
     L.check(L.lib.dsph_run_case_ex(C.byref(o)))

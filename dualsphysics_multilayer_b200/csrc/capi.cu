@@ -4,6 +4,8 @@
 #include "host/casefile.h"
 #include "host/driver.h"
 #include "host/bi4.h"
+#include "host/partset.h"
+#include <vector>
 #include <cstring>
 #include <string>
 #include <new>
@@ -236,12 +238,67 @@ int dsph_part_load(dsph_case *out,const char *file,double *timestep,uint32_t *st
   });
   return r==DSPH_OK? r: DSPH_ERR_IO;
 }
+static void CaseFromC(const dsph_case *c,CaseData &cd){
+  cd.cfg=c->cfg; cd.name=c->name;
+  cd.idp.assign(c->idp,c->idp+c->np); cd.pos.assign(c->pos_xyz,c->pos_xyz+size_t(c->np)*3); cd.velrhop.assign(c->velrhop_xyzw,c->velrhop_xyzw+size_t(c->np)*4);
+  memcpy(cd.caseposmin,c->caseposmin,24); memcpy(cd.caseposmax,c->caseposmax,24);
+  if(c->cfg.casenfixed)cd.blocks.push_back({0,0,cd.mkboundfirst,0,c->cfg.casenfixed});
+  if(c->nfluidblocks>1){ unsigned beg=c->cfg.casenfixed; for(unsigned b=0;b<c->nfluidblocks;b++){ cd.blocks.push_back({3,b,cd.mkfluidfirst+b,beg,c->fluidblock_count[b]}); beg+=c->fluidblock_count[b]; } }
+  else cd.blocks.push_back({3,0,cd.mkfluidfirst,c->cfg.casenfixed,c->cfg.casenfluid});
+}
+int dsph_partset_save(const dsph_case *c,const char *dirout,uint32_t cpart,double timestep,uint32_t step,double symplecticdtpre,uint32_t piecemax,
+                      uint32_t nout,const uint32_t *out_idp,const double *out_pos,const float *out_velrhop,const uint8_t *out_motive){
+  if(!c||!dirout||(nout && (!out_idp||!out_pos||!out_velrhop||!out_motive))){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  const int r=Guard([&]{
+    CaseData cd; CaseFromC(c,cd);
+    SphConst k; DeriveConstants(cd.cfg,k);
+    PartSetHead head; MakePartSetHead(head,cd,k.maprealposmin,k.maprealposmax,k.periactive,k.perixinc,k.periyinc,k.perizinc);
+    PartSet ps(dirout,head,0,1,0,piecemax? piecemax: PartSet::PIECE_MAX_DEFAULT,true);
+    ps.SaveHead();
+    PartMeta m; m.cpart=cpart; m.timestep=timestep; m.step=step; m.nout=nout; m.symplecticdtpre=symplecticdtpre;
+    const unsigned n=c->np;
+    for(int i=0;i<3;i++){ m.domainmin[i]=k.domposmin[i]; m.domainmax[i]=k.domposmax[i]; }
+    std::vector<float> vel(size_t(n)*3),rhop(n);
+    for(unsigned q=0;q<n;q++){ vel[3*size_t(q)]=c->velrhop_xyzw[4*size_t(q)]; vel[3*size_t(q)+1]=c->velrhop_xyzw[4*size_t(q)+1]; vel[3*size_t(q)+2]=c->velrhop_xyzw[4*size_t(q)+2]; rhop[q]=c->velrhop_xyzw[4*size_t(q)+3]; }
+    PartInfoPlus info; info.on=true; info.npf=n-c->npb; info.npbin=c->npb; info.npused=n; info.npalloc=n;
+    ps.SavePart(m,n,c->idp,c->pos_xyz,vel.data(),rhop.data(),&info);
+    std::vector<float> ovel(size_t(nout)*3),orhop(nout);
+    for(unsigned q=0;q<nout;q++){ ovel[3*size_t(q)]=out_velrhop[4*size_t(q)]; ovel[3*size_t(q)+1]=out_velrhop[4*size_t(q)+1]; ovel[3*size_t(q)+2]=out_velrhop[4*size_t(q)+2]; orhop[q]=out_velrhop[4*size_t(q)+3]; }
+    const bool ro=(cd.cfg.rhopoutmin<cd.cfg.rhopoutmax);
+    ps.SaveOut(cpart,timestep,nout,out_idp,out_pos,ovel.data(),orhop.data(),out_motive,ro? cd.cfg.rhopoutmin: 0.f,ro? cd.cfg.rhopoutmax: 0.f);
+  });
+  return r==DSPH_OK? r: DSPH_ERR_IO;
+}
+int dsph_partset_load(dsph_case *out,const char *dir,uint32_t cpart,double *timestep,uint32_t *step,uint32_t *npiece){
+  if(!out||!dir){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  const int r=Guard([&]{
+    PartHead h; PartData p; LoadPartPieces(dir,cpart,h,p);
+    CaseData cd; ConfigDefaults(cd.cfg);
+    cd.cfg.casenp=unsigned(h.casenp); cd.cfg.casenfixed=unsigned(h.casenfixed); cd.cfg.casenmoving=unsigned(h.casenmoving);
+    cd.cfg.casenfloat=unsigned(h.casenfloat); cd.cfg.casenfluid=unsigned(h.casenfluid);
+    cd.cfg.dp=h.dp; cd.cfg.kernelh=float(h.h); cd.cfg.cteb=float(h.b); cd.cfg.rhopzero=float(h.rhop0); cd.cfg.gamma=float(h.gamma);
+    cd.cfg.massbound=float(h.massbound); cd.cfg.massfluid=float(h.massfluid); cd.cfg.simulate2d=(h.data2d? 1: 0);
+    memcpy(cd.caseposmin,h.caseposmin,24); memcpy(cd.caseposmax,h.caseposmax,24);
+    memcpy(cd.cfg.maprealposmin,h.mapposmin,24); memcpy(cd.cfg.maprealposmax,h.mapposmax,24);
+    cd.name=h.casename;
+    cd.idp=p.idp; cd.pos=p.pos; cd.velrhop.resize(size_t(p.npok)*4);
+    for(unsigned i=0;i<p.npok;i++){ cd.velrhop[4*size_t(i)]=p.vel[3*size_t(i)]; cd.velrhop[4*size_t(i)+1]=p.vel[3*size_t(i)+1]; cd.velrhop[4*size_t(i)+2]=p.vel[3*size_t(i)+2]; cd.velrhop[4*size_t(i)+3]=p.rhop[i]; }
+    CaseToC(cd,out);
+    unsigned nb=0; for(unsigned id:cd.idp)if(id<cd.cfg.casenfixed+cd.cfg.casenmoving)nb++;
+    out->npb=nb;
+    if(timestep)*timestep=p.timestep;
+    if(step)*step=p.step;
+    if(npiece)*npiece=h.npiece;
+  });
+  return r==DSPH_OK? r: DSPH_ERR_IO;
+}
 int dsph_run_case_ex(const dsph_runopts *r){
   if(!r||!r->dir||!r->casename||!r->dirout){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
   return Guard([&]{
     RunOptions o; o.dir=r->dir; o.casename=r->casename; o.dirout=r->dirout; o.device=r->device; o.nsteps=r->nsteps; o.savepart=(r->savepart!=0);
     o.timemax=r->timemax; o.timeout=r->timeout; o.forcevariant=r->forcevariant;
     o.partbegin=(r->restart? r->partbegin: -1); if(r->partbegindir)o.partbegindir=r->partbegindir;
+    o.mgpu=r->mgpu; o.rebalancesteps=r->rebalancesteps; o.boundweight=r->boundweight; o.piecemax=r->piecemax;
     RunCase(o);
   });
 }

@@ -63,6 +63,8 @@ Engine::Engine(int device_,const dsph_config &c,unsigned capacity):device(device
 Engine::~Engine(){
   cudaSetDevice(device);
   MgCommDestroy();
+  if(stmcopy){ cudaStreamSynchronize(stmcopy); cudaStreamDestroy(stmcopy); cudaEventDestroy(evsnap); cudaEventDestroy(evsnapfree); }
+  if(snapdev)cudaFree(snapdev);
   FreeAll();
   for(int i=0;i<NEVENTS;i++)if(ev[i])cudaEventDestroy(ev[i]);
   if(hpin)cudaFreeHost(hpin);
@@ -258,6 +260,59 @@ void Engine::Download(unsigned first,unsigned count,unsigned *hidp,typecode *hco
 }
 
 // ------------------------------------------------------------------------------------------------
+// PART snapshots
+// ------------------------------------------------------------------------------------------------
+void Engine::HostSnapAlloc(HostSnap &hs,unsigned capacity){
+  CUCHECK(cudaSetDevice(device));
+  HostSnapFree(hs);
+  CUCHECK(cudaHostAlloc((void**)&hs.idp,size_t(capacity)*4,cudaHostAllocDefault));
+  CUCHECK(cudaHostAlloc((void**)&hs.code,size_t(capacity)*sizeof(typecode),cudaHostAllocDefault));
+  CUCHECK(cudaHostAlloc((void**)&hs.pos,size_t(capacity)*24,cudaHostAllocDefault));
+  CUCHECK(cudaHostAlloc((void**)&hs.velrhop,size_t(capacity)*16,cudaHostAllocDefault));
+  CUCHECK(cudaEventCreateWithFlags(&hs.done,cudaEventDisableTiming));
+  hs.capacity=capacity; hs.np=0;
+}
+void Engine::HostSnapFree(HostSnap &hs){
+  if(hs.done){ cudaEventSynchronize(hs.done); cudaEventDestroy(hs.done); hs.done=nullptr; }
+  if(hs.idp)cudaFreeHost(hs.idp); if(hs.code)cudaFreeHost(hs.code); if(hs.pos)cudaFreeHost(hs.pos); if(hs.velrhop)cudaFreeHost(hs.velrhop);
+  hs.idp=nullptr; hs.code=nullptr; hs.pos=nullptr; hs.velrhop=nullptr; hs.capacity=0;
+}
+void Engine::SnapshotBegin(HostSnap &hs){
+  CUCHECK(cudaSetDevice(device));
+  if(np>hs.capacity)throw EngineError(DSPH_ERR_ARG,"Snapshot buffers are smaller than the number of particles.");
+  if(!stmcopy){
+    CUCHECK(cudaStreamCreateWithFlags(&stmcopy,cudaStreamNonBlocking));
+    CUCHECK(cudaEventCreateWithFlags(&evsnap,cudaEventDisableTiming));
+    CUCHECK(cudaEventCreateWithFlags(&evsnapfree,cudaEventDisableTiming));
+  }
+  if(snapcap<cap){                                   // 46 bytes per particle: idp 4, code 2, pos 24, velrhop 16
+    if(snapdev){ CUCHECK(cudaStreamSynchronize(stmcopy)); cudaFree(snapdev); snapdev=nullptr; }
+    CUCHECK(cudaMalloc((void**)&snapdev,size_t(cap)*48));
+    snapcap=cap; snapbusy=false;
+  }
+  char *dpos=snapdev, *dvr=snapdev+size_t(snapcap)*24, *did=dvr+size_t(snapcap)*16, *dcode=did+size_t(snapcap)*4;
+  const size_t n=np;
+  if(snapbusy)CUCHECK(cudaStreamWaitEvent(stm,evsnapfree,0));          // the previous snapshot has left the staging area
+  CUCHECK(cudaMemcpyAsync(dpos,pos[cur],n*24,cudaMemcpyDeviceToDevice,stm));
+  CUCHECK(cudaMemcpyAsync(dvr,velrhop[cur],n*16,cudaMemcpyDeviceToDevice,stm));
+  CUCHECK(cudaMemcpyAsync(did,idp[cur],n*4,cudaMemcpyDeviceToDevice,stm));
+  CUCHECK(cudaMemcpyAsync(dcode,code[cur],n*sizeof(typecode),cudaMemcpyDeviceToDevice,stm));
+  CUCHECK(cudaEventRecord(evsnap,stm));
+  CUCHECK(cudaStreamWaitEvent(stmcopy,evsnap,0));
+  CUCHECK(cudaMemcpyAsync(hs.pos,dpos,n*24,cudaMemcpyDeviceToHost,stmcopy));
+  CUCHECK(cudaMemcpyAsync(hs.velrhop,dvr,n*16,cudaMemcpyDeviceToHost,stmcopy));
+  CUCHECK(cudaMemcpyAsync(hs.idp,did,n*4,cudaMemcpyDeviceToHost,stmcopy));
+  CUCHECK(cudaMemcpyAsync(hs.code,dcode,n*sizeof(typecode),cudaMemcpyDeviceToHost,stmcopy));
+  CUCHECK(cudaEventRecord(evsnapfree,stmcopy));
+  CUCHECK(cudaEventRecord(hs.done,stmcopy));
+  hs.np=np; snapbusy=true;
+}
+void Engine::SnapshotWait(const HostSnap &hs){
+  CUCHECK(cudaSetDevice(device));
+  if(hs.done)CUCHECK(cudaEventSynchronize(hs.done));
+}
+
+// ------------------------------------------------------------------------------------------------
 // Periodic duplicates (JSphCpuSingle::RunPeriodic order, S/JSphCpuSingle.cpp:361-431)
 // ------------------------------------------------------------------------------------------------
 void Engine::RunPeriodic(){
@@ -382,6 +437,16 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
   npfout_last=dp.npfout; npout_total+=dp.npfout;
   np=dp.npfinal; npb=dp.npbfinal; npbok=npb-dp.npbignore;
   boundchanged=false; forcesok=false;
+  if(keepout && dp.npfout){
+    // excluded fluid particles sit right behind the kept ones in the sorted arrays (boxes: ..., BoundOut, FluidOut, ...)
+    const size_t o=outidp.size(), n=dp.npfout, first=size_t(dp.npfinal)+dp.npbout;
+    outidp.resize(o+n); outcode.resize(o+n); outpos.resize((o+n)*3); outvelrhop.resize((o+n)*4);
+    CUCHECK(cudaMemcpyAsync(outidp.data()+o,idp[cur]+first,n*4,cudaMemcpyDeviceToHost,stm));
+    CUCHECK(cudaMemcpyAsync(outcode.data()+o,code[cur]+first,n*sizeof(typecode),cudaMemcpyDeviceToHost,stm));
+    CUCHECK(cudaMemcpyAsync(outpos.data()+o*3,pos[cur]+first*3,n*24,cudaMemcpyDeviceToHost,stm));
+    CUCHECK(cudaMemcpyAsync(outvelrhop.data()+o*4,velrhop[cur]+first,n*16,cudaMemcpyDeviceToHost,stm));
+    CUCHECK(cudaStreamSynchronize(stm));
+  }
   if(dp.npbout)throw EngineError(DSPH_ERR_PHYSICS,"Boundary particles were excluded from the domain (AbortBoundOut, S/JSph.cpp:2477).");
   AccumTimers(true);
   if(info)LastDivInfo(info);

@@ -81,6 +81,16 @@ class Engine {
   void SetVelrhopM1(const float *h);
   void SetSpsTau(const float *h);
   void Download(unsigned first,unsigned count,unsigned *idp,typecode *code,unsigned *dcell,double *pos,float *velrhop);
+  // PART snapshots (SURVEY.md 8f-2, S/JSphGpuSingle.cpp:889-935 SaveData): a device-side copy of the live state on the solver's
+  // stream (the only thing the time loop waits for), then D2H into pinned host buffers on a copy stream while the next steps run
+  struct HostSnap { unsigned *idp=nullptr; typecode *code=nullptr; double *pos=nullptr; float *velrhop=nullptr; unsigned capacity=0, np=0; cudaEvent_t done=nullptr; };
+  cudaStream_t stmcopy=nullptr; cudaEvent_t evsnap=nullptr, evsnapfree=nullptr; char *snapdev=nullptr; unsigned snapcap=0; bool snapbusy=false;
+  void HostSnapAlloc(HostSnap &hs,unsigned capacity);
+  void HostSnapFree(HostSnap &hs);
+  void SnapshotBegin(HostSnap &hs);                 // returns at once; hs.done fires when the host buffers are complete
+  void SnapshotWait(const HostSnap &hs);            // host wait for hs.done (any thread)
+  // excluded fluid particles of every divide are kept on the host until the caller takes them (JDsPartsOut, S/JSph.cpp:2467-2471)
+  bool keepout=false; std::vector<unsigned> outidp; std::vector<typecode> outcode; std::vector<double> outpos; std::vector<float> outvelrhop;
   void RunPeriodic();
   void CellDivide(bool updateperiodic,dsph_divinfo *info);
   void LastDivInfo(dsph_divinfo *info)const;
@@ -111,6 +121,7 @@ class Engine {
   void MgCommInit(const void *uid128,int rank,int nranks);
   void MgCommAttach(void *ncclcomm,int rank,int nranks);
   void MgCommDestroy();
+  void MgCommAbort();
   void MgConfigCuts(int rank,int nranks,const unsigned *cuts);
   void MgExchange();
   void MgCellDivide(dsph_divinfo *info);
@@ -136,6 +147,7 @@ class Engine {
   void GetTimers(dsph_timers *t,bool reset);
 };
 
+std::vector<unsigned> MgBalancedCuts(const std::vector<double> &columnweight,int nranks,unsigned minwidth);   // nranks+1 cut columns
 void MgUniqueId(void *id128);   // ncclGetUniqueId (mgpu_comm.cu)
 int MgNcclVersion();
 

@@ -53,6 +53,7 @@ void Bi4Item::SetBool(const std::string &n,bool v){ int i=v?1:0; memcpy(Slot(n,B
 void Bi4Item::SetInt(const std::string &n,int v){ memcpy(Slot(n,BI4_INT).raw,&v,4); }
 void Bi4Item::SetUint(const std::string &n,unsigned v){ memcpy(Slot(n,BI4_UINT).raw,&v,4); }
 void Bi4Item::SetUllong(const std::string &n,unsigned long long v){ memcpy(Slot(n,BI4_ULLONG).raw,&v,8); }
+void Bi4Item::SetLlong(const std::string &n,long long v){ memcpy(Slot(n,BI4_LLONG).raw,&v,8); }
 void Bi4Item::SetFloat(const std::string &n,float v){ memcpy(Slot(n,BI4_FLOAT).raw,&v,4); }
 void Bi4Item::SetDouble(const std::string &n,double v){ memcpy(Slot(n,BI4_DOUBLE).raw,&v,8); }
 void Bi4Item::SetDouble3(const std::string &n,const double v[3]){ memcpy(Slot(n,BI4_DOUBLE3).raw,v,24); }
@@ -94,6 +95,11 @@ Bi4Array& Bi4Item::AddArray(const std::string &n,int type,unsigned count,const v
   a.data.resize(sz); if(sz)memcpy(a.data.data(),data,sz);
   return a;
 }
+Bi4Array& Bi4Item::AddArrayRef(const std::string &n,int type,unsigned count,const void *data){
+  arrays.emplace_back(); Bi4Array &a=arrays.back();
+  a.name=n; a.type=type; a.count=count; a.ext=data; a.extsize=ArrayElemSize(type)*size_t(count);
+  return a;
+}
 const Bi4Array* Bi4Item::FindArray(const std::string &n)const{
   for(auto &a:arrays)if(a.name==n)return &a;
   return nullptr;
@@ -115,28 +121,34 @@ static void PutValues(Sink &s,const Bi4Item &it){
     else s.raw(v.raw,Bi4TypeSize(v.type));
   }
 }
-static void PutItemDef(Sink &s,const Bi4Item &it,unsigned sizevalues){
+// `all` = false leaves hidden arrays / items (and the values of items with hidevalues) out of the file, and the counts of the
+// item record are those of the visible ones (JBinaryData::InItemBase, S/JBinaryData.cpp:853-865).
+static void PutItemDef(Sink &s,const Bi4Item &it,unsigned sizevalues,bool all){
+  unsigned na=0,ni=0;
+  for(auto &a:it.arrays)if(all||!a.hide)na++;
+  for(auto &c:it.items)if(all||!c->hide)ni++;
   s.str(kCodeItem); s.str(it.name); s.boolean(it.hide); s.boolean(it.hidevalues);
   s.str(it.fmtfloat); s.str(it.fmtdouble);
-  s.u32((unsigned)it.arrays.size()); s.u32((unsigned)it.items.size()); s.u32(sizevalues);
+  s.u32(na); s.u32(ni); s.u32((all||!it.hidevalues)? sizevalues: 0u);
 }
 static void PutArrayDef(Sink &s,const Bi4Array &a){
-  s.str(kCodeArray); s.str(a.name); s.boolean(a.hide); s.i32(a.type); s.u32(a.count); s.u32((unsigned)a.data.size());
+  s.str(kCodeArray); s.str(a.name); s.boolean(a.hide); s.i32(a.type); s.u32(a.count); s.u32((unsigned)a.DataSize());
 }
-static void WriteItem(FILE *f,const Bi4Item &it){
+static void WriteItem(FILE *f,const Bi4Item &it,bool all){
   Sink vals; PutValues(vals,it);
-  Sink def; PutItemDef(def,it,(unsigned)vals.b.size());
+  Sink def; PutItemDef(def,it,(unsigned)vals.b.size(),all);
   unsigned sz=(unsigned)def.b.size();
   fwrite(&sz,4,1,f); fwrite(def.b.data(),1,def.b.size(),f);
-  fwrite(vals.b.data(),1,vals.b.size(),f);
-  for(auto &a:it.arrays){
+  if(all||!it.hidevalues)fwrite(vals.b.data(),1,vals.b.size(),f);
+  for(auto &a:it.arrays)if(all||!a.hide){
     if(a.type==BI4_TEXT)throw std::runtime_error("bi4: text arrays are not supported");
+    if(a.DataSize()>=(size_t(1)<<32))throw std::runtime_error("bi4: array '"+a.name+"' is larger than 4 GB (use several pieces)");
     Sink ad; PutArrayDef(ad,a);
     unsigned asz=(unsigned)ad.b.size();
     fwrite(&asz,4,1,f); fwrite(ad.b.data(),1,ad.b.size(),f);
-    if(!a.data.empty())fwrite(a.data.data(),1,a.data.size(),f);
+    if(a.DataSize())fwrite(a.DataPtr(),1,a.DataSize(),f);
   }
-  for(auto &c:it.items)WriteItem(f,*c);
+  for(auto &c:it.items)if(all||!c->hide)WriteItem(f,*c,all);
 }
 
 static void MakeHead(const std::string &filecode,unsigned char head[64]){
@@ -148,17 +160,45 @@ static void MakeHead(const std::string &filecode,unsigned char head[64]){
   head[58]='\n'; head[60]=0; // byteorder 0 = little endian
 }
 
-void Bi4Save(const std::string &file,const Bi4Item &root){
+void Bi4Save(const std::string &file,const Bi4Item &root,bool all){
   FILE *f=fopen(file.c_str(),"wb");
   if(!f)throw std::runtime_error("bi4: cannot open file for writing: "+file);
   unsigned char head[64]; MakeHead(root.name,head);
   fwrite(head,1,64,f);
-  WriteItem(f,root);
+  WriteItem(f,root,all);
   const bool bad=ferror(f)!=0;
   const long long fsize=ftell(f);
   fclose(f);
   if(bad)throw std::runtime_error("bi4: file writing failure: "+file);
   if(fsize>=(1ll<<32))throw std::runtime_error("bi4: file is larger than 4 GB (use several pieces): "+file);
+}
+
+// JBinaryData::SaveFileListApp (S/JBinaryData.cpp:1555-1571): a list file is the 64-byte header with `filecode`, the parent item
+// (written once, when the file is created) and then one item record per call, appended.
+void Bi4AppendList(const std::string &file,const std::string &filecode,const Bi4Item &parent,const Bi4Item &item,bool all){
+  FILE *f=fopen(file.c_str(),"rb");
+  long long fsize=0;
+  if(f){
+    unsigned char got[64]; const size_t n=fread(got,1,64,f);
+    fseek(f,0,SEEK_END); fsize=ftell(f); fclose(f);
+    if(fsize){
+      unsigned char head[64]; MakeHead(filecode,head);
+      if(n<64 || memcmp(got,head,58)!=0 || got[60]!=0)throw std::runtime_error("bi4: the file code is invalid: "+file);
+    }
+  }
+  f=fopen(file.c_str(),fsize? "ab": "wb");
+  if(!f)throw std::runtime_error("bi4: cannot open the file: "+file);
+  if(!fsize){
+    unsigned char head[64]; MakeHead(filecode,head);
+    fwrite(head,1,64,f);
+    WriteItem(f,parent,all);
+  }
+  WriteItem(f,item,all);
+  const bool bad=ferror(f)!=0;
+  const long long fend=ftell(f);
+  fclose(f);
+  if(bad)throw std::runtime_error("bi4: file writing failure: "+file);
+  if(fend>=(1ll<<32))throw std::runtime_error("bi4: file is larger than 4 GB: "+file);
 }
 
 static void ReadItem(Source &s,Bi4Item &it){

@@ -35,6 +35,9 @@ struct Bi4Array {
   int type=BI4_NULL;
   unsigned count=0;
   std::vector<unsigned char> data; // count*Bi4TypeSize(type) bytes
+  const void *ext=nullptr; size_t extsize=0;   // AddArrayRef: the caller's buffer is written as is (no copy), it must outlive the save
+  const void* DataPtr()const{ return ext? ext: (const void*)data.data(); }
+  size_t DataSize()const{ return ext? extsize: data.size(); }
 };
 
 struct Bi4Item {
@@ -52,6 +55,7 @@ struct Bi4Item {
   void SetInt(const std::string &n,int v);
   void SetUint(const std::string &n,unsigned v);
   void SetUllong(const std::string &n,unsigned long long v);
+  void SetLlong(const std::string &n,long long v);
   void SetFloat(const std::string &n,float v);
   void SetDouble(const std::string &n,double v);
   void SetDouble3(const std::string &n,const double v[3]);
@@ -69,13 +73,17 @@ struct Bi4Item {
   void GetDouble3(const std::string &n,double out[3],bool optional=false)const;
   // ---- arrays / children ----
   Bi4Array& AddArray(const std::string &n,int type,unsigned count,const void *data);
+  Bi4Array& AddArrayRef(const std::string &n,int type,unsigned count,const void *data);
   const Bi4Array* FindArray(const std::string &n)const;
   Bi4Item& AddItem(const std::string &n);
   const Bi4Item* FindItem(const std::string &n)const;
 };
 
 // Writes `root` as a bi4 file whose file code is root.name (e.g. "JPartDataBi4").
-void Bi4Save(const std::string &file,const Bi4Item &root);
+// all=false: hidden arrays / items are left out (JBinaryData::SaveFile(file,memory,all)).
+void Bi4Save(const std::string &file,const Bi4Item &root,bool all=true);
+// Appends `item` to the list file (created with header + `parent` when missing): JBinaryData::SaveFileListApp.
+void Bi4AppendList(const std::string &file,const std::string &filecode,const Bi4Item &parent,const Bi4Item &item,bool all);
 // Loads a bi4 file; filecode (if not empty) is validated against the header like CheckHead.
 std::unique_ptr<Bi4Item> Bi4Load(const std::string &file,const std::string &filecode);
 

@@ -5,6 +5,7 @@
 #include "driver.h"
 #include "casefile.h"
 #include "bi4.h"
+#include "partset.h"
 #include "../engine.h"
 #include <chrono>
 #include <cstdio>
@@ -12,6 +13,8 @@
 #include <cmath>
 #include <algorithm>
 #include <vector>
+#include <deque>
+#include <atomic>
 #include <thread>
 #include <mutex>
 #include <condition_variable>
@@ -40,72 +43,99 @@ double NextTime(double t,double tout){
 }
 }
 
-// PART output: the state is copied off the device by the time loop (one D2H per array), everything else --
-// dropping the halo/periodic copies, building the bi4 container and writing it -- runs on a writer thread while the
-// simulation goes on.  One job in flight: a new PART waits for the previous file to be complete.
+// PART output (S/JSphGpuSingle.cpp:889-935 SaveData, S/JSph.cpp:2581-2711 SavePartData).  The time loop only enqueues
+// a device-side copy of the state (Engine::SnapshotBegin, ~0.3 ms per 20 M particles); the D2H transfer into one of two pinned host
+// buffers runs on a copy stream and -- dropping the halo/periodic copies, building the bi4 containers, writing Part_NNNN.bi4 (or the
+// pieces), PartInfo.ibi4 and PartOut_BBB.obi4 -- on a writer thread, all while the simulation goes on.  A new PART only waits when
+// both host buffers are still in use.
 struct PartJob {
-  std::string file; PartHead h; PartData p;
-  std::vector<unsigned> idp; std::vector<typecode> code; std::vector<double> pos; std::vector<float> vr;
+  int slot=-1; PartMeta meta; PartInfoPlus info;
+  std::vector<unsigned> outidp; std::vector<typecode> outcode; std::vector<double> outpos; std::vector<float> outvelrhop;
+  float rhopmin=0,rhopmax=0;
 };
 class PartWriter {
+  Engine &eng; PartSet &pset;
+  Engine::HostSnap snap[2]; bool inuse[2]={false,false};
   std::thread th; std::mutex mx; std::condition_variable cv;
-  std::unique_ptr<PartJob> job; bool stop=false; std::string error;
-  static void Write(PartJob &j){
-    PartData &p=j.p; const size_t np=j.idp.size();
-    p.idp.reserve(np); p.pos.reserve(np*3); p.vel.reserve(np*3); p.rhop.reserve(np);
-    for(size_t q=0;q<np;q++)if((j.code[q]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL){   // periodic / halo copies are not saved (S/JSphGpuSingle.cpp:897)
-      p.idp.push_back(j.idp[q]);
-      p.pos.push_back(j.pos[3*q]); p.pos.push_back(j.pos[3*q+1]); p.pos.push_back(j.pos[3*q+2]);
-      p.vel.push_back(j.vr[4*q]); p.vel.push_back(j.vr[4*q+1]); p.vel.push_back(j.vr[4*q+2]);
-      p.rhop.push_back(j.vr[4*q+3]);
+  std::deque<std::unique_ptr<PartJob>> queue; bool stop=false; std::string error;
+  std::vector<float> rhop;
+  void Write(PartJob &j){
+    Engine::HostSnap &hs=snap[j.slot];
+    eng.SnapshotWait(hs);
+    // in-place compaction of the pinned buffers: periodic / halo copies are not saved (S/JSphGpuSingle.cpp:897)
+    const size_t np=hs.np; size_t n=0;
+    rhop.resize(np);
+    float *vel=hs.velrhop;                          // xyzw -> packed xyz, moving towards lower addresses only
+    for(size_t q=0;q<np;q++)if((hs.code[q]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL){
+      hs.idp[n]=hs.idp[q];
+      hs.pos[3*n]=hs.pos[3*q]; hs.pos[3*n+1]=hs.pos[3*q+1]; hs.pos[3*n+2]=hs.pos[3*q+2];
+      const float vx=hs.velrhop[4*q],vy=hs.velrhop[4*q+1],vz=hs.velrhop[4*q+2],r=hs.velrhop[4*q+3];
+      vel[3*n]=vx; vel[3*n+1]=vy; vel[3*n+2]=vz; rhop[n]=r;
+      n++;
     }
-    p.npok=unsigned(p.idp.size());
-    SavePartFile(j.file,j.h,p,true);
+    pset.SavePart(j.meta,unsigned(n),hs.idp,hs.pos,vel,rhop.data(),&j.info);
+    // excluded particles since the previous PART
+    const unsigned nout=unsigned(j.outidp.size());
+    std::vector<float> ovel(size_t(nout)*3),orhop(nout); std::vector<unsigned char> motive(nout);
+    for(unsigned q=0;q<nout;q++){
+      ovel[3*q]=j.outvelrhop[4*q]; ovel[3*q+1]=j.outvelrhop[4*q+1]; ovel[3*q+2]=j.outvelrhop[4*q+2]; orhop[q]=j.outvelrhop[4*q+3];
+      const unsigned sp=j.outcode[q]&DSPH_CODE_MASKSPECIAL;
+      motive[q]=(sp==DSPH_CODE_OUTPOS? 1: (sp==DSPH_CODE_OUTRHOP? 2: (sp==DSPH_CODE_OUTMOVE? 3: 0)));
+    }
+    pset.SaveOut(j.meta.cpart,j.meta.timestep,nout,j.outidp.data(),j.outpos.data(),ovel.data(),orhop.data(),motive.data(),j.rhopmin,j.rhopmax);
   }
   void Loop(){
     for(;;){
       std::unique_ptr<PartJob> j;
-      { std::unique_lock<std::mutex> lk(mx); cv.wait(lk,[&]{ return job || stop; }); if(!job && stop)return; j=std::move(job); }
-      try{ Write(*j); }catch(const std::exception &e){ std::lock_guard<std::mutex> lk(mx); error=e.what(); }
-      { std::lock_guard<std::mutex> lk(mx); busy=false; }
+      { std::unique_lock<std::mutex> lk(mx); cv.wait(lk,[&]{ return !queue.empty() || stop; }); if(queue.empty())return; j=std::move(queue.front()); queue.pop_front(); }
+      try{ Write(*j); }catch(const std::exception &e){ std::lock_guard<std::mutex> lk(mx); if(error.empty())error=e.what(); }
+      { std::lock_guard<std::mutex> lk(mx); inuse[j->slot]=false; }
       cv.notify_all();
     }
   }
-  bool busy=false;
  public:
-  PartWriter(){ th=std::thread([this]{ Loop(); }); }
-  ~PartWriter(){ try{ Finish(); }catch(...){} { std::lock_guard<std::mutex> lk(mx); stop=true; } cv.notify_all(); if(th.joinable())th.join(); }
+  double waited_s=0;      // time the simulation loop spent waiting for a free host buffer
+  PartWriter(Engine &e,PartSet &ps,unsigned capacity):eng(e),pset(ps){
+    for(int i=0;i<2;i++)eng.HostSnapAlloc(snap[i],capacity);
+    th=std::thread([this]{ Loop(); });
+  }
+  ~PartWriter(){ try{ Finish(); }catch(...){} { std::lock_guard<std::mutex> lk(mx); stop=true; } cv.notify_all(); if(th.joinable())th.join(); for(int i=0;i<2;i++)eng.HostSnapFree(snap[i]); }
+  // called by the time loop: takes a free host buffer, enqueues the snapshot copies and hands the rest to the writer thread
   void Submit(std::unique_ptr<PartJob> j){
     std::unique_lock<std::mutex> lk(mx);
-    cv.wait(lk,[&]{ return !busy; });
+    const auto t0=std::chrono::steady_clock::now();
+    cv.wait(lk,[&]{ return !inuse[0] || !inuse[1]; });
+    waited_s+=std::chrono::duration<double>(std::chrono::steady_clock::now()-t0).count();
     if(!error.empty())throw std::runtime_error("PART output failed: "+error);
-    job=std::move(j); busy=true;
-    lk.unlock(); cv.notify_all();
+    j->slot=(!inuse[0]? 0: 1); inuse[j->slot]=true;
+    lk.unlock();
+    eng.SnapshotBegin(snap[j->slot]);
+    lk.lock(); queue.push_back(std::move(j)); lk.unlock();
+    cv.notify_all();
   }
-  void Finish(){ std::unique_lock<std::mutex> lk(mx); cv.wait(lk,[&]{ return !busy; }); if(!error.empty()){ std::string e=error; error.clear(); throw std::runtime_error("PART output failed: "+e); } }
+  void Finish(){ std::unique_lock<std::mutex> lk(mx); cv.wait(lk,[&]{ return !inuse[0] && !inuse[1] && queue.empty(); }); if(!error.empty()){ std::string e=error; error.clear(); throw std::runtime_error("PART output failed: "+e); } }
 };
 
-static void SavePart(Engine &eng,const CaseData &cd,const std::string &dirout,unsigned cpart,double timestep,unsigned step,double runtime,unsigned long long nout,Log &log,PartWriter &writer){
-  const unsigned np=eng.np;
+struct PartStats { double dtmin=1e300, dtmax=0, timem1=0; unsigned long long stepm1=0; };
+
+static void SavePart(Engine &eng,const CaseData &cd,unsigned cpart,double timestep,unsigned long long step,double runtime,unsigned long long nout,PartStats &st,Log &log,PartWriter &writer){
   std::unique_ptr<PartJob> j(new PartJob);
-  j->idp.resize(np); j->code.resize(np); j->pos.resize(size_t(np)*3); j->vr.resize(size_t(np)*4);
-  eng.Download(0,np,j->idp.data(),j->code.data(),nullptr,j->pos.data(),j->vr.data());
-  PartHead &h=j->h; PartData &p=j->p;
   const dsph_config &c=cd.cfg;
-  h.casename=cd.name; h.data2d=c.simulate2d!=0; h.data2dposy=c.simulate2dposy;
-  h.casenp=c.casenp; h.casenfixed=c.casenfixed; h.casenmoving=c.casenmoving; h.casenfloat=c.casenfloat; h.casenfluid=c.casenfluid;
-  for(int i=0;i<3;i++){ h.caseposmin[i]=cd.caseposmin[i]; h.caseposmax[i]=cd.caseposmax[i]; h.mapposmin[i]=eng.k.maprealposmin[i]; h.mapposmax[i]=eng.k.maprealposmax[i];
-    h.perixinc[i]=eng.k.perixinc[i]; h.periyinc[i]=eng.k.periyinc[i]; h.perizinc[i]=eng.k.perizinc[i]; }
-  h.perimode=eng.k.periactive;
-  h.dp=c.dp; h.h=c.kernelh; h.b=c.cteb; h.rhop0=c.rhopzero; h.gamma=c.gamma; h.massbound=c.massbound; h.massfluid=c.massfluid;
-  p.cpart=cpart; p.timestep=timestep; p.step=step; p.runtime=runtime; p.nout=unsigned(nout);
-  p.symplecticdtpre=(c.tstep==DSPH_STEP_SYMPLECTIC? eng.symplecticdtpre: 0);
+  PartMeta &m=j->meta;
+  m.cpart=cpart; m.timestep=timestep; m.step=unsigned(step); m.runtime=runtime; m.nout=unsigned(nout);
+  m.symplecticdtpre=(c.tstep==DSPH_STEP_SYMPLECTIC? eng.symplecticdtpre: 0);
   const double sc=eng.k.scell;
-  for(int i=0;i<3;i++){ p.domainmin[i]=eng.k.domposmin[i]+sc*eng.dp.cellmin[i]; p.domainmax[i]=eng.k.domposmin[i]+sc*(eng.dp.cellmax[i]+1); }
-  j->file=dirout+"/"+PartFileName(cpart);
-  const unsigned nsave=np-eng.npbper-eng.npfper;
+  for(int i=0;i<3;i++){ m.domainmin[i]=eng.k.domposmin[i]+sc*eng.dp.cellmin[i]; m.domainmax[i]=eng.k.domposmin[i]+sc*(eng.dp.cellmax[i]+1); }
+  PartInfoPlus &f=j->info; f.on=true;
+  f.dtmean=(step>st.stepm1? (timestep-st.timem1)/double(step-st.stepm1): 0); f.dtmin=(step? st.dtmin: 0); f.dtmax=(step? st.dtmax: 0);
+  f.timesim=runtime; f.nct=eng.dp.nct; f.npbin=eng.npbok; f.npbout=eng.npb-eng.npbok; f.npf=eng.np-eng.npb; f.npbper=eng.npbper; f.npfper=eng.npfper;
+  f.npalloc=(long long)eng.cap; f.npused=(long long)eng.np; f.nctalloc=(long long)eng.maxnctt; f.nctused=(long long)eng.dp.nctt;
+  st.dtmin=1e300; st.dtmax=0; st.timem1=timestep; st.stepm1=step;
+  j->outidp.swap(eng.outidp); j->outcode.swap(eng.outcode); j->outpos.swap(eng.outpos); j->outvelrhop.swap(eng.outvelrhop);
+  j->rhopmin=(c.rhopoutmin<c.rhopoutmax? c.rhopoutmin: 0); j->rhopmax=(c.rhopoutmin<c.rhopoutmax? c.rhopoutmax: 0);
+  const unsigned nsave=eng.np-eng.npbper-eng.npfper;
   writer.Submit(std::move(j));
-  log.Printf("Part_%04u  %12.6f  %12u  %10u particles stored",cpart,timestep,step,nsave);
+  log.Printf("Part_%04u  %12.6f  %12llu  %10u particles stored",cpart,timestep,step,nsave);
 }
 
 // Probe points: <dir>/<casename>_Points.txt, one "x y z" per line (separators blank , ;  comments #), the file format of the
@@ -139,52 +169,106 @@ static void SaveProbes(Engine &eng,const std::vector<double> &pts,const std::str
   fclose(f);
 }
 
-RunSummary RunCase(const RunOptions &opt){
+// ------------------------------------------------------------------------------------------------
+// x-slab runs (-mgpu:N): one host thread per GPU of this process, each with its own Engine; the exchange and the dt all-reduce go
+// through the library's NCCL transport (mgpu_comm.cu), so the threads run in lockstep without any host-side message passing.
+// ------------------------------------------------------------------------------------------------
+struct SlabGroup {
+  int nranks=1;
+  unsigned char uid[128]={0};
+  std::vector<unsigned> cuts;
+  std::mutex mx; std::condition_variable cv; int arrived=0; unsigned long long generation=0;
+  std::vector<Engine*> engines; std::atomic<bool> failed{false}; std::string error;
+  std::vector<unsigned long long> nout, partsteps; std::vector<unsigned> np0;
+  explicit SlabGroup(int n):nranks(n),engines(n,nullptr),nout(n,0),partsteps(n,0),np0(n,0){}
+  void Barrier(){
+    std::unique_lock<std::mutex> lk(mx);
+    const unsigned long long g=generation;
+    if(++arrived==nranks){ arrived=0; generation++; cv.notify_all(); }
+    else cv.wait(lk,[&]{ return generation!=g || failed.load(); });
+    if(failed.load())throw std::runtime_error("another rank of the slab run failed");
+  }
+  void Fail(int rank,const std::string &msg){
+    { std::lock_guard<std::mutex> lk(mx); if(error.empty()){ char tx[32]; snprintf(tx,sizeof(tx),"[rank %d] ",rank); error=tx+msg; } }
+    failed.store(true);
+    for(int r=0;r<nranks;r++)if(r!=rank && engines[r])engines[r]->MgCommAbort();
+    cv.notify_all();
+  }
+};
+
+static RunSummary RunRank(const RunOptions &opt,CaseData &cd,int rank,SlabGroup *grp,double timestep,unsigned part,double restartdtpre){
   RunSummary sum;
-  mkdir(opt.dirout.c_str(),0755);
-  Log log; log.echo=opt.verbose; log.Open(opt.dirout+"/Run.out");
-  log.Printf("dsph_b200 (B200-native DualSPHysics hot path)  case=%s/%s",opt.dir.c_str(),opt.casename.c_str());
-  CaseData cd; LoadCase(cd,opt.dir,opt.casename);
+  const int nranks=(grp? grp->nranks: 1);
+  const bool slabs=(nranks>1);
+  Log log; log.echo=(opt.verbose && rank==0);
+  { char nm[32]; if(rank)snprintf(nm,sizeof(nm),"/Run_p%02d.out",rank); else snprintf(nm,sizeof(nm),"/Run.out"); log.Open(opt.dirout+nm); }
   dsph_config &c=cd.cfg;
-  if(opt.timemax>0)c.timemax=opt.timemax;
-  if(opt.timeout>0)c.timeout=opt.timeout;
-  double timestep=0; unsigned part=0; double restartdtpre=0;
-  if(opt.partbegin>=0){
-    // restart: particle state, time and the Symplectic dt of the next step come from a PART file of a previous run
-    // (JPartsLoad4::LoadParticles with partbegin + JSph::RestartCheckData, S/JSph.cpp:2005-2040); excluded particles stay excluded
-    PartHead ph; PartData pd;
-    const std::string dirb=(opt.partbegindir.empty()? opt.dirout: opt.partbegindir);
-    LoadPartFile(dirb+"/"+PartFileName(unsigned(opt.partbegin)),ph,pd,unsigned(opt.partbegin));
-    if(ph.casenp!=c.casenp || ph.casenfixed!=c.casenfixed || ph.casenfluid!=c.casenfluid)throw std::runtime_error("The PART file of -partbegin does not belong to this case.");
-    cd.idp=pd.idp; cd.pos=pd.pos; cd.velrhop.resize(size_t(pd.npok)*4);
-    for(unsigned i=0;i<pd.npok;i++){ cd.velrhop[4*i]=pd.vel[3*i]; cd.velrhop[4*i+1]=pd.vel[3*i+1]; cd.velrhop[4*i+2]=pd.vel[3*i+2]; cd.velrhop[4*i+3]=pd.rhop[i]; }
-    timestep=pd.timestep; part=unsigned(opt.partbegin); restartdtpre=pd.symplecticdtpre;
-    log.Printf("Restart from %s/%s: TimeStep=%.9g  np=%u",dirb.c_str(),PartFileName(part).c_str(),timestep,pd.npok);
+  const unsigned npcase=cd.np();
+  // ---- particles of this rank
+  std::vector<unsigned> sel;                 // indices into the case arrays (slab runs)
+  unsigned np0=npcase;
+  if(slabs){
+    SphConst k; DeriveConstants(c,k);
+    const double sc=double(k.scell);
+    for(unsigned i=0;i<npcase;i++){
+      const unsigned cx=unsigned((cd.pos[3*size_t(i)]-k.domposmin[0])/sc);       // the arithmetic of the cell hash (celldiv.cuh)
+      if(cx>=grp->cuts[rank] && cx<grp->cuts[rank+1])sel.push_back(i);
+    }
+    np0=unsigned(sel.size());
   }
-  const unsigned np0=cd.np();
-  // JSph::CheckRhopLimits (S/JSph.cpp:2021-2030): the initial density of every fluid particle must be inside RhopOut
-  if(c.rhopoutmin<c.rhopoutmax)for(unsigned i=0;i<np0;i++)if(cd.idp[i]>=c.casenfixed+c.casenmoving+c.casenfloat){
-    const float r=cd.velrhop[4*size_t(i)+3];
-    if(r<c.rhopoutmin || c.rhopoutmax<r)throw std::runtime_error("Initial fluid density is out of limits. *** To change the limits modify the value of 'RhopOutMin' and 'RhopOutMax' in the XML file (parameters section).");
-  }
-  unsigned capacity=std::max(np0,c.casenp)+c.casenp/20+1024;
+  if(grp)grp->np0[rank]=np0;
+  unsigned capacity=std::max(np0,slabs? 0u: c.casenp)+np0/20+1024;
   if(c.perix||c.periy||c.periz)capacity=unsigned(np0*1.7)+65536;
-  Engine eng(opt.device,c,capacity);
+  if(slabs)capacity=unsigned(np0*1.5)+200000;                                    // room for halo copies and for the re-balancing
+  Engine eng(opt.device+rank,c,capacity);
+  if(grp)grp->engines[rank]=&eng;
   if(opt.forcevariant)eng.forcevariant=opt.forcevariant;
-  log.Printf("Particles: np=%u nbound=%u nfluid=%u  dp=%g h=%g cs0=%g  cells(map)=%ux%ux%u",np0,c.casenfixed,c.casenfluid,c.dp,double(c.kernelh),eng.k.cs0,eng.k.mapcells[0],eng.k.mapcells[1],eng.k.mapcells[2]);
-  std::vector<typecode> code(np0); ComputeCodes(cd,np0,cd.idp.data(),code.data());
-  unsigned npb0=0; for(unsigned i=0;i<np0;i++)if(cd.idp[i]<c.casenfixed+c.casenmoving)npb0++;     // boundary ids come first (CheckSortParticles)
-  eng.Upload(np0,npb0,cd.idp.data(),code.data(),cd.pos.data(),cd.velrhop.data());
+  eng.keepout=opt.savepart;
+  log.Printf("dsph_b200 (B200-native DualSPHysics hot path)  case=%s/%s%s",opt.dir.c_str(),opt.casename.c_str(),slabs? "  [x-slab run]": "");
+  if(timestep>0)log.Printf("Restart from Part_%04u: TimeStep=%.9g",part,timestep);
+  log.Printf("Particles: np=%u nbound=%u nfluid=%u  dp=%g h=%g cs0=%g  cells(map)=%ux%ux%u",npcase,c.casenfixed,c.casenfluid,c.dp,double(c.kernelh),eng.k.cs0,eng.k.mapcells[0],eng.k.mapcells[1],eng.k.mapcells[2]);
+  if(!eng.ringbase_ok)log.Printf("*** WARNING: the shared-memory window of this device/driver does not start where the ring force kernels expect it (probe at context creation): "
+                                 "the plain kernels (variant 4) run instead, about 1.5x slower in Interaction_Forces.");
+  {
+    std::vector<typecode> code(np0); std::vector<unsigned> idp; std::vector<double> pos; std::vector<float> vr;
+    const unsigned *pidp=cd.idp.data(); const double *ppos=cd.pos.data(); const float *pvr=cd.velrhop.data();
+    if(slabs){
+      idp.resize(np0); pos.resize(size_t(np0)*3); vr.resize(size_t(np0)*4);
+      for(unsigned q=0;q<np0;q++){ const size_t i=sel[q]; idp[q]=cd.idp[i]; memcpy(&pos[3*size_t(q)],&cd.pos[3*i],24); memcpy(&vr[4*size_t(q)],&cd.velrhop[4*i],16); }
+      pidp=idp.data(); ppos=pos.data(); pvr=vr.data();
+    }
+    ComputeCodes(cd,np0,pidp,code.data());
+    unsigned npb0=0; for(unsigned i=0;i<np0;i++)if(pidp[i]<c.casenfixed+c.casenmoving)npb0++;     // boundary ids come first (CheckSortParticles)
+    eng.Upload(np0,npb0,pidp,code.data(),ppos,pvr);
+  }
   if(restartdtpre>0)eng.symplecticdtpre=restartdtpre;
-  dsph_divinfo di; eng.CellDivide(true,&di);
+  dsph_divinfo di;
+  if(slabs){
+    eng.MgCommInit(grp->uid,rank,nranks);
+    eng.MgConfigCuts(rank,nranks,grp->cuts.data());
+    log.Printf("Slab %d of %d: cell columns [%u,%u)  np=%u  (NCCL %d)",rank,nranks,grp->cuts[rank],grp->cuts[rank+1],np0,MgNcclVersion());
+    eng.MgCellDivide(&di);
+  }
+  else eng.CellDivide(true,&di);
+  // ---- output set
+  PartSetHead head;
+  MakePartSetHead(head,cd,eng.k.maprealposmin,eng.k.maprealposmax,eng.k.periactive,eng.k.perixinc,eng.k.periyinc,eng.k.perizinc);
+  head.firstpart=(opt.partbegin>=0? part: 0);
+  if(slabs){ char tx[16]; unsigned v=0; for(int i=0;i<128;i++)v=v*131u+grp->uid[i]; snprintf(tx,sizeof(tx),"%08x",v); head.runcode=tx; }   // the same run code on every piece
+  PartSet pset(opt.dirout,head,unsigned(rank),unsigned(nranks),slabs? 1: 0,opt.piecemax? opt.piecemax: PartSet::PIECE_MAX_DEFAULT,opt.partbegin>=0);
+  if(opt.savepart && rank==0)pset.SaveHead();
+  if(pset.Npiece()>1 && !slabs)log.Printf("PART files are written in %u pieces (4 GB limit of the bi4 container).",pset.Npiece());
+  std::unique_ptr<PartWriter> writer;
+  if(opt.savepart)writer.reset(new PartWriter(eng,pset,capacity));
   unsigned long long nstep=0;
   const auto t0=std::chrono::steady_clock::now();
   auto Elapsed=[&]{ return std::chrono::duration<double>(std::chrono::steady_clock::now()-t0).count(); };
-  const std::vector<double> probes=LoadPoints(opt.dir+"/"+opt.casename+"_Points.txt");
+  std::vector<double> probes;
+  if(!slabs)probes=LoadPoints(opt.dir+"/"+opt.casename+"_Points.txt");
   if(!probes.empty())log.Printf("Probe points: %u (%s_Points.txt) -> MeasurePoints.csv",unsigned(probes.size()/3),opt.casename.c_str());
-  PartWriter writer;
+  PartStats pst; pst.timem1=timestep;
   if(opt.partbegin<0){
-    if(opt.savepart)SavePart(eng,cd,opt.dirout,part,timestep,0,0,0,log,writer);
+    if(opt.savepart)SavePart(eng,cd,part,timestep,0,0,0,pst,log,*writer);
     SaveProbes(eng,probes,opt.dirout,part,timestep);
   }
   part++;
@@ -192,15 +276,30 @@ RunSummary RunCase(const RunOptions &opt){
   eng.GetTimers(nullptr,true);
   const auto tsim0=std::chrono::steady_clock::now();
   unsigned long long partsteps=0;
+  const int rebalance_every=(opt.rebalancesteps>0? opt.rebalancesteps: 50);
+  unsigned nrebalanced=0;
   while(timestep<c.timemax){
     double dt; dsph_forceres fr;
-    eng.Step(&dt,&fr);
-    partsteps+=eng.np;
+    if(slabs)eng.MgStep(&dt,&fr); else eng.Step(&dt,&fr);
+    partsteps+=eng.np-eng.npbper-eng.npfper;
     timestep+=dt; nstep++;
-    const unsigned long long nout=eng.npout_total;
-    const bool partoutstop=(c.partsoutmax_on && double(nout)>double(c.partsoutmax)*double(c.casenfluid)) || !eng.np;
-    if(timestep>=timepartnext || partoutstop){
-      if(opt.savepart)SavePart(eng,cd,opt.dirout,part,timestep,unsigned(nstep),Elapsed(),nout,log,writer);
+    pst.dtmin=std::min(pst.dtmin,dt); pst.dtmax=std::max(pst.dtmax,dt);
+    if(slabs && nstep%rebalance_every==0){
+      // collective: the same decision on every rank (the histogram and the costs are all-reduced)
+      if(eng.MgRebalance(opt.boundweight>0? opt.boundweight: 0.05,eng.MgMeasuredCost(),nullptr)){ eng.MgCellDivide(nullptr); nrebalanced++; }
+    }
+    unsigned long long nout=eng.npout_total;
+    const bool dopart=(timestep>=timepartnext);          // dt is the same on every rank: the same decision everywhere
+    bool partoutstop=false;
+    if(!slabs)partoutstop=(c.partsoutmax_on && double(nout)>double(c.partsoutmax)*double(c.casenfluid)) || !eng.np;
+    else if(dopart){                                      // slab runs check the limit of excluded particles at PART times, on the global count
+      grp->nout[rank]=nout; grp->Barrier();
+      unsigned long long tot=0; for(int r=0;r<nranks;r++)tot+=grp->nout[r];
+      grp->Barrier();
+      partoutstop=(c.partsoutmax_on && double(tot)>double(c.partsoutmax)*double(c.casenfluid));
+    }
+    if(dopart || partoutstop){
+      if(opt.savepart)SavePart(eng,cd,part,timestep,nstep,Elapsed(),nout,pst,log,*writer);
       else log.Printf("Part_%04u  %12.6f  %12llu  dt=%.6g  np=%u",part,timestep,nstep,dt,eng.np);
       SaveProbes(eng,probes,opt.dirout,part,timestep);
       part++;
@@ -209,12 +308,22 @@ RunSummary RunCase(const RunOptions &opt){
     }
     if(opt.nsteps>0 && nstep>=(unsigned long long)opt.nsteps)break;
   }
+  eng.FlushStepTimer();
   const double tsim=std::chrono::duration<double>(std::chrono::steady_clock::now()-tsim0).count();
-  writer.Finish();                                   // the last PART file must be complete before the run reports success
+  double twrite=0;
+  if(writer){ const auto tw0=std::chrono::steady_clock::now(); writer->Finish(); twrite=std::chrono::duration<double>(std::chrono::steady_clock::now()-tw0).count(); }   // the last PART must be complete before the run reports success
   dsph_timers tm; eng.GetTimers(&tm,false);
   sum.np0=np0; sum.steps=nstep; sum.simtime=timestep; sum.runtime_s=tsim; sum.parts=part; sum.npout=eng.npout_total;
   sum.mpartsteps_s=(tsim>0? double(partsteps)/tsim/1e6: 0);
+  if(grp){
+    grp->partsteps[rank]=partsteps; grp->nout[rank]=eng.npout_total; grp->Barrier();
+    unsigned long long ps=0,no=0; unsigned n0=0; for(int r=0;r<nranks;r++){ ps+=grp->partsteps[r]; no+=grp->nout[r]; n0+=grp->np0[r]; }
+    sum.np0=n0; sum.npout=no; sum.mpartsteps_s=(tsim>0? double(ps)/tsim/1e6: 0);
+    grp->Barrier();
+  }
   log.Printf("[Simulation finished]  steps=%llu  TimeStep=%.9g  runtime=%.4f s  %.3f Mparticle-steps/s  excluded=%llu",nstep,timestep,tsim,sum.mpartsteps_s,sum.npout);
+  if(writer)log.Printf("PART pipeline: the time loop waited %.4f s for a free host buffer; %.4f s to finish the last files after the loop",writer->waited_s,twrite);
+  if(slabs)log.Printf("Slab re-balancing: every %d steps, cuts moved %u times",rebalance_every,nrebalanced);
   log.Printf("[GPU Timers] (device ms)");
   log.Printf("NL-Limits........: %.3f",tm.nl_limits); log.Printf("NL-PreSort.......: %.3f",tm.nl_presort);
   log.Printf("NL-RadixSort.....: %.3f",tm.nl_radixsort); log.Printf("NL-CellBegin.....: %.3f",tm.nl_cellbegin);
@@ -223,14 +332,71 @@ RunSummary RunCase(const RunOptions &opt){
   log.Printf("SU-ComputeStep...: %.3f",tm.su_computestep); log.Printf("SU-Periodic......: %.3f",tm.su_periodic);
   log.Printf("Kernel launches..: %llu",(unsigned long long)tm.kernel_launches);
   { // Run.csv one-line summary (S/JSph.cpp:2962-3006)
-    FILE *f=fopen((opt.dirout+"/Run.csv").c_str(),"w");
+    char nm[32]; if(rank)snprintf(nm,sizeof(nm),"/Run_p%02d.csv",rank); else snprintf(nm,sizeof(nm),"/Run.csv");
+    FILE *f=fopen((opt.dirout+nm).c_str(),"w");
     if(f){
       fprintf(f,"#RunName;Np;Steps;TSimul;TimeStep;MPartStepsPerSec;NL-Limits;NL-PreSort;NL-RadixSort;NL-CellBegin;NL-SortData;CF-Forces;SU-ComputeStep\n");
-      fprintf(f,"%s;%u;%llu;%.6f;%.9g;%.4f;%.3f;%.3f;%.3f;%.3f;%.3f;%.3f;%.3f\n",opt.casename.c_str(),np0,nstep,tsim,timestep,sum.mpartsteps_s,tm.nl_limits,tm.nl_presort,tm.nl_radixsort,tm.nl_cellbegin,tm.nl_sortdata,tm.cf_forces,tm.su_computestep);
+      fprintf(f,"%s;%u;%llu;%.6f;%.9g;%.4f;%.3f;%.3f;%.3f;%.3f;%.3f;%.3f;%.3f\n",opt.casename.c_str(),sum.np0,nstep,tsim,timestep,sum.mpartsteps_s,tm.nl_limits,tm.nl_presort,tm.nl_radixsort,tm.nl_cellbegin,tm.nl_sortdata,tm.cf_forces,tm.su_computestep);
       fclose(f);
     }
   }
+  writer.reset();
+  if(grp)grp->engines[rank]=nullptr;
   return sum;
+}
+
+RunSummary RunCase(const RunOptions &opt){
+  mkdir(opt.dirout.c_str(),0755);
+  CaseData cd; LoadCase(cd,opt.dir,opt.casename);
+  dsph_config &c=cd.cfg;
+  if(opt.timemax>0)c.timemax=opt.timemax;
+  if(opt.timeout>0)c.timeout=opt.timeout;
+  double timestep=0; unsigned part=0; double restartdtpre=0;
+  if(opt.partbegin>=0){
+    // restart: particle state, time and the Symplectic dt of the next step come from the PART file(s) of a previous run
+    // (JPartsLoad4::LoadParticles with partbegin + JSph::RestartCheckData, S/JSph.cpp:2005-2040); excluded particles stay excluded
+    PartHead ph; PartData pd;
+    const std::string dirb=(opt.partbegindir.empty()? opt.dirout: opt.partbegindir);
+    LoadPartPieces(dirb,unsigned(opt.partbegin),ph,pd);
+    if(ph.casenp!=c.casenp || ph.casenfixed!=c.casenfixed || ph.casenfluid!=c.casenfluid)throw std::runtime_error("The PART file of -partbegin does not belong to this case.");
+    cd.idp=pd.idp; cd.pos=pd.pos; cd.velrhop.resize(size_t(pd.npok)*4);
+    for(unsigned i=0;i<pd.npok;i++){ cd.velrhop[4*size_t(i)]=pd.vel[3*size_t(i)]; cd.velrhop[4*size_t(i)+1]=pd.vel[3*size_t(i)+1]; cd.velrhop[4*size_t(i)+2]=pd.vel[3*size_t(i)+2]; cd.velrhop[4*size_t(i)+3]=pd.rhop[i]; }
+    timestep=pd.timestep; part=unsigned(opt.partbegin); restartdtpre=pd.symplecticdtpre;
+  }
+  const unsigned np0=cd.np();
+  // JSph::CheckRhopLimits (S/JSph.cpp:2021-2030): the initial density of every fluid particle must be inside RhopOut
+  if(c.rhopoutmin<c.rhopoutmax)for(unsigned i=0;i<np0;i++)if(cd.idp[i]>=c.casenfixed+c.casenmoving+c.casenfloat){
+    const float r=cd.velrhop[4*size_t(i)+3];
+    if(r<c.rhopoutmin || c.rhopoutmax<r)throw std::runtime_error("Initial fluid density is out of limits. *** To change the limits modify the value of 'RhopOutMin' and 'RhopOutMax' in the XML file (parameters section).");
+  }
+  if(opt.mgpu<=1)return RunRank(opt,cd,0,nullptr,timestep,part,restartdtpre);
+  // ---- slab run: cuts from the per-column histogram of the work (fluid 1, boundary weight), one thread per GPU
+  if(c.perix||c.periy||c.periz)throw std::runtime_error("Periodic boundaries cannot be combined with -mgpu yet.");
+  SlabGroup grp(opt.mgpu);
+  {
+    SphConst k; DeriveConstants(c,k);
+    const double sc=double(k.scell), bw=(opt.boundweight>0? opt.boundweight: 0.05);
+    std::vector<double> col(k.domcells[0],0.0);
+    const unsigned nbound=c.casenfixed+c.casenmoving+c.casenfloat;
+    for(unsigned i=0;i<np0;i++){
+      const unsigned cx=unsigned((cd.pos[3*size_t(i)]-k.domposmin[0])/sc);
+      if(cx<col.size())col[cx]+=(cd.idp[i]<nbound? bw: 1.0);
+    }
+    const unsigned halo=unsigned(k.scelldiv)*(c.nn_on && c.nn_velgrad==DSPH_VELGRAD_SPH && c.tvisco!=DSPH_VISCO_ARTIFICIAL? 2u: 1u);
+    const unsigned minwidth=2*halo+1;
+    if(unsigned(opt.mgpu)*minwidth>col.size())throw std::runtime_error("Too many GPUs for the cell columns of the domain.");
+    grp.cuts=MgBalancedCuts(col,opt.mgpu,minwidth);
+  }
+  MgUniqueId(grp.uid);
+  std::vector<RunSummary> sums(opt.mgpu);
+  std::vector<std::thread> ths;
+  for(int r=0;r<opt.mgpu;r++)ths.emplace_back([&,r]{
+    try{ sums[r]=RunRank(opt,cd,r,&grp,timestep,part,restartdtpre); }
+    catch(const std::exception &e){ grp.Fail(r,e.what()); }
+  });
+  for(auto &t:ths)t.join();
+  if(grp.failed.load())throw std::runtime_error(grp.error.empty()? std::string("slab run failed"): grp.error);
+  return sums[0];
 }
 
 } // namespace dsph

@@ -30,6 +30,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*)=nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*,int,ncclUniqueId,int)=nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t)=nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t)=nullptr;
   ncclResult_t (*Send)(const void*,size_t,ncclDataType_t,int,ncclComm_t,cudaStream_t)=nullptr;
   ncclResult_t (*Recv)(void*,size_t,ncclDataType_t,int,ncclComm_t,cudaStream_t)=nullptr;
   ncclResult_t (*AllReduce)(const void*,void*,size_t,ncclDataType_t,ncclRedOp_t,ncclComm_t,cudaStream_t)=nullptr;
@@ -49,6 +50,7 @@ struct NcclApi {
     GetUniqueId=(decltype(GetUniqueId))sym("ncclGetUniqueId");
     CommInitRank=(decltype(CommInitRank))sym("ncclCommInitRank");
     CommDestroy=(decltype(CommDestroy))sym("ncclCommDestroy");
+    CommAbort=(decltype(CommAbort))sym("ncclCommAbort");
     Send=(decltype(Send))sym("ncclSend"); Recv=(decltype(Recv))sym("ncclRecv");
     AllReduce=(decltype(AllReduce))sym("ncclAllReduce");
     GroupStart=(decltype(GroupStart))sym("ncclGroupStart"); GroupEnd=(decltype(GroupEnd))sym("ncclGroupEnd");
@@ -104,6 +106,11 @@ void Engine::MgCommAttach(void *ncclcomm,int rank,int nranks){
   mgcomm=ncclcomm; mgcomm_own=false;
   if(!mgcntdev)CUCHECK2(cudaMalloc((void**)&mgcntdev,32*sizeof(unsigned)));
   CUCHECK2(cudaMemsetAsync(mgcntdev,0,32*sizeof(unsigned),stm));
+}
+// Called by ANOTHER thread when a rank of the group failed: pending and future collectives of this communicator return with an error
+// instead of waiting for the failed rank for ever.
+void Engine::MgCommAbort(){
+  if(mgcomm && g_nccl.handle && g_nccl.CommAbort){ void *c=mgcomm; mgcomm=nullptr; g_nccl.CommAbort((ncclComm_t)c); }
 }
 void Engine::MgCommDestroy(){
   if(mgcomm && mgcomm_own && g_nccl.handle){ cudaStreamSynchronize(stm); g_nccl.CommDestroy((ncclComm_t)mgcomm); }
@@ -209,7 +216,7 @@ void Engine::MgStep(double *stepdt,dsph_forceres *res){
 // narrower of its two slabs, so a particle changes owner by at most one rank; the next exchange migrates fluid AND boundary
 // particles that are outside the new range.  Returns true when the cuts changed (the caller then runs dsph_mgpu_celldiv).
 // ------------------------------------------------------------------------------------------------
-static std::vector<unsigned> BalancedCuts(const std::vector<double> &col,int nranks,unsigned minwidth){
+std::vector<unsigned> MgBalancedCuts(const std::vector<double> &col,int nranks,unsigned minwidth){
   const unsigned ncol=unsigned(col.size());
   std::vector<double> cum(ncol+1,0.0);
   for(unsigned i=0;i<ncol;i++)cum[i+1]=cum[i]+col[i];
@@ -250,7 +257,7 @@ bool Engine::MgRebalance(double bound_weight,double rank_cost,unsigned *cuts_out
     double tot=0; for(unsigned i=mgcuts[r];i<mgcuts[r+1];i++)tot+=hist[i];
     if(tot>0){ const double f=h[ncol+r]/tot; for(unsigned i=mgcuts[r];i<mgcuts[r+1];i++)hist[i]*=f; }
   }
-  const std::vector<unsigned> target=BalancedCuts(hist,mgnranks,minwidth);
+  const std::vector<unsigned> target=MgBalancedCuts(hist,mgnranks,minwidth);
   std::vector<unsigned> nw(mgcuts);
   for(int r=1;r<mgnranks;r++){
     const long long room=(long long)std::min(mgcuts[r]-mgcuts[r-1],mgcuts[r+1]-mgcuts[r])-1;

@@ -331,8 +331,25 @@ typedef struct dsph_runopts {
   double timemax, timeout;
   int32_t restart, partbegin;
   const char *partbegindir;
+  /* x-slab run: mgpu > 1 uses the GPUs device..device+mgpu-1 of this process, one host thread and one PART piece
+   * (Part_pXX_NNNN.bi4, AxisDiv = X; S/JPartDataBi4.h:81,122-133) per GPU; exchange and dt all-reduce through the library's NCCL
+   * transport (section 5b).  rebalancesteps: steps between re-balancing attempts (0 = 50); boundweight: 0 = 0.05.
+   * piecemax: particles per PART file piece of a single-GPU run (0 = 80 M: the 4 GB limit of the container, S/JBinaryData.cpp:1223-1235) */
+  int32_t mgpu, rebalancesteps;
+  double boundweight;
+  uint32_t piecemax, reserved_;
 } dsph_runopts;
 int dsph_run_case_ex(const dsph_runopts *opts);
+
+/* ---- PART output set, host only (no device needed): what dsph_run_case writes for every PART, callable on host arrays.
+ *      Part_Head.ibi4 (S/JPartDataHead.cpp:208-272), Part_NNNN.bi4 or Part_pXX_NNNN.bi4 pieces of at most piecemax particles
+ *      (S/JPartDataBi4.cpp:98-102,437-439), PartInfo.ibi4 (S/JPartDataBi4.cpp:445-450) and, when nout > 0, PartOut_000.obi4
+ *      (S/JPartOutBi4Save.cpp:212-231).  Particles in `c` must have boundary ids first.  out_* may be NULL when nout = 0;
+ *      out_motive: 1 position, 2 density, 3 velocity. */
+int dsph_partset_save(const dsph_case *c,const char *dirout,uint32_t cpart,double timestep,uint32_t step,double symplecticdtpre,uint32_t piecemax,
+                      uint32_t nout,const uint32_t *out_idp,const double *out_pos_xyz,const float *out_velrhop_xyzw,const uint8_t *out_motive);
+/* every piece of PART cpart of dir, concatenated (boundary particles first); free with dsph_case_free */
+int dsph_partset_load(dsph_case *out,const char *dir,uint32_t cpart,double *timestep,uint32_t *step,uint32_t *npiece);
 
 #ifdef __cplusplus
 }

@@ -116,3 +116,65 @@ def test_gpu_restart_from_part_continues_the_run(gpu_lib, tmp_path):
     assert np.abs(a.pos[oa] - b.pos[ob]).max() < 1e-7
     den = np.linalg.norm(a.velrhop[oa].astype(np.float64))
     assert np.linalg.norm((a.velrhop[oa] - b.velrhop[ob]).astype(np.float64)) / den < 1e-5
+
+
+def _sorted_state(cd):
+    o = np.argsort(cd.idp)
+    return cd.idp[o], cd.pos[o], cd.velrhop[o]
+
+
+@pytest.mark.gpu
+def test_gpu_driver_output_set_pieces_and_excluded_particles(gpu_lib, tmp_path):
+    """the driver's asynchronous PART pipeline writes Part_Head.ibi4, PartInfo.ibi4, PartOut_000.obi4 and, with a piece
+    limit below the particle count, Part_pXX_NNNN.bi4 pieces; the pieces hold the state of the single-file run bit for bit, and the
+    particles the divide excluded (a RhopOut window the flow leaves) are in PartOut with their motive."""
+    from test_partset import read_bi4
+    cd = dsph.make_case("dambreak", 30000)
+    cd.cfg.rhopoutmin, cd.cfg.rhopoutmax = 995.0, float(cd.velrhop[:, 3].max()) + 0.6      # a few particles pass it during the collapse
+    dsph.save_case(cd, str(tmp_path), "Case")
+    one = tmp_path / "one"; pcs = tmp_path / "pieces"
+    dsph.run_case(str(tmp_path), "Case", str(one), timemax=0.03, timeout=0.005)
+    dsph.run_case(str(tmp_path), "Case", str(pcs), timemax=0.03, timeout=0.005, piecemax=cd.np_ // 3 + 1)
+    names = sorted(os.listdir(str(one)))
+    assert {"Part_Head.ibi4", "PartInfo.ibi4", "PartOut_000.obi4", "Part_0000.bi4", "Part_0006.bi4", "Run.out", "Run.csv"} <= set(names), names
+    assert {"Part_p00_0006.bi4", "Part_p01_0006.bi4", "Part_p02_0006.bi4", "PartInfo_p02.ibi4"} <= set(os.listdir(str(pcs)))
+    a, ta, sa, npa = dsph.load_partset(str(one), 6)
+    b, tb, sb, npb_ = dsph.load_partset(str(pcs), 6)
+    assert (npa, npb_) == (1, 3) and ta == tb and sa == sb
+    for x, y in zip(_sorted_state(a), _sorted_state(b)):
+        assert np.array_equal(x, y)
+    inf = read_bi4(str(one / "PartInfo.ibi4"), "JPartDataBi4_Info")
+    assert [i["name"] for i in inf] == ["JPartDataBi4"] + ["PART_%04d" % k for k in range(7)]
+    assert inf[-1]["values"]["Npok"] == a.np_ and inf[-1]["values"]["dtmin"] > 0 and inf[-1]["values"]["dtmax"] >= inf[-1]["values"]["dtmin"]
+    po = read_bi4(str(one / "PartOut_000.obi4"), "JPartOutBi4")
+    nout = sum(i["values"]["Nout"] for i in po[1:])
+    txt = open(str(one / "Run.out")).read()
+    print(txt[-900:])
+    assert nout > 0 and nout == cd.np_ - a.np_ and ("excluded=%d" % nout) in txt
+    mot = np.concatenate([i["arrays"]["Motive"] for i in po[1:]])
+    rh = np.concatenate([i["arrays"]["Rhop"] for i in po[1:]])
+    assert np.all(mot == 2) and np.all((rh < 995.0) | (rh > cd.cfg.rhopoutmax))
+    assert "PART pipeline" in txt
+
+
+@pytest.mark.gpu
+def test_gpu_driver_slab_run_matches_single_gpu_run(gpu_lib, tmp_path):
+    """bin/dsph_b200 -mgpu:2 (one host thread, one NCCL rank and one PART piece per GPU) against the single-GPU run of
+    the same case: same particle set in the pieces, same time, state within the single-step tolerance."""
+    if dsph.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    cd = dsph.make_case("dambreak", 200000)
+    dsph.save_case(cd, str(tmp_path), "Case")
+    one = tmp_path / "one"; two = tmp_path / "two"
+    dsph.run_case(str(tmp_path), "Case", str(one), nsteps=30, timeout=2e-4)
+    dsph.run_case(str(tmp_path), "Case", str(two), nsteps=30, timeout=2e-4, mgpu=2, rebalancesteps=10)
+    last = max(int(f[5:9]) for f in os.listdir(str(one)) if f.startswith("Part_0") and f.endswith(".bi4"))
+    assert last >= 2 and os.path.exists(str(two / ("Part_p01_%04d.bi4" % last))) and os.path.exists(str(two / "Run_p01.out"))
+    a, ta, sa, npa = dsph.load_partset(str(one), last)
+    b, tb, sb, npb_ = dsph.load_partset(str(two), last)
+    assert (npa, npb_) == (1, 2) and sa == sb and abs(ta - tb) <= 1e-9 * ta
+    ia, pa, va = _sorted_state(a); ib, pb, vb = _sorted_state(b)
+    assert np.array_equal(ia, ib)
+    assert np.abs(pa - pb).max() < 1e-7
+    assert np.linalg.norm((va - vb).astype(np.float64)) / np.linalg.norm(va.astype(np.float64)) < 1e-5
+    print(open(str(two / "Run.out")).read()[-1200:])
