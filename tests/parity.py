@@ -19,16 +19,26 @@ GOLDEN_CASES = ["db_sym_wend_art_ddt2", "db_ver_cubic_art_ddt1_shift", "db_sym_w
 GPU_PENDING = []                             # cases the CUDA path does not cover yet
 
 
+PROPAGATION_TOL = 1e-4      # forces evaluated on a chained (not re-synchronised) state, see run_step_stages
+
+
 def rl2(a, b):
     a = np.asarray(a, np.float64).ravel(); b = np.asarray(b, np.float64).ravel()
     den = np.linalg.norm(b)
     return float(np.linalg.norm(a - b) / den) if den > 0 else float(np.linalg.norm(a - b))
 
 
+class _Pack(dict):
+    """In-memory stand-in for a loaded npz (live dumps of the reference harness, tests/live_reference.py)."""
+    @property
+    def files(self):
+        return list(self.keys())
+
+
 class Golden:
-    def __init__(self, name):
+    def __init__(self, name, pack=None):
         self.name = name
-        self.z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        self.z = np.load(os.path.join(GOLDEN, name + ".npz")) if pack is None else _Pack(pack)
         self.cfg = Config.from_buffer_copy(self.z["config"].tobytes())
         self.steps = [int(s) for s in self.z["steps"]]
         self.nsteps = int(self.z["nsteps"])
@@ -118,10 +128,7 @@ def run_step_stages(lib, g: Golden, step, tol, capacity=0):
     upload_state(ctx, s0, cfg)
     ctx.celldiv(False)                         # the state already holds its periodic duplicates
     check_divide(ctx, s0)                      # divide of the reference's own state: must reproduce it exactly
-    noisy = (step == 0)                        # at t=0 the density rate is pure rounding noise of the DDT term
-    t2 = dict(tol)
-    if noisy:
-        t2["ar"] = 1.0
+    t2 = tol                                   # one tolerance for every step (round 1 did not check Ar at step 0)
     if g.symplectic:
         dt = float(s0["symplecticdtpre"])
         _, results["fpre"] = check_forces(ctx, g.stage(step, "fpre"), cfg, t2, capi.INTERSTEP_SYMPREDICTOR)
@@ -138,7 +145,17 @@ def run_step_stages(lib, g: Golden, step, tol, capacity=0):
         d1 = g.stage(step, "div1")
         st = ctx.download()
         assert np.array_equal(st["idp"], d1["idp"]) and np.array_equal(ctx.begincell(), d1["begincell"]), "mid-step divide"
-        _, results["fcor"] = check_forces(ctx, g.stage(step, "fcor"), cfg, t2 if noisy else tol, capi.INTERSTEP_SYMCORRECTOR)
+        # Corrector forces, the parity criterion: evaluated on the REFERENCE's own mid-step state (same inputs -> outputs within tol).
+        c2 = make_ctx(lib, cfg, capacity)
+        upload_state(c2, d1, cfg)
+        c2.celldiv(False)
+        _, results["fcor"] = check_forces(c2, g.stage(step, "fcor"), cfg, tol, capi.INTERSTEP_SYMCORRECTOR)
+        c2.close()
+        # The chained context (its mid-step state is this solver's own predictor result, equal to the reference's to 1e-6) goes on to
+        # feed the corrector update.  Its forces are bounded too, but by a propagation bound, not by the parity tolerance: Tait's
+        # equation turns a last-bit difference of rho into a relative pressure difference of 2^-23/(rho/rho0-1), which in a nearly
+        # uniform field (periodic box at step 0: rho/rho0-1 ~ 1e-4) is 1e-3 of the pressure.
+        _, results["fcor_chained"] = check_forces(ctx, g.stage(step, "fcor"), cfg, dict(tol, ace=PROPAGATION_TOL, ar=PROPAGATION_TOL), capi.INTERSTEP_SYMCORRECTOR)
         ctx.step_symcor(dt)
         u = g.stage(step, "ucor")
     else:

@@ -13,14 +13,13 @@ pytestmark = pytest.mark.gpu
 
 # north_star: cell assignment and sorted order bit-exact; single-step Ace/Ar/dt within 1e-5 relative L2 (fp32)
 TOL = dict(default=2e-5, ace=1e-5, ar=1e-5, dt=1e-5, viscdt=1e-5, acemax=1e-5, velmax=1e-6, pos=1e-8, state=1e-6)
-# Periodic box: the case starts from exactly uniform density, so in the corrector of step 0 the pressure field is nothing but the
-# float quantisation of rho/rho0 (steps of 0.13 Pa) and Ace is its residue: the production kernel measures 3.7e-5 there (the CPU
-# checker 1.8e-7 by doing the same roundings term by term).  At step 15 of the same case the production kernel is at 4.2e-7.
-TOL_PB = dict(TOL, ace=1e-4)
+# ONE tolerance for every case, stage and step.  Round 1 loosened Ace to 1e-4 for the periodic box and did not check Ar at step 0;
+# with the pressure of the reorder rounded like the reference's EOS both are inside 1e-5 (measured, tools/parity_floors.py on the 17
+# dumps: Ace <= 2.7e-6, Ar <= 6.7e-6, the periodic-box corrector of step 0 at 4.6e-7).
 
 
 def tol_for(name):
-    return TOL_PB if name.startswith("pb_") else TOL
+    return TOL
 
 
 @pytest.mark.parametrize("name", parity.GOLDEN_CASES)
@@ -73,10 +72,10 @@ def test_gpu_vs_oracle_steps(gpu_lib, oracle_lib, kind, n, nsteps):
         acea, ara = a.forces_download(); aceb, arb = b.forces_download()
         npb = ib.npb
         tol = tol_for("pb_" if kind == "periodicbox" else "db_")
-        if s > 0:
-            assert rl2(acea[npb:], aceb[npb:]) <= tol["ace"], ("ace", s, rl2(acea[npb:], aceb[npb:]))
+        assert rl2(acea[npb:], aceb[npb:]) <= tol["ace"], ("ace", s, rl2(acea[npb:], aceb[npb:]))
+        if s > 0 or np.linalg.norm(arb) > 1e-3 * np.sqrt(arb.size) * float(cd.cfg.rhopzero):   # v=0 at t=0: Ar is identically ~0 there
             assert rl2(ara, arb) <= tol["ar"], ("ar", s, rl2(ara, arb))
-            assert abs(fa.dt - fb.dt) / fb.dt <= tol["dt"]
+        assert abs(fa.dt - fb.dt) / fb.dt <= tol["dt"]
         dt = b.symplectic_dtpre
         a.step_sympre(dt); b.step_sympre(dt)
         ia, ib = a.celldiv(True), b.celldiv(True)
@@ -349,3 +348,48 @@ def test_gpu_excluded_particles_match_oracle(gpu_lib, oracle_lib, tstep):
     gone = set(st["idp"][[fl[10], fl[200], fl[400]]].tolist())
     assert gone.isdisjoint(set(sb["idp"].tolist()))
     a.close(); b.close()
+
+
+# ---- the reference solver run LIVE on the GPU box at the configuration sizes ---------------------------------
+@pytest.mark.parametrize("name,np_target,steps,nsteps", [("C1_dambreak_170k", 170000, [0, 12], 13), ("DB_2M", 2000000, [3], 4)])
+def test_gpu_stages_vs_live_reference(gpu_lib, name, np_target, steps, nsteps):
+    """C1 (BASELINE.json configs[0]: ~170 k particles, Symplectic + Wendland + delta-SPH) and DB(2 M): every stage of the dumped
+    steps -- divide (bit-exact order, cells, begin-cell table), predictor/corrector forces (Ace/Ar/dt <= 1e-5), updates -- against
+    the reference's JSphCpuSingle executed now, on this box."""
+    import live_reference
+    if not live_reference.available():
+        pytest.skip("oracle/_ref/ref_harness52 or bin/mkcase missing")
+    g, cd = live_reference.live_golden(name, "dambreak", np_target, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2"], steps, nsteps)
+    print(name, "np", cd.np_, "boundary fraction %.3f" % (cd.npb / cd.np_))
+    for step in g.steps:
+        res = parity.run_step_stages(gpu_lib, g, step, TOL, capacity=int(cd.np_ * 1.1) + 1000)
+        print(name, step, res)
+    if nsteps <= 20 and cd.np_ < 500000:
+        out = parity.run_trajectory(gpu_lib, g, capacity=int(cd.np_ * 1.1) + 1000)
+        print(name, "trajectory", out)
+        assert out["np"][0] == out["np"][1] and out["time"] < 1e-5 and out["pos"] < 1e-6 and out["velrhop"] < 1e-4
+
+
+def test_gpu_production_kernel_vs_ieee_kernel_at_20m(gpu_lib):
+    """DB(20 M), the benchmark state: the production kernel (variant 10: packed-half culling, deferred pair ring,
+    division-free body, row order of its own) against variant 1 (plain IEEE loop in the reference's structure and pair order, the
+    kernel the 17 reference dumps pin) on the same divide: Ace/Ar/dt within 1e-5."""
+    cd = dsph.make_case("dambreak", 20_000_000)
+    ctx = dsph.create_context(cd)
+    ctx.upload(cd.idp, cd.pos, cd.velrhop, cd.npb, cd.codes())
+    ctx.celldiv(True)
+    for _ in range(3):
+        ctx.step()
+    res = {}
+    for variant in (1, 10):
+        gpu_lib.lib.dsph_set_force_variant(ctx.h, variant)
+        ctx.celldiv(False)
+        fr = ctx.forces()
+        res[variant] = (ctx.forces_download(), fr)
+    (ace1, ar1), f1 = res[1]
+    (ace10, ar10), f10 = res[10]
+    npb = ctx.npb
+    out = dict(ace=rl2(ace10[npb:], ace1[npb:]), ar=rl2(ar10, ar1), dt=abs(f10.dt - f1.dt) / f1.dt, np=ctx.np_)
+    print("DB(20 M) production vs IEEE kernel:", out)
+    ctx.close()
+    assert out["ace"] <= TOL["ace"] and out["ar"] <= TOL["ar"] and out["dt"] <= TOL["dt"], out
