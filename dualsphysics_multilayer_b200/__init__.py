@@ -121,6 +121,15 @@ def load_case(dirname: str, casename: str) -> CaseData:
     return _case_from_c(c)
 
 
+def case_gauges(dirname: str, casename: str):
+    """Gauge definitions of <special><gauges> in <dirname>/<casename>.xml (list of capi.Gauge)."""
+    L = lib()
+    n = C.c_uint32()
+    out = (capi.Gauge * 256)()
+    L.check(L.fn("case_gauges")(dirname.encode(), casename.encode(), out, 256, C.byref(n)))
+    return [out[i] for i in range(min(n.value, 256))]
+
+
 def load_part(filename: str):
     """Reads one PART file (Part_NNNN.bi4 of this driver or of the reference).  Returns (CaseData, timestep, step)."""
     c = Case()

@@ -99,6 +99,23 @@ class Case(C.Structure):
                 ("nfluidblocks", C.c_uint32), ("fluidblock_count", C.c_uint32 * MAXPHASES)]
 
 
+class Gauge(C.Structure):
+    """dsph_gauge (include/dsph_b200.h): one in-solver gauge."""
+    _fields_ = [("type", C.c_int32), ("output", C.c_int32), ("name", C.c_char * 32),
+                ("computestart", C.c_double), ("computeend", C.c_double), ("computedt", C.c_double),
+                ("outputstart", C.c_double), ("outputend", C.c_double), ("outputdt", C.c_double),
+                ("point0", C.c_double * 3), ("point2", C.c_double * 3), ("pointdp", C.c_double), ("masslimit", C.c_float),
+                ("distlimit", C.c_float), ("height", C.c_double),
+                ("mkbound", C.c_uint32), ("idbegin", C.c_uint32), ("count", C.c_uint32), ("code", C.c_uint16), ("pad_", C.c_uint16)]
+
+
+class GaugeRes(C.Structure):
+    _fields_ = [("timestep", C.c_double), ("value", C.c_float * 3), ("computed", C.c_int32)]
+
+
+GAUGE_VEL, GAUGE_SWL, GAUGE_MAXZ, GAUGE_FORCE = 1, 2, 3, 4
+
+
 class SphError(RuntimeError):
     pass
 
@@ -165,6 +182,12 @@ class SphLib:
             f("mgpu_profile", C.c_int, vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64))
             f("mgpu_sent_records", C.c_int, vp, C.POINTER(C.c_uint64))
             f("celldiv_last_info", C.c_int, vp, C.POINTER(DivInfo))
+        if prefix == "dsph_":
+            f("gauges_config", C.c_int, vp, C.c_uint32, C.POINTER(Gauge))
+            f("gauges_run", C.c_int, vp, C.c_double, C.c_int, C.POINTER(GaugeRes))
+            f("gauges_results", C.c_int, vp, C.POINTER(GaugeRes))
+            f("gauges_set_time", C.c_int, vp, C.c_double)
+            f("case_gauges", C.c_int, C.c_char_p, C.c_char_p, C.POINTER(Gauge), C.c_uint32, C.POINTER(C.c_uint32))
         f("forces_launch", C.c_int, vp, C.c_int)
         f("forces_maxima_ptr", C.c_void_p, vp)
         f("forces_finish", C.c_int, vp, C.POINTER(ForceRes))
@@ -286,6 +309,25 @@ class SphContext:
     @symplectic_dtpre.setter
     def symplectic_dtpre(self, v):
         self.lib.check(self.lib.fn("set_symplectic_dtpre")(self.h, float(v)))
+
+    # -- in-solver gauges
+    def gauges_config(self, gauges):
+        arr = (Gauge * len(gauges))(*gauges)
+        self._ngauges = len(gauges)
+        self.lib.check(self.lib.fn("gauges_config")(self.h, len(gauges), arr))
+
+    def gauges_run(self, timestep, force_all=False):
+        res = (GaugeRes * self._ngauges)()
+        self.lib.check(self.lib.fn("gauges_run")(self.h, float(timestep), 1 if force_all else 0, res))
+        return list(res)
+
+    def gauges_results(self):
+        res = (GaugeRes * self._ngauges)()
+        self.lib.check(self.lib.fn("gauges_results")(self.h, res))
+        return list(res)
+
+    def gauges_set_time(self, t):
+        self.lib.check(self.lib.fn("gauges_set_time")(self.h, float(t)))
 
     # -- x-slab multi-GPU (see mgpu.py)
     def measure_points(self, points):

@@ -141,6 +141,19 @@ int dsph_mgpu_comm_attach(dsph_ctx *ctx,void *ncclcomm,int rank,int nranks){ NEE
 int dsph_mgpu_config_cuts(dsph_ctx *ctx,int rank,int nranks,const uint32_t *cuts){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgConfigCuts(rank,nranks,cuts); }); }
 uint32_t dsph_mgpu_halo_cells(const dsph_ctx *ctx){ return (ctx&&ctx->eng)? ctx->eng->MgHalo(): 0u; }
 int dsph_mgpu_exchange(dsph_ctx *ctx){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgExchange(); }); }
+int dsph_gauges_config(dsph_ctx *ctx,uint32_t n,const dsph_gauge *g){ NEEDCTX(ctx); if(n && !g){ g_lasterror="Null argument."; return DSPH_ERR_ARG; } return Guard([&]{ ctx->eng->GaugesConfig(n,g); }); }
+int dsph_gauges_run(dsph_ctx *ctx,double timestep,int force_all,dsph_gaugeres *res){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->GaugesRun(timestep,force_all!=0,res); }); }
+int dsph_gauges_results(dsph_ctx *ctx,dsph_gaugeres *res){ NEEDCTX(ctx); if(!res){ g_lasterror="Null argument."; return DSPH_ERR_ARG; } return Guard([&]{ if(!ctx->eng->gaugeres.empty())memcpy(res,ctx->eng->gaugeres.data(),ctx->eng->gaugeres.size()*sizeof(dsph_gaugeres)); }); }
+int dsph_gauges_set_time(dsph_ctx *ctx,double timestep){ NEEDCTX(ctx); ctx->eng->gaugetime=timestep; return DSPH_OK; }
+int dsph_case_gauges(const char *dir,const char *casename,dsph_gauge *out,uint32_t max,uint32_t *n){
+  if(!dir||!casename||!n){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  const int r=Guard([&]{
+    CaseData cd; LoadCase(cd,dir,casename);
+    *n=uint32_t(cd.gauges.size());
+    for(uint32_t i=0;i<*n && i<max && out;i++)out[i]=cd.gauges[i];
+  });
+  return r==DSPH_OK? r: DSPH_ERR_IO;
+}
 int dsph_celldiv_last_info(dsph_ctx *ctx,dsph_divinfo *info){ NEEDCTX(ctx); if(!info){ g_lasterror="Null argument."; return DSPH_ERR_ARG; } return Guard([&]{ ctx->eng->LastDivInfo(info); }); }
 int dsph_mgpu_sent_records(dsph_ctx *ctx,uint64_t *sent){ NEEDCTX(ctx); if(sent)*sent=ctx->eng->mgsentrecords; return DSPH_OK; }
 int dsph_mgpu_celldiv(dsph_ctx *ctx,dsph_divinfo *info){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgCellDivide(info); ctx->eng->FlushStepTimer(); }); }

@@ -63,6 +63,7 @@ Engine::Engine(int device_,const dsph_config &c,unsigned capacity):device(device
 Engine::~Engine(){
   cudaSetDevice(device);
   MgCommDestroy();
+  GaugesFree();
   if(stmcopy){ cudaStreamSynchronize(stmcopy); cudaStreamDestroy(stmcopy); cudaEventDestroy(evsnap); cudaEventDestroy(evsnapfree); }
   if(snapdev)cudaFree(snapdev);
   FreeAll();
@@ -202,7 +203,7 @@ void Engine::Upload(unsigned np_,unsigned npb_,const unsigned *hidp,const typeco
   CUCHECK(cudaSetDevice(device));
   if(np_>cap)throw EngineError(DSPH_ERR_ARG,"The number of particles exceeds the capacity of the context.");
   if(npb_>np_)throw EngineError(DSPH_ERR_ARG,"npb > np.");
-  np=np_; npb=npb_; npbok=npb_; npbper=npfper=0; haspre=false; boundchanged=true; blimok=false; divok=false;
+  np=np_; npb=npb_; npbok=npb_; npbper=npfper=0; haspre=false; boundchanged=true; blimok=false; divok=false; celltableok=false;
   std::vector<typecode> tmpcode;
   if(!hcode){
     tmpcode.resize(np);
@@ -320,7 +321,7 @@ void Engine::RunPeriodic(){
   // mark current periodic particles to be ignored
   ker_peri_ignore<<<(np+B-1)/B,B,0,stm>>>(np,code[cur]); launches++;
   const unsigned npb0=npb, npf0=np-npb;
-  npbper=npfper=0; boundchanged=true;
+  npbper=npfper=0; boundchanged=true; celltableok=false;
   for(unsigned ctype=0;ctype<2;ctype++){
     const unsigned pini=(ctype? npb0: 0), num=(ctype? npf0: npb0);
     for(unsigned cper=0;cper<3;cper++)if((cper==0&&cfg.perix)||(cper==1&&cfg.periy)||(cper==2&&cfg.periz)){
@@ -433,7 +434,7 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
   for(int i=0;i<3;i++)if(lastcellmin[i]!=dp.cellmin[i] || lastcellmax[i]!=dp.cellmax[i])same=false;
   dividefull=!same;
   for(int i=0;i<3;i++){ lastcellmin[i]=dp.cellmin[i]; lastcellmax[i]=dp.cellmax[i]; }
-  divok=true;
+  divok=true; celltableok=true;
   npfout_last=dp.npfout; npout_total+=dp.npfout;
   np=dp.npfinal; npb=dp.npbfinal; npbok=npb-dp.npbignore;
   boundchanged=false; forcesok=false;
@@ -701,6 +702,7 @@ void Engine::Step(double *stepdt,dsph_forceres *res){
     dt=DtVariable(nullptr,nullptr);
     StepVerlet(dt);
   }
+  if(!gauges.empty()){ GaugesRun(gaugetime+dt,false,nullptr); gaugetime+=dt; }   // RunGaugeSystem(TimeStep+stepdt), S/JSphCpuSingle.cpp:1095
   CellDivide(true,nullptr); FlushStepTimer();
   if(stepdt)*stepdt=dt;
 }
@@ -798,7 +800,7 @@ void Engine::MgUnpackAsync(const unsigned counts[8],const void *recvleft,const v
   up(fl,(const char*)recvleft+size_t(bgl)*d.recbytes);
   up(fr,(const char*)recvright+size_t(bgr)*d.recbytes);
   npbper=bgl+bgr; npfper=fl+fr; np+=total;
-  boundchanged=true;
+  boundchanged=true; celltableok=false;
 }
 void Engine::MgUnpack(const unsigned counts[8],const void *recvleft,const void *recvright){
   MgUnpackAsync(counts,recvleft,recvright);

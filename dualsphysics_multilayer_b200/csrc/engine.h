@@ -133,6 +133,13 @@ class Engine {
   void MgUnpack(const unsigned counts[8],const void *recvleft,const void *recvright);
   void ForcesDownload(unsigned first,unsigned count,float *ace,float *ar);
   void MeasurePoints(unsigned n,const double *points,float *press,float *vel,float *kcorr);
+  // in-solver gauges (gauges.cu)
+  std::vector<dsph_gauge> gauges; std::vector<double> gaugenext; std::vector<dsph_gaugeres> gaugeres;
+  double gaugetime=0; bool celltableok=false;
+  char *gaugedev=nullptr; size_t gaugedevcap=0; float *gaugehost=nullptr; size_t gaugehostcap=0; float *gaugepartace=nullptr; unsigned gaugepartacecap=0;
+  void GaugesConfig(unsigned n,const dsph_gauge *g);
+  unsigned GaugesRun(double timestep,bool all,dsph_gaugeres *res);
+  void GaugesFree();
   void Pips(unsigned long long *fr,unsigned long long *fc,unsigned long long *br,unsigned long long *bc);
   double DtVariable(double *dt1,double *dt2,double *dt3=nullptr)const;
   void FillForceRes(dsph_forceres *res)const;

@@ -263,6 +263,68 @@ void LoadCase(CaseData &cd,const std::string &dir,const std::string &casename){
     }
     std::sort(c.phases,c.phases+c.nn_nphases,[](const dsph_phase &a,const dsph_phase &b){ return a.mkfluid<b.mkfluid; });
   }
+  // ---- gauges (JGaugeSystem::ReadXml / ReadXmlCommon, S/JDsGaugeSystem.cpp:186-275); defaults of JGaugeSystem::ResetCfgDefault (:84-93)
+  cd.gauges.clear();
+  if(const XmlNode *gs=ex->Path("special.gauges")){
+    struct Common { double computedt,computestart,computeend,outputdt,outputstart,outputend; bool output; };
+    auto readcommon=[&](const XmlNode *e,Common cm){
+      if(e){
+        auto V=[&](const char *n,const char *a,double def){ const XmlNode *q=e->Child(n); return (q && q->Has(a))? q->Dbl(a): def; };
+        cm.computedt=V("computedt","value",cm.computedt); cm.computestart=V("computetime","start",cm.computestart); cm.computeend=V("computetime","end",cm.computeend);
+        if(const XmlNode *q=e->Child("output"))if(q->Has("value"))cm.output=q->Bool("value");
+        cm.outputdt=V("outputdt","value",cm.outputdt); cm.outputstart=V("outputtime","start",cm.outputstart); cm.outputend=V("outputtime","end",cm.outputend);
+      }
+      return cm;
+    };
+    Common def{c.timeout,0,c.timemax,c.timeout,0,c.timemax,false};
+    def=readcommon(gs->Child("default"),def);
+    auto P3=[&](const XmlNode *e,const char *n,double *v){ const XmlNode *q=e->Child(n); if(!q)throw std::runtime_error(std::string("xml: <gauges> element <")+n+"> is missing"); v[0]=q->Dbl("x"); v[1]=q->Dbl("y"); v[2]=q->Dbl("z"); };
+    for(auto &ep:gs->children){
+      const XmlNode *e=ep.get();
+      if(e->name.empty() || e->name[0]=='_' || e->name=="default")continue;
+      if(e->Has("active") && !e->Bool("active"))continue;
+      const Common cm=readcommon(e,def);
+      dsph_gauge g; memset(&g,0,sizeof(g));
+      const std::string name=e->Str("name");
+      for(auto &o:cd.gauges)if(name==o.name)throw std::runtime_error("The gauge name '"+name+"' already exists.");
+      strncpy(g.name,name.c_str(),sizeof(g.name)-1);
+      g.computedt=cm.computedt; g.computestart=cm.computestart; g.computeend=cm.computeend;
+      g.output=cm.output? 1: 0; g.outputdt=cm.outputdt; g.outputstart=cm.outputstart; g.outputend=cm.outputend;
+      if(e->name=="velocity"){ g.type=DSPH_GAUGE_VEL; P3(e,"point",g.point0); }
+      else if(e->name=="swl"){
+        g.type=DSPH_GAUGE_SWL;
+        g.masslimit=c.massfluid*(c.simulate2d? 0.4f: 0.5f);
+        if(const XmlNode *q=e->Child("masslimit")){ if(q->Has("value"))g.masslimit=float(q->Dbl("value")); else if(q->Has("coef"))g.masslimit=c.massfluid*float(q->Dbl("coef")); }
+        if(!(g.masslimit>0))throw std::runtime_error("The masslimit of gauge '"+name+"' is invalid.");
+        if(const XmlNode *q=e->Child("pointdp")){ if(q->Has("coefdp"))g.pointdp=c.dp*float(q->Dbl("coefdp")); else g.pointdp=float(q->Dbl("value")); }
+        if(!(g.pointdp>0))throw std::runtime_error("The pointdp of gauge '"+name+"' is invalid.");
+        P3(e,"point0",g.point0); P3(e,"point2",g.point2);
+      }
+      else if(e->name=="maxz"){
+        g.type=DSPH_GAUGE_MAXZ; P3(e,"point0",g.point0);
+        { const XmlNode *q=e->Child("height"); if(!q)throw std::runtime_error("xml: <maxz><height> is missing"); g.height=float(q->Dbl("value")); }
+        if(const XmlNode *q=e->Child("distlimit")){
+          if(q->Has("coefdp"))g.distlimit=float(c.dp*float(q->Dbl("coefdp")));
+          else if(q->Has("coefh"))g.distlimit=float(c.kernelh*float(q->Dbl("coefh")));
+          else g.distlimit=float(q->Dbl("value"));
+        }
+        if(!(g.distlimit>0))throw std::runtime_error("The distlimit of gauge '"+name+"' is invalid.");
+      }
+      else if(e->name=="force"){
+        g.type=DSPH_GAUGE_FORCE;
+        const XmlNode *q=e->Child("target"); if(!q)throw std::runtime_error("xml: <force><target> is missing");
+        g.mkbound=unsigned(q->Int("mkbound"));
+        const MkBlock *mb=nullptr; unsigned rank=0,rk[4]={0,0,0,0};
+        for(auto &b:cd.blocks){ if(b.type<3 && b.mktype==g.mkbound && !mb){ mb=&b; rank=rk[b.type]; } rk[b.type]++; }
+        if(!mb)throw std::runtime_error("Error loading boundary objects. Mkbound of gauge '"+name+"' is unknown.");
+        if(mb->type!=0 && mb->type!=1)throw std::runtime_error("Type of boundary particles of gauge '"+name+"' is invalid. Only fixed or moving particles are allowed.");
+        g.idbegin=mb->begin; g.count=mb->count;
+        g.code=dsph_typecode((mb->type==0? DSPH_CODE_TYPE_FIXED: DSPH_CODE_TYPE_MOVING)|rank);      // JSphMk: type | index of the block within its type
+      }
+      else throw std::runtime_error("Gauge type '"+e->name+"' is invalid.");
+      cd.gauges.push_back(g);
+    }
+  }
   // ---- particle data (JPartsLoad4::LoadParticles)
   PartHead h; PartData p;
   LoadPartFile(dir+"/"+casename+".bi4",h,p,0);

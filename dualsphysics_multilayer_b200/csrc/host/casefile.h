@@ -23,6 +23,7 @@ struct CaseData {
   std::vector<unsigned> idp;
   std::vector<double> pos;                 // xyz packed
   std::vector<float> velrhop;              // xyzw packed
+  std::vector<dsph_gauge> gauges;          // <special><gauges> (S/JDsGaugeSystem.cpp:186-275)
   unsigned np()const{ return (unsigned)idp.size(); }
   unsigned npb()const{ return cfg.casenfixed+cfg.casenmoving; }
 };

@@ -169,6 +169,42 @@ static void SaveProbes(Engine &eng,const std::vector<double> &pts,const std::str
   fclose(f);
 }
 
+// Gauge results -> Gauges<Type>_<name>.csv in the output directory, columns and number format of JGauge*::SaveResults
+// (S/JDsGaugeItem.cpp:276-298,489-512,694-714,936-957); rows are buffered and written at every PART like JGaugeSystem::SaveResults(Part).
+struct GaugeOutput {
+  std::vector<dsph_gauge> defs; std::vector<double> outnext; std::vector<std::string> buf; std::vector<bool> started; std::string dir;
+  void Config(const std::vector<dsph_gauge> &g,const std::string &dirout){ defs=g; outnext.assign(g.size(),0.0); buf.assign(g.size(),std::string()); started.assign(g.size(),false); dir=dirout; }
+  void Collect(const std::vector<dsph_gaugeres> &res){
+    for(size_t i=0;i<defs.size() && i<res.size();i++){
+      const dsph_gauge &g=defs[i]; const dsph_gaugeres &r=res[i];
+      if(!r.computed || !g.output)continue;
+      const double t=r.timestep;
+      if(!(t>=outnext[i] && g.outputstart<=t && t<=g.outputend))continue;              // JGaugeItem::Output (S/JDsGaugeItem.h:165)
+      char tx[512];
+      const float *v=r.value;
+      if(g.type==DSPH_GAUGE_VEL)snprintf(tx,sizeof(tx),"%g;%g;%g;%g;%g;%g;%g\n",t,v[0],v[1],v[2],float(g.point0[0]),float(g.point0[1]),float(g.point0[2]));
+      else if(g.type==DSPH_GAUGE_SWL)snprintf(tx,sizeof(tx),"%g;%g;%g;%g;%g;%g;%g;%g;%g;%g\n",t,v[0],v[1],v[2],float(g.point0[0]),float(g.point0[1]),float(g.point0[2]),float(g.point2[0]),float(g.point2[1]),float(g.point2[2]));
+      else if(g.type==DSPH_GAUGE_MAXZ)snprintf(tx,sizeof(tx),"%g;%g;%g;%g;%g\n",t,v[2],float(g.point0[0]),float(g.point0[1]),float(g.point0[2]));
+      else snprintf(tx,sizeof(tx),"%g;%g;%g;%g;%g\n",t,std::sqrt(v[0]*v[0]+v[1]*v[1]+v[2]*v[2]),v[0],v[1],v[2]);
+      buf[i]+=tx;
+      if(g.outputdt){ const unsigned nt=unsigned(t/g.outputdt); outnext[i]=g.outputdt*nt; if(outnext[i]<=t)outnext[i]=g.outputdt*(nt+1); }
+    }
+  }
+  void Save(){
+    static const char *tn[5]={"","Vel","SWL","MaxZ","Force"};
+    static const char *hd[5]={"","time [s];velx [m/s];vely [m/s];velz [m/s];posx [m];posy [m];posz [m]","time [s];swlx [m];swly [m];swlz [m];pos0x [m];pos0y [m];pos0z [m];pos2x [m];pos2y [m];pos2z [m]",
+                              "time [s];zmax [m];posx [m];posy [m];posz [m]","time [s];force [N];forcex [N];forcey [N];forcez [N]"};
+    for(size_t i=0;i<defs.size();i++)if(!buf[i].empty()){
+      const std::string file=dir+"/Gauges"+tn[defs[i].type]+"_"+defs[i].name+".csv";
+      FILE *f=fopen(file.c_str(),started[i]? "a": "w");
+      if(!f)continue;
+      if(!started[i])fprintf(f,"%s\n",hd[defs[i].type]);
+      fputs(buf[i].c_str(),f); fclose(f);
+      started[i]=true; buf[i].clear();
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // x-slab runs (-mgpu:N): one host thread per GPU of this process, each with its own Engine; the exchange and the dt all-reduce go
 // through the library's NCCL transport (mgpu_comm.cu), so the threads run in lockstep without any host-side message passing.
@@ -250,6 +286,18 @@ static RunSummary RunRank(const RunOptions &opt,CaseData &cd,int rank,SlabGroup 
     eng.MgCellDivide(&di);
   }
   else eng.CellDivide(true,&di);
+  // ---- gauges: first evaluation on the initial state (RunGaugeSystem(TimeStep,true), S/JSphCpuSingle.cpp:1070)
+  GaugeOutput gout;
+  if(!cd.gauges.empty()){
+    if(slabs)log.Printf("*** WARNING: gauges are not evaluated in x-slab runs.");
+    else{
+      eng.GaugesConfig(unsigned(cd.gauges.size()),cd.gauges.data());
+      gout.Config(cd.gauges,opt.dirout);
+      eng.gaugetime=timestep;
+      eng.GaugesRun(timestep,false,nullptr); gout.Collect(eng.gaugeres);
+      log.Printf("Gauges: %u (<special><gauges>) -> Gauges<Type>_<name>.csv",unsigned(cd.gauges.size()));
+    }
+  }
   // ---- output set
   PartSetHead head;
   MakePartSetHead(head,cd,eng.k.maprealposmin,eng.k.maprealposmax,eng.k.periactive,eng.k.perixinc,eng.k.periyinc,eng.k.perizinc);
@@ -270,6 +318,7 @@ static RunSummary RunRank(const RunOptions &opt,CaseData &cd,int rank,SlabGroup 
   if(opt.partbegin<0){
     if(opt.savepart)SavePart(eng,cd,part,timestep,0,0,0,pst,log,*writer);
     SaveProbes(eng,probes,opt.dirout,part,timestep);
+    gout.Save();
   }
   part++;
   double timepartnext=NextTime(timestep,c.timeout);
@@ -283,6 +332,7 @@ static RunSummary RunRank(const RunOptions &opt,CaseData &cd,int rank,SlabGroup 
     if(slabs)eng.MgStep(&dt,&fr); else eng.Step(&dt,&fr);
     partsteps+=eng.np-eng.npbper-eng.npfper;
     timestep+=dt; nstep++;
+    if(!gout.defs.empty())gout.Collect(eng.gaugeres);
     pst.dtmin=std::min(pst.dtmin,dt); pst.dtmax=std::max(pst.dtmax,dt);
     if(slabs && nstep%rebalance_every==0){
       // collective: the same decision on every rank (the histogram and the costs are all-reduced)
@@ -302,6 +352,7 @@ static RunSummary RunRank(const RunOptions &opt,CaseData &cd,int rank,SlabGroup 
       if(opt.savepart)SavePart(eng,cd,part,timestep,nstep,Elapsed(),nout,pst,log,*writer);
       else log.Printf("Part_%04u  %12.6f  %12llu  dt=%.6g  np=%u",part,timestep,nstep,dt,eng.np);
       SaveProbes(eng,probes,opt.dirout,part,timestep);
+      gout.Save();
       part++;
       timepartnext=NextTime(timestep,c.timeout);
       if(partoutstop){ log.Printf("Particles OUT limit reached..."); break; }
@@ -309,6 +360,7 @@ static RunSummary RunRank(const RunOptions &opt,CaseData &cd,int rank,SlabGroup 
     if(opt.nsteps>0 && nstep>=(unsigned long long)opt.nsteps)break;
   }
   eng.FlushStepTimer();
+  gout.Save();
   const double tsim=std::chrono::duration<double>(std::chrono::steady_clock::now()-tsim0).count();
   double twrite=0;
   if(writer){ const auto tw0=std::chrono::steady_clock::now(); writer->Finish(); twrite=std::chrono::duration<double>(std::chrono::steady_clock::now()-tw0).count(); }   // the last PART must be complete before the run reports success

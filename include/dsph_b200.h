@@ -294,6 +294,38 @@ int dsph_forces_finish(dsph_ctx *ctx,dsph_forceres *res);
 /* domain constants needed to place the cuts: cell size, origin and number of cell columns (JSph::ConfigCellDivision) */
 int dsph_domain_info(const dsph_config *cfg,double *scell,double domposmin[3],uint32_t domcells[3]);
 
+/* ---- in-solver gauges: what JGaugeVelocity / JGaugeSwl / JGaugeMaxZ / JGaugeForce compute (CPU:
+ *      S/JDsGaugeItem.cpp:325-367,575-600,736-776,986-1041; GPU: S/JDsGauge_ker.cu:50,168,250,311), evaluated on the device for all the
+ *      gauges of a step at once.  Definitions come from <special><gauges> of Case.xml (S/JDsGaugeSystem.cpp:186-275; dsph_case_gauges)
+ *      or from the caller.  Timing follows JGaugeItem (S/JDsGaugeItem.h:164-165, S/JDsGaugeItem.cpp:204-211): a gauge is computed at
+ *      a step when timestep >= its next compute time inside [computestart, computeend].  dsph_step runs the configured gauges where
+ *      the reference runs them: after the step update, BEFORE the closing divide (S/JSphCpuSingle.cpp:1094-1098), with
+ *      timestep = (time set by dsph_gauges_set_time) + dt. ---------------------------------------------------------------------- */
+enum { DSPH_GAUGE_VEL=1, DSPH_GAUGE_SWL=2, DSPH_GAUGE_MAXZ=3, DSPH_GAUGE_FORCE=4 };
+typedef struct dsph_gauge {
+  int32_t type; int32_t output;                 /* output: results go to Gauges<Type>_<name>.csv (driver) */
+  char name[32];
+  double computestart, computeend, computedt;   /* computedt = 0: every step */
+  double outputstart, outputend, outputdt;
+  double point0[3], point2[3];                  /* vel: point0 | swl: point0 -> point2 | maxz: point0 */
+  double pointdp; float masslimit;              /* swl: spacing of the line points, mass threshold (default 0.5*massfluid, 0.4 in 2-D) */
+  float distlimit; double height;               /* maxz */
+  uint32_t mkbound, idbegin, count; dsph_typecode code; uint16_t pad_;   /* force: boundary mk block (id range and particle code) */
+} dsph_gauge;
+typedef struct dsph_gaugeres {
+  double timestep;      /* time of the last evaluation */
+  float value[3];       /* vel: velocity | swl: surface point | maxz: (0,0,zmax) | force: force [N] */
+  int32_t computed;     /* 1 when the last dsph_gauges_run / dsph_step evaluated this gauge */
+} dsph_gaugeres;
+int dsph_gauges_config(dsph_ctx *ctx,uint32_t n,const dsph_gauge *gauges);
+/* evaluates the gauges that are due at `timestep` (all of them when force_all != 0) on the current state and cell table;
+ * results (n entries, every gauge: the last result of those not evaluated now) may be NULL */
+int dsph_gauges_run(dsph_ctx *ctx,double timestep,int force_all,dsph_gaugeres *results);
+int dsph_gauges_results(dsph_ctx *ctx,dsph_gaugeres *results);
+int dsph_gauges_set_time(dsph_ctx *ctx,double timestep);   /* simulation time at the START of the next dsph_step */
+/* gauge definitions of <dir>/<casename>.xml; returns the number found in *n (at most max are written) */
+int dsph_case_gauges(const char *dir,const char *casename,dsph_gauge *out,uint32_t max,uint32_t *n);
+
 /* ---- case tooling (host only, no GPU): GenCase is a missing blob in the reference, these build the
  *      synthetic benchmark cases of SURVEY.md 8(d) and read/write Case.xml + Case.bi4 ------------- */
 typedef struct dsph_case {

@@ -23,6 +23,10 @@
 #include "JArraysCpu.h"
 #include "JSphShifting.h"
 #include "JDsOutputTime.h"
+#ifndef HARNESS_NN
+#include "JDsGaugeSystem.h"
+#include "JDsGaugeItem.h"
+#endif
 #include "Functions.h"
 #include "ref_dump.h"
 #include <set>
@@ -118,6 +122,28 @@ class RefHarness : public JSphCpuSingle {
 #endif
   }
 
+#ifndef HARNESS_NN
+  //-Last results of the reference's own gauges (JGaugeSystem, configured from <special><gauges> of the case): type and 9 floats per gauge
+  // (vel: point,vel | swl: point0,point2,posswl | maxz: point0,(0,0,zmax) | force: force), computed by RunGaugeSystem where
+  // JSphCpuSingle::Run computes them (S/JSphCpuSingle.cpp:1070,1095).
+  void DumpGauges(unsigned step,const char *stage,double timestep){
+    const unsigned ng=GaugeSystem->GetCount();
+    RefDumpWriter w(DumpName(step,stage));
+    w.U32("count",ng); w.F64("timestep",timestep);
+    std::vector<unsigned> type(ng); std::vector<float> val(size_t(ng)*9,0.f); std::vector<double> tim(ng,0.0);
+    for(unsigned c=0;c<ng;c++){
+      JGaugeItem *g=GaugeSystem->GetGauge(c);
+      type[c]=unsigned(g->Type);
+      float *v=&val[size_t(c)*9];
+      if(g->Type==JGaugeItem::GAUGE_Vel){ const JGaugeVelocity::StGaugeVelRes &r=((JGaugeVelocity*)g)->GetResult(); tim[c]=r.timestep; v[0]=r.point.x; v[1]=r.point.y; v[2]=r.point.z; v[3]=r.vel.x; v[4]=r.vel.y; v[5]=r.vel.z; }
+      else if(g->Type==JGaugeItem::GAUGE_Swl){ const JGaugeSwl::StGaugeSwlRes &r=((JGaugeSwl*)g)->GetResult(); tim[c]=r.timestep; v[0]=r.point0.x; v[1]=r.point0.y; v[2]=r.point0.z; v[3]=r.point2.x; v[4]=r.point2.y; v[5]=r.point2.z; v[6]=r.posswl.x; v[7]=r.posswl.y; v[8]=r.posswl.z; }
+      else if(g->Type==JGaugeItem::GAUGE_MaxZ){ const JGaugeMaxZ::StGaugeMaxzRes &r=((JGaugeMaxZ*)g)->GetResult(); tim[c]=r.timestep; v[0]=r.point0.x; v[1]=r.point0.y; v[2]=r.point0.z; v[5]=r.zmax; }
+      else if(g->Type==JGaugeItem::GAUGE_Force){ const JGaugeForce::StGaugeForceRes &r=((JGaugeForce*)g)->GetResult(); tim[c]=r.timestep; v[0]=r.force.x; v[1]=r.force.y; v[2]=r.force.z; }
+    }
+    w.Add("type",2,1,ng,type.data()); w.Add("values",3,9,ng,val.data()); w.Add("time",4,1,ng,tim.data());
+  }
+#endif
+
   //-Same call sequence as JSphCpuSingle::ComputeStep_Sym, with dumps in between.
   double StepSymDump(unsigned step){
     const double dt=SymplecticDtPre;
@@ -182,6 +208,8 @@ class RefHarness : public JSphCpuSingle {
     ConfigRunMode();
     VisuParticleSummary();
     InitRunCpu();
+    RunGaugeSystem(TimeStep,true);
+    if(GaugeSystem->GetCount())DumpGauges(0,"ginit",TimeStep);
     FreePartsInit();
     UpdateMaxValues();
     SaveData();
@@ -201,6 +229,9 @@ class RefHarness : public JSphCpuSingle {
         stepdt=(TStep==STEP_Symplectic? StepSymDump(step): StepVerDump(step));
       }
       else stepdt=ComputeStep();
+#ifndef HARNESS_NN
+      if(GaugeSystem->GetCount()){ RunGaugeSystem(TimeStep+stepdt); if(dump)DumpGauges(step,"gauges",TimeStep+stepdt); }
+#endif
       RunCellDivide(true);
       TimeStep+=stepdt;
       LastDt=stepdt;

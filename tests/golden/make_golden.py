@@ -50,15 +50,51 @@ CASES = [
     # particles leaving: a RhopOut window just above the initial hydrostatic maximum excludes 4 / 20 / 146 particles by steps 10 / 20 / 40 (OUTRHOP marking in
     # the step update, special boxes of the divide, NpfOut bookkeeping); options after "xml:" patch <parameter> values of Case.xml
     ("db_sym_wend_art_ddt2_rhopout", "dambreak", 3000, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2", "xml:RhopOutMax=1002.14", "xml:RhopOutMin=999.2"], [10, 20, 40], 41),
+    # in-solver gauges of the reference (JGaugeSystem: velocity, swl, maxz, force; computed every step), dumped by the harness at the
+    # initial state and at the listed steps; "gauges:" injects the <special><gauges> block below into Case.xml
+    ("db_sym_wend_art_ddt2_gauges", "dambreak", 3000, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2", "gauges:"], [0, 20, 60], 61),
+    ("db_ver_wend_art_ddt2_gauges", "dambreak", 6000, ["tstep=1", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2", "verletsteps=10", "gauges:"], [35], 36),
     ("db_ver_wend_art_ddt1_rhopout", "dambreak", 3000, ["tstep=1", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=1", "verletsteps=3", "xml:RhopOutMax=1002.14", "xml:RhopOutMin=999.2"], [12, 30], 31),
 ]
+
+
+GAUGES_XML = """    <special>
+      <gauges>
+        <default>
+          <savevtkpart value="false" />
+          <computedt value="0" />
+          <computetime start="0" end="10" />
+          <output value="true" />
+          <outputdt value="0" />
+          <outputtime start="0" end="10" />
+        </default>
+        <velocity name="Vcol"><point x="0.2" y="0.33" z="0.1" /></velocity>
+        <velocity name="Vtoe"><point x="0.38" y="0.30" z="0.06" /></velocity>
+        <velocity name="Vdry"><point x="0.9" y="0.33" z="0.05" /></velocity>
+        <swl name="Hcol"><point0 x="0.2" y="0.33" z="0.0" /><point2 x="0.2" y="0.33" z="0.4" /><pointdp coefdp="0.5" /><masslimit coef="0.5" /></swl>
+        <swl name="Front"><point0 x="0.05" y="0.33" z="0.03" /><point2 x="1.55" y="0.33" z="0.03" /><pointdp coefdp="0.5" /></swl>
+        <maxz name="Zcol"><point0 x="0.3" y="0.33" z="0.0" /><height value="0.4" /><distlimit coefdp="3" /></maxz>
+        <maxz name="Zdry"><point0 x="1.2" y="0.33" z="0.0" /><height value="0.4" /><distlimit coefh="2" /></maxz>
+        <force name="Ftank"><target mkbound="0" /></force>
+      </gauges>
+    </special>
+"""
+
+
+def inject_gauges(xmlfile):
+    """<special><gauges> of GAUGES_XML right behind <execution> (the synthetic single-phase cases have no <special> of their own)."""
+    xml = open(xmlfile).read()
+    assert "<special>" not in xml and "<execution>" in xml
+    open(xmlfile, "w").write(xml.replace("<execution>\n", "<execution>\n" + GAUGES_XML, 1))
 
 
 def run(name, kind, nptarget, opts, steps, nsteps, outdir):
     tmp = tempfile.mkdtemp(prefix="golden_")
     try:
-        subprocess.check_call([MKCASE, kind, str(nptarget), tmp, "Case"] + [o for o in opts if not o.startswith("xml:")], stdout=subprocess.DEVNULL)
+        subprocess.check_call([MKCASE, kind, str(nptarget), tmp, "Case"] + [o for o in opts if not o.startswith("xml:") and o != "gauges:"], stdout=subprocess.DEVNULL)
         xmlfile = os.path.join(tmp, "Case.xml")
+        if "gauges:" in opts:
+            inject_gauges(xmlfile)
         xml = open(xmlfile).read()
         for o in opts:
             if o.startswith("xml:"):
@@ -80,6 +116,8 @@ def run(name, kind, nptarget, opts, steps, nsteps, outdir):
         pack = {"config": np.frombuffer(bytes(cd.cfg), np.uint8).copy(), "case/idp": cd.idp, "case/pos": cd.pos,
                 "case/velrhop": cd.velrhop, "case/code": cd.codes(), "case/npb": np.uint32(cd.npb), "steps": np.array(steps, np.uint32),
                 "nsteps": np.uint32(nsteps), "case/caseposmin": np.array(cd.caseposmin), "case/caseposmax": np.array(cd.caseposmax)}
+        if "gauges:" in opts:
+            pack["case/xml"] = np.frombuffer(open(xmlfile, "rb").read(), np.uint8).copy()
         for f in sorted(os.listdir(os.path.join(tmp, "dump"))):
             d = read_dump(os.path.join(tmp, "dump", f))
             stem = f[:-4]
