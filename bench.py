@@ -138,7 +138,7 @@ def _run_refgpu(tmp, nsteps, svtimers):
     return float(m1.group(1)), int(m2.group(1)), int(m3.group(1)), tim
 
 
-def reference_gpu_baseline(npart, kind="dambreak", lengths=(20, 60, 120), repeats=3):
+def reference_gpu_baseline(npart, kind="dambreak", lengths=(20, 50, 80), repeats=2):
     """The reference's OWN GPU solver (JSphGpuSingle + its CUDA kernels, S/Makefile flags) recompiled for sm_100 by
     `make -C oracle gpu52`, run on this GPU on the same workload.  Method: one discarded warm-up process
     (driver/context start-up, module load, file cache), then `repeats` series of runs of `lengths` steps each; the per-step
@@ -183,15 +183,24 @@ def reference_gpu_baseline(npart, kind="dambreak", lengths=(20, 60, 120), repeat
         span = max(best) - min(best)
         fit_ok = bool(b_all and b_all > 0 and res_all <= 0.05 * span)
         agree = bool(bt and b_all and abs(bt - b_all) <= 0.10 * b_all)
+        timers_consistent = bool(bt and tsum and abs(tsum / (1e3 * bt) - 1.0) <= 0.10)
+        # What is stable and what is not (measured on three boxes): the reference's CF-Forces slope repeats to ~1 % (112.7 / 113 ms per
+        # step = 2 evaluations), its NL-RadixSort slope does not (26 ... 130 ms per step: thrust::sort_by_key allocates and frees its
+        # temporaries in every call, and cudaMalloc/cudaFree serialise with everything else on the device).  `value` is therefore the
+        # reference's BEST case (slope through its fastest runs); `reliable` says that this line fits AND that the reference's own
+        # synchronising timers add up to its run time within 10 % (the internal-consistency check VERDICT r01 asked for);
+        # `agrees_with_timer_series` is reported but the two series differ by the erratic sort.
         return {"value": npa / b_all / 1e6 if b_all and b_all > 0 else None, "unit": UNIT, "np": npa, "ms_per_step": 1e3 * b_all,
                 "rms_residual_ms": 1e3 * res_all, "fastest_runtime_s": best, "series": series, "series_slope_spread": spread,
-                "reliable": bool(fit_ok and agree), "fit_ok": fit_ok, "agrees_with_timer_series": agree,
+                "reliable": bool(fit_ok and timers_consistent), "fit_ok": fit_ok, "timers_consistent": timers_consistent, "agrees_with_timer_series": agree,
                 "with_sync_timers": {"ms_per_step": 1e3 * bt, "rms_residual_ms": 1e3 * rest, "timers_ms_per_step": split, "timers_sum_ms_per_step": tsum,
                                      "timers_sum_over_runtime": (tsum / (1e3 * bt) if bt else None)},
+                "cf_forces_ms_per_evaluation": (split.get("CF-Forces", 0.0) / 2.0 if split.get("CF-Forces") else None),
                 "wall_s": time.time() - t0,
                 "what": "reference DualSPHysics5.2 GPU solver (its own CUDA kernels + thrust sort, nvcc 12.9 -O3 -use_fast_math, sm_100) on this GPU, %s at %d "
                         "particles: least-squares slope of its 'Simulation Runtime' over the fastest of %d runs of each of %s steps, after one discarded warm-up process; "
-                        "timer split from a third series with -svtimers:1" % (WORKLOADS[kind][0], npa, repeats, "/".join(str(v) for v in lengths))}
+                        "timer split from a further series with -svtimers:1; cf_forces_ms_per_evaluation = its CF-Forces slope / 2 (Symplectic), to be "
+                        "compared with roofline.avg_launch_ms + the boundary kernel of this repository" % (WORKLOADS[kind][0], npa, repeats, "/".join(str(v) for v in lengths))}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

@@ -3,6 +3,7 @@
 // timed with CUDA events on it.  Sequencing follows JSphGpuSingle::RunCellDivide / Interaction_Forces /
 // ComputeStep_Sym / ComputeStep_Ver (S/JSphGpuSingle.cpp:331-417,435-486,548-596).
 #include "engine.h"
+#include <nvtx3/nvToolsExt.h>
 #include "radixsort.cuh"
 #include "celldiv.cuh"
 #include "forces_api.h"
@@ -17,6 +18,14 @@
 #include <algorithm>
 
 namespace dsph {
+
+// NVTX ranges named like the reference's GPU timers (S/JDsTimersGpu.h:64-88: NL-Limits ... SU-ComputeStep): host-side ranges around the
+// enqueue of each phase, projected onto the stream by Nsight Systems / Compute.  nvtx3 is header-only and resolves the tool's
+// injection library at run time: no link dependency, a few ns per call without a tool attached.
+static inline void NvtxBegin(const char *name){ nvtxRangePushA(name); }
+static inline void NvtxEnd(){ nvtxRangePop(); }
+static inline void NvtxNext(const char *name){ nvtxRangePop(); nvtxRangePushA(name); }
+
 
 #define CUCHECK(x) do{ cudaError_t e_=(x); if(e_!=cudaSuccess)throw EngineError(DSPH_ERR_CUDA,std::string(#x)+": "+cudaGetErrorString(e_)); }while(0)
 
@@ -45,6 +54,7 @@ Engine::Engine(int device_,const dsph_config &c,unsigned capacity):device(device
   if(cudaGetDeviceCount(&ndev)!=cudaSuccess || ndev<=0)throw EngineError(DSPH_ERR_NOGPU,"No CUDA device is available: the B200 hot path has no CPU fallback.");
   if(device<0 || device>=ndev)throw EngineError(DSPH_ERR_ARG,"Invalid CUDA device index.");
   CUCHECK(cudaSetDevice(device));
+  { int v=0; if(cudaDeviceGetAttribute(&v,cudaDevAttrMultiProcessorCount,device)==cudaSuccess && v>0)numsm=v; }
   CUCHECK(cudaStreamCreateWithFlags(&stm,cudaStreamNonBlocking));
   for(int i=0;i<NEVENTS;i++)CUCHECK(cudaEventCreate(&ev[i]));
   CUCHECK(cudaHostAlloc((void**)&hpin,sizeof(HostPinned),cudaHostAllocMapped|cudaHostAllocPortable));
@@ -64,6 +74,7 @@ Engine::~Engine(){
   cudaSetDevice(device);
   MgCommDestroy();
   GaugesFree();
+  if(measuredev)cudaFree(measuredev);
   if(stmcopy){ cudaStreamSynchronize(stmcopy); cudaStreamDestroy(stmcopy); cudaEventDestroy(evsnap); cudaEventDestroy(evsnapfree); }
   if(snapdev)cudaFree(snapdev);
   FreeAll();
@@ -366,8 +377,10 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
   CUCHECK(cudaSetDevice(device));
   EnsureDcell();
   const int B=DIV_THREADS;
+  NvtxBegin("SU-Periodic");
   CUCHECK(cudaEventRecord(ev[0],stm));
   if(updateperiodic && k.periactive && !mgpu)RunPeriodic();
+  NvtxNext("NL-Limits");
   CUCHECK(cudaEventRecord(ev[1],stm));
   const unsigned npb1=npb, npf1=np-npb-npbper-npfper, npb2=npbper, npf2=npfper;
   const unsigned nptot=np;
@@ -377,18 +390,21 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
     unsigned init[12]={0xffffffffu,0xffffffffu,0xffffffffu,0,0,0, 0xffffffffu,0xffffffffu,0xffffffffu,0,0,0};
     memcpy(hpin->limitsinit,init,sizeof(init));
     SmallCopy(limits,hpind->limitsinit,sizeof(init),stm);
-    const int nsm=148*4;
+    const int nsm=numsm*4;
     auto lim=[&](unsigned n,unsigned pini,unsigned *dst){ if(n){ ker_div_limits<<<std::min<unsigned>((n+B-1)/B,nsm),B,0,stm>>>(n,pini,dcell[cur],code[cur],k.domcellcode,dst); launches++; } };
     if(!blimok){ lim(npb1,0,limits); lim(npb2,npb1+npf1,limits); }
     lim(npf1,npb1,limits+6); lim(npf2,npb1+npf1+npb2,limits+6);
     ker_div_prepare<<<1,1,0,stm>>>(limits,limits+6,blimok? 0: 1,k.domcells[0],k.domcells[1],k.domcells[2],unsigned(k.scelldiv),nptot,maxnctt,divparams); launches++;
     blimok=true;
   }
+  NvtxNext("NL-PreSort");
   CUCHECK(cudaEventRecord(ev[2],stm));
   // ---- sort keys
   if(nptot){ ker_div_presort<<<(nptot+B-1)/B,B,0,stm>>>(nptot,dcell[cur],code[cur],k.domcellcode,divparams,rs.keys[0]); launches++; }
+  NvtxNext("NL-RadixSort");
   CUCHECK(cudaEventRecord(ev[3],stm));
   const int sidx=RadixSortPairs(rs,nptot,keybits,1,stm,&launches);
+  NvtxNext("NL-CellBegin");
   CUCHECK(cudaEventRecord(ev[4],stm));
   // ---- begin-cell table
   CUCHECK(cudaMemsetAsync(begincell,0xff,size_t(maxnctt)*4,stm));
@@ -404,6 +420,7 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
     ker_div_maxpop<<<(maxnctt+255)/256,256,0,stm>>>(begincell,divparams); launches++;
     ker_div_counts<<<1,1,0,stm>>>(begincell,npb1+npb2,divparams); launches++;
   }
+  NvtxNext("NL-SortData");
   CUCHECK(cudaEventRecord(ev[5],stm));
   // ---- fused reorder of every array (+ cell-relative position and pressure)
   if(nptot){
@@ -420,10 +437,12 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
     launches++;
     cur=o;
   }
+  NvtxNext("NL-OutCheck");
   CUCHECK(cudaEventRecord(ev[6],stm));
   // ---- the only device->host transfer of the divide: cell domain + counts (one small async copy + sync)
   SmallCopy(&hpind->dp,divparams,sizeof(DivParams),stm);
   CUCHECK(cudaEventRecord(ev[7],stm));
+  NvtxEnd();
   CUCHECK(cudaStreamSynchronize(stm));
   CUCHECK(cudaGetLastError());
   dp=hpin->dp;
@@ -515,8 +534,10 @@ void Engine::ForcesLaunch(int interstep){
   (void)interstep;
   CUCHECK(cudaSetDevice(device));
   if(!divok)throw EngineError(DSPH_ERR_STATE,"dsph_forces_run needs a cell division first (dsph_celldiv_run).");
+  NvtxBegin("CF-PreForces");
   CUCHECK(cudaEventRecord(ev[8],stm));
   CUCHECK(cudaMemsetAsync(fmax,0,sizeof(ForceMax),stm));
+  NvtxNext("CF-Forces");
   CUCHECK(cudaEventRecord(ev[9],stm));
   const ForceParams t=MakeForceParams();
   const unsigned npf=np-npb;
@@ -534,8 +555,9 @@ void Engine::ForcesLaunch(int interstep){
     if(sps){ LaunchSpsTau(npf,npb,velrhop[cur],spsgradvel,spstau[cur],dc,stm); launches++; }
   }
   CUCHECK(cudaEventRecord(ev[13],stm));
-  if(npb){ LaunchForcesBound(cfg.tkernel,t,dc,stm); launches++; }
+  if(npb){ LaunchForcesBound(forcevariant,cfg.tkernel,numsm,t,dc,stm); launches++; }
   CUCHECK(cudaEventRecord(ev[10],stm));
+  NvtxEnd();
   forceslaunched=true;
 }
 
@@ -594,26 +616,23 @@ void Engine::ForcesDownload(unsigned first,unsigned count,float *ace,float *ar){
 void Engine::MeasurePoints(unsigned n,const double *hpoints,float *hpress,float *hvel,float *hkcorr){
   if(!divok)throw EngineError(DSPH_ERR_STATE,"dsph_measure_points needs a cell division first (dsph_celldiv_run).");
   if(!n)return;
-  double *dpts=nullptr; float *dout=nullptr;
-  CUCHECK(cudaMalloc((void**)&dpts,size_t(n)*24));
-  if(cudaMalloc((void**)&dout,size_t(n)*20)!=cudaSuccess){ cudaFree(dpts); throw EngineError(DSPH_ERR_CUDA,"cudaMalloc failed (probe results)."); }
-  try{
-    CUCHECK(cudaMemcpyAsync(dpts,hpoints,size_t(n)*24,cudaMemcpyHostToDevice,stm));
-    MeasureArgs m; m.npoints=n; m.points=dpts; m.pos=pos[cur]; m.press=dout; m.vel=dout+n; m.kcorr=dout+size_t(n)*4;
-    const ForceParams t=MakeForceParams();
-    const unsigned nb=(n+127)/128;
-    const bool wend=(cfg.tkernel==DSPH_KERNEL_WENDLAND);
-    if(cfg.nn_on){ if(wend)ker_measure_points<DSPH_KERNEL_WENDLAND,true><<<nb,128,0,stm>>>(m,t,dc,dph); else ker_measure_points<DSPH_KERNEL_CUBIC,true><<<nb,128,0,stm>>>(m,t,dc,dph); }
-    else{ if(wend)ker_measure_points<DSPH_KERNEL_WENDLAND,false><<<nb,128,0,stm>>>(m,t,dc,dph); else ker_measure_points<DSPH_KERNEL_CUBIC,false><<<nb,128,0,stm>>>(m,t,dc,dph); }
-    launches++;
-    if(hpress)CUCHECK(cudaMemcpyAsync(hpress,dout,size_t(n)*4,cudaMemcpyDeviceToHost,stm));
-    if(hvel)CUCHECK(cudaMemcpyAsync(hvel,dout+n,size_t(n)*12,cudaMemcpyDeviceToHost,stm));
-    if(hkcorr)CUCHECK(cudaMemcpyAsync(hkcorr,dout+size_t(n)*4,size_t(n)*4,cudaMemcpyDeviceToHost,stm));
-    CUCHECK(cudaStreamSynchronize(stm));
-    CUCHECK(cudaGetLastError());
-  }
-  catch(...){ cudaFree(dpts); cudaFree(dout); throw; }
-  cudaFree(dpts); cudaFree(dout);
+  // persistent scratch (grown on demand): no allocation per call
+  const size_t need=size_t(n)*24+size_t(n)*20;
+  if(measurecap<need){ if(measuredev)cudaFree(measuredev); measuredev=nullptr; measurecap=0; CUCHECK(cudaMalloc((void**)&measuredev,need+4096)); measurecap=need+4096; }
+  double *dpts=(double*)measuredev; float *dout=(float*)(measuredev+size_t(n)*24);
+  CUCHECK(cudaMemcpyAsync(dpts,hpoints,size_t(n)*24,cudaMemcpyHostToDevice,stm));
+  MeasureArgs m; m.npoints=n; m.points=dpts; m.pos=pos[cur]; m.press=dout; m.vel=dout+n; m.kcorr=dout+size_t(n)*4;
+  const ForceParams t=MakeForceParams();
+  const unsigned nb=(n+127)/128;
+  const bool wend=(cfg.tkernel==DSPH_KERNEL_WENDLAND);
+  if(cfg.nn_on){ if(wend)ker_measure_points<DSPH_KERNEL_WENDLAND,true><<<nb,128,0,stm>>>(m,t,dc,dph); else ker_measure_points<DSPH_KERNEL_CUBIC,true><<<nb,128,0,stm>>>(m,t,dc,dph); }
+  else{ if(wend)ker_measure_points<DSPH_KERNEL_WENDLAND,false><<<nb,128,0,stm>>>(m,t,dc,dph); else ker_measure_points<DSPH_KERNEL_CUBIC,false><<<nb,128,0,stm>>>(m,t,dc,dph); }
+  launches++;
+  if(hpress)CUCHECK(cudaMemcpyAsync(hpress,dout,size_t(n)*4,cudaMemcpyDeviceToHost,stm));
+  if(hvel)CUCHECK(cudaMemcpyAsync(hvel,dout+n,size_t(n)*12,cudaMemcpyDeviceToHost,stm));
+  if(hkcorr)CUCHECK(cudaMemcpyAsync(hkcorr,dout+size_t(n)*4,size_t(n)*4,cudaMemcpyDeviceToHost,stm));
+  CUCHECK(cudaStreamSynchronize(stm));
+  CUCHECK(cudaGetLastError());
 }
 
 void Engine::Pips(unsigned long long *fr,unsigned long long *fc,unsigned long long *br,unsigned long long *bc){
@@ -647,25 +666,30 @@ void Engine::ShiftCoefs(double dt,double &coefumagn,double &coeftfs,float &maxdi
 void Engine::StepSymPre(double dt){
   if(!forcesok)throw EngineError(DSPH_ERR_STATE,"dsph_step_sympre needs dsph_forces_run first.");
   if(cfg.tstep!=DSPH_STEP_SYMPLECTIC)throw EngineError(DSPH_ERR_STATE,"The context is not configured for Symplectic.");
+  NvtxBegin("SU-ComputeStep");
   CUCHECK(cudaEventRecord(ev[11],stm));
   StepArrays a=MakeStepArrays();
   ker_step_sympre<<<(np+STEP_THREADS-1)/STEP_THREADS,STEP_THREADS,0,stm>>>(a,dt,dc); launches++;
   CUCHECK(cudaEventRecord(ev[12],stm));
+  NvtxEnd();
   haspre=true; forcesok=false; divok=false; steppending=true;
 }
 void Engine::StepSymCor(double dt){
   if(!forcesok)throw EngineError(DSPH_ERR_STATE,"dsph_step_symcor needs dsph_forces_run first.");
   if(!haspre)throw EngineError(DSPH_ERR_STATE,"dsph_step_symcor needs dsph_step_sympre first.");
+  NvtxBegin("SU-ComputeStep");
   CUCHECK(cudaEventRecord(ev[11],stm));
   StepArrays a=MakeStepArrays();
   double cu,ct; float md; ShiftCoefs(dt,cu,ct,md);
   ker_step_symcor<<<(np+STEP_THREADS-1)/STEP_THREADS,STEP_THREADS,0,stm>>>(a,dt,cu,ct,md,dc); launches++;
   CUCHECK(cudaEventRecord(ev[12],stm));
+  NvtxEnd();
   haspre=false; forcesok=false; divok=false; steppending=true;
 }
 void Engine::StepVerlet(double dt){
   if(!forcesok)throw EngineError(DSPH_ERR_STATE,"dsph_step_verlet needs dsph_forces_run first.");
   if(cfg.tstep!=DSPH_STEP_VERLET)throw EngineError(DSPH_ERR_STATE,"The context is not configured for Verlet.");
+  NvtxBegin("SU-ComputeStep");
   CUCHECK(cudaEventRecord(ev[11],stm));
   verletstep++;
   const int euler=(verletstep<cfg.verletsteps? 0: 1);
@@ -675,6 +699,7 @@ void Engine::StepVerlet(double dt){
   std::swap(velrhop[cur],velrhopm1[cur]);
   if(euler)verletstep=0;
   CUCHECK(cudaEventRecord(ev[12],stm));
+  NvtxEnd();
   forcesok=false; divok=false; steppending=true;
 }
 void Engine::FlushStepTimer(){

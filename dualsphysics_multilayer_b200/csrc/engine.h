@@ -133,6 +133,8 @@ class Engine {
   void MgUnpack(const unsigned counts[8],const void *recvleft,const void *recvright);
   void ForcesDownload(unsigned first,unsigned count,float *ace,float *ar);
   void MeasurePoints(unsigned n,const double *points,float *press,float *vel,float *kcorr);
+  char *measuredev=nullptr; size_t measurecap=0;
+  int numsm=148;                // multiprocessors of the device (grid sizing of the grid-stride kernels)
   // in-solver gauges (gauges.cu)
   std::vector<dsph_gauge> gauges; std::vector<double> gaugenext; std::vector<dsph_gaugeres> gaugeres;
   double gaugetime=0; bool celltableok=false;

@@ -12,7 +12,7 @@ namespace dsph {
 int LaunchForcesFluid(int variant,bool ringbase_ok,int tkernel,int tvisco,int tddt,bool shift,const ForceParams &t,const DevCtes &c,cudaStream_t stm);
 int EffectiveFluidVariant(int variant,bool ringbase_ok,const ForceParams &t,const DevCtes &c);
 // Boundary particles [0,npb): density rate + viscdt (KerInteractionForcesBound S/JSphGpu_ker.cu:420-506)
-void LaunchForcesBound(int tkernel,const ForceParams &t,const DevCtes &c,cudaStream_t stm);
+void LaunchForcesBound(int variant,int tkernel,int numsm,const ForceParams &t,const DevCtes &c,cudaStream_t stm);   // variant 1: IEEE thread-per-particle loop, else warp per particle
 // SPS stress tensor from the velocity gradient (ComputeSpsTau S/JSphGpu_ker.cu:1516-1558)
 void LaunchSpsTau(unsigned npf,unsigned npb,const float4 *velrhop,const float *gradvel,float *tau,const DevCtes &c,cudaStream_t stm);
 // pair counters (JDsPips S/JDsPips_ker.cu:66) accumulated into t.fmax->pips_*

@@ -1,5 +1,6 @@
 // forces_fluid.cu -- translation unit of the single-phase Interaction_Forces kernels and their dispatch
 // (cusph::Interaction_Forces dispatcher, S/JSphGpu_ker.cu:788-885: template selection by kernel, viscosity, DDT, shifting).
+#include <algorithm>
 #include "forces_api.h"
 #include "forces.cuh"
 #include "forces_fast.cuh"
@@ -69,11 +70,19 @@ int LaunchForcesFluid(int variant,bool ringbase_ok,int tkernel,int tvisco,int td
   return ok? v: 0;
 }
 
-void LaunchForcesBound(int tkernel,const ForceParams &t,const DevCtes &c,cudaStream_t stm){
+void LaunchForcesBound(int variant,int tkernel,int numsm,const ForceParams &t,const DevCtes &c,cudaStream_t stm){
   if(!t.npb)return;
-  const unsigned nb=(t.npb+FORCES_THREADS-1)/FORCES_THREADS;
-  if(tkernel==DSPH_KERNEL_WENDLAND)ker_forces_bound_v1<DSPH_KERNEL_WENDLAND><<<nb,FORCES_THREADS,0,stm>>>(t,c);
-  else ker_forces_bound_v1<DSPH_KERNEL_CUBIC><<<nb,FORCES_THREADS,0,stm>>>(t,c);
+  if(variant==1){                                           // IEEE cross-check: one thread per particle
+    const unsigned nb=(t.npb+FORCES_THREADS-1)/FORCES_THREADS;
+    if(tkernel==DSPH_KERNEL_WENDLAND)ker_forces_bound_v1<DSPH_KERNEL_WENDLAND><<<nb,FORCES_THREADS,0,stm>>>(t,c);
+    else ker_forces_bound_v1<DSPH_KERNEL_CUBIC><<<nb,FORCES_THREADS,0,stm>>>(t,c);
+    return;
+  }
+  // production: one warp per particle, grid-stride; at most 16 CTAs per SM
+  const unsigned need=(t.npb+(FORCES_THREADS/32)-1)/(FORCES_THREADS/32);
+  const unsigned nb=std::min(need,unsigned(numsm)*16u);
+  if(tkernel==DSPH_KERNEL_WENDLAND)ker_forces_bound_v2<DSPH_KERNEL_WENDLAND><<<nb,FORCES_THREADS,0,stm>>>(t,c);
+  else ker_forces_bound_v2<DSPH_KERNEL_CUBIC><<<nb,FORCES_THREADS,0,stm>>>(t,c);
 }
 void LaunchSpsTau(unsigned npf,unsigned npb,const float4 *velrhop,const float *gradvel,float *tau,const DevCtes &c,cudaStream_t stm){
   if(npf)ker_sps_tau<<<(npf+255)/256,256,0,stm>>>(npf,npb,velrhop,gradvel,tau,c);
