@@ -45,7 +45,7 @@ class Config(C.Structure):
         ("shiftmode", C.c_int32), ("cellmode", C.c_int32), ("verletsteps", C.c_int32), ("simulate2d", C.c_int32),
         ("perix", C.c_int32), ("periy", C.c_int32), ("periz", C.c_int32),
         ("dtallparticles", C.c_int32), ("dtfixed_on", C.c_int32), ("stable", C.c_int32),
-        ("nn_on", C.c_int32), ("nn_velgrad", C.c_int32), ("nn_nphases", C.c_int32), ("reserved_i", C.c_int32),
+        ("nn_on", C.c_int32), ("nn_velgrad", C.c_int32), ("nn_nphases", C.c_int32), ("tboundary", C.c_int32),
         ("kernelh", C.c_float), ("cteb", C.c_float), ("gamma", C.c_float), ("rhopzero", C.c_float),
         ("massfluid", C.c_float), ("massbound", C.c_float),
         ("gravity", C.c_float * 3),

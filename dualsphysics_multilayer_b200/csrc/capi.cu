@@ -6,6 +6,7 @@
 #include "host/bi4.h"
 #include "host/partset.h"
 #include <vector>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <new>
@@ -141,6 +142,20 @@ int dsph_mgpu_comm_attach(dsph_ctx *ctx,void *ncclcomm,int rank,int nranks){ NEE
 int dsph_mgpu_config_cuts(dsph_ctx *ctx,int rank,int nranks,const uint32_t *cuts){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgConfigCuts(rank,nranks,cuts); }); }
 uint32_t dsph_mgpu_halo_cells(const dsph_ctx *ctx){ return (ctx&&ctx->eng)? ctx->eng->MgHalo(): 0u; }
 int dsph_mgpu_exchange(dsph_ctx *ctx){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgExchange(); }); }
+int dsph_excluded_keep(dsph_ctx *ctx,int keep){ NEEDCTX(ctx); ctx->eng->keepout=(keep!=0); return DSPH_OK; }
+int dsph_excluded_take(dsph_ctx *ctx,uint32_t max,uint32_t *n,uint32_t *idp,dsph_typecode *code,double *pos,float *velrhop){
+  NEEDCTX(ctx);
+  return Guard([&]{
+    Engine *e=ctx->eng;
+    const size_t have=e->outidp.size(), m=std::min<size_t>(have,max);
+    if(n)*n=uint32_t(have);
+    if(idp && m)memcpy(idp,e->outidp.data(),m*4);
+    if(code && m)memcpy(code,e->outcode.data(),m*sizeof(typecode));
+    if(pos && m)memcpy(pos,e->outpos.data(),m*24);
+    if(velrhop && m)memcpy(velrhop,e->outvelrhop.data(),m*16);
+    e->outidp.clear(); e->outcode.clear(); e->outpos.clear(); e->outvelrhop.clear();
+  });
+}
 int dsph_gauges_config(dsph_ctx *ctx,uint32_t n,const dsph_gauge *g){ NEEDCTX(ctx); if(n && !g){ g_lasterror="Null argument."; return DSPH_ERR_ARG; } return Guard([&]{ ctx->eng->GaugesConfig(n,g); }); }
 int dsph_gauges_run(dsph_ctx *ctx,double timestep,int force_all,dsph_gaugeres *res){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->GaugesRun(timestep,force_all!=0,res); }); }
 int dsph_gauges_results(dsph_ctx *ctx,dsph_gaugeres *res){ NEEDCTX(ctx); if(!res){ g_lasterror="Null argument."; return DSPH_ERR_ARG; } return Guard([&]{ if(!ctx->eng->gaugeres.empty())memcpy(res,ctx->eng->gaugeres.data(),ctx->eng->gaugeres.size()*sizeof(dsph_gaugeres)); }); }

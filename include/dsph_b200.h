@@ -89,7 +89,8 @@ typedef struct dsph_config {
   int32_t perix, periy, periz;            /* periodic axes (JSph.cpp:716-730)                    */
   int32_t dtallparticles, dtfixed_on, stable;
   int32_t nn_on;                          /* 1: multiphase non-Newtonian formulation (src_mphase) */
-  int32_t nn_velgrad, nn_nphases, reserved_i;
+  int32_t nn_velgrad, nn_nphases;
+  int32_t tboundary;                      /* low byte: TpBoundary 1 DBC (0 = DBC too), 2 mDBC (S/JSph.cpp:626-641); bit 8: MDBCCorrector */
   /* constants (float where the reference stores float, JSph.cpp:567-586) */
   float kernelh, cteb, gamma, rhopzero, massfluid, massbound;
   float gravity[3];
@@ -293,6 +294,28 @@ void* dsph_cuda_stream(dsph_ctx *ctx);
 int dsph_forces_finish(dsph_ctx *ctx,dsph_forceres *res);
 /* domain constants needed to place the cuts: cell size, origin and number of cell columns (JSph::ConfigCellDivision) */
 int dsph_domain_info(const dsph_config *cfg,double *scell,double domposmin[3],uint32_t domcells[3]);
+
+/* ---- mDBC boundary correction (JSphCpu::InteractionMdbcCorrectionT2 S/JSphCpu.cpp:1020-1190, GPU twin
+ *      KerInteractionMdbcCorrection_Fast/_Dbl S/JSphGpu_ker.cu:912-1282): with cfg.tboundary = 2 every force evaluation (the corrector
+ *      one only with MDBCCorrector) first extrapolates the fluid density to the ghost node of every boundary particle (position + its
+ *      normal vector, first-order corrected by the 4x4 / 3x3 moment matrix) and mirrors it back (slip mode velocity = 0, the only one
+ *      the reference accepts, S/JSph.cpp:788).  The normal vectors are per-particle data like the velocities: upload them (xyz per
+ *      particle of the last dsph_particles_upload, boundary particles first; fluid entries ignored) in the units of
+ *      JSph::ConfigBoundNormals (S/JSph.cpp:1300-1340: particle -> ghost node = 2 x the GenCase vector particle -> boundary limit). */
+#define DSPH_BOUNDARY_DBC 1
+#define DSPH_BOUNDARY_MDBC 2
+#define DSPH_BOUNDARY_MDBCCORRECTOR 0x100
+int dsph_particles_set_boundnormals(dsph_ctx *ctx,const float *normal_xyz,uint32_t count);
+int dsph_set_mdbc_threshold(dsph_ctx *ctx,float threshold);      /* command-line option -mdbc_threshold of the reference (default 0) */
+/* <dir>/<casename>_Normals.nbi4 (JPartNormalData, S/JPartNormalData.cpp:222-262): vectors particle -> boundary limit of the
+ * boundary particles in id order; *n = number stored in the file (0 when there is none), at most max vectors are written */
+int dsph_case_normals(const char *dir,const char *casename,double *normal_xyz,uint32_t max,uint32_t *n);
+
+/* ---- excluded particles (JSph::AddParticlesOut <- JSphGpuSingle::RunCellDivide, S/JSphGpuSingle.cpp:405-412): with keep = 1 every
+ *      divide copies the fluid particles it excludes (out of the domain, RhopOut, speed limit) to the host; dsph_excluded_take hands
+ *      them over (at most max; *n = how many were pending) and empties the store.  Arrays may be NULL to discard. ------------------- */
+int dsph_excluded_keep(dsph_ctx *ctx,int keep);
+int dsph_excluded_take(dsph_ctx *ctx,uint32_t max,uint32_t *n,uint32_t *idp,dsph_typecode *code,double *pos_xyz,float *velrhop_xyzw);
 
 /* ---- in-solver gauges: what JGaugeVelocity / JGaugeSwl / JGaugeMaxZ / JGaugeForce compute (CPU:
  *      S/JDsGaugeItem.cpp:325-367,575-600,736-776,986-1041; GPU: S/JDsGauge_ker.cu:50,168,250,311), evaluated on the device for all the
