@@ -121,6 +121,18 @@ def load_case(dirname: str, casename: str) -> CaseData:
     return _case_from_c(c)
 
 
+def case_normals(dirname: str, casename: str):
+    """mDBC normal vectors (particle -> boundary limit) of <casename>_Normals.nbi4, one row per boundary particle in id order
+    (empty array when the case has no such file)."""
+    L = lib()
+    n = C.c_uint32()
+    L.check(L.fn("case_normals")(dirname.encode(), casename.encode(), None, 0, C.byref(n)))
+    out = np.zeros((n.value, 3), np.float64)
+    if n.value:
+        L.check(L.fn("case_normals")(dirname.encode(), casename.encode(), out.ctypes.data_as(C.POINTER(C.c_double)), n.value, C.byref(n)))
+    return out
+
+
 def case_gauges(dirname: str, casename: str):
     """Gauge definitions of <special><gauges> in <dirname>/<casename>.xml (list of capi.Gauge)."""
     L = lib()

@@ -183,6 +183,9 @@ class SphLib:
             f("mgpu_sent_records", C.c_int, vp, C.POINTER(C.c_uint64))
             f("celldiv_last_info", C.c_int, vp, C.POINTER(DivInfo))
         if prefix == "dsph_":
+            f("particles_set_boundnormals", C.c_int, vp, C.POINTER(C.c_float), C.c_uint32)
+            f("set_mdbc_threshold", C.c_int, vp, C.c_float)
+            f("case_normals", C.c_int, C.c_char_p, C.c_char_p, C.POINTER(C.c_double), C.c_uint32, C.POINTER(C.c_uint32))
             f("gauges_config", C.c_int, vp, C.c_uint32, C.POINTER(Gauge))
             f("gauges_run", C.c_int, vp, C.c_double, C.c_int, C.POINTER(GaugeRes))
             f("gauges_results", C.c_int, vp, C.POINTER(GaugeRes))
@@ -243,6 +246,11 @@ class SphContext:
     def set_velrhopm1(self, v):
         v = np.ascontiguousarray(v, np.float32).reshape(-1, 4)
         self.lib.check(self.lib.fn("particles_set_velrhopm1")(self.h, _ptr(v, C.c_float)))
+
+    def set_boundnormals(self, n):
+        """mDBC: vectors particle -> ghost node (xyz) of the first len(n) particles of the uploaded order (boundary particles first)."""
+        n = np.ascontiguousarray(n, np.float32).reshape(-1, 3)
+        self.lib.check(self.lib.fn("particles_set_boundnormals")(self.h, _ptr(n, C.c_float), n.shape[0]))
 
     def set_spstau(self, t):
         t = np.ascontiguousarray(t, np.float32).reshape(-1, 6)

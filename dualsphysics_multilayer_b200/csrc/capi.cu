@@ -142,6 +142,17 @@ int dsph_mgpu_comm_attach(dsph_ctx *ctx,void *ncclcomm,int rank,int nranks){ NEE
 int dsph_mgpu_config_cuts(dsph_ctx *ctx,int rank,int nranks,const uint32_t *cuts){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgConfigCuts(rank,nranks,cuts); }); }
 uint32_t dsph_mgpu_halo_cells(const dsph_ctx *ctx){ return (ctx&&ctx->eng)? ctx->eng->MgHalo(): 0u; }
 int dsph_mgpu_exchange(dsph_ctx *ctx){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgExchange(); }); }
+int dsph_particles_set_boundnormals(dsph_ctx *ctx,const float *n,uint32_t count){ NEEDCTX(ctx); if(!n && count){ g_lasterror="Null argument."; return DSPH_ERR_ARG; } return Guard([&]{ ctx->eng->SetBoundNormals(n,count); }); }
+int dsph_set_mdbc_threshold(dsph_ctx *ctx,float v){ NEEDCTX(ctx); ctx->eng->mdbcthreshold=v; return DSPH_OK; }
+int dsph_case_normals(const char *dir,const char *casename,double *out,uint32_t max,uint32_t *n){
+  if(!dir||!casename||!n){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  const int r=Guard([&]{
+    std::vector<double> v; LoadCaseNormals(v,dir,casename);
+    *n=uint32_t(v.size()/3);
+    if(out)memcpy(out,v.data(),std::min<size_t>(v.size(),size_t(max)*3)*8);
+  });
+  return r==DSPH_OK? r: DSPH_ERR_IO;
+}
 int dsph_excluded_keep(dsph_ctx *ctx,int keep){ NEEDCTX(ctx); ctx->eng->keepout=(keep!=0); return DSPH_OK; }
 int dsph_excluded_take(dsph_ctx *ctx,uint32_t max,uint32_t *n,uint32_t *idp,dsph_typecode *code,double *pos,float *velrhop){
   NEEDCTX(ctx);

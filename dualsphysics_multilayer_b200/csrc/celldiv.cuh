@@ -241,6 +241,7 @@ struct ReorderArrays {
   const double *pospre_in; double *pospre_out;         // Symplectic (mid-step divide)
   const float4 *velrhoppre_in; float4 *velrhoppre_out;
   const float *spstau_in; float *spstau_out;           // 6 floats
+  const float4 *boundnormal_in; float4 *boundnormal_out;   // mDBC: normal vectors of the boundary particles (JSphCpuSingle.cpp:464-467)
   float4 *posp;                                        // out: cell-relative xyz + pressure
   uint4 *posh;                                         // out: packed-half culling copy (forces_v10.cuh), one uint4 per 2 particles
 };
@@ -294,6 +295,7 @@ template<bool NN> __global__ void __launch_bounds__(DIV_THREADS) ker_div_reorder
       #pragma unroll
       for(int k=0;k<6;k++)a.spstau_out[6*size_t(p)+k]=a.spstau_in[6*size_t(s)+k];
     }
+    if(a.boundnormal_in && (rcode&DSPH_CODE_MASKTYPE)!=DSPH_CODE_TYPE_FLUID)a.boundnormal_out[p]=a.boundnormal_in[s];
     // cell-relative position (float) + pressure; excluded particles (dcell=0xffffffff) get zeros
     if(rcell!=0xffffffffu){
       const unsigned cx=DcCellx(c.domcellcode,rcell), cy=DcCelly(c.domcellcode,rcell), cz=DcCellz(c.domcellcode,rcell);

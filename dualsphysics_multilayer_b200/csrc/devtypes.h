@@ -38,6 +38,7 @@ struct DevCtes {
   // shifting (S/JSphShifting.cpp:387-417)
   int shiftmode; float shifttfs;
   int nn_on;              // multiphase non-Newtonian fork: per-phase EOS, v5.0 shifting clamp
+  int mdbc;               // TBoundary = mDBC: boundary neighbours take part in DDT1 instead of switching it off (S/JSphCpu.cpp:730)
   int reftail;            // test switch (dsph_set_refbinary_tail): reproduce the pressure rounding of the reference BINARY's loop epilogue
 };
 

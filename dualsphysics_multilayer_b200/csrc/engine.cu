@@ -4,6 +4,7 @@
 // ComputeStep_Sym / ComputeStep_Ver (S/JSphGpuSingle.cpp:331-417,435-486,548-596).
 #include "engine.h"
 #include <nvtx3/nvToolsExt.h>
+#include "mdbc.cuh"
 #include "radixsort.cuh"
 #include "celldiv.cuh"
 #include "forces_api.h"
@@ -136,6 +137,10 @@ void Engine::Configure(const dsph_config &c){
   dc.simulate2d=cfg.simulate2d; dc.dtallparticles=cfg.dtallparticles;
   dc.shiftmode=cfg.shiftmode; dc.shifttfs=cfg.shifttfs;
   dc.reftail=(reftail? 1: 0);
+  mdbc=((cfg.tboundary&0xff)==DSPH_BOUNDARY_MDBC); mdbccorrector=(mdbc && (cfg.tboundary&DSPH_BOUNDARY_MDBCCORRECTOR)!=0);
+  dc.mdbc=(mdbc? 1: 0);
+  if(mdbc && cfg.nn_on)throw EngineError(DSPH_ERR_ARG,"mDBC belongs to the v5.2 formulation: it cannot be combined with the multiphase fork.");
+  if(mdbc && (cfg.perix||cfg.periy||cfg.periz))throw EngineError(DSPH_ERR_ARG,"mDBC with periodic boundaries is not implemented (the duplicates would need their normals).");
   symplecticdtpre=k.dtini; verletstep=0;
 }
 
@@ -144,7 +149,7 @@ void Engine::Configure(const dsph_config &c){
 // at creation: those fields are compared and the call is rejected with DSPH_ERR_ARG, the context stays untouched.
 void Engine::Reconfigure(const dsph_config &c){
   SphConst k2; DeriveConstants(c,k2);
-  bool same=(c.tstep==cfg.tstep && c.shiftmode==cfg.shiftmode && c.tvisco==cfg.tvisco && c.tkernel==cfg.tkernel && c.nn_on==cfg.nn_on &&
+  bool same=(c.tboundary==cfg.tboundary && c.tstep==cfg.tstep && c.shiftmode==cfg.shiftmode && c.tvisco==cfg.tvisco && c.tkernel==cfg.tkernel && c.nn_on==cfg.nn_on &&
     c.nn_velgrad==cfg.nn_velgrad && c.nn_nphases==cfg.nn_nphases && c.perix==cfg.perix && c.periy==cfg.periy && c.periz==cfg.periz &&
     c.simulate2d==cfg.simulate2d && c.cellmode==cfg.cellmode && c.casenfixed==cfg.casenfixed && c.casenmoving==cfg.casenmoving &&
     c.casenfloat==cfg.casenfloat && k2.scell==k.scell && k2.scelldiv==k.scelldiv && k2.domcellcode==k.domcellcode && k2.periactive==k.periactive);
@@ -159,7 +164,7 @@ void Engine::Reconfigure(const dsph_config &c){
 void Engine::FreeAll(){
   for(int b=0;b<2;b++){
     DevFree(idp[b]); DevFree(code[b]); DevFree(dcell[b]); DevFree(pos[b]); DevFree(velrhop[b]);
-    DevFree(velrhopm1[b]); DevFree(pospre[b]); DevFree(velrhoppre[b]); DevFree(spstau[b]);
+    DevFree(velrhopm1[b]); DevFree(pospre[b]); DevFree(velrhoppre[b]); DevFree(spstau[b]); DevFree(boundnormal[b]);
     DevFree(rs.keys[b]); DevFree(rs.vals[b]);
   }
   DevFree(posp); DevFree(posh); DevFree(acear); DevFree(shiftposfs); DevFree(spsgradvel); DevFree(viscoeta); DevFree(nntau);
@@ -179,6 +184,7 @@ void Engine::Allocate(unsigned capacity){
     if(verlet)DevAlloc(velrhopm1[b],cap);
     if(sympl){ DevAlloc(pospre[b],size_t(cap)*3); DevAlloc(velrhoppre[b],cap); }
     if(sps)DevAlloc(spstau[b],size_t(cap)*6);
+    if(mdbc){ DevAlloc(boundnormal[b],cap); CUCHECK(cudaMemsetAsync(boundnormal[b],0,size_t(cap)*sizeof(float4),stm)); }
     DevAlloc(rs.keys[b],cap); DevAlloc(rs.vals[b],cap);
   }
   // padded: the chunked candidate loops of the ring kernels read past a lane's own cell range (forces_ring.cuh: up to the
@@ -258,6 +264,28 @@ void Engine::SetSpsTau(const float *h){
   if(!sps)throw EngineError(DSPH_ERR_STATE,"SpsTau is only used by Laminar+SPS.");
   CUCHECK(cudaMemcpyAsync(spstau[cur],h,size_t(np)*24,cudaMemcpyHostToDevice,stm));
   CUCHECK(cudaStreamSynchronize(stm));
+}
+
+// normal vectors particle -> ghost node of the first `count` particles of the uploaded order (boundary particles come first)
+void Engine::SetBoundNormals(const float *h,unsigned count){
+  if(!mdbc)throw EngineError(DSPH_ERR_STATE,"Normal vectors are only used with cfg.tboundary = DSPH_BOUNDARY_MDBC.");
+  if(count>np)throw EngineError(DSPH_ERR_ARG,"More normal vectors than particles.");
+  std::vector<float4> tmp(count);
+  for(unsigned i=0;i<count;i++)tmp[i]=make_float4(h[3*size_t(i)],h[3*size_t(i)+1],h[3*size_t(i)+2],0.f);
+  CUCHECK(cudaMemsetAsync(boundnormal[cur],0,size_t(cap)*sizeof(float4),stm));
+  if(count)CUCHECK(cudaMemcpyAsync(boundnormal[cur],tmp.data(),size_t(count)*sizeof(float4),cudaMemcpyHostToDevice,stm));
+  CUCHECK(cudaStreamSynchronize(stm));
+}
+void Engine::MdbcCorrection(){
+  if(!npbok)return;
+  MdbcArgs m; m.npbok=npbok; m.pos=pos[cur]; m.boundnormal=boundnormal[cur]; m.velrhop=velrhop[cur]; m.posp=posp;
+  m.determlimit=1e-3f; m.threshold=mdbcthreshold;                      // S/JSphCpu.cpp:1197
+  const ForceParams t=MakeForceParams();
+  const unsigned need=(npbok+(FORCES_THREADS/32)-1)/(FORCES_THREADS/32), nb=std::min(need,unsigned(numsm)*16u);
+  const bool wend=(cfg.tkernel==DSPH_KERNEL_WENDLAND);
+  if(cfg.simulate2d){ if(wend)ker_mdbc_correction<DSPH_KERNEL_WENDLAND,true><<<nb,FORCES_THREADS,0,stm>>>(m,t,dc); else ker_mdbc_correction<DSPH_KERNEL_CUBIC,true><<<nb,FORCES_THREADS,0,stm>>>(m,t,dc); }
+  else{ if(wend)ker_mdbc_correction<DSPH_KERNEL_WENDLAND,false><<<nb,FORCES_THREADS,0,stm>>>(m,t,dc); else ker_mdbc_correction<DSPH_KERNEL_CUBIC,false><<<nb,FORCES_THREADS,0,stm>>>(m,t,dc); }
+  launches++;
 }
 
 void Engine::Download(unsigned first,unsigned count,unsigned *hidp,typecode *hcode,unsigned *hdcell,double *hpos,float *hvelrhop){
@@ -431,6 +459,7 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
     if(cfg.tstep==DSPH_STEP_VERLET){ a.velrhopm1_in=velrhopm1[cur]; a.velrhopm1_out=velrhopm1[o]; }
     if(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre){ a.pospre_in=pospre[cur]; a.pospre_out=pospre[o]; a.velrhoppre_in=velrhoppre[cur]; a.velrhoppre_out=velrhoppre[o]; }
     if(sps){ a.spstau_in=spstau[cur]; a.spstau_out=spstau[o]; }
+    if(mdbc){ a.boundnormal_in=boundnormal[cur]; a.boundnormal_out=boundnormal[o]; }
     a.posp=posp; a.posh=posh;
     if(cfg.nn_on)ker_div_reorder<true><<<(nptot+B-1)/B,B,0,stm>>>(nptot,rs.vals[sidx],a,dc,dph,divparams);
     else ker_div_reorder<false><<<(nptot+B-1)/B,B,0,stm>>>(nptot,rs.vals[sidx],a,dc,dph,divparams);
@@ -537,6 +566,8 @@ void Engine::ForcesLaunch(int interstep){
   NvtxBegin("CF-PreForces");
   CUCHECK(cudaEventRecord(ev[8],stm));
   CUCHECK(cudaMemsetAsync(fmax,0,sizeof(ForceMax),stm));
+  // boundary correction for mDBC (S/JSphCpuSingle.cpp:525: before every force evaluation, the corrector one only with MDBCCorrector)
+  if(mdbc && (mdbccorrector || interstep!=DSPH_INTERSTEP_SYMCORRECTOR))MdbcCorrection();
   NvtxNext("CF-Forces");
   CUCHECK(cudaEventRecord(ev[9],stm));
   const ForceParams t=MakeForceParams();

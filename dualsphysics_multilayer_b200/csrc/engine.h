@@ -40,6 +40,10 @@ class Engine {
   unsigned *idp[2]={}, *dcell[2]={}; typecode *code[2]={};
   double *pos[2]={}; float4 *velrhop[2]={}, *velrhopm1[2]={}, *velrhoppre[2]={}; double *pospre[2]={};
   float *spstau[2]={};
+  // mDBC (mdbc.cuh): normal vectors particle -> ghost node of the boundary particles, sorted with the particles
+  bool mdbc=false, mdbccorrector=false; float mdbcthreshold=0; float4 *boundnormal[2]={};
+  void SetBoundNormals(const float *h,unsigned count);
+  void MdbcCorrection();
   static const unsigned POSP_PAD=512;
   float4 *posp=nullptr; uint4 *posh=nullptr; float4 *acear=nullptr, *shiftposfs=nullptr; float *spsgradvel=nullptr;
   // multiphase non-Newtonian fork (src_mphase): phases + scratch of the SPH velocity-gradient approach

@@ -88,7 +88,7 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT,bool BOUNDP2> __device__ __forc
       const float visc_densi=c.ddtkh*cbar*(rhop1over2-1.f)/(rr2+c.eta2);
       const float dot3=(drx*frx+dry*fry+drz*frz);
       const float delta=visc_densi*dot3*massp2;
-      a.delta=(BOUNDP2? FLT_MAX: a.delta+delta);
+      a.delta=(BOUNDP2 && !c.mdbc? FLT_MAX: a.delta+delta);
     }
   }
   if(TDDT==DSPH_DDT_DDT2 || (TDDT==DSPH_DDT_DDT2FULL && !BOUNDP2)){

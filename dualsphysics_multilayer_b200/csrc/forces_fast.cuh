@@ -79,8 +79,8 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT,bool NOBRANCH=false> __device__
   const float ovrr=FastRcp(rr2+c.eta2);
   const float cbar=c.cs0;
   if(TDDT==DSPH_DDT_DDT){
-    if(boundflag)anybound=1u;
-    if(!boundp2){
+    if(boundflag && !c.mdbc)anybound=1u;
+    if(!boundp2 || c.mdbc){
       // rho1/rho2-1 cancels to ~1e-4: the oracle's value is dominated by the rounding of the IEEE quotient, so this one
       // division is kept correctly rounded (an approximate reciprocal here changed Ar by 6e-5 in the periodic box).
       // (cubic + laminar/SPS: the reference binary multiplies by the rounded reciprocal instead, see forces.cuh)

@@ -1,5 +1,6 @@
 // casefile.cpp -- see casefile.h.
 #include "casefile.h"
+#include <memory>
 #include "bi4.h"
 #include "xmlmini.h"
 #include "sphconst.h"
@@ -126,6 +127,8 @@ void SaveCase(const CaseData &cd,const std::string &dir,const std::string &casen
     P("RheologyTreatment","2"); P("VelocityGradientType",I(c.nn_velgrad)); P("RelaxationDt",D(c.nn_relaxationdt));
   }
   P("ViscoTreatment",I(c.tvisco)); P("Visco",D(c.visco)); P("ViscoBoundFactor",D(c.viscoboundfactor));
+  if((c.tboundary&0xff)==DSPH_BOUNDARY_MDBC){ P("Boundary","2"); P("SlipMode","1"); P("MDBCCorrector",(c.tboundary&DSPH_BOUNDARY_MDBCCORRECTOR)? "1": "0"); }
+  else P("Boundary","1");
   P("DensityDT",I(c.tdensity)); P("DensityDTvalue",D(c.ddtvalue));
   P("Shifting",I(c.shiftmode)); P("ShiftCoef",D(c.shiftcoef)); P("ShiftTFS",D(c.shifttfs));
   P("RigidAlgorithm","1"); P("FtPause","0.0");
@@ -155,6 +158,17 @@ void SaveCase(const CaseData &cd,const std::string &dir,const std::string &casen
   fprintf(f,"      <massbound value=\"%s\" />\n      <massfluid value=\"%s\" />\n",D(c.massbound).c_str(),D(c.massfluid).c_str());
   fprintf(f,"    </constants>\n  </execution>\n</case>\n");
   fclose(f);
+  if((c.tboundary&0xff)==DSPH_BOUNDARY_MDBC){
+    // <name>_Normals.nbi4: the "final normals" file of GenCase >= 5.0.268 (JPartNormalData::SaveFile, S/JPartNormalData.cpp:179-207)
+    const unsigned nbound=c.casenfixed+c.casenmoving+c.casenfloat;
+    if(cd.normals.size()!=size_t(nbound)*3)throw std::runtime_error("mDBC needs one normal vector per boundary particle (CaseData::normals).");
+    Bi4Item b; b.name="JPartNormalData";
+    b.SetUint("FmtVersion",220911u); b.SetText("AppName","dsph_b200 mkcase"); b.SetText("Date","-"); b.SetText("CaseName",casename);
+    b.SetBool("Data2d",c.simulate2d!=0); b.SetDouble("Data2dPosY",c.simulate2dposy); b.SetDouble("Dp",c.dp); b.SetDouble("H",c.kernelh);
+    b.SetDouble("Dist",c.dp*0.5); b.SetText("PartNormalsName","tank"); b.SetUint("Nbound",nbound); b.SetUint("CountNormals",0u);
+    b.AddArray("PartNormals",BI4_DOUBLE3,nbound,cd.normals.data());
+    Bi4Save(dir+"/"+casename+"_Normals.nbi4",b,true);
+  }
 
   PartHead h; PartData p;
   h.casename=casename; h.data2d=c.simulate2d!=0; h.data2dposy=c.simulate2dposy;
@@ -192,7 +206,15 @@ void LoadCase(CaseData &cd,const std::string &dir,const std::string &casename){
   auto PI=[&](const char *k,int def){ return int(PD(k,true,def)); };
   c.tkernel=PI("Kernel",2); c.tstep=PI("StepAlgorithm",1); c.verletsteps=PI("VerletSteps",40);
   c.tvisco=PI("ViscoTreatment",1); c.visco=float(PD("Visco",false,0)); c.viscoboundfactor=float(PD("ViscoBoundFactor",true,1));
-  if(PI("Boundary",1)!=1)throw std::runtime_error("Only DBC boundaries (Boundary=1) are supported by the hot path.");
+  { // boundary method (S/JSph.cpp:626-641)
+    const int tb=PI("Boundary",1);
+    if(tb!=1 && tb!=2)throw std::runtime_error("Boundary Condition method is not valid.");
+    c.tboundary=(tb==2? DSPH_BOUNDARY_MDBC: 0);      // 0 and DSPH_BOUNDARY_DBC both mean DBC; 0 keeps the configuration bytes of DBC cases as they were
+    if(tb==2){
+      if(PI("SlipMode",1)!=1)throw std::runtime_error("Only the slip mode velocity=0 is allowed with mDBC conditions.");   // S/JSph.cpp:788
+      if(PI("MDBCCorrector",0)!=0)c.tboundary|=DSPH_BOUNDARY_MDBCCORRECTOR;
+    }
+  }
   c.tdensity=PI("DensityDT",0); c.ddtvalue=float(PD("DensityDTvalue",true,0.1));
   c.shiftmode=PI("Shifting",0);
   if(c.shiftmode){ c.shiftcoef=float(PD("ShiftCoef",true,-2)); if(c.shiftcoef==0)c.shiftmode=0; else c.shifttfs=float(PD("ShiftTFS",true,0)); }
@@ -347,6 +369,13 @@ void LoadCase(CaseData &cd,const std::string &dir,const std::string &casename){
       cd.velrhop[4*i+3]=c.phases[cp].rho;
     }
   }
+  cd.normals.clear();
+  if((c.tboundary&0xff)==DSPH_BOUNDARY_MDBC){
+    LoadCaseNormals(cd.normals,dir,casename);
+    const unsigned nbound=c.casenfixed+c.casenmoving+c.casenfloat;
+    if(cd.normals.empty())throw std::runtime_error("No valid normal vectors for using mDBC (file "+casename+"_Normals.nbi4).");
+    if(cd.normals.size()!=size_t(nbound)*3)throw std::runtime_error("The number of final normals does not match boundary particles.");
+  }
   const bool mapsizeloaded=(h.mapposmin[0]!=h.mapposmax[0]||h.mapposmin[1]!=h.mapposmax[1]||h.mapposmin[2]!=h.mapposmax[2]);
   if(mapsizeloaded){ memcpy(c.maprealposmin,h.mapposmin,24); memcpy(c.maprealposmax,h.mapposmax,24); }
   else ComputeMapRealPos(cd);
@@ -487,6 +516,38 @@ static void MakePeriodicBox(CaseData &cd,unsigned long long nptarget,unsigned se
   cd.blocks.clear(); cd.blocks.push_back({3,0,cd.mkfluidfirst+0,0,np});
   for(int i=0;i<3;i++){ cd.caseposmin[i]=0.5*dp; cd.caseposmax[i]=(n-0.5)*dp; } // lattice extremes, not jittered positions
   ComputeMapRealPos(cd);
+}
+
+void LoadCaseNormals(std::vector<double> &normals,const std::string &dir,const std::string &casename){
+  normals.clear();
+  const std::string file=dir+"/"+casename+"_Normals.nbi4";
+  FILE *f=fopen(file.c_str(),"rb");
+  if(!f)return;
+  fclose(f);
+  std::unique_ptr<Bi4Item> b=Bi4Load(file,"JPartNormalData");
+  const unsigned nbound=b->GetUint("Nbound");
+  const Bi4Array *a=b->FindArray("PartNormals");
+  if(!a || a->type!=BI4_DOUBLE3 || a->count!=nbound)return;
+  normals.resize(size_t(nbound)*3);
+  if(nbound)memcpy(normals.data(),a->data.data(),size_t(nbound)*24);
+}
+
+void MakeTankNormals(CaseData &cd){
+  const dsph_config &c=cd.cfg;
+  const unsigned nbound=c.casenfixed;
+  const double dp=c.dp, hd=0.5*dp;
+  const bool twod=(c.simulate2d!=0);
+  const long long NX=llround(cd.caseposmax[0]/dp), NY=llround(cd.caseposmax[1]/dp);
+  cd.normals.assign(size_t(nbound)*3,0.0);
+  for(size_t q=0;q<cd.idp.size();q++){
+    const unsigned id=cd.idp[q];
+    if(id>=nbound)continue;
+    const long long i=llround(cd.pos[3*q]/dp), j=llround(cd.pos[3*q+1]/dp), k=llround(cd.pos[3*q+2]/dp);
+    double *n=&cd.normals[size_t(id)*3];
+    if(i==0)n[0]=hd; else if(i==NX)n[0]=-hd;
+    if(!twod){ if(j==0)n[1]=hd; else if(j==NY)n[1]=-hd; }
+    if(k==0)n[2]=hd;
+  }
 }
 
 void MakeCaseSlab(CaseData &cd,const std::string &kind,unsigned long long nptarget,unsigned seed,unsigned cxlo,unsigned cxhi){

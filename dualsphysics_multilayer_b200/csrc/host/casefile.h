@@ -24,6 +24,7 @@ struct CaseData {
   std::vector<double> pos;                 // xyz packed
   std::vector<float> velrhop;              // xyzw packed
   std::vector<dsph_gauge> gauges;          // <special><gauges> (S/JDsGaugeSystem.cpp:186-275)
+  std::vector<double> normals;             // mDBC: vector particle -> boundary limit per boundary particle, id order, xyz packed (<name>_Normals.nbi4)
   unsigned np()const{ return (unsigned)idp.size(); }
   unsigned npb()const{ return cfg.casenfixed+cfg.casenmoving; }
 };
@@ -34,6 +35,10 @@ void ComputeMapRealPos(CaseData &cd);
 // particle code from id (JSph::LoadCodeParticles -> JSphMk::GetCodeById)
 void ComputeCodes(const CaseData &cd,unsigned np,const unsigned *idp,dsph_typecode *code);
 
+// mDBC normal vectors of the synthetic tank cases: every wall particle points half a particle spacing into the tank along each wall it lies on
+void MakeTankNormals(CaseData &cd);
+// <dir>/<casename>_Normals.nbi4 (JPartNormalData::LoadFile/SaveFile, S/JPartNormalData.cpp:179-262); empty when the file does not exist
+void LoadCaseNormals(std::vector<double> &normals,const std::string &dir,const std::string &casename);
 void SaveCase(const CaseData &cd,const std::string &dir,const std::string &casename);
 void LoadCase(CaseData &cd,const std::string &dir,const std::string &casename);
 

@@ -276,6 +276,16 @@ static RunSummary RunRank(const RunOptions &opt,CaseData &cd,int rank,SlabGroup 
     ComputeCodes(cd,np0,pidp,code.data());
     unsigned npb0=0; for(unsigned i=0;i<np0;i++)if(pidp[i]<c.casenfixed+c.casenmoving)npb0++;     // boundary ids come first (CheckSortParticles)
     eng.Upload(np0,npb0,pidp,code.data(),ppos,pvr);
+    if(eng.mdbc){
+      // JSph::LoadBoundNormals + ConfigBoundNormals (S/JSph.cpp:1262-1340): vector particle -> boundary limit from the normals file,
+      // doubled = particle -> ghost node
+      if(opt.partbegin>=0)throw std::runtime_error("Restart with mDBC needs the extra data of the PART (not written by this driver).");
+      if(slabs)throw std::runtime_error("mDBC cannot be combined with -mgpu yet (the halo records carry no normals).");
+      std::vector<float> nrm(size_t(npb0)*3,0.f);
+      for(unsigned q=0;q<npb0;q++){ const size_t id=pidp[q]; if(3*id+2<cd.normals.size())for(int i=0;i<3;i++)nrm[3*size_t(q)+i]=float(cd.normals[3*id+i])*2.f; }
+      eng.SetBoundNormals(nrm.data(),npb0);
+      log.Printf("Boundary: mDBC (slip mode velocity=0%s), %u normal vectors",eng.mdbccorrector? ", corrector": "",npb0);
+    }
   }
   if(restartdtpre>0)eng.symplecticdtpre=restartdtpre;
   dsph_divinfo di;

@@ -36,23 +36,29 @@ __device__ __forceinline__ float MdbcWarpSumF(float v){
   return v;
 }
 
-// kernel value and gradient factor (fsph::GetKernel_WabFac, S/FunSphKernel.h:226-234 Wendland, :97-118 cubic)
+// kernel value and gradient factor (fsph::GetKernel_WabFac, S/FunSphKernel.h:226-234 Wendland, :97-118 cubic).  Every operation is an
+// explicitly rounded one (no FMA contraction): the CPU reference is an x86-64 build without FMA, and the corrected density is compared at
+// the level of the last bit of a float near 1000 (see the ordered sums below): the 4x4 system amplifies a last-bit difference of a kernel
+// value into ~10 ulp of the corrected density, i.e. 6e-5 of the wall pressure and of Ace next to the wall (measured: 421 of 692 wall
+// particles off by up to 10 ulp with q = r*(1/h) instead of the quotient r/h; 7 of 692 off by 1 ulp with the operations below).
 template<int TKER> __device__ __forceinline__ float MdbcWabFac(float rr2,const DevCtes &c,float &fac){
-  const float rad=sqrtf(rr2), qq=rad/c.kernelh;
+  const float rad=__fsqrt_rn(rr2), qq=__fdiv_rn(rad,c.kernelh);
   if(TKER==DSPH_KERNEL_WENDLAND){
-    const float wqq1=1.f-0.5f*qq, wqq2=wqq1*wqq1;
-    fac=c.bwen*qq*wqq2*wqq1/rad;
-    const float wqq=qq+qq+1.f;
-    return c.awen*wqq*wqq2*wqq2;
+    const float wqq1=__fsub_rn(1.f,__fmul_rn(0.5f,qq)), wqq2=__fmul_rn(wqq1,wqq1);
+    // the association of the reference binary (objdump of oracle/_ref/obj52/JSphCpu.o, -O3 -ffast-math re-associates the products):
+    // fac = ((bwen*q)*(w^2*w))/r,  wab = (awen*(1+2q))*(w^2*w^2)
+    fac=__fdiv_rn(__fmul_rn(__fmul_rn(c.bwen,qq),__fmul_rn(wqq1,wqq2)),rad);
+    const float wqq=__fadd_rn(__fadd_rn(qq,qq),1.f);
+    return __fmul_rn(__fmul_rn(c.awen,wqq),__fmul_rn(wqq2,wqq2));
   }
   if(rad>c.kernelh){
-    const float wqq1=2.0f-qq, wqq2=wqq1*wqq1;
-    fac=c.cub_c2*wqq2/rad;
-    return c.cub_a24*(wqq2*wqq1);
+    const float wqq1=__fsub_rn(2.0f,qq), wqq2=__fmul_rn(wqq1,wqq1);
+    fac=__fdiv_rn(__fmul_rn(c.cub_c2,wqq2),rad);
+    return __fmul_rn(__fmul_rn(c.cub_a24,wqq1),wqq2);            // (a24*w)*w^2 in the reference binary
   }
-  const float wqq2=qq*qq;
-  fac=(c.cub_c1*qq+c.cub_d1*wqq2)/rad;
-  return c.cub_a2*(1.0f+(0.75f*qq-1.5f)*wqq2);
+  const float wqq2=__fmul_rn(qq,qq);
+  fac=__fdiv_rn(__fadd_rn(__fmul_rn(c.cub_c1,qq),__fmul_rn(c.cub_d1,wqq2)),rad);
+  return __fmul_rn(c.cub_a2,__fadd_rn(1.0f,__fmul_rn(__fsub_rn(__fmul_rn(0.75f,qq),1.5f),wqq2)));
 }
 
 // x = A^-1 b by cofactors (the inverse the reference builds with fmath::InverseMatrix4x4 / 3x3, applied to b on the fly)
@@ -104,35 +110,50 @@ template<int TKER,bool SIM2D> __global__ void __launch_bounds__(FORCES_THREADS) 
     if(xini<xfin)for(int z=zini;z<zfin;z++)for(int y=yini;y<yfin;y++){
       const unsigned v=unsigned(t.nsheet*z+t.ncx*y)+t.cellfluid;
       const unsigned pini=t.begincell[v+xini], pfin=t.begincell[v+xfin];
-      for(unsigned p2=pini+lane;p2<pfin;p2+=32u){
-        const float drx=float(gx-m.pos[3*size_t(p2)]), dry=float(gy-m.pos[3*size_t(p2)+1]), drz=float(gz-m.pos[3*size_t(p2)+2]);
-        const float rr2=drx*drx+dry*dry+drz*drz;
-        if(rr2<=c.kernelsize2 && (t.code[p2]&DSPH_CODE_MASKTYPE)==DSPH_CODE_TYPE_FLUID){
-          float fac;
-          const float wab=MdbcWabFac<TKER>(rr2,c,fac);
-          const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
-          const float rhop2=m.velrhop[p2].w;
-          const float massp2=c.massfluid;
-          const float volp2=massp2/rhop2;
-          rhopp1+=massp2*wab; grx+=massp2*frx; gry+=massp2*fry; grz+=massp2*frz;
-          const float vwab=wab*volp2;
-          sumwab+=vwab;
-          const float vfrx=frx*volp2, vfry=fry*volp2, vfrz=frz*volp2;
-          if(SIM2D){
-            a[0][0]+=vwab; a[0][1]+=drx*vwab; a[0][2]+=drz*vwab;
-            a[1][0]+=vfrx; a[1][1]+=drx*vfrx; a[1][2]+=drz*vfrx;
-            a[2][0]+=vfrz; a[2][1]+=drx*vfrz; a[2][2]+=drz*vfrz;
+      for(unsigned base=pini;base<pfin;base+=32u){
+        const unsigned p2=base+lane;
+        float t_rho=0,t_gx=0,t_gy=0,t_gz=0,t_w=0;
+        bool hit=false;
+        if(p2<pfin){
+          const float drx=float(gx-m.pos[3*size_t(p2)]), dry=float(gy-m.pos[3*size_t(p2)+1]), drz=float(gz-m.pos[3*size_t(p2)+2]);
+          const float rr2=__fadd_rn(__fadd_rn(__fmul_rn(drx,drx),__fmul_rn(dry,dry)),__fmul_rn(drz,drz));
+          if(rr2<=c.kernelsize2 && (t.code[p2]&DSPH_CODE_MASKTYPE)==DSPH_CODE_TYPE_FLUID){
+            hit=true;
+            float fac;
+            const float wab=MdbcWabFac<TKER>(rr2,c,fac);
+            const float frx=__fmul_rn(fac,drx), fry=__fmul_rn(fac,dry), frz=__fmul_rn(fac,drz);
+            const float rhop2=m.velrhop[p2].w;
+            const float massp2=c.massfluid;
+            const float volp2=__fdiv_rn(massp2,rhop2);
+            t_rho=__fmul_rn(massp2,wab); t_gx=__fmul_rn(massp2,frx); t_gy=__fmul_rn(massp2,fry); t_gz=__fmul_rn(massp2,frz);
+            const float vwab=__fmul_rn(wab,volp2);
+            t_w=vwab;
+            const float vfrx=__fmul_rn(frx,volp2), vfry=__fmul_rn(fry,volp2), vfrz=__fmul_rn(frz,volp2);
+            if(SIM2D){
+              a[0][0]+=vwab; a[0][1]+=__fmul_rn(drx,vwab); a[0][2]+=__fmul_rn(drz,vwab);
+              a[1][0]+=vfrx; a[1][1]+=__fmul_rn(drx,vfrx); a[1][2]+=__fmul_rn(drz,vfrx);
+              a[2][0]+=vfrz; a[2][1]+=__fmul_rn(drx,vfrz); a[2][2]+=__fmul_rn(drz,vfrz);
+            }
+            else{
+              a[0][0]+=vwab; a[0][1]+=__fmul_rn(drx,vwab); a[0][2]+=__fmul_rn(dry,vwab); a[0][3]+=__fmul_rn(drz,vwab);
+              a[1][0]+=vfrx; a[1][1]+=__fmul_rn(drx,vfrx); a[1][2]+=__fmul_rn(dry,vfrx); a[1][3]+=__fmul_rn(drz,vfrx);
+              a[2][0]+=vfry; a[2][1]+=__fmul_rn(drx,vfry); a[2][2]+=__fmul_rn(dry,vfry); a[2][3]+=__fmul_rn(drz,vfry);
+              a[3][0]+=vfrz; a[3][1]+=__fmul_rn(drx,vfrz); a[3][2]+=__fmul_rn(dry,vfrz); a[3][3]+=__fmul_rn(drz,vfrz);
+            }
           }
-          else{
-            a[0][0]+=vwab; a[0][1]+=drx*vwab; a[0][2]+=dry*vwab; a[0][3]+=drz*vwab;
-            a[1][0]+=vfrx; a[1][1]+=drx*vfrx; a[1][2]+=dry*vfrx; a[1][3]+=drz*vfrx;
-            a[2][0]+=vfry; a[2][1]+=drx*vfry; a[2][2]+=dry*vfry; a[2][3]+=drz*vfry;
-            a[3][0]+=vfrz; a[3][1]+=drx*vfrz; a[3][2]+=dry*vfrz; a[3][3]+=drz*vfrz;
-          }
+        }
+        // The five FLOAT sums are added in the reference's order (ascending particle index): the corrected density is the small
+        // difference rho-rho0 of sums of magnitude rho, so another order of the same float additions moves it by 1e-4 of itself
+        // (measured) -- and with it the pressure of every wall particle.  The terms are computed by 32 lanes at once; only the
+        // additions are serial (every lane keeps the same accumulators).
+        unsigned mask=__ballot_sync(0xffffffffu,hit);
+        while(mask){
+          const int l=__ffs(int(mask))-1; mask&=mask-1u;
+          rhopp1+=__shfl_sync(0xffffffffu,t_rho,l); grx+=__shfl_sync(0xffffffffu,t_gx,l); gry+=__shfl_sync(0xffffffffu,t_gy,l);
+          grz+=__shfl_sync(0xffffffffu,t_gz,l); sumwab+=__shfl_sync(0xffffffffu,t_w,l);
         }
       }
     }
-    rhopp1=MdbcWarpSumF(rhopp1); grx=MdbcWarpSumF(grx); gry=MdbcWarpSumF(gry); grz=MdbcWarpSumF(grz); sumwab=MdbcWarpSumF(sumwab);
     constexpr int N=(SIM2D? 3: 4);
     #pragma unroll
     for(int i=0;i<N;i++){
@@ -147,8 +168,8 @@ template<int TKER,bool SIM2D> __global__ void __launch_bounds__(FORCES_THREADS) 
         double x[4]; MdbcSolve<N>(a,b,determ,x);
         //-Ghost node density mirrored back to the boundary particle: dpos = -normal.
         const float rhoghost=float(x[0]);
-        if(SIM2D){ const float gxx=-float(x[1]), gzz=-float(x[2]); rhopfinal=rhoghost+gxx*(-bn.x)+gzz*(-bn.z); }
-        else{ const float gxx=-float(x[1]), gyy=-float(x[2]), gzz=-float(x[3]); rhopfinal=rhoghost+gxx*(-bn.x)+gyy*(-bn.y)+gzz*(-bn.z); }
+        if(SIM2D){ const float gxx=-float(x[1]), gzz=-float(x[2]); rhopfinal=__fadd_rn(__fadd_rn(rhoghost,__fmul_rn(gxx,-bn.x)),__fmul_rn(gzz,-bn.z)); }
+        else{ const float gxx=-float(x[1]), gyy=-float(x[2]), gzz=-float(x[3]); rhopfinal=__fadd_rn(__fadd_rn(__fadd_rn(rhoghost,__fmul_rn(gxx,-bn.x)),__fmul_rn(gyy,-bn.y)),__fmul_rn(gzz,-bn.z)); }
       }
       else if(a[0][0]>0)rhopfinal=float(double(rhopp1)/a[0][0]);          // determinant too small: zeroth order
       rhopfinal=(rhopfinal!=FLT_MAX? rhopfinal: c.rhopzero);

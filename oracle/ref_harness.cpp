@@ -57,6 +57,9 @@ class RefHarness : public JSphCpuSingle {
     if(PosPrec)w.Add("pospre",4,3,Np,PosPrec);
     if(VelrhopPrec)w.Add("velrhoppre",3,4,Np,VelrhopPrec);
     if(SpsTauc)w.Add("spstau",3,6,Np,SpsTauc);
+#ifndef HARNESS_NN
+    if(UseNormals && BoundNormalc)w.Add("boundnormal",3,3,Np,BoundNormalc);   // mDBC: particle -> ghost node, in the current particle order
+#endif
     if(withcells){
       const tuint3 cmin=CellDivSingle->GetCellDomainMin(), cmax=CellDivSingle->GetCellDomainMax();
       const unsigned cm[6]={cmin.x,cmin.y,cmin.z,cmax.x,cmax.y,cmax.z};
@@ -78,6 +81,9 @@ class RefHarness : public JSphCpuSingle {
     RefDumpWriter w(DumpName(step,stage));
     w.U32("np",Np); w.U32("npb",Npb); w.U32("npbok",NpbOk);
     w.Add("ace",3,3,Np,Acec); w.Add("ar",3,1,Np,Arc);
+#ifndef HARNESS_NN
+    if(TBoundary==BC_MDBC)w.Add("velrhop",3,4,Np,Velrhopc);                   // boundary densities after MdbcBoundCorrection
+#endif
     if(ShiftPosfsc)w.Add("shiftposfs",3,4,Np,ShiftPosfsc);
     if(SpsTauc)w.Add("spstau",3,6,Np,SpsTauc);
     if(Pressc)w.Add("press",3,1,Np,Pressc);

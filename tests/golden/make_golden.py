@@ -50,6 +50,11 @@ CASES = [
     # particles leaving: a RhopOut window just above the initial hydrostatic maximum excludes 4 / 20 / 146 particles by steps 10 / 20 / 40 (OUTRHOP marking in
     # the step update, special boxes of the divide, NpfOut bookkeeping); options after "xml:" patch <parameter> values of Case.xml
     ("db_sym_wend_art_ddt2_rhopout", "dambreak", 3000, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2", "xml:RhopOutMax=1002.14", "xml:RhopOutMin=999.2"], [10, 20, 40], 41),
+    # mDBC boundary correction (Boundary=2, slip mode velocity=0): normals file written by mkcase, boundary densities after
+    # JSphCpu::Interaction_MdbcCorrection dumped with the forces; DDT1 so that the boundary rule of S/JSphCpu.cpp:730 is on the path
+    ("db_sym_wend_art_ddt1_mdbc", "dambreak", 3000, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=1", "boundary=2"], [0, 30], 31),
+    ("db_sym_cubic_art_ddt2_mdbccorr", "dambreak", 3000, ["tstep=2", "tkernel=1", "tvisco=1", "visco=0.1", "ddt=2", "boundary=2", "mdbccorrector=1"], [20], 21),
+    ("db2d_ver_wend_art_ddt1_mdbc", "dambreak2d", 3000, ["tstep=1", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=1", "boundary=2", "verletsteps=10"], [25], 26),
     # in-solver gauges of the reference (JGaugeSystem: velocity, swl, maxz, force; computed every step), dumped by the harness at the
     # initial state and at the listed steps; "gauges:" injects the <special><gauges> block below into Case.xml
     ("db_sym_wend_art_ddt2_gauges", "dambreak", 3000, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2", "gauges:"], [0, 20, 60], 61),
@@ -116,6 +121,8 @@ def run(name, kind, nptarget, opts, steps, nsteps, outdir):
         pack = {"config": np.frombuffer(bytes(cd.cfg), np.uint8).copy(), "case/idp": cd.idp, "case/pos": cd.pos,
                 "case/velrhop": cd.velrhop, "case/code": cd.codes(), "case/npb": np.uint32(cd.npb), "steps": np.array(steps, np.uint32),
                 "nsteps": np.uint32(nsteps), "case/caseposmin": np.array(cd.caseposmin), "case/caseposmax": np.array(cd.caseposmax)}
+        if "boundary=2" in opts:
+            pack["case/normals"] = dsph.case_normals(tmp, "Case")
         if "gauges:" in opts:
             pack["case/xml"] = np.frombuffer(open(xmlfile, "rb").read(), np.uint8).copy()
         for f in sorted(os.listdir(os.path.join(tmp, "dump"))):

@@ -16,6 +16,9 @@ GOLDEN_CASES = ["db_sym_wend_art_ddt2", "db_ver_cubic_art_ddt1_shift", "db_sym_w
                 "nn_sym_fda_lam_ddt3_shift", "nn_ver_sph_lam_ddt1", "nn_sym_sph_conseq_ddt2_shift", "nn_sym_fda_conseq_cubic",
                 "nn_sym_fda_art_ddt1", "db2d_sym_wend_art_ddt2_shift", "db2d_ver_cubic_lamsps_ddt1", "nn2d_sym_sph_lam_ddt3_shift",
                 "nn2d_sym_fda_conseq_ddt2", "db_sym_wend_art_ddt2_rhopout", "db_ver_wend_art_ddt1_rhopout"]
+# mDBC boundary correction: dumps of the reference with Boundary=2; the CPU checker has no mDBC, the CUDA path is compared with the
+# reference directly (tests/test_gpu_parity.py)
+MDBC_CASES = ["db_sym_wend_art_ddt1_mdbc", "db_sym_cubic_art_ddt2_mdbccorr", "db2d_ver_wend_art_ddt1_mdbc"]
 GPU_PENDING = []                             # cases the CUDA path does not cover yet
 
 
@@ -74,6 +77,8 @@ def upload_state(ctx, st, cfg):
         ctx.set_velrhopm1(st["velrhopm1"][keep])
     if "spstau" in st:
         ctx.set_spstau(st["spstau"][keep])
+    if "boundnormal" in st:                       # mDBC: vectors particle -> ghost node in the dumped particle order
+        ctx.set_boundnormals(st["boundnormal"][keep][:npb])
     if cfg.tstep == capi.STEP_SYMPLECTIC:
         ctx.symplectic_dtpre = float(st["symplecticdtpre"])
     else:
@@ -114,6 +119,9 @@ def check_forces(ctx, ref, cfg, tol, interstep):
                viscdt=abs(fr.viscdtmax - float(ref["viscdtmax"])) / max(abs(float(ref["viscdtmax"])), 1e-30),
                acemax=abs(fr.acemax - float(ref["acemax"])) / max(float(ref["acemax"]), 1e-30),
                velmax=abs(fr.velmax - float(ref["velmax"])) / max(float(ref["velmax"]), 1e-30))
+    if "velrhop" in ref:                          # mDBC: densities of the boundary particles after the correction
+        st = ctx.download()
+        out["mdbc_rhop"] = rl2(st["velrhop"][:npb, 3] - float(cfg.rhopzero), ref["velrhop"][:npb, 3] - float(cfg.rhopzero))
     for k, v in out.items():
         assert v <= tol.get(k, tol["default"]), (k, v, out)
     return fr, out
@@ -186,6 +194,8 @@ def run_trajectory(lib, g: Golden, capacity=0):
     else:
         code = np.where(idp < cfg.casenfixed, capi.CODE_TYPE_FIXED, capi.CODE_TYPE_FLUID).astype(np.uint16)
     ctx.upload(idp, z["case/pos"], z["case/velrhop"], npb, code)
+    if "case/normals" in z.files:                 # mDBC: file vectors (particle -> boundary limit) doubled, JSph::ConfigBoundNormals
+        ctx.set_boundnormals((2.0 * z["case/normals"][idp[:npb]]).astype(np.float32))
     ctx.celldiv(True)
     t = 0.0
     for _ in range(g.nsteps):

@@ -178,3 +178,49 @@ def test_gpu_driver_slab_run_matches_single_gpu_run(gpu_lib, tmp_path):
     assert np.abs(pa - pb).max() < 1e-7
     assert np.linalg.norm((va - vb).astype(np.float64)) / np.linalg.norm(va.astype(np.float64)) < 1e-5
     print(open(str(two / "Run.out")).read()[-1200:])
+
+
+def test_mkcase_writes_mdbc_normals_the_reference_accepts(tmp_path):
+    """CPU: `mkcase ... boundary=2` writes <case>_Normals.nbi4 (JPartNormalData format); the library reads it back, and the reference CPU
+    solver runs the case with Boundary="mDBC" from that file."""
+    import subprocess
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    mkcase = os.path.join(root, "dualsphysics_multilayer_b200", "bin", "mkcase")
+    subprocess.check_call([mkcase, "dambreak", "3000", str(tmp_path), "Case", "boundary=2", "ddt=1"], stdout=subprocess.DEVNULL)
+    assert os.path.exists(str(tmp_path / "Case_Normals.nbi4"))
+    cd = dsph.load_case(str(tmp_path), "Case")
+    assert cd.cfg.tboundary == 2
+    n = dsph.case_normals(str(tmp_path), "Case")
+    assert n.shape == (cd.npb, 3)
+    hd = 0.5 * cd.cfg.dp
+    assert np.all(np.isin(np.round(n / hd).astype(int), (-1, 0, 1))) and np.all(np.abs(n).sum(axis=1) > 0)
+    bed = np.isclose(cd.pos[:cd.npb, 2], 0.0)
+    assert np.allclose(n[bed, 2], hd) and np.all(n[~bed, 2] == 0)
+    ref = os.path.join(root, "oracle", "_ref", "DualSPHysics5.2CPU_linux64")
+    if os.path.exists(ref):
+        r = subprocess.run([ref, "Case", "out", "-cpu", "-ompthreads:2", "-sv:none", "-nsteps:3"], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert 'Boundary="mDBC"' in r.stdout and 'NormalDataFile="Case_Normals.nbi4"' in r.stdout and "Finished execution (code=0)" in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.gpu
+def test_gpu_driver_runs_mdbc_case_like_the_reference(gpu_lib, tmp_path):
+    """bin/dsph_b200 on an mDBC case (Boundary=2 in Case.xml + Case_Normals.nbi4): its last PART equals the final state the reference CPU
+    solver reached after the same number of steps (golden dump db_sym_wend_art_ddt1_mdbc)."""
+    import subprocess
+    from parity import Golden
+    g = Golden("db_sym_wend_art_ddt1_mdbc")
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    mkcase = os.path.join(root, "dualsphysics_multilayer_b200", "bin", "mkcase")
+    subprocess.check_call([mkcase, "dambreak", "3000", str(tmp_path), "Case", "tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=1", "boundary=2"], stdout=subprocess.DEVNULL)
+    cd = dsph.load_case(str(tmp_path), "Case")
+    assert np.array_equal(cd.pos, g.z["case/pos"]) and cd.cfg.tboundary == 2
+    out = tmp_path / "out"
+    dsph.run_case(str(tmp_path), "Case", str(out), nsteps=g.nsteps, timeout=1e-5)          # a PART at every step: the last one is the state after nsteps
+    assert "mDBC" in open(str(out / "Run.out")).read()
+    a, ta, sa, _ = dsph.load_partset(str(out), g.nsteps)
+    fin = g.stage(g.nsteps, "final")
+    assert sa == g.nsteps and abs(ta - float(fin["timestep"])) <= 1e-6 * ta
+    oa = np.argsort(a.idp); ob = np.argsort(fin["idp"])
+    assert np.array_equal(a.idp[oa], fin["idp"][ob])
+    assert np.abs(a.pos[oa] - fin["pos"][ob]).max() < 1e-6
+    assert np.linalg.norm((a.velrhop[oa] - fin["velrhop"][ob]).astype(np.float64)) / np.linalg.norm(fin["velrhop"][ob].astype(np.float64)) < 1e-6

@@ -3,7 +3,7 @@
 // in the reference solver (oracle/_ref) and in dsph_b200.
 //   mkcase <dambreak|periodicbox|nn2layer> <np_target> <dir> <name> [key=value ...]
 // keys: tstep=1|2 tkernel=1|2 tvisco=1|2 visco=v ddt=0..3 ddtvalue=v shifting=0..3 shiftcoef=v shifttfs=v
-//       timemax=t timeout=t cellmode=1|2 seed=n
+//       timemax=t timeout=t cellmode=1|2 seed=n boundary=1|2 (2 = mDBC: writes <name>_Normals.nbi4) mdbccorrector=0|1
 #include "../dualsphysics_multilayer_b200/csrc/host/casefile.h"
 #include <cstdio>
 #include <cstdlib>
@@ -27,8 +27,10 @@ int main(int argc,char **argv){
       else if(k=="shifting")c.shiftmode=int(v); else if(k=="shiftcoef")c.shiftcoef=float(v); else if(k=="shifttfs")c.shifttfs=float(v);
       else if(k=="timemax")c.timemax=v; else if(k=="timeout")c.timeout=v; else if(k=="cellmode")c.cellmode=int(v);
       else if(k=="verletsteps")c.verletsteps=int(v); else if(k=="velgrad")c.nn_velgrad=int(v);
+      else if(k=="boundary"){ c.tboundary=(c.tboundary&~0xff)|int(v); } else if(k=="mdbccorrector"){ if(int(v))c.tboundary|=DSPH_BOUNDARY_MDBCCORRECTOR; }
       else if(k=="seed"){} else throw std::runtime_error("unknown option "+k);
     }
+    if((c.tboundary&0xff)==DSPH_BOUNDARY_MDBC)MakeTankNormals(cd);      // <name>_Normals.nbi4 for the reference and for dsph_b200
     mkdir(argv[3],0755);
     SaveCase(cd,argv[3],argv[4]);
     printf("%s: np=%u nb=%u nf=%u dp=%.9g h=%.9g\n",argv[4],cd.np(),c.casenfixed,c.casenfluid,c.dp,double(c.kernelh));
