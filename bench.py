@@ -187,12 +187,17 @@ def reference_gpu_baseline(npart, kind="dambreak", lengths=(20, 50, 80), repeats
         # What is stable and what is not (measured on three boxes): the reference's CF-Forces slope repeats to ~1 % (112.7 / 113 ms per
         # step = 2 evaluations), its NL-RadixSort slope does not (26 ... 130 ms per step: thrust::sort_by_key allocates and frees its
         # temporaries in every call, and cudaMalloc/cudaFree serialise with everything else on the device).  `value` is therefore the
-        # reference's BEST case (slope through its fastest runs); `reliable` says that this line fits AND that the reference's own
-        # synchronising timers add up to its run time within 10 % (the internal-consistency check VERDICT r01 asked for);
-        # `agrees_with_timer_series` is reported but the two series differ by the erratic sort.
-        return {"value": npa / b_all / 1e6 if b_all and b_all > 0 else None, "unit": UNIT, "np": npa, "ms_per_step": 1e3 * b_all,
+        # reference's BEST case: the smallest per-step slope of any series (fastest-run line, single series, timer series);
+        # `reliable` says that the reference's own synchronising timers add up to its run time within 10 % (the internal-consistency
+        # check VERDICT r01 asked for); `fit_ok` / `agrees_with_timer_series` / `series_slope_spread` document the erratic sort.
+        # The comparison that IS stable is kernel against kernel: cf_forces_ms_per_evaluation vs roofline.avg_launch_ms.
+        # every positive slope seen (fastest-run line, each series, the timer series): the SMALLEST one is the reference's best case
+        cands = [v for v in [b_all, bt] + [sr["ms_per_step"] * 1e-3 for sr in series] if v and v > 0]
+        b_best = min(cands) if cands else None
+        return {"value": npa / b_best / 1e6 if b_best else None, "unit": UNIT, "np": npa, "ms_per_step": 1e3 * b_best if b_best else None,
+                "ms_per_step_fastest_runs_line": 1e3 * b_all if b_all else None,
                 "rms_residual_ms": 1e3 * res_all, "fastest_runtime_s": best, "series": series, "series_slope_spread": spread,
-                "reliable": bool(fit_ok and timers_consistent), "fit_ok": fit_ok, "timers_consistent": timers_consistent, "agrees_with_timer_series": agree,
+                "reliable": bool(timers_consistent), "fit_ok": fit_ok, "timers_consistent": timers_consistent, "agrees_with_timer_series": agree,
                 "with_sync_timers": {"ms_per_step": 1e3 * bt, "rms_residual_ms": 1e3 * rest, "timers_ms_per_step": split, "timers_sum_ms_per_step": tsum,
                                      "timers_sum_over_runtime": (tsum / (1e3 * bt) if bt else None)},
                 "cf_forces_ms_per_evaluation": (split.get("CF-Forces", 0.0) / 2.0 if split.get("CF-Forces") else None),

