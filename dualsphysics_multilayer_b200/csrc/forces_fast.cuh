@@ -19,6 +19,17 @@ __device__ __forceinline__ float FastRsqrt(float x){ float r; asm("rsqrt.approx.
 
 struct FastP1 { float4 velrhop; float press, ovrhop; };
 
+// Store condition of the reference (S/JSphCpu.cpp:800-818, ker_forces_fluid_v1 above): what the fluid-fluid pass accumulated -- the DDT term
+// and the SPS velocity gradient with it -- is kept only when one of ar, ace, viscdt is non-zero (always with shifting).  The variants with
+// ONE accumulator for both passes apply it when the fluid-fluid pass is complete.  It only matters for a fluid at rest with a uniform
+// pressure field, where the reference drops the DDT term.
+template<int TVISCO,bool SHIFT> __device__ __forceinline__ void FluidPassStore(PairAcc &a){
+  if(!SHIFT && a.ar==0 && a.ax==0 && a.ay==0 && a.az==0 && a.visc==0){
+    a.delta=0;
+    if(TVISCO==DSPH_VISCO_LAMINARSPS){ a.gxx=a.gxy=a.gxz=a.gyy=a.gyz=a.gzz=0; }
+  }
+}
+
 // packed fp32x2 arithmetic of sm_100 (FADD2/FMUL2/FFMA2: two IEEE fp32 operations per issue slot, same rounding as the scalar forms)
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 Pk(float a,float b){ f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
@@ -195,6 +206,7 @@ ker_forces_fluid_v4(ForceParams t,DevCtes c)
           }
         }
       }
+      if(pass==0)FluidPassStore<TVISCO,SHIFT>(a);
     }
     float ar=a.ar, ax=a.ax, ay=a.ay, az=a.az;
     if(c.simulate2d)ay=0;

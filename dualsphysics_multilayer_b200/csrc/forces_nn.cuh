@@ -543,12 +543,19 @@ ker_nn_fda_ring(ForceParams t,DevCtes c,DevPhases ph)
   fp.ph=code1&DSPH_CODE_MASKVALUE; if(fp.ph>=unsigned(ph.count))fp.ph=0;
   fp.tau_max=ph.ph[fp.ph].tau_max; fp.bi_multi=ph.ph[fp.ph].bi_multi; fp.mass=ph.ph[fp.ph].mass;
   NNFastAcc a; a.ax=a.ay=a.az=a.ar=a.delta=a.visc=a.visceta=0; a.shift=make_float4(0,0,0,0);
-  unsigned anyb=0,nosh=0;
+  unsigned anyb=0,nosh=0,ffdone=0;
+  // Store condition of the reference (M/JSphCpu_NN_FDA.cpp:317-323, NNStore above): the results of the fluid-fluid pass -- the DDT term and
+  // the viscous-dt maximum with them -- are kept only when one of ar, ace, viscdt is non-zero (always with shifting).  It matters for a
+  // fluid at rest with uniform pressure (step 0 of a stacked-layer case): there the reference drops the DDT term.  The ring has been
+  // drained when the first boundary pair arrives, so the accumulators hold exactly the fluid-fluid sums at that moment.
+  auto ffstore=[&]{ ffdone=1u; if(!SHIFT && a.ar==0 && a.ax==0 && a.ay==0 && a.az==0 && a.visc==0){ a.delta=0; a.visceta=0; } };
   V8Traverse(t,c,active,pp1,t.dcell[p1c],q,[&](unsigned p2,float drx,float dry,float drz,float rr2,float pressp2,bool boundp2,bool valid){
+    if(boundp2 && !ffdone)ffstore();
     const float4 vr2=__ldg(&t.velrhop[p2]);
     unsigned codep2=0; if(!boundp2 || SHIFT)codep2=t.code[p2];
     NNPairFast<TKER,TVISCO,TDDT,SHIFT>(drx,dry,drz,rr2,fp,vr2,pressp2,boundp2,codep2,valid,c,ph,a,anyb,nosh);
   });
+  if(!ffdone)ffstore();
   float viscmax=0,ace2=0,vel2=0,etamax=0;
   if(active){
     float ar=a.ar, ax=a.ax, ay=a.ay, az=a.az;
@@ -599,8 +606,11 @@ ker_nn_sph_pressgrad_ring(ForceParams t,DevCtes c,DevPhases ph)
   fp.tau_max=ph.ph[fp.ph].tau_max; fp.bi_multi=ph.ph[fp.ph].bi_multi; fp.mass=ph.ph[fp.ph].mass;
   NNFastAcc a; a.ax=a.ay=a.az=a.ar=a.delta=a.visc=a.visceta=0; a.shift=make_float4(0,0,0,0);
   float g0=0,g1=0,g2=0,g3=0,g4=0,g5=0;
-  unsigned anyb=0,nosh=0;
+  unsigned anyb=0,nosh=0,ffdone=0;
+  // store condition of the fluid-fluid pass (see ker_nn_fda_ring): DDT term and velocity gradient are dropped when ar, ace and viscdt are all zero
+  auto ffstore=[&]{ ffdone=1u; if(!SHIFT && a.ar==0 && a.ax==0 && a.ay==0 && a.az==0 && a.visc==0){ a.delta=0; g0=g1=g2=g3=g4=g5=0; } };
   RingTraverse(t,c,active,pp1,t.dcell[p1c],q,[&](unsigned p2,float drx,float dry,float drz,float rr2,float pressp2,bool boundp2,bool valid){
+    if(boundp2 && !ffdone)ffstore();
     const float4 velrhop2=__ldg(&t.velrhop[p2]);
     unsigned codep2=0; if(!boundp2 || SHIFT)codep2=t.code[p2];
     const unsigned pp2=(boundp2? fp.ph: (codep2&DSPH_CODE_MASKVALUE));
@@ -664,6 +674,7 @@ ker_nn_sph_pressgrad_ring(ForceParams t,DevCtes c,DevPhases ph)
             dv=dvz*volp2; g2+=dv*frx; g4+=dv*fry; g5+=dv*frz;
     }
   });
+  if(!ffdone)ffstore();
   float viscmax=0,vel2=0,etamax=0;
   if(active){
     float ar=a.ar;

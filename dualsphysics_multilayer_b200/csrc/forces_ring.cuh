@@ -182,13 +182,15 @@ ker_forces_fluid_v9(ForceParams t,DevCtes c)
     for(int k=0;k<6;k++)taup1[k]=t.spstau[6*size_t(p1c)+k];
   }
   PairAcc a; ZeroAcc(a);
-  unsigned anyb=0,nosh=0;
+  unsigned anyb=0,nosh=0,ffdone=0;
   V8Traverse(t,c,active,pp1,t.dcell[p1c],q,[&](unsigned p2,float drx,float dry,float drz,float rr2,float pressp2,bool boundp2,bool valid){
+    if(boundp2 && !ffdone){ ffdone=1u; FluidPassStore<TVISCO,SHIFT>(a); }   // the ring was drained at the end of the fluid-fluid pass
     const float4 vr2=__ldg(&t.velrhop[p2]);
     unsigned codep2=0; if(SHIFT && boundp2)codep2=t.code[p2];
     const float *taup2=(TVISCO==DSPH_VISCO_LAMINARSPS && !boundp2? t.spstau+6*size_t(p2): nullptr);
     PairFast<TKER,TVISCO,TDDT,SHIFT,true>(drx,dry,drz,rr2,fp,vr2,pressp2,boundp2,taup1,taup2,codep2,c,a,anyb,nosh,valid);
   });
+  if(!ffdone)FluidPassStore<TVISCO,SHIFT>(a);
   float viscmax=0,ace2=0,vel2=0;
   if(active){
     float ar=a.ar, ax=a.ax, ay=a.ay, az=a.az;

@@ -172,6 +172,7 @@ ker_forces_fluid_v10(ForceParams t,DevCtes c)
     // end of the pass: the boundary pass uses other constants, drain everything
     while(__any_sync(FULL,(head!=tail)||curm))
       V10Round<TKER,TVISCO,TDDT,SHIFT,Q>(q,head,tail,cure,curm,pp1,fp,taup1,boundp2,t,c,ks2,a,anyb,nosh);
+    if(pass==0)FluidPassStore<TVISCO,SHIFT>(a);
   }
   float viscmax=0,ace2=0,vel2=0;
   if(active){
