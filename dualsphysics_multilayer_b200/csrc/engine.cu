@@ -76,6 +76,7 @@ Engine::~Engine(){
   MgCommDestroy();
   GaugesFree();
   if(measuredev)cudaFree(measuredev);
+  if(mgown)cudaFree(mgown);
   if(stmcopy){ cudaStreamSynchronize(stmcopy); cudaStreamDestroy(stmcopy); cudaEventDestroy(evsnap); cudaEventDestroy(evsnapfree); }
   if(snapdev)cudaFree(snapdev);
   FreeAll();
@@ -482,7 +483,7 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
   for(int i=0;i<3;i++)if(lastcellmin[i]!=dp.cellmin[i] || lastcellmax[i]!=dp.cellmax[i])same=false;
   dividefull=!same;
   for(int i=0;i<3;i++){ lastcellmin[i]=dp.cellmin[i]; lastcellmax[i]=dp.cellmax[i]; }
-  divok=true; celltableok=true;
+  divok=true; celltableok=true; mgownok=false;
   npfout_last=dp.npfout; npout_total+=dp.npfout;
   np=dp.npfinal; npb=dp.npbfinal; npbok=npb-dp.npbignore;
   boundchanged=false; forcesok=false;
@@ -570,9 +571,10 @@ void Engine::ForcesLaunch(int interstep){
   if(mdbc && (mdbccorrector || interstep!=DSPH_INTERSTEP_SYMCORRECTOR))MdbcCorrection();
   NvtxNext("CF-Forces");
   CUCHECK(cudaEventRecord(ev[9],stm));
-  const ForceParams t=MakeForceParams();
+  ForceParams t=MakeForceParams();
   const unsigned npf=np-npb;
   const bool shift=(cfg.shiftmode!=0);
+  if(mgpu && npf && !cfg.nn_on && EffectiveForceVariant()==10){ MgBuildOwnList(); t.ownlist=mgown; t.nown=mgscratch[1]+8; }
   if(npf && cfg.nn_on){
     const unsigned nl=LaunchForcesNN((ringbase_ok && RingVariant()!=4? RingVariant(): 1),cfg.tkernel,cfg.tvisco,cfg.tdensity,shift,t,dc,dph,stm);
     if(!nl)throw EngineError(DSPH_ERR_ARG,"Kernel / viscosity / DDT choice is not valid for the multiphase formulation.");
@@ -778,6 +780,18 @@ void Engine::MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi){
     DevAlloc(mgscratch[1],size_t(2*k.domcells[0]+16));               // class totals; column histograms (fluid, boundary)
     DevAlloc(mgscratch[2],size_t(cap)/4+2);                          // one flag byte per particle
   }
+}
+// owned fluid particles of the current divide in index order (mgpu.cuh); their number stays on the device (mgscratch[1][8])
+void Engine::MgBuildOwnList(){
+  if(mgownok)return;
+  const unsigned npf=np-npb;
+  if(mgowncap<npf){ if(mgown)cudaFree(mgown); mgown=nullptr; mgowncap=0; CUCHECK(cudaMalloc((void**)&mgown,size_t(cap)*sizeof(unsigned))); mgowncap=cap; }
+  const unsigned nb=(npf+MG_BLOCK-1)/MG_BLOCK;
+  ker_mg_own_count<<<nb,MG_BLOCK,0,stm>>>(np,npb,code[cur],mgscratch[0]);
+  ker_mg_scanblocks<<<1,1024,0,stm>>>(nb,mgscratch[0],mgscratch[1]+8);
+  ker_mg_own_write<<<nb,MG_BLOCK,0,stm>>>(np,npb,code[cur],mgscratch[0],mgown);
+  launches+=3;
+  mgownok=true;
 }
 void Engine::MgColumnCounts(unsigned *fluid,unsigned *bound,unsigned ncol){
   if(!mgpu)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_column_counts needs dsph_mgpu_config with more than one rank.");

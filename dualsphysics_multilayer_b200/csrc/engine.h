@@ -106,6 +106,8 @@ class Engine {
   // x-slab multi-GPU
   bool mgpu=false; int mgrank=0, mgnranks=1; unsigned mgxlo=0, mgxhi=0;
   unsigned *mgscratch[3]={}; unsigned mgcounts[8]={}; bool mgcounted=false;
+  unsigned *mgown=nullptr; unsigned mgowncap=0; bool mgownok=false;   // owned fluid particles of the current divide (force kernel variant 10)
+  void MgBuildOwnList();
   bool forceslaunched=false;
   void MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi);
   // halo width in cells: 2h; 4h for the SPH velocity-gradient approach of the multiphase fork (its second pair pass reads eta_eff / tau of

@@ -12,6 +12,8 @@ constexpr int FORCES_THREADS=128;
 struct ForceParams {
   unsigned np, npb, npbok;
   int skipghosts;              // multi-GPU: CODE_PERIODIC fluid particles are halo copies, no forces needed
+  const unsigned* __restrict__ ownlist;   // multi-GPU, variant 10: the owned fluid particles in index order (ker_mg_own_write), else null
+  const unsigned* __restrict__ nown;      // their number (device)
   int ncx, ncy, ncz, nsheet;
   unsigned cellfluid;          // nct+1: offset of the fluid boxes in begincell
   unsigned cellzero[3];        // CellDomainMin

@@ -90,9 +90,16 @@ ker_forces_fluid_v10(ForceParams t,DevCtes c)
   __syncthreads();
   unsigned q=threadIdx.x*8u;
   asm volatile("" : "+r"(q));
-  const unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
-  const unsigned p1c=min(p1,t.np-1);
-  const bool active=(p1<t.np && !(t.skipghosts && (t.code[p1c]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_PERIODIC));
+  unsigned p1=t.npb+blockIdx.x*blockDim.x+threadIdx.x;
+  unsigned p1c=min(p1,t.np-1);
+  bool active;
+  if(t.ownlist){                                           // x-slab halo copies take no lanes: thread -> owned fluid particle
+    const unsigned nown=__ldg(t.nown), tid=blockIdx.x*blockDim.x+threadIdx.x;
+    if(blockIdx.x*blockDim.x>=nown)return;
+    active=(tid<nown);
+    p1=p1c=__ldg(t.ownlist+min(tid,nown-1u));
+  }
+  else active=(p1<t.np && !(t.skipghosts && (t.code[p1c]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_PERIODIC));
   const float4 pp1=t.posp[p1c];
   FastP1 fp; fp.velrhop=t.velrhop[p1c]; fp.press=pp1.w; fp.ovrhop=1.f/fp.velrhop.w;
   const unsigned rcell=t.dcell[p1c];

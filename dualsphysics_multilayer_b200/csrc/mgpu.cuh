@@ -113,6 +113,36 @@ __global__ void __launch_bounds__(1024) ker_mg_scanblocks(unsigned nb,unsigned* 
   if(threadIdx.x==0)total[blockIdx.x]=carry;
 }
 
+// List of the OWNED fluid particles of the sorted state (index order kept): the force kernels take their particle from this list so
+// that halo copies, which are interleaved with the owned particles at both ends of every cell row, occupy no lanes.
+//  ker_mg_own_count -> ker_mg_scanblocks (1 class) -> ker_mg_own_write
+__global__ void __launch_bounds__(MG_BLOCK) ker_mg_own_count(unsigned np,unsigned npb,const typecode* __restrict__ code,unsigned* __restrict__ blockcnt){
+  __shared__ unsigned wcnt[MG_BLOCK/32];
+  const unsigned p=npb+blockIdx.x*MG_BLOCK+threadIdx.x;
+  const bool own=(p<np && (code[p]&DSPH_CODE_MASKSPECIAL)!=DSPH_CODE_PERIODIC);
+  const unsigned bal=__ballot_sync(0xffffffffu,own);
+  if((threadIdx.x&31)==0)wcnt[threadIdx.x>>5]=__popc(bal);
+  __syncthreads();
+  if(threadIdx.x==0){
+    unsigned t=0;
+    #pragma unroll
+    for(int i=0;i<MG_BLOCK/32;i++)t+=wcnt[i];
+    blockcnt[blockIdx.x]=t;
+  }
+}
+__global__ void __launch_bounds__(MG_BLOCK) ker_mg_own_write(unsigned np,unsigned npb,const typecode* __restrict__ code,const unsigned* __restrict__ blockoff,unsigned* __restrict__ ownlist){
+  __shared__ unsigned wcnt[MG_BLOCK/32];
+  const unsigned p=npb+blockIdx.x*MG_BLOCK+threadIdx.x;
+  const bool own=(p<np && (code[p]&DSPH_CODE_MASKSPECIAL)!=DSPH_CODE_PERIODIC);
+  const unsigned bal=__ballot_sync(0xffffffffu,own);
+  const unsigned w=threadIdx.x>>5, lane=threadIdx.x&31;
+  if(lane==0)wcnt[w]=__popc(bal);
+  __syncthreads();
+  unsigned base=blockoff[blockIdx.x];
+  for(unsigned i=0;i<w;i++)base+=wcnt[i];
+  if(own)ownlist[base+__popc(bal&((1u<<lane)-1u))]=p;
+}
+
 // owned (normal) particles per cell column, fluid and boundary separately: input of the slab re-balancing
 __global__ void ker_mg_column_counts(unsigned n,const unsigned* __restrict__ dcell,const typecode* __restrict__ code,unsigned domcellcode,
   unsigned ncol,unsigned* __restrict__ fluid,unsigned* __restrict__ bound)
