@@ -609,6 +609,7 @@ def main():
                 stepfn()
             ph, _sent = drv.profile(False)
             mine = {k: v / 3 for k, v in zip(("xch_classify", "xch_totals_comm_and_host_wait", "xch_pack", "xch_records_comm", "xch_unpack", "dt_allreduce"), ph)}
+            mine["transport"], mine["exchanges_fallen_back_to_nccl_records"] = drv.transport()
         mine["np_owned"] = ctx.np_ - int(ctx.divinfo.npbper) - int(ctx.divinfo.npfper)
         mine["np_ghost"] = int(ctx.divinfo.npbper) + int(ctx.divinfo.npfper)
         phases = [None] * world
@@ -623,7 +624,7 @@ def main():
                "config": {"workload": WORKLOADS[a.workload][1],
                           "np_per_gpu": n, "nfluid": int(cd.cfg.casenfluid), "pre_steps": a.pre_steps, "timed_steps": [win["first_step"], win["first_step"] + a.steps],
                           "np_global": nglobal,
-                          "parallelism": ("single GPU" if world == 1 else "%d x-slabs of balanced work (fluid 1, boundary %g); per divide: ncclSend/ncclRecv of migrants + 2h halo copies with <=2 neighbours; per force evaluation: ncclAllReduce(max) of the dt maxima, both issued by the library on its own stream (%s); cuts re-balanced %d times with the measured kernel time per rank before warm-up (%s -> %s)" % (world, a.bound_weight, "python/torch.distributed exchange" if a.python_mgpu else "native transport, dsph_mgpu_step", a.balance_steps, cuts_initial, list(drv.cuts))),
+                          "parallelism": ("single GPU" if world == 1 else "%d x-slabs of balanced work (fluid 1, boundary %g); per divide: migrants + 2h halo copies to <=2 neighbours (%s); per force evaluation: ncclAllReduce(max) of the dt maxima, both issued by the library on its own stream (%s); cuts re-balanced %d times with the measured kernel time per rank before warm-up (%s -> %s)" % (world, a.bound_weight, ("ncclSend/ncclRecv" if a.python_mgpu or drv.transport()[0] != "peer_memory" else "written by the pack kernel into the neighbour's receive buffer over NVLink peer memory, 20-byte NCCL token"), "python/torch.distributed exchange" if a.python_mgpu else "native transport, dsph_mgpu_step", a.balance_steps, cuts_initial, list(drv.cuts))),
                           "l2": "working set (np*~230 B) is far larger than the 126 MB L2; no flush needed"},
                "roofline": roofline, "e2e": e2e, "gpu_launches": int(tm.kernel_launches), "clocks": win["clocks"],
                "timers_ms_per_step": {k: getattr(tm, k) / a.steps for k in ("nl_limits", "nl_presort", "nl_radixsort", "nl_cellbegin", "nl_sortdata",

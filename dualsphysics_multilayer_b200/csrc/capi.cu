@@ -182,6 +182,7 @@ int dsph_case_gauges(const char *dir,const char *casename,dsph_gauge *out,uint32
 }
 int dsph_celldiv_last_info(dsph_ctx *ctx,dsph_divinfo *info){ NEEDCTX(ctx); if(!info){ g_lasterror="Null argument."; return DSPH_ERR_ARG; } return Guard([&]{ ctx->eng->LastDivInfo(info); }); }
 int dsph_mgpu_sent_records(dsph_ctx *ctx,uint64_t *sent){ NEEDCTX(ctx); if(sent)*sent=ctx->eng->mgsentrecords; return DSPH_OK; }
+int dsph_mgpu_transport(dsph_ctx *ctx,int *direct,uint64_t *fallbacks){ NEEDCTX(ctx); if(direct)*direct=ctx->eng->mgdirect; if(fallbacks)*fallbacks=ctx->eng->mgdfallbacks; return DSPH_OK; }
 int dsph_mgpu_celldiv(dsph_ctx *ctx,dsph_divinfo *info){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgCellDivide(info); ctx->eng->FlushStepTimer(); }); }
 int dsph_mgpu_forces(dsph_ctx *ctx,int interstep,dsph_forceres *res){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgForces(interstep,res); }); }
 int dsph_mgpu_step(dsph_ctx *ctx,double *stepdt,dsph_forceres *res){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgStep(stepdt,res); }); }

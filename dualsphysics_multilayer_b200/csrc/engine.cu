@@ -209,6 +209,7 @@ void Engine::Allocate(unsigned capacity){
   if(nctmax*2+6>=0x7fffffffull)throw EngineError(DSPH_ERR_ARG,"The number of cells is too big.");
   maxnctt=unsigned(nctmax*2+6);
   keybits=KeyBits(maxnctt);
+  UpdateCellBound();
   DevAlloc(begincell,size_t(maxnctt)+8);
   DevAlloc(sufmin,size_t((maxnctt+SM_CHUNK-1)/SM_CHUNK)+8);
   DevAlloc(divparams,1); DevAlloc(limits,12); DevAlloc(fmax,1);
@@ -423,7 +424,7 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
     auto lim=[&](unsigned n,unsigned pini,unsigned *dst){ if(n){ ker_div_limits<<<std::min<unsigned>((n+B-1)/B,nsm),B,0,stm>>>(n,pini,dcell[cur],code[cur],k.domcellcode,dst); launches++; } };
     if(!blimok){ lim(npb1,0,limits); lim(npb2,npb1+npf1,limits); }
     lim(npf1,npb1,limits+6); lim(npf2,npb1+npf1+npb2,limits+6);
-    ker_div_prepare<<<1,1,0,stm>>>(limits,limits+6,blimok? 0: 1,k.domcells[0],k.domcells[1],k.domcells[2],unsigned(k.scelldiv),nptot,maxnctt,divparams); launches++;
+    ker_div_prepare<<<1,1,0,stm>>>(limits,limits+6,blimok? 0: 1,k.domcells[0],k.domcells[1],k.domcells[2],unsigned(k.scelldiv),nptot,effnctt,divparams); launches++;
     blimok=true;
   }
   NvtxNext("NL-PreSort");
@@ -432,21 +433,21 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
   if(nptot){ ker_div_presort<<<(nptot+B-1)/B,B,0,stm>>>(nptot,dcell[cur],code[cur],k.domcellcode,divparams,rs.keys[0]); launches++; }
   NvtxNext("NL-RadixSort");
   CUCHECK(cudaEventRecord(ev[3],stm));
-  const int sidx=RadixSortPairs(rs,nptot,keybits,1,stm,&launches);
+  const int sidx=RadixSortPairs(rs,nptot,effkeybits,1,stm,&launches);
   NvtxNext("NL-CellBegin");
   CUCHECK(cudaEventRecord(ev[4],stm));
   // ---- begin-cell table
-  CUCHECK(cudaMemsetAsync(begincell,0xff,size_t(maxnctt)*4,stm));
+  CUCHECK(cudaMemsetAsync(begincell,0xff,size_t(effnctt)*4,stm));
   {
     const unsigned nb=std::max(1u,(nptot+B-1)/B);
     ker_div_cellmark<<<nb,B,0,stm>>>(nptot,rs.keys[sidx],divparams,begincell); launches++;
-    const unsigned nchunks=(maxnctt+SM_CHUNK-1)/SM_CHUNK;
+    const unsigned nchunks=(effnctt+SM_CHUNK-1)/SM_CHUNK;
     ker_div_sufmin_chunks<<<nchunks,SM_THREADS,0,stm>>>(begincell,divparams,sufmin); launches++;
     if(nchunks>1){
       ker_div_sufmin_sums<<<1,SM_THREADS,0,stm>>>(sufmin,nchunks); launches++;
       ker_div_sufmin_apply<<<nchunks,SM_THREADS,0,stm>>>(begincell,divparams,sufmin); launches++;
     }
-    ker_div_maxpop<<<(maxnctt+255)/256,256,0,stm>>>(begincell,divparams); launches++;
+    ker_div_maxpop<<<(effnctt+255)/256,256,0,stm>>>(begincell,divparams); launches++;
     ker_div_counts<<<1,1,0,stm>>>(begincell,npb1+npb2,divparams); launches++;
   }
   NvtxNext("NL-SortData");
@@ -476,7 +477,7 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
   CUCHECK(cudaStreamSynchronize(stm));
   CUCHECK(cudaGetLastError());
   dp=hpin->dp;
-  if(dp.error)throw EngineError(DSPH_ERR_STATE,"The number of cells is too big for the allocated cell table.");
+  if(dp.error)throw EngineError(DSPH_ERR_STATE,(effnctt<maxnctt? "Particles outside the slab + halo columns of this rank (a divide without the slab exchange?).": "The number of cells is too big for the allocated cell table."));
   // DivideFull bookkeeping (S/JCellDivCpuSingle.cpp:299-305); this implementation always sorts every particle,
   // which yields the same order as the reference's fluid-only sort because the sort is stable.
   bool same=divok;
@@ -768,12 +769,25 @@ void Engine::Step(double *stepdt,dsph_forceres *res){
 // ------------------------------------------------------------------------------------------------
 // x-slab multi-GPU: pack / unpack of migrants and halo copies; transport is done by the caller (NCCL)
 // ------------------------------------------------------------------------------------------------
+// Cells a divide can meet: after the slab exchange every live particle of a rank lies in its columns + one halo width per side,
+// so the sort needs the key bits of that block only (N=8, DB(160 M): 3 radix passes instead of 4) and the cell table is cleared,
+// scanned and reduced over that block.  ker_div_prepare raises DivParams.error when the particles need more.
+void Engine::UpdateCellBound(){
+  effnctt=maxnctt;
+  if(mgpu && maxnctt){
+    const unsigned long long cols=std::min<unsigned long long>(k.domcells[0],(unsigned long long)(mgxhi-mgxlo)+2ull*MgHalo()+2ull);
+    const unsigned long long n=cols*k.domcells[1]*k.domcells[2]*2ull+6ull;
+    effnctt=unsigned(std::min<unsigned long long>(n,maxnctt));
+  }
+  effkeybits=KeyBits(effnctt);
+}
 void Engine::MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi){
   if(k.periactive)throw EngineError(DSPH_ERR_ARG,"x-slab decomposition cannot be combined with periodic boundaries yet.");
   if(nranks<1 || rank<0 || rank>=nranks || xlo>=xhi || xhi>k.domcells[0])throw EngineError(DSPH_ERR_ARG,"Invalid slab configuration.");
   if(nranks>1 && xhi-xlo<2u*MgHalo()+1u)throw EngineError(DSPH_ERR_ARG,"The slab is narrower than 2 halo widths + 1 cell.");
   mgpu=(nranks>1); mgrank=rank; mgnranks=nranks; mgxlo=xlo; mgxhi=xhi;
   dc.ghosts=(k.periactive||mgpu)? 1: 0;
+  UpdateCellBound();
   if(!mgpu)for(int i=0;i<3;i++)DevFree(mgscratch[i]);
   else if(!mgscratch[0]){                                            // (re-balancing calls MgConfig again: keep the scratch)
     DevAlloc(mgscratch[0],MG_CLASSES*((size_t(cap)+MG_BLOCK-1)/MG_BLOCK)+8);   // per-block class counts -> offsets
@@ -845,7 +859,21 @@ void Engine::MgPackAsync(void *sendleft,void *sendright){
     if(base && !sendbuf[d])throw EngineError(DSPH_ERR_ARG,"Null send buffer.");
     total+=base;
   }
-  if(total){ ker_mg_pack<<<nb,MG_BLOCK,0,stm>>>(a,(const unsigned char*)mgscratch[2],mgscratch[0],bases,sp,(char*)sendleft,(char*)sendright); launches++; }
+  if(total){ ker_mg_pack<false><<<nb,MG_BLOCK,0,stm>>>(a,(const unsigned char*)mgscratch[2],mgscratch[0],bases,sp,(char*)sendleft,(char*)sendright,MgDirect()); launches++; }
+}
+// direct transport: the pack kernel writes into the neighbours' receive buffers (peer memory) with the class bases taken from the
+// device-side totals; token = 10 words {to left: 4 totals, used; to right: 4 totals, used}
+void Engine::MgPackDirectAsync(void *peerleft,void *peerright,unsigned capleft,unsigned capright,unsigned *token){
+  const unsigned nb=std::max(1u,(np+MG_BLOCK-1)/MG_BLOCK);
+  MgArgs a; a.np=np; a.npb=npb; a.xlo=mgxlo; a.xhi=mgxhi; a.sd=MgHalo();
+  a.hasleft=(mgrank>0); a.hasright=(mgrank<mgnranks-1); a.domcellcode=k.domcellcode; a.dcell=dcell[cur]; a.code=code[cur];
+  MgPackArrays sp; sp.idp=idp[cur]; sp.code=code[cur]; sp.pos=pos[cur]; sp.velrhop=velrhop[cur];
+  sp.pospre=(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre? pospre[cur]: nullptr);
+  sp.aux=(cfg.tstep==DSPH_STEP_SYMPLECTIC? (haspre? velrhoppre[cur]: nullptr): velrhopm1[cur]);
+  sp.spstau=(sps? spstau[cur]: nullptr); sp.recbytes=MgRecordBytes();
+  MgDirect dr; dr.totals=mgscratch[1]; dr.capleft=capleft; dr.capright=capright; dr.token=token;
+  MgBases bases; memset(&bases,0,sizeof(bases));
+  ker_mg_pack<true><<<nb,MG_BLOCK,0,stm>>>(a,(const unsigned char*)mgscratch[2],mgscratch[0],bases,sp,(char*)peerleft,(char*)peerright,dr); launches++;
 }
 void Engine::MgPack(void *sendleft,void *sendright){
   MgPackAsync(sendleft,sendright);

@@ -23,6 +23,7 @@ struct HostPinned {
   unsigned limitsinit[12];
   unsigned scratch[8];
   unsigned mgtot[16];   // class totals of the slab exchange: [0..7] own (to left, to right), [8..15] announced by the neighbours
+  unsigned mgtoken[20]; // direct transport: own tokens [0..9], the neighbours' [10..14] from left, [15..19] from right
   unsigned probe;
 };
 
@@ -54,7 +55,9 @@ class Engine {
   RadixSortBuffers rs;
   unsigned *begincell=nullptr, *sufmin=nullptr, *limits=nullptr, *perilist=nullptr, *pericount=nullptr;
   DivParams *divparams=nullptr; DivParams dp={};
-  unsigned maxnctt=0; int keybits=0;
+  unsigned maxnctt=0; int keybits=0;          // capacity of the cell table (whole domain)
+  unsigned effnctt=0; int effkeybits=0;       // bound of the cells a divide can meet: the domain, or this rank's slab + halo (UpdateCellBound)
+  void UpdateCellBound();
   bool boundchanged=true, blimok=false, divok=false, dividefull=false, haspre=false, forcesok=false, steppending=false;
   unsigned lastcellmin[3]={0,0,0}, lastcellmax[3]={0,0,0};
   unsigned npfout_last=0; unsigned long long npout_total=0;
@@ -115,12 +118,19 @@ class Engine {
   unsigned MgHalo()const{ return unsigned(k.scelldiv)*(cfg.nn_on && cfg.nn_velgrad==DSPH_VELGRAD_SPH && cfg.tvisco!=DSPH_VISCO_ARTIFICIAL? 2u: 1u); }
   unsigned MgRecordBytes()const{ return sps? 112u: 88u; }   // pos 24, velrhop 16, pospre 24, velrhoppre|velrhopm1 16, idp 4, code 4 [+ SpsTau 24]
   void MgCount(unsigned counts[8]);
+  void MgPackDirectAsync(void *peerleft,void *peerright,unsigned capleft,unsigned capright,unsigned *token);
   void MgClassifyAsync(); void MgPackAsync(void *sendleft,void *sendright); void MgUnpackAsync(const unsigned counts[8],const void *recvleft,const void *recvright);
   double mgcostmark=0; double MgMeasuredCost();
   // native transport (mgpu_comm.cu): NCCL communicator of the slab group, exchange buffers, whole-step sequencing
   void *mgcomm=nullptr; bool mgcomm_own=false;
   char *mgsend[2]={nullptr,nullptr}, *mgrecv[2]={nullptr,nullptr}; size_t mgsendcap[2]={0,0}, mgrecvcap[2]={0,0};
   unsigned *mgcntdev=nullptr; double *mghistdev=nullptr; unsigned mghistcap=0;
+  // direct transport: receive buffers of this rank [from left|right][parity], the neighbours' buffers this rank writes to [left|right][parity]
+  int mgdirect=-1;                          // -1 not negotiated yet, 0 NCCL records, 1 peer memory
+  char *mgdrecv[2][2]={{nullptr,nullptr},{nullptr,nullptr}}; unsigned mgdcaprec=0;
+  char *mgdpeer[2][2]={{nullptr,nullptr},{nullptr,nullptr}}; unsigned mgdpeercap[2]={0,0}; bool mgdpeeripc[2]={false,false};
+  int mgdparity=0; unsigned long long mgdfallbacks=0;
+  void MgDirectSetup(); void MgDirectFree(); void MgExchangeDirect();
   std::vector<unsigned> mgcuts;             // cell columns of all the cuts (nranks+1), needed by the re-balancing
   unsigned long long mgsentrecords=0; double mgphase_ms[6]={0,0,0,0,0,0}; bool mgprofile=false;
   void SmallCopyAsync(void *dst,const void *src,size_t bytes);   // 4..128-byte transfers through a one-warp kernel (see engine.cu)

@@ -80,7 +80,10 @@ __global__ void __launch_bounds__(MG_BLOCK) ker_mg_classify(MgArgs a,unsigned ch
     blockcnt[size_t(threadIdx.x)*gridDim.x+blockIdx.x]=t;
   }
 }
-// grid = MG_CLASSES CTAs of 1024 threads: in-place exclusive scan of blockcnt[g*nb .. g*nb+nb), total[g]
+// grid = MG_CLASSES CTAs of 1024 threads: in-place exclusive scan of blockcnt[g*nb .. g*nb+nb), total[g].  Every thread owns
+// MG_SCAN_ITEMS consecutive counts, so one sweep of the CTA covers 16 384 block counts (22 M particles = 86 k counts: 6 sweeps; the
+// first version, one count per thread and sweep, spent 0.1 ms per exchange in its 84 serial sweeps).
+constexpr int MG_SCAN_ITEMS=16;
 __global__ void __launch_bounds__(1024) ker_mg_scanblocks(unsigned nb,unsigned* __restrict__ blockcnt,unsigned* __restrict__ total){
   __shared__ unsigned wsum[32];
   __shared__ unsigned carry;
@@ -88,10 +91,12 @@ __global__ void __launch_bounds__(1024) ker_mg_scanblocks(unsigned nb,unsigned* 
   const unsigned w=threadIdx.x>>5, lane=threadIdx.x&31;
   if(threadIdx.x==0)carry=0;
   __syncthreads();
-  for(unsigned base=0;base<nb;base+=1024){
-    const unsigned i=base+threadIdx.x;
-    const unsigned x=(i<nb? v[i]: 0u);
-    unsigned inc=x;
+  for(unsigned base=0;base<nb;base+=1024u*MG_SCAN_ITEMS){
+    const unsigned i0=base+threadIdx.x*MG_SCAN_ITEMS;
+    unsigned x[MG_SCAN_ITEMS]; unsigned sum=0;
+    #pragma unroll
+    for(int j=0;j<MG_SCAN_ITEMS;j++){ x[j]=(i0+j<nb? v[i0+j]: 0u); sum+=x[j]; }
+    unsigned inc=sum;
     #pragma unroll
     for(int d=1;d<32;d<<=1){ const unsigned y=__shfl_up_sync(0xffffffffu,inc,d); if(lane>=unsigned(d))inc+=y; }
     if(lane==31)wsum[w]=inc;
@@ -104,8 +109,9 @@ __global__ void __launch_bounds__(1024) ker_mg_scanblocks(unsigned nb,unsigned* 
     }
     __syncthreads();
     const unsigned c0=carry;
-    const unsigned excl=c0+(w? wsum[w-1]: 0u)+inc-x;
-    if(i<nb)v[i]=excl;
+    unsigned excl=c0+(w? wsum[w-1]: 0u)+inc-sum;
+    #pragma unroll
+    for(int j=0;j<MG_SCAN_ITEMS;j++){ if(i0+j<nb)v[i0+j]=excl; excl+=x[j]; }
     __syncthreads();
     if(threadIdx.x==1023)carry=c0+wsum[31];
     __syncthreads();
@@ -166,10 +172,32 @@ struct MgBases { unsigned v[MG_CLASSES]; };   // first record slot of each class
 
 // writes the records of all classes; migrants are converted locally: inside the halo band of the
 // neighbour they stay as ghosts (CODE_PERIODIC), otherwise they are dropped by the next sort (CODE_OUTIGNORE)
-__global__ void __launch_bounds__(MG_BLOCK) ker_mg_pack(MgArgs a,const unsigned char* __restrict__ flags,const unsigned* __restrict__ blockoff,
-  MgBases bases,MgPackArrays s,char* __restrict__ outleft,char* __restrict__ outright)
+// DIRECT (transport through peer memory, mgpu_comm.cu): outleft / outright are the receive buffers of the neighbours, mapped into
+// this GPU's address space (NVLink peer access / CUDA IPC); the class bases come from the class totals the scan left on the device,
+// so no host round trip separates classification and packing.  Thread 0 of block 0 writes the token {4 totals, used} per side that
+// travels to the neighbour after this kernel (NCCL, 20 bytes): its arrival tells the neighbour that the records have landed.  When a
+// side's records would not fit the neighbour's buffer (capleft / capright records) the kernel changes nothing and sets used=0: both
+// ends then fall back to packing into a local buffer and ncclSend/ncclRecv for this exchange.
+struct MgDirect { const unsigned *totals; unsigned capleft, capright; unsigned *token; };
+template<bool DIRECT> __global__ void __launch_bounds__(MG_BLOCK) ker_mg_pack(MgArgs a,const unsigned char* __restrict__ flags,const unsigned* __restrict__ blockoff,
+  MgBases bases,MgPackArrays s,char* __restrict__ outleft,char* __restrict__ outright,MgDirect dr)
 {
   __shared__ unsigned wcnt[MG_CLASSES][MG_BLOCK/32];
+  if(DIRECT){
+    unsigned tot[MG_CLASSES];
+    #pragma unroll
+    for(int g=0;g<MG_CLASSES;g++)tot[g]=dr.totals[g];
+    const unsigned nl=tot[0]+tot[1]+tot[2]+tot[3], nr=tot[4]+tot[5]+tot[6]+tot[7];
+    const bool fits=(nl<=dr.capleft && nr<=dr.capright);
+    if(blockIdx.x==0 && threadIdx.x==0){
+      #pragma unroll
+      for(int g=0;g<4;g++){ dr.token[g]=tot[g]; dr.token[5+g]=tot[4+g]; }
+      dr.token[4]=dr.token[9]=(fits? 1u: 0u);
+    }
+    if(!fits)return;
+    bases.v[0]=0; bases.v[1]=tot[0]; bases.v[2]=tot[0]+tot[1]; bases.v[3]=tot[0]+tot[1]+tot[2];
+    bases.v[4]=0; bases.v[5]=tot[4]; bases.v[6]=tot[4]+tot[5]; bases.v[7]=tot[4]+tot[5]+tot[6];
+  }
   const unsigned p=blockIdx.x*MG_BLOCK+threadIdx.x;
   const unsigned f=(p<a.np? flags[p]: 0u);
   const unsigned w=threadIdx.x>>5, lane=threadIdx.x&31;

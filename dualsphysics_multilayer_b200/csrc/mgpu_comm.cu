@@ -21,6 +21,8 @@
 #include <algorithm>
 #include <cmath>
 #include <chrono>
+#include <cstdlib>
+#include <unistd.h>
 
 namespace dsph {
 
@@ -115,6 +117,7 @@ void Engine::MgCommAbort(){
 void Engine::MgCommDestroy(){
   if(mgcomm && mgcomm_own && g_nccl.handle){ cudaStreamSynchronize(stm); g_nccl.CommDestroy((ncclComm_t)mgcomm); }
   mgcomm=nullptr; mgcomm_own=false;
+  MgDirectFree();
   for(int d=0;d<2;d++){ if(mgsend[d]){ cudaFree(mgsend[d]); mgsend[d]=nullptr; mgsendcap[d]=0; } if(mgrecv[d]){ cudaFree(mgrecv[d]); mgrecv[d]=nullptr; mgrecvcap[d]=0; } }
   if(mgcntdev){ cudaFree(mgcntdev); mgcntdev=nullptr; }
   if(mghistdev){ cudaFree(mghistdev); mghistdev=nullptr; mghistcap=0; }
@@ -128,12 +131,167 @@ void Engine::MgConfigCuts(int rank,int nranks,const unsigned *cuts){
 }
 
 // ------------------------------------------------------------------------------------------------
+// direct transport: records are written by the pack kernel straight into the neighbour's receive buffer over NVLink
+// ------------------------------------------------------------------------------------------------
+// Negotiated once per communicator (collective, first exchange).  Every rank allocates two receive buffers per side (alternating
+// per exchange), tells its <= 2 neighbours where they are {host, pid, device, pointers, CUDA IPC handles, capacity} with ncclSend /
+// ncclRecv, and maps the neighbours' buffers: the pointer itself + cudaDeviceEnablePeerAccess when the neighbour is a thread of this
+// process (bin/dsph_b200 -mgpu:N), cudaIpcOpenMemHandle when it is another process (torchrun).  An all-reduce(min) of "mapping
+// worked" decides for the whole group; DSPH_MGPU_DIRECT=0 keeps the ncclSend/ncclRecv transport of the records.
+// Why two buffers: a rank may pack exchange k+1 while its neighbour still unpacks exchange k; the token of exchange k+1 that the
+// neighbour sends after that unpack (stream order) is received before this rank packs exchange k+2 into the first buffer again.
+namespace {
+struct MgHello {
+  unsigned long long host; int pid; int device; unsigned caprec; unsigned recbytes; unsigned valid; unsigned pad;
+  unsigned long long ptr[2][2];
+  cudaIpcMemHandle_t handle[2][2];
+};
+unsigned long long HostHash(){
+  char name[256]; memset(name,0,sizeof(name)); gethostname(name,sizeof(name)-1);
+  unsigned long long h=1469598103934665603ull; for(const char *c=name;*c;c++){ h^=(unsigned char)*c; h*=1099511628211ull; }
+  return h;
+}
+}
+void Engine::MgDirectFree(){
+  for(int d=0;d<2;d++)for(int q=0;q<2;q++){
+    if(mgdpeer[d][q] && mgdpeeripc[d])cudaIpcCloseMemHandle(mgdpeer[d][q]);
+    mgdpeer[d][q]=nullptr;
+    if(mgdrecv[d][q]){ cudaFree(mgdrecv[d][q]); mgdrecv[d][q]=nullptr; }
+  }
+  mgdpeeripc[0]=mgdpeeripc[1]=false; mgdpeercap[0]=mgdpeercap[1]=0; mgdcaprec=0; mgdirect=-1; mgdparity=0;
+}
+void Engine::MgDirectSetup(){
+  if(mgdirect>=0)return;
+  NcclApi &N=Nccl();
+  ncclComm_t comm=(ncclComm_t)mgcomm;
+  const int left=(mgrank>0? mgrank-1: -1), right=(mgrank<mgnranks-1? mgrank+1: -1);
+  const char *env=getenv("DSPH_MGPU_DIRECT");
+  unsigned ok=(env && atoi(env)==0? 0u: 1u);
+  MgHello me; memset(&me,0,sizeof(me));
+  me.host=HostHash(); me.pid=int(getpid()); me.device=device; me.recbytes=MgRecordBytes();
+  if(ok){
+    const char *ecap=getenv("DSPH_MGPU_DIRECT_CAP");        // records per buffer (tests: a small value forces the fall-back path)
+    mgdcaprec=(ecap && atoi(ecap)>0? unsigned(atoi(ecap)): cap/4u+1024u);
+    for(int d=0;d<2 && ok;d++)for(int q=0;q<2 && ok;q++){
+      if(cudaMalloc((void**)&mgdrecv[d][q],size_t(mgdcaprec)*me.recbytes)!=cudaSuccess){ cudaGetLastError(); mgdrecv[d][q]=nullptr; ok=0; break; }
+      me.ptr[d][q]=(unsigned long long)(uintptr_t)mgdrecv[d][q];
+      if(cudaIpcGetMemHandle(&me.handle[d][q],mgdrecv[d][q])!=cudaSuccess){ cudaGetLastError(); ok=0; }
+    }
+    me.caprec=mgdcaprec;
+  }
+  me.valid=ok;
+  // hello to / from the neighbours (device staging: [0] mine, [1] left's, [2] right's)
+  MgHello *dev=nullptr; CUCHECK2(cudaMalloc((void**)&dev,3*sizeof(MgHello)));
+  CUCHECK2(cudaMemsetAsync(dev,0,3*sizeof(MgHello),stm));
+  CUCHECK2(cudaMemcpyAsync(dev,&me,sizeof(me),cudaMemcpyHostToDevice,stm));
+  NCCLCHECK(N.GroupStart());
+  if(left>=0){  NCCLCHECK(N.Send(dev,sizeof(MgHello),ncclUint8,left,comm,stm));  NCCLCHECK(N.Recv(dev+1,sizeof(MgHello),ncclUint8,left,comm,stm)); }
+  if(right>=0){ NCCLCHECK(N.Send(dev,sizeof(MgHello),ncclUint8,right,comm,stm)); NCCLCHECK(N.Recv(dev+2,sizeof(MgHello),ncclUint8,right,comm,stm)); }
+  NCCLCHECK(N.GroupEnd());
+  MgHello nb[2];
+  CUCHECK2(cudaMemcpyAsync(nb,dev+1,2*sizeof(MgHello),cudaMemcpyDeviceToHost,stm));
+  CUCHECK2(cudaStreamSynchronize(stm));
+  // map: this rank is the RIGHT neighbour of its left neighbour (writes its "from right" buffers) and vice versa
+  for(int d=0;d<2;d++){
+    const int peer=(d==0? left: right);
+    if(peer<0)continue;
+    const MgHello &h=nb[d];
+    const int theirside=(d==0? 1: 0);
+    if(!ok || !h.valid || h.host!=me.host || h.recbytes!=me.recbytes){ ok=0; continue; }
+    mgdpeercap[d]=h.caprec;
+    if(h.pid==me.pid){
+      if(h.device!=device){
+        int can=0; cudaDeviceCanAccessPeer(&can,device,h.device);
+        if(!can){ ok=0; continue; }
+        const cudaError_t e=cudaDeviceEnablePeerAccess(h.device,0);
+        if(e!=cudaSuccess && e!=cudaErrorPeerAccessAlreadyEnabled){ ok=0; cudaGetLastError(); continue; }
+        cudaGetLastError();
+      }
+      for(int q=0;q<2;q++)mgdpeer[d][q]=(char*)(uintptr_t)h.ptr[theirside][q];
+      mgdpeeripc[d]=false;
+    }
+    else{
+      mgdpeeripc[d]=true;
+      for(int q=0;q<2;q++){
+        void *p=nullptr;
+        if(cudaIpcOpenMemHandle(&p,h.handle[theirside][q],cudaIpcMemLazyEnablePeerAccess)!=cudaSuccess){ cudaGetLastError(); ok=0; p=nullptr; }
+        mgdpeer[d][q]=(char*)p;
+      }
+    }
+  }
+  // the whole group uses the same transport
+  unsigned *flag=(unsigned*)dev;
+  CUCHECK2(cudaMemcpyAsync(flag,&ok,sizeof(unsigned),cudaMemcpyHostToDevice,stm));
+  NCCLCHECK(N.AllReduce(flag,flag,1,ncclUint32,ncclMin,comm,stm));
+  unsigned all=0;
+  CUCHECK2(cudaMemcpyAsync(&all,flag,sizeof(unsigned),cudaMemcpyDeviceToHost,stm));
+  CUCHECK2(cudaStreamSynchronize(stm));
+  cudaFree(dev);
+  if(!all){ const int keep=0; MgDirectFree(); mgdirect=keep; return; }
+  mgdirect=1; mgdparity=0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // halo + migrant exchange, one host synchronisation
 // ------------------------------------------------------------------------------------------------
+// Peer-memory transport (default, MgDirectSetup):
+//   classify + scan (2 kernels) -> pack kernel writing into the neighbours' buffers (bases from the device-side totals)
+//   -> ncclSend/Recv of the 20-byte tokens {4 totals, used} = "records landed" -> ONE host synchronisation -> unpack kernels.
+void Engine::MgExchangeDirect(){
+  NcclApi &N=Nccl();
+  ncclComm_t comm=(ncclComm_t)mgcomm;
+  const int left=(mgrank>0? mgrank-1: -1), right=(mgrank<mgnranks-1? mgrank+1: -1);
+  const int q=mgdparity; mgdparity^=1;
+  Stopwatch sw(mgprofile,stm);
+  MgClassifyAsync();
+  sw.Lap(mgphase_ms[0]);
+  MgPackDirectAsync(mgdpeer[0][q],mgdpeer[1][q],(left>=0? mgdpeercap[0]: 0xffffffffu),(right>=0? mgdpeercap[1]: 0xffffffffu),mgcntdev);
+  sw.Lap(mgphase_ms[2]);
+  NCCLCHECK(N.GroupStart());
+  if(left>=0){  NCCLCHECK(N.Send(mgcntdev,5,ncclUint32,left,comm,stm));    NCCLCHECK(N.Recv(mgcntdev+16,5,ncclUint32,left,comm,stm)); }
+  if(right>=0){ NCCLCHECK(N.Send(mgcntdev+5,5,ncclUint32,right,comm,stm)); NCCLCHECK(N.Recv(mgcntdev+21,5,ncclUint32,right,comm,stm)); }
+  NCCLCHECK(N.GroupEnd());
+  SmallCopyAsync(hpind->mgtoken,mgcntdev,10*sizeof(unsigned));
+  SmallCopyAsync(hpind->mgtoken+10,mgcntdev+16,10*sizeof(unsigned));
+  CUCHECK2(cudaStreamSynchronize(stm));                           // the only host wait of the exchange
+  unsigned rcv[8]; bool rdirect[2];
+  for(int g=0;g<4;g++){ mgcounts[g]=hpin->mgtoken[g]; mgcounts[4+g]=hpin->mgtoken[5+g]; rcv[g]=hpin->mgtoken[10+g]; rcv[4+g]=hpin->mgtoken[15+g]; }
+  const bool mydirect=(hpin->mgtoken[4]!=0);
+  rdirect[0]=(left<0 || hpin->mgtoken[14]!=0); rdirect[1]=(right<0 || hpin->mgtoken[19]!=0);
+  if(left<0)for(int g=0;g<4;g++)rcv[g]=0;
+  if(right<0)for(int g=0;g<4;g++)rcv[4+g]=0;
+  sw.Lap(mgphase_ms[1]);
+  const size_t rb=MgRecordBytes();
+  const size_t nsend[2]={size_t(mgcounts[0])+mgcounts[1]+mgcounts[2]+mgcounts[3],size_t(mgcounts[4])+mgcounts[5]+mgcounts[6]+mgcounts[7]};
+  const size_t nrecv[2]={size_t(rcv[0])+rcv[1]+rcv[2]+rcv[3],size_t(rcv[4])+rcv[5]+rcv[6]+rcv[7]};
+  const void *src[2]={mgdrecv[0][q],mgdrecv[1][q]};
+  if(!mydirect || !rdirect[0] || !rdirect[1]){
+    // fall-back of this exchange for the sides whose records did not fit: local pack + ncclSend / ncclRecv
+    mgdfallbacks++;
+    if(!mydirect){
+      for(int d=0;d<2;d++)GrowBuffer(mgsend[d],mgsendcap[d],std::max<size_t>(nsend[d],1)*rb);
+      mgcounted=true;
+      MgPackAsync(mgsend[0],mgsend[1]);
+    }
+    for(int d=0;d<2;d++)if(!rdirect[d]){ GrowBuffer(mgrecv[d],mgrecvcap[d],std::max<size_t>(nrecv[d],1)*rb); src[d]=mgrecv[d]; }
+    NCCLCHECK(N.GroupStart());
+    if(left>=0){  if(!mydirect && nsend[0])NCCLCHECK(N.Send(mgsend[0],nsend[0]*rb,ncclUint8,left,comm,stm));   if(!rdirect[0] && nrecv[0])NCCLCHECK(N.Recv(mgrecv[0],nrecv[0]*rb,ncclUint8,left,comm,stm)); }
+    if(right>=0){ if(!mydirect && nsend[1])NCCLCHECK(N.Send(mgsend[1],nsend[1]*rb,ncclUint8,right,comm,stm));  if(!rdirect[1] && nrecv[1])NCCLCHECK(N.Recv(mgrecv[1],nrecv[1]*rb,ncclUint8,right,comm,stm)); }
+    NCCLCHECK(N.GroupEnd());
+  }
+  mgcounted=false;
+  sw.Lap(mgphase_ms[3]);
+  MgUnpackAsync(rcv,src[0],src[1]);
+  sw.Lap(mgphase_ms[4]);
+  mgsentrecords+=nsend[0]+nsend[1];
+}
+
 void Engine::MgExchange(){
   if(!mgpu)return;
   if(!mgcomm)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_exchange needs dsph_mgpu_comm_init (or dsph_mgpu_comm_attach) first.");
   CUCHECK2(cudaSetDevice(device));
+  MgDirectSetup();
+  if(mgdirect==1){ MgExchangeDirect(); return; }
   NcclApi &N=Nccl();
   ncclComm_t comm=(ncclComm_t)mgcomm;
   const int left=(mgrank>0? mgrank-1: -1), right=(mgrank<mgnranks-1? mgrank+1: -1);

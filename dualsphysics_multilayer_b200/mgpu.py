@@ -306,6 +306,12 @@ class NativeSlabDriver:
         self.ctx.lib.check(self.ctx.lib.fn("mgpu_sent_records")(self.ctx.h, C.byref(sent)))
         return int(sent.value)
 
+    def transport(self):
+        """("peer_memory" | "nccl_sendrecv" | "unset", exchanges that fell back to ncclSend/ncclRecv)."""
+        d = C.c_int(); fb = C.c_uint64()
+        self.ctx.lib.check(self.ctx.lib.fn("mgpu_transport")(self.ctx.h, C.byref(d), C.byref(fb)))
+        return {1: "peer_memory", 0: "nccl_sendrecv"}.get(int(d.value), "unset"), int(fb.value)
+
     def update_divinfo(self):
         """DivInfo of the last divide (dsph_mgpu_step runs its own divides)."""
         info = capi.DivInfo()

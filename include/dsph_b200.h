@@ -258,6 +258,12 @@ int dsph_mgpu_column_counts(dsph_ctx *ctx,uint32_t *fluid,uint32_t *bound,uint32
  *      a 128-byte ncclUniqueId that rank 0 obtained with dsph_mgpu_unique_id and distributed by any means), halo exchange and
  *      migration are one call (dsph_mgpu_exchange: classify -> class totals to the neighbours -> ONE host wait -> pack ->
  *      ncclSend/ncclRecv of the records -> unpack, all on the context's stream), and
+ *      Default transport of the records = PEER MEMORY: at the first exchange the ranks trade the addresses / CUDA IPC handles of
+ *      their receive buffers and from then on the pack kernel writes the records straight into the neighbour's buffer over NVLink
+ *      (class bases from the device-side totals: no host wait between classification and packing); a 20-byte ncclSend/ncclRecv
+ *      token {totals, used} after the kernel announces "records landed", then the ONE host wait, then unpack.  Records that do
+ *      not fit the neighbour's buffer fall back to ncclSend/ncclRecv for that exchange; DSPH_MGPU_DIRECT=0 (environment) or GPUs
+ *      without peer access keep the ncclSend/ncclRecv transport altogether (dsph_mgpu_transport tells which is active).
  *        dsph_mgpu_celldiv = dsph_mgpu_exchange + dsph_celldiv_run(updateperiodic=0)
  *        dsph_mgpu_forces  = dsph_forces_launch + ncclAllReduce(max) of the four maxima + dsph_forces_finish
  *        dsph_mgpu_step    = dsph_step with those two in place of RunCellDivide / Interaction_Forces (S/JSphGpuSingle.cpp:548-596)
@@ -281,6 +287,9 @@ double dsph_mgpu_measured_cost(dsph_ctx *ctx);
  * records send/recv, unpack, dt all-reduce [ms accumulated since the last call]; records sent so far */
 int dsph_mgpu_profile(dsph_ctx *ctx,int on,double phases_ms[6],uint64_t *sent_records);
 int dsph_mgpu_sent_records(dsph_ctx *ctx,uint64_t *sent_records);
+/* *direct: 1 = records travel through peer memory, 0 = ncclSend/ncclRecv, -1 = not negotiated yet (before the first exchange);
+ * *fallbacks: exchanges of this rank that used ncclSend/ncclRecv for a side because the records did not fit the peer buffer */
+int dsph_mgpu_transport(dsph_ctx *ctx,int *direct,uint64_t *fallbacks);
 /* the dsph_divinfo of the most recent divide (dsph_step / dsph_mgpu_step run their own divides) */
 int dsph_celldiv_last_info(dsph_ctx *ctx,dsph_divinfo *info);
 /* 1 when the ring kernels (variants 9, 10, multiphase ring) can run on this device/driver (shared-window probe at creation);

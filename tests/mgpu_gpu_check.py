@@ -47,7 +47,8 @@ def main():
         sys.exit(1)
     own = drv.owned()
     gathered = [None] * world
-    dist.all_gather_object(gathered, dict(t=t, idp=own["idp"], pos=own["pos"], velrhop=own["velrhop"], sent=drv.sent_records))
+    transport = drv.transport() if native else ("python", 0)
+    dist.all_gather_object(gathered, dict(t=t, idp=own["idp"], pos=own["pos"], velrhop=own["velrhop"], sent=drv.sent_records, transport=transport))
     ok = True
     if rank == 0:
         ref = dsph.create_context(cd, device=local)
@@ -66,6 +67,12 @@ def main():
         dts = [abs(g["t"] - tr) / tr for g in gathered]
         print("MGPU_CHECK world=%d np=%d steps=%d same_set=%s max|dpos|=%.3e relL2(velrhop)=%.3e dt_rel=%s sent=%s cuts=%s" % (world, cd.np_, nsteps, same_set, dpos, dvr, ["%.1e" % d for d in dts], [g["sent"] for g in gathered], cuts))
         ok = same_set and dpos < 1e-7 and dvr < 1e-5 and max(dts) < 1e-6
+        print("MGPU_TRANSPORT", [g["transport"] for g in gathered])
+        want = os.environ.get("DSPH_MGPU_EXPECT")                      # "peer_memory" | "nccl_sendrecv" | "fallback"
+        if want == "fallback":
+            ok = ok and all(g["transport"][0] == "peer_memory" and g["transport"][1] > 0 for g in gathered)
+        elif want:
+            ok = ok and all(g["transport"][0] == want and g["transport"][1] == 0 for g in gathered)
         print("MGPU_CHECK", "PASS" if ok else "FAIL")
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -273,6 +273,26 @@ def test_gpu_two_slabs_equal_single_gpu(kind):
     assert "MGPU_CHECK PASS" in r.stdout, r.stdout[-3000:]
 
 
+@pytest.mark.parametrize("mode", ["peer_memory", "nccl_sendrecv", "fallback"])
+def test_gpu_two_slabs_record_transports(mode):
+    """The three ways the halo / migrant records travel give the single-GPU result: written by the pack kernel into the neighbour's
+    buffer (peer memory, default), ncclSend/ncclRecv (DSPH_MGPU_DIRECT=0), and the per-exchange fall-back when the records do not
+    fit the peer buffer (forced with a 64-record buffer)."""
+    import subprocess, sys, os, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    env = dict(os.environ, DSPH_MGPU_EXPECT=mode)
+    if mode == "nccl_sendrecv":
+        env["DSPH_MGPU_DIRECT"] = "0"
+    if mode == "fallback":
+        env["DSPH_MGPU_DIRECT_CAP"] = "64"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tests", "mgpu_gpu_check.py"), "200000", "10", "dambreak@rebalance"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
+    assert "MGPU_CHECK PASS" in r.stdout, r.stdout[-3000:]
+
+
 def _matrix():
     """Option combinations across kernel x viscosity x DDT x shifting x step algorithm x cell mode (+ multiphase variants)."""
     combos = []
