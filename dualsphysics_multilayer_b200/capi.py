@@ -182,6 +182,7 @@ class SphLib:
             f("mgpu_profile", C.c_int, vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64))
             f("mgpu_sent_records", C.c_int, vp, C.POINTER(C.c_uint64))
             f("mgpu_transport", C.c_int, vp, C.POINTER(C.c_int), C.POINTER(C.c_uint64))
+            f("mgpu_balanced_cuts", C.c_int, C.POINTER(C.c_double), C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_uint32))
             f("celldiv_last_info", C.c_int, vp, C.POINTER(DivInfo))
         if prefix == "dsph_":
             f("particles_set_boundnormals", C.c_int, vp, C.POINTER(C.c_float), C.c_uint32)

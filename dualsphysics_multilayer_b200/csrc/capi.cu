@@ -190,6 +190,11 @@ int dsph_mgpu_rebalance(dsph_ctx *ctx,double bound_weight,double rank_cost,int *
   NEEDCTX(ctx);
   return Guard([&]{ const bool ch=ctx->eng->MgRebalance(bound_weight,rank_cost,cuts_out); if(changed)*changed=(ch? 1: 0); });
 }
+int dsph_mgpu_balanced_cuts(const double *column_work,uint32_t ncol,int nranks,uint32_t minwidth,uint32_t *cuts_out){
+  if(!column_work || !cuts_out || nranks<1 || !minwidth){ g_lasterror="Invalid argument."; return DSPH_ERR_ARG; }
+  if((unsigned long long)nranks*minwidth>ncol){ g_lasterror="Too many ranks for the cell columns (minimum slab width)."; return DSPH_ERR_ARG; }
+  return Guard([&]{ const std::vector<unsigned> c=MgBalancedCuts(std::vector<double>(column_work,column_work+ncol),nranks,minwidth); for(int r=0;r<=nranks;r++)cuts_out[r]=c[r]; });
+}
 double dsph_mgpu_measured_cost(dsph_ctx *ctx){ return (ctx&&ctx->eng)? ctx->eng->MgMeasuredCost(): 0; }
 int dsph_mgpu_profile(dsph_ctx *ctx,int on,double phases_ms[6],uint64_t *sent_records){
   NEEDCTX(ctx); Engine *e=ctx->eng;

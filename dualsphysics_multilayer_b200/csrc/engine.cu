@@ -875,6 +875,9 @@ void Engine::MgPackDirectAsync(void *peerleft,void *peerright,unsigned capleft,u
   MgBases bases; memset(&bases,0,sizeof(bases));
   ker_mg_pack<true><<<nb,MG_BLOCK,0,stm>>>(a,(const unsigned char*)mgscratch[2],mgscratch[0],bases,sp,(char*)peerleft,(char*)peerright,dr); launches++;
 }
+void Engine::MgPushAsync(const void *srcleft,void *peerleft,const void *srcright,void *peerright,const unsigned *token){
+  ker_mg_push<<<numsm*8,256,0,stm>>>((const uint4*)srcleft,(uint4*)peerleft,(const uint4*)srcright,(uint4*)peerright,token,MgRecordBytes()); launches++;
+}
 void Engine::MgPack(void *sendleft,void *sendright){
   MgPackAsync(sendleft,sendright);
   CUCHECK(cudaStreamSynchronize(stm));

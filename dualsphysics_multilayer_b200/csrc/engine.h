@@ -118,6 +118,7 @@ class Engine {
   unsigned MgHalo()const{ return unsigned(k.scelldiv)*(cfg.nn_on && cfg.nn_velgrad==DSPH_VELGRAD_SPH && cfg.tvisco!=DSPH_VISCO_ARTIFICIAL? 2u: 1u); }
   unsigned MgRecordBytes()const{ return sps? 112u: 88u; }   // pos 24, velrhop 16, pospre 24, velrhoppre|velrhopm1 16, idp 4, code 4 [+ SpsTau 24]
   void MgCount(unsigned counts[8]);
+  void MgPushAsync(const void *srcleft,void *peerleft,const void *srcright,void *peerright,const unsigned *token);
   void MgPackDirectAsync(void *peerleft,void *peerright,unsigned capleft,unsigned capright,unsigned *token);
   void MgClassifyAsync(); void MgPackAsync(void *sendleft,void *sendright); void MgUnpackAsync(const unsigned counts[8],const void *recvleft,const void *recvright);
   double mgcostmark=0; double MgMeasuredCost();
@@ -128,6 +129,7 @@ class Engine {
   // direct transport: receive buffers of this rank [from left|right][parity], the neighbours' buffers this rank writes to [left|right][parity]
   int mgdirect=-1;                          // -1 not negotiated yet, 0 NCCL records, 1 peer memory
   char *mgdrecv[2][2]={{nullptr,nullptr},{nullptr,nullptr}}; unsigned mgdcaprec=0;
+  char *mgdsend[2]={nullptr,nullptr};       // local staging of the packed records (left, right), mgdcaprec records each
   char *mgdpeer[2][2]={{nullptr,nullptr},{nullptr,nullptr}}; unsigned mgdpeercap[2]={0,0}; bool mgdpeeripc[2]={false,false};
   int mgdparity=0; unsigned long long mgdfallbacks=0;
   void MgDirectSetup(); void MgDirectFree(); void MgExchangeDirect();

@@ -22,21 +22,16 @@ from . import capi
 
 
 def balanced_cuts(colcount: np.ndarray, nranks: int, minwidth: int) -> list:
-    """Cut positions (cell columns) so that every slab owns about the same number of particles; slabs keep at least
-    `minwidth` columns.  Returns nranks+1 increasing column indices, first 0 and last len(colcount)."""
-    ncol = len(colcount)
-    if nranks * minwidth > ncol:
-        raise ValueError("too many ranks for %d cell columns (minimum slab width %d)" % (ncol, minwidth))
-    cum = np.concatenate([[0], np.cumsum(colcount, dtype=np.float64)])
-    cuts = [0]
-    for r in range(1, nranks):
-        target = cum[-1] * r / nranks
-        c = int(np.searchsorted(cum, target))
-        c = max(c, cuts[-1] + minwidth)
-        c = min(c, ncol - (nranks - r) * minwidth)
-        cuts.append(c)
-    cuts.append(ncol)
-    return cuts
+    """Cut positions (cell columns) that minimise the work of the busiest slab; slabs keep at least `minwidth` columns.
+    Returns nranks+1 increasing column indices, first 0 and last len(colcount) (dsph_mgpu_balanced_cuts: host code of the library)."""
+    col = np.ascontiguousarray(colcount, dtype=np.float64)
+    if nranks * minwidth > len(col):
+        raise ValueError("too many ranks for %d cell columns (minimum slab width %d)" % (len(col), minwidth))
+    from . import lib as _getlib
+    lib = _getlib()
+    out = (C.c_uint32 * (nranks + 1))()
+    lib.check(lib.fn("mgpu_balanced_cuts")(col.ctypes.data_as(C.POINTER(C.c_double)), len(col), int(nranks), int(minwidth), out))
+    return [int(v) for v in out]
 
 
 class _CudaView:

@@ -259,7 +259,7 @@ int dsph_mgpu_column_counts(dsph_ctx *ctx,uint32_t *fluid,uint32_t *bound,uint32
  *      migration are one call (dsph_mgpu_exchange: classify -> class totals to the neighbours -> ONE host wait -> pack ->
  *      ncclSend/ncclRecv of the records -> unpack, all on the context's stream), and
  *      Default transport of the records = PEER MEMORY: at the first exchange the ranks trade the addresses / CUDA IPC handles of
- *      their receive buffers and from then on the pack kernel writes the records straight into the neighbour's buffer over NVLink
+ *      their receive buffers and from then on the records go from the pack kernel (local staging) into the neighbour's buffer over NVLink with one coalesced copy kernel
  *      (class bases from the device-side totals: no host wait between classification and packing); a 20-byte ncclSend/ncclRecv
  *      token {totals, used} after the kernel announces "records landed", then the ONE host wait, then unpack.  Records that do
  *      not fit the neighbour's buffer fall back to ncclSend/ncclRecv for that exchange; DSPH_MGPU_DIRECT=0 (environment) or GPUs
@@ -283,6 +283,9 @@ int dsph_mgpu_forces(dsph_ctx *ctx,int interstep,dsph_forceres *res);
 int dsph_mgpu_step(dsph_ctx *ctx,double *stepdt,dsph_forceres *res);
 int dsph_mgpu_rebalance(dsph_ctx *ctx,double bound_weight,double rank_cost,int *changed,uint32_t *cuts_out);
 double dsph_mgpu_measured_cost(dsph_ctx *ctx);
+/* host only (no device, no context): nranks+1 cut columns that minimise the work of the busiest slab for the given work per cell
+ * column, every slab at least minwidth columns wide (what dsph_mgpu_rebalance uses).  DSPH_ERR_ARG when nranks*minwidth > ncol. */
+int dsph_mgpu_balanced_cuts(const double *column_work,uint32_t ncol,int nranks,uint32_t minwidth,uint32_t *cuts_out);
 /* per-phase host timers of the exchange (adds stream synchronisations while on): classify, totals exchange + host wait, pack,
  * records send/recv, unpack, dt all-reduce [ms accumulated since the last call]; records sent so far */
 int dsph_mgpu_profile(dsph_ctx *ctx,int on,double phases_ms[6],uint64_t *sent_records);

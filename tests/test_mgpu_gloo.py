@@ -112,5 +112,24 @@ def test_balanced_cuts():
     assert cuts[0] == 0 and cuts[-1] == 40 and all(b - a >= 3 for a, b in zip(cuts, cuts[1:]))
     owned = [col[a:b].sum() for a, b in zip(cuts, cuts[1:])]
     assert max(owned) <= 1.6 * (col.sum() / 4)
+    # the busiest slab is as light as any admissible partition allows (brute force over all cut positions)
+    import itertools
+    rng = np.random.default_rng(5)
+    for ncol, nranks, minwidth in ((12, 3, 2), (14, 4, 3), (16, 4, 1), (20, 3, 5)):
+        for _ in range(6):
+            col = rng.integers(0, 50, ncol).astype(np.float64)
+            col[rng.integers(0, ncol)] += 200
+            cuts = mgpu.balanced_cuts(col, nranks, minwidth)
+            assert cuts[0] == 0 and cuts[-1] == ncol and all(b - a >= minwidth for a, b in zip(cuts, cuts[1:]))
+            got = max(col[a:b].sum() for a, b in zip(cuts, cuts[1:]))
+            best = min(max(col[a:b].sum() for a, b in zip((0,) + c, c + (ncol,)))
+                       for c in itertools.combinations(range(1, ncol), nranks - 1)
+                       if all(b - a >= minwidth for a, b in zip((0,) + c, c + (ncol,))))
+            assert got <= best * (1 + 1e-9) + 1e-9, (col, cuts, got, best)
+    # DB(160 M)-like: 127 equal fluid columns + a long light tail over 8 slabs -> no slab carries a column more than needed
+    col = np.concatenate([np.full(127, 1.0), np.full(449, 0.02)])
+    cuts = mgpu.balanced_cuts(col, 8, 3)
+    owned = [col[a:b].sum() for a, b in zip(cuts, cuts[1:])]
+    assert max(owned) <= 17.0 + 1e-9, (cuts, owned)
     with pytest.raises(ValueError):
         mgpu.balanced_cuts(np.ones(5), 4, 3)
