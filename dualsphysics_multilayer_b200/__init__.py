@@ -77,12 +77,45 @@ class CaseData:
         """typecode per particle: fixed block 0, fluid blocks by rank (JSphMk::GetCodeById)."""
         code = np.full(self.np_, capi.CODE_TYPE_FIXED, np.uint16)
         nb = int(self.cfg.casenfixed)
-        start = nb
+        nmov = int(self.cfg.casenmoving)
+        if nmov:                                         # one moving block (the synthetic cases have one plate)
+            code[(self.idp >= nb) & (self.idp < nb + nmov)] = capi.CODE_TYPE_MOVING
+        start = nb + nmov
         for rank, cnt in enumerate(self.fluidblocks):
             sel = (self.idp >= start) & (self.idp < start + cnt)
             code[sel] = capi.CODE_TYPE_FLUID | rank
             start += cnt
         return code
+
+
+class CaseMotion:
+    """Motion laws of <case><execution><motion> evaluated by the library's host code (dsph_case_motion_*), JDsMotion work-alike."""
+
+    def __init__(self, directory, casename="Case"):
+        L = lib()
+        self._lib = L
+        self.h = C.c_void_p()
+        n = C.c_uint32()
+        L.check(L.fn("case_motion_open")(str(directory).encode(), casename.encode(), C.byref(self.h), C.byref(n)))
+        self.nobj = int(n.value)
+
+    def process(self, timestep, dt):
+        """= JDsMotion::ProcesTime(simple, timestep, dt) + GetMotionData of every object -> (list of MotionData, active)."""
+        out = (capi.MotionData * max(1, self.nobj))()
+        act = C.c_int()
+        self._lib.check(self._lib.fn("case_motion_process")(self.h, float(timestep), float(dt), out, C.byref(act)))
+        return list(out)[: self.nobj], bool(act.value)
+
+    def close(self):
+        if self.h:
+            self._lib.fn("case_motion_close")(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _case_from_c(c: Case) -> CaseData:

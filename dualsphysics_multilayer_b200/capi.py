@@ -23,6 +23,7 @@ CODE_OUTPOS = 0x8000
 CODE_OUTRHOP = 0xA000
 CODE_MASKTYPE = 0x1800
 CODE_TYPE_FIXED = 0x0000
+CODE_TYPE_MOVING = 0x0800
 CODE_TYPE_FLUID = 0x1800
 CODE_MASKVALUE = 0x07FF
 
@@ -84,6 +85,12 @@ class DivInfo(C.Structure):
 class ForceRes(C.Structure):
     _fields_ = [("viscdtmax", C.c_float), ("acemax", C.c_float), ("velmax", C.c_float), ("viscetadtmax", C.c_float),
                 ("dt1", C.c_double), ("dt2", C.c_double), ("dt3", C.c_double), ("dt", C.c_double)]
+
+
+class MotionData(C.Structure):
+    """dsph_motiondata = StMotionData (S/JDsMotionDef.h:33-44)."""
+    _fields_ = [("idbegin", C.c_uint32), ("count", C.c_uint32), ("type", C.c_int32), ("reserved", C.c_int32),
+                ("linmov", C.c_double * 3), ("linvel", C.c_double * 3), ("matmov", C.c_double * 16)]
 
 
 class Timers(C.Structure):
@@ -186,6 +193,7 @@ class SphLib:
             f("celldiv_last_info", C.c_int, vp, C.POINTER(DivInfo))
         if prefix == "dsph_":
             f("particles_set_boundnormals", C.c_int, vp, C.POINTER(C.c_float), C.c_uint32)
+            f("particles_get_boundnormals", C.c_int, vp, C.POINTER(C.c_float), C.c_uint32)
             f("set_mdbc_threshold", C.c_int, vp, C.c_float)
             f("case_normals", C.c_int, C.c_char_p, C.c_char_p, C.POINTER(C.c_double), C.c_uint32, C.POINTER(C.c_uint32))
             f("gauges_config", C.c_int, vp, C.c_uint32, C.POINTER(Gauge))
@@ -193,6 +201,12 @@ class SphLib:
             f("gauges_results", C.c_int, vp, C.POINTER(GaugeRes))
             f("gauges_set_time", C.c_int, vp, C.c_double)
             f("case_gauges", C.c_int, C.c_char_p, C.c_char_p, C.POINTER(Gauge), C.c_uint32, C.POINTER(C.c_uint32))
+        f("motion_run", C.c_int, vp, C.POINTER(MotionData), C.c_uint32, C.c_double)
+        if prefix == "dsph_":
+            f("case_motion_open", C.c_int, C.c_char_p, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_uint32))
+            f("case_motion_process", C.c_int, vp, C.c_double, C.c_double, C.POINTER(MotionData), C.POINTER(C.c_int))
+            f("case_motion_close", C.c_int, vp)
+            f("motion_attach", C.c_int, vp, vp)
         f("forces_launch", C.c_int, vp, C.c_int)
         f("forces_maxima_ptr", C.c_void_p, vp)
         f("forces_finish", C.c_int, vp, C.POINTER(ForceRes))
@@ -253,6 +267,11 @@ class SphContext:
         """mDBC: vectors particle -> ghost node (xyz) of the first len(n) particles of the uploaded order (boundary particles first)."""
         n = np.ascontiguousarray(n, np.float32).reshape(-1, 3)
         self.lib.check(self.lib.fn("particles_set_boundnormals")(self.h, _ptr(n, C.c_float), n.shape[0]))
+
+    def boundnormals(self, count):
+        n = np.zeros((int(count), 3), np.float32)
+        self.lib.check(self.lib.fn("particles_get_boundnormals")(self.h, _ptr(n, C.c_float), int(count)))
+        return n
 
     def set_spstau(self, t):
         t = np.ascontiguousarray(t, np.float32).reshape(-1, 6)
@@ -319,6 +338,17 @@ class SphContext:
     @symplectic_dtpre.setter
     def symplectic_dtpre(self, v):
         self.lib.check(self.lib.fn("set_symplectic_dtpre")(self.h, float(v)))
+
+    # -- moving boundaries
+    def motion_run(self, objs, stepdt):
+        """RunMotion with the motion data of this step (list of MotionData)."""
+        arr = (MotionData * max(1, len(objs)))(*objs)
+        self.lib.check(self.lib.fn("motion_run")(self.h, arr, len(objs), float(stepdt)))
+
+    def motion_attach(self, motion):
+        """Let step() evaluate and apply the motion laws of a CaseMotion (None detaches)."""
+        self._motion = motion
+        self.lib.check(self.lib.fn("motion_attach")(self.h, motion.h if motion is not None else None))
 
     # -- in-solver gauges
     def gauges_config(self, gauges):

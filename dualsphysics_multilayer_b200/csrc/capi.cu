@@ -142,7 +142,22 @@ int dsph_mgpu_comm_attach(dsph_ctx *ctx,void *ncclcomm,int rank,int nranks){ NEE
 int dsph_mgpu_config_cuts(dsph_ctx *ctx,int rank,int nranks,const uint32_t *cuts){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgConfigCuts(rank,nranks,cuts); }); }
 uint32_t dsph_mgpu_halo_cells(const dsph_ctx *ctx){ return (ctx&&ctx->eng)? ctx->eng->MgHalo(): 0u; }
 int dsph_mgpu_exchange(dsph_ctx *ctx){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MgExchange(); }); }
+int dsph_motion_run(dsph_ctx *ctx,const dsph_motiondata *objs,uint32_t nobj,double stepdt){ NEEDCTX(ctx); return Guard([&]{ ctx->eng->MotionRun(objs,nobj,stepdt); }); }
+struct dsph_motionset { MotionSet ms; };
+int dsph_case_motion_open(const char *dir,const char *casename,dsph_motionset **ms,uint32_t *nobj){
+  if(!dir||!casename||!ms){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  *ms=nullptr;
+  const int r=Guard([&]{ dsph_motionset *m=new dsph_motionset; try{ LoadCaseMotion(m->ms,dir,casename); }catch(...){ delete m; throw; } m->ms.Reset(); *ms=m; if(nobj)*nobj=uint32_t(m->ms.objs.size()); });
+  return r==DSPH_OK? r: DSPH_ERR_IO;
+}
+int dsph_case_motion_process(dsph_motionset *ms,double timestep,double dt,dsph_motiondata *out,int *active){
+  if(!ms||(!out && !ms->ms.objs.empty())){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }
+  return Guard([&]{ std::vector<dsph_motiondata> v; const bool a=ms->ms.Process(timestep,dt,v); for(size_t i=0;i<v.size();i++)out[i]=v[i]; if(active)*active=(a? 1: 0); });
+}
+int dsph_case_motion_close(dsph_motionset *ms){ delete ms; return DSPH_OK; }
+int dsph_motion_attach(dsph_ctx *ctx,dsph_motionset *ms){ NEEDCTX(ctx); ctx->eng->motionset=(ms? &ms->ms: nullptr); return DSPH_OK; }
 int dsph_particles_set_boundnormals(dsph_ctx *ctx,const float *n,uint32_t count){ NEEDCTX(ctx); if(!n && count){ g_lasterror="Null argument."; return DSPH_ERR_ARG; } return Guard([&]{ ctx->eng->SetBoundNormals(n,count); }); }
+int dsph_particles_get_boundnormals(dsph_ctx *ctx,float *n,uint32_t count){ NEEDCTX(ctx); if(!n && count){ g_lasterror="Null argument."; return DSPH_ERR_ARG; } return Guard([&]{ ctx->eng->GetBoundNormals(n,count); }); }
 int dsph_set_mdbc_threshold(dsph_ctx *ctx,float v){ NEEDCTX(ctx); ctx->eng->mdbcthreshold=v; return DSPH_OK; }
 int dsph_case_normals(const char *dir,const char *casename,double *out,uint32_t max,uint32_t *n){
   if(!dir||!casename||!n){ g_lasterror="Null argument."; return DSPH_ERR_ARG; }

@@ -9,6 +9,7 @@
 #include "celldiv.cuh"
 #include "forces_api.h"
 #include "step.cuh"
+#include "motion.cuh"
 #include "periodic.cuh"
 #include "mgpu.cuh"
 #include "measure.cuh"
@@ -77,6 +78,7 @@ Engine::~Engine(){
   GaugesFree();
   if(measuredev)cudaFree(measuredev);
   if(mgown)cudaFree(mgown);
+  if(ridpmove)cudaFree(ridpmove);
   if(stmcopy){ cudaStreamSynchronize(stmcopy); cudaStreamDestroy(stmcopy); cudaEventDestroy(evsnap); cudaEventDestroy(evsnapfree); }
   if(snapdev)cudaFree(snapdev);
   FreeAll();
@@ -88,7 +90,7 @@ Engine::~Engine(){
 void Engine::Configure(const dsph_config &c){
   cfg=c;
   DeriveConstants(cfg,k);
-  if(cfg.casenmoving || cfg.casenfloat)throw EngineError(DSPH_ERR_ARG,"Moving and floating particles are outside the hot-path scope.");
+  if(cfg.casenfloat)throw EngineError(DSPH_ERR_ARG,"Floating bodies are outside the hot-path scope (moving boundaries are supported: dsph_motion_run).");
   if(cfg.tvisco==DSPH_VISCO_CONSTEQ && !cfg.nn_on)throw EngineError(DSPH_ERR_ARG,"ViscoTreatment 'Constitutive eq.' not valid for Single-phase classic formulation.");
   sps=(cfg.tvisco==DSPH_VISCO_LAMINARSPS && !cfg.nn_on);
   memset(&dc,0,sizeof(dc)); memset(&dph,0,sizeof(dph));
@@ -226,7 +228,7 @@ void Engine::Upload(unsigned np_,unsigned npb_,const unsigned *hidp,const typeco
   std::vector<typecode> tmpcode;
   if(!hcode){
     tmpcode.resize(np);
-    for(unsigned p=0;p<np;p++)tmpcode[p]=typecode(hidp[p]<cfg.casenfixed? DSPH_CODE_TYPE_FIXED: DSPH_CODE_TYPE_FLUID);
+    for(unsigned p=0;p<np;p++)tmpcode[p]=typecode(hidp[p]<cfg.casenfixed? DSPH_CODE_TYPE_FIXED: (hidp[p]<cfg.casenfixed+cfg.casenmoving? DSPH_CODE_TYPE_MOVING: DSPH_CODE_TYPE_FLUID));
     hcode=tmpcode.data();
   }
   CUCHECK(cudaMemcpyAsync(idp[cur],hidp,size_t(np)*4,cudaMemcpyHostToDevice,stm));
@@ -277,6 +279,14 @@ void Engine::SetBoundNormals(const float *h,unsigned count){
   CUCHECK(cudaMemsetAsync(boundnormal[cur],0,size_t(cap)*sizeof(float4),stm));
   if(count)CUCHECK(cudaMemcpyAsync(boundnormal[cur],tmp.data(),size_t(count)*sizeof(float4),cudaMemcpyHostToDevice,stm));
   CUCHECK(cudaStreamSynchronize(stm));
+}
+void Engine::GetBoundNormals(float *h,unsigned count){
+  if(!mdbc)throw EngineError(DSPH_ERR_STATE,"Normal vectors are only used with cfg.tboundary = DSPH_BOUNDARY_MDBC.");
+  if(count>np)throw EngineError(DSPH_ERR_ARG,"More normal vectors than particles.");
+  std::vector<float4> tmp(count);
+  if(count)CUCHECK(cudaMemcpyAsync(tmp.data(),boundnormal[cur],size_t(count)*sizeof(float4),cudaMemcpyDeviceToHost,stm));
+  CUCHECK(cudaStreamSynchronize(stm));
+  for(unsigned i=0;i<count;i++){ h[3*size_t(i)]=tmp[i].x; h[3*size_t(i)+1]=tmp[i].y; h[3*size_t(i)+2]=tmp[i].z; }
 }
 void Engine::MdbcCorrection(){
   if(!npbok)return;
@@ -745,8 +755,10 @@ void Engine::FlushStepTimer(){
 
 void Engine::Step(double *stepdt,dsph_forceres *res){
   double dt;
+  bool moving=false;
   if(cfg.tstep==DSPH_STEP_SYMPLECTIC){
     dt=symplecticdtpre;
+    if(motionset)moving=motionset->Process(gaugetime,dt,motiondata);          // CalcMotion(dt), S/JSphCpuSingle.cpp:697
     Forces(DSPH_INTERSTEP_SYMPREDICTOR,nullptr);
     const double ddt_p=DtVariable(nullptr,nullptr);
     StepSymPre(dt);
@@ -759,9 +771,12 @@ void Engine::Step(double *stepdt,dsph_forceres *res){
   else{
     Forces(DSPH_INTERSTEP_VERLET,res);
     dt=DtVariable(nullptr,nullptr);
+    if(motionset)moving=motionset->Process(gaugetime,dt,motiondata);          // S/JSphCpuSingle.cpp:677
     StepVerlet(dt);
   }
-  if(!gauges.empty()){ GaugesRun(gaugetime+dt,false,nullptr); gaugetime+=dt; }   // RunGaugeSystem(TimeStep+stepdt), S/JSphCpuSingle.cpp:1095
+  if(!gauges.empty())GaugesRun(gaugetime+dt,false,nullptr);                    // RunGaugeSystem(TimeStep+stepdt), S/JSphCpuSingle.cpp:1095
+  if(moving)MotionRun(motiondata.data(),unsigned(motiondata.size()),dt);       // RunMotion(stepdt), :1096
+  gaugetime+=dt;
   CellDivide(true,nullptr); FlushStepTimer();
   if(stepdt)*stepdt=dt;
 }
@@ -921,6 +936,47 @@ void Engine::GetTimers(dsph_timers *t,bool reset){
   tm.kernel_launches=launches;
   if(t)*t=tm;
   if(reset){ memset(&tm,0,sizeof(tm)); launches=0; mgcostmark=0; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// moving boundaries (kernels: motion.cuh): JSphGpu::RunMotion (S/JSphGpu.cpp:1035-1075)
+// ------------------------------------------------------------------------------------------------
+// The host (the reference's JDsMotion, or host/motion.cpp of the stand-alone driver) evaluated the motion laws for [TimeStep,TimeStep+dt);
+// this applies them to the particles, after ComputeStep and before the divide like JSphGpuSingle::Run (S/JSphGpuSingle.cpp:859).
+void Engine::MotionRun(const dsph_motiondata *objs,unsigned nobj,double stepdt){
+  CUCHECK(cudaSetDevice(device));
+  if(!cfg.casenmoving)throw EngineError(DSPH_ERR_STATE,"The case has no moving boundary particles.");
+  if(nobj && !objs)throw EngineError(DSPH_ERR_ARG,"Null argument.");
+  bool any=false;
+  for(unsigned i=0;i<nobj;i++){
+    const dsph_motiondata &m=objs[i];
+    if(m.type==DSPH_MOTION_NONE)continue;
+    if(m.type!=DSPH_MOTION_LINEAR && m.type!=DSPH_MOTION_MATRIX)throw EngineError(DSPH_ERR_ARG,"Motion type is invalid.");
+    if(m.idbegin<cfg.casenfixed || size_t(m.idbegin)+m.count>size_t(cfg.casenfixed)+cfg.casenmoving)throw EngineError(DSPH_ERR_ARG,"The ids of a moving object are outside the moving range of the case.");
+    if(m.type==DSPH_MOTION_MATRIX && !(stepdt>0))throw EngineError(DSPH_ERR_ARG,"A matrix motion needs the dt of the step.");
+    any=true;
+  }
+  if(!any)return;
+  NvtxBegin("SU-Motion");
+  EnsureDcell();
+  if(!ridpmove)CUCHECK(cudaMalloc((void**)&ridpmove,size_t(cfg.casenmoving)*sizeof(unsigned)));
+  CUCHECK(cudaMemsetAsync(ridpmove,0xff,size_t(cfg.casenmoving)*sizeof(unsigned),stm));
+  if(npb){ ker_motion_ridp<<<(npb+255)/256,256,0,stm>>>(npb,cfg.casenfixed,cfg.casenfixed+cfg.casenmoving,(k.periactive||mgpu)? 1: 0,idp[cur],code[cur],ridpmove); launches++; }
+  MotionArrays a; a.pos=pos[cur]; a.dcell=dcell[cur]; a.velrhop=velrhop[cur]; a.code=code[cur]; a.boundnormal=(mdbc? boundnormal[cur]: nullptr);
+  for(unsigned i=0;i<nobj;i++){
+    const dsph_motiondata &m=objs[i];
+    if(m.type==DSPH_MOTION_NONE || !m.count)continue;
+    const unsigned ini=m.idbegin-cfg.casenfixed;
+    if(m.type==DSPH_MOTION_LINEAR)
+      ker_motion_linear<<<(m.count+255)/256,256,0,stm>>>(m.count,ini,m.linmov[0],m.linmov[1],m.linmov[2],float(m.linvel[0]),float(m.linvel[1]),float(m.linvel[2]),ridpmove,a,dc);
+    else{
+      Mat4d mt; memcpy(mt.a,m.matmov,sizeof(mt.a));
+      ker_motion_matrix<<<(m.count+255)/256,256,0,stm>>>(m.count,ini,mt,stepdt,ridpmove,a,dc);
+    }
+    launches++;
+  }
+  NvtxEnd();
+  boundchanged=true; divok=false; celltableok=false;
 }
 
 } // namespace dsph

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <string>
 #include <vector>
+#include "host/motion.h"
 #include <stdexcept>
 
 namespace dsph {
@@ -43,7 +44,7 @@ class Engine {
   float *spstau[2]={};
   // mDBC (mdbc.cuh): normal vectors particle -> ghost node of the boundary particles, sorted with the particles
   bool mdbc=false, mdbccorrector=false; float mdbcthreshold=0; float4 *boundnormal[2]={};
-  void SetBoundNormals(const float *h,unsigned count);
+  void SetBoundNormals(const float *h,unsigned count); void GetBoundNormals(float *h,unsigned count);
   void MdbcCorrection();
   static const unsigned POSP_PAD=512;
   float4 *posp=nullptr; uint4 *posh=nullptr; float4 *acear=nullptr, *shiftposfs=nullptr; float *spsgradvel=nullptr;
@@ -111,6 +112,10 @@ class Engine {
   unsigned *mgscratch[3]={}; unsigned mgcounts[8]={}; bool mgcounted=false;
   unsigned *mgown=nullptr; unsigned mgowncap=0; bool mgownok=false;   // owned fluid particles of the current divide (force kernel variant 10)
   void MgBuildOwnList();
+  // moving boundaries (motion.cuh, engine.cu)
+  unsigned *ridpmove=nullptr;
+  MotionSet *motionset=nullptr; std::vector<dsph_motiondata> motiondata;   // attached motion laws (dsph_motion_attach): evaluated inside Step / MgStep
+  void MotionRun(const dsph_motiondata *objs,unsigned nobj,double stepdt);
   bool forceslaunched=false;
   void MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi);
   // halo width in cells: 2h; 4h for the SPH velocity-gradient approach of the multiphase fork (its second pair pass reads eta_eff / tau of
@@ -155,7 +160,8 @@ class Engine {
   int numsm=148;                // multiprocessors of the device (grid sizing of the grid-stride kernels)
   // in-solver gauges (gauges.cu)
   std::vector<dsph_gauge> gauges; std::vector<double> gaugenext; std::vector<dsph_gaugeres> gaugeres;
-  double gaugetime=0; bool celltableok=false;
+  double gaugetime=0;        // TimeStep of the run as dsph_step / dsph_mgpu_step advance it (gauges and attached motion laws use it)
+  bool celltableok=false;
   char *gaugedev=nullptr; size_t gaugedevcap=0; float *gaugehost=nullptr; size_t gaugehostcap=0; float *gaugepartace=nullptr; unsigned gaugepartacecap=0;
   void GaugesConfig(unsigned n,const dsph_gauge *g);
   unsigned GaugesRun(double timestep,bool all,dsph_gaugeres *res);

@@ -148,7 +148,10 @@ void SaveCase(const CaseData &cd,const std::string &dir,const std::string &casen
     np,np-c.casenfluid,c.casenfixed,cd.mkboundfirst,cd.mkfluidfirst);
   static const char *tn[4]={"fixed","moving","floating","fluid"};
   for(auto &b:cd.blocks)
-    fprintf(f,"      <%s %s=\"%u\" mk=\"%u\" begin=\"%u\" count=\"%u\" />\n",tn[b.type],(b.type==3? "mkfluid":"mkbound"),b.mktype,b.mk,b.begin,b.count);
+  {
+    if(b.type==1)fprintf(f,"      <moving mkbound=\"%u\" mk=\"%u\" begin=\"%u\" count=\"%u\" refmotion=\"%u\" />\n",b.mktype,b.mk,b.begin,b.count,b.refmotion);
+    else fprintf(f,"      <%s %s=\"%u\" mk=\"%u\" begin=\"%u\" count=\"%u\" />\n",tn[b.type],(b.type==3? "mkfluid":"mkbound"),b.mktype,b.mk,b.begin,b.count);
+  }
   fprintf(f,"    </particles>\n    <constants>\n");
   fprintf(f,"      <data2d value=\"%s\" />\n",c.simulate2d? "true":"false");
   if(c.simulate2d)fprintf(f,"      <data2dposy value=\"%s\" />\n",D(c.simulate2dposy).c_str());
@@ -156,7 +159,9 @@ void SaveCase(const CaseData &cd,const std::string &dir,const std::string &casen
   fprintf(f,"      <cflnumber value=\"%s\" />\n      <gamma value=\"%s\" />\n      <rhop0 value=\"%s\" />\n",D(c.cflnumber).c_str(),D(c.gamma).c_str(),D(c.rhopzero).c_str());
   fprintf(f,"      <dp value=\"%s\" />\n      <h value=\"%s\" />\n      <b value=\"%s\" />\n",D(c.dp).c_str(),D(c.kernelh).c_str(),D(c.cteb).c_str());
   fprintf(f,"      <massbound value=\"%s\" />\n      <massfluid value=\"%s\" />\n",D(c.massbound).c_str(),D(c.massfluid).c_str());
-  fprintf(f,"    </constants>\n  </execution>\n</case>\n");
+  fprintf(f,"    </constants>\n");
+  if(c.casenmoving)cd.motion.SaveXml(f,"    ");
+  fprintf(f,"  </execution>\n</case>\n");
   fclose(f);
   if((c.tboundary&0xff)==DSPH_BOUNDARY_MDBC){
     // <name>_Normals.nbi4: the "final normals" file of GenCase >= 5.0.268 (JPartNormalData::SaveFile, S/JPartNormalData.cpp:179-207)
@@ -180,6 +185,23 @@ void SaveCase(const CaseData &cd,const std::string &dir,const std::string &casen
   for(unsigned i=0;i<np;i++){ p.vel[3*i]=cd.velrhop[4*i]; p.vel[3*i+1]=cd.velrhop[4*i+1]; p.vel[3*i+2]=cd.velrhop[4*i+2]; p.rhop[i]=cd.velrhop[4*i+3]; }
   memcpy(p.domainmin,cd.caseposmin,24); memcpy(p.domainmax,cd.caseposmax,24);
   SavePartFile(dir+"/"+casename+".bi4",h,p,true);
+}
+
+// only the moving blocks of <particles> and <motion> of Case.xml (no particle file needed)
+void LoadCaseMotion(MotionSet &ms,const std::string &dir,const std::string &casename){
+  XmlDoc doc=XmlDoc::LoadFile(dir+"/"+casename+".xml");
+  const XmlNode *ex=doc.root->Path("case.execution");
+  if(!ex)throw std::runtime_error("Cannot find the element 'case.execution'.");
+  ms=MotionSet();
+  if(const XmlNode *ct=ex->Child("constants"))if(const XmlNode *e=ct->Child("data2d"))ms.simulate2d=e->Bool("value");
+  const XmlNode *pt=ex->Child("particles");
+  if(!pt)throw std::runtime_error("Cannot find the element 'case.execution.particles'.");
+  unsigned nmov=0;
+  for(auto &e:pt->children)if(e->name=="moving"){
+    MotionObj o; o.ref=int(e->Int("refmotion",true,nmov)); o.mkbound=unsigned(e->Int("mkbound")); o.idbegin=unsigned(e->Int("begin")); o.count=unsigned(e->Int("count"));
+    ms.objs.push_back(o); nmov++;
+  }
+  if(nmov)ms.LoadXml(ex->Child("motion"));
 }
 
 void LoadCase(CaseData &cd,const std::string &dir,const std::string &casename){
@@ -262,11 +284,22 @@ void LoadCase(CaseData &cd,const std::string &dir,const std::string &casename){
     if(tp<0)continue;
     MkBlock b; b.type=tp; b.mktype=unsigned(e->Int(tp==3? "mkfluid":"mkbound")); b.mk=unsigned(e->Int("mk",true,0));
     b.begin=unsigned(e->Int("begin")); b.count=unsigned(e->Int("count"));
+    if(tp==1)b.refmotion=unsigned(e->Int("refmotion",true,0xffffffffll));
     cd.blocks.push_back(b); cnt[tp]+=b.count; total+=b.count;
   }
   if(total!=unsigned(pt->Int("np")) || unsigned(pt->Int("nb"))!=total-cnt[3] || unsigned(pt->Int("nbf"))!=cnt[0])
     throw std::runtime_error("The amount of particles does not match the header.");
-  if(cnt[1] || cnt[2])throw std::runtime_error("Moving and floating particles are outside the hot-path scope (SURVEY.md 2.2 rows 17-18).");
+  if(cnt[2])throw std::runtime_error("Floating bodies are outside the hot-path scope (SURVEY.md 2.2 row 18).");
+  // moving objects in the order of their blocks (JDsMotion::ConfigObjects) + their motion laws
+  cd.motion=MotionSet(); cd.motion.simulate2d=(c.simulate2d!=0);
+  { unsigned nmov=0;
+    for(auto &b:cd.blocks)if(b.type==1){
+      if(b.refmotion==0xffffffffu)b.refmotion=nmov;
+      MotionObj o; o.ref=int(b.refmotion); o.mkbound=b.mktype; o.idbegin=b.begin; o.count=b.count;
+      cd.motion.objs.push_back(o); nmov++;
+    }
+    if(nmov)cd.motion.LoadXml(ex->Child("motion"));
+  }
   c.casenp=total; c.casenfixed=cnt[0]; c.casenmoving=cnt[1]; c.casenfloat=cnt[2]; c.casenfluid=cnt[3];
   if(c.nn_on){
     const XmlNode *nn=ex->Path("special.nnphases");
@@ -412,7 +445,9 @@ static thread_local SlabFilter g_slab;
 // twod: the x-z section at y=0 as a 2-D simulation (data2d: h=coefh*sqrt(2)*dp, mass=rho0*dp^2, no walls in y)
 // nlayers: 1 = single-phase dam break; 2 = two stacked layers (phases 2/3 of the fork's example); 3 = the three stacked layers of
 // R/examples/mphase_nnewtonian/01_WetDambreak/CaseWetDambreak2DNN_Def.xml:72-97 (rho 2000/1500/1000, shear-thickening Bingham-like bottom layer)
-static void MakeDamBreak(CaseData &cd,unsigned long long nptarget,int nlayers,bool twod=false){
+// moving: 0 none; a one-particle-thick plate right of the water column as moving object 0 with 1 = gate lifted at constant speed, then at
+// rest (mvrect -> wait), 2 = flap oscillating about its lower edge (mvrotsinu), 3 = piston oscillating along x (mvrectsinu)
+static void MakeDamBreak(CaseData &cd,unsigned long long nptarget,int nlayers,bool twod=false,int moving=0){
   const bool twolayer=(nlayers>=2);
   dsph_config &c=cd.cfg; ConfigDefaults(c);
   const double a=0.4;
@@ -457,6 +492,11 @@ static void MakeDamBreak(CaseData &cd,unsigned long long nptarget,int nlayers,bo
     const bool wall=(k==0||i==0||i==NX||(!twod && (j==0||j==NY)));
     if(wall)add(i,j,k,rhohyd(k*dp));
   }
+  const unsigned nbfixed=nextid;
+  const unsigned GX=FX+1, GZ=std::min(NZ-1,FZ+2);               // plate: column of lattice nodes at i=GX, k=1..GZ
+  if(moving && GX<NX){
+    for(unsigned k=1;k<=GZ;k++)for(unsigned j=(twod? 0u: 1u);j<=(twod? 0u: NY-1);j++)add(GX,j,k,rhohyd(k*dp));
+  }
   const unsigned nb=nextid;
   unsigned nfl[3]={0,0,0};
   if(!twolayer){
@@ -476,10 +516,31 @@ static void MakeDamBreak(CaseData &cd,unsigned long long nptarget,int nlayers,bo
   }
   const unsigned nf0=nfl[0], nf1=nfl[1], nf2=nfl[2];
   const unsigned np=nextid;
-  c.casenp=np; c.casenfixed=nb; c.casenfluid=np-nb;
+  c.casenp=np; c.casenfixed=nbfixed; c.casenmoving=nb-nbfixed; c.casenfluid=np-nb;
   cd.mkboundfirst=11; cd.mkfluidfirst=1;
   cd.blocks.clear();
-  cd.blocks.push_back({0,0,cd.mkboundfirst+0,0,nb});
+  cd.blocks.push_back({0,0,cd.mkboundfirst+0,0,nbfixed});
+  cd.motion=MotionSet(); cd.motion.simulate2d=twod;
+  if(nb>nbfixed){
+    MkBlock mb{1,1,cd.mkboundfirst+1,nbfixed,nb-nbfixed}; mb.refmotion=0;
+    cd.blocks.push_back(mb);
+    MotionObj o; o.ref=0; o.mkbound=1; o.idbegin=nbfixed; o.count=nb-nbfixed;
+    MotionEvent ev; ev.movid=1; ev.start=0; ev.finish=-1; o.events.push_back(ev);
+    MotionMov m; m.id=1;
+    if(moving==1){
+      m.type=MotionMov::Rect; m.time=0.004; m.nextid=2; m.vel[2]=1.5; o.movs.push_back(m);
+      MotionMov w; w.id=2; w.type=MotionMov::Wait; w.time=100; o.movs.push_back(w);
+    }
+    else if(moving==2){
+      m.type=MotionMov::RotSinu; m.time=100; m.freq[0]=2; m.ampl[0]=10; m.phase[0]=0;
+      m.axisp1[0]=GX*dp; m.axisp1[1]=0; m.axisp1[2]=dp; m.axisp2[0]=GX*dp; m.axisp2[1]=1; m.axisp2[2]=dp;
+      o.movs.push_back(m);
+    }
+    else{
+      m.type=MotionMov::RectSinu; m.time=100; m.freq[0]=2; m.ampl[0]=0.25*a; m.phase[0]=0; o.movs.push_back(m);
+    }
+    cd.motion.objs.push_back(o);
+  }
   cd.blocks.push_back({3,0,cd.mkfluidfirst+0,nb,nf0});
   if(twolayer)cd.blocks.push_back({3,1,cd.mkfluidfirst+1,nb+nf0,nf1});
   if(nlayers==3)cd.blocks.push_back({3,2,cd.mkfluidfirst+2,nb+nf0+nf1,nf2});
@@ -546,7 +607,7 @@ void LoadCaseNormals(std::vector<double> &normals,const std::string &dir,const s
 
 void MakeTankNormals(CaseData &cd){
   const dsph_config &c=cd.cfg;
-  const unsigned nbound=c.casenfixed;
+  const unsigned nbound=c.casenfixed+c.casenmoving;
   const double dp=c.dp, hd=0.5*dp;
   const bool twod=(c.simulate2d!=0);
   const long long NX=llround(cd.caseposmax[0]/dp), NY=llround(cd.caseposmax[1]/dp);
@@ -556,6 +617,7 @@ void MakeTankNormals(CaseData &cd){
     if(id>=nbound)continue;
     const long long i=llround(cd.pos[3*q]/dp), j=llround(cd.pos[3*q+1]/dp), k=llround(cd.pos[3*q+2]/dp);
     double *n=&cd.normals[size_t(id)*3];
+    if(id>=c.casenfixed){ n[0]=-hd; continue; }          // moving plate: the water is on its -x side
     if(i==0)n[0]=hd; else if(i==NX)n[0]=-hd;
     if(!twod){ if(j==0)n[1]=hd; else if(j==NY)n[1]=-hd; }
     if(k==0)n[2]=hd;
@@ -576,6 +638,10 @@ void MakeCase(CaseData &cd,const std::string &kind,unsigned long long nptarget,u
   else if(kind=="nn3layer"){ MakeDamBreak(cd,nptarget,3); cd.name="DamBreakNN3"; }
   else if(kind=="nn3layer2d"){ MakeDamBreak(cd,nptarget,3,true); cd.name="DamBreakNN3_2D"; }
   else if(kind=="dambreak2d"){ MakeDamBreak(cd,nptarget,1,true); cd.name="DamBreak2D"; }
+  else if(kind=="movgate"){ MakeDamBreak(cd,nptarget,1,false,1); cd.name="DamBreakGate"; }
+  else if(kind=="movflap"){ MakeDamBreak(cd,nptarget,1,false,2); cd.name="DamBreakFlap"; }
+  else if(kind=="movpiston"){ MakeDamBreak(cd,nptarget,1,false,3); cd.name="DamBreakPiston"; }
+  else if(kind=="movflap2d"){ MakeDamBreak(cd,nptarget,1,true,2); cd.name="DamBreakFlap2D"; }
   else if(kind=="nn2layer2d"){ MakeDamBreak(cd,nptarget,2,true); cd.name="DamBreakNN2D"; }
   else if(kind=="periodicbox"){ MakePeriodicBox(cd,nptarget,seed); cd.name="PeriodicBox"; }
   else throw std::runtime_error("Unknown case kind: "+kind+" (dambreak | periodicbox | nn2layer | nn3layer | dambreak2d | nn2layer2d | nn3layer2d)");

@@ -4,12 +4,13 @@
 // multiphase fork, M/JSph.cpp:608-628,3137-3214.
 #pragma once
 #include "../../../include/dsph_b200.h"
+#include "motion.h"
 #include <string>
 #include <vector>
 
 namespace dsph {
 
-struct MkBlock { int type; /*0 fixed,1 moving,2 floating,3 fluid*/ unsigned mktype, mk, begin, count; };
+struct MkBlock { int type; /*0 fixed,1 moving,2 floating,3 fluid*/ unsigned mktype, mk, begin, count; unsigned refmotion=0; };
 
 struct DomainLimit { int mode=0; /*0 default,1 default+-value,2 default+-prc,3 fixed*/ double value=0; };
 
@@ -24,6 +25,7 @@ struct CaseData {
   std::vector<double> pos;                 // xyz packed
   std::vector<float> velrhop;              // xyzw packed
   std::vector<dsph_gauge> gauges;          // <special><gauges> (S/JDsGaugeSystem.cpp:186-275)
+  MotionSet motion;                        // <execution><motion> of the moving blocks (S/JDsMotion.cpp:94-106)
   std::vector<double> normals;             // mDBC: vector particle -> boundary limit per boundary particle, id order, xyz packed (<name>_Normals.nbi4)
   unsigned np()const{ return (unsigned)idp.size(); }
   unsigned npb()const{ return cfg.casenfixed+cfg.casenmoving; }
@@ -41,6 +43,7 @@ void MakeTankNormals(CaseData &cd);
 void LoadCaseNormals(std::vector<double> &normals,const std::string &dir,const std::string &casename);
 void SaveCase(const CaseData &cd,const std::string &dir,const std::string &casename);
 void LoadCase(CaseData &cd,const std::string &dir,const std::string &casename);
+void LoadCaseMotion(MotionSet &ms,const std::string &dir,const std::string &casename);
 
 // kind: "dambreak", "periodicbox", "nn2layer" (DB(N), PB(N), NN(N))
 void MakeCase(CaseData &cd,const std::string &kind,unsigned long long nptarget,unsigned seed);

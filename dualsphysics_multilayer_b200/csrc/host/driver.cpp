@@ -296,6 +296,16 @@ static RunSummary RunRank(const RunOptions &opt,CaseData &cd,int rank,SlabGroup 
     eng.MgCellDivide(&di);
   }
   else eng.CellDivide(true,&di);
+  // ---- moving boundaries: every rank evaluates the motion laws of Case.xml itself (its own copy of the stateful objects) and moves the
+  //      moving particles it owns; a restart replays the laws up to the restart time (JMotion::ResetTime, S/JMotion.cpp:432-440)
+  MotionSet motion;
+  eng.gaugetime=timestep;
+  if(cd.cfg.casenmoving){
+    motion=cd.motion; motion.Reset();
+    if(timestep>0){ std::vector<dsph_motiondata> skip; motion.Process(0,timestep,skip); }
+    eng.motionset=&motion;
+    if(!rank)log.Printf("Motion: %u moving object(s), %u particles (<motion> of Case.xml)",unsigned(motion.objs.size()),cd.cfg.casenmoving);
+  }
   // ---- gauges: first evaluation on the initial state (RunGaugeSystem(TimeStep,true), S/JSphCpuSingle.cpp:1070)
   GaugeOutput gout;
   if(!cd.gauges.empty()){

@@ -352,8 +352,10 @@ void Engine::MgForces(int interstep,dsph_forceres *res){
 
 void Engine::MgStep(double *stepdt,dsph_forceres *res){
   double dt;
+  bool moving=false;
   if(cfg.tstep==DSPH_STEP_SYMPLECTIC){
     dt=symplecticdtpre;
+    if(motionset)moving=motionset->Process(gaugetime,dt,motiondata);
     MgForces(DSPH_INTERSTEP_SYMPREDICTOR,nullptr);
     const double ddt_p=DtVariable(nullptr,nullptr);
     StepSymPre(dt);
@@ -366,8 +368,11 @@ void Engine::MgStep(double *stepdt,dsph_forceres *res){
   else{
     MgForces(DSPH_INTERSTEP_VERLET,res);
     dt=DtVariable(nullptr,nullptr);
+    if(motionset)moving=motionset->Process(gaugetime,dt,motiondata);
     StepVerlet(dt);
   }
+  if(moving)MotionRun(motiondata.data(),unsigned(motiondata.size()),dt);   // every rank moves the moving particles it owns
+  gaugetime+=dt;
   MgCellDivide(nullptr); FlushStepTimer();
   if(stepdt)*stepdt=dt;
 }

@@ -318,10 +318,41 @@ int dsph_domain_info(const dsph_config *cfg,double *scell,double domposmin[3],ui
 #define DSPH_BOUNDARY_MDBC 2
 #define DSPH_BOUNDARY_MDBCCORRECTOR 0x100
 int dsph_particles_set_boundnormals(dsph_ctx *ctx,const float *normal_xyz,uint32_t count);
+int dsph_particles_get_boundnormals(dsph_ctx *ctx,float *normal_xyz,uint32_t count);   /* current (sorted) order; a matrix motion rotates them */
 int dsph_set_mdbc_threshold(dsph_ctx *ctx,float threshold);      /* command-line option -mdbc_threshold of the reference (default 0) */
 /* <dir>/<casename>_Normals.nbi4 (JPartNormalData, S/JPartNormalData.cpp:222-262): vectors particle -> boundary limit of the
  * boundary particles in id order; *n = number stored in the file (0 when there is none), at most max vectors are written */
 int dsph_case_normals(const char *dir,const char *casename,double *normal_xyz,uint32_t max,uint32_t *n);
+
+/* ---- moving boundaries: JSphGpu::RunMotion (S/JSphGpu.cpp:1035-1075 -> cusph::CalcRidp / MoveLinBound / MoveMatBound;
+ *      CPU twin S/JSphCpu.cpp:1660-1730,1762-1805).  dsph_motiondata = StMotionData (S/JDsMotionDef.h:33-44): what the host's motion
+ *      objects (the reference's JDsMotion::ProcesTime + GetMotionData, S/JSph.cpp:2308-2322, called at the start of ComputeStep_Sym or
+ *      after DtVariable in ComputeStep_Ver) computed for [TimeStep,TimeStep+dt).  dsph_motion_run applies it where JSphGpuSingle::Run
+ *      calls RunMotion (S/JSphGpuSingle.cpp:859: after ComputeStep and the gauges, before RunCellDivide): positions through the same
+ *      UpdatePos as the fluid (periodic wrap, new cell), velocity = linvel or displacement/stepdt, mDBC normals rotated with a matrix
+ *      motion; the next divide re-sorts the boundary (BoundChanged).  cfg.casenmoving ids follow the cfg.casenfixed fixed ones.
+ *      Floating bodies (RunFloating) are not built: contexts with cfg.casenfloat != 0 are refused. ----------------------------------- */
+#define DSPH_MOTION_NONE   0
+#define DSPH_MOTION_LINEAR 1
+#define DSPH_MOTION_MATRIX 2
+typedef struct dsph_motiondata {
+  uint32_t idbegin, count;    /* ids of the object's particles */
+  int32_t type, reserved;
+  double linmov[3], linvel[3];
+  double matmov[16];          /* tmatrix4d a11..a44, row major */
+} dsph_motiondata;
+int dsph_motion_run(dsph_ctx *ctx,const dsph_motiondata *objs,uint32_t nobj,double stepdt);
+/* host only: the motion laws of <case><execution><motion> (objects = the <moving> blocks of <particles>) evaluated like JDsMotion in
+ * simple mode, for hosts without the reference's JMotion library (bin/dsph_b200): wait, mvrect, mvrectace, mvrot, mvrotace, mvrectsinu,
+ * mvrotsinu with next-chains and begin events; other content is refused.  *nobj = moving objects; out[] needs nobj entries. */
+typedef struct dsph_motionset dsph_motionset;
+int dsph_case_motion_open(const char *dir,const char *casename,dsph_motionset **ms,uint32_t *nobj);
+int dsph_case_motion_process(dsph_motionset *ms,double timestep,double dt,dsph_motiondata *out,int *active);
+int dsph_case_motion_close(dsph_motionset *ms);
+/* dsph_step / dsph_mgpu_step evaluate the attached laws themselves (CalcMotion at the start of a Symplectic step or after DtVariable of
+ * a Verlet step, RunMotion before the closing divide) with the run time they advance (start value: dsph_gauges_set_time).  The set
+ * must outlive the context or be detached with ms = NULL.  Hosts that call the stages one by one use dsph_motion_run. */
+int dsph_motion_attach(dsph_ctx *ctx,dsph_motionset *ms);
 
 /* ---- excluded particles (JSph::AddParticlesOut <- JSphGpuSingle::RunCellDivide, S/JSphGpuSingle.cpp:405-412): with keep = 1 every
  *      divide copies the fluid particles it excludes (out of the domain, RhopOut, speed limit) to the host; dsph_excluded_take hands

@@ -25,6 +25,7 @@
 #include "JDsOutputTime.h"
 #ifndef HARNESS_NN
 #include "JDsGaugeSystem.h"
+#include "JDsMotion.h"
 #include "JDsGaugeItem.h"
 #endif
 #include "Functions.h"
@@ -150,9 +151,33 @@ class RefHarness : public JSphCpuSingle {
   }
 #endif
 
+#ifndef HARNESS_NN
+  std::vector<double> MotionLogT,MotionLogV;
+  //-What JDsMotion computed for this step (StMotionData of every moving object): type, linmov, linvel, matmov.
+  void DumpMotion(unsigned step){
+    RefDumpWriter w(DumpName(step,"motion"));
+    const unsigned nref=DsMotion->GetNumObjects();
+    w.U32("nobj",nref);
+    std::vector<unsigned> head; std::vector<double> val;
+    for(unsigned ref=0;ref<nref;ref++){
+      const StMotionData& m=DsMotion->GetMotionData(ref);
+      head.push_back(m.idbegin); head.push_back(m.count); head.push_back(unsigned(m.type));
+      const double lin[6]={m.linmov.x,m.linmov.y,m.linmov.z,m.linvel.x,m.linvel.y,m.linvel.z};
+      val.insert(val.end(),lin,lin+6);
+      const tmatrix4d &t=m.matmov;
+      const double mt[16]={t.a11,t.a12,t.a13,t.a14,t.a21,t.a22,t.a23,t.a24,t.a31,t.a32,t.a33,t.a34,t.a41,t.a42,t.a43,t.a44};
+      val.insert(val.end(),mt,mt+16);
+    }
+    w.Add("head",2,1,head.size(),head.data()); w.Add("val",4,1,val.size(),val.data());
+  }
+#endif
+
   //-Same call sequence as JSphCpuSingle::ComputeStep_Sym, with dumps in between.
   double StepSymDump(unsigned step){
     const double dt=SymplecticDtPre;
+#ifndef HARNESS_NN
+    if(CaseNmoving){ CalcMotion(dt); DumpMotion(step); }
+#endif
     Interaction_Forces(INTERSTEP_SymPredictor);
     const double ddt_p=DtVariable(false);
     DumpForces(step,"fpre",ddt_p);
@@ -177,6 +202,9 @@ class RefHarness : public JSphCpuSingle {
     Interaction_Forces(INTERSTEP_Verlet);
     const double dt=DtVariable(true);
     DumpForces(step,"fver",dt);
+#ifndef HARNESS_NN
+    if(CaseNmoving){ CalcMotion(dt); DumpMotion(step); }
+#endif
     if(Shifting)RunShifting(dt);
     ComputeVerlet(dt);
     PosInteraction_Forces();
@@ -238,7 +266,24 @@ class RefHarness : public JSphCpuSingle {
 #ifndef HARNESS_NN
       if(GaugeSystem->GetCount()){ RunGaugeSystem(TimeStep+stepdt); if(dump)DumpGauges(step,"gauges",TimeStep+stepdt); }
 #endif
+#ifndef HARNESS_NN
+      if(CaseNmoving){
+        //-Log of what JDsMotion computed for every step (the evaluation is stateful: a checker needs all the steps).
+        MotionLogT.push_back(TimeStep); MotionLogT.push_back(stepdt);
+        for(unsigned ref=0;ref<DsMotion->GetNumObjects();ref++){
+          const StMotionData& m=DsMotion->GetMotionData(ref);
+          const tmatrix4d &t=m.matmov;
+          const double v[23]={double(m.type),m.linmov.x,m.linmov.y,m.linmov.z,m.linvel.x,m.linvel.y,m.linvel.z,
+            t.a11,t.a12,t.a13,t.a14,t.a21,t.a22,t.a23,t.a24,t.a31,t.a32,t.a33,t.a34,t.a41,t.a42,t.a43,t.a44};
+          MotionLogV.insert(MotionLogV.end(),v,v+23);
+        }
+        RunMotion(stepdt);
+      }
+#endif
       RunCellDivide(true);
+#ifndef HARNESS_NN
+      if(dump && CaseNmoving)DumpState(step,"dmot",true);   //-sorted state after RunMotion + RunCellDivide
+#endif
       TimeStep+=stepdt;
       LastDt=stepdt;
       if(dump){
@@ -249,6 +294,14 @@ class RefHarness : public JSphCpuSingle {
       Nstep++;
     }
     DumpState(unsigned(Nstep),"final",true);
+#ifndef HARNESS_NN
+    if(CaseNmoving){
+      RefDumpWriter w(DumpName(unsigned(Nstep),"motionlog"));
+      w.U32("nobj",DsMotion->GetNumObjects());
+      w.Add("t_dt",4,2,MotionLogT.size()/2,MotionLogT.data());
+      w.Add("val",4,23,MotionLogV.size()/23,MotionLogV.data());
+    }
+#endif
     TimerSim.Stop(); TimerTot.Stop();
     log->Printf("refharness: finished %d steps, TimeStep=%.9g",Nstep,TimeStep);
   }

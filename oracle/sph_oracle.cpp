@@ -1379,6 +1379,49 @@ int orc_step(orc_state *s,double *stepdt,dsph_forceres *res){
   });
 }
 double orc_symplectic_dtpre(const orc_state *s){ return s->o.SymplecticDtPre; }
+// JSphCpu::RunMotion S/JSphCpu.cpp:1762-1805 for the motion data of one step: CalcRidp (:1660-1687), MoveLinBound (:1692-1703),
+// MoveMatBound (:1709-1730; mDBC normals are not carried by the checker)
+int orc_motion_run(orc_state *s,const dsph_motiondata *objs,uint32_t nobj,double stepdt){
+  return Guard([&]{
+    Oracle &o=s->o;
+    const unsigned idini=o.cfg.casenfixed, idfin=o.cfg.casenfixed+o.cfg.casenmoving;
+    if(idfin==idini)throw std::runtime_error("The case has no moving boundary particles.");
+    bool any=false; for(uint32_t i=0;i<nobj;i++)if(objs[i].type!=DSPH_MOTION_NONE)any=true;
+    if(!any)return;
+    std::vector<unsigned> ridp(idfin-idini,0xffffffffu);
+    for(unsigned p=0;p<o.Npb;p++){
+      const unsigned id=o.Idp[p];
+      if(idini<=id && id<idfin && (!o.PeriActive || CodeSpecial(o.Code[p])==DSPH_CODE_NORMAL))ridp[id-idini]=p;
+    }
+    o.BoundChanged=true;
+    for(uint32_t i=0;i<nobj;i++){
+      const dsph_motiondata &m=objs[i];
+      const unsigned ini=m.idbegin-idini, fin=ini+m.count;
+      if(m.type==DSPH_MOTION_LINEAR){
+        for(unsigned id=ini;id<fin;id++){
+          const unsigned pid=ridp[id];
+          if(pid==0xffffffffu)continue;
+          o.UpdatePos(o.Pos[pid],m.linmov[0],m.linmov[1],m.linmov[2],false,pid);
+          o.Velrhop[pid].x=float(m.linvel[0]); o.Velrhop[pid].y=float(m.linvel[1]); o.Velrhop[pid].z=float(m.linvel[2]);
+        }
+      }
+      else if(m.type==DSPH_MOTION_MATRIX){
+        const double *a=m.matmov;
+        for(unsigned id=ini;id<fin;id++){
+          const unsigned pid=ridp[id];
+          if(pid==0xffffffffu)continue;
+          const d3 ps=o.Pos[pid];
+          // association of the reference binary (-ffast-math pairs the four terms; pinned by the mv_* dumps)
+          d3 ps2; ps2.x=(a[0]*ps.x+a[1]*ps.y)+(a[2]*ps.z+a[3]); ps2.y=(a[4]*ps.x+a[5]*ps.y)+(a[6]*ps.z+a[7]); ps2.z=(a[8]*ps.x+a[9]*ps.y)+(a[10]*ps.z+a[11]);
+          if(o.Simulate2D)ps2.y=ps.y;
+          const double dx=ps2.x-ps.x, dy=ps2.y-ps.y, dz=ps2.z-ps.z;
+          o.UpdatePos(ps,dx,dy,dz,false,pid);
+          o.Velrhop[pid].x=float(dx/stepdt); o.Velrhop[pid].y=float(dy/stepdt); o.Velrhop[pid].z=float(dz/stepdt);
+        }
+      }
+    }
+  });
+}
 int orc_set_symplectic_dtpre(orc_state *s,double dt){ s->o.SymplecticDtPre=dt; return DSPH_OK; }
 int orc_set_verletstep(orc_state *s,int v){ s->o.VerletStep=v; return DSPH_OK; }
 int orc_pips(orc_state *s,uint64_t *fr,uint64_t *fc,uint64_t *br,uint64_t *bc){

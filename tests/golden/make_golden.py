@@ -64,6 +64,13 @@ CASES = [
     # initial state and at the listed steps; "gauges:" injects the <special><gauges> block below into Case.xml
     ("db_sym_wend_art_ddt2_gauges", "dambreak", 3000, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2", "gauges:"], [0, 20, 60], 61),
     ("db_ver_wend_art_ddt2_gauges", "dambreak", 6000, ["tstep=1", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2", "verletsteps=10", "gauges:"], [35], 36),
+    # moving boundaries (a plate right of the water column): gate lifted at constant speed for 0.004 s then at rest (mvrect -> wait: the
+    # chain ends inside a step), flap oscillating about its lower edge (mvrotsinu: matrix motion) and piston oscillating along x
+    # (mvrectsinu); the harness logs what JDsMotion computed at every step (motionlog) next to the usual stages
+    ("mv_sym_gate_rect_wait", "movgate", 3000, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2"], [0, 9, 30], 31),
+    ("mv_ver_flap_rotsinu", "movflap", 3000, ["tstep=1", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=1", "verletsteps=10"], [0, 25], 26),
+    ("mv_sym_piston_rectsinu_cubic", "movpiston", 3000, ["tstep=2", "tkernel=1", "tvisco=1", "visco=0.1", "ddt=2", "shifting=3", "shiftcoef=-2"], [25], 26),
+    ("mv2d_sym_flap_rotsinu_mdbc", "movflap2d", 3000, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=1", "boundary=2"], [25], 26),
     ("db_ver_wend_art_ddt1_rhopout", "dambreak", 3000, ["tstep=1", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=1", "verletsteps=3", "xml:RhopOutMax=1002.14", "xml:RhopOutMin=999.2"], [12, 30], 31),
 ]
 
@@ -128,7 +135,7 @@ def run(name, kind, nptarget, opts, steps, nsteps, outdir):
                 "nsteps": np.uint32(nsteps), "case/caseposmin": np.array(cd.caseposmin), "case/caseposmax": np.array(cd.caseposmax)}
         if "boundary=2" in opts:
             pack["case/normals"] = dsph.case_normals(tmp, "Case")
-        if "gauges:" in opts:
+        if "gauges:" in opts or kind.startswith("mov"):
             pack["case/xml"] = np.frombuffer(open(xmlfile, "rb").read(), np.uint8).copy()
         for f in sorted(os.listdir(os.path.join(tmp, "dump"))):
             d = read_dump(os.path.join(tmp, "dump", f))

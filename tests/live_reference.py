@@ -37,6 +37,7 @@ def live_golden(name, kind, np_target, opts, steps, nsteps, threads=None):
         cd = dsph.load_case(tmp, "Case")
         pack = {"config": np.frombuffer(bytes(cd.cfg), np.uint8).copy(), "case/idp": cd.idp, "case/pos": cd.pos, "case/velrhop": cd.velrhop,
                 "case/code": cd.codes(), "case/npb": np.uint32(cd.npb), "steps": np.array(steps, np.uint32), "nsteps": np.uint32(nsteps)}
+        pack["case/xml"] = np.frombuffer(open(os.path.join(tmp, "Case.xml"), "rb").read(), np.uint8).copy()
         for f in sorted(os.listdir(os.path.join(tmp, "dump"))):
             d = read_dump(os.path.join(tmp, "dump", f))
             for k, v in d.items():

@@ -19,6 +19,9 @@ GOLDEN_CASES = ["db_sym_wend_art_ddt2", "db_ver_cubic_art_ddt1_shift", "db_sym_w
                 "nn3_2d_sym_fda_lam_ddt3_shift", "nn3_sym_sph_conseq_ddt2"]
 # mDBC boundary correction: dumps of the reference with Boundary=2; the CPU checker has no mDBC, the CUDA path is compared with the
 # reference directly (tests/test_gpu_parity.py)
+# moving boundaries: the mDBC one needs normals, which the CPU checker does not carry
+MOVING_CASES = ["mv_sym_gate_rect_wait", "mv_ver_flap_rotsinu", "mv_sym_piston_rectsinu_cubic"]
+MOVING_MDBC_CASES = ["mv2d_sym_flap_rotsinu_mdbc"]
 MDBC_CASES = ["db_sym_wend_art_ddt1_mdbc", "db_sym_cubic_art_ddt2_mdbccorr", "db2d_ver_wend_art_ddt1_mdbc"]
 GPU_PENDING = []                             # cases the CUDA path does not cover yet
 
@@ -54,7 +57,8 @@ class Golden:
         return {k[len(pre):]: self.z[k] for k in self.z.files if k.startswith(pre)}
 
     def has(self, step, stage):
-        return ("s%04d_%s/np" % (step, stage)) in self.z.files
+        pre = "s%04d_%s/" % (step, stage)
+        return any(k.startswith(pre) for k in self.z.files)
 
 
 def make_ctx(lib, cfg, capacity=0):
@@ -181,7 +185,52 @@ def run_step_stages(lib, g: Golden, step, tol, capacity=0):
     assert np.array_equal(st["dcell"][same], u["dcell"][same]), "dcell after update"
     assert results["u_pos"] <= tol["pos"] and results["u_velrhop"] <= tol["state"], results
     ctx.close()
+    if g.has(step, "motion") and g.has(step, "dmot"):
+        # RunMotion + RunCellDivide of the reference's own updated state with the motion data JDsMotion computed: moved positions,
+        # velocities, cells and the re-sorted boundary must be those of the dump, bit for bit (double adds, unfused matrix products)
+        stepdt = float(g.stage(step, "end")["stepdt"])
+        c3 = make_ctx(lib, cfg, capacity)
+        upload_state(c3, u, cfg)
+        c3.motion_run(motion_from_dump(g.stage(step, "motion")), stepdt)
+        c3.celldiv(True)
+        dm = g.stage(step, "dmot")
+        check_divide(c3, dm)
+        if "boundnormal" in dm and lib.prefix == "dsph_":
+            npb = int(dm["npb"])
+            results["motion_normals"] = float(np.abs(c3.boundnormals(npb) - dm["boundnormal"][:npb]).max())
+            assert results["motion_normals"] <= 1e-7, results
+        c3.close()
     return results
+
+
+def motion_from_dump(m):
+    """s<step>_motion dump of the harness (StMotionData of every object) -> list of capi.MotionData."""
+    nobj = int(m["nobj"])
+    head = np.asarray(m["head"]).reshape(nobj, 3); val = np.asarray(m["val"]).reshape(nobj, 22)
+    out = []
+    for i in range(nobj):
+        d = capi.MotionData()
+        d.idbegin, d.count, d.type = int(head[i, 0]), int(head[i, 1]), int(head[i, 2])
+        d.linmov[:] = list(val[i, 0:3]); d.linvel[:] = list(val[i, 3:6]); d.matmov[:] = list(val[i, 6:22])
+        out.append(d)
+    return out
+
+
+def motion_log(g):
+    """Per-step log of the harness: (timestep, dt, [type, linmov3, linvel3, matmov16] per object) for every step of the run."""
+    z = g.z
+    key = "s%04d_motionlog" % g.nsteps
+    nobj = int(z[key + "/nobj"])
+    tdt = np.asarray(z[key + "/t_dt"]).reshape(-1, 2)
+    val = np.asarray(z[key + "/val"]).reshape(tdt.shape[0], nobj, 23)
+    return tdt, val
+
+
+def write_case_xml(g, directory, casename="Case"):
+    """Case.xml of a golden (stored for the cases whose host-side definitions live in it: gauges, motion)."""
+    import os
+    with open(os.path.join(directory, casename + ".xml"), "wb") as f:
+        f.write(bytes(g.z["case/xml"]))
 
 
 def run_trajectory(lib, g: Golden, capacity=0):
@@ -199,9 +248,40 @@ def run_trajectory(lib, g: Golden, capacity=0):
         ctx.set_boundnormals((2.0 * z["case/normals"][idp[:npb]]).astype(np.float32))
     ctx.celldiv(True)
     t = 0.0
-    for _ in range(g.nsteps):
-        dt, _ = ctx.step()
-        t += dt
+    moving = int(cfg.casenmoving) > 0
+    if moving and lib.prefix == "dsph_":
+        # the product evaluates the motion laws of Case.xml itself (host/motion.cpp) inside dsph_step
+        import tempfile
+        import dualsphysics_multilayer_b200 as dsph
+        with tempfile.TemporaryDirectory() as tmp:
+            write_case_xml(g, tmp)
+            motion = dsph.CaseMotion(tmp, "Case")
+        ctx.motion_attach(motion)
+    if moving and lib.prefix != "dsph_":
+        # the checker is driven stage by stage with the motion data the reference logged for every step
+        tdt, val = motion_log(g)
+        head = np.asarray(g.stage(int(g.steps[0]), "motion")["head"]).reshape(-1, 3)
+        for s in range(g.nsteps):
+            objs = []
+            for i in range(val.shape[1]):
+                d = capi.MotionData(); d.idbegin, d.count, d.type = int(head[i, 0]), int(head[i, 1]), int(val[s, i, 0])
+                d.linmov[:] = list(val[s, i, 1:4]); d.linvel[:] = list(val[s, i, 4:7]); d.matmov[:] = list(val[s, i, 7:23])
+                objs.append(d)
+            if g.symplectic:
+                dt = ctx.symplectic_dtpre
+                fp = ctx.forces(capi.INTERSTEP_SYMPREDICTOR); ctx.step_sympre(dt); ctx.celldiv(True)
+                fc = ctx.forces(capi.INTERSTEP_SYMCORRECTOR); ctx.step_symcor(dt)
+                ctx.symplectic_dtpre = min(fp.dt, fc.dt)
+            else:
+                dt = ctx.forces(capi.INTERSTEP_VERLET).dt
+                ctx.step_verlet(dt)
+            ctx.motion_run(objs, dt)
+            ctx.celldiv(True)
+            t += dt
+    else:
+        for _ in range(g.nsteps):
+            dt, _ = ctx.step()
+            t += dt
     fin = g.stage(g.nsteps, "final")
     st = ctx.download()
     out = dict(time=abs(t - float(fin["timestep"])) / float(fin["timestep"]), np=(ctx.np_, int(fin["np"])))

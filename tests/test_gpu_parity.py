@@ -28,7 +28,7 @@ def tol_for(name):
 TOL["mdbc_rhop"] = 1e-5
 
 
-@pytest.mark.parametrize("name", parity.GOLDEN_CASES + parity.MDBC_CASES)
+@pytest.mark.parametrize("name", parity.GOLDEN_CASES + parity.MDBC_CASES + parity.MOVING_CASES + parity.MOVING_MDBC_CASES)
 def test_gpu_stages_vs_reference(gpu_lib, name):
     g = Golden(name)
     for step in g.steps:
@@ -36,7 +36,7 @@ def test_gpu_stages_vs_reference(gpu_lib, name):
         print(name, step, res)
 
 
-@pytest.mark.parametrize("name", parity.GOLDEN_CASES + parity.MDBC_CASES)
+@pytest.mark.parametrize("name", parity.GOLDEN_CASES + parity.MDBC_CASES + parity.MOVING_CASES + parity.MOVING_MDBC_CASES)
 def test_gpu_trajectory_vs_reference(gpu_lib, name):
     g = Golden(name)
     out = parity.run_trajectory(gpu_lib, g, capacity=20000)
@@ -394,6 +394,23 @@ def test_gpu_stages_vs_live_reference(gpu_lib, name, np_target, steps, nsteps):
         out = parity.run_trajectory(gpu_lib, g, capacity=int(cd.np_ * 1.1) + 1000)
         print(name, "trajectory", out)
         assert out["np"][0] == out["np"][1] and out["time"] < 1e-5 and out["pos"] < 1e-6 and out["velrhop"] < 1e-4
+
+
+def test_gpu_moving_piston_vs_live_reference(gpu_lib):
+    """Moving boundaries at 150 k particles against the reference's JSphCpuSingle executed now: an oscillating piston next to the water
+    column (mvrectsinu).  Stages of two steps (the motion stage bit-exact) and the 15-step trajectory with the library evaluating the
+    motion laws of Case.xml itself."""
+    import live_reference
+    if not live_reference.available():
+        pytest.skip("oracle/_ref/ref_harness52 or bin/mkcase missing")
+    g, cd = live_reference.live_golden("movpiston_150k", "movpiston", 150000, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2"], [0, 14], 15)
+    assert int(cd.cfg.casenmoving) > 1000
+    for step in g.steps:
+        res = parity.run_step_stages(gpu_lib, g, step, TOL, capacity=int(cd.np_ * 1.1) + 1000)
+        print("movpiston_150k", step, res)
+    out = parity.run_trajectory(gpu_lib, g, capacity=int(cd.np_ * 1.1) + 1000)
+    print("movpiston_150k trajectory", out)
+    assert out["np"][0] == out["np"][1] and out["time"] < 1e-5 and out["pos"] < 1e-6 and out["velrhop"] < 1e-4
 
 
 def test_gpu_production_kernel_vs_ieee_kernel_at_20m(gpu_lib):

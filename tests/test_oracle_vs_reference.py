@@ -19,7 +19,7 @@ def tol_for(name):
     return TOL
 
 
-@pytest.mark.parametrize("name", parity.GOLDEN_CASES)
+@pytest.mark.parametrize("name", parity.GOLDEN_CASES + parity.MOVING_CASES)
 def test_oracle_stages(oracle_lib, name):
     g = Golden(name)
     for step in g.steps:
@@ -27,7 +27,7 @@ def test_oracle_stages(oracle_lib, name):
         print(name, step, res)
 
 
-@pytest.mark.parametrize("name", parity.GOLDEN_CASES)
+@pytest.mark.parametrize("name", parity.GOLDEN_CASES + parity.MOVING_CASES)
 def test_oracle_trajectory(oracle_lib, name):
     g = Golden(name)
     out = parity.run_trajectory(oracle_lib, g)

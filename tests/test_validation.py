@@ -224,3 +224,56 @@ def test_gpu_driver_runs_mdbc_case_like_the_reference(gpu_lib, tmp_path):
     assert np.array_equal(a.idp[oa], fin["idp"][ob])
     assert np.abs(a.pos[oa] - fin["pos"][ob]).max() < 1e-6
     assert np.linalg.norm((a.velrhop[oa] - fin["velrhop"][ob]).astype(np.float64)) / np.linalg.norm(fin["velrhop"][ob].astype(np.float64)) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kind,opts", [("mv_sym_gate_rect_wait", "movgate", ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2"]),
+                                            ("mv_ver_flap_rotsinu", "movflap", ["tstep=1", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=1", "verletsteps=10"])])
+def test_gpu_driver_runs_moving_boundary_case_like_the_reference(gpu_lib, tmp_path, name, kind, opts):
+    """bin/dsph_b200 on a case with a moving object (<moving> block + <motion> laws in Case.xml): its last PART equals the final state the
+    reference CPU solver reached after the same number of steps (golden dumps mv_*), moved plate included."""
+    import subprocess
+    from parity import Golden
+    g = Golden(name)
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    mkcase = os.path.join(root, "dualsphysics_multilayer_b200", "bin", "mkcase")
+    subprocess.check_call([mkcase, kind, "3000", str(tmp_path), "Case"] + opts, stdout=subprocess.DEVNULL)
+    cd = dsph.load_case(str(tmp_path), "Case")
+    assert np.array_equal(cd.pos, g.z["case/pos"]) and int(cd.cfg.casenmoving) > 0
+    out = tmp_path / "out"
+    dsph.run_case(str(tmp_path), "Case", str(out), nsteps=g.nsteps, timeout=1e-5)
+    assert "Motion: 1 moving object" in open(str(out / "Run.out")).read()
+    a, ta, sa, _ = dsph.load_partset(str(out), g.nsteps)
+    fin = g.stage(g.nsteps, "final")
+    assert sa == g.nsteps and abs(ta - float(fin["timestep"])) <= 1e-6 * ta
+    oa = np.argsort(a.idp); ob = np.argsort(fin["idp"])
+    assert np.array_equal(a.idp[oa], fin["idp"][ob])
+    nf, nm = int(cd.cfg.casenfixed), int(cd.cfg.casenmoving)
+    moved = np.abs(a.pos[oa][nf:nf + nm] - cd.pos[np.argsort(cd.idp)][nf:nf + nm]).max()
+    assert moved > 1e-4, moved                                        # the plate did move
+    assert np.abs(a.pos[oa][nf:nf + nm] - fin["pos"][ob][nf:nf + nm]).max() < 1e-12       # and exactly as in the reference run
+    assert np.abs(a.pos[oa] - fin["pos"][ob]).max() < 1e-6
+    assert np.linalg.norm((a.velrhop[oa] - fin["velrhop"][ob]).astype(np.float64)) / np.linalg.norm(fin["velrhop"][ob].astype(np.float64)) < 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_driver_slab_run_with_moving_piston_matches_single_gpu_run(gpu_lib, tmp_path):
+    """A moving object in an x-slab run: every rank evaluates the motion laws and moves the plate particles it owns; halo copies of the
+    plate are refreshed by the exchange.  -mgpu:2 against the single-GPU run of the same case."""
+    import subprocess
+    if dsph.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    mkcase = os.path.join(root, "dualsphysics_multilayer_b200", "bin", "mkcase")
+    subprocess.check_call([mkcase, "movpiston", "200000", str(tmp_path), "Case"], stdout=subprocess.DEVNULL)
+    one = tmp_path / "one"; two = tmp_path / "two"
+    dsph.run_case(str(tmp_path), "Case", str(one), nsteps=30, timeout=2e-4)
+    dsph.run_case(str(tmp_path), "Case", str(two), nsteps=30, timeout=2e-4, mgpu=2)
+    last = max(int(f[5:9]) for f in os.listdir(str(one)) if f.startswith("Part_0") and f.endswith(".bi4"))
+    a, ta, sa, npa = dsph.load_partset(str(one), last)
+    b, tb, sb, npb_ = dsph.load_partset(str(two), last)
+    assert (npa, npb_) == (1, 2) and sa == sb and abs(ta - tb) <= 1e-9 * ta
+    ia, pa, va = _sorted_state(a); ib, pb, vb = _sorted_state(b)
+    assert np.array_equal(ia, ib)
+    assert np.abs(pa - pb).max() < 1e-7
+    assert np.linalg.norm((va - vb).astype(np.float64)) / np.linalg.norm(va.astype(np.float64)) < 1e-5
