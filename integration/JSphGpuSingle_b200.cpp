@@ -15,16 +15,18 @@
 //   JSphGpuSingle::ComputeStep_Ver      S/JSphGpuSingle.cpp:548-560   -> dsph_forces_run / dsph_step_verlet
 //   JSphGpuSingle::RunGaugeSystem       S/JSphGpuSingle.cpp:776-786   -> (cases with <gauges> are refused: the reference's gauge objects read its own arrays)
 //   JSphGpu::ParticlesDataDown          S/JSphGpu.cpp:556-590         -> dsph_particles_download (what SaveData stores in the PART files)
+//   JSphGpu::RunMotion                  S/JSphGpu.cpp:1035-1075       -> dsph_motion_run with the StMotionData of the reference's JDsMotion
 //   JCellDivGpu::GetDomainLimits        S/JCellDivGpu.cpp             -> cell domain of dsph_celldiv_last_info (PART header DomainMin/Max)
 //
 // Particle state lives in the dsph context from the first RunCellDivide on (the reference's own device arrays, allocated by its
-// ConfigDomain, are left untouched).  Scope = the scope of the library: DBC boundaries, no moving / floating bodies, no inlet,
+// ConfigDomain, are left untouched).  Scope = the scope of the library: DBC boundaries, moving boundaries (JSphGpu::RunMotion -> dsph_motion_run), no floating bodies, no inlet,
 // no damping / relaxation zones (refused loudly below).
 #include "JSphGpuSingle.h"
 #include "JCellDivGpuSingle.h"
 #include "JSphShifting.h"
 #include "JDsGaugeSystem.h"
 #include "JDsFixedDt.h"
+#include "JDsMotion.h"
 #include "JDsPartsOut.h"
 #include "JPartsLoad4.h"
 #include "JDsTimersGpu.h"
@@ -55,7 +57,8 @@ void Check(int rc,const char *what){
 //==============================================================================
 void JSphGpuSingle::RunCellDivide(bool updateperiodic){
   if(!Ctx){
-    if(CaseNmoving || CaseNfloat)Run_Exceptioon("libdsph_b200 binding: moving and floating particles are outside the scope of the library.");
+    if(CaseNfloat)Run_Exceptioon("libdsph_b200 binding: floating bodies are outside the scope of the library.");
+    if(CaseNmoving && (WaveGen || MLPistons))Run_Exceptioon("libdsph_b200 binding: wave generation and multi-layer pistons are outside the scope of the library.");
     if(TBoundary!=BC_DBC)Run_Exceptioon("libdsph_b200 binding: only DBC boundaries.");
     if(InOut || Damping || RelaxZones || MLPistons || AccInput)Run_Exceptioon("libdsph_b200 binding: inlet/outlet, damping, relaxation zones, pistons and external accelerations are outside the scope of the library.");
     dsph_config c; memset(&c,0,sizeof(c));
@@ -119,6 +122,7 @@ void JSphGpuSingle::Interaction_Forces(TpInterStep interstep){
 //==============================================================================
 double JSphGpuSingle::ComputeStep_Sym(){
   const double dt=SymplecticDtPre;
+  if(CaseNmoving)CalcMotion(dt);               // the reference's JDsMotion (S/JSphGpuSingle.cpp:571)
   //-Predictor
   Interaction_Forces(INTERSTEP_SymPredictor);
   const double ddt_p=DtVariable(false);
@@ -143,10 +147,35 @@ double JSphGpuSingle::ComputeStep_Sym(){
 double JSphGpuSingle::ComputeStep_Ver(){
   Interaction_Forces(INTERSTEP_Verlet);
   const double dt=DtVariable(true);
+  if(CaseNmoving)CalcMotion(dt);               // S/JSphGpuSingle.cpp:551
   Timersg->TmStart(TMG_SuComputeStep,false);
   Check(dsph_step_verlet(Ctx,dt),"dsph_step_verlet");
   Timersg->TmStop(TMG_SuComputeStep,false);
   return(dt);
+}
+
+//==============================================================================
+/// Predefined motion of the moving boundaries (S/JSphGpu.cpp:1035-1075): the reference's JDsMotion has computed the motion data of the
+/// step (JSph::CalcMotion, called by ComputeStep_Sym / _Ver below like in the reference); the library applies it to its particles.
+//==============================================================================
+void JSphGpu::RunMotion(double stepdt){
+  BoundChanged=false;
+  if(!Ctx || !DsMotion->GetActiveMotion())return;
+  const unsigned nref=DsMotion->GetNumObjects();
+  std::vector<dsph_motiondata> objs(nref);
+  for(unsigned ref=0;ref<nref;ref++){
+    const StMotionData& m=DsMotion->GetMotionData(ref);
+    dsph_motiondata &d=objs[ref]; memset(&d,0,sizeof(d));
+    d.idbegin=m.idbegin; d.count=m.count;
+    d.type=(m.type==MOTT_Linear? DSPH_MOTION_LINEAR: (m.type==MOTT_Matrix? DSPH_MOTION_MATRIX: DSPH_MOTION_NONE));
+    d.linmov[0]=m.linmov.x; d.linmov[1]=m.linmov.y; d.linmov[2]=m.linmov.z;
+    d.linvel[0]=m.linvel.x; d.linvel[1]=m.linvel.y; d.linvel[2]=m.linvel.z;
+    const tmatrix4d &t=m.matmov;
+    const double mt[16]={t.a11,t.a12,t.a13,t.a14,t.a21,t.a22,t.a23,t.a24,t.a31,t.a32,t.a33,t.a34,t.a41,t.a42,t.a43,t.a44};
+    memcpy(d.matmov,mt,sizeof(mt));
+  }
+  if(dsph_motion_run(Ctx,objs.data(),nref,stepdt)!=DSPH_OK)Run_Exceptioon(string("libdsph_b200: ")+dsph_last_error());
+  BoundChanged=true;
 }
 
 //==============================================================================

@@ -1,5 +1,5 @@
 """The compiled drop-in: oracle/_ref/DualSPHysics5.2_b200dropin is the REFERENCE's own GPU program (main.cpp, JSph,
-JSphGpu, JSphGpuSingle ... compiled from the unmodified sources by `make -C oracle gpu52_b200`) with seven member functions rebound to
+JSphGpu, JSphGpuSingle ... compiled from the unmodified sources by `make -C oracle gpu52_b200`) with eight member functions rebound to
 libdsph_b200.so by integration/JSphGpuSingle_b200.cpp.  On C1 (BASELINE.json configs[0], ~170 k particles) it must write the PART files
 the stock reference writes: same particles, same output instants, state within the tolerances of the 1-s validation."""
 import os
@@ -20,7 +20,7 @@ MKCASE = os.path.join(ROOT, "dualsphysics_multilayer_b200", "bin", "mkcase")
 
 
 def test_dropin_binary_is_the_reference_program_bound_to_the_library():
-    """CPU check: the binary exists where the reference was available, links libdsph_b200.so, and its seven rebound member functions
+    """CPU check: the binary exists where the reference was available, links libdsph_b200.so, and its eight rebound member functions
     are the binding's (strong) definitions."""
     if not os.path.exists(DROPIN):
         pytest.skip("oracle/_ref/DualSPHysics5.2_b200dropin not built here (make -C oracle gpu52_b200 needs /root/reference)")
@@ -29,9 +29,10 @@ def test_dropin_binary_is_the_reference_program_bound_to_the_library():
     nm = subprocess.run(["nm", "-C", DROPIN], stdout=subprocess.PIPE, text=True).stdout
     for sym in ("JSphGpuSingle::RunCellDivide(bool)", "JSphGpuSingle::Interaction_Forces(TpInterStep)", "JSphGpuSingle::ComputeStep_Sym()",
                 "JSphGpuSingle::ComputeStep_Ver()", "JSphGpuSingle::RunGaugeSystem(double, bool)",
-                "JSphGpu::ParticlesDataDown(unsigned int, unsigned int, bool, bool)", "JCellDivGpu::GetDomainLimits(bool, unsigned int) const"):
+                "JSphGpu::ParticlesDataDown(unsigned int, unsigned int, bool, bool)", "JCellDivGpu::GetDomainLimits(bool, unsigned int) const",
+                "JSphGpu::RunMotion(double)"):
         assert re.search(r" T " + re.escape(sym) + r"$", nm, flags=re.M), sym
-    assert re.search(r" U dsph_forces_run", nm) and re.search(r" U dsph_celldiv_run", nm)
+    assert re.search(r" U dsph_forces_run", nm) and re.search(r" U dsph_celldiv_run", nm) and re.search(r" U dsph_motion_run", nm)
     assert " T JSphGpuSingle::Run(" in nm and " T JSph::SaveData(" in nm          # the reference's own driver and output code
 
 
@@ -77,3 +78,31 @@ def test_gpu_dropin_writes_the_reference_part_files_on_c1(gpu_lib, tmp_path):
     print("drop-in vs reference CPU solver on C1:", rep)
     runout = open(os.path.join(tmp, "out_dropin", "Run.out")).read()
     assert "Particles of simulation (initial): " in runout and "NL-SortData" in runout
+
+
+@pytest.mark.gpu
+def test_gpu_dropin_runs_a_moving_boundary_case_like_the_reference(gpu_lib, tmp_path):
+    """Moving boundaries through the drop-in: the reference's own JDsMotion evaluates <motion>, JSphGpu::RunMotion (rebound) hands the
+    StMotionData to dsph_motion_run.  An oscillating piston next to the water column, 60 k particles, against the reference CPU solver."""
+    if not (os.path.exists(DROPIN) and os.path.exists(STOCKCPU)):
+        pytest.skip("drop-in or reference CPU binary not built")
+    tmp = str(tmp_path)
+    subprocess.check_call([MKCASE, "movpiston", "60000", tmp, "Case"], stdout=subprocess.DEVNULL)
+    opts = ["-svres:1", "-tmax:0.01", "-tout:0.005"]
+    _run(DROPIN, tmp, "out_dropin", ["-gpu"] + opts)
+    _run(STOCKCPU, tmp, "out_cpu", ["-cpu", "-ompthreads:%d" % min(os.cpu_count() or 1, 32)] + opts)
+    cd = dsph.load_case(tmp, "Case")
+    nf, nm = int(cd.cfg.casenfixed), int(cd.cfg.casenmoving)
+    rep = {}
+    for part in (1, 2):
+        da = os.path.join(tmp, "out_dropin", "data"); db = os.path.join(tmp, "out_cpu", "data")
+        ia, pa, va, ta, sa = _state(da if os.path.isdir(da) else os.path.join(tmp, "out_dropin"), part)
+        ib, pb, vb, tb, sb = _state(db if os.path.isdir(db) else os.path.join(tmp, "out_cpu"), part)
+        assert np.array_equal(ia, ib) and sa == sb and abs(ta - tb) <= 1e-7 * max(tb, 1e-3), (part, sa, sb, ta, tb)
+        plate = float(np.abs(pa[nf:nf + nm] - pb[nf:nf + nm]).max())
+        moved = float(np.abs(pa[nf:nf + nm, 0] - cd.pos[np.argsort(cd.idp)][nf:nf + nm, 0]).max())
+        dpos = float(np.abs(pa - pb).max())
+        dvel = float(np.linalg.norm((va - vb).astype(np.float64)) / np.linalg.norm(vb.astype(np.float64)))
+        rep[part] = dict(step=sa, plate_moved=moved, plate_diff=plate, dpos=dpos, dvelrhop=dvel)
+        assert moved > 1e-4 and plate == 0.0 and dpos <= 1e-6 and dvel <= 1e-5, rep
+    print("drop-in vs reference CPU solver, moving piston:", rep)
