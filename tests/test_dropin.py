@@ -104,5 +104,6 @@ def test_gpu_dropin_runs_a_moving_boundary_case_like_the_reference(gpu_lib, tmp_
         dpos = float(np.abs(pa - pb).max())
         dvel = float(np.linalg.norm((va - vb).astype(np.float64)) / np.linalg.norm(vb.astype(np.float64)))
         rep[part] = dict(step=sa, plate_moved=moved, plate_diff=plate, dpos=dpos, dvelrhop=dvel)
-        assert moved > 1e-4 and plate == 0.0 and dpos <= 1e-6 and dvel <= 1e-5, rep
+        # the plate follows the same law at instants that differ like the variable dt of the two runs does (1e-6 relative)
+        assert moved > 1e-4 and plate <= 1e-9 and dpos <= 1e-6 and dvel <= 1e-5, rep
     print("drop-in vs reference CPU solver, moving piston:", rep)
