@@ -70,6 +70,35 @@ __global__ void __launch_bounds__(DIV_THREADS) ker_div_limits(unsigned n,unsigne
   }
 }
 
+// the same over one range that mixes boundary and fluid particles (slab runs with periodic copies appended in any order): every
+// particle goes to the boundary (limb) or the fluid (limf) limits by the type bits of its code
+__global__ void __launch_bounds__(DIV_THREADS) ker_div_limits_bytype(unsigned n,const unsigned* __restrict__ dcell,
+  const typecode* __restrict__ code,unsigned domcellcode,unsigned* __restrict__ limb,unsigned* __restrict__ limf)
+{
+  unsigned mn[2][3]={{0xffffffffu,0xffffffffu,0xffffffffu},{0xffffffffu,0xffffffffu,0xffffffffu}}, mx[2][3]={{0,0,0},{0,0,0}};
+  for(unsigned p=blockIdx.x*blockDim.x+threadIdx.x;p<n;p+=gridDim.x*blockDim.x){
+    const unsigned rc=code[p];
+    if((rc&DSPH_CODE_MASKSPECIAL)<DSPH_CODE_OUTIGNORE){
+      const int t=((rc&DSPH_CODE_MASKTYPE)<DSPH_CODE_TYPE_FLOATING? 0: 1);
+      const unsigned rcell=dcell[p];
+      const unsigned c[3]={DcCellx(domcellcode,rcell),DcCelly(domcellcode,rcell),DcCellz(domcellcode,rcell)};
+      #pragma unroll
+      for(int k=0;k<3;k++){
+        if(t==0){ mn[0][k]=min(mn[0][k],c[k]); mx[0][k]=max(mx[0][k],c[k]); }
+        else{     mn[1][k]=min(mn[1][k],c[k]); mx[1][k]=max(mx[1][k],c[k]); }
+      }
+    }
+  }
+  #pragma unroll
+  for(int t=0;t<2;t++){
+    #pragma unroll
+    for(int k=0;k<3;k++){
+      const unsigned a=__reduce_min_sync(0xffffffffu,mn[t][k]), b=__reduce_max_sync(0xffffffffu,mx[t][k]);
+      if((threadIdx.x&31)==0){ unsigned *lim=(t? limf: limb); atomicMin(&lim[k],a); atomicMax(&lim[3+k],b); }
+    }
+  }
+}
+
 // limb/limf: raw limits of boundary / fluid particles.  useblim: recompute the cached boundary limits.
 __global__ void ker_div_prepare(const unsigned* __restrict__ limb,const unsigned* __restrict__ limf,int useblim,
   unsigned dcx,unsigned dcy,unsigned dcz,unsigned scelldiv,unsigned nptot,unsigned maxnctt,DivParams* __restrict__ dp)

@@ -410,6 +410,50 @@ void Engine::RunPeriodic(){
   }
 }
 
+// Slab runs: periodic copies along y / z are made AFTER the slab exchange, from every live particle of the rank (owned, freshly arrived
+// migrants and x-halo copies alike, so the copies at the edges of the cut faces exist too).  The stale copies were retired by the
+// classification of the exchange.  Sources of an axis = the particle blocks of the type + the copies earlier axes appended; the
+// order of the copies differs from the single-GPU list (S/JSphCpuSingle.cpp:182-213), which slab runs do not promise to reproduce.
+void Engine::RunPeriodicSlab(unsigned npb_owned,unsigned np_owned,unsigned nbrecv,unsigned nfrecv){
+  const int B=256;
+  struct Range{ unsigned ini,num; };
+  std::vector<Range> src[2];
+  src[0].push_back({0u,npb_owned}); src[0].push_back({np_owned,nbrecv});
+  src[1].push_back({npb_owned,np_owned-npb_owned}); src[1].push_back({np_owned+nbrecv,nfrecv});
+  for(unsigned cper=1;cper<3;cper++)if((cper==1&&cfg.periy)||(cper==2&&cfg.periz)){
+    const double *inc=(cper==1? k.periyinc: k.perizinc);
+    std::vector<Range> added[2];
+    for(unsigned ctype=0;ctype<2;ctype++)for(const Range &r:src[ctype]){
+      if(!r.num)continue;
+      PeriArgs pa; pa.n=r.num; pa.pini=r.ini;
+      for(int i=0;i<3;i++){ pa.inc[i]=inc[i]; pa.mapmin[i]=k.mapposmin[i]; pa.mapmax[i]=k.mapposmax[i]; }
+      pa.code=code[cur]; pa.pos=pos[cur];
+      unsigned *flags=rs.keys[0];
+      ker_peri_count<<<(r.num+B-1)/B,B,0,stm>>>(pa,flags); launches++;
+      SmallCopy(&hpind->scratch[0],flags+(r.num-1),4,stm);
+      if(DeviceExclusiveScan(flags,r.num,rs.chunksum,rs.chunksumcap,rs.chunksum2,rs.chunksum2cap,stm,&launches)<0)
+        throw EngineError(DSPH_ERR_STATE,"Scan scratch too small for the periodic pass.");
+      SmallCopy(&hpind->scratch[1],flags+(r.num-1),4,stm);
+      CUCHECK(cudaStreamSynchronize(stm));
+      const unsigned count=hpin->scratch[0]+hpin->scratch[1];
+      if(!count)continue;
+      if(size_t(np)+count>cap)throw EngineError(DSPH_ERR_STATE,"Periodic particles exceed the capacity of the context (create it with a larger np_capacity).");
+      PeriDupArrays d;
+      d.idp=idp[cur]; d.code=code[cur]; d.dcell=dcell[cur]; d.pos=pos[cur]; d.velrhop=velrhop[cur];
+      d.velrhopm1=(cfg.tstep==DSPH_STEP_VERLET? velrhopm1[cur]: nullptr);
+      d.pospre=(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre? pospre[cur]: nullptr);
+      d.velrhoppre=(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre? velrhoppre[cur]: nullptr);
+      d.spstau=(sps? spstau[cur]: nullptr);
+      ker_peri_duplicate<<<(r.num+B-1)/B,B,0,stm>>>(pa,flags,np,d,dc); launches++;
+      added[ctype].push_back({np,count});
+      np+=count;
+      if(!ctype)npbper+=count; else npfper+=count;
+    }
+    for(unsigned ctype=0;ctype<2;ctype++)for(const Range &r:added[ctype])src[ctype].push_back(r);
+  }
+  boundchanged=true; celltableok=false;
+}
+
 // ------------------------------------------------------------------------------------------------
 // RunCellDivide
 // ------------------------------------------------------------------------------------------------
@@ -432,8 +476,13 @@ void Engine::CellDivide(bool updateperiodic,dsph_divinfo *info){
     SmallCopy(limits,hpind->limitsinit,sizeof(init),stm);
     const int nsm=numsm*4;
     auto lim=[&](unsigned n,unsigned pini,unsigned *dst){ if(n){ ker_div_limits<<<std::min<unsigned>((n+B-1)/B,nsm),B,0,stm>>>(n,pini,dcell[cur],code[cur],k.domcellcode,dst); launches++; } };
-    if(!blimok){ lim(npb1,0,limits); lim(npb2,npb1+npf1,limits); }
-    lim(npf1,npb1,limits+6); lim(npf2,npb1+npf1+npb2,limits+6);
+    if(mgpu && k.periactive){      // slab + periodic: boundary and fluid copies are appended in any order behind the owned particles
+      if(nptot){ ker_div_limits_bytype<<<std::min<unsigned>((nptot+B-1)/B,nsm),B,0,stm>>>(nptot,dcell[cur],code[cur],k.domcellcode,limits,limits+6); launches++; }
+    }
+    else{
+      if(!blimok){ lim(npb1,0,limits); lim(npb2,npb1+npf1,limits); }
+      lim(npf1,npb1,limits+6); lim(npf2,npb1+npf1+npb2,limits+6);
+    }
     ker_div_prepare<<<1,1,0,stm>>>(limits,limits+6,blimok? 0: 1,k.domcells[0],k.domcells[1],k.domcells[2],unsigned(k.scelldiv),nptot,effnctt,divparams); launches++;
     blimok=true;
   }
@@ -797,7 +846,7 @@ void Engine::UpdateCellBound(){
   effkeybits=KeyBits(effnctt);
 }
 void Engine::MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi){
-  if(k.periactive)throw EngineError(DSPH_ERR_ARG,"x-slab decomposition cannot be combined with periodic boundaries yet.");
+  if(cfg.perix && nranks>1)throw EngineError(DSPH_ERR_ARG,"x-slab decomposition cannot be combined with periodic boundaries along x yet (y and z are supported).");
   if(nranks<1 || rank<0 || rank>=nranks || xlo>=xhi || xhi>k.domcells[0])throw EngineError(DSPH_ERR_ARG,"Invalid slab configuration.");
   if(nranks>1 && xhi-xlo<2u*MgHalo()+1u)throw EngineError(DSPH_ERR_ARG,"The slab is narrower than 2 halo widths + 1 cell.");
   mgpu=(nranks>1); mgrank=rank; mgnranks=nranks; mgxlo=xlo; mgxhi=xhi;

@@ -100,6 +100,7 @@ class Engine {
   // excluded fluid particles of every divide are kept on the host until the caller takes them (JDsPartsOut, S/JSph.cpp:2467-2471)
   bool keepout=false; std::vector<unsigned> outidp; std::vector<typecode> outcode; std::vector<double> outpos; std::vector<float> outvelrhop;
   void RunPeriodic();
+  void RunPeriodicSlab(unsigned npb_owned,unsigned np_owned,unsigned nbrecv,unsigned nfrecv);
   void CellDivide(bool updateperiodic,dsph_divinfo *info);
   void LastDivInfo(dsph_divinfo *info)const;
   void GetBeginCell(unsigned *h,unsigned capacity);

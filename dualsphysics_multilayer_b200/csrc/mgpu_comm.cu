@@ -334,7 +334,10 @@ void Engine::MgExchange(){
 }
 
 void Engine::MgCellDivide(dsph_divinfo *info){
+  const unsigned npb0=npb, np0=np;
   MgExchange();
+  // periodic copies along y / z of everything the rank holds now (received particles sit behind the np0 it had: boundary block, fluid block)
+  if(mgpu && (cfg.periy || cfg.periz))RunPeriodicSlab(npb0,np0,npbper,npfper);
   CellDivide(false,info);
 }
 
