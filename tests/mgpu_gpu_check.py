@@ -59,6 +59,8 @@ def main():
             dt, _ = ref.step()
             tr += dt
         st = ref.download()
+        keep = (st["code"] & dsph.capi.CODE_MASKSPECIAL) == dsph.capi.CODE_NORMAL      # periodic copies of the single-GPU run are not particles
+        st = {k: v[keep] for k, v in st.items()}
         idp = np.concatenate([g["idp"] for g in gathered]); pos = np.concatenate([g["pos"] for g in gathered]); vr = np.concatenate([g["velrhop"] for g in gathered])
         o1 = np.argsort(idp); o2 = np.argsort(st["idp"])
         same_set = len(idp) == len(st["idp"]) and np.array_equal(idp[o1], st["idp"][o2])
