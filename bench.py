@@ -365,22 +365,32 @@ def main():
     else:
         # weak scaling: DB(world*np) split into x-slabs of balanced work (fluid 1, boundary w); every rank generates only its slab
         nglobal_target = a.np * world
-        info = dsph.make_case_slab("dambreak", nglobal_target, 0, 0)          # constants + counts of the full case
+        if a.workload not in ("dambreak", "periodicbox"):
+            raise SystemExit("multi-GPU runs: --workload dambreak or periodicbox")
+        info = dsph.make_case_slab(a.workload, nglobal_target, 0, 0)          # constants + counts of the full case
         sc = C.c_double(); pm = (C.c_double * 3)(); dcl = (C.c_uint32 * 3)()
         L.check(L.fn("domain_info")(C.byref(info.cfg), C.byref(sc), pm, dcl))
         ncol = int(dcl[0])
-        # particles per lattice x-index of DB(N) (mkcase geometry: walls at index 0 and NX, bottom at k=0, water column
-        # a x 1.675a x 0.75a at x=0), mapped to cell columns with the arithmetic of the cell hash
-        dp = info.cfg.dp; a_len = 0.4
-        NX, NY, NZ = (int(round(v / dp)) for v in info.caseposmax)
-        FX, FY, FZ = min(int(round(a_len / dp)), NX - 1), NY - 1, min(int(round(0.75 * a_len / dp)), NZ - 1)
-        ii = np.arange(NX + 1)
-        percol = a.bound_weight * np.where((ii == 0) | (ii == NX), (NY + 1) * (NZ + 1), (NY + 1) + 2 * NZ).astype(np.float64)
-        percol[1:FX + 1] += FY * FZ                                     # work-weighted: fluid 1, boundary --bound-weight
-        colidx = ((ii * dp - pm[0]) / sc.value).astype(np.int64)
-        colcount = np.bincount(colidx, weights=percol, minlength=ncol)
-        cuts = mgpu.balanced_cuts(colcount, world, 4)
-        cd = dsph.make_case_slab("dambreak", nglobal_target, cuts[rank], cuts[rank + 1])
+        if a.workload == "periodicbox":
+            # PB(world*np): a ring of x-slabs (periodic along x through the exchange, along y and z by local copies); n^3 lattice, uniform work
+            nlat = int(round((info.caseposmax[0] - info.caseposmin[0]) / info.cfg.dp)) + 1
+            colidx = (((np.arange(nlat) + 0.5) * info.cfg.dp - pm[0]) / sc.value).astype(np.int64)
+            colcount = np.bincount(colidx, weights=np.full(nlat, float(nlat) * nlat), minlength=ncol)
+            cuts = mgpu.balanced_cuts(colcount, world, 4)
+            cd = dsph.make_case_slab("periodicbox", nglobal_target, cuts[rank], cuts[rank + 1])
+        else:
+            # particles per lattice x-index of DB(N) (mkcase geometry: walls at index 0 and NX, bottom at k=0, water column
+            # a x 1.675a x 0.75a at x=0), mapped to cell columns with the arithmetic of the cell hash
+            dp = info.cfg.dp; a_len = 0.4
+            NX, NY, NZ = (int(round(v / dp)) for v in info.caseposmax)
+            FX, FY, FZ = min(int(round(a_len / dp)), NX - 1), NY - 1, min(int(round(0.75 * a_len / dp)), NZ - 1)
+            ii = np.arange(NX + 1)
+            percol = a.bound_weight * np.where((ii == 0) | (ii == NX), (NY + 1) * (NZ + 1), (NY + 1) + 2 * NZ).astype(np.float64)
+            percol[1:FX + 1] += FY * FZ                                     # work-weighted: fluid 1, boundary --bound-weight
+            colidx = ((ii * dp - pm[0]) / sc.value).astype(np.int64)
+            colcount = np.bincount(colidx, weights=percol, minlength=ncol)
+            cuts = mgpu.balanced_cuts(colcount, world, 4)
+            cd = dsph.make_case_slab("dambreak", nglobal_target, cuts[rank], cuts[rank + 1])
         n = cd.np_
         code = cd.codes()
         ctx = dsph.create_context(cd.cfg, int(n * 1.5) + 200_000, local)

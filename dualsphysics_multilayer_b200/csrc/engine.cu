@@ -846,10 +846,11 @@ void Engine::UpdateCellBound(){
   effkeybits=KeyBits(effnctt);
 }
 void Engine::MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi){
-  if(cfg.perix && nranks>1)throw EngineError(DSPH_ERR_ARG,"x-slab decomposition cannot be combined with periodic boundaries along x yet (y and z are supported).");
+  if(cfg.perix && nranks>1 && (k.perixinc[1]!=0 || k.perixinc[2]!=0))throw EngineError(DSPH_ERR_ARG,"x-slabs with a sheared periodic face along x are not supported.");
   if(nranks<1 || rank<0 || rank>=nranks || xlo>=xhi || xhi>k.domcells[0])throw EngineError(DSPH_ERR_ARG,"Invalid slab configuration.");
   if(nranks>1 && xhi-xlo<2u*MgHalo()+1u)throw EngineError(DSPH_ERR_ARG,"The slab is narrower than 2 halo widths + 1 cell.");
   mgpu=(nranks>1); mgrank=rank; mgnranks=nranks; mgxlo=xlo; mgxhi=xhi;
+  mgring=(mgpu && cfg.perix!=0);     // periodic along x: rank 0 and rank nranks-1 are neighbours through the periodic face
   dc.ghosts=(k.periactive||mgpu)? 1: 0;
   UpdateCellBound();
   if(!mgpu)for(int i=0;i<3;i++)DevFree(mgscratch[i]);
@@ -882,14 +883,30 @@ void Engine::MgColumnCounts(unsigned *fluid,unsigned *bound,unsigned ncol){
   CUCHECK(cudaMemcpyAsync(bound,d+ncol,size_t(ncol)*4,cudaMemcpyDeviceToHost,stm));
   CUCHECK(cudaStreamSynchronize(stm));
 }
+// slab geometry of the kernels (ring of ranks when the case is periodic along x)
+void Engine::MgFillArgs(MgArgs &a){
+  memset(&a,0,sizeof(a));
+  a.np=np; a.npb=npb; a.xlo=mgxlo; a.xhi=mgxhi; a.sd=MgHalo();
+  a.domcellcode=k.domcellcode; a.dcell=dcell[cur]; a.code=code[cur]; a.pos=pos[cur];
+  a.ring=(mgring? 1: 0);
+  a.hasleft=(mgring || mgrank>0); a.hasright=(mgring || mgrank<mgnranks-1);
+  if(mgring){
+    a.wrapleft=(mgrank==0); a.wrapright=(mgrank==mgnranks-1);
+    const double sc=dc.scell_d;
+    a.bandwidth=double(MgHalo())*sc;
+    a.xs0=std::max(k.domposmin[0]+double(mgxlo)*sc,k.maprealposmin[0]);
+    a.xs1=std::min(k.domposmin[0]+double(mgxhi)*sc,k.maprealposmin[0]+k.maprealsize[0]);
+    a.xlen=k.maprealsize[0];
+    for(int i=0;i<3;i++){ a.shiftleft[i]=(a.wrapleft? -k.perixinc[i]: 0.0); a.shiftright[i]=(a.wrapright? k.perixinc[i]: 0.0); }   // perixinc.x = -length
+  }
+}
 // classification + per-class totals on the stream, no host synchronisation: totals land in mgscratch[1][0..7]
 void Engine::MgClassifyAsync(){
   if(!mgpu)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_count needs dsph_mgpu_config with more than one rank.");
   EnsureDcell();
   const unsigned nb=(np+MG_BLOCK-1)/MG_BLOCK;
   if(!np){ CUCHECK(cudaMemsetAsync(mgscratch[1],0,MG_CLASSES*sizeof(unsigned),stm)); return; }
-  MgArgs a; a.np=np; a.npb=npb; a.xlo=mgxlo; a.xhi=mgxhi; a.sd=MgHalo();
-  a.hasleft=(mgrank>0); a.hasright=(mgrank<mgnranks-1); a.domcellcode=k.domcellcode; a.dcell=dcell[cur]; a.code=code[cur];
+  MgArgs a; MgFillArgs(a);
   // one pass: retire the halo copies of the previous divide (dropped by the next sort), classify, count per block
   ker_mg_classify<<<nb,MG_BLOCK,0,stm>>>(a,(unsigned char*)mgscratch[2],mgscratch[0]); launches++;
   ker_mg_scanblocks<<<MG_CLASSES,1024,0,stm>>>(nb,mgscratch[0],mgscratch[1]); launches++;
@@ -908,11 +925,11 @@ void Engine::MgPackAsync(void *sendleft,void *sendright){
   if(!mgcounted)throw EngineError(DSPH_ERR_STATE,"dsph_mgpu_pack needs dsph_mgpu_count first.");
   mgcounted=false;
   const unsigned nb=(np+MG_BLOCK-1)/MG_BLOCK;
-  MgArgs a; a.np=np; a.npb=npb; a.xlo=mgxlo; a.xhi=mgxhi; a.sd=MgHalo();
-  a.hasleft=(mgrank>0); a.hasright=(mgrank<mgnranks-1); a.domcellcode=k.domcellcode; a.dcell=dcell[cur]; a.code=code[cur];
+  MgArgs a; MgFillArgs(a);
   const unsigned *counts=mgcounts;
   void *sendbuf[2]={sendleft,sendright};
   MgPackArrays sp; sp.idp=idp[cur]; sp.code=code[cur]; sp.pos=pos[cur]; sp.velrhop=velrhop[cur];
+  sp.dcell=dcell[cur]; for(int i=0;i<3;i++)sp.domposmin[i]=dc.domposmin[i]; sp.scell=dc.scell_d;
   sp.pospre=(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre? pospre[cur]: nullptr);
   sp.aux=(cfg.tstep==DSPH_STEP_SYMPLECTIC? (haspre? velrhoppre[cur]: nullptr): velrhopm1[cur]);
   sp.spstau=(sps? spstau[cur]: nullptr); sp.recbytes=MgRecordBytes();
@@ -929,9 +946,9 @@ void Engine::MgPackAsync(void *sendleft,void *sendright){
 // device-side totals; token = 10 words {to left: 4 totals, used; to right: 4 totals, used}
 void Engine::MgPackDirectAsync(void *peerleft,void *peerright,unsigned capleft,unsigned capright,unsigned *token){
   const unsigned nb=std::max(1u,(np+MG_BLOCK-1)/MG_BLOCK);
-  MgArgs a; a.np=np; a.npb=npb; a.xlo=mgxlo; a.xhi=mgxhi; a.sd=MgHalo();
-  a.hasleft=(mgrank>0); a.hasright=(mgrank<mgnranks-1); a.domcellcode=k.domcellcode; a.dcell=dcell[cur]; a.code=code[cur];
+  MgArgs a; MgFillArgs(a);
   MgPackArrays sp; sp.idp=idp[cur]; sp.code=code[cur]; sp.pos=pos[cur]; sp.velrhop=velrhop[cur];
+  sp.dcell=dcell[cur]; for(int i=0;i<3;i++)sp.domposmin[i]=dc.domposmin[i]; sp.scell=dc.scell_d;
   sp.pospre=(cfg.tstep==DSPH_STEP_SYMPLECTIC && haspre? pospre[cur]: nullptr);
   sp.aux=(cfg.tstep==DSPH_STEP_SYMPLECTIC? (haspre? velrhoppre[cur]: nullptr): velrhopm1[cur]);
   sp.spstau=(sps? spstau[cur]: nullptr); sp.recbytes=MgRecordBytes();

@@ -16,7 +16,7 @@ struct EngineError : public std::runtime_error {
   EngineError(int c,const std::string &m):std::runtime_error(m),code(c){}
 };
 
-struct ForceParams; struct StepArrays;
+struct ForceParams; struct StepArrays; struct MgArgs;
 
 struct HostPinned {
   DivParams dp;
@@ -109,7 +109,10 @@ class Engine {
   void ForcesLaunch(int interstep);
   void ForcesFinish(dsph_forceres *res);
   // x-slab multi-GPU
-  bool mgpu=false; int mgrank=0, mgnranks=1; unsigned mgxlo=0, mgxhi=0;
+  bool mgpu=false, mgring=false; int mgrank=0, mgnranks=1; unsigned mgxlo=0, mgxhi=0;
+  void MgFillArgs(MgArgs &a);
+  int MgLeft()const{ return mgring? (mgrank+mgnranks-1)%mgnranks: (mgrank>0? mgrank-1: -1); }
+  int MgRight()const{ return mgring? (mgrank+1)%mgnranks: (mgrank<mgnranks-1? mgrank+1: -1); }
   unsigned *mgscratch[3]={}; unsigned mgcounts[8]={}; bool mgcounted=false;
   unsigned *mgown=nullptr; unsigned mgowncap=0; bool mgownok=false;   // owned fluid particles of the current divide (force kernel variant 10)
   void MgBuildOwnList();

@@ -575,16 +575,22 @@ static void MakePeriodicBox(CaseData &cd,unsigned long long nptarget,unsigned se
   std::uniform_real_distribution<double> U(-1.0,1.0);
   const double A=0.1*cs0/10, k=2*3.14159265358979323846/L;
   cd.pos.clear(); cd.velrhop.clear(); cd.idp.clear();
+  for(int i=0;i<3;i++){ cd.caseposmin[i]=0.5*dp; cd.caseposmax[i]=(n-0.5)*dp; } // lattice extremes, not jittered positions
+  ComputeMapRealPos(cd);
+  SphConst kc; DeriveConstants(c,kc);
+  unsigned nextid=0;
   for(unsigned kz=0;kz<n;kz++)for(unsigned j=0;j<n;j++)for(unsigned i=0;i<n;i++){
     const double x=(i+0.5)*dp+0.05*dp*U(rng), y=(j+0.5)*dp+0.05*dp*U(rng), z=(kz+0.5)*dp+0.05*dp*U(rng);
+    const unsigned id=nextid++;
+    if(g_slab.on){ const unsigned cx=unsigned((x-kc.domposmin[0])/kc.scell); if(cx<g_slab.cxlo || cx>=g_slab.cxhi)continue; }   // (the random stream is consumed for every particle: the field does not depend on the slabs)
     cd.pos.push_back(x); cd.pos.push_back(y); cd.pos.push_back(z);
     cd.velrhop.push_back(float( A*sin(k*x)*cos(k*y)*cos(k*z)));
     cd.velrhop.push_back(float(-A*cos(k*x)*sin(k*y)*cos(k*z)));
     cd.velrhop.push_back(0.f);
     cd.velrhop.push_back(float(rho0));
-    cd.idp.push_back(unsigned(cd.idp.size()));
+    cd.idp.push_back(id);
   }
-  const unsigned np=unsigned(cd.idp.size());
+  const unsigned np=nextid;
   c.casenp=np; c.casenfixed=0; c.casenfluid=np;
   cd.blocks.clear(); cd.blocks.push_back({3,0,cd.mkfluidfirst+0,0,np});
   for(int i=0;i<3;i++){ cd.caseposmin[i]=0.5*dp; cd.caseposmax[i]=(n-0.5)*dp; } // lattice extremes, not jittered positions
@@ -625,7 +631,7 @@ void MakeTankNormals(CaseData &cd){
 }
 
 void MakeCaseSlab(CaseData &cd,const std::string &kind,unsigned long long nptarget,unsigned seed,unsigned cxlo,unsigned cxhi){
-  if(kind!="dambreak" && kind!="nn2layer")throw std::runtime_error("Slab generation is available for the dam-break cases only.");
+  if(kind!="dambreak" && kind!="nn2layer" && kind!="periodicbox")throw std::runtime_error("Slab generation is available for dambreak, nn2layer and periodicbox.");
   g_slab.on=true; g_slab.cxlo=cxlo; g_slab.cxhi=cxhi;
   try{ MakeCase(cd,kind,nptarget,seed); }catch(...){ g_slab.on=false; throw; }
   g_slab.on=false;

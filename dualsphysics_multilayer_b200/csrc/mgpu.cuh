@@ -26,6 +26,12 @@ struct MgArgs {
   int hasleft, hasright;
   unsigned domcellcode;
   const unsigned *dcell; typecode *code;
+  // periodic along x: the ranks form a ring; the left link of the first rank and the right link of the last rank cross the periodic face
+  int ring; int wrapleft, wrapright;
+  double xs0, xs1, xlen;      // physical x range of the slab inside the real domain, length of the period
+  double bandwidth;           // halo width in space (sd cells)
+  double shiftleft[3], shiftright[3];   // added to the position of halo copies sent through a wrapping link
+  const double *pos;
 };
 
 // classes per particle and direction; kind: 0 boundary ghost, 1 boundary migrant (only after the cuts moved: re-balancing),
@@ -39,6 +45,26 @@ __device__ __forceinline__ void MgClassify(unsigned p,const MgArgs &a,int &tolef
   if(cel==0xFFFFFFFFu)return;
   const unsigned cx=DcCellx(a.domcellcode,cel);
   const bool fluid=((rc&DSPH_CODE_MASKTYPE)==DSPH_CODE_TYPE_FLUID);
+  if(a.ring){
+    // Ring of slabs.  A particle that left through the periodic face was wrapped to the other end of the domain by the update
+    // (UpdatePos), so "left of the slab" / "right of the slab" is decided by the shorter way round; a step moves a particle by less than
+    // a cell, so that way is always the short one.
+    if(cx<a.xlo || cx>=a.xhi){
+      const double x=a.pos[3*size_t(p)];
+      double dr=x-a.xs1; if(dr<0)dr+=a.xlen;
+      double dl=a.xs0-x; if(dl<0)dl+=a.xlen;
+      if(dr<dl)toright=(fluid? 2: 1); else toleft=(fluid? 2: 1);
+    }
+    else{
+      // halo bands: whole cell columns at the cuts between slabs; at the periodic face the band is measured in space, because the
+      // shifted copy must fall inside the margin of the map (the face may cut the last real column anywhere)
+      if(a.wrapleft){ if(a.pos[3*size_t(p)]<a.xs0+a.bandwidth)toleft=(fluid? 3: 0); }
+      else if(cx<a.xlo+a.sd)toleft=(fluid? 3: 0);
+      if(a.wrapright){ if(a.pos[3*size_t(p)]>=a.xs1-a.bandwidth)toright=(fluid? 3: 0); }
+      else if(cx+a.sd>=a.xhi)toright=(fluid? 3: 0);
+    }
+    return;
+  }
   if(a.hasleft){
     if(cx<a.xlo)toleft=(fluid? 2: 1);
     else if(cx<a.xlo+a.sd)toleft=(fluid? 3: 0);
@@ -162,7 +188,8 @@ __global__ void ker_mg_column_counts(unsigned n,const unsigned* __restrict__ dce
 }
 
 struct MgPackArrays {
-  const unsigned *idp; typecode *code; const double *pos; const float4 *velrhop;
+  const unsigned *idp; typecode *code; double *pos; const float4 *velrhop;
+  unsigned *dcell; double domposmin[3]; double scell;    // ring: the local copy of a migrant that crossed the periodic face is moved back beyond the face
   const double *pospre; const float4 *aux;
   const float *spstau;      // laminar+SPS: 6 floats per particle appended to the record (record = 88 + 24 bytes)
   unsigned recbytes;        // 88 or 112
@@ -226,7 +253,13 @@ template<bool DIRECT> __global__ void __launch_bounds__(MG_BLOCK) ker_mg_pack(Mg
     const bool migrant=(kind==1 || kind==2);
     r.code=(migrant? rc: ((rc&(~DSPH_CODE_MASKSPECIAL))|DSPH_CODE_PERIODIC));   // migrants stay normal, halo copies are ghosts
     char *dst=(g<4? outleft: outright)+size_t(slot)*s.recbytes;
-    *reinterpret_cast<MgRecord*>(dst)=r;
+    const bool wrap=(a.ring && (g<4? a.wrapleft: a.wrapright));
+    MgRecord rw=r;
+    if(wrap && !migrant){          // halo copy through the periodic face: it appears beyond the face on the other side
+      const double *sh=(g<4? a.shiftleft: a.shiftright);
+      rw.pos[0]+=sh[0]; rw.pos[1]+=sh[1]; rw.pos[2]+=sh[2];
+    }
+    *reinterpret_cast<MgRecord*>(dst)=rw;
     if(s.spstau){
       float *tau=reinterpret_cast<float*>(dst+sizeof(MgRecord));
       #pragma unroll
@@ -234,7 +267,16 @@ template<bool DIRECT> __global__ void __launch_bounds__(MG_BLOCK) ker_mg_pack(Mg
     }
     if(migrant){ // local copy becomes a ghost when it is still inside the neighbour's halo band, else it is dropped
       const unsigned cx=DcCellx(a.domcellcode,a.dcell[p]);
-      const bool band=(g<4? (cx+a.sd>=a.xlo): (cx<a.xhi+a.sd));
+      bool band=(g<4? (cx+a.sd>=a.xlo): (cx<a.xhi+a.sd));
+      if(wrap){
+        // the update wrapped it to the other end of the domain (its position on the new owner); here it stays as the halo copy just
+        // beyond the face it crossed: the opposite of the shift that halo copies get on this link
+        const double *sh=(g<4? a.shiftleft: a.shiftright);
+        const double x=r.pos[0]-sh[0], y=r.pos[1]-sh[1], z=r.pos[2]-sh[2];
+        s.pos[3*size_t(p)]=x; s.pos[3*size_t(p)+1]=y; s.pos[3*size_t(p)+2]=z;
+        s.dcell[p]=DcCell(a.domcellcode,unsigned((x-s.domposmin[0])/s.scell),unsigned((y-s.domposmin[1])/s.scell),unsigned((z-s.domposmin[2])/s.scell));
+        band=true;
+      }
       s.code[p]=typecode((rc&(~DSPH_CODE_MASKSPECIAL))|(band? DSPH_CODE_PERIODIC: DSPH_CODE_OUTIGNORE));
     }
   }

@@ -165,7 +165,7 @@ void Engine::MgDirectSetup(){
   if(mgdirect>=0)return;
   NcclApi &N=Nccl();
   ncclComm_t comm=(ncclComm_t)mgcomm;
-  const int left=(mgrank>0? mgrank-1: -1), right=(mgrank<mgnranks-1? mgrank+1: -1);
+  const int left=MgLeft(), right=MgRight();
   const char *env=getenv("DSPH_MGPU_DIRECT");
   unsigned ok=(env && atoi(env)==0? 0u: 1u);
   MgHello me; memset(&me,0,sizeof(me));
@@ -187,8 +187,10 @@ void Engine::MgDirectSetup(){
   CUCHECK2(cudaMemsetAsync(dev,0,3*sizeof(MgHello),stm));
   CUCHECK2(cudaMemcpyAsync(dev,&me,sizeof(me),cudaMemcpyHostToDevice,stm));
   NCCLCHECK(N.GroupStart());
-  if(left>=0){  NCCLCHECK(N.Send(dev,sizeof(MgHello),ncclUint8,left,comm,stm));  NCCLCHECK(N.Recv(dev+1,sizeof(MgHello),ncclUint8,left,comm,stm)); }
-  if(right>=0){ NCCLCHECK(N.Send(dev,sizeof(MgHello),ncclUint8,right,comm,stm)); NCCLCHECK(N.Recv(dev+2,sizeof(MgHello),ncclUint8,right,comm,stm)); }
+  if(left>=0)NCCLCHECK(N.Send(dev,sizeof(MgHello),ncclUint8,left,comm,stm));
+  if(right>=0)NCCLCHECK(N.Send(dev,sizeof(MgHello),ncclUint8,right,comm,stm));
+  if(right>=0)NCCLCHECK(N.Recv(dev+2,sizeof(MgHello),ncclUint8,right,comm,stm));
+  if(left>=0)NCCLCHECK(N.Recv(dev+1,sizeof(MgHello),ncclUint8,left,comm,stm));
   NCCLCHECK(N.GroupEnd());
   MgHello nb[2];
   CUCHECK2(cudaMemcpyAsync(nb,dev+1,2*sizeof(MgHello),cudaMemcpyDeviceToHost,stm));
@@ -242,7 +244,7 @@ void Engine::MgDirectSetup(){
 void Engine::MgExchangeDirect(){
   NcclApi &N=Nccl();
   ncclComm_t comm=(ncclComm_t)mgcomm;
-  const int left=(mgrank>0? mgrank-1: -1), right=(mgrank<mgnranks-1? mgrank+1: -1);
+  const int left=MgLeft(), right=MgRight();
   const int q=mgdparity; mgdparity^=1;
   Stopwatch sw(mgprofile,stm);
   MgClassifyAsync();
@@ -252,8 +254,12 @@ void Engine::MgExchangeDirect(){
   MgPushAsync(mgdsend[0],mgdpeer[0][q],mgdsend[1],mgdpeer[1][q],mgcntdev);
   sw.Lap(mgphase_ms[3]);
   NCCLCHECK(N.GroupStart());
-  if(left>=0){  NCCLCHECK(N.Send(mgcntdev,5,ncclUint32,left,comm,stm));    NCCLCHECK(N.Recv(mgcntdev+16,5,ncclUint32,left,comm,stm)); }
-  if(right>=0){ NCCLCHECK(N.Send(mgcntdev+5,5,ncclUint32,right,comm,stm)); NCCLCHECK(N.Recv(mgcntdev+21,5,ncclUint32,right,comm,stm)); }
+  // order: sends (left, right), then receives (right, left).  In a ring of TWO ranks both neighbours are the same peer, and NCCL matches
+  // the operations with one peer in the order they were posted: what goes to the peer's right side must meet its "from right" receive.
+  if(left>=0)NCCLCHECK(N.Send(mgcntdev,5,ncclUint32,left,comm,stm));
+  if(right>=0)NCCLCHECK(N.Send(mgcntdev+5,5,ncclUint32,right,comm,stm));
+  if(right>=0)NCCLCHECK(N.Recv(mgcntdev+21,5,ncclUint32,right,comm,stm));
+  if(left>=0)NCCLCHECK(N.Recv(mgcntdev+16,5,ncclUint32,left,comm,stm));
   NCCLCHECK(N.GroupEnd());
   SmallCopyAsync(hpind->mgtoken,mgcntdev,10*sizeof(unsigned));
   SmallCopyAsync(hpind->mgtoken+10,mgcntdev+16,10*sizeof(unsigned));
@@ -279,8 +285,10 @@ void Engine::MgExchangeDirect(){
     }
     for(int d=0;d<2;d++)if(!rdirect[d]){ GrowBuffer(mgrecv[d],mgrecvcap[d],std::max<size_t>(nrecv[d],1)*rb); src[d]=mgrecv[d]; }
     NCCLCHECK(N.GroupStart());
-    if(left>=0){  if(!mydirect && nsend[0])NCCLCHECK(N.Send(mgsend[0],nsend[0]*rb,ncclUint8,left,comm,stm));   if(!rdirect[0] && nrecv[0])NCCLCHECK(N.Recv(mgrecv[0],nrecv[0]*rb,ncclUint8,left,comm,stm)); }
-    if(right>=0){ if(!mydirect && nsend[1])NCCLCHECK(N.Send(mgsend[1],nsend[1]*rb,ncclUint8,right,comm,stm));  if(!rdirect[1] && nrecv[1])NCCLCHECK(N.Recv(mgrecv[1],nrecv[1]*rb,ncclUint8,right,comm,stm)); }
+    if(left>=0 && !mydirect && nsend[0])NCCLCHECK(N.Send(mgsend[0],nsend[0]*rb,ncclUint8,left,comm,stm));
+    if(right>=0 && !mydirect && nsend[1])NCCLCHECK(N.Send(mgsend[1],nsend[1]*rb,ncclUint8,right,comm,stm));
+    if(right>=0 && !rdirect[1] && nrecv[1])NCCLCHECK(N.Recv(mgrecv[1],nrecv[1]*rb,ncclUint8,right,comm,stm));
+    if(left>=0 && !rdirect[0] && nrecv[0])NCCLCHECK(N.Recv(mgrecv[0],nrecv[0]*rb,ncclUint8,left,comm,stm));
     NCCLCHECK(N.GroupEnd());
   }
   mgcounted=false;
@@ -298,15 +306,17 @@ void Engine::MgExchange(){
   if(mgdirect==1){ MgExchangeDirect(); return; }
   NcclApi &N=Nccl();
   ncclComm_t comm=(ncclComm_t)mgcomm;
-  const int left=(mgrank>0? mgrank-1: -1), right=(mgrank<mgnranks-1? mgrank+1: -1);
+  const int left=MgLeft(), right=MgRight();
   Stopwatch sw(mgprofile,stm);
   // 1. classify, class totals -> mgscratch[1][0..7] (to left: 0..3, to right: 4..7)
   MgClassifyAsync();
   sw.Lap(mgphase_ms[0]);
   // 2. totals to the neighbours, theirs into mgcntdev[8..15] (from left: 8..11, from right: 12..15; zero without neighbour)
   NCCLCHECK(N.GroupStart());
-  if(left>=0){  NCCLCHECK(N.Send(mgscratch[1],4,ncclUint32,left,comm,stm));    NCCLCHECK(N.Recv(mgcntdev+8,4,ncclUint32,left,comm,stm)); }
-  if(right>=0){ NCCLCHECK(N.Send(mgscratch[1]+4,4,ncclUint32,right,comm,stm)); NCCLCHECK(N.Recv(mgcntdev+12,4,ncclUint32,right,comm,stm)); }
+  if(left>=0)NCCLCHECK(N.Send(mgscratch[1],4,ncclUint32,left,comm,stm));           // sends (left, right), receives (right, left): see MgExchangeDirect
+  if(right>=0)NCCLCHECK(N.Send(mgscratch[1]+4,4,ncclUint32,right,comm,stm));
+  if(right>=0)NCCLCHECK(N.Recv(mgcntdev+12,4,ncclUint32,right,comm,stm));
+  if(left>=0)NCCLCHECK(N.Recv(mgcntdev+8,4,ncclUint32,left,comm,stm));
   NCCLCHECK(N.GroupEnd());
   SmallCopyAsync(hpind->mgtot,mgscratch[1],8*sizeof(unsigned));
   SmallCopyAsync(hpind->mgtot+8,mgcntdev+8,8*sizeof(unsigned));
@@ -324,8 +334,10 @@ void Engine::MgExchange(){
   MgPackAsync(mgsend[0],mgsend[1]);
   sw.Lap(mgphase_ms[2]);
   NCCLCHECK(N.GroupStart());
-  if(left>=0){  if(nsend[0])NCCLCHECK(N.Send(mgsend[0],nsend[0]*rb,ncclUint8,left,comm,stm));   if(nrecv[0])NCCLCHECK(N.Recv(mgrecv[0],nrecv[0]*rb,ncclUint8,left,comm,stm)); }
-  if(right>=0){ if(nsend[1])NCCLCHECK(N.Send(mgsend[1],nsend[1]*rb,ncclUint8,right,comm,stm));  if(nrecv[1])NCCLCHECK(N.Recv(mgrecv[1],nrecv[1]*rb,ncclUint8,right,comm,stm)); }
+  if(left>=0 && nsend[0])NCCLCHECK(N.Send(mgsend[0],nsend[0]*rb,ncclUint8,left,comm,stm));
+  if(right>=0 && nsend[1])NCCLCHECK(N.Send(mgsend[1],nsend[1]*rb,ncclUint8,right,comm,stm));
+  if(right>=0 && nrecv[1])NCCLCHECK(N.Recv(mgrecv[1],nrecv[1]*rb,ncclUint8,right,comm,stm));
+  if(left>=0 && nrecv[0])NCCLCHECK(N.Recv(mgrecv[0],nrecv[0]*rb,ncclUint8,left,comm,stm));
   NCCLCHECK(N.GroupEnd());
   sw.Lap(mgphase_ms[3]);
   MgUnpackAsync(rcv,mgrecv[0],mgrecv[1]);

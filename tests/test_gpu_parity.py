@@ -262,7 +262,9 @@ def test_gpu_large_case_properties(gpu_lib):
 @pytest.mark.parametrize("kind", ["dambreak", "nn2layer", "dambreak:tstep=1,verletsteps=5,tvisco=2,visco=0.01,shiftmode=3,shiftcoef=-2",
                                   "dambreak@rebalance", "nn2layer@rebalance", "nn2layer:nn_velgrad=2", "nn2layer:nn_velgrad=2,tvisco=3",
                                   # periodic along y and z + slabs along x (periodic copies of owned particles, migrants and halo copies alike)
-                                  "periodicbox:perix=0", "periodicbox:perix=0,tstep=1,verletsteps=5"])
+                                  "periodicbox:perix=0", "periodicbox:perix=0,tstep=1,verletsteps=5",
+                                  # periodic along x too: the two ranks form a ring, halo copies cross the periodic face shifted by the period
+                                  "periodicbox", "periodicbox@rebalance", "periodicbox:tstep=1,verletsteps=5"])
 def test_gpu_two_slabs_equal_single_gpu(kind):
     """x-slab decomposition over 2 GPUs (NCCL send/recv halos + all-reduce dt) reproduces the single-GPU run."""
     import subprocess, sys, os, torch
