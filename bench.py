@@ -338,8 +338,8 @@ def main():
     import torch.distributed as dist
     import dualsphysics_multilayer_b200 as dsph
 
-    if world > 1 and a.workload != "dambreak":
-        raise SystemExit("bench.py: the x-slab runs use the dam-break workload")
+    if world > 1 and a.workload not in ("dambreak", "periodicbox"):
+        raise SystemExit("bench.py: the x-slab runs use the dam-break or the periodic-box workload")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
@@ -365,8 +365,6 @@ def main():
     else:
         # weak scaling: DB(world*np) split into x-slabs of balanced work (fluid 1, boundary w); every rank generates only its slab
         nglobal_target = a.np * world
-        if a.workload not in ("dambreak", "periodicbox"):
-            raise SystemExit("multi-GPU runs: --workload dambreak or periodicbox")
         info = dsph.make_case_slab(a.workload, nglobal_target, 0, 0)          # constants + counts of the full case
         sc = C.c_double(); pm = (C.c_double * 3)(); dcl = (C.c_uint32 * 3)()
         L.check(L.fn("domain_info")(C.byref(info.cfg), C.byref(sc), pm, dcl))

@@ -264,7 +264,11 @@ int dsph_mgpu_column_counts(dsph_ctx *ctx,uint32_t *fluid,uint32_t *bound,uint32
  *      token {totals, used} after the kernel announces "records landed", then the ONE host wait, then unpack.  Records that do
  *      not fit the neighbour's buffer fall back to ncclSend/ncclRecv for that exchange; DSPH_MGPU_DIRECT=0 (environment) or GPUs
  *      without peer access keep the ncclSend/ncclRecv transport altogether (dsph_mgpu_transport tells which is active).
- *        dsph_mgpu_celldiv = dsph_mgpu_exchange + dsph_celldiv_run(updateperiodic=0)
+ *        dsph_mgpu_celldiv = dsph_mgpu_exchange + periodic copies along y / z + dsph_celldiv_run(updateperiodic=0)
+ *      Periodic cases: along y and z every rank copies what it holds after the exchange (owned particles, arrivals and x-halo copies
+ *      alike); along x the ranks form a ring -- rank 0 and rank nranks-1 are neighbours through the periodic face, halo copies cross it
+ *      shifted by the period, and a particle that leaves through the face (wrapped by the update) migrates the short way round.  The
+ *      cuts still cover all the cell columns of the domain (the margin columns outside the real domain belong to the end ranks).
  *        dsph_mgpu_forces  = dsph_forces_launch + ncclAllReduce(max) of the four maxima + dsph_forces_finish
  *        dsph_mgpu_step    = dsph_step with those two in place of RunCellDivide / Interaction_Forces (S/JSphGpuSingle.cpp:548-596)
  *      dsph_mgpu_rebalance (collective) moves the cuts to the measured load: per-column histogram of owned particles (fluid 1,
