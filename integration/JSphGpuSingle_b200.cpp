@@ -19,7 +19,7 @@
 //   JCellDivGpu::GetDomainLimits        S/JCellDivGpu.cpp             -> cell domain of dsph_celldiv_last_info (PART header DomainMin/Max)
 //
 // Particle state lives in the dsph context from the first RunCellDivide on (the reference's own device arrays, allocated by its
-// ConfigDomain, are left untouched).  Scope = the scope of the library: DBC boundaries, moving boundaries (JSphGpu::RunMotion -> dsph_motion_run), no floating bodies, no inlet,
+// ConfigDomain, are left untouched).  Scope = the scope of the library: DBC and mDBC boundaries, moving boundaries (JSphGpu::RunMotion -> dsph_motion_run), no floating bodies, no inlet,
 // no damping / relaxation zones (refused loudly below).
 #include "JSphGpuSingle.h"
 #include "JCellDivGpuSingle.h"
@@ -59,7 +59,8 @@ void JSphGpuSingle::RunCellDivide(bool updateperiodic){
   if(!Ctx){
     if(CaseNfloat)Run_Exceptioon("libdsph_b200 binding: floating bodies are outside the scope of the library.");
     if(CaseNmoving && (WaveGen || MLPistons))Run_Exceptioon("libdsph_b200 binding: wave generation and multi-layer pistons are outside the scope of the library.");
-    if(TBoundary!=BC_DBC)Run_Exceptioon("libdsph_b200 binding: only DBC boundaries.");
+    if(TBoundary!=BC_DBC && TBoundary!=BC_MDBC)Run_Exceptioon("libdsph_b200 binding: DBC or mDBC boundaries.");
+    if(TBoundary==BC_MDBC && (SlipMode!=SLIP_Vel0 || UseNormalsFt))Run_Exceptioon("libdsph_b200 binding: mDBC with slip mode velocity=0 and without floating normals.");
     if(InOut || Damping || RelaxZones || MLPistons || AccInput)Run_Exceptioon("libdsph_b200 binding: inlet/outlet, damping, relaxation zones, pistons and external accelerations are outside the scope of the library.");
     dsph_config c; memset(&c,0,sizeof(c));
     c.tkernel=int(TKernel); c.tstep=int(TStep); c.tvisco=int(TVisco); c.tdensity=int(TDensity);
@@ -80,11 +81,19 @@ void JSphGpuSingle::RunCellDivide(bool updateperiodic){
     c.periyinc[0]=PeriYinc.x; c.periyinc[1]=PeriYinc.y; c.periyinc[2]=PeriYinc.z;
     c.perizinc[0]=PeriZinc.x; c.perizinc[1]=PeriZinc.y; c.perizinc[2]=PeriZinc.z;
     c.casenp=CaseNp; c.casenfixed=CaseNfixed; c.casenmoving=CaseNmoving; c.casenfloat=CaseNfloat; c.casenfluid=CaseNfluid;
+    c.tboundary=(TBoundary==BC_MDBC? (DSPH_BOUNDARY_MDBC|(MdbcCorrector? DSPH_BOUNDARY_MDBCCORRECTOR: 0)): 0);   // 0 = DBC (the value the library stores for it)
     c.partsoutmax_on=0;                                    // JSph::Run checks Np<NpMinimum itself
     const unsigned capacity=Np+Np/10+1024;
     Check(dsph_ctx_create(&Ctx,GpuInfo->GetGpuId(),&c,capacity),"dsph_ctx_create");
     // initial state as ConfigDomain left it on the host (S/JSphGpuSingle.cpp:158-195): ids, positions, velocity+density, codes
     Check(dsph_particles_upload(Ctx,Np,Npb,Idp,Code,&AuxPos[0].x,&Velrhop[0].x),"dsph_particles_upload");
+    if(TBoundary==BC_MDBC){
+      // mDBC: the vectors particle -> ghost node that ConfigBoundNormals prepared and ParticlesDataUp left in BoundNormalg (S/JSphGpuSingle.cpp:169-195)
+      std::vector<float> nrm(size_t(Npb)*3);
+      if(Npb && cudaMemcpy(nrm.data(),BoundNormalg,sizeof(float)*3*Npb,cudaMemcpyDeviceToHost)!=cudaSuccess)Run_Exceptioon("libdsph_b200 binding: cannot read the boundary normals.");
+      Check(dsph_particles_set_boundnormals(Ctx,nrm.data(),Npb),"dsph_particles_set_boundnormals");
+      Check(dsph_set_mdbc_threshold(Ctx,MdbcThreshold),"dsph_set_mdbc_threshold");
+    }
     if(TStep==STEP_Symplectic && SymplecticDtPre)Check(dsph_set_symplectic_dtpre(Ctx,SymplecticDtPre),"dsph_set_symplectic_dtpre");
     Check(dsph_excluded_keep(Ctx,1),"dsph_excluded_keep");
     Log->Print("**libdsph_b200: the cell list, Interaction_Forces and ComputeStep run through the C ABI of dsph_b200.h");

@@ -107,3 +107,29 @@ def test_gpu_dropin_runs_a_moving_boundary_case_like_the_reference(gpu_lib, tmp_
         # the plate follows the same law at instants that differ like the variable dt of the two runs does (1e-6 relative)
         assert moved > 1e-4 and plate <= 1e-9 and dpos <= 1e-6 and dvel <= 1e-5, rep
     print("drop-in vs reference CPU solver, moving piston:", rep)
+
+
+@pytest.mark.gpu
+def test_gpu_dropin_runs_an_mdbc_case_like_the_reference(gpu_lib, tmp_path):
+    """mDBC through the drop-in: the reference's own LoadBoundNormals / ConfigBoundNormals prepare the vectors particle -> ghost node, the
+    binding hands them to dsph_particles_set_boundnormals, and the correction runs inside dsph_forces_run.  60 k particles, Boundary=2 with
+    DDT1 (the boundary rule of the density diffusion is on the path), against the reference CPU solver."""
+    if not (os.path.exists(DROPIN) and os.path.exists(STOCKCPU)):
+        pytest.skip("drop-in or reference CPU binary not built")
+    tmp = str(tmp_path)
+    subprocess.check_call([MKCASE, "dambreak", "60000", tmp, "Case", "boundary=2", "ddt=1"], stdout=subprocess.DEVNULL)
+    opts = ["-svres:1", "-tmax:0.01", "-tout:0.005"]
+    txt = _run(DROPIN, tmp, "out_dropin", ["-gpu"] + opts)
+    assert 'Boundary="mDBC"' in txt and "libdsph_b200" in txt
+    _run(STOCKCPU, tmp, "out_cpu", ["-cpu", "-ompthreads:%d" % min(os.cpu_count() or 1, 32)] + opts)
+    rep = {}
+    for part in (1, 2):
+        da = os.path.join(tmp, "out_dropin", "data"); db = os.path.join(tmp, "out_cpu", "data")
+        ia, pa, va, ta, sa = _state(da if os.path.isdir(da) else os.path.join(tmp, "out_dropin"), part)
+        ib, pb, vb, tb, sb = _state(db if os.path.isdir(db) else os.path.join(tmp, "out_cpu"), part)
+        assert np.array_equal(ia, ib) and sa == sb and abs(ta - tb) <= 1e-7 * max(tb, 1e-3), (part, sa, sb, ta, tb)
+        dpos = float(np.abs(pa - pb).max())
+        dvel = float(np.linalg.norm((va - vb).astype(np.float64)) / np.linalg.norm(vb.astype(np.float64)))
+        rep[part] = dict(step=sa, dpos=dpos, dvelrhop=dvel)
+        assert dpos <= 1e-6 and dvel <= 1e-5, rep
+    print("drop-in vs reference CPU solver, mDBC:", rep)
