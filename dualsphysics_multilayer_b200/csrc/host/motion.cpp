@@ -203,7 +203,7 @@ void MotionSet::LoadXml(const XmlNode *motion){
       const std::string &n=e->name;
       if(n.empty() || n[0]=='_')continue;
       if(n=="begin"){ MotionEvent ev; ev.movid=int(e->Int("mov")); ev.start=double(float(e->Dbl("start"))); ev.finish=double(float(e->Dbl("finish",true,-1)));   /* JXml::GetAttributeFloat: single precision */ o->events.push_back(ev); continue; }
-      MotionMov m; m.id=int(e->Int("id")); m.time=double(float(e->Dbl("duration")));   // read in single precision by the reference (S/JMotion.cpp:573) m.nextid=int(e->Int("next",true,0));
+      MotionMov m; m.id=int(e->Int("id")); m.time=double(float(e->Dbl("duration"))); m.nextid=int(e->Int("next",true,0));   // duration: read in single precision by the reference (S/JMotion.cpp:573)
       const std::string units=e->Str("anglesunits",true,"degrees");
       if(units!="degrees" && units!="radians")throw std::runtime_error("xml: anglesunits must be degrees or radians.");
       const bool deg=(units=="degrees");

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Motion-law fixtures: what the reference's JDsMotion / JMotion computed at EVERY step of a short run, for <motion> blocks that the
+physics goldens (mv_*) do not reach: accelerated rectilinear and rotational movements, chains, a delayed start, two concurrent
+movements of one object (translation composed with rotation), angles given in radians, an event with a finish time.
+
+mkcase writes the dam break with the moving plate, the <motion> block of Case.xml is replaced, oracle/_ref/ref_harness52 (the
+reference's JSphCpuSingle) runs NSTEPS steps and logs the StMotionData of every step (oracle/ref_harness.cpp: motionlog).
+Output: tests/golden/motionlog_<name>.npz {xml, t_dt, val, nobj, casenfixed, casenmoving}.  Needs /root/reference (harness build)."""
+import os, re, shutil, subprocess, sys, tempfile
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from make_golden import MKCASE, HARNESS, read_dump   # noqa: E402
+import dualsphysics_multilayer_b200 as dsph          # noqa: E402
+
+NSTEPS = 40
+AX = '<axisp1 x="0.44" y="0" z="0.04" /><axisp2 x="0.44" y="1" z="0.04" />'
+CASES = {
+    # delayed start, accelerated translation handing its velocity to nothing, then accelerated rotation, then constant rotation
+    "chain_rectace_rotace_rot": """<objreal ref="0"><begin mov="1" start="0.0012" />
+        <mvrectace id="1" duration="0.003" next="2"><ace x="0" y="0" z="30" /><velini x="0.2" y="0" z="0" /></mvrectace>
+        <mvrotace id="2" duration="0.004" next="3">%s<ace ang="4000" /><velini ang="50" /></mvrotace>
+        <mvrot id="3" duration="100">%s<vel ang="300" /></mvrot></objreal>""" % (AX, AX),
+    # two movements of the same object active at once: the second one starts later and ends by its event's finish time
+    "concurrent_rect_rot": """<objreal ref="0"><begin mov="1" start="0" /><begin mov="3" start="0.004" finish="0.011" />
+        <mvrect id="1" duration="100"><vel x="0.3" y="0" z="0.1" /></mvrect>
+        <mvrot id="3" duration="100">%s<vel ang="200" /></mvrot></objreal>""" % AX,
+    # sinusoidal rotation with the angles in radians, previous phase kept by the second link of the chain
+    "rotsinu_radians_chain": """<objreal ref="0"><begin mov="1" start="0" />
+        <mvrotsinu id="1" duration="0.006" next="2" anglesunits="radians">%s<freq v="20" /><ampl v="0.2" /><phase v="0.3" /></mvrotsinu>
+        <mvrotsinu id="2" duration="100" anglesunits="radians">%s<freq v="35" /><ampl v="0.1" /></mvrotsinu></objreal>""" % (AX, AX),
+    # wait in the middle of a chain, accelerated translation that keeps the velocity of the previous link
+    "rect_wait_rectace_prev": """<objreal ref="0"><begin mov="1" start="0" />
+        <mvrectace id="1" duration="0.003" next="2"><ace x="40" y="0" z="0" /><velini x="0" y="0" z="0" /></mvrectace>
+        <wait id="2" duration="0.002" next="3" />
+        <mvrectsinu id="3" duration="100"><freq x="30" y="0" z="12" /><ampl x="0.01" y="0" z="0.02" /><phase x="20" y="0" z="70" /></mvrectsinu></objreal>""",
+}
+
+
+def run(name, body, outdir):
+    tmp = tempfile.mkdtemp(prefix="motionlog_")
+    try:
+        subprocess.check_call([MKCASE, "movgate", "3000", tmp, "Case", "tstep=2", "tkernel=2", "tvisco=1", "visco=0.1", "ddt=2"], stdout=subprocess.DEVNULL)
+        xmlfile = os.path.join(tmp, "Case.xml")
+        xml = open(xmlfile).read()
+        xml, n = re.subn(r"<motion>.*</motion>", "<motion>\n" + body + "\n    </motion>", xml, flags=re.S)
+        assert n == 1
+        open(xmlfile, "w").write(xml)
+        cmd = [HARNESS, "Case", "out", "-cpu", "-ompthreads:1", "-sv:none", "-hdir:" + os.path.join(tmp, "dump"), "-hsteps:%d" % (NSTEPS + 5), "-hnsteps:%d" % NSTEPS]
+        r = subprocess.run(cmd, cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            print(r.stdout[-3000:]); raise RuntimeError("reference harness failed for " + name)
+        d = read_dump(os.path.join(tmp, "dump", "s%04d_motionlog.dmp" % NSTEPS))
+        cd = dsph.load_case(tmp, "Case")
+        out = os.path.join(outdir, "motionlog_" + name + ".npz")
+        np.savez_compressed(out, xml=np.frombuffer(xml.encode(), np.uint8), t_dt=d["t_dt"], val=d["val"], nobj=d["nobj"],
+                            casenfixed=np.uint32(cd.cfg.casenfixed), casenmoving=np.uint32(cd.cfg.casenmoving))
+        val = np.asarray(d["val"]).reshape(-1, 23)
+        print("%-28s %d steps, types %s, %.1f KB" % (name, val.shape[0], sorted(set(int(v) for v in val[:, 0])), os.path.getsize(out) / 1024))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    out = os.path.dirname(os.path.abspath(__file__))
+    for k, v in CASES.items():
+        if len(sys.argv) < 2 or k in sys.argv[1:]:
+            run(k, v, out)

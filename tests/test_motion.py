@@ -58,3 +58,39 @@ def test_motion_xml_refuses_unsupported():
         open(os.path.join(tmp, "Case.xml"), "w").write(xml)
         with pytest.raises(dsph.SphError):
             dsph.CaseMotion(tmp, "Case")
+
+
+MOTIONLOGS = ["chain_rectace_rotace_rot", "concurrent_rect_rot", "rotsinu_radians_chain", "rect_wait_rectace_prev"]
+
+
+@pytest.mark.parametrize("name", MOTIONLOGS)
+def test_motion_laws_other_movements_match_reference_log(name):
+    """Accelerated movements, chains (next), a delayed start, a wait inside a chain, two concurrent movements of one object (translation
+    composed with rotation), radians, an event with a finish time: tests/golden/motionlog_*.npz hold what JDsMotion computed at each of
+    40 steps of a reference run (generator: tests/golden/make_motionlogs.py)."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "motionlog_" + name + ".npz"))
+    tdt = np.asarray(z["t_dt"]).reshape(-1, 2)
+    nobj = int(z["nobj"])
+    val = np.asarray(z["val"]).reshape(tdt.shape[0], nobj, 23)
+    with tempfile.TemporaryDirectory() as tmp:
+        open(os.path.join(tmp, "Case.xml"), "wb").write(bytes(z["xml"]))
+        motion = dsph.CaseMotion(tmp, "Case")
+    assert motion.nobj == nobj == 1
+    types = set()
+    worst = 0.0
+    for s in range(tdt.shape[0]):
+        objs, active = motion.process(float(tdt[s, 0]), float(tdt[s, 1]))
+        d = objs[0]; ref = val[s, 0]
+        assert d.type == int(ref[0]), (name, s, d.type, ref[0], float(tdt[s, 0]))
+        types.add(d.type)
+        if d.type == 1:
+            got = np.array(list(d.linmov) + list(d.linvel)); want = ref[1:7]
+        elif d.type == 2:
+            got = np.array(list(d.matmov)); want = ref[7:23]
+        else:
+            continue
+        err = float(np.abs(got - want).max() / max(1e-300, np.abs(want).max()))
+        worst = max(worst, err)
+        assert err < 1e-11, (name, s, got, want)
+    print(name, "types seen:", sorted(types), "worst relative difference: %.2e" % worst)
+    motion.close()
