@@ -255,7 +255,7 @@ static RunSummary RunRank(const RunOptions &opt,CaseData &cd,int rank,SlabGroup 
   if(grp)grp->np0[rank]=np0;
   unsigned capacity=std::max(np0,slabs? 0u: c.casenp)+np0/20+1024;
   if(c.perix||c.periy||c.periz)capacity=unsigned(np0*1.7)+65536;
-  if(slabs)capacity=unsigned(np0*1.5)+200000;                                    // room for halo copies and for the re-balancing
+  if(slabs)capacity=unsigned(np0*((c.perix||c.periy||c.periz)? 2.0: 1.5))+200000;   // room for halo copies, periodic copies and for the re-balancing
   Engine eng(opt.device+rank,c,capacity);
   if(grp)grp->engines[rank]=&eng;
   if(opt.forcevariant)eng.forcevariant=opt.forcevariant;
@@ -443,7 +443,6 @@ RunSummary RunCase(const RunOptions &opt){
   }
   if(opt.mgpu<=1)return RunRank(opt,cd,0,nullptr,timestep,part,restartdtpre);
   // ---- slab run: cuts from the per-column histogram of the work (fluid 1, boundary weight), one thread per GPU
-  if(c.perix||c.periy||c.periz)throw std::runtime_error("Periodic boundaries cannot be combined with -mgpu yet.");
   SlabGroup grp(opt.mgpu);
   {
     SphConst k; DeriveConstants(c,k);

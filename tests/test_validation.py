@@ -279,3 +279,25 @@ def test_gpu_driver_slab_run_with_moving_piston_matches_single_gpu_run(gpu_lib, 
     assert np.array_equal(ia, ib)
     assert np.abs(pa - pb).max() < 1e-7
     assert np.linalg.norm((va - vb).astype(np.float64)) / np.linalg.norm(va.astype(np.float64)) < 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_driver_slab_run_of_the_periodic_box_matches_single_gpu_run(gpu_lib, tmp_path):
+    """bin/dsph_b200 -mgpu:2 on the fully periodic box: the two ranks form a ring through the periodic face along x and copy along y and z
+    themselves; against the single-GPU run of the same case."""
+    if dsph.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    cd = dsph.make_case("periodicbox", 200000)
+    dsph.save_case(cd, str(tmp_path), "Case")
+    one = tmp_path / "one"; two = tmp_path / "two"
+    dsph.run_case(str(tmp_path), "Case", str(one), nsteps=20, timeout=1e-3)
+    dsph.run_case(str(tmp_path), "Case", str(two), nsteps=20, timeout=1e-3, mgpu=2)
+    last = max(int(f[5:9]) for f in os.listdir(str(one)) if f.startswith("Part_0") and f.endswith(".bi4"))
+    a, ta, sa, npa = dsph.load_partset(str(one), last)
+    b, tb, sb, npb_ = dsph.load_partset(str(two), last)
+    assert last >= 1 and (npa, npb_) == (1, 2) and sa == sb and abs(ta - tb) <= 1e-9 * ta
+    ia, pa, va = _sorted_state(a); ib, pb, vb = _sorted_state(b)
+    assert np.array_equal(ia, ib)
+    d = np.abs(pa - pb); d = np.minimum(d, np.abs(d - 1.0))          # a particle may sit on either side of a periodic face (period 1)
+    assert d.max() < 1e-7
+    assert np.linalg.norm((va - vb).astype(np.float64)) / np.linalg.norm(va.astype(np.float64)) < 1e-5
