@@ -116,6 +116,7 @@ class Engine {
   unsigned *mgscratch[3]={}; unsigned mgcounts[8]={}; bool mgcounted=false;
   unsigned *mgown=nullptr; unsigned mgowncap=0; bool mgownok=false;   // owned fluid particles of the current divide (force kernel variant 10)
   void MgBuildOwnList();
+  void MgAllReduceFloats(float *dev,size_t n,bool max);
   // moving boundaries (motion.cuh, engine.cu)
   unsigned *ridpmove=nullptr;
   MotionSet *motionset=nullptr; std::vector<dsph_motiondata> motiondata;   // attached motion laws (dsph_motion_attach): evaluated inside Step / MgStep

@@ -26,7 +26,7 @@ void Engine::GaugesConfig(unsigned n,const dsph_gauge *g){
     if(q.type==DSPH_GAUGE_SWL && !(q.masslimit>0))q.masslimit=cfg.massfluid*(cfg.simulate2d? 0.4f: 0.5f);
     if(q.type==DSPH_GAUGE_MAXZ && !(q.distlimit>0))throw EngineError(DSPH_ERR_ARG,"The distlimit of a maxz gauge is invalid.");
   }
-  if(n && mgpu)throw EngineError(DSPH_ERR_STATE,"Gauges are not evaluated in x-slab runs (their sums span the cuts).");
+  if(n && mgpu && k.periactive)throw EngineError(DSPH_ERR_STATE,"Gauges are not evaluated in x-slab runs of periodic cases (the sums of a rank leave out the periodic copies it holds).");
 }
 
 // JGaugeSwl::SetPoints (S/JDsGaugeItem.cpp:447-465)
@@ -79,11 +79,17 @@ unsigned Engine::GaugesRun(double timestep,bool all,dsph_gaugeres *res){
   GaugeArgs ga; ga.pos=pos[cur]; for(int i=0;i<3;i++)ga.domposmax[i]=k.domposmax[i];
   const ForceParams t=MakeForceParams();
   if(!vel.empty()){ const unsigned n=unsigned(vel.size()); ker_gauge_points<0><<<(n*32+127)/128,128,0,stm>>>(n,(const double*)(gaugedev+o_pts),nullptr,0,dout+r_vel,ga,t,dc); launches++; }
+  if(mgpu && !vel.empty())MgAllReduceFloats(dout+r_vel,vel.size()*4,false);   // x-slab runs: partial sums over the owned particles of every rank
   if(!swl.empty()){
+    // (slab runs: the masses at the line points are partial sums over owned particles: reduced below, before the scan)
     ker_gauge_points<1><<<(nlinepts*32+127)/128,128,0,stm>>>(nlinepts,nullptr,(const GaugeLine*)(gaugedev+o_lines),unsigned(lines.size()),dout+r_mass,ga,t,dc); launches++;
+    if(mgpu)MgAllReduceFloats(dout+r_mass,nlinepts,false);
     ker_gauge_swl_scan<<<(unsigned(swl.size())+63)/64,64,0,stm>>>(unsigned(swl.size()),(const GaugeLine*)(gaugedev+o_lines),dout+r_mass,(const float*)(gaugedev+o_lim),dout+r_swl); launches++;
   }
-  if(!mxz.empty()){ const unsigned n=unsigned(mxz.size()); ker_gauge_maxz<<<(n*32+127)/128,128,0,stm>>>(n,(const GaugeMaxzDef*)(gaugedev+o_mz),dout+r_mz,ga,t,dc); launches++; }
+  if(!mxz.empty()){
+    const unsigned n=unsigned(mxz.size()); ker_gauge_maxz<<<(n*32+127)/128,128,0,stm>>>(n,(const GaugeMaxzDef*)(gaugedev+o_mz),dout+r_mz,ga,t,dc); launches++;
+    if(mgpu)MgAllReduceFloats(dout+r_mz,mxz.size(),true);          // the highest particle any rank found
+  }
   for(size_t kf=0;kf<frc.size();kf++){
     const dsph_gauge &q=gauges[frc[kf]];
     if(gaugepartacecap<q.count){ if(gaugepartace)cudaFree(gaugepartace); CUCHECKG(cudaMalloc((void**)&gaugepartace,size_t(q.count)*12+16)); gaugepartacecap=q.count; }
@@ -91,6 +97,7 @@ unsigned Engine::GaugesRun(double timestep,bool all,dsph_gaugeres *res){
     if(npbok){ ker_gauge_force<<<(npbok*32u+127u)/128u,128,0,stm>>>(npbok,q.code,q.idbegin,q.count,idp[cur],gaugepartace,ga,t,dc); launches++; }
     ker_gauge_force_sum<<<1,256,0,stm>>>(q.count,gaugepartace,cfg.massbound,dout+r_frc+3*kf); launches++;
   }
+  if(mgpu && !frc.empty())MgAllReduceFloats(dout+r_frc,frc.size()*3,false);   // every rank summed over the boundary particles it owns
   CUCHECKG(cudaMemcpyAsync(hb+o_out,dout,out_floats*4,cudaMemcpyDeviceToHost,stm));
   CUCHECKG(cudaStreamSynchronize(stm));
   CUCHECKG(cudaGetLastError());

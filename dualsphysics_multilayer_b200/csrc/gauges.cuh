@@ -94,7 +94,8 @@ template<int MODE> __global__ void __launch_bounds__(128) ker_gauge_points(unsig
     for(unsigned p2=pini+lane;p2<pfin;p2+=32){
       const float drx=float(px-g.pos[3*size_t(p2)]), dry=float(py-g.pos[3*size_t(p2)+1]), drz=float(pz-g.pos[3*size_t(p2)+2]);
       const float rr2=drx*drx+dry*dry+drz*drz;
-      if(rr2<=c.kernelsize2 && rr2>=1e-18f && GaugeIsFluid(t.code[p2])){
+      // x-slab runs: every rank sums over the particles it owns (halo copies are owned elsewhere), the partial sums are all-reduced
+      if(rr2<=c.kernelsize2 && rr2>=1e-18f && GaugeIsFluid(t.code[p2]) && (!t.skipghosts || (t.code[p2]&DSPH_CODE_MASKSPECIAL)==DSPH_CODE_NORMAL)){
         const float4 vr=t.velrhop[p2];
         float wab=GaugeWab(rr2,c);
         wab*=c.massfluid/vr.w;

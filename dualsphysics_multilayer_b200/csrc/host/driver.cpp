@@ -309,12 +309,12 @@ static RunSummary RunRank(const RunOptions &opt,CaseData &cd,int rank,SlabGroup 
   // ---- gauges: first evaluation on the initial state (RunGaugeSystem(TimeStep,true), S/JSphCpuSingle.cpp:1070)
   GaugeOutput gout;
   if(!cd.gauges.empty()){
-    if(slabs)log.Printf("*** WARNING: gauges are not evaluated in x-slab runs.");
+    if(slabs && (c.perix||c.periy||c.periz))log.Printf("*** WARNING: gauges are not evaluated in x-slab runs of periodic cases.");
     else{
       eng.GaugesConfig(unsigned(cd.gauges.size()),cd.gauges.data());
-      gout.Config(cd.gauges,opt.dirout);
+      if(!rank)gout.Config(cd.gauges,opt.dirout);                 // slab runs: every rank evaluates (collective), rank 0 writes the files
       eng.gaugetime=timestep;
-      eng.GaugesRun(timestep,false,nullptr); gout.Collect(eng.gaugeres);
+      eng.GaugesRun(timestep,false,nullptr); if(!rank)gout.Collect(eng.gaugeres);
       log.Printf("Gauges: %u (<special><gauges>) -> Gauges<Type>_<name>.csv",unsigned(cd.gauges.size()));
     }
   }

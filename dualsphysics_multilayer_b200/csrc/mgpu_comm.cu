@@ -365,6 +365,13 @@ void Engine::MgForces(int interstep,dsph_forceres *res){
   ForcesFinish(res);
 }
 
+// in-place all-reduce of a small float block on the stream (gauges of slab runs): sum, or max
+void Engine::MgAllReduceFloats(float *dev,size_t n,bool max){
+  if(!mgpu || !n)return;
+  if(!mgcomm)throw EngineError(DSPH_ERR_STATE,"Gauges of an x-slab run need dsph_mgpu_comm_init first (their evaluation is collective).");
+  NCCLCHECK(Nccl().AllReduce(dev,dev,n,ncclFloat,max? ncclMax: ncclSum,(ncclComm_t)mgcomm,stm));
+}
+
 void Engine::MgStep(double *stepdt,dsph_forceres *res){
   double dt;
   bool moving=false;
@@ -386,6 +393,7 @@ void Engine::MgStep(double *stepdt,dsph_forceres *res){
     if(motionset)moving=motionset->Process(gaugetime,dt,motiondata);
     StepVerlet(dt);
   }
+  if(!gauges.empty())GaugesRun(gaugetime+dt,false,nullptr);                // collective: partial sums of every rank, all-reduced
   if(moving)MotionRun(motiondata.data(),unsigned(motiondata.size()),dt);   // every rank moves the moving particles it owns
   gaugetime+=dt;
   MgCellDivide(nullptr); FlushStepTimer();

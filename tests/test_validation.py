@@ -301,3 +301,32 @@ def test_gpu_driver_slab_run_of_the_periodic_box_matches_single_gpu_run(gpu_lib,
     d = np.abs(pa - pb); d = np.minimum(d, np.abs(d - 1.0))          # a particle may sit on either side of a periodic face (period 1)
     assert d.max() < 1e-7
     assert np.linalg.norm((va - vb).astype(np.float64)) / np.linalg.norm(va.astype(np.float64)) < 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_driver_slab_run_writes_the_gauges_of_the_single_gpu_run(gpu_lib, tmp_path):
+    """In-solver gauges in an x-slab run: every rank sums over the particles it owns, the partial results are all-reduced (sum for velocity,
+    line masses and the force, max for maxz) and rank 0 writes the Gauges*.csv files.  -mgpu:2 against the single-GPU run of the same case:
+    the same rows at the same instants, values equal up to the order of the float sums."""
+    import subprocess, sys
+    if dsph.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    from make_golden import inject_gauges
+    mkcase = os.path.join(root, "dualsphysics_multilayer_b200", "bin", "mkcase")
+    subprocess.check_call([mkcase, "dambreak", "200000", str(tmp_path), "Case"], stdout=subprocess.DEVNULL)
+    inject_gauges(str(tmp_path / "Case.xml"))
+    one = tmp_path / "one"; two = tmp_path / "two"
+    dsph.run_case(str(tmp_path), "Case", str(one), nsteps=25, timeout=1e-3)
+    dsph.run_case(str(tmp_path), "Case", str(two), nsteps=25, timeout=1e-3, mgpu=2)
+    files = sorted(f for f in os.listdir(str(one)) if f.startswith("Gauges") and f.endswith(".csv"))
+    assert len(files) == 8, files
+    worst = {}
+    for f in files:
+        a = np.genfromtxt(str(one / f), delimiter=";", skip_header=1); b = np.genfromtxt(str(two / f), delimiter=";", skip_header=1)
+        assert a.shape == b.shape and a.shape[0] >= 20, (f, a.shape, b.shape)
+        scale = max(1e-3, float(np.abs(a[:, 1:]).max()))
+        worst[f] = float(np.abs(a - b).max() / scale)
+        assert worst[f] < 2e-5, (f, worst[f])
+    print("gauges of the slab run vs single GPU (max difference / largest value):", worst)
