@@ -393,10 +393,13 @@ void Engine::MgStep(double *stepdt,dsph_forceres *res){
     if(motionset)moving=motionset->Process(gaugetime,dt,motiondata);
     StepVerlet(dt);
   }
-  if(!gauges.empty())GaugesRun(gaugetime+dt,false,nullptr);                // collective: partial sums of every rank, all-reduced
   if(moving)MotionRun(motiondata.data(),unsigned(motiondata.size()),dt);   // every rank moves the moving particles it owns
   gaugetime+=dt;
   MgCellDivide(nullptr); FlushStepTimer();
+  // Gauges (collective: partial sums of every rank, all-reduced).  The single-GPU step evaluates them before the closing divide, like
+  // the reference (S/JSphCpuSingle.cpp:1095); here the halo copies still hold the state of the mid-step exchange at that point, so the
+  // evaluation waits for the exchange of the closing divide: same particles, same states, the neighbour list of the new divide.
+  if(!gauges.empty())GaugesRun(gaugetime,false,nullptr);
   if(stepdt)*stepdt=dt;
 }
 
