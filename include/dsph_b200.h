@@ -370,7 +370,9 @@ int dsph_excluded_take(dsph_ctx *ctx,uint32_t max,uint32_t *n,uint32_t *idp,dsph
  *      or from the caller.  Timing follows JGaugeItem (S/JDsGaugeItem.h:164-165, S/JDsGaugeItem.cpp:204-211): a gauge is computed at
  *      a step when timestep >= its next compute time inside [computestart, computeend].  dsph_step runs the configured gauges where
  *      the reference runs them: after the step update, BEFORE the closing divide (S/JSphCpuSingle.cpp:1094-1098), with
- *      timestep = (time set by dsph_gauges_set_time) + dt. ---------------------------------------------------------------------- */
+ *      timestep = (time set by dsph_gauges_set_time) + dt. ----------------------------------------------------------------------  *      In x-slab runs dsph_gauges_run is COLLECTIVE (every rank calls it at the same instants): each rank sums over the particles it owns
+ *      and the partial results are all-reduced over the communicator of the context; dsph_mgpu_step evaluates the gauges after the exchange
+ *      of its closing divide (fresh halo copies).  Not available for periodic cases in slab runs. */
 enum { DSPH_GAUGE_VEL=1, DSPH_GAUGE_SWL=2, DSPH_GAUGE_MAXZ=3, DSPH_GAUGE_FORCE=4 };
 typedef struct dsph_gauge {
   int32_t type; int32_t output;                 /* output: results go to Gauges<Type>_<name>.csv (driver) */
