@@ -201,7 +201,7 @@ void LoadCaseMotion(MotionSet &ms,const std::string &dir,const std::string &case
     MotionObj o; o.ref=int(e->Int("refmotion",true,nmov)); o.mkbound=unsigned(e->Int("mkbound")); o.idbegin=unsigned(e->Int("begin")); o.count=unsigned(e->Int("count"));
     ms.objs.push_back(o); nmov++;
   }
-  if(nmov)ms.LoadXml(ex->Child("motion"));
+  if(nmov)ms.LoadXml(ex->Child("motion"),dir+"/");
 }
 
 void LoadCase(CaseData &cd,const std::string &dir,const std::string &casename){
@@ -298,7 +298,7 @@ void LoadCase(CaseData &cd,const std::string &dir,const std::string &casename){
       MotionObj o; o.ref=int(b.refmotion); o.mkbound=b.mktype; o.idbegin=b.begin; o.count=b.count;
       cd.motion.objs.push_back(o); nmov++;
     }
-    if(nmov)cd.motion.LoadXml(ex->Child("motion"));
+    if(nmov)cd.motion.LoadXml(ex->Child("motion"),dir+"/");
   }
   c.casenp=total; c.casenfixed=cnt[0]; c.casenmoving=cnt[1]; c.casenfloat=cnt[2]; c.casenfluid=cnt[3];
   if(c.nn_on){

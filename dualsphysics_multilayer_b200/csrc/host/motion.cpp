@@ -64,8 +64,61 @@ void ConfigActive(MotionActive &a){
     case MotionMov::Rot: case MotionMov::RotAce: a.velang=m.velang; break;
     case MotionMov::RectSinu: for(int i=0;i<3;i++)a.phase[i]=m.phase[i]; break;
     case MotionMov::RotSinu: a.phaseuni=m.phase[0]; break;
+    case MotionMov::Cir: case MotionMov::CirAce: a.velang=m.velang; for(int i=0;i<3;i++)a.refp[i]=m.ref[i]; break;
+    case MotionMov::CirSinu: a.phaseuni=m.phase[0]; for(int i=0;i<3;i++)a.refp[i]=m.ref[i]; break;
+    case MotionMov::RectFile: a.dfindex=0; for(int i=0;i<3;i++)a.dflastpos[i]=m.fvals[i]; break;       // JMotionMovActive::DfConfig S/JMotionObj.cpp:96-116
+    case MotionMov::RotFile: a.dfindex=0; a.dflastang=m.fvals[0]; break;
     default: break;
   }
+}
+// position in times[] of the closest value below t, as the reference finds it (JMotionMovActive::BinarySearch S/JMotionObj.cpp:122-145)
+unsigned DfBinarySearch(const std::vector<double> &times,double t){
+  const unsigned size=unsigned(times.size());
+  unsigned ret=0;
+  if(size>1){
+    int ccen=0,cmin=0,cmax=int(size)-1;
+    while(cmin<=cmax){
+      ccen=((cmax-cmin)/2)+cmin;
+      if(times[ccen]==t)cmin=cmax+1;
+      else if(t<times[ccen])cmax=ccen-1;
+      else cmin=ccen+1;
+    }
+    if(ccen && ccen<int(size) && t<times[ccen])ccen--;
+    ret=unsigned(ccen);
+    while(ret && t==times[ret-1])ret--;
+  }
+  return ret;
+}
+// linear interpolation of the data file at t; the interval index only moves forward (DfGetNewPos / DfGetNewAng S/JMotionObj.cpp:150-183)
+void DfQuery(const MotionMov &m,MotionActive &a,double t,int ncomp,double *out){
+  const unsigned count=unsigned(m.ftimes.size());
+  if(a.dfindex==0)a.dfindex=DfBinarySearch(m.ftimes,t);
+  while(a.dfindex<count && t>m.ftimes[a.dfindex])a.dfindex++;
+  if(a.dfindex>=count){ for(int c=0;c<ncomp;c++)out[c]=m.fvals[size_t(count-1)*ncomp+c]; return; }
+  const unsigned i1=a.dfindex, i0=(i1? i1-1: 0);
+  const double tfactor=(i1? (t-m.ftimes[i0])/(m.ftimes[i1]-m.ftimes[i0]): 0.0);
+  for(int c=0;c<ncomp;c++){ const double v0=m.fvals[size_t(i0)*ncomp+c], v1=m.fvals[size_t(i1)*ncomp+c]; out[c]=v0+tfactor*(v1-v0); }
+}
+// rows of a text data file: lines starting with # are remarks, values separated by blanks, tabs, ; or , (JReadDatafile)
+std::vector<std::vector<double>> ReadDataFile(const std::string &file){
+  FILE *f=fopen(file.c_str(),"r");
+  if(!f)throw std::runtime_error("motion: cannot open the data file "+file);
+  std::vector<std::vector<double>> rows; char line[4096];
+  while(fgets(line,sizeof(line),f)){
+    char *p=line; while(*p==' '||*p=='\t')p++;
+    if(*p=='#'||*p=='\n'||*p=='\r'||*p==0)continue;
+    std::vector<double> v;
+    while(*p){
+      while(*p==' '||*p=='\t'||*p==';'||*p==','||*p=='\n'||*p=='\r')p++;
+      if(!*p)break;
+      char *e=nullptr; const double x=strtod(p,&e);
+      if(e==p)break;
+      v.push_back(x); p=e;
+    }
+    if(!v.empty())rows.push_back(v);
+  }
+  fclose(f);
+  return rows;
 }
 const MotionMov* FindMov(const MotionObj &o,int id){ for(auto &m:o.movs)if(m.id==id)return &m; return nullptr; }
 
@@ -81,9 +134,9 @@ void NextMov(const MotionObj &o,MotionActive &a){
   ConfigActive(a);
   switch(nx->type){
     case MotionMov::RectAce:  if(nx->velprev)for(int i=0;i<3;i++)a.vel[i]=velp[i]; break;
-    case MotionMov::RotAce:   if(nx->velprev)a.velang=velangp; break;
+    case MotionMov::RotAce: case MotionMov::CirAce: if(nx->velprev)a.velang=velangp; break;
     case MotionMov::RectSinu: if(nx->phaseprev)for(int i=0;i<3;i++)a.phase[i]=php[i]; break;
-    case MotionMov::RotSinu:  if(nx->phaseprev)a.phaseuni=phunip; break;
+    case MotionMov::RotSinu: case MotionMov::CirSinu: if(nx->phaseprev)a.phaseuni=phunip; break;
     default: break;
   }
 }
@@ -149,6 +202,34 @@ bool MotionSet::Process(double timestep,double dt,std::vector<dsph_motiondata> &
               ang=mv.ampl[0]*std::sin(ph)-ang;
               mp.Rotate(ang,mv.axisp1,mv.axisp2); am.phaseuni=ph; modif=true;
             }break;
+            // circular: the reference point travels round the axis and the object is translated with it (no rotation of the object)
+            case MotionMov::Cir: case MotionMov::CirAce: case MotionMov::CirSinu:{
+              double ang;
+              if(mv.type==MotionMov::Cir)ang=mv.velang*t;
+              else if(mv.type==MotionMov::CirAce){ const double at=mv.aceang*t; ang=am.velang*t+0.5f*at*t; am.velang+=at; }
+              else{ double ph=am.phaseuni; const double a0=mv.ampl[0]*std::sin(ph); ph+=double(mv.freq[0]*(kPi+kPi)*t); ang=mv.ampl[0]*std::sin(ph)-a0; am.phaseuni=ph; }
+              const Mat4 m=Mat4::Rot(ang,mv.axisp1,mv.axisp2);
+              const double *p1=am.refp; double p2[3];
+              for(int i=0;i<3;i++)p2[i]=m(i,0)*p1[0]+m(i,1)*p1[1]+m(i,2)*p1[2]+m(i,3);
+              const double m3[3]={p2[0]-p1[0],p2[1]-p1[1],p2[2]-p1[2]};
+              mp.Move(m3); for(int i=0;i<3;i++)am.refp[i]=p2[i]; modif=true;
+            }break;
+            // file-driven: the time of the data is the time since the start of the movement measured from the START of the step
+            // (S/JMotionObj.cpp:524-545 uses timestep, not the split time), plus the first time of the file, plus the part of dt that is used
+            case MotionMov::RectFile:{
+              double tq=timestep-am.start; if(tq<0)tq=0;
+              tq+=mv.ftimes[0]; tq+=t;
+              double np3[3]; DfQuery(mv,am,tq,3,np3);
+              if(mv.fieldx<0)np3[0]=0; if(mv.fieldy<0)np3[1]=0; if(mv.fieldz<0)np3[2]=0;
+              const double m3[3]={np3[0]-am.dflastpos[0],np3[1]-am.dflastpos[1],np3[2]-am.dflastpos[2]};
+              mp.Move(m3); for(int i=0;i<3;i++)am.dflastpos[i]=np3[i]; modif=true;
+            }break;
+            case MotionMov::RotFile:{
+              double tq=timestep-am.start; if(tq<0)tq=0;
+              tq+=mv.ftimes[0]; tq+=t;
+              double na; DfQuery(mv,am,tq,1,&na);
+              mp.Rotate(na-am.dflastang,mv.axisp1,mv.axisp2); am.dflastang=na; modif=true;
+            }break;
             default: break;
           }
         }
@@ -186,7 +267,7 @@ static double Read1(const XmlNode *e,const char *name,const char *att){
   return q->Dbl(att);
 }
 
-void MotionSet::LoadXml(const XmlNode *motion){
+void MotionSet::LoadXml(const XmlNode *motion,const std::string &dirdata){
   // objs[] already holds one entry per moving block (ref, mkbound, idbegin, count); this adds movements and events
   for(auto &o:objs){ o.movs.clear(); o.events.clear(); o.active.clear(); }
   if(!motion)return;
@@ -226,7 +307,41 @@ void MotionSet::LoadXml(const XmlNode *motion){
         if(!deg)m.ampl[0]*=kToDeg;
         if(deg)m.phase[0]*=kToRad;
       }
-      else throw std::runtime_error("motion: <"+n+"> is not supported by the stand-alone driver (wait, mvrect, mvrectace, mvrot, mvrotace, mvrectsinu, mvrotsinu are).");
+      else if(n=="mvcir"){ m.type=MotionMov::Cir; Read3(e,"axisp1",m.axisp1); Read3(e,"axisp2",m.axisp2); Read3(e,"ref",m.ref); m.velang=Read1(e,"vel","ang"); if(!deg)m.velang*=kToDeg; }
+      else if(n=="mvcirace"){
+        m.type=MotionMov::CirAce; Read3(e,"axisp1",m.axisp1); Read3(e,"axisp2",m.axisp2); Read3(e,"ref",m.ref); m.aceang=Read1(e,"ace","ang");
+        m.velprev=e->Child("velini")==nullptr; if(!m.velprev)m.velang=Read1(e,"velini","ang");
+        if(!deg){ m.aceang*=kToDeg; m.velang*=kToDeg; }
+      }
+      else if(n=="mvcirsinu"){
+        m.type=MotionMov::CirSinu; Read3(e,"axisp1",m.axisp1); Read3(e,"axisp2",m.axisp2); Read3(e,"ref",m.ref); m.freq[0]=Read1(e,"freq","v"); m.ampl[0]=Read1(e,"ampl","v");
+        m.phaseprev=e->Child("phase")==nullptr; if(!m.phaseprev)m.phase[0]=Read1(e,"phase","v");
+        if(!deg)m.ampl[0]*=kToDeg;
+        if(deg)m.phase[0]*=kToRad;
+      }
+      else if(n=="mvrectfile" || n=="mvfile" || n=="mvpredef" || n=="mvrotfile"){
+        const XmlNode *ef=e->Child("file");
+        if(!ef)throw std::runtime_error("xml: <"+n+"><file> is missing");
+        std::string file=ef->Str("name");
+        if(file.find('/')==std::string::npos && file.find('\\')==std::string::npos)file=dirdata+file;       // only a name: next to the case (S/JMotionMov.cpp:290)
+        const std::vector<std::vector<double>> rows=ReadDataFile(file);
+        if(rows.size()<2)throw std::runtime_error("motion: the data file "+file+" cannot have less than two rows.");
+        if(n=="mvrotfile"){
+          m.type=MotionMov::RotFile; Read3(e,"axisp1",m.axisp1); Read3(e,"axisp2",m.axisp2);
+          for(auto &r:rows){ if(r.size()<2)throw std::runtime_error("motion: a row of "+file+" has less than two values."); m.ftimes.push_back(r[0]); m.fvals.push_back(deg? r[1]: r[1]*kToDeg); }
+        }
+        else{
+          m.type=MotionMov::RectFile;
+          const int fields=int(ef->Int("fields")), ft=int(ef->Int("fieldtime"));
+          m.fieldx=int(ef->Int("fieldx",true,-1)); m.fieldy=int(ef->Int("fieldy",true,-1)); m.fieldz=int(ef->Int("fieldz",true,-1));
+          for(auto &r:rows){
+            if(int(r.size())<fields || ft<0 || ft>=fields)throw std::runtime_error("motion: a row of "+file+" has less values than fields.");
+            m.ftimes.push_back(r[ft]);
+            m.fvals.push_back(m.fieldx>=0 && m.fieldx<fields? r[m.fieldx]: 0.0); m.fvals.push_back(m.fieldy>=0 && m.fieldy<fields? r[m.fieldy]: 0.0); m.fvals.push_back(m.fieldz>=0 && m.fieldz<fields? r[m.fieldz]: 0.0);
+          }
+        }
+      }
+      else throw std::runtime_error("motion: <"+n+"> is not supported by the stand-alone driver (wait, mvrect, mvrectace, mvrot, mvrotace, mvcir, mvcirace, mvrectsinu, mvrotsinu, mvcirsinu, mvrectfile, mvrotfile are).");
       o->movs.push_back(m);
     }
   }
@@ -245,6 +360,7 @@ void MotionSet::SaveXml(FILE *f,const char *ind)const{
     }
     for(auto &m:o.movs){
       static const char *tn[]={"wait","mvrect","mvrectace","mvrot","mvrotace","mvrectsinu","mvrotsinu"};
+      if(m.type>MotionMov::RotSinu)throw std::runtime_error("motion: circular and file-driven movements are read, not written, by this library.");
       std::string head=std::string(ind)+"    <"+tn[m.type]+" id=\""+std::to_string(m.id)+"\" duration=\""+D(m.time)+"\"";
       if(m.nextid)head+=" next=\""+std::to_string(m.nextid)+"\"";
       if(m.type>=MotionMov::Rot)head+=" anglesunits=\"radians\"";

@@ -35,6 +35,20 @@ CASES = {
         <mvrectace id="1" duration="0.003" next="2"><ace x="40" y="0" z="0" /><velini x="0" y="0" z="0" /></mvrectace>
         <wait id="2" duration="0.002" next="3" />
         <mvrectsinu id="3" duration="100"><freq x="30" y="0" z="12" /><ampl x="0.01" y="0" z="0.02" /><phase x="20" y="0" z="70" /></mvrectsinu></objreal>""",
+    # circular movements: the object is translated along a circle (no rotation), constant / accelerated / sinusoidal angle
+    "chain_cir_cirace_cirsinu": """<objreal ref="0"><begin mov="1" start="0.0005" />
+        <mvcir id="1" duration="0.004" next="2">%s<ref x="0.44" y="0.3" z="0.2" /><vel ang="400" /></mvcir>
+        <mvcirace id="2" duration="0.004" next="3">%s<ref x="0.44" y="0.3" z="0.2" /><ace ang="9000" /></mvcirace>
+        <mvcirsinu id="3" duration="100">%s<ref x="0.44" y="0.3" z="0.2" /><freq v="40" /><ampl v="8" /><phase v="30" /></mvcirsinu></objreal>""" % (AX, AX, AX),
+    # file-driven movements (wave-maker style): positions from a 4-column file with remarks and mixed separators, angles in radians
+    "rectfile_then_rotfile": """<objreal ref="0"><begin mov="1" start="0.001" />
+        <mvrectfile id="1" duration="0.006" next="2"><file name="piston.dat" fields="4" fieldtime="0" fieldx="1" fieldz="3" /></mvrectfile>
+        <mvrotfile id="2" duration="100" anglesunits="radians"><file name="flap.dat" />%s</mvrotfile></objreal>""" % AX,
+}
+
+DATAFILES = {
+    "piston.dat": "# time; x; unused; z\n" + "".join("%.6f;%.8f;7;%.8f\n" % (0.002 + 0.0007 * i, 0.004 * (i ** 1.3) * 0.1, 0.002 * i * (1 if i % 2 else -0.5)) for i in range(14)),
+    "flap.dat": "# time angle[rad]\n" + "".join("%.6f\t%.8f\n" % (0.0009 * i, 0.05 * ((i * 0.37) % 1.0 - 0.3)) for i in range(30)),
 }
 
 
@@ -47,6 +61,10 @@ def run(name, body, outdir):
         xml, n = re.subn(r"<motion>.*</motion>", "<motion>\n" + body + "\n    </motion>", xml, flags=re.S)
         assert n == 1
         open(xmlfile, "w").write(xml)
+        used = {}
+        for fn, text in DATAFILES.items():
+            if fn in body:
+                open(os.path.join(tmp, fn), "w").write(text); used[fn] = text
         cmd = [HARNESS, "Case", "out", "-cpu", "-ompthreads:1", "-sv:none", "-hdir:" + os.path.join(tmp, "dump"), "-hsteps:%d" % (NSTEPS + 5), "-hnsteps:%d" % NSTEPS]
         r = subprocess.run(cmd, cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
@@ -55,7 +73,8 @@ def run(name, body, outdir):
         cd = dsph.load_case(tmp, "Case")
         out = os.path.join(outdir, "motionlog_" + name + ".npz")
         np.savez_compressed(out, xml=np.frombuffer(xml.encode(), np.uint8), t_dt=d["t_dt"], val=d["val"], nobj=d["nobj"],
-                            casenfixed=np.uint32(cd.cfg.casenfixed), casenmoving=np.uint32(cd.cfg.casenmoving))
+                            casenfixed=np.uint32(cd.cfg.casenfixed), casenmoving=np.uint32(cd.cfg.casenmoving),
+                            **{"file_" + fn: np.frombuffer(text.encode(), np.uint8) for fn, text in used.items()})
         val = np.asarray(d["val"]).reshape(-1, 23)
         print("%-28s %d steps, types %s, %.1f KB" % (name, val.shape[0], sorted(set(int(v) for v in val[:, 0])), os.path.getsize(out) / 1024))
     finally:

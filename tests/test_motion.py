@@ -52,7 +52,7 @@ def test_motion_xml_refuses_unsupported():
     xml = """<case><execution><particles np="4" nb="2" nbf="1" mkboundfirst="11" mkfluidfirst="1">
       <fixed mkbound="0" mk="11" begin="0" count="1" /><moving mkbound="1" mk="12" begin="1" count="1" refmotion="0" />
       <fluid mkfluid="0" mk="1" begin="2" count="2" /></particles>
-      <motion><objreal ref="0"><begin mov="1" start="0" /><mvcir id="1" duration="1"><vel ang="3" /></mvcir></objreal></motion>
+      <motion><obj><objreal ref="0"><begin mov="1" start="0" /><mvrect id="1" duration="1"><vel x="1" y="0" z="0" /></mvrect></objreal></obj></motion>
       </execution></case>"""
     with tempfile.TemporaryDirectory() as tmp:
         open(os.path.join(tmp, "Case.xml"), "w").write(xml)
@@ -60,13 +60,15 @@ def test_motion_xml_refuses_unsupported():
             dsph.CaseMotion(tmp, "Case")
 
 
-MOTIONLOGS = ["chain_rectace_rotace_rot", "concurrent_rect_rot", "rotsinu_radians_chain", "rect_wait_rectace_prev"]
+MOTIONLOGS = ["chain_rectace_rotace_rot", "concurrent_rect_rot", "rotsinu_radians_chain", "rect_wait_rectace_prev",
+              "chain_cir_cirace_cirsinu", "rectfile_then_rotfile"]
 
 
 @pytest.mark.parametrize("name", MOTIONLOGS)
 def test_motion_laws_other_movements_match_reference_log(name):
     """Accelerated movements, chains (next), a delayed start, a wait inside a chain, two concurrent movements of one object (translation
-    composed with rotation), radians, an event with a finish time: tests/golden/motionlog_*.npz hold what JDsMotion computed at each of
+    composed with rotation), radians, an event with a finish time, circular movements, file-driven movements (positions / angles
+    interpolated from data files): tests/golden/motionlog_*.npz hold what JDsMotion computed at each of
     40 steps of a reference run (generator: tests/golden/make_motionlogs.py)."""
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "motionlog_" + name + ".npz"))
     tdt = np.asarray(z["t_dt"]).reshape(-1, 2)
@@ -74,6 +76,9 @@ def test_motion_laws_other_movements_match_reference_log(name):
     val = np.asarray(z["val"]).reshape(tdt.shape[0], nobj, 23)
     with tempfile.TemporaryDirectory() as tmp:
         open(os.path.join(tmp, "Case.xml"), "wb").write(bytes(z["xml"]))
+        for k in z.files:
+            if k.startswith("file_"):                      # data files of the file-driven movements, next to the case
+                open(os.path.join(tmp, k[5:]), "wb").write(bytes(z[k]))
         motion = dsph.CaseMotion(tmp, "Case")
     assert motion.nobj == nobj == 1
     types = set()
