@@ -539,6 +539,7 @@ static void MakeDamBreak(CaseData &cd,unsigned long long nptarget,int nlayers,bo
     else{
       m.type=MotionMov::RectSinu; m.time=100; m.freq[0]=2; m.ampl[0]=0.25*a; m.phase[0]=0; o.movs.push_back(m);
     }
+    for(auto &q:o.movs)for(int i=0;i<3;i++){ q.iaxisp1[i]=q.axisp1[i]; q.iaxisp2[i]=q.axisp2[i]; q.iref[i]=q.ref[i]; }
     cd.motion.objs.push_back(o);
   }
   cd.blocks.push_back({3,0,cd.mkfluidfirst+0,nb,nf0});

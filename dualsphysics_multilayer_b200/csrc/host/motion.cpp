@@ -54,6 +54,15 @@ struct ModPos {
   bool simple=true; double s[3]={0,0,0}; Mat4 m;
   void Move(const double d[3]){ if(simple){ s[0]+=d[0]; s[1]+=d[1]; s[2]+=d[2]; } else m.MulRight(Mat4::Move(d)); }
   void Rotate(double ang,const double p1[3],const double p2[3]){ if(simple){ m=Mat4::Move(s); simple=false; } m.MulRight(Mat4::Rot(ang,p1,p2)); }
+  // JMotionPos::MoveMix / PointMove (S/JMotionPos.cpp:82-107): the motion of a parent object applied to a child, to a point
+  void MoveMix(const ModPos &o){ if(simple && !o.simple){ m=Mat4::Move(s); simple=false; } if(o.simple)Move(o.s); else m.MulRight(o.m); }
+  void PointMove(double p[3])const{
+    if(simple){ p[0]+=s[0]; p[1]+=s[1]; p[2]+=s[2]; return; }
+    const double x=p[0],y=p[1],z=p[2];
+    for(int i=0;i<3;i++)p[i]=m(i,0)*x+m(i,1)*y+m(i,2)*z+m(i,3);
+  }
+  void Store(MotionObj &o)const{ o.mpsimple=simple; for(int i=0;i<3;i++)o.mps[i]=s[i]; memcpy(o.mpm,m.a,sizeof(o.mpm)); }
+  static ModPos Of(const MotionObj &o){ ModPos r; r.simple=o.mpsimple; for(int i=0;i<3;i++)r.s[i]=o.mps[i]; memcpy(r.m.a,o.mpm,sizeof(o.mpm)); return r; }
 };
 
 void ConfigActive(MotionActive &a){
@@ -64,8 +73,8 @@ void ConfigActive(MotionActive &a){
     case MotionMov::Rot: case MotionMov::RotAce: a.velang=m.velang; break;
     case MotionMov::RectSinu: for(int i=0;i<3;i++)a.phase[i]=m.phase[i]; break;
     case MotionMov::RotSinu: a.phaseuni=m.phase[0]; break;
-    case MotionMov::Cir: case MotionMov::CirAce: a.velang=m.velang; for(int i=0;i<3;i++)a.refp[i]=m.ref[i]; break;
-    case MotionMov::CirSinu: a.phaseuni=m.phase[0]; for(int i=0;i<3;i++)a.refp[i]=m.ref[i]; break;
+    case MotionMov::Cir: case MotionMov::CirAce: a.velang=m.velang; break;      // (the travelling point keeps its state in the movement, like the
+    case MotionMov::CirSinu: a.phaseuni=m.phase[0]; break;                      //  reference's JMotionAxis: it is not reset by an activation)
     case MotionMov::RectFile: a.dfindex=0; for(int i=0;i<3;i++)a.dflastpos[i]=m.fvals[i]; break;       // JMotionMovActive::DfConfig S/JMotionObj.cpp:96-116
     case MotionMov::RotFile: a.dfindex=0; a.dflastang=m.fvals[0]; break;
     default: break;
@@ -144,19 +153,35 @@ void NextMov(const MotionObj &o,MotionActive &a){
 
 void MotionSet::Reset(){
   lasttime=0;
-  for(auto &o:objs){ o.active.clear(); for(auto &e:o.events)e.done=false; }
+  for(auto *list:{&objs,&groups})for(auto &o:*list){
+    o.active.clear(); o.moving=false;
+    for(auto &e:o.events)e.done=false;
+    for(auto &m:o.movs)for(int i=0;i<3;i++){ m.axisp1[i]=m.iaxisp1[i]; m.axisp2[i]=m.iaxisp2[i]; m.ref[i]=m.iref[i]; }     // JMotionAxis::ResetTime
+  }
 }
 
 bool MotionSet::Process(double timestep,double dt,std::vector<dsph_motiondata> &out){
   if(lasttime>timestep)throw std::runtime_error("The previous timestep+dt is higher than the requested timestep. It is invalid for simple mode.");
   out.assign(objs.size(),dsph_motiondata());
+  for(size_t io=0;io<objs.size();io++){ dsph_motiondata &d=out[io]; memset(&d,0,sizeof(d)); d.idbegin=objs[io].idbegin; d.count=objs[io].count; d.type=DSPH_MOTION_NONE; }
   bool anymove=false;
+  if(roots.empty())for(size_t io=0;io<objs.size();io++)roots.push_back({0,int(io)});   // a set filled in memory (mkcase): every object is a first-level one
+  for(auto &r:roots)ProcessNode(r.first,r.second,timestep,dt,out,anymove);
+  lasttime=timestep+dt;
+  return anymove;
+}
+
+// JMotionObj::ProcesTime (S/JMotionObj.cpp:368-575) of one object, then of its children
+void MotionSet::ProcessNode(int kind,int idx,double timestep,double dt,std::vector<dsph_motiondata> &out,bool &anymove){
+  MotionObj &o=(kind==0? objs[idx]: groups[idx]);
   const double tstepfin=timestep+dt;
-  for(size_t io=0;io<objs.size();io++){
-    MotionObj &o=objs[io];
-    dsph_motiondata &d=out[io];
-    memset(&d,0,sizeof(d));
-    d.idbegin=o.idbegin; d.count=o.count; d.type=DSPH_MOTION_NONE;
+  const MotionObj *parent=(o.pkind<0? nullptr: (o.pkind==0? &objs[o.pidx]: &groups[o.pidx]));
+  {
+    // the motion of the parent in this step carries the axes (and the travelling points of circular movements) of this object along
+    if(parent && parent->moving){
+      const ModPos pm=ModPos::Of(*parent);
+      for(auto &m:o.movs){ pm.PointMove(m.axisp1); pm.PointMove(m.axisp2); if(m.type>=MotionMov::Cir && m.type<=MotionMov::CirSinu)pm.PointMove(m.ref); }
+    }
     // events that start before the end of this step
     for(auto &e:o.events)if(!e.done && e.start<tstepfin){
       e.done=true;
@@ -209,10 +234,10 @@ bool MotionSet::Process(double timestep,double dt,std::vector<dsph_motiondata> &
               else if(mv.type==MotionMov::CirAce){ const double at=mv.aceang*t; ang=am.velang*t+0.5f*at*t; am.velang+=at; }
               else{ double ph=am.phaseuni; const double a0=mv.ampl[0]*std::sin(ph); ph+=double(mv.freq[0]*(kPi+kPi)*t); ang=mv.ampl[0]*std::sin(ph)-a0; am.phaseuni=ph; }
               const Mat4 m=Mat4::Rot(ang,mv.axisp1,mv.axisp2);
-              const double *p1=am.refp; double p2[3];
+              double *p1=const_cast<MotionMov&>(mv).ref; double p2[3];
               for(int i=0;i<3;i++)p2[i]=m(i,0)*p1[0]+m(i,1)*p1[1]+m(i,2)*p1[2]+m(i,3);
               const double m3[3]={p2[0]-p1[0],p2[1]-p1[1],p2[2]-p1[2]};
-              mp.Move(m3); for(int i=0;i<3;i++)am.refp[i]=p2[i]; modif=true;
+              mp.Move(m3); for(int i=0;i<3;i++)p1[i]=p2[i]; modif=true;
             }break;
             // file-driven: the time of the data is the time since the start of the movement measured from the START of the step
             // (S/JMotionObj.cpp:524-545 uses timestep, not the split time), plus the first time of the file, plus the part of dt that is used
@@ -241,8 +266,15 @@ bool MotionSet::Process(double timestep,double dt,std::vector<dsph_motiondata> &
       }while(rep);
       if(tstepfin>am.finish)am.del=true;
     }
-    if(modif){
+    if(parent && parent->moving){                                    // S/JMotionObj.cpp:562-565
+      const ModPos pm=ModPos::Of(*parent);
+      if(modif)mp.MoveMix(pm); else mp=pm;
+      modif=true;
+    }
+    o.moving=modif; mp.Store(o);
+    if(modif && kind==0){
       anymove=true;
+      dsph_motiondata &d=out[idx];
       if(mp.simple){
         d.type=DSPH_MOTION_LINEAR;
         for(int i=0;i<3;i++){ d.linmov[i]=mp.s[i]; d.linvel[i]=mp.s[i]/dt; }
@@ -251,8 +283,7 @@ bool MotionSet::Process(double timestep,double dt,std::vector<dsph_motiondata> &
       else{ d.type=DSPH_MOTION_MATRIX; memcpy(d.matmov,mp.m.a,sizeof(d.matmov)); }
     }
   }
-  lasttime=tstepfin;
-  return anymove;
+  for(auto &c:o.children)ProcessNode(c.first,c.second,timestep,dt,out,anymove);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -268,21 +299,41 @@ static double Read1(const XmlNode *e,const char *name,const char *att){
 }
 
 void MotionSet::LoadXml(const XmlNode *motion,const std::string &dirdata){
-  // objs[] already holds one entry per moving block (ref, mkbound, idbegin, count); this adds movements and events
-  for(auto &o:objs){ o.movs.clear(); o.events.clear(); o.active.clear(); }
-  if(!motion)return;
-  for(auto &ep:motion->children){
+  // objs[] already holds one entry per moving block (ref, mkbound, idbegin, count); this adds the object tree, movements and events
+  for(auto &o:objs){ o.movs.clear(); o.events.clear(); o.active.clear(); o.children.clear(); o.pkind=o.pidx=-1; }
+  groups.clear(); roots.clear();
+  if(motion)for(auto &ep:motion->children){
     const XmlNode *ob=ep.get();
     if(ob->name.empty() || ob->name[0]=='_')continue;
-    if(ob->name!="objreal")throw std::runtime_error("motion: only <objreal> objects at the first level are supported (found <"+ob->name+">).");
+    if(ob->name!="objreal" && ob->name!="obj")throw std::runtime_error("motion: <"+ob->name+"> is not expected at the first level of <motion>.");
+    LoadObj(ob,-1,-1,dirdata);
+  }
+  for(auto &o:objs)if(o.pkind<0){ bool isroot=false; for(auto &r:roots)if(r.first==0 && &objs[r.second]==&o)isroot=true; if(!isroot)roots.push_back({0,int(&o-&objs[0])}); }   // moving blocks without motion
+  // JMotion processes its events from the latest to the earliest start (S/JMotion.cpp:446-460): order of activation = order of start
+  for(auto *list:{&objs,&groups})for(auto &o:*list)for(size_t i=1;i<o.events.size();i++)for(size_t j=i;j>0 && o.events[j].start<o.events[j-1].start;j--)std::swap(o.events[j],o.events[j-1]);
+  Reset();
+}
+
+// one <obj> / <objreal> element: its movements, its events and, recursively, the objects inside it (JMotion::ReadXml S/JMotion.cpp:557-700)
+void MotionSet::LoadObj(const XmlNode *ob,int pkind,int pidx,const std::string &dirdata){
+  int kind,idx;
+  if(ob->name=="objreal"){
     const int ref=int(ob->Int("ref"));
-    MotionObj *o=nullptr;
-    for(auto &q:objs)if(q.ref==ref)o=&q;
-    if(!o)throw std::runtime_error("The number of mobile objects do not match the predefined motions in XML file.");
+    idx=-1; for(size_t q=0;q<objs.size();q++)if(objs[q].ref==ref)idx=int(q);
+    if(idx<0)throw std::runtime_error("The number of mobile objects do not match the predefined motions in XML file.");
+    kind=0;
+  }
+  else{ groups.push_back(MotionObj()); kind=1; idx=int(groups.size())-1; }
+  { MotionObj &o=(kind==0? objs[idx]: groups[idx]); o.pkind=pkind; o.pidx=pidx; }
+  if(pkind<0)roots.push_back({kind,idx});
+  else (pkind==0? objs[pidx]: groups[pidx]).children.push_back({kind,idx});
+  {
     for(auto &mp:ob->children){
       const XmlNode *e=mp.get();
       const std::string &n=e->name;
       if(n.empty() || n[0]=='_')continue;
+      if(n=="obj" || n=="objreal"){ LoadObj(e,kind,idx,dirdata); continue; }
+      MotionObj *o=(kind==0? &objs[idx]: &groups[idx]);          // (groups may have grown: fetched again for every element)
       if(n=="begin"){ MotionEvent ev; ev.movid=int(e->Int("mov")); ev.start=double(float(e->Dbl("start"))); ev.finish=double(float(e->Dbl("finish",true,-1)));   /* JXml::GetAttributeFloat: single precision */ o->events.push_back(ev); continue; }
       MotionMov m; m.id=int(e->Int("id")); m.time=double(float(e->Dbl("duration"))); m.nextid=int(e->Int("next",true,0));   // duration: read in single precision by the reference (S/JMotion.cpp:573)
       const std::string units=e->Str("anglesunits",true,"degrees");
@@ -342,11 +393,10 @@ void MotionSet::LoadXml(const XmlNode *motion,const std::string &dirdata){
         }
       }
       else throw std::runtime_error("motion: <"+n+"> is not supported by the stand-alone driver (wait, mvrect, mvrectace, mvrot, mvrotace, mvcir, mvcirace, mvrectsinu, mvrotsinu, mvcirsinu, mvrectfile, mvrotfile are).");
+      for(int i=0;i<3;i++){ m.iaxisp1[i]=m.axisp1[i]; m.iaxisp2[i]=m.axisp2[i]; m.iref[i]=m.ref[i]; }
       o->movs.push_back(m);
     }
   }
-  // JMotion processes its events from the latest to the earliest start (S/JMotion.cpp:446-460): order of activation = order of start
-  for(auto &o:objs)for(size_t i=1;i<o.events.size();i++)for(size_t j=i;j>0 && o.events[j].start<o.events[j-1].start;j--)std::swap(o.events[j],o.events[j-1]);
 }
 
 void MotionSet::SaveXml(FILE *f,const char *ind)const{

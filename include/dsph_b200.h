@@ -348,8 +348,8 @@ typedef struct dsph_motiondata {
 int dsph_motion_run(dsph_ctx *ctx,const dsph_motiondata *objs,uint32_t nobj,double stepdt);
 /* host only: the motion laws of <case><execution><motion> (objects = the <moving> blocks of <particles>) evaluated like JDsMotion in
  * simple mode, for hosts without the reference's JMotion library (bin/dsph_b200): wait, mvrect, mvrectace, mvrot, mvrotace, mvcir, mvcirace,
- * mvrectsinu, mvrotsinu, mvcirsinu, mvrectfile (= mvfile, mvpredef) and mvrotfile (data files next to the case) with next-chains and begin
- * events; nested objects are refused.  *nobj = moving objects; out[] needs nobj entries. */
+ * mvrectsinu, mvrotsinu, mvcirsinu, mvrectfile (= mvfile, mvpredef) and mvrotfile (data files next to the case) with next-chains, begin
+ * events and nested <obj> / <objreal> objects (a child moves with its parent); other elements are refused.  *nobj = moving objects; out[] needs nobj entries. */
 typedef struct dsph_motionset dsph_motionset;
 int dsph_case_motion_open(const char *dir,const char *casename,dsph_motionset **ms,uint32_t *nobj);
 int dsph_case_motion_process(dsph_motionset *ms,double timestep,double dt,dsph_motiondata *out,int *active);

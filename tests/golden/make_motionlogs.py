@@ -44,6 +44,14 @@ CASES = {
     "rectfile_then_rotfile": """<objreal ref="0"><begin mov="1" start="0.001" />
         <mvrectfile id="1" duration="0.006" next="2"><file name="piston.dat" fields="4" fieldtime="0" fieldx="1" fieldz="3" /></mvrectfile>
         <mvrotfile id="2" duration="100" anglesunits="radians"><file name="flap.dat" />%s</mvrotfile></objreal>""" % AX,
+    # nested objects: a group that translates (and later also rotates) carries a real object that rotates about its own axis; the
+    # child's axis travels with the parent
+    "nested_parent_rect_child_rot": """<obj><begin mov="1" start="0" /><begin mov="5" start="0.008" />
+        <mvrect id="1" duration="100"><vel x="0.5" y="0" z="0.2" /></mvrect>
+        <mvrot id="5" duration="100"><axisp1 x="0.2" y="0" z="0.5" /><axisp2 x="0.2" y="1" z="0.5" /><vel ang="150" /></mvrot>
+        <objreal ref="0"><begin mov="1" start="0.002" />
+          <mvrot id="1" duration="0.009" next="2">%s<vel ang="300" /></mvrot>
+          <mvcir id="2" duration="100">%s<ref x="0.44" y="0.3" z="0.2" /><vel ang="250" /></mvcir></objreal></obj>""" % (AX, AX),
 }
 
 DATAFILES = {

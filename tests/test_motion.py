@@ -52,7 +52,7 @@ def test_motion_xml_refuses_unsupported():
     xml = """<case><execution><particles np="4" nb="2" nbf="1" mkboundfirst="11" mkfluidfirst="1">
       <fixed mkbound="0" mk="11" begin="0" count="1" /><moving mkbound="1" mk="12" begin="1" count="1" refmotion="0" />
       <fluid mkfluid="0" mk="1" begin="2" count="2" /></particles>
-      <motion><obj><objreal ref="0"><begin mov="1" start="0" /><mvrect id="1" duration="1"><vel x="1" y="0" z="0" /></mvrect></objreal></obj></motion>
+      <motion><objreal ref="0"><begin mov="1" start="0" /><mvspline id="1" duration="1"><vel x="1" y="0" z="0" /></mvspline></objreal></motion>
       </execution></case>"""
     with tempfile.TemporaryDirectory() as tmp:
         open(os.path.join(tmp, "Case.xml"), "w").write(xml)
@@ -61,7 +61,7 @@ def test_motion_xml_refuses_unsupported():
 
 
 MOTIONLOGS = ["chain_rectace_rotace_rot", "concurrent_rect_rot", "rotsinu_radians_chain", "rect_wait_rectace_prev",
-              "chain_cir_cirace_cirsinu", "rectfile_then_rotfile"]
+              "chain_cir_cirace_cirsinu", "rectfile_then_rotfile", "nested_parent_rect_child_rot"]
 
 
 @pytest.mark.parametrize("name", MOTIONLOGS)
