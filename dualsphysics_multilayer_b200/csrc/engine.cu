@@ -848,6 +848,7 @@ void Engine::UpdateCellBound(){
 void Engine::MgConfig(int rank,int nranks,unsigned xlo,unsigned xhi){
   if(cfg.perix && nranks>1 && (k.perixinc[1]!=0 || k.perixinc[2]!=0))throw EngineError(DSPH_ERR_ARG,"x-slabs with a sheared periodic face along x are not supported.");
   if(nranks<1 || rank<0 || rank>=nranks || xlo>=xhi || xhi>k.domcells[0])throw EngineError(DSPH_ERR_ARG,"Invalid slab configuration.");
+  if(nranks>1 && mdbc)throw EngineError(DSPH_ERR_ARG,"mDBC cannot be combined with x-slabs (the halo records carry no normal vectors).");
   if(nranks>1 && xhi-xlo<2u*MgHalo()+1u)throw EngineError(DSPH_ERR_ARG,"The slab is narrower than 2 halo widths + 1 cell.");
   mgpu=(nranks>1); mgrank=rank; mgnranks=nranks; mgxlo=xlo; mgxhi=xhi;
   mgring=(mgpu && cfg.perix!=0);     // periodic along x: rank 0 and rank nranks-1 are neighbours through the periodic face
