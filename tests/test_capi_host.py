@@ -82,3 +82,38 @@ def test_reference_solver_accepts_our_case(tmp_path):
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert "Finished execution (code=0)" in r.stdout, r.stdout[-2000:]
     assert "Particles of simulation (initial): %d" % cd.np_ in r.stdout
+
+
+def test_plain_c_host_program_uses_the_host_side_of_the_abi(tmp_path):
+    """A C99 program (no C++, no Python) linked against libdsph_b200.so: the slab cuts of dsph_mgpu_balanced_cuts and the motion laws of a
+    case through dsph_case_motion_open / process / close -- the calls a C host makes around the device entry points.  No GPU needed."""
+    mkcase = os.path.join(ROOT, "dualsphysics_multilayer_b200", "bin", "mkcase")
+    subprocess.check_call([mkcase, "movpiston", "3000", str(tmp_path), "Case"], stdout=subprocess.DEVNULL)
+    src = r'''
+    #include "dsph_b200.h"
+    #include <stdio.h>
+    #include <math.h>
+    int main(int argc,char **argv){
+      double work[40]; uint32_t cuts[5]; int i;
+      for(i=0;i<40;i++)work[i]=(i<10? 100.0: 5.0);
+      if(dsph_mgpu_balanced_cuts(work,40,4,3,cuts)!=DSPH_OK){ printf("cuts failed: %s\n",dsph_last_error()); return 1; }
+      if(cuts[0]!=0 || cuts[4]!=40)return 2;
+      if(dsph_mgpu_balanced_cuts(work,5,4,3,cuts)==DSPH_OK)return 3;            /* too many ranks for 5 columns */
+      dsph_motionset *ms=0; uint32_t nobj=0;
+      if(dsph_case_motion_open(argv[1],"Case",&ms,&nobj)!=DSPH_OK){ printf("motion failed: %s\n",dsph_last_error()); return 4; }
+      if(nobj!=1)return 5;
+      dsph_motiondata d; int active=0; double t=0,dt=1e-3,x=0;
+      for(i=0;i<50;i++){ if(dsph_case_motion_process(ms,t,dt,&d,&active)!=DSPH_OK)return 6; if(!active || d.type!=DSPH_MOTION_LINEAR)return 7; x+=d.linmov[0]; t+=dt; }
+      /* mvrectsinu of mkcase: x(t) = 0.1 sin(2 pi 2 t) */
+      if(fabs(x-0.1*sin(2*3.14159265358979323846*2*t))>1e-12){ printf("x=%.15g\n",x); return 8; }
+      dsph_case_motion_close(ms);
+      printf("c host ok %u %u %u\n",cuts[1],cuts[2],cuts[3]);
+      return 0;
+    }
+    '''
+    open(str(tmp_path / "h.c"), "w").write(src)
+    libdir = os.path.dirname(dsph.LIBPATH)
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(tmp_path / "h"), str(tmp_path / "h.c"),
+                           "-L", libdir, "-ldsph_b200", "-lm", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(tmp_path / "h"), str(tmp_path)], stdout=subprocess.PIPE, text=True)
+    assert out.returncode == 0 and "c host ok" in out.stdout, (out.returncode, out.stdout)
