@@ -192,8 +192,6 @@ class SphLib:
             f("mgpu_balanced_cuts", C.c_int, C.POINTER(C.c_double), C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_uint32))
             f("celldiv_last_info", C.c_int, vp, C.POINTER(DivInfo))
         if prefix == "dsph_":
-            f("particles_set_boundnormals", C.c_int, vp, C.POINTER(C.c_float), C.c_uint32)
-            f("particles_get_boundnormals", C.c_int, vp, C.POINTER(C.c_float), C.c_uint32)
             f("set_mdbc_threshold", C.c_int, vp, C.c_float)
             f("case_normals", C.c_int, C.c_char_p, C.c_char_p, C.POINTER(C.c_double), C.c_uint32, C.POINTER(C.c_uint32))
             f("gauges_config", C.c_int, vp, C.c_uint32, C.POINTER(Gauge))
@@ -202,6 +200,8 @@ class SphLib:
             f("gauges_set_time", C.c_int, vp, C.c_double)
             f("case_gauges", C.c_int, C.c_char_p, C.c_char_p, C.POINTER(Gauge), C.c_uint32, C.POINTER(C.c_uint32))
         f("motion_run", C.c_int, vp, C.POINTER(MotionData), C.c_uint32, C.c_double)
+        f("particles_set_boundnormals", C.c_int, vp, C.POINTER(C.c_float), C.c_uint32)
+        f("particles_get_boundnormals", C.c_int, vp, C.POINTER(C.c_float), C.c_uint32)
         if prefix == "dsph_":
             f("case_motion_open", C.c_int, C.c_char_p, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_uint32))
             f("case_motion_process", C.c_int, vp, C.c_double, C.c_double, C.POINTER(MotionData), C.POINTER(C.c_int))

@@ -91,6 +91,8 @@ struct Oracle {
   double VelMax=0,AceMax=0; float ViscDtMax=0;
   double SymplecticDtPre=0; int VerletStep=0;
   bool BoundChanged=true;
+  // ---- mDBC (S/JSph.h:192-199): boundary mode, vectors particle -> ghost node of the boundary particles, sorted with them
+  bool Mdbc=false,MdbcCorrector=false; float MdbcThreshold=0; std::vector<f3> BoundNormal;
   // ---- cell division (JCellDivCpu members S/JCellDivCpu.h:44-150)
   std::vector<unsigned> CellPart,SortPart,PartsInCell,BeginCell;
   unsigned Ncx=0,Ncy=0,Ncz=0,Nsheet=0,Nct=0,Nctt=0;
@@ -121,6 +123,7 @@ struct Oracle {
   void Configure(const dsph_config &c){
     cfg=c;
     TKernel=c.tkernel; TStep=c.tstep; TVisco=c.tvisco; TDensity=c.tdensity; ShiftMode=c.shiftmode; VerletSteps=c.verletsteps;
+    Mdbc=((c.tboundary&0xff)==DSPH_BOUNDARY_MDBC); MdbcCorrector=(Mdbc && (c.tboundary&DSPH_BOUNDARY_MDBCCORRECTOR)!=0);
     ShiftCoef=c.shiftcoef; ShiftTFS=c.shifttfs;
     Simulate2D=c.simulate2d!=0;
     KernelH=c.kernelh; CteB=c.cteb; Gamma=c.gamma; RhopZero=c.rhopzero; MassFluid=c.massfluid; MassBound=c.massbound;
@@ -409,6 +412,7 @@ struct Oracle {
     if(TStep==DSPH_STEP_VERLET)SortArray(VelrhopM1);
     else if(TStep==DSPH_STEP_SYMPLECTIC && HasPre){ SortArray(PosPre); SortArray(VelrhopPre); }
     if(TVisco==DSPH_VISCO_LAMINARSPS)SortArray(SpsTau);
+    if(Mdbc && BoundNormal.size()>=Np)SortArray(BoundNormal);                           // S/JSphCpuSingle.cpp:465
     Np=NpFinal; Npb=NpbFinal; NpbOk=Npb-NpbIgnore;
     if(NpbOut)throw std::runtime_error("Boundary particles out of the domain (AbortBoundOut).");
     BoundChanged=false;
@@ -540,7 +544,7 @@ struct Oracle {
               const float visc_densi=DDTkh*cbar*(rhop1over2-1.f)/(rr2+Eta2);
               const float dot3=(drx*frx+dry*fry+drz*frz);
               const float delta=visc_densi*dot3*massp2;
-              deltap1=(boundp2? FLT_MAX: deltap1+delta);               // TBoundary==BC_DBC
+              deltap1=(boundp2 && !Mdbc? FLT_MAX: deltap1+delta);      // boundp2 && TBoundary==BC_DBC (S/JSphCpu.cpp:730)
             }
             if((TDensity==DSPH_DDT_DDT2 || (TDensity==DSPH_DDT_DDT2FULL && !boundp2)) && deltap1!=FLT_MAX){   // Fourtakas
               const float rh=1.f+DDTgz*drz;
@@ -973,7 +977,101 @@ struct Oracle {
   }
 
   // ---- JSphCpuSingle::Interaction_Forces S/JSphCpuSingle.cpp:524-567 + Interaction_ForcesCpuT S/JSphCpu.cpp:960-987
-  void InteractionForces(){
+  // ---- fsph::GetKernel_WabFac S/FunSphKernel.h:97-118 (cubic), :226-234 (Wendland) in the associations of the reference's -O3 -ffast-math
+  //      binary (read from the disassembly of oracle/_ref/obj52/JSphCpu.o): fac=((bwen*q)*(w^2*w))/r, wab=(awen*(1+2q))*(w^2*w^2); cubic far
+  //      branch wab=(a24*w)*w^2.  The corrected density is compared at the last bit of a float near 1000, and the 4x4 system amplifies a
+  //      last-bit difference of a kernel value into ~10 ulp of it.
+  inline float WabFac(float rr2,float &fac)const{
+    const float rad=sqrtf(rr2), qq=rad/KernelH;
+    if(TKernel==DSPH_KERNEL_WENDLAND){
+      const float wqq1=1.f-0.5f*qq, wqq2=wqq1*wqq1;
+      fac=((Bwen*qq)*(wqq1*wqq2))/rad;
+      const float wqq=(qq+qq)+1.f;
+      return (Awen*wqq)*(wqq2*wqq2);
+    }
+    if(rad>KernelH){ const float wqq1=2.0f-qq, wqq2=wqq1*wqq1; fac=(CubC2*wqq2)/rad; return (CubA24*wqq1)*wqq2; }
+    const float wqq2=qq*qq;
+    fac=(CubC1*qq+CubD1*wqq2)/rad;
+    return CubA2*(1.0f+(0.75f*qq-1.5f)*wqq2);
+  }
+  // ---- JSphCpu::InteractionMdbcCorrectionT2 S/JSphCpu.cpp:1020-1190, slip mode velocity=0 (the only one the reference accepts,
+  //      S/JSph.cpp:788): the fluid density extrapolated to the ghost node of every boundary particle with a first-order consistent
+  //      correction (moment matrix 4x4, 3x3 in 2-D, inverted by cofactors like fmath::InverseMatrix4x4 / 3x3), mirrored back.
+  void MdbcCorrection(){
+    const float determlimit=1e-3f;                                                       // S/JSphCpu.cpp:1197
+    const int n=(Simulate2D? 3: 4);
+    for(unsigned p1=0;p1<NpbOk;p1++){
+      const f3 bn=BoundNormal[p1];
+      if(bn.x==0 && bn.y==0 && bn.z==0)continue;
+      float rhopfinal=FLT_MAX, sumwab=0;
+      const d3 g={Pos[p1].x+double(bn.x),Pos[p1].y+double(bn.y),Pos[p1].z+double(bn.z)};
+      float rhopp1=0; f3 grad={0,0,0};
+      double a[4][4]; for(int i=0;i<4;i++)for(int j=0;j<4;j++)a[i][j]=0;
+      // nsearch::Init for a position (S/JCellSearch_inline.h:54-70)
+      const int cx=int((g.x-DomPosMin.x)/Scell)-int(CellDomainMin[0]);
+      const int cy=int((g.y-DomPosMin.y)/Scell)-int(CellDomainMin[1]);
+      const int cz=int((g.z-DomPosMin.z)/Scell)-int(CellDomainMin[2]);
+      const int ncx=int(Ncx),ncy=int(Ncy),ncz=int(Ncz),sd=ScellDiv;
+      const int cxini=std::max(cx-sd,0), cxfin=std::min(cx+sd,ncx-1)+1, yini=std::max(cy-sd,0), yfin=std::min(cy+sd,ncy-1)+1, zini=std::max(cz-sd,0), zfin=std::min(cz+sd,ncz-1)+1;
+      const int cellfluid=int(Nsheet*Ncz+1);
+      if(cxini<cxfin)for(int z=zini;z<zfin;z++)for(int y=yini;y<yfin;y++){
+        const int v=int(Nsheet)*z+ncx*y+cellfluid;
+        const unsigned pini=BeginCell[v+cxini], pfin=BeginCell[v+cxfin];
+        for(unsigned p2=pini;p2<pfin;p2++){
+          const float drx=float(g.x-Pos[p2].x), dry=float(g.y-Pos[p2].y), drz=float(g.z-Pos[p2].z);
+          const float rr2=(drx*drx+dry*dry+drz*drz);
+          if(rr2<=KernelSize2 && CodeIsFluid(Code[p2])){
+            float fac; const float wab=WabFac(rr2,fac);
+            const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
+            const float massp2=MassFluid, volp2=massp2/Velrhop[p2].w;
+            rhopp1+=massp2*wab; grad.x+=massp2*frx; grad.y+=massp2*fry; grad.z+=massp2*frz;
+            const float vwab=wab*volp2; sumwab+=vwab;
+            const float vfrx=frx*volp2, vfry=fry*volp2, vfrz=frz*volp2;
+            if(Simulate2D){
+              a[0][0]+=vwab; a[0][1]+=drx*vwab; a[0][2]+=drz*vwab;
+              a[1][0]+=vfrx; a[1][1]+=drx*vfrx; a[1][2]+=drz*vfrx;
+              a[2][0]+=vfrz; a[2][1]+=drx*vfrz; a[2][2]+=drz*vfrz;
+            }
+            else{
+              a[0][0]+=vwab; a[0][1]+=drx*vwab; a[0][2]+=dry*vwab; a[0][3]+=drz*vwab;
+              a[1][0]+=vfrx; a[1][1]+=drx*vfrx; a[1][2]+=dry*vfrx; a[1][3]+=drz*vfrx;
+              a[2][0]+=vfry; a[2][1]+=drx*vfry; a[2][2]+=dry*vfry; a[2][3]+=drz*vfry;
+              a[3][0]+=vfrz; a[3][1]+=drx*vfrz; a[3][2]+=dry*vfrz; a[3][3]+=drz*vfrz;
+            }
+          }
+        }
+      }
+      if(sumwab>=MdbcThreshold || (MdbcThreshold>=2 && sumwab+2>=MdbcThreshold)){
+        // minors and determinant of the n x n block; inverse(r,c) = (-1)^(r+c) * minor(c,r) / det
+        auto det3=[](const double m[3][3]){ return m[0][0]*(m[1][1]*m[2][2]-m[1][2]*m[2][1])-m[0][1]*(m[1][0]*m[2][2]-m[1][2]*m[2][0])+m[0][2]*(m[1][0]*m[2][1]-m[1][1]*m[2][0]); };
+        auto minor=[&](int ri,int ci){                       // determinant of the block without row ri and column ci
+          if(n==3){ int r[2],c[2],k=0; for(int i=0;i<3;i++)if(i!=ri)r[k++]=i; k=0; for(int j=0;j<3;j++)if(j!=ci)c[k++]=j; return a[r[0]][c[0]]*a[r[1]][c[1]]-a[r[0]][c[1]]*a[r[1]][c[0]]; }
+          double m[3][3]; int rr=0;
+          for(int i=0;i<4;i++)if(i!=ri){ int cc=0; for(int j=0;j<4;j++)if(j!=ci){ m[rr][cc]=a[i][j]; cc++; } rr++; }
+          return det3(m);
+        };
+        double determ=0;
+        for(int j=0;j<n;j++)determ+=((j&1)? -a[0][j]: a[0][j])*minor(0,j);
+        if(fabs(determ)>=double(determlimit)){
+          const double b[4]={double(rhopp1),double(grad.x),Simulate2D? double(grad.z): double(grad.y),double(grad.z)};
+          double x[4]={0,0,0,0};
+          for(int r=0;r<n;r++){ double sum=0; for(int c=0;c<n;c++)sum+=((((r+c)&1)? -minor(c,r): minor(c,r))/determ)*b[c]; x[r]=sum; }
+          const float rhoghost=float(x[0]);
+          if(Simulate2D){ const float grx=-float(x[1]), grz=-float(x[2]); rhopfinal=(rhoghost+grx*(-bn.x)+grz*(-bn.z)); }
+          else{ const float grx=-float(x[1]), gry=-float(x[2]), grz=-float(x[3]); rhopfinal=(rhoghost+grx*(-bn.x)+gry*(-bn.y)+grz*(-bn.z)); }
+        }
+        else if(a[0][0]>0)rhopfinal=float(double(rhopp1)/a[0][0]);
+        rhopfinal=(rhopfinal!=FLT_MAX? rhopfinal: RhopZero);
+        Velrhop[p1].w=rhopfinal;
+      }
+    }
+  }
+  void InteractionForces(int interstep=-1){
+    // boundary correction for mDBC before every force evaluation, the corrector one only with MDBCCorrector (S/JSphCpuSingle.cpp:525)
+    if(Mdbc && (MdbcCorrector || interstep!=DSPH_INTERSTEP_SYMCORRECTOR)){
+      if(BoundNormal.size()<Npb)throw std::runtime_error("mDBC needs the normal vectors of the boundary particles (orc_particles_set_boundnormals).");
+      MdbcCorrection();
+    }
     PreInteraction();
     float viscdt=0;
     if(MultiPhase){ float viscetadt=0; InteractionForcesNN(viscdt,viscetadt); ViscEtaDtMax=viscetadt; }   // M/JSphCpuSingle.cpp:594-636
@@ -1287,9 +1385,26 @@ int orc_particles_upload(orc_state *s,uint32_t np,uint32_t npb,const uint32_t *i
     }
     if(o.TStep==DSPH_STEP_VERLET)for(unsigned p=0;p<np;p++)o.VelrhopM1[p]=o.Velrhop[p];     // InitRunCpu S/JSphCpu.cpp:422
     if(o.TVisco==DSPH_VISCO_LAMINARSPS)for(unsigned p=0;p<np;p++)o.SpsTau[p]=sym3{0,0,0,0,0,0};
-    o.HasPre=false; o.BoundChanged=true; o.BoundLimitOk=o.BoundDivideOk=false;
+    o.HasPre=false; o.BoundChanged=true; o.BoundLimitOk=o.BoundDivideOk=false; o.BoundNormal.clear();
     o.SymplecticDtPre=o.DtIni; o.VerletStep=0;
     o.LoadDcellParticles();
+  });
+}
+// vectors particle -> ghost node (xyz) of the first `count` particles of the current order (boundary particles first); zero for the rest
+int orc_particles_set_boundnormals(orc_state *s,const float *n,uint32_t count){
+  return Guard([&]{
+    Oracle &o=s->o;
+    if(!o.Mdbc)throw std::runtime_error("Normal vectors are only used with cfg.tboundary = DSPH_BOUNDARY_MDBC.");
+    if(count>o.Np)throw std::runtime_error("More normal vectors than particles.");
+    o.BoundNormal.assign(o.Np,f3{0,0,0});
+    for(uint32_t i=0;i<count;i++)o.BoundNormal[i]=f3{n[3*size_t(i)],n[3*size_t(i)+1],n[3*size_t(i)+2]};
+  });
+}
+int orc_particles_get_boundnormals(orc_state *s,float *n,uint32_t count){
+  return Guard([&]{
+    Oracle &o=s->o;
+    if(count>o.BoundNormal.size())throw std::runtime_error("More normal vectors requested than stored.");
+    for(uint32_t i=0;i<count;i++){ n[3*size_t(i)]=o.BoundNormal[i].x; n[3*size_t(i)+1]=o.BoundNormal[i].y; n[3*size_t(i)+2]=o.BoundNormal[i].z; }
   });
 }
 int orc_particles_set_velrhopm1(orc_state *s,const float *v){
@@ -1336,8 +1451,7 @@ static void FillForceRes(const Oracle &o,dsph_forceres *res){
   res->dt=o.DtVariable(&res->dt1,&res->dt2,&res->dt3);
 }
 int orc_forces_run(orc_state *s,int interstep,dsph_forceres *res){
-  (void)interstep;
-  return Guard([&]{ s->o.InteractionForces(); FillForceRes(s->o,res); });
+  return Guard([&]{ s->o.InteractionForces(interstep); FillForceRes(s->o,res); });
 }
 int orc_forces_download(orc_state *s,uint32_t first,uint32_t count,float *ace,float *ar){
   return Guard([&]{
@@ -1355,12 +1469,12 @@ int orc_step(orc_state *s,double *stepdt,dsph_forceres *res){
     Oracle &o=s->o; double dt;
     if(o.TStep==DSPH_STEP_SYMPLECTIC){
       dt=o.SymplecticDtPre;
-      o.InteractionForces();
+      o.InteractionForces(DSPH_INTERSTEP_SYMPREDICTOR);
       const double ddt_p=o.DtVariable(nullptr,nullptr);
       if(o.ShiftMode)o.RunShifting(dt*.5);
       o.ComputeSymplecticPre(dt);
       o.RunCellDivide(true);
-      o.InteractionForces();
+      o.InteractionForces(DSPH_INTERSTEP_SYMCORRECTOR);
       const double ddt_c=o.DtVariable(nullptr,nullptr);
       FillForceRes(o,res);
       if(o.ShiftMode)o.RunShifting(dt);
@@ -1368,7 +1482,7 @@ int orc_step(orc_state *s,double *stepdt,dsph_forceres *res){
       o.SymplecticDtPre=std::min(ddt_p,ddt_c);
     }
     else{
-      o.InteractionForces();
+      o.InteractionForces(DSPH_INTERSTEP_VERLET);
       dt=o.DtVariable(nullptr,nullptr);
       FillForceRes(o,res);
       if(o.ShiftMode)o.RunShifting(dt);
@@ -1380,7 +1494,7 @@ int orc_step(orc_state *s,double *stepdt,dsph_forceres *res){
 }
 double orc_symplectic_dtpre(const orc_state *s){ return s->o.SymplecticDtPre; }
 // JSphCpu::RunMotion S/JSphCpu.cpp:1762-1805 for the motion data of one step: CalcRidp (:1660-1687), MoveLinBound (:1692-1703),
-// MoveMatBound (:1709-1730; mDBC normals are not carried by the checker)
+// MoveMatBound (:1709-1730, with the mDBC normals)
 int orc_motion_run(orc_state *s,const dsph_motiondata *objs,uint32_t nobj,double stepdt){
   return Guard([&]{
     Oracle &o=s->o;
@@ -1417,6 +1531,12 @@ int orc_motion_run(orc_state *s,const dsph_motiondata *objs,uint32_t nobj,double
           const double dx=ps2.x-ps.x, dy=ps2.y-ps.y, dz=ps2.z-ps.z;
           o.UpdatePos(ps,dx,dy,dz,false,pid);
           o.Velrhop[pid].x=float(dx/stepdt); o.Velrhop[pid].y=float(dy/stepdt); o.Velrhop[pid].z=float(dz/stepdt);
+          if(o.Mdbc && pid<o.BoundNormal.size()){                          // the image of the ghost node minus the image of the particle
+            const f3 bn=o.BoundNormal[pid];
+            const d3 gs={ps.x+double(bn.x),ps.y+double(bn.y),ps.z+double(bn.z)};
+            d3 gs2; gs2.x=(a[0]*gs.x+a[1]*gs.y)+(a[2]*gs.z+a[3]); gs2.y=(a[4]*gs.x+a[5]*gs.y)+(a[6]*gs.z+a[7]); gs2.z=(a[8]*gs.x+a[9]*gs.y)+(a[10]*gs.z+a[11]);
+            o.BoundNormal[pid]=f3{float(gs2.x-ps2.x),float(gs2.y-ps2.y),float(gs2.z-ps2.z)};
+          }
         }
       }
     }
@@ -1448,7 +1568,7 @@ int orc_mgpu_pack(orc_state *s,void *sl,void *sr){ return Guard([&]{ s->o.MgPack
 int orc_mgpu_unpack(orc_state *s,const uint32_t counts[8],const void *rl,const void *rr){ return Guard([&]{ unsigned c[8]; for(int i=0;i<8;i++)c[i]=counts[i]; s->o.MgUnpack(c,rl,rr); }); }
 int orc_forces_launch(orc_state *s,int interstep){
   (void)interstep;
-  return Guard([&]{ Oracle &o=s->o; o.InteractionForces();
+  return Guard([&]{ Oracle &o=s->o; o.InteractionForces(interstep);
     float f; f=o.ViscDtMax; memcpy(&o.MaxBits[0],&f,4); f=o.LastAce2; memcpy(&o.MaxBits[1],&f,4); f=o.LastVel2; memcpy(&o.MaxBits[2],&f,4); o.MaxBits[3]=0; });
 }
 void* orc_forces_maxima_ptr(orc_state *s){ return (void*)s->o.MaxBits; }

@@ -195,7 +195,7 @@ def run_step_stages(lib, g: Golden, step, tol, capacity=0):
         c3.celldiv(True)
         dm = g.stage(step, "dmot")
         check_divide(c3, dm)
-        if "boundnormal" in dm and lib.prefix == "dsph_":
+        if "boundnormal" in dm:
             npb = int(dm["npb"])
             results["motion_normals"] = float(np.abs(c3.boundnormals(npb) - dm["boundnormal"][:npb]).max())
             assert results["motion_normals"] <= 1e-7, results
