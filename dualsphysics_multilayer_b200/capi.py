@@ -194,12 +194,12 @@ class SphLib:
         if prefix == "dsph_":
             f("set_mdbc_threshold", C.c_int, vp, C.c_float)
             f("case_normals", C.c_int, C.c_char_p, C.c_char_p, C.POINTER(C.c_double), C.c_uint32, C.POINTER(C.c_uint32))
-            f("gauges_config", C.c_int, vp, C.c_uint32, C.POINTER(Gauge))
-            f("gauges_run", C.c_int, vp, C.c_double, C.c_int, C.POINTER(GaugeRes))
-            f("gauges_results", C.c_int, vp, C.POINTER(GaugeRes))
-            f("gauges_set_time", C.c_int, vp, C.c_double)
             f("case_gauges", C.c_int, C.c_char_p, C.c_char_p, C.POINTER(Gauge), C.c_uint32, C.POINTER(C.c_uint32))
         f("motion_run", C.c_int, vp, C.POINTER(MotionData), C.c_uint32, C.c_double)
+        f("gauges_config", C.c_int, vp, C.c_uint32, C.POINTER(Gauge))
+        f("gauges_run", C.c_int, vp, C.c_double, C.c_int, C.POINTER(GaugeRes))
+        f("gauges_results", C.c_int, vp, C.POINTER(GaugeRes))
+        f("gauges_set_time", C.c_int, vp, C.c_double)
         f("particles_set_boundnormals", C.c_int, vp, C.POINTER(C.c_float), C.c_uint32)
         f("particles_get_boundnormals", C.c_int, vp, C.POINTER(C.c_float), C.c_uint32)
         if prefix == "dsph_":

@@ -93,6 +93,8 @@ struct Oracle {
   bool BoundChanged=true;
   // ---- mDBC (S/JSph.h:192-199): boundary mode, vectors particle -> ghost node of the boundary particles, sorted with them
   bool Mdbc=false,MdbcCorrector=false; float MdbcThreshold=0; std::vector<f3> BoundNormal;
+  // ---- in-solver gauges (JGaugeSystem / JGaugeItem, S/JDsGaugeItem.cpp): definitions, next compute time, last results, run time
+  std::vector<dsph_gauge> Gauges; std::vector<double> GaugeNext; std::vector<dsph_gaugeres> GaugeRes; double GaugeTime=0;
   // ---- cell division (JCellDivCpu members S/JCellDivCpu.h:44-150)
   std::vector<unsigned> CellPart,SortPart,PartsInCell,BeginCell;
   unsigned Ncx=0,Ncy=0,Ncz=0,Nsheet=0,Nct=0,Nctt=0;
@@ -977,6 +979,140 @@ struct Oracle {
   }
 
   // ---- JSphCpuSingle::Interaction_Forces S/JSphCpuSingle.cpp:524-567 + Interaction_ForcesCpuT S/JSphCpu.cpp:960-987
+  // ---- gauges: JGaugeVelocity / JGaugeSwl / JGaugeMaxZ / JGaugeForce::CalculeCpu (S/JDsGaugeItem.cpp:325-367, 542-600, 780-822, 986-1041)
+  inline float WabWendland(float rr2)const{                            // S/FunSphKernel.h:206-213
+    const float rad=sqrtf(rr2), qq=rad/KernelH; const float wqq=qq+qq+1.f, wqq1=1.f-0.5f*qq, wqq2=wqq1*wqq1;
+    return Awen*wqq*wqq2*wqq2;
+  }
+  inline float Wab(float rr2)const{ return TKernel==DSPH_KERNEL_WENDLAND? WabWendland(rr2): WabCubic(rr2); }
+  // fluid particle range of one (y,z) row of cells around a position (nsearch::Init(pos) + ParticleRange, S/JCellSearch_inline.h:54-83)
+  struct PosRange{ int cxini,cxfin,yini,yfin,zini,zfin; };
+  PosRange PosCells(const d3 &ps)const{
+    const int cx=int((ps.x-DomPosMin.x)/Scell)-int(CellDomainMin[0]);
+    const int cy=int((ps.y-DomPosMin.y)/Scell)-int(CellDomainMin[1]);
+    const int cz=int((ps.z-DomPosMin.z)/Scell)-int(CellDomainMin[2]);
+    const int ncx=int(Ncx),ncy=int(Ncy),ncz=int(Ncz),sd=ScellDiv;
+    PosRange r; r.cxini=std::max(cx-sd,0); r.cxfin=std::min(cx+sd,ncx-1)+1; r.yini=std::max(cy-sd,0); r.yfin=std::min(cy+sd,ncy-1)+1; r.zini=std::max(cz-sd,0); r.zfin=std::min(cz+sd,ncz-1)+1;
+    return r;
+  }
+  template<class F> void ForFluidNeighbours(const d3 &ps,F f)const{
+    const PosRange r=PosCells(ps);
+    const int cellfluid=int(Nsheet*Ncz+1);
+    if(r.cxini<r.cxfin)for(int z=r.zini;z<r.zfin;z++)for(int y=r.yini;y<r.yfin;y++){
+      const int v=int(Nsheet)*z+int(Ncx)*y+cellfluid;
+      for(unsigned p2=BeginCell[v+r.cxini];p2<BeginCell[v+r.cxfin];p2++){
+        const float drx=float(ps.x-Pos[p2].x), dry=float(ps.y-Pos[p2].y), drz=float(ps.z-Pos[p2].z);
+        const float rr2=drx*drx+dry*dry+drz*drz;
+        if(rr2<=KernelSize2 && rr2>=1e-18f && CodeIsFluid(Code[p2]))f(p2,drx,dry,drz,rr2);
+      }
+    }
+  }
+  float GaugeMass(const d3 &ps)const{                                   // JGaugeSwl::CalculeMassCpu :542-567
+    double summass=0;
+    ForFluidNeighbours(ps,[&](unsigned p2,float,float,float,float rr2){ float wab=Wab(rr2); wab*=MassFluid/Velrhop[p2].w; summass+=wab*MassFluid; });
+    return float(summass);
+  }
+  // the pressure of the gauges: fsph::ComputePress with the rounding of the reference build (see PreInteraction: product form, double pow)
+  float GaugePress(float rhop)const{ const float x=rhop*(1.0f/RhopZero); return float(double(CteB)*(pow(double(x),double(Gamma))-1.0)); }
+  void GaugesConfig(unsigned n,const dsph_gauge *g){
+    Gauges.assign(g,g+n); GaugeNext.assign(n,0.0); GaugeRes.assign(n,dsph_gaugeres());
+    for(auto &q:Gauges){
+      if(q.type<DSPH_GAUGE_VEL || q.type>DSPH_GAUGE_FORCE)throw std::runtime_error("Gauge type is invalid.");
+      if(q.type==DSPH_GAUGE_SWL && !(q.masslimit>0))q.masslimit=MassFluid*(Simulate2D? 0.4f: 0.5f);   // JGaugeSwl defaults, S/JDsGaugeSystem.cpp:240
+    }
+  }
+  unsigned GaugesRun(double timestep,bool all){
+    unsigned ndue=0;
+    for(auto &r:GaugeRes)r.computed=0;
+    for(size_t i=0;i<Gauges.size();i++){
+      const dsph_gauge &q=Gauges[i];
+      if(!(all || (timestep>=GaugeNext[i] && q.computestart<=timestep && timestep<=q.computeend)))continue;   // JGaugeItem::Update S/JDsGaugeItem.h:164
+      ndue++;
+      float res[3]={0,0,0};
+      if(q.type==DSPH_GAUGE_VEL){
+        const d3 pt={q.point0[0],q.point0[1],q.point0[2]};
+        const bool ptout=(pt.x!=pt.x||pt.y!=pt.y||pt.z!=pt.z||pt.x<DomPosMin.x||pt.y<DomPosMin.y||pt.z<DomPosMin.z||pt.x>=DomPosMax.x||pt.y>=DomPosMax.y||pt.z>=DomPosMax.z);
+        double sv[3]={0,0,0};
+        if(!ptout)ForFluidNeighbours(pt,[&](unsigned p2,float,float,float,float rr2){
+          float wab=Wab(rr2); const f4 v2=Velrhop[p2]; wab*=MassFluid/v2.w;
+          sv[0]+=wab*v2.x; sv[1]+=wab*v2.y; sv[2]+=wab*v2.z;
+        });
+        res[0]=float(sv[0]); res[1]=float(sv[1]); res[2]=float(sv[2]);
+      }
+      else if(q.type==DSPH_GAUGE_SWL){
+        // JGaugeSwl::SetPoints :447-465
+        const double d[3]={q.point2[0]-q.point0[0],q.point2[1]-q.point0[1],q.point2[2]-q.point0[2]};
+        const double dis=sqrt(d[0]*d[0]+d[1]*d[1]+d[2]*d[2]);
+        unsigned pointnp=0; d3 dir={0,0,0};
+        if(dis>0 && q.pointdp>0){
+          pointnp=unsigned(dis/q.pointdp);
+          if(dis-(q.pointdp*pointnp)>=q.pointdp*0.1)pointnp++;
+          if(pointnp<1)pointnp++;
+          const double dp=dis/pointnp;
+          dir={d[0]/dis*dp,d[1]/dis*dp,d[2]/dis*dp};
+        }
+        // first change from fluid to empty along the line (:575-600)
+        const d3 p0={q.point0[0],q.point0[1],q.point0[2]};
+        d3 ptsurf={DBL_MAX,DBL_MAX,DBL_MAX}; float mpre=0; d3 ptpos=p0;
+        for(unsigned cp=0;cp<=pointnp;cp++){
+          const float mass=GaugeMass(ptpos);
+          if(mass>q.masslimit)mpre=mass;
+          if(mass<q.masslimit && mpre){
+            const float fxm1=(q.masslimit-mpre)/(mass-mpre)-1;
+            ptsurf={ptpos.x+dir.x*double(fxm1),ptpos.y+dir.y*double(fxm1),ptpos.z+dir.z*double(fxm1)};
+            cp=pointnp+1;
+          }
+          ptpos={ptpos.x+dir.x,ptpos.y+dir.y,ptpos.z+dir.z};
+        }
+        if(ptsurf.x==DBL_MAX){ const double kk=(mpre? double(pointnp): 0.0); ptsurf={p0.x+dir.x*kk,p0.y+dir.y*kk,p0.z+dir.z*kk}; }
+        res[0]=float(ptsurf.x); res[1]=float(ptsurf.y); res[2]=float(ptsurf.z);
+      }
+      else if(q.type==DSPH_GAUGE_MAXZ){
+        // GetInteractionCellsMaxZ :760-775 + CalculeCpu :780-822
+        const float maxdist2=q.distlimit*q.distlimit;
+        const int cx=int((q.point0[0]-DomPosMin.x)/Scell)-int(CellDomainMin[0]);
+        const int cy=int((q.point0[1]-DomPosMin.y)/Scell)-int(CellDomainMin[1]);
+        const int cz=int((q.point0[2]-DomPosMin.z)/Scell)-int(CellDomainMin[2]);
+        const int cz2=int((q.point0[2]+q.height-DomPosMin.z)/Scell)-int(CellDomainMin[2]);
+        const int ncel=int(ceil(q.distlimit/Scell));
+        const int cxini=std::max(cx-ncel,0), cxfin=std::min(cx+ncel+1,int(Ncx)), yini=std::max(cy-ncel,0), yfin=std::min(cy+ncel+1,int(Ncy)), zini=std::max(cz-ncel,0), zfin=std::min(cz2+ncel+1,int(Ncz));
+        const int cellfluid=int(Nsheet*Ncz+1);
+        unsigned pmax=UINT_MAX; float zmax=-FLT_MAX;
+        if(cxini<cxfin)for(int z=zfin-1;z>=zini && pmax==UINT_MAX;z--)for(int y=yini;y<yfin;y++){
+          const int ymod=int(Nsheet)*z+cellfluid+int(Ncx)*y;
+          for(unsigned p2=BeginCell[cxini+ymod];p2<BeginCell[cxfin+ymod];p2++)if(Pos[p2].z>zmax){
+            const float drx=float(q.point0[0]-Pos[p2].x), dry=float(q.point0[1]-Pos[p2].y);
+            if(drx*drx+dry*dry<=maxdist2 && CodeIsFluid(Code[p2])){ zmax=float(Pos[p2].z); pmax=p2; }
+          }
+        }
+        res[2]=std::max(zmax,float(DomPosMin.z));
+      }
+      else{
+        // force on the boundary particles of one mk block from the pressure term of the momentum equation, fluid neighbours only (:986-1041)
+        std::vector<f3> partace(q.count,f3{0,0,0});
+        for(unsigned p1=0;p1<NpbOk;p1++)if((Code[p1]&(DSPH_CODE_MASKTYPE|DSPH_CODE_MASKVALUE))==q.code && CodeIsNormal(Code[p1])){
+          const f4 v1=Velrhop[p1]; const float press1=GaugePress(v1.w);
+          f3 ace={0,0,0};
+          ForFluidNeighbours(Pos[p1],[&](unsigned p2,float drx,float dry,float drz,float rr2){
+            const float fac=Fac(rr2);
+            const float frx=fac*drx, fry=fac*dry, frz=fac*drz;
+            const f4 v2=Velrhop[p2]; const float press2=GaugePress(v2.w);
+            const float prs=(press1+press2)/(v1.w*v2.w)+(TKernel==DSPH_KERNEL_CUBIC? TensilCubic(rr2,v1.w,press1,v2.w,press2): 0.f);
+            const float pv=-prs*MassFluid;
+            ace.x+=pv*frx; ace.y+=pv*fry; ace.z+=pv*frz;
+          });
+          const unsigned kk=Idp[p1]-q.idbegin; if(kk<q.count)partace[kk]=ace;
+        }
+        f3 sum={0,0,0}; for(auto &a:partace){ sum.x+=a.x; sum.y+=a.y; sum.z+=a.z; }
+        res[0]=sum.x*MassBound; res[1]=sum.y*MassBound; res[2]=sum.z*MassBound;
+      }
+      dsph_gaugeres &r=GaugeRes[i]; r.timestep=timestep; r.value[0]=res[0]; r.value[1]=res[1]; r.value[2]=res[2]; r.computed=1;
+      const double cdt=q.computedt;                                          // JGaugeItem::SetTimeStep :204-211
+      if(cdt){ const unsigned nt=unsigned(timestep/cdt); GaugeNext[i]=cdt*nt; if(GaugeNext[i]<=timestep)GaugeNext[i]=cdt*(nt+1); }
+    }
+    return ndue;
+  }
+
   // ---- fsph::GetKernel_WabFac S/FunSphKernel.h:97-118 (cubic), :226-234 (Wendland) in the associations of the reference's -O3 -ffast-math
   //      binary (read from the disassembly of oracle/_ref/obj52/JSphCpu.o): fac=((bwen*q)*(w^2*w))/r, wab=(awen*(1+2q))*(w^2*w^2); cubic far
   //      branch wab=(a24*w)*w^2.  The corrected density is compared at the last bit of a float near 1000, and the 4x4 system amplifies a
@@ -1407,6 +1543,12 @@ int orc_particles_get_boundnormals(orc_state *s,float *n,uint32_t count){
     for(uint32_t i=0;i<count;i++){ n[3*size_t(i)]=o.BoundNormal[i].x; n[3*size_t(i)+1]=o.BoundNormal[i].y; n[3*size_t(i)+2]=o.BoundNormal[i].z; }
   });
 }
+int orc_gauges_config(orc_state *s,uint32_t n,const dsph_gauge *g){ return Guard([&]{ s->o.GaugesConfig(n,g); }); }
+int orc_gauges_run(orc_state *s,double timestep,int force_all,dsph_gaugeres *res){
+  return Guard([&]{ s->o.GaugesRun(timestep,force_all!=0); if(res)for(size_t i=0;i<s->o.GaugeRes.size();i++)res[i]=s->o.GaugeRes[i]; });
+}
+int orc_gauges_results(orc_state *s,dsph_gaugeres *res){ return Guard([&]{ for(size_t i=0;i<s->o.GaugeRes.size();i++)res[i]=s->o.GaugeRes[i]; }); }
+int orc_gauges_set_time(orc_state *s,double timestep){ s->o.GaugeTime=timestep; return DSPH_OK; }
 int orc_particles_set_velrhopm1(orc_state *s,const float *v){
   return Guard([&]{ Oracle &o=s->o; if(o.TStep!=DSPH_STEP_VERLET)throw std::runtime_error("VelrhopM1 is only used by Verlet."); for(unsigned p=0;p<o.Np;p++)o.VelrhopM1[p]={v[4*p],v[4*p+1],v[4*p+2],v[4*p+3]}; });
 }
@@ -1488,6 +1630,8 @@ int orc_step(orc_state *s,double *stepdt,dsph_forceres *res){
       if(o.ShiftMode)o.RunShifting(dt);
       o.ComputeVerlet(dt);
     }
+    if(!o.Gauges.empty())o.GaugesRun(o.GaugeTime+dt,false);        // RunGaugeSystem(TimeStep+stepdt), S/JSphCpuSingle.cpp:1095
+    o.GaugeTime+=dt;
     o.RunCellDivide(true);
     if(stepdt)*stepdt=dt;
   });

@@ -61,13 +61,11 @@ def _check(res, ref, cfg, what):
     return rep
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", GAUGE_CASES)
-def test_gpu_gauges_match_reference(gpu_lib, name, tmp_path):
+def _run_gauges(lib, name, tmp_path):
     g = Golden(name)
     _write_case(g, tmp_path)
     gauges = dsph.case_gauges(str(tmp_path), "Case")
-    ctx = parity.make_ctx(gpu_lib, g.cfg, 20000)
+    ctx = parity.make_ctx(lib, g.cfg, 20000)
     z = g.z
     ctx.upload(z["case/idp"], z["case/pos"], z["case/velrhop"], int(z["case/npb"]), z["case/code"])
     ctx.celldiv(True)
@@ -81,6 +79,18 @@ def test_gpu_gauges_match_reference(gpu_lib, name, tmp_path):
         if step in g.steps:
             print(name, step, _check(ctx.gauges_results(), g.stage(step, "gauges"), g.cfg, "step %d" % step))
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GAUGE_CASES)
+def test_gpu_gauges_match_reference(gpu_lib, name, tmp_path):
+    _run_gauges(gpu_lib, name, tmp_path)
+
+
+@pytest.mark.parametrize("name", GAUGE_CASES)
+def test_oracle_gauges_match_reference(oracle_lib, name, tmp_path):
+    """The CPU restatement of the four gauges (oracle/sph_oracle.cpp: Oracle::GaugesRun) against the same reference results, no GPU."""
+    _run_gauges(oracle_lib, name, tmp_path)
 
 
 @pytest.mark.gpu
